@@ -1,0 +1,148 @@
+/*
+ * nanorepeat_b200.h -- C ABI of libnanorepeat_b200.so, the B200 (sm_100a) drop-in for NanoRepeat's
+ * repeat-size estimation hot path (rounds 2 and 3).
+ *
+ * What it replaces in the reference (paths relative to the reference tree, src/NanoRepeat/):
+ *   - the alignment engine call `pymm2.main(cmd)` at nanoRepeat_bam.py:362 (round 2: every read core
+ *     against ONE template  left_anchor + motif*T)            -> nr_round2_region()
+ *   - the per-read engine call at nanoRepeat_bam.py:497 (round 3: one core against the ladder
+ *     left_anchor + motif*k + right_anchor, k = kmin..kmax) together with the PAF parse / top-score /
+ *     span-predicate selection of nanoRepeat_bam.py:408-434     -> nr_round3_region()
+ *   - the generic engine shape (any query against any target, PAF fields AS/tstart/tend of
+ *     paf.py:39-64)                                             -> nr_score_tasks()
+ *   - the data-type -> preset table tk.py:502-517               -> nr_get_preset()
+ *
+ * Plain pointers and sizes only; the caller owns every buffer; the library keeps device / pinned pools
+ * between calls and never calls exit()/abort().  Every function returns NR_OK (0) or a negative error code;
+ * nr_last_error() describes the last failure on the calling thread.  CUDA is initialised lazily on the first
+ * compute call (never at load time), so the library is safe to load before the reference's fork()
+ * (nanoRepeat_bam.py:719-724); each worker process then owns its own context.
+ *
+ * Alignment contract (bit-exact with oracle/nr_oracle.c): exact local alignment, match +a, mismatch -b,
+ * gap of length l costs min(q + l*e, q2 + l*e2);
+ *   score  = best local score (0: nothing aligns),
+ *   tend   = smallest target end (0-based exclusive) among alignments reaching score,
+ *   tstart = largest target start (0-based) among alignments reaching score and ending at tend.
+ */
+#ifndef NANOREPEAT_B200_H
+#define NANOREPEAT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NR_OK                0
+#define NR_ERR_CUDA         -1   /* CUDA runtime failure (no device, launch error, out of memory on device) */
+#define NR_ERR_ARG          -2   /* null pointer / negative size / inconsistent arguments */
+#define NR_ERR_BAD_BASE     -3   /* a sequence holds a character other than ACGTacgt (2-bit device encoding) */
+#define NR_ERR_TOO_LARGE    -4   /* a task exceeds the packed score/coordinate range (see nr_limits) */
+#define NR_ERR_NOMEM        -5   /* host allocation failure */
+#define NR_ERR_UNKNOWN_TYPE -6   /* nr_get_preset: data type not in the reference's table */
+
+typedef struct nr_scoring_t {
+    int32_t match;        /* minimap2 -A  (map-ont: 2)  */
+    int32_t mismatch;     /* minimap2 -B  (4), charged as -mismatch */
+    int32_t gap_open1;    /* minimap2 -O first value (4) */
+    int32_t gap_ext1;     /* minimap2 -E first value (2) */
+    int32_t gap_open2;    /* minimap2 -O second value (24) */
+    int32_t gap_ext2;     /* minimap2 -E second value (1) */
+    int32_t ambiguous;    /* minimap2 --score-N (1); kept for ABI parity with the oracle, unused on device */
+    int32_t min_dp_score; /* minimap2 -s (80): alignments scoring below it are "not printed" by the selection */
+} nr_scoring_t;
+
+/* One alignment record: the three PAF fields rounds 2-3 read (paf.py:47-52,57-58). */
+typedef struct nr_aln_t { int32_t score, tstart, tend; } nr_aln_t;
+
+/* Per-rung summary produced by the round-3 ladder kernel: everything nanoRepeat_bam.py:423-431 looks at. */
+typedef struct nr_rung_t {
+    int32_t score;        /* AS:i of core vs left + motif*k + right */
+    uint8_t starts_in_left;  /* tstart < |left|            (nanoRepeat_bam.py:427, strict) */
+    uint8_t ends_in_right;   /* tlen - tend < |right|      (nanoRepeat_bam.py:427, strict) */
+    uint8_t pad[2];
+} nr_rung_t;
+
+/* Work counters of the last completed call on this thread's context (for bench.py / roofline). */
+typedef struct nr_stats_t {
+    int64_t algorithmic_cells;  /* sum over tasks of |query| * |template| (full rectangles) */
+    int64_t executed_cells;     /* DP cells the kernels actually updated (padding and shared prefixes accounted) */
+    int64_t n_tasks;
+    int32_t kernel_launches;    /* launches of this library's kernels */
+    int32_t reserved;
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+} nr_stats_t;
+
+/* Data-type preset table (reference tk.py:502-517: ont, ont_sup, ont_q20, clr, hifi -- all map-ont). */
+int nr_get_preset(const char* data_type, nr_scoring_t* out);
+
+/* Lazy, idempotent. device < 0: use NR_DEVICE env var, else LOCAL_RANK, else device 0. */
+int nr_init(int device);
+int nr_shutdown(void);
+const char* nr_last_error(void);
+int nr_device_info(int32_t* device, int32_t* sm_count, int32_t* clock_khz);
+
+/* Largest task the packed kernels accept: match * min(qlen, tlen) <= max_score and tlen <= max_tlen. */
+int nr_limits(int32_t* max_score, int32_t* max_tlen);
+
+/* Generic engine: n independent (query, target) tasks -> out[i]. Replaces pymm2.main at the PAF level. */
+int nr_score_tasks(const nr_scoring_t* sc, int32_t n_tasks,
+                   const char* const* queries, const int32_t* qlen,
+                   const char* const* targets, const int32_t* tlen,
+                   nr_aln_t* out);
+
+/* Round 2 (nanoRepeat_bam.py:349-362): every core vs left + motif*T. out[r] for read r. */
+int nr_round2_region(const nr_scoring_t* sc,
+                     const char* left, int32_t n_left, const char* motif, int32_t motif_len, int32_t T,
+                     int32_t n_reads, const char* const* cores, const int32_t* core_len,
+                     nr_aln_t* out);
+
+/*
+ * Round 3 (nanoRepeat_bam.py:452-500 + :408-434): read r against left + motif*k + right, k = kmin[r]..kmax[r].
+ * Outputs per read: top_score[r] = best AS over reportable rungs (0 when none reaches min_dp_score: the
+ * reference then leaves round3_repeat_size untouched), n_k[r] / sum_k[r] = count and sum of the rungs k tied at
+ * top_score that start inside left and end inside right (n_k == 0: reference falls back to round 2).
+ * The host computes np.mean as sum_k / n_k in float64 exactly like :431.
+ * rungs (nullable) receives every rung's summary at rungs[rung_offset[r] + k - kmin[r]]; rung_offset has
+ * n_reads + 1 entries and may be NULL when rungs is NULL.
+ */
+int nr_round3_region(const nr_scoring_t* sc,
+                     const char* left, int32_t n_left, const char* right, int32_t n_right,
+                     const char* motif, int32_t motif_len,
+                     int32_t n_reads, const char* const* cores, const int32_t* core_len,
+                     const int32_t* kmin, const int32_t* kmax,
+                     const int64_t* rung_offset, nr_rung_t* rungs,
+                     int64_t* sum_k, int32_t* n_k, int32_t* top_score);
+
+/*
+ * Device-resident batches (bench.py `value`: inputs already in HBM when the timed region starts).
+ * create = pack + upload; run = kernel launches only, asynchronous on `stream` (a cudaStream_t, NULL = the
+ * library's own stream); fetch = synchronise + device->host copy + selection.
+ */
+typedef struct nr_batch nr_batch_t;
+nr_batch_t* nr_batch_create_tasks(const nr_scoring_t* sc, int32_t n_tasks,
+                                  const char* const* queries, const int32_t* qlen,
+                                  const char* const* targets, const int32_t* tlen);
+nr_batch_t* nr_batch_create_round2(const nr_scoring_t* sc,
+                                   const char* left, int32_t n_left, const char* motif, int32_t motif_len, int32_t T,
+                                   int32_t n_reads, const char* const* cores, const int32_t* core_len);
+nr_batch_t* nr_batch_create_round3(const nr_scoring_t* sc,
+                                   const char* left, int32_t n_left, const char* right, int32_t n_right,
+                                   const char* motif, int32_t motif_len,
+                                   int32_t n_reads, const char* const* cores, const int32_t* core_len,
+                                   const int32_t* kmin, const int32_t* kmax);
+int nr_batch_run(nr_batch_t* b, void* stream);
+int nr_batch_fetch_alns(nr_batch_t* b, nr_aln_t* out);                      /* tasks / round2 batches */
+int nr_batch_fetch_round3(nr_batch_t* b, const int64_t* rung_offset, nr_rung_t* rungs,
+                          int64_t* sum_k, int32_t* n_k, int32_t* top_score);  /* round3 batches */
+int nr_batch_stats(const nr_batch_t* b, nr_stats_t* out);
+void nr_batch_destroy(nr_batch_t* b);
+
+/* Counters of the last nr_score_tasks / nr_round2_region / nr_round3_region call on this thread. */
+int nr_last_stats(nr_stats_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NANOREPEAT_B200_H */

@@ -1,0 +1,640 @@
+// nr_api.cu -- C ABI host side of libnanorepeat_b200.so (declared in include/nanorepeat_b200.h).
+//
+// Host work done here, natively: 2-bit packing of reads and templates into one sequence pool, ladder template
+// generation (left + motif*k + right stored once per k and shared by all reads of the region, reference
+// nanoRepeat_bam.py:474-481), task construction, cost sorting and bucketing by stripe shape, launches of the
+// sm_100a kernels in nr_kernels.cuh, result gather and the round-3 selection of nanoRepeat_bam.py:423-431.
+// There is no CPU compute fallback: without a CUDA device every compute call fails with NR_ERR_CUDA.
+#include "../../include/nanorepeat_b200.h"
+#include "nr_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+thread_local int g_code = 0;
+thread_local nr_stats_t g_last_stats = {};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    g_code = code;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return fail(NR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),   \
+                        __FILE__, __LINE__);                                                    \
+    } while (0)
+
+struct Context {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 0;
+    int clock_khz = 0;
+    cudaStream_t stream = nullptr;
+};
+Context g_ctx;
+std::mutex g_ctx_mu;
+
+constexpr int kMaxScore = 32767;   // signed 16-bit score field of the packed DP word
+constexpr int kMaxTlen = 65535;    // unsigned 16-bit start-column field
+constexpr int kMinR = 4, kMaxR = 16;
+constexpr int kWarpsPerBlock = 4;
+
+int ensure_init(int device) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (g_ctx.ready) return NR_OK;
+    if (device < 0) {
+        const char* e = getenv("NR_DEVICE");
+        if (!e) e = getenv("LOCAL_RANK");
+        device = e ? atoi(e) : 0;
+    }
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess || n == 0)
+        return fail(NR_ERR_CUDA, "no CUDA device available (%s); libnanorepeat_b200 has no CPU fallback",
+                    err == cudaSuccess ? "device count 0" : cudaGetErrorString(err));
+    device %= n;
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(NR_ERR_CUDA, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 part", device, prop.name,
+                    prop.major, prop.minor);
+    CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    g_ctx.device = device;
+    g_ctx.sm_count = prop.multiProcessorCount;
+    g_ctx.clock_khz = prop.clockRate;
+    g_ctx.ready = true;
+    return NR_OK;
+}
+
+// ---- 2-bit packing -------------------------------------------------------------------------------------------
+struct CodeTable {
+    int8_t t[256];
+    CodeTable() {
+        memset(t, -1, sizeof t);
+        t[(int)'A'] = t[(int)'a'] = 0;
+        t[(int)'C'] = t[(int)'c'] = 1;
+        t[(int)'G'] = t[(int)'g'] = 2;
+        t[(int)'T'] = t[(int)'t'] = 3;
+    }
+};
+const CodeTable g_codes;
+
+// Sequence pool: 16 bases per 32-bit word, base i of a sequence at bits 2*(i%16) of word i/16.  Every sequence
+// starts on a word boundary and is followed by one zero slack word (kernels prefetch one word ahead).
+struct Pool {
+    std::vector<uint32_t> words;
+    // append; returns first word index, or -1 on a non-ACGT character
+    long long add(const char* s, int len) {
+        size_t w0 = words.size();
+        size_t nw = (size_t)(len + 15) / 16 + 1;
+        words.resize(w0 + nw, 0u);
+        uint32_t* w = words.data() + w0;
+        int bad = 0;
+        for (int i = 0; i < len; ++i) {
+            int c = g_codes.t[(unsigned char)s[i]];
+            bad |= c;
+            w[i >> 4] |= (uint32_t)(c & 3) << (2 * (i & 15));
+        }
+        if (bad < 0) { words.resize(w0); return -1; }
+        return (long long)w0;
+    }
+};
+
+struct Bucket {
+    int R;
+    bool multi;
+    int order_off;   // offset into the order array
+    int count;
+    int blocks;
+    long long scratch_stride;   // int4 per boundary row (multi only)
+    size_t scratch_off;         // int4 offset into d_scratch
+};
+
+void stripe_shape(int q_len, int& R, bool& multi, int& n_stripes) {
+    if (q_len <= 32 * kMaxR) {
+        multi = false;
+        n_stripes = 1;
+        R = std::max(kMinR, (q_len + 31) / 32);
+    } else {
+        multi = true;
+        n_stripes = (q_len + 32 * kMaxR - 1) / (32 * kMaxR);
+        R = (q_len + 32 * n_stripes - 1) / (32 * n_stripes);
+    }
+}
+
+}  // namespace
+
+enum BatchKind { KIND_TASKS = 0, KIND_ROUND2 = 1, KIND_ROUND3 = 2 };
+
+struct nr_batch {
+    BatchKind kind = KIND_TASKS;
+    nr_scoring_t sc = {};
+    std::vector<nr::Task> tasks;
+    std::vector<int32_t> order;
+    std::vector<Bucket> buckets;
+    Pool pool;
+    // round 3 bookkeeping
+    int n_reads = 0, n_left = 0, n_right = 0, motif_len = 0;
+    std::vector<int32_t> kmin, kmax;
+    std::vector<int64_t> rung_off;   // n_reads + 1
+    // device
+    nr::Task* d_tasks = nullptr;
+    int32_t* d_order = nullptr;
+    uint32_t* d_pool = nullptr;
+    int* d_counters = nullptr;
+    int4* d_out = nullptr;
+    int4* d_scratch = nullptr;
+    int4* h_out = nullptr;   // pinned
+    nr_stats_t stats = {};
+    bool ran = false;
+};
+
+namespace {
+
+typedef void (*ExactKernel)(const nr::Task*, const int32_t*, int, const uint32_t*, nr::ScoreP32, int*, int4*,
+                            long long, int4*);
+
+template <int R>
+ExactKernel pick_exact(int r, bool multi) {
+    if (r == R) return multi ? (ExactKernel)nr::exact_kernel<R, true> : (ExactKernel)nr::exact_kernel<R, false>;
+    if constexpr (R < kMaxR) return pick_exact<R + 1>(r, multi);
+    return nullptr;
+}
+
+size_t exact_smem_bytes(int R) { return (size_t)kWarpsPerBlock * 4 * ((R + 3) / 4) * 32 * sizeof(int4); }
+
+int check_scoring(const nr_scoring_t* sc) {
+    if (!sc) return fail(NR_ERR_ARG, "scoring is NULL");
+    if (sc->match <= 0 || sc->mismatch < 0 || sc->gap_open1 < 0 || sc->gap_ext1 <= 0 || sc->gap_open2 < 0 ||
+        sc->gap_ext2 <= 0)
+        return fail(NR_ERR_ARG, "scoring values out of range");
+    if (sc->gap_open1 + sc->gap_ext1 > 4096 || sc->gap_open2 + sc->gap_ext2 > 4096 || sc->mismatch > 4096 ||
+        sc->match > 4096)
+        return fail(NR_ERR_ARG, "scoring values too large for the packed kernels");
+    return NR_OK;
+}
+
+// Sort tasks into buckets (by stripe shape), each ordered by decreasing cost, and size the launches.
+int plan_batch(nr_batch* b) {
+    const int n = (int)b->tasks.size();
+    b->stats = {};
+    b->stats.n_tasks = n;
+    std::vector<int> shapeR(n);
+    std::vector<uint8_t> shapeM(n);
+    std::vector<long long> cost(n);
+    std::vector<int> bucket_count(2 * (kMaxR + 1), 0);
+    for (int i = 0; i < n; ++i) {
+        const nr::Task& t = b->tasks[i];
+        long long m = (long long)b->sc.match * std::min(t.q_len, t.t_len);
+        if (m > kMaxScore || t.t_len > kMaxTlen)
+            return fail(NR_ERR_TOO_LARGE,
+                        "task %d (query %d x target %d) exceeds the packed range (score <= %d, target <= %d)", i,
+                        t.q_len, t.t_len, kMaxScore, kMaxTlen);
+        int R, ns;
+        bool multi;
+        stripe_shape(t.q_len, R, multi, ns);
+        shapeR[i] = R;
+        shapeM[i] = multi;
+        cost[i] = (long long)t.q_len * t.t_len;
+        b->stats.algorithmic_cells += cost[i];
+        b->stats.executed_cells += (long long)ns * 32 * R * t.t_len;
+        bucket_count[(multi ? kMaxR + 1 : 0) + R]++;
+    }
+    b->order.resize(n);
+    b->buckets.clear();
+    std::vector<int> fill(2 * (kMaxR + 1), 0);
+    int off = 0;
+    std::vector<int> bucket_off(2 * (kMaxR + 1), 0);
+    for (int k = 0; k < 2 * (kMaxR + 1); ++k) { bucket_off[k] = off; off += bucket_count[k]; }
+    for (int i = 0; i < n; ++i) {
+        int k = (shapeM[i] ? kMaxR + 1 : 0) + shapeR[i];
+        b->order[bucket_off[k] + fill[k]++] = i;
+    }
+    size_t scratch_total = 0;
+    // largest buckets first so their tails overlap with the small launches behind them
+    for (int k = 0; k < 2 * (kMaxR + 1); ++k) {
+        if (!bucket_count[k]) continue;
+        Bucket bk;
+        bk.multi = k > kMaxR;
+        bk.R = bk.multi ? k - (kMaxR + 1) : k;
+        bk.order_off = bucket_off[k];
+        bk.count = bucket_count[k];
+        std::sort(b->order.begin() + bk.order_off, b->order.begin() + bk.order_off + bk.count,
+                  [&](int x, int y) { return cost[x] != cost[y] ? cost[x] > cost[y] : x < y; });
+        int max_blocks = g_ctx.sm_count * 4;
+        bk.blocks = std::min(max_blocks, (bk.count + kWarpsPerBlock - 1) / kWarpsPerBlock);
+        bk.scratch_stride = 0;
+        bk.scratch_off = 0;
+        if (bk.multi) {
+            int tmax = 0;
+            for (int j = 0; j < bk.count; ++j) tmax = std::max(tmax, b->tasks[b->order[bk.order_off + j]].t_len);
+            bk.scratch_stride = ((long long)tmax + 63) / 32 * 32;
+            bk.scratch_off = scratch_total;
+            scratch_total += (size_t)bk.blocks * kWarpsPerBlock * 2 * (size_t)bk.scratch_stride;
+        }
+        b->buckets.push_back(bk);
+    }
+    std::sort(b->buckets.begin(), b->buckets.end(), [&](const Bucket& x, const Bucket& y) {
+        return x.count > y.count;
+    });
+    // device allocations + uploads
+    const size_t pool_words = b->pool.words.size() + 4;
+    CUDA_TRY(cudaMalloc(&b->d_tasks, sizeof(nr::Task) * std::max(n, 1)));
+    CUDA_TRY(cudaMalloc(&b->d_order, sizeof(int32_t) * std::max(n, 1)));
+    CUDA_TRY(cudaMalloc(&b->d_pool, sizeof(uint32_t) * pool_words));
+    CUDA_TRY(cudaMalloc(&b->d_counters, sizeof(int) * std::max<size_t>(b->buckets.size(), 1)));
+    CUDA_TRY(cudaMalloc(&b->d_out, sizeof(int4) * std::max(n, 1)));
+    if (scratch_total) CUDA_TRY(cudaMalloc(&b->d_scratch, sizeof(int4) * scratch_total));
+    CUDA_TRY(cudaMallocHost(&b->h_out, sizeof(int4) * std::max(n, 1)));
+    cudaStream_t st = g_ctx.stream;
+    CUDA_TRY(cudaMemsetAsync(b->d_pool, 0, sizeof(uint32_t) * pool_words, st));
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(b->d_tasks, b->tasks.data(), sizeof(nr::Task) * n, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(b->d_order, b->order.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(b->d_pool, b->pool.words.data(), sizeof(uint32_t) * b->pool.words.size(),
+                                 cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    b->stats.h2d_bytes = (int64_t)(sizeof(nr::Task) * n + sizeof(int32_t) * n +
+                                   sizeof(uint32_t) * b->pool.words.size());
+    b->stats.d2h_bytes = (int64_t)sizeof(int4) * n;
+    return NR_OK;
+}
+
+int run_batch(nr_batch* b, cudaStream_t st) {
+    if (b->tasks.empty()) { b->ran = true; return NR_OK; }
+    nr::ScoreP32 k;
+    k.match = b->sc.match << 16;
+    k.mismatch_neg = -(b->sc.mismatch << 16);
+    k.qe1_neg = -((b->sc.gap_open1 + b->sc.gap_ext1) << 16);
+    k.e1_neg = -(b->sc.gap_ext1 << 16);
+    k.qe2_neg = -((b->sc.gap_open2 + b->sc.gap_ext2) << 16);
+    k.e2_neg = -(b->sc.gap_ext2 << 16);
+    CUDA_TRY(cudaMemsetAsync(b->d_counters, 0, sizeof(int) * b->buckets.size(), st));
+    int launches = 0;
+    for (size_t i = 0; i < b->buckets.size(); ++i) {
+        const Bucket& bk = b->buckets[i];
+        ExactKernel fn = pick_exact<kMinR>(bk.R, bk.multi);
+        if (!fn) return fail(NR_ERR_ARG, "no kernel for stripe height %d", bk.R);
+        size_t smem = exact_smem_bytes(bk.R);
+        CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+        fn<<<bk.blocks, kWarpsPerBlock * 32, smem, st>>>(b->d_tasks, b->d_order + bk.order_off, bk.count, b->d_pool,
+                                                        k, b->d_counters + i,
+                                                        bk.multi ? b->d_scratch + bk.scratch_off : nullptr,
+                                                        bk.scratch_stride, b->d_out);
+        CUDA_TRY(cudaGetLastError());
+        ++launches;
+    }
+    b->stats.kernel_launches = launches;
+    b->ran = true;
+    return NR_OK;
+}
+
+int fetch_raw(nr_batch* b) {
+    if (!b->ran) return fail(NR_ERR_ARG, "batch was not run");
+    const size_t n = b->tasks.size();
+    if (!n) return NR_OK;
+    CUDA_TRY(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(int4) * n, cudaMemcpyDeviceToHost, g_ctx.stream));
+    CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
+    return NR_OK;
+}
+
+int add_seq(nr_batch* b, const char* s, int len, const char* what, int idx, uint32_t* word) {
+    if (!s && len > 0) return fail(NR_ERR_ARG, "%s %d is NULL", what, idx);
+    if (len < 0) return fail(NR_ERR_ARG, "%s %d has negative length", what, idx);
+    long long w = b->pool.add(s, len);
+    if (w < 0) return fail(NR_ERR_BAD_BASE, "%s %d contains a character other than ACGT", what, idx);
+    if (w > 0xfffffff0LL) return fail(NR_ERR_TOO_LARGE, "sequence pool exceeds 2^32 words");
+    *word = (uint32_t)w;
+    return NR_OK;
+}
+
+}  // namespace
+
+// ---- exported C ABI --------------------------------------------------------------------------------------------
+extern "C" {
+
+int nr_get_preset(const char* data_type, nr_scoring_t* out) {
+    if (!data_type || !out) return fail(NR_ERR_ARG, "nr_get_preset: NULL argument");
+    // reference tk.py:502-517: all five data types map to `-x map-ont`
+    static const char* names[] = {"ont", "ont_sup", "ont_q20", "clr", "hifi"};
+    for (const char* n : names) {
+        if (strcmp(n, data_type) == 0) {
+            nr_scoring_t s = {2, 4, 4, 2, 24, 1, 1, 80};
+            *out = s;
+            return NR_OK;
+        }
+    }
+    return fail(NR_ERR_UNKNOWN_TYPE, "Unknown data type: %s", data_type);
+}
+
+int nr_init(int device) { return ensure_init(device); }
+
+int nr_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (g_ctx.ready) {
+        cudaStreamDestroy(g_ctx.stream);
+        g_ctx = Context();
+    }
+    return NR_OK;
+}
+
+const char* nr_last_error(void) { return g_err.c_str(); }
+
+int nr_device_info(int32_t* device, int32_t* sm_count, int32_t* clock_khz) {
+    int rc = ensure_init(-1);
+    if (rc) return rc;
+    if (device) *device = g_ctx.device;
+    if (sm_count) *sm_count = g_ctx.sm_count;
+    if (clock_khz) *clock_khz = g_ctx.clock_khz;
+    return NR_OK;
+}
+
+int nr_limits(int32_t* max_score, int32_t* max_tlen) {
+    if (max_score) *max_score = kMaxScore;
+    if (max_tlen) *max_tlen = kMaxTlen;
+    return NR_OK;
+}
+
+void nr_batch_destroy(nr_batch_t* b) {
+    if (!b) return;
+    cudaFree(b->d_tasks);
+    cudaFree(b->d_order);
+    cudaFree(b->d_pool);
+    cudaFree(b->d_counters);
+    cudaFree(b->d_out);
+    cudaFree(b->d_scratch);
+    if (b->h_out) cudaFreeHost(b->h_out);
+    delete b;
+}
+
+nr_batch_t* nr_batch_create_tasks(const nr_scoring_t* sc, int32_t n_tasks, const char* const* queries,
+                                  const int32_t* qlen, const char* const* targets, const int32_t* tlen) {
+    if (check_scoring(sc)) return nullptr;
+    if (n_tasks < 0 || (n_tasks > 0 && (!queries || !qlen || !targets || !tlen))) {
+        fail(NR_ERR_ARG, "nr_batch_create_tasks: bad arguments");
+        return nullptr;
+    }
+    if (ensure_init(-1)) return nullptr;
+    nr_batch* b = new (std::nothrow) nr_batch();
+    if (!b) { fail(NR_ERR_NOMEM, "out of host memory"); return nullptr; }
+    b->kind = KIND_TASKS;
+    b->sc = *sc;
+    b->tasks.resize(n_tasks);
+    std::unordered_map<const char*, std::pair<int, uint32_t>> seen;   // pointer -> (len, word): callers often
+    for (int i = 0; i < n_tasks; ++i) {                                // pass one template for many reads
+        nr::Task& t = b->tasks[i];
+        t.q_len = qlen[i];
+        t.t_len = tlen[i];
+        const char* ptrs[2] = {queries[i], targets[i]};
+        const int lens[2] = {qlen[i], tlen[i]};
+        uint32_t words[2];
+        for (int s = 0; s < 2; ++s) {
+            auto it = seen.find(ptrs[s]);
+            if (it != seen.end() && it->second.first == lens[s]) { words[s] = it->second.second; continue; }
+            if (add_seq(b, ptrs[s], lens[s], s ? "target" : "query", i, &words[s])) { nr_batch_destroy(b); return nullptr; }
+            seen[ptrs[s]] = std::make_pair(lens[s], words[s]);
+        }
+        t.q_word = words[0];
+        t.t_word = words[1];
+    }
+    if (plan_batch(b)) { nr_batch_destroy(b); return nullptr; }
+    return b;
+}
+
+nr_batch_t* nr_batch_create_round2(const nr_scoring_t* sc, const char* left, int32_t n_left, const char* motif,
+                                   int32_t motif_len, int32_t T, int32_t n_reads, const char* const* cores,
+                                   const int32_t* core_len) {
+    if (check_scoring(sc)) return nullptr;
+    if (n_left < 0 || motif_len <= 0 || T < 0 || n_reads < 0 || !motif || (n_left > 0 && !left) ||
+        (n_reads > 0 && (!cores || !core_len))) {
+        fail(NR_ERR_ARG, "nr_batch_create_round2: bad arguments");
+        return nullptr;
+    }
+    if (ensure_init(-1)) return nullptr;
+    nr_batch* b = new (std::nothrow) nr_batch();
+    if (!b) { fail(NR_ERR_NOMEM, "out of host memory"); return nullptr; }
+    b->kind = KIND_ROUND2;
+    b->sc = *sc;
+    // template = left + motif * T   (nanoRepeat_bam.py:352-354)
+    std::string tpl(left ? left : "", (size_t)n_left);
+    tpl.reserve((size_t)n_left + (size_t)motif_len * T);
+    for (int k = 0; k < T; ++k) tpl.append(motif, (size_t)motif_len);
+    uint32_t tw;
+    if (add_seq(b, tpl.data(), (int)tpl.size(), "round-2 template", 0, &tw)) { nr_batch_destroy(b); return nullptr; }
+    b->tasks.resize(n_reads);
+    for (int r = 0; r < n_reads; ++r) {
+        nr::Task& t = b->tasks[r];
+        if (add_seq(b, cores[r], core_len[r], "core", r, &t.q_word)) { nr_batch_destroy(b); return nullptr; }
+        t.q_len = core_len[r];
+        t.t_word = tw;
+        t.t_len = (int)tpl.size();
+    }
+    if (plan_batch(b)) { nr_batch_destroy(b); return nullptr; }
+    return b;
+}
+
+nr_batch_t* nr_batch_create_round3(const nr_scoring_t* sc, const char* left, int32_t n_left, const char* right,
+                                   int32_t n_right, const char* motif, int32_t motif_len, int32_t n_reads,
+                                   const char* const* cores, const int32_t* core_len, const int32_t* kmin,
+                                   const int32_t* kmax) {
+    if (check_scoring(sc)) return nullptr;
+    if (n_left < 0 || n_right < 0 || motif_len <= 0 || n_reads < 0 || !motif || (n_left > 0 && !left) ||
+        (n_right > 0 && !right) || (n_reads > 0 && (!cores || !core_len || !kmin || !kmax))) {
+        fail(NR_ERR_ARG, "nr_batch_create_round3: bad arguments");
+        return nullptr;
+    }
+    if (ensure_init(-1)) return nullptr;
+    nr_batch* b = new (std::nothrow) nr_batch();
+    if (!b) { fail(NR_ERR_NOMEM, "out of host memory"); return nullptr; }
+    b->kind = KIND_ROUND3;
+    b->sc = *sc;
+    b->n_reads = n_reads;
+    b->n_left = n_left;
+    b->n_right = n_right;
+    b->motif_len = motif_len;
+    b->kmin.assign(kmin, kmin + n_reads);
+    b->kmax.assign(kmax, kmax + n_reads);
+    b->rung_off.assign(n_reads + 1, 0);
+    int klo = INT32_MAX, khi = -1;
+    for (int r = 0; r < n_reads; ++r) {
+        if (kmin[r] < 0) { fail(NR_ERR_ARG, "kmin[%d] < 0", r); nr_batch_destroy(b); return nullptr; }
+        long long n = kmax[r] >= kmin[r] ? (long long)kmax[r] - kmin[r] + 1 : 0;
+        b->rung_off[r + 1] = b->rung_off[r] + n;
+        if (n) { klo = std::min(klo, kmin[r]); khi = std::max(khi, kmax[r]); }
+    }
+    if (b->rung_off[n_reads] > 0x7fffffffLL) {
+        fail(NR_ERR_TOO_LARGE, "more than 2^31 rungs in one call");
+        nr_batch_destroy(b);
+        return nullptr;
+    }
+    // ladder templates left + motif*k + right, one per distinct k that any read uses (nanoRepeat_bam.py:478-479)
+    std::vector<uint32_t> tpl_word;
+    std::vector<uint8_t> used;
+    if (khi >= klo) {
+        used.assign(khi - klo + 1, 0);
+        for (int r = 0; r < n_reads; ++r)
+            for (int k = kmin[r]; k <= kmax[r]; ++k) used[k - klo] = 1;
+        tpl_word.assign(khi - klo + 1, 0);
+        std::string tpl;
+        for (int k = klo; k <= khi; ++k) {
+            if (!used[k - klo]) continue;
+            tpl.assign(left ? left : "", (size_t)n_left);
+            for (int u = 0; u < k; ++u) tpl.append(motif, (size_t)motif_len);
+            tpl.append(right ? right : "", (size_t)n_right);
+            if (add_seq(b, tpl.data(), (int)tpl.size(), "ladder template", k, &tpl_word[k - klo])) {
+                nr_batch_destroy(b);
+                return nullptr;
+            }
+        }
+    }
+    b->tasks.resize((size_t)b->rung_off[n_reads]);
+    for (int r = 0; r < n_reads; ++r) {
+        if (b->rung_off[r + 1] == b->rung_off[r]) continue;
+        uint32_t qw;
+        if (add_seq(b, cores[r], core_len[r], "core", r, &qw)) { nr_batch_destroy(b); return nullptr; }
+        for (int k = kmin[r]; k <= kmax[r]; ++k) {
+            nr::Task& t = b->tasks[(size_t)(b->rung_off[r] + (k - kmin[r]))];
+            t.q_word = qw;
+            t.q_len = core_len[r];
+            t.t_word = tpl_word[k - klo];
+            t.t_len = n_left + motif_len * k + n_right;
+        }
+    }
+    if (plan_batch(b)) { nr_batch_destroy(b); return nullptr; }
+    return b;
+}
+
+int nr_batch_run(nr_batch_t* b, void* stream) {
+    if (!b) return fail(NR_ERR_ARG, "nr_batch_run: NULL batch");
+    return run_batch(b, stream ? (cudaStream_t)stream : g_ctx.stream);
+}
+
+int nr_batch_fetch_alns(nr_batch_t* b, nr_aln_t* out) {
+    if (!b || (!out && !b->tasks.empty())) return fail(NR_ERR_ARG, "nr_batch_fetch_alns: NULL argument");
+    int rc = fetch_raw(b);
+    if (rc) return rc;
+    for (size_t i = 0; i < b->tasks.size(); ++i) {
+        out[i].score = b->h_out[i].x;
+        out[i].tstart = b->h_out[i].y;
+        out[i].tend = b->h_out[i].z;
+    }
+    return NR_OK;
+}
+
+int nr_batch_fetch_round3(nr_batch_t* b, const int64_t* rung_offset, nr_rung_t* rungs, int64_t* sum_k,
+                          int32_t* n_k, int32_t* top_score) {
+    if (!b || b->kind != KIND_ROUND3) return fail(NR_ERR_ARG, "nr_batch_fetch_round3: not a round-3 batch");
+    if (b->n_reads > 0 && (!sum_k || !n_k || !top_score)) return fail(NR_ERR_ARG, "nr_batch_fetch_round3: NULL output");
+    if (rungs && !rung_offset) return fail(NR_ERR_ARG, "rungs given without rung_offset");
+    int rc = fetch_raw(b);
+    if (rc) return rc;
+    const int min_score = std::max(1, b->sc.min_dp_score);
+    for (int r = 0; r < b->n_reads; ++r) {
+        const int64_t o = b->rung_off[r];
+        const int n = (int)(b->rung_off[r + 1] - o);
+        int top = 0;
+        for (int i = 0; i < n; ++i) {
+            int s = b->h_out[o + i].x;
+            if (s >= min_score && s > top) top = s;
+        }
+        int64_t sum = 0;
+        int cnt = 0;
+        for (int i = 0; i < n; ++i) {
+            const int4 a = b->h_out[o + i];
+            const int k = b->kmin[r] + i;
+            const int tlen = b->n_left + b->motif_len * k + b->n_right;
+            const bool in_left = a.x > 0 && a.y < b->n_left;               // tstart < |left|  (:427)
+            const bool in_right = a.x > 0 && tlen - a.z < b->n_right;      // tlen - tend < |right|
+            if (rungs) {
+                nr_rung_t& g = rungs[rung_offset[r] + i];
+                g.score = a.x;
+                g.starts_in_left = in_left;
+                g.ends_in_right = in_right;
+                g.pad[0] = g.pad[1] = 0;
+            }
+            if (top > 0 && a.x == top && in_left && in_right) { sum += k; ++cnt; }
+        }
+        sum_k[r] = sum;
+        n_k[r] = cnt;
+        top_score[r] = top;
+    }
+    return NR_OK;
+}
+
+int nr_batch_stats(const nr_batch_t* b, nr_stats_t* out) {
+    if (!b || !out) return fail(NR_ERR_ARG, "nr_batch_stats: NULL argument");
+    *out = b->stats;
+    return NR_OK;
+}
+
+int nr_last_stats(nr_stats_t* out) {
+    if (!out) return fail(NR_ERR_ARG, "nr_last_stats: NULL argument");
+    *out = g_last_stats;
+    return NR_OK;
+}
+
+int nr_score_tasks(const nr_scoring_t* sc, int32_t n_tasks, const char* const* queries, const int32_t* qlen,
+                   const char* const* targets, const int32_t* tlen, nr_aln_t* out) {
+    if (n_tasks > 0 && !out) return fail(NR_ERR_ARG, "nr_score_tasks: out is NULL");
+    nr_batch_t* b = nr_batch_create_tasks(sc, n_tasks, queries, qlen, targets, tlen);
+    if (!b) return g_code;
+    int rc = nr_batch_run(b, nullptr);
+    if (!rc) rc = nr_batch_fetch_alns(b, out);
+    g_last_stats = b->stats;
+    nr_batch_destroy(b);
+    return rc;
+}
+
+int nr_round2_region(const nr_scoring_t* sc, const char* left, int32_t n_left, const char* motif,
+                     int32_t motif_len, int32_t T, int32_t n_reads, const char* const* cores,
+                     const int32_t* core_len, nr_aln_t* out) {
+    if (n_reads > 0 && !out) return fail(NR_ERR_ARG, "nr_round2_region: out is NULL");
+    nr_batch_t* b = nr_batch_create_round2(sc, left, n_left, motif, motif_len, T, n_reads, cores, core_len);
+    if (!b) return g_code;
+    int rc = nr_batch_run(b, nullptr);
+    if (!rc) rc = nr_batch_fetch_alns(b, out);
+    g_last_stats = b->stats;
+    nr_batch_destroy(b);
+    return rc;
+}
+
+int nr_round3_region(const nr_scoring_t* sc, const char* left, int32_t n_left, const char* right, int32_t n_right,
+                     const char* motif, int32_t motif_len, int32_t n_reads, const char* const* cores,
+                     const int32_t* core_len, const int32_t* kmin, const int32_t* kmax,
+                     const int64_t* rung_offset, nr_rung_t* rungs, int64_t* sum_k, int32_t* n_k,
+                     int32_t* top_score) {
+    nr_batch_t* b = nr_batch_create_round3(sc, left, n_left, right, n_right, motif, motif_len, n_reads, cores,
+                                           core_len, kmin, kmax);
+    if (!b) return g_code;
+    int rc = nr_batch_run(b, nullptr);
+    if (!rc) rc = nr_batch_fetch_round3(b, rung_offset, rungs, sum_k, n_k, top_score);
+    g_last_stats = b->stats;
+    nr_batch_destroy(b);
+    return rc;
+}
+
+}  // extern "C"

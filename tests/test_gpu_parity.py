@@ -1,0 +1,207 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle and the golden fixtures.
+Integer work: everything is compared bit-exact."""
+import random
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_SETS, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_seq(rng, n):
+    return "".join(rng.choice("ACGT") for _ in range(n))
+
+
+def _mutate(rng, s, rate):
+    out = []
+    for ch in s:
+        u = rng.random()
+        if u < rate / 3:
+            continue
+        if u < 2 * rate / 3:
+            out.append(rng.choice("ACGT"))
+            continue
+        if u < rate:
+            out.append(rng.choice("ACGT"))
+        out.append(ch)
+    return "".join(out)
+
+
+def _assert_same(got, ref, ctx=""):
+    if not np.array_equal(got, ref):
+        bad = [i for i in range(len(ref)) if tuple(got[i]) != tuple(ref[i])]
+        raise AssertionError(f"{ctx}: {len(bad)} of {len(ref)} records differ; first: task {bad[0]} got "
+                             f"{tuple(got[bad[0]])} expected {tuple(ref[bad[0]])}")
+
+
+def test_micro_known_answers(engine, oracle):
+    from test_oracle import micro_cases
+    cases = micro_cases()
+    sc = engine.get_preset("ont")
+    got = engine.score_tasks([c[1] for c in cases], [c[2] for c in cases], sc)
+    for c, g in zip(cases, got):
+        assert tuple(int(v) for v in g) == c[3], c[0]
+
+
+@pytest.mark.parametrize("seed,qmax,tmax,n", [(1, 40, 90, 400), (2, 300, 700, 300), (3, 520, 2400, 120),
+                                              (4, 1500, 3000, 40), (5, 130, 130, 300)])
+def test_random_tasks_match_oracle(engine, oracle, seed, qmax, tmax, n):
+    """Every stripe height (R = 4..16), single- and multi-stripe, related and unrelated pairs."""
+    rng = random.Random(seed)
+    qs, ts = [], []
+    for it in range(n):
+        ql = rng.randint(1, qmax)
+        q = _rand_seq(rng, ql)
+        kind = it % 4
+        if kind == 0:
+            t = _rand_seq(rng, rng.randint(1, tmax))
+        elif kind == 1:      # query embedded with errors
+            pad = rng.randint(0, max(0, tmax - ql) // 2)
+            t = _rand_seq(rng, pad) + _mutate(rng, q, 0.1) + _rand_seq(rng, rng.randint(0, pad))
+        elif kind == 2:      # low-complexity repeats: many ties
+            unit = _rand_seq(rng, rng.randint(1, 6))
+            q = (unit * (ql // len(unit) + 1))[:ql]
+            t = _rand_seq(rng, rng.randint(0, 30)) + unit * rng.randint(1, max(1, tmax // (2 * len(unit)))) + _rand_seq(rng, rng.randint(0, 30))
+        else:                # long gap in the middle (second affine piece)
+            gap = rng.randint(1, 60)
+            t = q[:ql // 2] + _rand_seq(rng, gap) + q[ql // 2:]
+        qs.append(q)
+        ts.append(t[:tmax] if len(t) > tmax else t)
+    sc = engine.get_preset("ont")
+    got = engine.score_tasks(qs, ts, sc)
+    ref = oracle.align_batch(qs, ts, n_threads=oracle.max_threads())
+    _assert_same(got, ref, f"seed {seed}")
+
+
+def test_stripe_boundaries_exact_sizes(engine, oracle):
+    """Query lengths around every stripe-shape boundary (32*R, 512, 1024 ...)."""
+    rng = random.Random(9)
+    qs, ts = [], []
+    for ql in [1, 2, 31, 32, 33, 127, 128, 129, 160, 161, 287, 288, 289, 511, 512, 513, 544, 1023, 1024, 1025, 1537]:
+        q = _rand_seq(rng, ql)
+        t = _rand_seq(rng, 40) + _mutate(rng, q, 0.08) + _rand_seq(rng, 70)
+        qs.append(q)
+        ts.append(t)
+    for tl in [1, 15, 16, 17, 31, 32, 33, 63, 64, 65]:
+        q = _rand_seq(rng, 50)
+        qs.append(q)
+        ts.append((q + _rand_seq(rng, 100))[:tl])
+    sc = engine.get_preset("hifi")
+    _assert_same(engine.score_tasks(qs, ts, sc), oracle.align_batch(qs, ts), "boundaries")
+
+
+def test_other_scoring_values(engine, oracle):
+    rng = random.Random(21)
+    qs = [_rand_seq(rng, rng.randint(20, 200)) for _ in range(60)]
+    ts = [_rand_seq(rng, 20) + _mutate(rng, q, 0.15) + _rand_seq(rng, 20) for q in qs]
+    for kw in (dict(match=1, mismatch=3, gap_open1=5, gap_ext1=2, gap_open2=30, gap_ext2=1),
+               dict(match=3, mismatch=2, gap_open1=1, gap_ext1=3, gap_open2=10, gap_ext2=2)):
+        osc = oracle.scoring(**kw)
+        sc = engine.Scoring(**{n: getattr(osc, n) for n, _ in engine.Scoring._fields_})
+        _assert_same(engine.score_tasks(qs, ts, sc), oracle.align_batch(qs, ts, osc), str(kw))
+
+
+def test_empty_and_degenerate_inputs(engine):
+    sc = engine.get_preset("ont")
+    assert len(engine.score_tasks([], [], sc)) == 0
+    got = engine.score_tasks(["", "ACGT", ""], ["ACGT", "", ""], sc)
+    assert [tuple(int(v) for v in g) for g in got] == [(0, 0, 0)] * 3
+    assert len(engine.round2_region(sc, "ACGT" * 10, "CAG", 5, [])) == 0
+    s, n, t = engine.round3_region(sc, "ACGT" * 10, "TTGA" * 10, "CAG", [], np.zeros(0, np.int32), np.zeros(0, np.int32))
+    assert len(s) == 0 and len(n) == 0 and len(t) == 0
+    # empty ladder (kmax < kmin) for one read
+    s, n, t = engine.round3_region(sc, "ACGT" * 10, "TTGA" * 10, "CAG", ["ACGTACGTCAGCAGTTGATTGA"], [3], [2])
+    assert (int(s[0]), int(n[0]), int(t[0])) == (0, 0, 0)
+
+
+def test_errors_are_reported_not_fatal(engine):
+    sc = engine.get_preset("ont")
+    with pytest.raises(engine.NanoRepeatB200Error) as ei:
+        engine.score_tasks(["ACGTN"], ["ACGT"], sc)
+    assert ei.value.code == -3
+    with pytest.raises(engine.NanoRepeatB200Error) as ei:
+        engine.score_tasks(["A" * 20000], ["A" * 20000], sc)
+    assert ei.value.code == -4
+    with pytest.raises(ValueError):
+        engine.get_preset("pacbio")
+    # the library is still usable afterwards
+    assert tuple(int(v) for v in engine.score_tasks(["ACGT"], ["ACGT"], sc)[0]) == (8, 0, 4)
+
+
+def test_round3_rungs_match_oracle(engine, oracle):
+    from nanorepeat_b200 import synth
+    reg = synth.config1(seed=3, n_regions=1, reads_per_region=10)[0]
+    sc = engine.get_preset("ont_q20")
+    n = len(reg.core_seqs)
+    kmin = np.array([max(0, k - 15) for k in reg.true_sizes], dtype=np.int32)
+    kmax = np.array([k + 15 for k in reg.true_sizes], dtype=np.int32)
+    sum_k, n_k, top, rungs, off = engine.round3_region(sc, reg.left_anchor_seq, reg.right_anchor_seq,
+                                                       reg.repeat_unit_seq, reg.core_seqs, kmin, kmax, want_rungs=True)
+    ref, roff = oracle.align_ladders(reg.core_seqs, reg.left_anchor_seq, reg.right_anchor_seq, reg.repeat_unit_seq,
+                                     kmin, kmax, n_threads=oracle.max_threads())
+    assert np.array_equal(off, roff)
+    nl, nr_, m = len(reg.left_anchor_seq), len(reg.right_anchor_seq), len(reg.repeat_unit_seq)
+    for r in range(n):
+        for i in range(int(off[r]), int(off[r + 1])):
+            k = int(kmin[r]) + i - int(off[r])
+            a = ref[i]
+            assert int(rungs[i]["score"]) == int(a["score"])
+            assert bool(rungs[i]["starts_in_left"]) == (a["score"] > 0 and a["tstart"] < nl)
+            assert bool(rungs[i]["ends_in_right"]) == (a["score"] > 0 and (nl + m * k + nr_) - a["tend"] < nr_)
+
+
+@pytest.mark.parametrize("name", GOLDEN_SETS)
+def test_golden_fixtures_through_operator_api(engine, name):
+    """Reads like the reference's own use: fill a RepeatRegion, call the two operators, compare the attributes
+    with what the reference's unmodified functions produced (tests/golden/make_golden.py)."""
+    import nanorepeat_b200 as nrb
+    doc = load_golden(name)
+    for reg in doc["regions"]:
+        rr = nrb.RepeatRegion()
+        rr.left_anchor_seq, rr.right_anchor_seq = reg["left"], reg["right"]
+        rr.left_anchor_len, rr.right_anchor_len = len(reg["left"]), len(reg["right"])
+        rr.repeat_unit_seq = reg["motif"]
+        for nme, core, dist in zip(reg["read_names"], reg["cores"], reg["dists"]):
+            rr.read_dict[nme] = nrb.Read(nme, dist)
+            rr.read_core_seq_dict[nme] = core
+        nrb.round1_and_round2_estimation(reg["data_type"], rr, 1)
+        nrb.round3_estimation(reg["data_type"], doc["fast_mode"], rr, 1)
+        for nme, exp in zip(reg["read_names"], reg["expected"]):
+            rd = rr.read_dict[nme]
+            assert rd.round1_repeat_size == exp["r1"], (reg["name"], nme)
+            assert rd.round2_repeat_size == exp["r2"], (reg["name"], nme)
+            g3 = rd.round3_repeat_size
+            assert (None if g3 is None else float(g3)) == exp["r3"], (reg["name"], nme, g3, exp["r3"])
+
+
+def test_results_independent_of_batch_composition(engine):
+    """Determinism clause of the boundary: a task's record does not depend on its neighbours."""
+    rng = random.Random(31)
+    qs = [_rand_seq(rng, rng.randint(10, 900)) for _ in range(50)]
+    ts = [_rand_seq(rng, 30) + _mutate(rng, q, 0.1) + _rand_seq(rng, 30) for q in qs]
+    sc = engine.get_preset("ont")
+    full = engine.score_tasks(qs, ts, sc)
+    perm = list(range(50))
+    rng.shuffle(perm)
+    part = engine.score_tasks([qs[i] for i in perm[:17]], [ts[i] for i in perm[:17]], sc)
+    for j, i in enumerate(perm[:17]):
+        assert tuple(part[j]) == tuple(full[i])
+
+
+def test_long_expanded_allele_shape(engine, oracle):
+    """cfg4-like: core of a few kb (many stripes) against a template of ~3.5 kb, with the round-trip property
+    that a perfect read scores 2*|core| and spans the template exactly."""
+    from nanorepeat_b200 import synth
+    rng = np.random.default_rng(4)
+    L, R = synth.random_seq(rng, 1000), synth.random_seq(rng, 1000)
+    k = 500
+    perfect = L[-100:] + "CGG" * k + R[:100]
+    noisy, _, _ = synth.simulate_core(rng, L, R, "CGG", k, "ont_r9")
+    tpl = L + "CGG" * k + R
+    sc = engine.get_preset("ont")
+    got = engine.score_tasks([perfect, noisy], [tpl, tpl], sc)
+    assert tuple(int(v) for v in got[0]) == (2 * len(perfect), 900, 1000 + 3 * k + 100)
+    ref = oracle.align_batch([perfect, noisy], [tpl, tpl], n_threads=2)
+    _assert_same(got, ref, "long allele")
