@@ -98,17 +98,21 @@ def round3_estimation(data_type, fast_mode, repeat_region, num_cpu=1):
         kmax.append(hi)
     if not names:
         return
-    sum_k, n_k, top, rungs, off = engine.round3_region(
+    sum_k, n_k, top = engine.round3_region(
         sc, repeat_region.left_anchor_seq, repeat_region.right_anchor_seq, repeat_region.repeat_unit_seq,
-        cores, np.asarray(kmin, dtype=np.int32), np.asarray(kmax, dtype=np.int32), want_rungs=True)
+        cores, np.asarray(kmin, dtype=np.int32), np.asarray(kmax, dtype=np.int32))
+    # np.mean(list of k) == float64(sum k) / n exactly: the k are small integers, so every partial sum is an
+    # exactly representable float64 and numpy's pairwise summation cannot round (tests/test_host.py checks it)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mean_k = sum_k.astype(np.float64) / n_k.astype(np.float64)
     for i, read_name in enumerate(names):
         read = repeat_region.read_dict[read_name]
-        best = None
+        if top[i] <= 0:
+            continue                                                            # no PAF line at all (:421)
         if n_k[i] > 0:
-            r = rungs[off[i]:off[i + 1]]
-            sel = (r["score"] == top[i]) & (r["starts_in_left"] != 0) & (r["ends_in_right"] != 0)
-            best = (np.nonzero(sel)[0] + kmin[i]).tolist()
-        round3_estimation_for1read(read, int(n_k[i]), int(sum_k[i]), int(top[i]), best)
+            read.round3_repeat_size = mean_k[i]                                 # :431
+        else:
+            read.round3_repeat_size = read.round2_repeat_size                   # :433
     return
 
 

@@ -85,3 +85,15 @@ def test_synth_is_seeded_and_acgt_only():
     r2, r3 = synth.algorithmic_cells(1000, 1000, 5, 285, 27, 2, 32)
     assert r2 == 285 * (1000 + 135)
     assert r3 == 285 * sum(2000 + 5 * k for k in range(2, 33))
+
+
+def test_mean_of_tied_rungs_is_exact_as_sum_over_count():
+    """estimation.round3_estimation returns float64(sum k)/n; the reference calls np.mean(list) (:431)."""
+    rng = np.random.default_rng(3)
+    for _ in range(2000):
+        n = int(rng.integers(1, 302))
+        lo = int(rng.integers(0, 3000))
+        ks = sorted(rng.choice(np.arange(lo, lo + 301), size=n, replace=False).tolist())
+        a = np.mean(ks)
+        b = np.float64(np.int64(sum(ks))) / np.float64(np.int32(n))
+        assert a == b and type(a) is type(b)
