@@ -86,6 +86,15 @@ int nr_device_info(int32_t* device, int32_t* sm_count, int32_t* clock_khz);
 /* Largest task the packed kernels accept: match * min(qlen, tlen) <= max_score and tlen <= max_tlen. */
 int nr_limits(int32_t* max_score, int32_t* max_tlen);
 
+/*
+ * How round 3 is computed (results are identical, bit for bit; tests run both):
+ *   1 (default)  one backward sweep over the right anchor and one forward sweep over left + motif*kmax per read,
+ *                joined at every junction column |left| + k*|motif| (the rungs share their prefix and suffix);
+ *   0            every rung left + motif*k + right scored as its own full rectangle (what the reference hands its
+ *                aligner, nanoRepeat_bam.py:474-497).
+ */
+int nr_set_ladder_mode(int mode);
+
 /* Generic engine: n independent (query, target) tasks -> out[i]. Replaces pymm2.main at the PAF level. */
 int nr_score_tasks(const nr_scoring_t* sc, int32_t n_tasks,
                    const char* const* queries, const int32_t* qlen,

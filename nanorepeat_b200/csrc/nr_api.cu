@@ -9,6 +9,7 @@
 #include "nr_kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -56,7 +57,6 @@ std::mutex g_ctx_mu;
 
 constexpr int kMaxScore = 32767;   // signed 16-bit score field of the packed DP word
 constexpr int kMaxTlen = 65535;    // unsigned 16-bit start-column field
-constexpr int kMinR = 4, kMaxR = 16;
 constexpr int kWarpsPerBlock = 4;
 
 int ensure_init(int device) {
@@ -124,24 +124,18 @@ struct Pool {
 struct Bucket {
     int R;
     bool multi;
+    bool ladder;     // ladder_kernel over nr_batch::ltasks instead of exact_kernel over nr_batch::tasks
+                     // (R = tallest stripe of the launch: sizes the shared memory per warp)
     int order_off;   // offset into the order array
     int count;
     int blocks;
     long long scratch_stride;   // int4 per boundary row (multi only)
+    long long b_stride;         // ladder + multi: int4 of backward junction vectors per warp
+    long long tok_stride;       // ladder + multi: ulonglong2 per token row
     size_t scratch_off;         // int4 offset into d_scratch
 };
 
-void stripe_shape(int q_len, int& R, bool& multi, int& n_stripes) {
-    if (q_len <= 32 * kMaxR) {
-        multi = false;
-        n_stripes = 1;
-        R = std::max(kMinR, (q_len + 31) / 32);
-    } else {
-        multi = true;
-        n_stripes = (q_len + 32 * kMaxR - 1) / (32 * kMaxR);
-        R = (q_len + 32 * n_stripes - 1) / (32 * n_stripes);
-    }
-}
+std::atomic<int> g_ladder_mode{1};   // 1: round 3 shares sweeps across the ladder; 0: every rung its own rectangle
 
 }  // namespace
 
@@ -151,6 +145,10 @@ struct nr_batch {
     BatchKind kind = KIND_TASKS;
     nr_scoring_t sc = {};
     std::vector<nr::Task> tasks;
+    std::vector<nr::LadderTask> ltasks;   // round 3 in ladder mode (tasks stays empty)
+    nr::LadderRegion lreg = {};
+    bool ladder = false;
+    size_t n_out = 0;                     // records in d_out / h_out
     std::vector<int32_t> order;
     std::vector<Bucket> buckets;
     Pool pool;
@@ -160,6 +158,7 @@ struct nr_batch {
     std::vector<int64_t> rung_off;   // n_reads + 1
     // device
     nr::Task* d_tasks = nullptr;
+    nr::LadderTask* d_ltasks = nullptr;
     int32_t* d_order = nullptr;
     uint32_t* d_pool = nullptr;
     int* d_counters = nullptr;
@@ -168,21 +167,19 @@ struct nr_batch {
     int4* h_out = nullptr;   // pinned
     nr_stats_t stats = {};
     bool ran = false;
+    cudaStream_t run_stream = nullptr;    // stream of the last nr_batch_run: fetch orders itself behind it
 };
 
 namespace {
 
-typedef void (*ExactKernel)(const nr::Task*, const int32_t*, int, const uint32_t*, nr::ScoreP32, int*, int4*,
+typedef void (*ExactKernel)(const nr::Task*, const int32_t*, int, const uint32_t*, nr::ScoreW, int*, int, int4*,
                             long long, int4*);
+typedef void (*LadderKernel)(const nr::LadderTask*, const int32_t*, int, const uint32_t*, nr::LadderRegion,
+                             nr::ScoreW, int*, int, int4*, long long, long long, long long, int4*);
 
-template <int R>
-ExactKernel pick_exact(int r, bool multi) {
-    if (r == R) return multi ? (ExactKernel)nr::exact_kernel<R, true> : (ExactKernel)nr::exact_kernel<R, false>;
-    if constexpr (R < kMaxR) return pick_exact<R + 1>(r, multi);
-    return nullptr;
-}
-
-size_t exact_smem_bytes(int R) { return (size_t)kWarpsPerBlock * 4 * ((R + 3) / 4) * 32 * sizeof(int4); }
+// shared memory per warp, in int4: query profile (+ backward junction vectors for the ladder kernel)
+int exact_smem_int4(int R) { return 4 * ((R + 3) / 4) * 32; }
+int ladder_smem_int4(int R) { return exact_smem_int4(R) + R * 32; }
 
 int check_scoring(const nr_scoring_t* sc) {
     if (!sc) return fail(NR_ERR_ARG, "scoring is NULL");
@@ -195,116 +192,164 @@ int check_scoring(const nr_scoring_t* sc) {
     return NR_OK;
 }
 
+nr::ScoreW score_words(const nr_scoring_t& sc) {
+    nr::ScoreW k;
+    k.sub_match = (sc.match << 16) - 1;
+    k.sub_mismatch = -(sc.mismatch << 16) - 1;
+    k.h_open1 = -((sc.gap_open1 + sc.gap_ext1) << 16) - 1;
+    k.h_ext1 = -(sc.gap_ext1 << 16) - 1;
+    k.h_open2 = -((sc.gap_open2 + sc.gap_ext2) << 16) - 1;
+    k.h_ext2 = -(sc.gap_ext2 << 16) - 1;
+    k.v_open1 = -((sc.gap_open1 + sc.gap_ext1) << 16);
+    k.v_ext1 = -(sc.gap_ext1 << 16);
+    k.v_open2 = -((sc.gap_open2 + sc.gap_ext2) << 16);
+    k.v_ext2 = -(sc.gap_ext2 << 16);
+    k.refund1 = sc.gap_open1 << 16;
+    k.refund2 = sc.gap_open2 << 16;
+    return k;
+}
+
 // Sort tasks into buckets (by stripe shape), each ordered by decreasing cost, and size the launches.
 int plan_batch(nr_batch* b) {
-    const int n = (int)b->tasks.size();
+    const bool ladder = b->ladder;
+    const int n = ladder ? (int)b->ltasks.size() : (int)b->tasks.size();
+    if (!ladder) b->n_out = b->tasks.size();
     b->stats = {};
-    b->stats.n_tasks = n;
-    std::vector<int> shapeR(n);
+    b->stats.n_tasks = (int64_t)b->n_out;
     std::vector<uint8_t> shapeM(n);
     std::vector<long long> cost(n);
-    std::vector<int> bucket_count(2 * (kMaxR + 1), 0);
+    const int max_r = ladder ? nr::kMaxRLadder : nr::kMaxRExact;
+    int n_multi = 0;
+    int rmax[2] = {0, 0}, tmax[2] = {0, 0}, qmax[2] = {0, 0}, rungs_max[2] = {0, 0};
+    const int lad_cols = b->lreg.n_left + b->lreg.n_right;
     for (int i = 0; i < n; ++i) {
-        const nr::Task& t = b->tasks[i];
-        long long m = (long long)b->sc.match * std::min(t.q_len, t.t_len);
-        if (m > kMaxScore || t.t_len > kMaxTlen)
+        int q_len, t_len, t_sweep, rungs = 0;
+        if (ladder) {
+            const nr::LadderTask& t = b->ltasks[i];
+            q_len = t.q_len;
+            t_len = lad_cols + b->lreg.m * t.kmax;                 // longest rung = columns swept (|R| back, rest forward)
+            t_sweep = std::max(b->lreg.n_left + b->lreg.m * t.kmax, b->lreg.n_right);
+            rungs = t.kmax - t.kmin + 1;
+            b->stats.algorithmic_cells += (long long)q_len * ((long long)rungs * lad_cols +
+                                                              (long long)b->lreg.m * (t.kmin + t.kmax) * rungs / 2);
+        } else {
+            const nr::Task& t = b->tasks[i];
+            q_len = t.q_len;
+            t_len = t_sweep = t.t_len;
+            b->stats.algorithmic_cells += (long long)q_len * t_len;
+        }
+        long long m = (long long)b->sc.match * std::min(q_len, t_len);
+        if (m > kMaxScore || t_len > kMaxTlen)
             return fail(NR_ERR_TOO_LARGE,
                         "task %d (query %d x target %d) exceeds the packed range (score <= %d, target <= %d)", i,
-                        t.q_len, t.t_len, kMaxScore, kMaxTlen);
+                        q_len, t_len, kMaxScore, kMaxTlen);
         int R, ns;
-        bool multi;
-        stripe_shape(t.q_len, R, multi, ns);
-        shapeR[i] = R;
-        shapeM[i] = multi;
-        cost[i] = (long long)t.q_len * t.t_len;
-        b->stats.algorithmic_cells += cost[i];
-        b->stats.executed_cells += (long long)ns * 32 * R * t.t_len;
-        bucket_count[(multi ? kMaxR + 1 : 0) + R]++;
+        nr::stripe_shape(q_len, max_r, R, ns);
+        const int mi = ns > 1;
+        shapeM[i] = (uint8_t)mi;
+        n_multi += mi;
+        rmax[mi] = std::max(rmax[mi], R);
+        tmax[mi] = std::max(tmax[mi], t_sweep);
+        qmax[mi] = std::max(qmax[mi], ns * 32 * R);
+        rungs_max[mi] = std::max(rungs_max[mi], rungs);
+        cost[i] = (long long)ns * 32 * R * t_len;
+        b->stats.executed_cells += cost[i];
     }
+    // one launch per (single-stripe | multi-stripe) group, tasks in decreasing cost so the tail is short
     b->order.resize(n);
     b->buckets.clear();
-    std::vector<int> fill(2 * (kMaxR + 1), 0);
-    int off = 0;
-    std::vector<int> bucket_off(2 * (kMaxR + 1), 0);
-    for (int k = 0; k < 2 * (kMaxR + 1); ++k) { bucket_off[k] = off; off += bucket_count[k]; }
-    for (int i = 0; i < n; ++i) {
-        int k = (shapeM[i] ? kMaxR + 1 : 0) + shapeR[i];
-        b->order[bucket_off[k] + fill[k]++] = i;
+    {
+        int fill[2] = {0, n - n_multi};
+        for (int i = 0; i < n; ++i) b->order[fill[shapeM[i]]++] = i;
     }
     size_t scratch_total = 0;
-    // largest buckets first so their tails overlap with the small launches behind them
-    for (int k = 0; k < 2 * (kMaxR + 1); ++k) {
-        if (!bucket_count[k]) continue;
-        Bucket bk;
-        bk.multi = k > kMaxR;
-        bk.R = bk.multi ? k - (kMaxR + 1) : k;
-        bk.order_off = bucket_off[k];
-        bk.count = bucket_count[k];
+    for (int mi = 0; mi < 2; ++mi) {
+        Bucket bk = {};
+        bk.ladder = ladder;
+        bk.multi = mi == 1;
+        bk.R = rmax[mi];
+        bk.order_off = mi ? n - n_multi : 0;
+        bk.count = mi ? n_multi : n - n_multi;
+        if (!bk.count) continue;
         std::sort(b->order.begin() + bk.order_off, b->order.begin() + bk.order_off + bk.count,
                   [&](int x, int y) { return cost[x] != cost[y] ? cost[x] > cost[y] : x < y; });
-        int max_blocks = g_ctx.sm_count * 4;
-        bk.blocks = std::min(max_blocks, (bk.count + kWarpsPerBlock - 1) / kWarpsPerBlock);
-        bk.scratch_stride = 0;
-        bk.scratch_off = 0;
+        bk.blocks = std::min(g_ctx.sm_count * 4, (bk.count + kWarpsPerBlock - 1) / kWarpsPerBlock);
         if (bk.multi) {
-            int tmax = 0;
-            for (int j = 0; j < bk.count; ++j) tmax = std::max(tmax, b->tasks[b->order[bk.order_off + j]].t_len);
-            bk.scratch_stride = ((long long)tmax + 63) / 32 * 32;
+            bk.scratch_stride = ((long long)tmax[mi] + 63) / 32 * 32;
+            if (ladder) {
+                bk.b_stride = qmax[mi];
+                bk.tok_stride = rungs_max[mi];
+            }
             bk.scratch_off = scratch_total;
-            scratch_total += (size_t)bk.blocks * kWarpsPerBlock * 2 * (size_t)bk.scratch_stride;
+            scratch_total += (size_t)bk.blocks * kWarpsPerBlock *
+                             (size_t)(2 * bk.scratch_stride + bk.b_stride + 2 * bk.tok_stride);
         }
         b->buckets.push_back(bk);
     }
-    std::sort(b->buckets.begin(), b->buckets.end(), [&](const Bucket& x, const Bucket& y) {
-        return x.count > y.count;
-    });
     // device allocations + uploads
     const size_t pool_words = b->pool.words.size() + 4;
-    CUDA_TRY(cudaMalloc(&b->d_tasks, sizeof(nr::Task) * std::max(n, 1)));
+    const size_t n_out = std::max<size_t>(b->n_out, 1);
+    if (ladder) CUDA_TRY(cudaMalloc(&b->d_ltasks, sizeof(nr::LadderTask) * std::max(n, 1)));
+    else CUDA_TRY(cudaMalloc(&b->d_tasks, sizeof(nr::Task) * std::max(n, 1)));
     CUDA_TRY(cudaMalloc(&b->d_order, sizeof(int32_t) * std::max(n, 1)));
     CUDA_TRY(cudaMalloc(&b->d_pool, sizeof(uint32_t) * pool_words));
     CUDA_TRY(cudaMalloc(&b->d_counters, sizeof(int) * std::max<size_t>(b->buckets.size(), 1)));
-    CUDA_TRY(cudaMalloc(&b->d_out, sizeof(int4) * std::max(n, 1)));
+    CUDA_TRY(cudaMalloc(&b->d_out, sizeof(int4) * n_out));
     if (scratch_total) CUDA_TRY(cudaMalloc(&b->d_scratch, sizeof(int4) * scratch_total));
-    CUDA_TRY(cudaMallocHost(&b->h_out, sizeof(int4) * std::max(n, 1)));
+    CUDA_TRY(cudaMallocHost(&b->h_out, sizeof(int4) * n_out));
     cudaStream_t st = g_ctx.stream;
     CUDA_TRY(cudaMemsetAsync(b->d_pool, 0, sizeof(uint32_t) * pool_words, st));
+    CUDA_TRY(cudaMemsetAsync(b->d_out, 0, sizeof(int4) * n_out, st));
+    size_t task_bytes = 0;
     if (n) {
-        CUDA_TRY(cudaMemcpyAsync(b->d_tasks, b->tasks.data(), sizeof(nr::Task) * n, cudaMemcpyHostToDevice, st));
+        if (ladder) {
+            task_bytes = sizeof(nr::LadderTask) * n;
+            CUDA_TRY(cudaMemcpyAsync(b->d_ltasks, b->ltasks.data(), task_bytes, cudaMemcpyHostToDevice, st));
+        } else {
+            task_bytes = sizeof(nr::Task) * n;
+            CUDA_TRY(cudaMemcpyAsync(b->d_tasks, b->tasks.data(), task_bytes, cudaMemcpyHostToDevice, st));
+        }
         CUDA_TRY(cudaMemcpyAsync(b->d_order, b->order.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    }
+    if (!b->pool.words.empty())
         CUDA_TRY(cudaMemcpyAsync(b->d_pool, b->pool.words.data(), sizeof(uint32_t) * b->pool.words.size(),
                                  cudaMemcpyHostToDevice, st));
-    }
     CUDA_TRY(cudaStreamSynchronize(st));
-    b->stats.h2d_bytes = (int64_t)(sizeof(nr::Task) * n + sizeof(int32_t) * n +
-                                   sizeof(uint32_t) * b->pool.words.size());
-    b->stats.d2h_bytes = (int64_t)sizeof(int4) * n;
+    b->stats.h2d_bytes = (int64_t)(task_bytes + sizeof(int32_t) * n + sizeof(uint32_t) * b->pool.words.size());
+    b->stats.d2h_bytes = (int64_t)sizeof(int4) * (int64_t)b->n_out;
     return NR_OK;
 }
 
 int run_batch(nr_batch* b, cudaStream_t st) {
-    if (b->tasks.empty()) { b->ran = true; return NR_OK; }
-    nr::ScoreP32 k;
-    k.match = b->sc.match << 16;
-    k.mismatch_neg = -(b->sc.mismatch << 16);
-    k.qe1_neg = -((b->sc.gap_open1 + b->sc.gap_ext1) << 16);
-    k.e1_neg = -(b->sc.gap_ext1 << 16);
-    k.qe2_neg = -((b->sc.gap_open2 + b->sc.gap_ext2) << 16);
-    k.e2_neg = -(b->sc.gap_ext2 << 16);
+    b->run_stream = st;
+    if (b->buckets.empty()) { b->ran = true; return NR_OK; }
+    const nr::ScoreW k = score_words(b->sc);
     CUDA_TRY(cudaMemsetAsync(b->d_counters, 0, sizeof(int) * b->buckets.size(), st));
     int launches = 0;
     for (size_t i = 0; i < b->buckets.size(); ++i) {
         const Bucket& bk = b->buckets[i];
-        ExactKernel fn = pick_exact<kMinR>(bk.R, bk.multi);
-        if (!fn) return fail(NR_ERR_ARG, "no kernel for stripe height %d", bk.R);
-        size_t smem = exact_smem_bytes(bk.R);
-        CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxShared));
-        fn<<<bk.blocks, kWarpsPerBlock * 32, smem, st>>>(b->d_tasks, b->d_order + bk.order_off, bk.count, b->d_pool,
-                                                        k, b->d_counters + i,
-                                                        bk.multi ? b->d_scratch + bk.scratch_off : nullptr,
-                                                        bk.scratch_stride, b->d_out);
+        int4* scratch = bk.multi ? b->d_scratch + bk.scratch_off : nullptr;
+        if (bk.ladder) {
+            LadderKernel fn = bk.multi ? (LadderKernel)nr::ladder_kernel<true> : (LadderKernel)nr::ladder_kernel<false>;
+            const int stride = ladder_smem_int4(bk.R);
+            const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
+            CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          cudaSharedmemCarveoutMaxShared));
+            fn<<<bk.blocks, kWarpsPerBlock * 32, smem, st>>>(b->d_ltasks, b->d_order + bk.order_off, bk.count,
+                                                            b->d_pool, b->lreg, k, b->d_counters + i, stride, scratch,
+                                                            bk.scratch_stride, bk.b_stride, bk.tok_stride, b->d_out);
+        } else {
+            ExactKernel fn = bk.multi ? (ExactKernel)nr::exact_kernel<true> : (ExactKernel)nr::exact_kernel<false>;
+            const int stride = exact_smem_int4(bk.R);
+            const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
+            CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          cudaSharedmemCarveoutMaxShared));
+            fn<<<bk.blocks, kWarpsPerBlock * 32, smem, st>>>(b->d_tasks, b->d_order + bk.order_off, bk.count,
+                                                            b->d_pool, k, b->d_counters + i, stride, scratch,
+                                                            bk.scratch_stride, b->d_out);
+        }
         CUDA_TRY(cudaGetLastError());
         ++launches;
     }
@@ -315,10 +360,11 @@ int run_batch(nr_batch* b, cudaStream_t st) {
 
 int fetch_raw(nr_batch* b) {
     if (!b->ran) return fail(NR_ERR_ARG, "batch was not run");
-    const size_t n = b->tasks.size();
+    const size_t n = b->n_out;
     if (!n) return NR_OK;
-    CUDA_TRY(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(int4) * n, cudaMemcpyDeviceToHost, g_ctx.stream));
-    CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
+    cudaStream_t st = b->run_stream ? b->run_stream : g_ctx.stream;
+    CUDA_TRY(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(int4) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return NR_OK;
 }
 
@@ -373,6 +419,12 @@ int nr_device_info(int32_t* device, int32_t* sm_count, int32_t* clock_khz) {
     return NR_OK;
 }
 
+int nr_set_ladder_mode(int mode) {
+    if (mode != 0 && mode != 1) return fail(NR_ERR_ARG, "nr_set_ladder_mode: mode must be 0 or 1");
+    g_ladder_mode.store(mode);
+    return NR_OK;
+}
+
 int nr_limits(int32_t* max_score, int32_t* max_tlen) {
     if (max_score) *max_score = kMaxScore;
     if (max_tlen) *max_tlen = kMaxTlen;
@@ -382,6 +434,7 @@ int nr_limits(int32_t* max_score, int32_t* max_tlen) {
 void nr_batch_destroy(nr_batch_t* b) {
     if (!b) return;
     cudaFree(b->d_tasks);
+    cudaFree(b->d_ltasks);
     cudaFree(b->d_order);
     cudaFree(b->d_pool);
     cudaFree(b->d_counters);
@@ -491,6 +544,37 @@ nr_batch_t* nr_batch_create_round3(const nr_scoring_t* sc, const char* left, int
         nr_batch_destroy(b);
         return nullptr;
     }
+    b->n_out = (size_t)b->rung_off[n_reads];
+    if (g_ladder_mode.load() != 0) {
+        // shared sweeps (nr_kernels.cuh, ladder_kernel): the pool holds left + motif^khi once and reverse(right) once
+        b->ladder = true;
+        b->lreg.n_left = n_left;
+        b->lreg.n_right = n_right;
+        b->lreg.m = motif_len;
+        std::string fwd(left ? left : "", (size_t)n_left);
+        for (int u = 0; u < std::max(khi, 0); ++u) fwd.append(motif, (size_t)motif_len);
+        std::string rev(right ? right : "", (size_t)n_right);
+        std::reverse(rev.begin(), rev.end());
+        if (add_seq(b, fwd.data(), (int)fwd.size(), "ladder prefix", 0, &b->lreg.fwd_word) ||
+            add_seq(b, rev.data(), (int)rev.size(), "right anchor", 0, &b->lreg.rev_word)) {
+            nr_batch_destroy(b);
+            return nullptr;
+        }
+        for (int r = 0; r < n_reads; ++r) {
+            if (b->rung_off[r + 1] == b->rung_off[r]) continue;
+            if (core_len[r] < 0) { fail(NR_ERR_ARG, "core %d has negative length", r); nr_batch_destroy(b); return nullptr; }
+            if (core_len[r] == 0) continue;     // every rung scores 0: d_out is zero-filled
+            nr::LadderTask t = {};
+            if (add_seq(b, cores[r], core_len[r], "core", r, &t.q_word)) { nr_batch_destroy(b); return nullptr; }
+            t.q_len = core_len[r];
+            t.kmin = kmin[r];
+            t.kmax = kmax[r];
+            t.out_off = (int32_t)b->rung_off[r];
+            b->ltasks.push_back(t);
+        }
+        if (plan_batch(b)) { nr_batch_destroy(b); return nullptr; }
+        return b;
+    }
     // ladder templates left + motif*k + right, one per distinct k that any read uses (nanoRepeat_bam.py:478-479)
     std::vector<uint32_t> tpl_word;
     std::vector<uint8_t> used;
@@ -534,10 +618,10 @@ int nr_batch_run(nr_batch_t* b, void* stream) {
 }
 
 int nr_batch_fetch_alns(nr_batch_t* b, nr_aln_t* out) {
-    if (!b || (!out && !b->tasks.empty())) return fail(NR_ERR_ARG, "nr_batch_fetch_alns: NULL argument");
+    if (!b || (!out && b->n_out)) return fail(NR_ERR_ARG, "nr_batch_fetch_alns: NULL argument");
     int rc = fetch_raw(b);
     if (rc) return rc;
-    for (size_t i = 0; i < b->tasks.size(); ++i) {
+    for (size_t i = 0; i < b->n_out; ++i) {
         out[i].score = b->h_out[i].x;
         out[i].tstart = b->h_out[i].y;
         out[i].tend = b->h_out[i].z;

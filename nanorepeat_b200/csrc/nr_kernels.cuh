@@ -4,16 +4,27 @@
 // src/NanoRepeat/nanoRepeat_bam.py:362 (round 2) and :497 (round 3): an exact local alignment with
 // minimap2's map-ont two-piece affine gap model.  Contract = oracle/nr_oracle.c (score, tstart, tend).
 //
-// Exact kernel ("P32"): every DP value is ONE 32-bit integer holding (score << 16) | start_column.
-// Integer max on that word is the lexicographic max of (score, start), adding d << 16 adds d to the score and
-// keeps the start, so the whole recurrence is max/plus on packed words -- exactly the shape of Blackwell's DPX
-// instructions (VIADDMNMX = max(a + b, c), VIMNMX3 = max(a, b, c)); start tracking costs no instruction.
+// DP word ("W32"): every DP value is ONE 32-bit integer  w = score * 65536 - span,  span = number of target
+// columns the alignment has consumed so far (0 <= span < 65536), i.e. tstart = column - span.  Integer max on
+// that word is the lexicographic max of (score, -span) = (score, tstart), so the recurrence is plain max/plus on
+// packed words -- the shape of Blackwell's DPX instructions (VIADDMNMX = max(a + b, c), VIMNMX3 = max(a, b, c)).
+// A move that consumes a target column (diagonal, horizontal gap) subtracts 1 on top of its score; a fresh start
+// is the word 0, so the local-alignment floor is the free .RELU of VIMNMX3.  Per cell: 6 DPX-class instructions
+// (2 for H, 1 each for E1, E2, F1, F2) + 5 adds that issue on the other integer pipe.
 //
 // Mapping: one warp per task.  The query is cut into stripes of 32 * R rows; inside a stripe lane l owns R
 // consecutive rows whose H / E1 / E2 state lives in registers.  The warp sweeps the target column by column as
 // a skewed wavefront (lane l works on column step - l); the bottom row's H, F1, F2 move to lane l + 1 by warp
 // shuffle.  Substitution scores come from a per-warp query profile in shared memory (one LDS.128 per four rows,
-// off the integer pipe).  Between stripes the bottom row goes through an L2-resident scratch row.
+// off the integer pipes).  Between stripes the bottom row goes through an L2-resident scratch row.
+//
+// Ladder kernel (round 3): all rungs k of one read share their prefix L + motif^k and their suffix R, so the warp
+// does ONE backward sweep (reversed read x reversed R, final column kept in shared memory) and ONE forward sweep
+// over L + motif^kmax.  Whenever a lane finishes a junction column c_k = |L| + k*|motif| it joins its forward
+// state with the backward state row by row (three junction states: H, E1, E2 -- a gap may span the junction), and
+// a token (prefix best, junction best) travels down the lanes with the wavefront; the last lane combines it with
+// the R-only optimum and emits the rung's exact (score, tstart, tend).  Identical, bit for bit, to scoring every
+// rung as its own rectangle (tests/test_gpu_parity.py checks that against the oracle).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,153 +38,378 @@ struct Task {          // 16 bytes, one per (query, target) pair
     int32_t  t_len;
 };
 
-struct ScoreP32 {      // scoring constants already shifted into the score field (<< 16)
-    int match, mismatch_neg;   // +a << 16, -b << 16
-    int qe1_neg, e1_neg;       // -(q + e) << 16, -e << 16
-    int qe2_neg, e2_neg;
+struct LadderTask {    // 32 bytes, one per read of a round-3 region
+    uint32_t q_word;
+    int32_t  q_len;
+    int32_t  kmin, kmax;   // rungs of this read (kmax >= kmin >= 0)
+    int32_t  out_off;      // index of rung kmin in out[]
+    int32_t  pad[3];
 };
 
-constexpr int kPadScore = -(16384 << 16);   // substitution score of rows below the query's end
+struct LadderRegion {  // region constants of a ladder launch
+    uint32_t fwd_word;     // L + motif^K, K >= every kmax of the launch
+    uint32_t rev_word;     // reverse(R)
+    int32_t  n_left, n_right, m;
+};
+
+struct ScoreW {        // scoring constants as W32 increments
+    int sub_match, sub_mismatch;             // (a << 16) - 1, -(b << 16) - 1      (diagonal: one column consumed)
+    int h_open1, h_ext1, h_open2, h_ext2;    // horizontal gap: -((q + e) << 16) - 1, -(e << 16) - 1
+    int v_open1, v_ext1, v_open2, v_ext2;    // vertical gap:   -((q + e) << 16),     -(e << 16)
+    int refund1, refund2;                    // q << 16, q2 << 16: a gap that spans a junction pays its opening once
+};
+
+constexpr int kPadScore = -(16384 << 16);   // substitution score of rows below the query's end / void junction state
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kExact = 0, kBwd = 1, kFwd = 2;
+typedef unsigned long long u64;
 
-__device__ __forceinline__ int vmax3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
-__device__ __forceinline__ int vaddmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); }
+__device__ __forceinline__ int w_cap(int w) { return (w + 0xffff) & (int)0xffff0000; }   // score(w) << 16, any sign
 
-// One DP cell of the exact kernel.  hd: H(i-1, j-1); s: substitution score; e1/e2: E(i, j); f1/f2: F(i, j).
+// One DP cell.  hd: H(i-1, j-1); s: substitution increment; e1/e2: E(i, j); f1/f2: F(i, j).
 // On return h = H(i, j), e1/e2 = E(i, j+1), f1/f2 = F(i+1, j).
-__device__ __forceinline__ void cell_p32(int hd, int s, int fresh, const ScoreP32& sc,
-                                         int& h, int& e1, int& e2, int& f1, int& f2) {
-    int t = vaddmax(hd, s, e1);          // max(hd + s, E1)
-    t = vmax3(t, e2, fresh);             // ... E2, fresh start (0, j)
-    h = vmax3(t, f1, f2);                // vertical gaps last: they carry the row-to-row dependency
-    e1 = vaddmax(h, sc.qe1_neg, e1 + sc.e1_neg);
-    e2 = vaddmax(h, sc.qe2_neg, e2 + sc.e2_neg);
-    f1 = vaddmax(h, sc.qe1_neg, f1 + sc.e1_neg);
-    f2 = vaddmax(h, sc.qe2_neg, f2 + sc.e2_neg);
+__device__ __forceinline__ void cell_w32(int hd, int s, const ScoreW& sc, int& h, int& e1, int& e2, int& f1, int& f2) {
+    const int t = __vimax3_s32(hd + s, e1, e2);
+    h = __vimax3_s32_relu(t, f1, f2);        // vertical gaps last: they carry the row-to-row dependency
+    e1 = __viaddmax_s32(h, sc.h_open1, e1 + sc.h_ext1);
+    e2 = __viaddmax_s32(h, sc.h_open2, e2 + sc.h_ext2);
+    f1 = __viaddmax_s32(h, sc.v_open1, f1 + sc.v_ext1);
+    f2 = __viaddmax_s32(h, sc.v_open2, f2 + sc.v_ext2);
 }
 
-// Per-task result before the final warp reduction: (score<<16|start) and the column it was found in.
-struct Best { int v; int j; };
+// Junction candidate: forward word wf (score_f, span) joined with backward word wb (score_b, ext).
+// (bhi, blo) keeps the lexicographic best of (score_f + score_b, -ext, -span).
+__device__ __forceinline__ void jcand(int wf, int wb, int& bhi, int& blo) {
+    const int sfs = w_cap(wf);
+    const int klo = wf - sfs;      // -span
+    const int khi = sfs + wb;      // (score_f + score_b) << 16 - ext
+    if (khi > bhi || (khi == bhi && klo > blo)) { bhi = khi; blo = klo; }
+}
 
-// Lexicographic order of the contract: score desc, tend asc, tstart desc -> one 64-bit key, larger is better.
-__device__ __forceinline__ unsigned long long best_key(int v, int j) {
-    unsigned score = (unsigned)(v >> 16) & 0xffffu;       // scores here are >= 0
-    unsigned start = (unsigned)v & 0xffffu;
-    return ((unsigned long long)score << 32) | ((unsigned long long)(0xffffu - (unsigned)j) << 16) | start;
+// (best word, its column) -> 64-bit key ordered like the contract: score desc, tend asc, tstart desc.
+__device__ __forceinline__ u64 key_of_best(int w, int j) {
+    if (w <= 0) return 0ull;
+    const unsigned cap = (unsigned)w_cap(w);
+    const unsigned span = cap - (unsigned)w;
+    return ((u64)(cap >> 16) << 32) | ((u64)(0xffffu - (unsigned)j) << 16) | (u64)(0xffffu - span);
+}
+
+// junction best (khi, klo) -> key (score, 0xffff - ext, 0xffff - span)
+__device__ __forceinline__ u64 key_of_junction(int khi, int klo) {
+    if (khi <= 0) return 0ull;
+    const unsigned cap = (unsigned)w_cap(khi);
+    const unsigned ext = cap - (unsigned)khi;
+    return ((u64)(cap >> 16) << 32) | ((u64)(0xffffu - ext) << 16) | (u64)(0xffffu - (unsigned)(-klo));
+}
+
+__device__ __forceinline__ u64 shfl_up64(u64 v) {
+    unsigned lo = __shfl_up_sync(kFull, (unsigned)v, 1);
+    unsigned hi = __shfl_up_sync(kFull, (unsigned)(v >> 32), 1);
+    return ((u64)hi << 32) | lo;
+}
+
+__device__ __forceinline__ u64 warp_max64(u64 key) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        u64 other = __shfl_xor_sync(kFull, key, o);
+        key = other > key ? other : key;
+    }
+    return key;
+}
+
+// Rung k's record from its three alignment classes: P = ends at or before the junction column c, J = crosses it,
+// R-only = lies inside the right flank (same for every rung of the read).
+__device__ __forceinline__ int4 finalize_rung(u64 P, u64 J, int c, int r_score, int r_end, int r_start) {
+    int bs = 0, be = 0, bst = 0;
+    if (P) {
+        const int s = (int)(P >> 32), j = 0xffff - (int)((P >> 16) & 0xffffu), span = 0xffff - (int)(P & 0xffffu);
+        bs = s; be = j; bst = j - span;
+    }
+    if (J) {
+        const int s = (int)(J >> 32), e = c + 0xffff - (int)((J >> 16) & 0xffffu), st = c - (0xffff - (int)(J & 0xffffu));
+        if (s > bs || (s == bs && (e < be || (e == be && st > bst)))) { bs = s; be = e; bst = st; }
+    }
+    if (r_score > 0) {
+        const int e = c + r_end, st = c + r_start;
+        if (r_score > bs || (r_score == bs && (e < be || (e == be && st > bst)))) { bs = r_score; be = e; bst = st; }
+    }
+    return make_int4(bs, bst, be, 0);
 }
 
 template <int R>
 struct StripeCfg {
     static constexpr int CH = (R + 3) / 4;             // LDS.128 per column step
-    static constexpr int PROF_INT4 = 4 * CH * 32;      // int4 entries per warp
+    static constexpr int PROF_INT4 = 4 * CH * 32;      // int4 entries per warp: query profile
+    static constexpr int BVEC_INT4 = R * 32;           // int4 entries per warp: backward junction vectors
 };
 
-// Build the stripe's query profile: prof[(c * CH + chunk) * 32 + lane].{x,y,z,w} = score of rows 4*chunk..+3
-// of this lane against target code c.
+// Build the stripe's query profile: prof[(c * CH + chunk) * 32 + lane].{x,y,z,w} = substitution increment of rows
+// 4*chunk..+3 of this lane against target code c.  reverse: the stripe's rows index the reversed query.
 template <int R>
 __device__ __forceinline__ void build_profile(int4* prof, const uint32_t* __restrict__ qwords, int q_len,
-                                              int row0, int lane, const ScoreP32& sc) {
+                                              int row0, int lane, const ScoreW& sc, bool reverse) {
     constexpr int CH = StripeCfg<R>::CH;
     int* p = reinterpret_cast<int*>(prof);
 #pragma unroll
     for (int r = 0; r < 4 * CH; ++r) {
-        int i = row0 + r;
+        const int i = row0 + r;
         int code = 4;
-        if (r < R && i < q_len) code = (qwords[i >> 4] >> (2 * (i & 15))) & 3;
+        if (r < R && i < q_len) {
+            const int qi = reverse ? q_len - 1 - i : i;
+            code = (qwords[qi >> 4] >> (2 * (qi & 15))) & 3;
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            int v = (code == 4) ? kPadScore : (code == c ? sc.match : sc.mismatch_neg);
+            const int v = (code == 4) ? kPadScore : (code == c ? sc.sub_match : sc.sub_mismatch);
             p[((c * CH + (r >> 2)) * 32 + lane) * 4 + (r & 3)] = v;
         }
     }
 }
 
-// One stripe of one task.  MULTI = false: single-stripe task (no boundary traffic at all).
-// MULTI = true: `top` says the stripe has a predecessor (read bnd_in), `bot` says it has a successor
-// (lane 31 writes bnd_out).  Boundary entry for column j: (H(last row, j), F1(next row, j), F2(next row, j)).
-template <int R, bool MULTI>
-__device__ __forceinline__ Best run_stripe(const int4* prof, const uint32_t* __restrict__ twords, int t_len,
-                                           int lane, const ScoreP32& sc, bool top, bool bot,
-                                           const int4* bnd_in, int4* bnd_out) {
-    constexpr int CH = StripeCfg<R>::CH;
+// Position (int4 index inside the forward-layout backward-vector array) of forward cell row idx0.
+template <int R>
+__device__ __forceinline__ int bvec_pos(int idx0) {
+    const int stripe = idx0 / (32 * R), in = idx0 - stripe * (32 * R);
+    return stripe * (32 * R) + (in % R) * 32 + in / R;
+}
+
+// One stripe of one sweep.
+//   kExact: plain task, running best per the contract.
+//   kBwd:   reversed read x reversed right flank; best per the R-only ordering; the final column's junction
+//           state (H, E1 + refund1, E2 + refund2) is written to bdst in the forward layout.
+//   kFwd:   read x L + motif^kmax with junction tokens (see the file header).
+// MULTI: the task has several stripes; `top` = this stripe has a predecessor (read bnd_in), `bot` = it has a
+// successor (lane 31 writes bnd_out).  Boundary entry for column j: (H(last row, j), F1(next row, j), F2(next row, j)).
+template <int R, int MODE, bool MULTI>
+struct Sweep {
+    // inputs
+    const int4* prof;
+    const uint32_t* twords;
+    int t_len, lane;
+    bool top, bot;
+    const int4* bnd_in;
+    int4* bnd_out;
+    // kBwd
+    int4* bdst;
+    int q_len, brow0;
+    // kFwd
+    const int4* bsm;
+    const ulonglong2* tok_in;
+    ulonglong2* tok_out;
+    int4* out;
+    int jnext, m, kcnt;
+    int r_score, r_end, r_start;
+    // state
     int H[R], E1[R], E2[R];
+    int hup_prev, h_out, f1_out, f2_out;
+    int best, bestcap, bestj, best_rs;
+    uint32_t tw, tw_next;
+    int4 bcur, bnxt;
+    u64 tokP, tokJ;
+
+    __device__ __forceinline__ void init(const ScoreW& sc) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) { H[r] = 0; E1[r] = sc.qe1_neg; E2[r] = sc.qe2_neg; }
-    int hup_prev = 0;                       // H(row0 - 1, j - 1); column 0 is (0, start 0)
-    int h_out = 0, f1_out = 0, f2_out = 0;  // bottom-row outputs of the previous step
-    int best = 0, bestcap = 0xffff, bestj = 0;
-    uint32_t tw = 0, tw_next = twords[0];
-    int4 bcur = make_int4(0, 0, 0, 0), bnxt = make_int4(0, 0, 0, 0);
-    if (MULTI && top) bnxt = __ldcg(&bnd_in[lane < t_len ? lane : t_len - 1]);
-    const int nsteps = t_len + 31;
-    for (int step = 0; step < nsteps; ++step) {
-        const int jj = step - lane;         // 0-based target column of this lane
+        for (int r = 0; r < R; ++r) { H[r] = 0; E1[r] = sc.h_open1; E2[r] = sc.h_open2; }
+        hup_prev = 0;                       // H(row0 - 1, j - 1); column 0 is the word 0
+        h_out = 0; f1_out = 0; f2_out = 0;  // bottom-row outputs of the previous step
+        best = 0; bestcap = 0; bestj = 0; best_rs = 0x7fffffff;
+        tw = 0; tw_next = twords[0];
+        bcur = make_int4(0, 0, 0, 0); bnxt = make_int4(0, 0, 0, 0);
+        if (MULTI && top) bnxt = __ldcg(&bnd_in[lane < t_len ? lane : t_len - 1]);
+        tokP = 0; tokJ = 0;
+    }
+
+    template <bool JUNC>
+    __device__ __forceinline__ int cells(const int4* pp, int hd, int& f1, int& f2, const ScoreW& sc, int& jhi, int& jlo) {
+        constexpr int CH = StripeCfg<R>::CH;
+        int cm = 0;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int4 sv = pp[c * 32];
+            const int s4[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = 4 * c + u;
+                if (r < R) {
+                    const int hleft = H[r];
+                    const int e1pre = E1[r], e2pre = E2[r];
+                    int h;
+                    cell_w32(hd, s4[u], sc, h, E1[r], E2[r], f1, f2);
+                    if (JUNC) {
+                        const int4 b = bsm[r * 32 + lane];
+                        jcand(h, b.x, jhi, jlo);
+                        jcand(e1pre, b.y, jhi, jlo);
+                        jcand(e2pre, b.z, jhi, jlo);
+                    }
+                    hd = hleft;
+                    H[r] = h;
+                    if (r & 1) cm = __vimax3_s32(cm, h, H[r - 1]);
+                    else if (r == R - 1) cm = max(cm, h);
+                }
+            }
+        }
+        return cm;
+    }
+
+    // ZONE (kFwd only): some lane may be at a junction column, tokens are moving.
+    template <bool ZONE>
+    __device__ __forceinline__ void step(int st, const ScoreW& sc) {
+        constexpr int CH = StripeCfg<R>::CH;
+        const int jj = st - lane;           // 0-based target column of this lane
         int hup = __shfl_up_sync(kFull, h_out, 1);
         int f1 = __shfl_up_sync(kFull, f1_out, 1);
         int f2 = __shfl_up_sync(kFull, f2_out, 1);
+        u64 tP = 0, tJ = 0;
+        if (MODE == kFwd && ZONE) { tP = shfl_up64(tokP); tJ = shfl_up64(tokJ); }
         int bh = 0, bf1 = 0, bf2 = 0;
         if (MULTI && top) {                 // uniform branch
-            if ((step & 31) == 0) {
+            if ((st & 31) == 0) {
                 bcur = bnxt;
-                int nj = step + 32 + lane;
+                const int nj = st + 32 + lane;
                 bnxt = __ldcg(&bnd_in[nj < t_len ? nj : t_len - 1]);
             }
-            bh = __shfl_sync(kFull, bcur.x, step & 31);
-            bf1 = __shfl_sync(kFull, bcur.y, step & 31);
-            bf2 = __shfl_sync(kFull, bcur.z, step & 31);
+            bh = __shfl_sync(kFull, bcur.x, st & 31);
+            bf1 = __shfl_sync(kFull, bcur.y, st & 31);
+            bf2 = __shfl_sync(kFull, bcur.z, st & 31);
         }
         if (jj >= 0 && jj < t_len) {
-            const int fresh = jj + 1;       // (score 0, start = j): an alignment that starts after column j
             if (lane == 0) {
                 if (MULTI && top) { hup = bh; f1 = bf1; f2 = bf2; }
-                else { hup = fresh; f1 = fresh + sc.qe1_neg; f2 = fresh + sc.qe2_neg; }
+                else { hup = 0; f1 = sc.v_open1; f2 = sc.v_open2; }
             }
             if ((jj & 15) == 0) { tw = tw_next; tw_next = twords[(jj >> 4) + 1]; }
             const int tb = tw & 3;
             tw >>= 2;
             const int4* pp = prof + tb * (CH * 32) + lane;
-            int hd = hup_prev;
+            const int hd = hup_prev;
             hup_prev = hup;
-            int cm = 0;
+            const bool last_col = (MODE == kBwd) && jj == t_len - 1;
+            if (MODE == kBwd) {
+                if (last_col) {             // E(i', n_right): the state entering the last column
 #pragma unroll
-            for (int c = 0; c < CH; ++c) {
-                const int4 sv = pp[c * 32];
-                const int s4[4] = {sv.x, sv.y, sv.z, sv.w};
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int r = 4 * c + u;
-                    if (r < R) {
-                        int h;
-                        const int hleft = H[r];
-                        cell_p32(hd, s4[u], fresh, sc, h, E1[r], E2[r], f1, f2);
-                        hd = hleft;
-                        H[r] = h;
-                        if (r & 1) cm = vmax3(cm, h, H[r - 1]);
-                        else if (r == R - 1) cm = max(cm, h);
+                    for (int r = 0; r < R; ++r) {
+                        const int idx0 = q_len - 2 - (brow0 + r);
+                        if (idx0 >= 0) {
+                            int* d = reinterpret_cast<int*>(&bdst[bvec_pos<R>(idx0)]);
+                            d[1] = E1[r] + sc.refund1;
+                            d[2] = E2[r] + sc.refund2;
+                        }
                     }
                 }
             }
+            int cm, jhi = 0, jlo = 0;
+            bool junc = false;
+            if (MODE == kFwd && ZONE) junc = (jj + 1 == jnext);
+            if (MODE == kFwd && ZONE && junc) cm = cells<true>(pp, hd, f1, f2, sc, jhi, jlo);
+            else cm = cells<false>(pp, hd, f1, f2, sc, jhi, jlo);
             h_out = H[R - 1]; f1_out = f1; f2_out = f2;
-            if (cm > bestcap) { best = cm; bestcap = cm | 0xffff; bestj = fresh; }
+            if (MODE == kBwd) {
+                // R-only ordering in forward coordinates: score desc, end asc (= reversed start desc), start desc
+                // (= reversed end asc: keep the earlier column on a full tie)
+                const int cap = w_cap(cm);
+                const int rs = jj + 1 + cm - cap;          // reversed start of the column's best cell
+                if (cap > bestcap || (cap == bestcap && cap > 0 && rs > best_rs)) { bestcap = cap; best_rs = rs; bestj = jj + 1; }
+                if (last_col) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int idx0 = q_len - 2 - (brow0 + r);
+                        if (idx0 >= 0) reinterpret_cast<int*>(&bdst[bvec_pos<R>(idx0)])[0] = H[r];
+                    }
+                }
+            } else {
+                if (cm > bestcap) { best = cm; bestcap = w_cap(cm); bestj = jj + 1; }
+            }
+            if (MODE == kFwd && ZONE && junc) {
+                if (lane == 0) {
+                    if (MULTI && top) { const ulonglong2 t = __ldcg(&tok_in[kcnt]); tP = t.x; tJ = t.y; }
+                    else { tP = 0; tJ = 0; }
+                }
+                const u64 myP = key_of_best(best, bestj), myJ = key_of_junction(jhi, jlo);
+                tokP = myP > tP ? myP : tP;
+                tokJ = myJ > tJ ? myJ : tJ;
+                if (lane == 31) {
+                    if (MULTI && bot) __stcg(&tok_out[kcnt], make_ulonglong2(tokP, tokJ));
+                    else out[kcnt] = finalize_rung(tokP, tokJ, jj + 1, r_score, r_end, r_start);
+                }
+                jnext += m;
+                ++kcnt;
+            }
             if (MULTI && bot && lane == 31) __stcg(&bnd_out[jj], make_int4(h_out, f1_out, f2_out, 0));
         }
     }
-    Best b; b.v = best; b.j = bestj;
-    return b;
+
+    __device__ __forceinline__ void run(const ScoreW& sc, int zone_start) {
+        const int nsteps = t_len + 31;
+        int st = 0;
+        if (MODE == kFwd) {
+            for (; st < zone_start && st < nsteps; ++st) step<false>(st, sc);
+            for (; st < nsteps; ++st) step<true>(st, sc);
+        } else {
+            for (; st < nsteps; ++st) step<false>(st, sc);
+        }
+    }
+};
+
+constexpr int kMinR = 4;
+constexpr int kMaxRExact = 16;    // single-stripe tasks up to 512 rows
+constexpr int kMaxRLadder = 12;   // 384 rows: profile + junction vectors stay within 12 KB of shared memory per warp
+
+// Stripe height for a query: single stripe when it fits max_r rows per lane, else the fewest equal stripes.
+__host__ __device__ __forceinline__ void stripe_shape(int q_len, int max_r, int& R, int& n_stripes) {
+    if (q_len <= 32 * max_r) {
+        n_stripes = 1;
+        R = (q_len + 31) / 32;
+        if (R < kMinR) R = kMinR;
+    } else {
+        n_stripes = (q_len + 32 * max_r - 1) / (32 * max_r);
+        R = (q_len + 32 * n_stripes - 1) / (32 * n_stripes);
+    }
 }
 
-// Exact (score, tstart, tend) kernel.  Persistent: every warp pulls task indices from *counter.
-// order[] lists the tasks of this launch (host sorts them by decreasing cost); out[] is indexed by task id.
-// scratch: MULTI only; per warp 2 rows of scratch_stride int4.
 template <int R, bool MULTI>
+__device__ __forceinline__ u64 exact_task(const Task& tk, const uint32_t* __restrict__ pool, const ScoreW& sc,
+                                          int4* prof, int lane, int n_stripes, int4* bnd_a, int4* bnd_b) {
+    const uint32_t* qwords = pool + tk.q_word;
+    const int rows_per_stripe = 32 * R;
+    u64 key = 0;
+    for (int s = 0; s < n_stripes; ++s) {
+        __syncwarp();
+        build_profile<R>(prof, qwords, tk.q_len, s * rows_per_stripe + lane * R, lane, sc, false);
+        __syncwarp();
+        Sweep<R, kExact, MULTI> sw;
+        sw.prof = prof; sw.twords = pool + tk.t_word; sw.t_len = tk.t_len; sw.lane = lane;
+        sw.top = s > 0; sw.bot = s + 1 < n_stripes;
+        sw.bnd_in = (s & 1) ? bnd_a : bnd_b; sw.bnd_out = (s & 1) ? bnd_b : bnd_a;
+        sw.init(sc);
+        sw.run(sc, 0);
+        const u64 k = key_of_best(sw.best, sw.bestj);
+        key = k > key ? k : key;
+    }
+    return key;
+}
+
+template <int R, bool MULTI>
+__device__ __forceinline__ u64 exact_dispatch(int r, const Task& tk, const uint32_t* __restrict__ pool,
+                                              const ScoreW& sc, int4* prof, int lane, int n_stripes, int4* bnd_a,
+                                              int4* bnd_b) {
+    if (r == R) return exact_task<R, MULTI>(tk, pool, sc, prof, lane, n_stripes, bnd_a, bnd_b);
+    if constexpr (R < kMaxRExact) return exact_dispatch<R + 1, MULTI>(r, tk, pool, sc, prof, lane, n_stripes, bnd_a, bnd_b);
+    return 0ull;
+}
+
+// Exact (score, tstart, tend) kernel.  Persistent: every warp pulls task indices from *counter; the stripe
+// height is picked per task (warp-uniform dispatch), so one launch covers a whole batch.
+// order[] lists the tasks of this launch (host sorts them by decreasing cost); out[] is indexed by task id.
+// smem_stride: int4 of shared memory per warp.  scratch: MULTI only; per warp 2 rows of scratch_stride int4.
+template <bool MULTI>
 __global__ void __launch_bounds__(128, 4)
 exact_kernel(const Task* __restrict__ tasks, const int32_t* __restrict__ order, int n_order,
-             const uint32_t* __restrict__ pool, ScoreP32 sc, int* counter,
+             const uint32_t* __restrict__ pool, ScoreW sc, int* counter, int smem_stride,
              int4* scratch, long long scratch_stride, int4* out) {
     extern __shared__ int4 smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    int4* prof = smem + warp * StripeCfg<R>::PROF_INT4;
+    int4* prof = smem + warp * smem_stride;
     const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     int4* bnd_a = MULTI ? scratch + gwarp * 2 * scratch_stride : nullptr;
     int4* bnd_b = MULTI ? bnd_a + scratch_stride : nullptr;
@@ -184,32 +420,132 @@ exact_kernel(const Task* __restrict__ tasks, const int32_t* __restrict__ order, 
         if (oi >= n_order) break;
         const int tid = order[oi];
         const Task tk = tasks[tid];
-        const uint32_t* qwords = pool + tk.q_word;
-        const uint32_t* twords = pool + tk.t_word;
-        unsigned long long key = 0;
-        const int rows_per_stripe = 32 * R;
-        const int n_stripes = MULTI ? (tk.q_len + rows_per_stripe - 1) / rows_per_stripe : 1;
+        int R, n_stripes;
+        stripe_shape(tk.q_len, kMaxRExact, R, n_stripes);
+        u64 key = exact_dispatch<kMinR, MULTI>(R, tk, pool, sc, prof, lane, n_stripes, bnd_a, bnd_b);
+        key = warp_max64(key);
+        if (lane == 0) out[tid] = finalize_rung(key, 0ull, 0, 0, 0, 0);
+    }
+}
+
+template <int R, bool MULTI>
+__device__ __forceinline__ void ladder_task(const LadderTask& tk, const uint32_t* __restrict__ pool,
+                                            const LadderRegion& reg, const ScoreW& sc, int4* prof, int lane,
+                                            int n_stripes, int4* bnd_a, int4* bnd_b, int4* bglob, ulonglong2* tok_a,
+                                            ulonglong2* tok_b, int4* out) {
+    int4* bsm = prof + StripeCfg<R>::PROF_INT4;
+    const int rows_per_stripe = 32 * R;
+    const uint32_t* qwords = pool + tk.q_word;
+    const int q_len = tk.q_len;
+    int4* bdst = MULTI ? bglob : bsm;
+    // junction vectors: corner i (1-based) lives at forward cell row idx0 = i - 1.  Defaults: right part empty
+    // (H = 0, no gap state) for corners inside the read, void below it; the backward sweep overwrites idx0 <= q-2.
+    __syncwarp();
+    for (int s = 0; s < n_stripes; ++s)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int idx0 = s * rows_per_stripe + lane * R + r;
+            bdst[s * rows_per_stripe + r * 32 + lane] =
+                idx0 < q_len ? make_int4(0, kPadScore, kPadScore, 0) : make_int4(kPadScore, kPadScore, kPadScore, 0);
+        }
+    __syncwarp();
+    // ---- backward sweep: reversed read x reversed right flank ----
+    u64 rkey = 0;
+    if (reg.n_right > 0) {
         for (int s = 0; s < n_stripes; ++s) {
             __syncwarp();
-            build_profile<R>(prof, qwords, tk.q_len, s * rows_per_stripe + lane * R, lane, sc);
+            build_profile<R>(prof, qwords, q_len, s * rows_per_stripe + lane * R, lane, sc, true);
             __syncwarp();
-            const bool top = s > 0, bot = s + 1 < n_stripes;
-            Best b = run_stripe<R, MULTI>(prof, twords, tk.t_len, lane, sc, top, bot,
-                                          (s & 1) ? bnd_a : bnd_b, (s & 1) ? bnd_b : bnd_a);
-            unsigned long long k = (b.v >> 16) > 0 ? best_key(b.v, b.j) : 0ull;
-            key = k > key ? k : key;
+            Sweep<R, kBwd, MULTI> sw;
+            sw.prof = prof; sw.twords = pool + reg.rev_word; sw.t_len = reg.n_right; sw.lane = lane;
+            sw.top = s > 0; sw.bot = s + 1 < n_stripes;
+            sw.bnd_in = (s & 1) ? bnd_a : bnd_b; sw.bnd_out = (s & 1) ? bnd_b : bnd_a;
+            sw.bdst = bdst; sw.q_len = q_len; sw.brow0 = s * rows_per_stripe + lane * R;
+            sw.init(sc);
+            sw.run(sc, 0);
+            u64 k = 0;
+            if (sw.bestcap > 0)
+                k = ((u64)((unsigned)sw.bestcap >> 16) << 32) | ((u64)(unsigned)sw.best_rs << 16) |
+                    (u64)(0xffffu - (unsigned)sw.bestj);
+            rkey = k > rkey ? k : rkey;
         }
+        rkey = warp_max64(rkey);
+    }
+    int r_score = 0, r_end = 0, r_start = 0;
+    if (rkey) {
+        r_score = (int)(rkey >> 32);
+        r_end = reg.n_right - (int)((rkey >> 16) & 0xffffu);             // forward end inside R (exclusive)
+        r_start = reg.n_right - (0xffff - (int)(rkey & 0xffffu));        // forward start inside R
+    }
+    // ---- forward sweep over L + motif^kmax with junction tokens ----
+    const int c_first = reg.n_left + reg.m * tk.kmin;
+    const int t_len = reg.n_left + reg.m * tk.kmax;
+    int4* outp = out + tk.out_off;
+    if (t_len > 0) {
+        for (int s = 0; s < n_stripes; ++s) {
+            __syncwarp();
+            build_profile<R>(prof, qwords, q_len, s * rows_per_stripe + lane * R, lane, sc, false);
+            if (MULTI) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            unsigned long long other = __shfl_xor_sync(kFull, key, o);
-            key = other > key ? other : key;
+                for (int r = 0; r < R; ++r) bsm[r * 32 + lane] = __ldcg(&bglob[s * rows_per_stripe + r * 32 + lane]);
+            }
+            __syncwarp();
+            Sweep<R, kFwd, MULTI> sw;
+            sw.prof = prof; sw.twords = pool + reg.fwd_word; sw.t_len = t_len; sw.lane = lane;
+            sw.top = s > 0; sw.bot = s + 1 < n_stripes;
+            sw.bnd_in = (s & 1) ? bnd_a : bnd_b; sw.bnd_out = (s & 1) ? bnd_b : bnd_a;
+            sw.bsm = bsm;
+            sw.tok_in = (s & 1) ? tok_a : tok_b; sw.tok_out = (s & 1) ? tok_b : tok_a;
+            sw.out = outp;
+            sw.m = reg.m;
+            sw.jnext = c_first > 0 ? c_first : reg.m;     // a junction at column 0 has no forward part
+            sw.kcnt = c_first > 0 ? 0 : 1;
+            sw.r_score = r_score; sw.r_end = r_end; sw.r_start = r_start;
+            sw.init(sc);
+            sw.run(sc, sw.jnext - 1);
         }
-        if (lane == 0) {
-            int score = (int)(key >> 32);
-            int4 r = make_int4(0, 0, 0, 0);
-            if (score > 0) { r.x = score; r.y = (int)(key & 0xffffu); r.z = 0xffff - (int)((key >> 16) & 0xffffu); }
-            out[tid] = r;
-        }
+    }
+    if (c_first == 0 && lane == 0) outp[0] = finalize_rung(0ull, 0ull, 0, r_score, r_end, r_start);
+}
+
+template <int R, bool MULTI>
+__device__ __forceinline__ void ladder_dispatch(int r, const LadderTask& tk, const uint32_t* __restrict__ pool,
+                                                const LadderRegion& reg, const ScoreW& sc, int4* prof, int lane,
+                                                int n_stripes, int4* bnd_a, int4* bnd_b, int4* bglob,
+                                                ulonglong2* tok_a, ulonglong2* tok_b, int4* out) {
+    if (r == R) { ladder_task<R, MULTI>(tk, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out); return; }
+    if constexpr (R < kMaxRLadder)
+        ladder_dispatch<R + 1, MULTI>(r, tk, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out);
+}
+
+// Round-3 ladder kernel: one warp per read, all rungs kmin..kmax from one backward and one forward sweep.
+// scratch (MULTI only), per warp: 2 boundary rows of bnd_stride int4, b_stride int4 of backward vectors,
+// 2 token rows of tok_stride ulonglong2.
+template <bool MULTI>
+__global__ void __launch_bounds__(128, 4)
+ladder_kernel(const LadderTask* __restrict__ tasks, const int32_t* __restrict__ order, int n_order,
+              const uint32_t* __restrict__ pool, LadderRegion reg, ScoreW sc, int* counter, int smem_stride,
+              int4* scratch, long long bnd_stride, long long b_stride, long long tok_stride, int4* out) {
+    extern __shared__ int4 smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    int4* prof = smem + warp * smem_stride;
+    const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    const long long per_warp = 2 * bnd_stride + b_stride + 2 * tok_stride;
+    int4* bnd_a = MULTI ? scratch + gwarp * per_warp : nullptr;
+    int4* bnd_b = MULTI ? bnd_a + bnd_stride : nullptr;
+    int4* bglob = MULTI ? bnd_b + bnd_stride : nullptr;
+    ulonglong2* tok_a = MULTI ? reinterpret_cast<ulonglong2*>(bglob + b_stride) : nullptr;
+    ulonglong2* tok_b = MULTI ? tok_a + tok_stride : nullptr;
+    for (;;) {
+        int oi = 0;
+        if (lane == 0) oi = atomicAdd(counter, 1);
+        oi = __shfl_sync(kFull, oi, 0);
+        if (oi >= n_order) break;
+        const LadderTask tk = tasks[order[oi]];
+        int R, n_stripes;
+        stripe_shape(tk.q_len, kMaxRLadder, R, n_stripes);
+        ladder_dispatch<kMinR, MULTI>(R, tk, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out);
     }
 }
 

@@ -55,6 +55,7 @@ SYMBOLS = {
     "nr_last_error": (ctypes.c_char_p, []),
     "nr_device_info": (ctypes.c_int, [_i32p, _i32p, _i32p]),
     "nr_limits": (ctypes.c_int, [_i32p, _i32p]),
+    "nr_set_ladder_mode": (ctypes.c_int, [ctypes.c_int]),
     "nr_score_tasks": (ctypes.c_int, [_scp, ctypes.c_int32, _cpp, _i32p, _cpp, _i32p, ctypes.c_void_p]),
     "nr_round2_region": (ctypes.c_int, [_scp, ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32,
                                         ctypes.c_int32, ctypes.c_int32, _cpp, _i32p, ctypes.c_void_p]),
@@ -113,6 +114,12 @@ def device_info():
     d, s, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
     _check(lib().nr_device_info(ctypes.byref(d), ctypes.byref(s), ctypes.byref(c)))
     return dict(device=d.value, sm_count=s.value, clock_khz=c.value)
+
+
+def set_ladder_mode(mode):
+    """1 (default): round 3 shares one backward + one forward sweep across a read's ladder; 0: every rung is its
+    own full rectangle.  Same results either way."""
+    _check(lib().nr_set_ladder_mode(int(mode)))
 
 
 def last_stats():

@@ -152,6 +152,69 @@ def test_round3_rungs_match_oracle(engine, oracle):
             assert bool(rungs[i]["ends_in_right"]) == (a["score"] > 0 and (nl + m * k + nr_) - a["tend"] < nr_)
 
 
+def _ladder_case(rng, n_left, n_right, m, n_reads, kspan, qmode):
+    left, right = _rand_seq(rng, n_left), _rand_seq(rng, n_right)
+    motif = _rand_seq(rng, m)
+    cores, kmin, kmax = [], [], []
+    for _ in range(n_reads):
+        k_true = rng.randint(0, kspan)
+        lf = left[-rng.randint(0, min(n_left, 60)):] if n_left and rng.random() < 0.9 else ""
+        rf = right[:rng.randint(0, min(n_right, 60))] if n_right and rng.random() < 0.9 else ""
+        if qmode == "long":
+            k_true += 200
+        core = _mutate(rng, lf + motif * k_true + rf, rng.choice([0.0, 0.03, 0.12]))
+        if qmode == "junk" or not core:
+            core = _rand_seq(rng, rng.randint(1, 80))
+        lo = max(0, k_true - rng.randint(0, 12))
+        hi = k_true + rng.randint(0, 12)
+        cores.append(core); kmin.append(lo); kmax.append(hi)
+    return left, right, motif, cores, np.array(kmin, np.int32), np.array(kmax, np.int32)
+
+
+@pytest.mark.parametrize("seed,n_left,n_right,m,n_reads,kspan,qmode", [
+    (1, 40, 50, 3, 40, 20, "std"), (2, 0, 30, 2, 30, 10, "std"), (3, 25, 0, 4, 30, 10, "std"),
+    (4, 0, 0, 5, 20, 8, "std"), (5, 300, 250, 1, 30, 30, "std"), (6, 120, 130, 6, 30, 60, "std"),
+    (7, 60, 60, 3, 25, 15, "junk"), (8, 80, 90, 3, 12, 30, "long"), (9, 1000, 1000, 5, 16, 50, "std"),
+    (10, 7, 9, 2, 40, 5, "std")])
+def test_ladder_shared_sweeps_equal_independent_rectangles(engine, oracle, seed, n_left, n_right, m, n_reads, kspan, qmode):
+    """Round 3 through the shared-sweep ladder kernel == every rung as its own rectangle == the oracle, on the full
+    (score, tstart, tend) record of every rung (north_star: prefix sharing only if scores stay identical)."""
+    rng = random.Random(1000 + seed)
+    left, right, motif, cores, kmin, kmax = _ladder_case(rng, n_left, n_right, m, n_reads, kspan, qmode)
+    sc = engine.get_preset("ont")
+    ref, roff = oracle.align_ladders(cores, left, right, motif, kmin, kmax, n_threads=oracle.max_threads())
+    got = {}
+    try:
+        for mode in (1, 0):
+            engine.set_ladder_mode(mode)
+            b = engine.Batch.round3(sc, left, right, motif, cores, kmin, kmax)
+            b.run()
+            got[mode] = b.fetch_alns()
+            b.close()
+    finally:
+        engine.set_ladder_mode(1)
+    _assert_same(got[0], ref, f"independent rectangles, seed {seed}")
+    _assert_same(got[1], ref, f"shared sweeps, seed {seed}")
+
+
+def test_ladder_long_expanded_allele(engine, oracle):
+    """cfg4-like FMR1 shape: multi-stripe read, 1000-bp anchors, a +/-25 ladder around 500 units."""
+    from nanorepeat_b200 import synth
+    rng = np.random.default_rng(44)
+    L, R = synth.random_seq(rng, 1000), synth.random_seq(rng, 1000)
+    cores = [synth.simulate_core(rng, L, R, "CGG", k, "ont_r9")[0] for k in (480, 500, 523)]
+    kmin = np.array([470, 490, 515], np.int32)
+    kmax = np.array([486, 506, 530], np.int32)
+    sc = engine.get_preset("ont")
+    ref, _ = oracle.align_ladders(cores, L, R, "CGG", kmin, kmax, n_threads=oracle.max_threads())
+    b = engine.Batch.round3(sc, L, R, "CGG", cores, kmin, kmax)
+    b.run()
+    _assert_same(b.fetch_alns(), ref, "long ladder")
+    st = b.stats()
+    assert st["executed_cells"] * 5 < st["algorithmic_cells"]
+    b.close()
+
+
 @pytest.mark.parametrize("name", GOLDEN_SETS)
 def test_golden_fixtures_through_operator_api(engine, name):
     """Reads like the reference's own use: fill a RepeatRegion, call the two operators, compare the attributes
