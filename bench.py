@@ -32,7 +32,8 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 DPX_LANES_PER_CLK_PER_SM = 64       # measured: tools/microbench/pipe_rates.cu -> profiles/pipe_rates_r01.jsonl
-DPX_INSTR_PER_CELL = 7              # 3 (six-way max for H) + 4 (E1, E2, F1, F2 updates); see DESIGN.md
+DPX_INSTR_PER_CELL = 6              # irreducible for the 5-state cell: 2 (five-way max + floor for H) + 4 (E1, E2,
+                                    # F1, F2 updates); the running-max op (0.5/cell) counts against the kernel
 
 
 def load_peaks():
@@ -206,13 +207,9 @@ def main():
 
     # ---- e2e leg: the operator API, host strings in, attributes out ----
     def e2e_step():
-        out = []
-        for reg in regs:
-            rr = nrb.RepeatRegion.from_synth(reg)
-            nrb.round1_and_round2_estimation(data_type, rr, 1)
-            nrb.round3_estimation(data_type, False, rr, 1)
-            out.append(rr)
-        return out
+        rrs = [nrb.RepeatRegion.from_synth(reg) for reg in regs]
+        nrb.estimate_regions(rrs, data_type, False)      # round1_and_round2_estimation + round3_estimation, batched
+        return rrs
 
     rrs = e2e_step()            # also the first warm-up; gives r2 -> ladders for the resident batches
     h2d = d2h = 0
@@ -235,13 +232,27 @@ def main():
     cells_step = cells2 + cells3
     units_step = sum(len(r.core_seqs) for r in regs)
 
-    # ---- resident batches ----
-    batches = []
-    for reg, T, lo, hi, ok in zip(regs, T_list, kmins, kmaxs, valid):
-        batches.append(engine.Batch.round2(sc, reg.left_anchor_seq, reg.repeat_unit_seq, T, reg.core_seqs))
+    # ---- C-ABI leg: host byte buffers in, numpy records out (pack + H2D + kernels + D2H + selection) ----
+    r2_specs = [(reg.left_anchor_seq, reg.repeat_unit_seq, T, reg.core_seqs) for reg, T in zip(regs, T_list)]
+    r3_specs = []
+    for reg, lo, hi, ok in zip(regs, kmins, kmaxs, valid):
         idx = [i for i, v in enumerate(ok) if v]
-        batches.append(engine.Batch.round3(sc, reg.left_anchor_seq, reg.right_anchor_seq, reg.repeat_unit_seq,
-                                           [reg.core_seqs[i] for i in idx], lo[idx], hi[idx]))
+        r3_specs.append((reg.left_anchor_seq, reg.right_anchor_seq, reg.repeat_unit_seq,
+                         [reg.core_seqs[i] for i in idx], lo[idx], hi[idx]))
+
+    def cabi_step():
+        a = engine.round2_regions(sc, r2_specs)
+        s = engine.round3_regions(sc, r3_specs)
+        return a, s
+
+    # ---- resident batches: one per round over both regions ----
+    b2 = engine.Batch.begin(sc, "round2")
+    for spec in r2_specs:
+        b2.add_round2(*spec)
+    b3 = engine.Batch.begin(sc, "round3")
+    for spec in r3_specs:
+        b3.add_round3(*spec)
+    batches = [b2.commit(), b3.commit()]
     stats = [b.stats() for b in batches]
     executed_step = sum(s["executed_cells"] for s in stats)
     algorithmic_check = sum(s["algorithmic_cells"] for s in stats)
@@ -285,9 +296,10 @@ def main():
     wall = time.perf_counter() - wall0
     total_ms = float(sum(dev_ms))
 
-    # ---- e2e timed region ----
+    # ---- e2e timed regions ----
     for _ in range(2):
         e2e_step()
+        cabi_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -295,15 +307,22 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _a2, s3_cabi = cabi_step()
+    torch.cuda.synchronize()
+    cabi_s = time.perf_counter() - t0
+    barrier()
     clocks = sampler.stop()
 
-    # parity spot-check of the resident path against the e2e path (same numbers either way)
-    s3, n3, t3 = batches[1].fetch_round3()
+    # the resident path and the C-ABI path must give the same records
+    s3 = batches[1].fetch_round3()
+    assert all(np.array_equal(x, y) for x, y in zip(s3, s3_cabi)), "resident and C-ABI round-3 results differ"
 
     if world > 1:
-        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([total_ms, e2e_s, cabi_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s = float(t[0]), float(t[1])
+        total_ms, e2e_s, cabi_s = float(t[0]), float(t[1]), float(t[2])
         c = torch.tensor([cells_step, executed_step, units_step, launches_step], dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         cells_all, executed_all, units_all, launches_all = (float(x) for x in c)
@@ -321,14 +340,19 @@ def main():
         line = {
             "metric": "GCUPS", "value": value, "unit": "GCUPS (1e9 DP cells/s, full rectangles)", "n_gpus": world,
             "steps": K, "warmup": args.warmup, "ms_per_step": total_ms / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "s32 (score<<16|start packed)", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "s32 (score*65536 - span packed word)", "data": "synthetic",
             "reads_per_s": units_all * K / (total_ms * 1e-3),
             "config": {"workload": "config 2: HTT CAG/CCG amplicon, 5k ONT reads, two BED rows, rounds 2+3",
                        "reads": args.reads, "units_per_step_per_gpu": units_step,
                        "cells_per_step_per_gpu": cells_step, "l2": "flushed between timed steps (256 MB fill)",
                        "seed": args.seed},
             "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "reads_per_s": units_all * K / e2e_s, "ms_per_step": e2e_s / K * 1e3},
+                    "reads_per_s": units_all * K / e2e_s, "ms_per_step": e2e_s / K * 1e3,
+                    "path": "nanorepeat_b200.estimate_regions on RepeatRegion/Read objects (host strings in, "
+                            "Read.round{1,2,3}_repeat_size out)",
+                    "c_abi": {"value": cells_all * K / cabi_s / 1e9, "unit": "GCUPS",
+                              "reads_per_s": units_all * K / cabi_s, "ms_per_step": cabi_s / K * 1e3,
+                              "path": "nr_batch_begin/add/commit/run/fetch with host byte buffers in, records out"}},
             "gpu_launches": int(launches_all * K),
             "clocks": clocks,
             "roofline": {"bound": "dpx", "achieved": achieved, "peak": peak_gcups, "unit": "GCUPS",

@@ -141,6 +141,22 @@ nr_batch_t* nr_batch_create_round3(const nr_scoring_t* sc,
                                    const char* motif, int32_t motif_len,
                                    int32_t n_reads, const char* const* cores, const int32_t* core_len,
                                    const int32_t* kmin, const int32_t* kmax);
+/*
+ * Multi-region batches: one launch covers every region added (the reference walks regions one by one,
+ * nanoRepeat_bam.py:604-612; with 30 reads per region a B200 needs hundreds of regions per launch to fill up).
+ * begin -> add_round2 / add_round3 once per region -> commit (plan + upload) -> run -> fetch.  Reads are passed as
+ * one concatenated buffer with n_reads + 1 offsets.  Outputs are concatenated in the order the regions were added.
+ * On any error the batch stays valid only for nr_batch_destroy().
+ */
+#define NR_KIND_ROUND2 1
+#define NR_KIND_ROUND3 2
+nr_batch_t* nr_batch_begin(const nr_scoring_t* sc, int32_t kind);
+int nr_batch_add_round2(nr_batch_t* b, const char* left, int32_t n_left, const char* motif, int32_t motif_len,
+                        int32_t T, int32_t n_reads, const char* cores_concat, const int64_t* core_off);
+int nr_batch_add_round3(nr_batch_t* b, const char* left, int32_t n_left, const char* right, int32_t n_right,
+                        const char* motif, int32_t motif_len, int32_t n_reads, const char* cores_concat,
+                        const int64_t* core_off, const int32_t* kmin, const int32_t* kmax);
+int nr_batch_commit(nr_batch_t* b);
 int nr_batch_run(nr_batch_t* b, void* stream);
 int nr_batch_fetch_alns(nr_batch_t* b, nr_aln_t* out);                      /* tasks / round2 batches */
 int nr_batch_fetch_round3(nr_batch_t* b, const int64_t* rung_offset, nr_rung_t* rungs,

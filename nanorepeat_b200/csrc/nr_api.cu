@@ -1,9 +1,10 @@
 // nr_api.cu -- C ABI host side of libnanorepeat_b200.so (declared in include/nanorepeat_b200.h).
 //
-// Host work done here, natively: 2-bit packing of reads and templates into one sequence pool, ladder template
-// generation (left + motif*k + right stored once per k and shared by all reads of the region, reference
-// nanoRepeat_bam.py:474-481), task construction, cost sorting and bucketing by stripe shape, launches of the
-// sm_100a kernels in nr_kernels.cuh, result gather and the round-3 selection of nanoRepeat_bam.py:423-431.
+// Host work done here, natively: 2-bit packing of reads and templates into one sequence pool, template generation
+// (round 2: left + motif*T, reference nanoRepeat_bam.py:352-354; round 3: left + motif*kmax stored once per region
+// plus reverse(right), or one left + motif*k + right per distinct k in the independent mode, :474-481), task
+// construction over any number of regions, cost sorting, launches of the sm_100a kernels in nr_kernels.cuh, result
+// gather and the round-3 selection of nanoRepeat_bam.py:423-431.
 // There is no CPU compute fallback: without a CUDA device every compute call fails with NR_ERR_CUDA.
 #include "../../include/nanorepeat_b200.h"
 #include "nr_kernels.cuh"
@@ -45,19 +46,34 @@ int fail(int code, const char* fmt, ...) {
                         __FILE__, __LINE__);                                                    \
     } while (0)
 
+constexpr int kMaxScore = 32767;   // signed 16-bit score field of the packed DP word
+constexpr int kMaxTlen = 65535;    // unsigned 16-bit span field
+constexpr int kWarpsPerBlock = 4;
+
+// ---- context + caching allocator -----------------------------------------------------------------------------
+// Batches come and go once per region (or per group of regions); cudaMalloc / cudaMallocHost / cudaFree cost far
+// more than the copies they serve, so freed buffers are kept by power-of-two size class and handed out again.
+struct BufCache {
+    std::unordered_map<size_t, std::vector<void*>> free_dev, free_pin;
+    static size_t klass(size_t bytes) {
+        size_t c = 4096;
+        while (c < bytes) c <<= 1;
+        return c;
+    }
+};
+
 struct Context {
     bool ready = false;
     int device = -1;
     int sm_count = 0;
     int clock_khz = 0;
+    int blocks_per_sm = 4;
     cudaStream_t stream = nullptr;
+    BufCache cache;
 };
 Context g_ctx;
 std::mutex g_ctx_mu;
-
-constexpr int kMaxScore = 32767;   // signed 16-bit score field of the packed DP word
-constexpr int kMaxTlen = 65535;    // unsigned 16-bit start-column field
-constexpr int kWarpsPerBlock = 4;
+std::atomic<int> g_ladder_mode{1};   // 1: round 3 shares sweeps across the ladder; 0: every rung its own rectangle
 
 int ensure_init(int device) {
     std::lock_guard<std::mutex> lk(g_ctx_mu);
@@ -83,15 +99,34 @@ int ensure_init(int device) {
     g_ctx.device = device;
     g_ctx.sm_count = prop.multiProcessorCount;
     g_ctx.clock_khz = prop.clockRate;
+    if (const char* e = getenv("NR_BLOCKS_PER_SM")) g_ctx.blocks_per_sm = std::max(1, std::min(4, atoi(e)));
     g_ctx.ready = true;
     return NR_OK;
 }
 
+int cached_alloc(void** p, size_t bytes, bool pinned) {
+    const size_t k = BufCache::klass(bytes);
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        auto& fl = (pinned ? g_ctx.cache.free_pin : g_ctx.cache.free_dev)[k];
+        if (!fl.empty()) { *p = fl.back(); fl.pop_back(); return NR_OK; }
+    }
+    if (pinned) CUDA_TRY(cudaMallocHost(p, k));
+    else CUDA_TRY(cudaMalloc(p, k));
+    return NR_OK;
+}
+
+void cached_free(void* p, size_t bytes, bool pinned) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    (pinned ? g_ctx.cache.free_pin : g_ctx.cache.free_dev)[BufCache::klass(bytes)].push_back(p);
+}
+
 // ---- 2-bit packing -------------------------------------------------------------------------------------------
 struct CodeTable {
-    int8_t t[256];
+    uint8_t t[256];
     CodeTable() {
-        memset(t, -1, sizeof t);
+        memset(t, 0x80, sizeof t);     // bit 7 = not ACGT
         t[(int)'A'] = t[(int)'a'] = 0;
         t[(int)'C'] = t[(int)'c'] = 1;
         t[(int)'G'] = t[(int)'g'] = 2;
@@ -106,26 +141,40 @@ struct Pool {
     std::vector<uint32_t> words;
     // append; returns first word index, or -1 on a non-ACGT character
     long long add(const char* s, int len) {
-        size_t w0 = words.size();
-        size_t nw = (size_t)(len + 15) / 16 + 1;
+        const size_t w0 = words.size();
+        const size_t nw = (size_t)(len + 15) / 16 + 1;
         words.resize(w0 + nw, 0u);
         uint32_t* w = words.data() + w0;
-        int bad = 0;
-        for (int i = 0; i < len; ++i) {
-            int c = g_codes.t[(unsigned char)s[i]];
-            bad |= c;
-            w[i >> 4] |= (uint32_t)(c & 3) << (2 * (i & 15));
+        const unsigned char* u = reinterpret_cast<const unsigned char*>(s);
+        unsigned bad = 0;
+        int i = 0;
+        for (; i + 16 <= len; i += 16) {
+            uint32_t v = 0;
+            for (int j = 0; j < 16; ++j) {
+                const unsigned c = g_codes.t[u[i + j]];
+                bad |= c;
+                v |= (c & 3u) << (2 * j);
+            }
+            w[i >> 4] = v;
         }
-        if (bad < 0) { words.resize(w0); return -1; }
+        if (i < len) {
+            uint32_t v = 0;
+            for (int j = 0; i + j < len; ++j) {
+                const unsigned c = g_codes.t[u[i + j]];
+                bad |= c;
+                v |= (c & 3u) << (2 * j);
+            }
+            w[i >> 4] = v;
+        }
+        if (bad & 0x80u) { words.resize(w0); return -1; }
         return (long long)w0;
     }
 };
 
 struct Bucket {
-    int R;
-    bool multi;
+    bool multi;      // tasks with several stripes (boundary rows through L2 scratch)
     bool ladder;     // ladder_kernel over nr_batch::ltasks instead of exact_kernel over nr_batch::tasks
-                     // (R = tallest stripe of the launch: sizes the shared memory per warp)
+    int R;           // tallest stripe of the launch: sizes the shared memory per warp
     int order_off;   // offset into the order array
     int count;
     int blocks;
@@ -135,46 +184,58 @@ struct Bucket {
     size_t scratch_off;         // int4 offset into d_scratch
 };
 
-std::atomic<int> g_ladder_mode{1};   // 1: round 3 shares sweeps across the ladder; 0: every rung its own rectangle
+struct RegionInfo {   // one add_round2 / add_round3 call
+    int n_left = 0, n_right = 0, motif_len = 0;
+    int first_read = 0, n_reads = 0;
+};
 
 }  // namespace
 
-enum BatchKind { KIND_TASKS = 0, KIND_ROUND2 = 1, KIND_ROUND3 = 2 };
+enum BatchKind { KIND_TASKS = 0, KIND_ROUND2 = NR_KIND_ROUND2, KIND_ROUND3 = NR_KIND_ROUND3 };
 
 struct nr_batch {
     BatchKind kind = KIND_TASKS;
     nr_scoring_t sc = {};
+    bool committed = false;
     std::vector<nr::Task> tasks;
-    std::vector<nr::LadderTask> ltasks;   // round 3 in ladder mode (tasks stays empty)
-    nr::LadderRegion lreg = {};
+    std::vector<nr::LadderTask> ltasks;       // round 3 in ladder mode (tasks stays empty)
+    std::vector<nr::LadderRegion> lregs;
     bool ladder = false;
-    size_t n_out = 0;                     // records in d_out / h_out
+    size_t n_out = 0;                         // records in d_out / h_out
     std::vector<int32_t> order;
     std::vector<Bucket> buckets;
     Pool pool;
-    // round 3 bookkeeping
-    int n_reads = 0, n_left = 0, n_right = 0, motif_len = 0;
+    // per-read bookkeeping (rounds 2 and 3)
+    std::vector<RegionInfo> regions;
+    int n_reads = 0;
+    std::vector<int32_t> read_region;
     std::vector<int32_t> kmin, kmax;
-    std::vector<int64_t> rung_off;   // n_reads + 1
+    std::vector<int64_t> rung_off;            // n_reads + 1 (round 3)
     // device
+    void* d_blob = nullptr;                   // tasks | regions | order | pool | counters: one allocation, one H2D copy
+    size_t blob_bytes = 0;
+    void* h_blob = nullptr;                   // pinned staging of the same layout
     nr::Task* d_tasks = nullptr;
     nr::LadderTask* d_ltasks = nullptr;
+    nr::LadderRegion* d_lregs = nullptr;
     int32_t* d_order = nullptr;
     uint32_t* d_pool = nullptr;
     int* d_counters = nullptr;
     int4* d_out = nullptr;
+    size_t out_bytes = 0;
     int4* d_scratch = nullptr;
-    int4* h_out = nullptr;   // pinned
+    size_t scratch_bytes = 0;
+    int4* h_out = nullptr;                    // pinned
     nr_stats_t stats = {};
     bool ran = false;
-    cudaStream_t run_stream = nullptr;    // stream of the last nr_batch_run: fetch orders itself behind it
+    cudaStream_t run_stream = nullptr;        // stream of the last nr_batch_run: fetch orders itself behind it
 };
 
 namespace {
 
 typedef void (*ExactKernel)(const nr::Task*, const int32_t*, int, const uint32_t*, nr::ScoreW, int*, int, int4*,
                             long long, int4*);
-typedef void (*LadderKernel)(const nr::LadderTask*, const int32_t*, int, const uint32_t*, nr::LadderRegion,
+typedef void (*LadderKernel)(const nr::LadderTask*, const int32_t*, int, const uint32_t*, const nr::LadderRegion*,
                              nr::ScoreW, int*, int, int4*, long long, long long, long long, int4*);
 
 // shared memory per warp, in int4: query profile (+ backward junction vectors for the ladder kernel)
@@ -209,11 +270,13 @@ nr::ScoreW score_words(const nr_scoring_t& sc) {
     return k;
 }
 
-// Sort tasks into buckets (by stripe shape), each ordered by decreasing cost, and size the launches.
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Sort tasks (single-stripe | multi-stripe groups, each by decreasing cost), size the launches, upload.
 int plan_batch(nr_batch* b) {
     const bool ladder = b->ladder;
     const int n = ladder ? (int)b->ltasks.size() : (int)b->tasks.size();
-    if (!ladder) b->n_out = b->tasks.size();
+    if (b->kind != KIND_ROUND3) b->n_out = b->tasks.size();
     b->stats = {};
     b->stats.n_tasks = (int64_t)b->n_out;
     std::vector<uint8_t> shapeM(n);
@@ -221,17 +284,18 @@ int plan_batch(nr_batch* b) {
     const int max_r = ladder ? nr::kMaxRLadder : nr::kMaxRExact;
     int n_multi = 0;
     int rmax[2] = {0, 0}, tmax[2] = {0, 0}, qmax[2] = {0, 0}, rungs_max[2] = {0, 0};
-    const int lad_cols = b->lreg.n_left + b->lreg.n_right;
     for (int i = 0; i < n; ++i) {
         int q_len, t_len, t_sweep, rungs = 0;
         if (ladder) {
             const nr::LadderTask& t = b->ltasks[i];
+            const nr::LadderRegion& g = b->lregs[t.region];
+            const int flank = g.n_left + g.n_right;
             q_len = t.q_len;
-            t_len = lad_cols + b->lreg.m * t.kmax;                 // longest rung = columns swept (|R| back, rest forward)
-            t_sweep = std::max(b->lreg.n_left + b->lreg.m * t.kmax, b->lreg.n_right);
+            t_len = flank + g.m * t.kmax;                 // longest rung = columns swept (|R| backward, rest forward)
+            t_sweep = std::max(g.n_left + g.m * t.kmax, g.n_right);
             rungs = t.kmax - t.kmin + 1;
-            b->stats.algorithmic_cells += (long long)q_len * ((long long)rungs * lad_cols +
-                                                              (long long)b->lreg.m * (t.kmin + t.kmax) * rungs / 2);
+            b->stats.algorithmic_cells +=
+                (long long)q_len * ((long long)rungs * flank + (long long)g.m * (t.kmin + t.kmax) * rungs / 2);
         } else {
             const nr::Task& t = b->tasks[i];
             q_len = t.q_len;
@@ -273,7 +337,7 @@ int plan_batch(nr_batch* b) {
         if (!bk.count) continue;
         std::sort(b->order.begin() + bk.order_off, b->order.begin() + bk.order_off + bk.count,
                   [&](int x, int y) { return cost[x] != cost[y] ? cost[x] > cost[y] : x < y; });
-        bk.blocks = std::min(g_ctx.sm_count * 4, (bk.count + kWarpsPerBlock - 1) / kWarpsPerBlock);
+        bk.blocks = std::min(g_ctx.sm_count * g_ctx.blocks_per_sm, (bk.count + kWarpsPerBlock - 1) / kWarpsPerBlock);
         if (bk.multi) {
             bk.scratch_stride = ((long long)tmax[mi] + 63) / 32 * 32;
             if (ladder) {
@@ -286,41 +350,50 @@ int plan_batch(nr_batch* b) {
         }
         b->buckets.push_back(bk);
     }
-    // device allocations + uploads
-    const size_t pool_words = b->pool.words.size() + 4;
-    const size_t n_out = std::max<size_t>(b->n_out, 1);
-    if (ladder) CUDA_TRY(cudaMalloc(&b->d_ltasks, sizeof(nr::LadderTask) * std::max(n, 1)));
-    else CUDA_TRY(cudaMalloc(&b->d_tasks, sizeof(nr::Task) * std::max(n, 1)));
-    CUDA_TRY(cudaMalloc(&b->d_order, sizeof(int32_t) * std::max(n, 1)));
-    CUDA_TRY(cudaMalloc(&b->d_pool, sizeof(uint32_t) * pool_words));
-    CUDA_TRY(cudaMalloc(&b->d_counters, sizeof(int) * std::max<size_t>(b->buckets.size(), 1)));
-    CUDA_TRY(cudaMalloc(&b->d_out, sizeof(int4) * n_out));
-    if (scratch_total) CUDA_TRY(cudaMalloc(&b->d_scratch, sizeof(int4) * scratch_total));
-    CUDA_TRY(cudaMallocHost(&b->h_out, sizeof(int4) * n_out));
+    // ---- one device blob: [tasks | regions | order | pool (+4 slack words) | counters], staged in pinned memory ----
+    const size_t task_bytes = ladder ? sizeof(nr::LadderTask) * n : sizeof(nr::Task) * n;
+    const size_t reg_bytes = sizeof(nr::LadderRegion) * b->lregs.size();
+    const size_t order_bytes = sizeof(int32_t) * n;
+    const size_t pool_bytes = sizeof(uint32_t) * (b->pool.words.size() + 4);
+    const size_t off_reg = align_up(task_bytes, 256);
+    const size_t off_order = off_reg + align_up(reg_bytes, 256);
+    const size_t off_pool = off_order + align_up(order_bytes, 256);
+    const size_t off_cnt = off_pool + align_up(pool_bytes, 256);
+    b->blob_bytes = off_cnt + 256;
+    b->out_bytes = sizeof(int4) * std::max<size_t>(b->n_out, 1);
+    b->scratch_bytes = sizeof(int4) * scratch_total;
+    int rc;
+    if ((rc = cached_alloc(&b->d_blob, b->blob_bytes, false))) return rc;
+    if ((rc = cached_alloc(&b->h_blob, b->blob_bytes, true))) return rc;
+    if ((rc = cached_alloc((void**)&b->d_out, b->out_bytes, false))) return rc;
+    if ((rc = cached_alloc((void**)&b->h_out, b->out_bytes, true))) return rc;
+    if (scratch_total && (rc = cached_alloc((void**)&b->d_scratch, b->scratch_bytes, false))) return rc;
+    char* h = static_cast<char*>(b->h_blob);
+    char* d = static_cast<char*>(b->d_blob);
+    if (task_bytes) memcpy(h, ladder ? (const void*)b->ltasks.data() : (const void*)b->tasks.data(), task_bytes);
+    if (reg_bytes) memcpy(h + off_reg, b->lregs.data(), reg_bytes);
+    if (order_bytes) memcpy(h + off_order, b->order.data(), order_bytes);
+    if (!b->pool.words.empty()) memcpy(h + off_pool, b->pool.words.data(), pool_bytes - 16);
+    memset(h + off_pool + pool_bytes - 16, 0, 16);
+    memset(h + off_cnt, 0, 256);
+    b->d_tasks = reinterpret_cast<nr::Task*>(d);
+    b->d_ltasks = reinterpret_cast<nr::LadderTask*>(d);
+    b->d_lregs = reinterpret_cast<nr::LadderRegion*>(d + off_reg);
+    b->d_order = reinterpret_cast<int32_t*>(d + off_order);
+    b->d_pool = reinterpret_cast<uint32_t*>(d + off_pool);
+    b->d_counters = reinterpret_cast<int*>(d + off_cnt);
     cudaStream_t st = g_ctx.stream;
-    CUDA_TRY(cudaMemsetAsync(b->d_pool, 0, sizeof(uint32_t) * pool_words, st));
-    CUDA_TRY(cudaMemsetAsync(b->d_out, 0, sizeof(int4) * n_out, st));
-    size_t task_bytes = 0;
-    if (n) {
-        if (ladder) {
-            task_bytes = sizeof(nr::LadderTask) * n;
-            CUDA_TRY(cudaMemcpyAsync(b->d_ltasks, b->ltasks.data(), task_bytes, cudaMemcpyHostToDevice, st));
-        } else {
-            task_bytes = sizeof(nr::Task) * n;
-            CUDA_TRY(cudaMemcpyAsync(b->d_tasks, b->tasks.data(), task_bytes, cudaMemcpyHostToDevice, st));
-        }
-        CUDA_TRY(cudaMemcpyAsync(b->d_order, b->order.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
-    }
-    if (!b->pool.words.empty())
-        CUDA_TRY(cudaMemcpyAsync(b->d_pool, b->pool.words.data(), sizeof(uint32_t) * b->pool.words.size(),
-                                 cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d, h, b->blob_bytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(b->d_out, 0, b->out_bytes, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    b->stats.h2d_bytes = (int64_t)(task_bytes + sizeof(int32_t) * n + sizeof(uint32_t) * b->pool.words.size());
+    b->stats.h2d_bytes = (int64_t)(task_bytes + reg_bytes + order_bytes + pool_bytes);
     b->stats.d2h_bytes = (int64_t)sizeof(int4) * (int64_t)b->n_out;
+    b->committed = true;
     return NR_OK;
 }
 
 int run_batch(nr_batch* b, cudaStream_t st) {
+    if (!b->committed) return fail(NR_ERR_ARG, "batch was not committed");
     b->run_stream = st;
     if (b->buckets.empty()) { b->ran = true; return NR_OK; }
     const nr::ScoreW k = score_words(b->sc);
@@ -337,8 +410,9 @@ int run_batch(nr_batch* b, cudaStream_t st) {
             CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout,
                                           cudaSharedmemCarveoutMaxShared));
             fn<<<bk.blocks, kWarpsPerBlock * 32, smem, st>>>(b->d_ltasks, b->d_order + bk.order_off, bk.count,
-                                                            b->d_pool, b->lreg, k, b->d_counters + i, stride, scratch,
-                                                            bk.scratch_stride, bk.b_stride, bk.tok_stride, b->d_out);
+                                                            b->d_pool, b->d_lregs, k, b->d_counters + i, stride,
+                                                            scratch, bk.scratch_stride, bk.b_stride, bk.tok_stride,
+                                                            b->d_out);
         } else {
             ExactKernel fn = bk.multi ? (ExactKernel)nr::exact_kernel<true> : (ExactKernel)nr::exact_kernel<false>;
             const int stride = exact_smem_int4(bk.R);
@@ -378,6 +452,147 @@ int add_seq(nr_batch* b, const char* s, int len, const char* what, int idx, uint
     return NR_OK;
 }
 
+// reads either as an array of pointers (cores != NULL) or as one concatenated buffer with n_reads + 1 offsets
+struct ReadSrc {
+    const char* const* cores;
+    const int32_t* core_len;
+    const char* concat;
+    const int64_t* off;
+    const char* ptr(int r) const { return cores ? cores[r] : concat + off[r]; }
+    long long len(int r) const { return cores ? (long long)core_len[r] : (long long)(off[r + 1] - off[r]); }
+};
+
+int add_round2(nr_batch* b, const char* left, int32_t n_left, const char* motif, int32_t motif_len, int32_t T,
+               int32_t n_reads, const ReadSrc& src) {
+    if (!b || b->kind != KIND_ROUND2 || b->committed) return fail(NR_ERR_ARG, "not an open round-2 batch");
+    if (n_left < 0 || motif_len <= 0 || T < 0 || n_reads < 0 || !motif || (n_left > 0 && !left))
+        return fail(NR_ERR_ARG, "nr_batch_add_round2: bad arguments");
+    // template = left + motif * T   (nanoRepeat_bam.py:352-354)
+    std::string tpl(left ? left : "", (size_t)n_left);
+    tpl.reserve((size_t)n_left + (size_t)motif_len * T);
+    for (int k = 0; k < T; ++k) tpl.append(motif, (size_t)motif_len);
+    uint32_t tw;
+    int rc;
+    if ((rc = add_seq(b, tpl.data(), (int)tpl.size(), "round-2 template", 0, &tw))) return rc;
+    RegionInfo g;
+    g.n_left = n_left; g.motif_len = motif_len; g.first_read = b->n_reads; g.n_reads = n_reads;
+    b->regions.push_back(g);
+    const size_t base = b->tasks.size();
+    b->tasks.resize(base + n_reads);
+    for (int r = 0; r < n_reads; ++r) {
+        nr::Task& t = b->tasks[base + r];
+        const long long len = src.len(r);
+        if (len < 0 || len > 0x7fffffffLL) return fail(NR_ERR_ARG, "core %d has a bad length", r);
+        if ((rc = add_seq(b, src.ptr(r), (int)len, "core", r, &t.q_word))) return rc;
+        t.q_len = (int)len;
+        t.t_word = tw;
+        t.t_len = (int)tpl.size();
+    }
+    b->n_reads += n_reads;
+    return NR_OK;
+}
+
+int add_round3(nr_batch* b, const char* left, int32_t n_left, const char* right, int32_t n_right, const char* motif,
+               int32_t motif_len, int32_t n_reads, const ReadSrc& src, const int32_t* kmin, const int32_t* kmax) {
+    if (!b || b->kind != KIND_ROUND3 || b->committed) return fail(NR_ERR_ARG, "not an open round-3 batch");
+    if (n_left < 0 || n_right < 0 || motif_len <= 0 || n_reads < 0 || !motif || (n_left > 0 && !left) ||
+        (n_right > 0 && !right) || (n_reads > 0 && (!kmin || !kmax)))
+        return fail(NR_ERR_ARG, "nr_batch_add_round3: bad arguments");
+    RegionInfo g;
+    g.n_left = n_left; g.n_right = n_right; g.motif_len = motif_len; g.first_read = b->n_reads; g.n_reads = n_reads;
+    const int region = (int)b->regions.size();
+    b->regions.push_back(g);
+    if (b->rung_off.empty()) b->rung_off.push_back(0);
+    int klo = INT32_MAX, khi = -1;
+    for (int r = 0; r < n_reads; ++r) {
+        if (kmin[r] < 0) return fail(NR_ERR_ARG, "kmin[%d] < 0", r);
+        const long long n = kmax[r] >= kmin[r] ? (long long)kmax[r] - kmin[r] + 1 : 0;
+        b->rung_off.push_back(b->rung_off.back() + n);
+        b->kmin.push_back(kmin[r]);
+        b->kmax.push_back(kmax[r]);
+        b->read_region.push_back(region);
+        if (n) { klo = std::min(klo, kmin[r]); khi = std::max(khi, kmax[r]); }
+    }
+    if (b->rung_off.back() > 0x7fffffffLL) return fail(NR_ERR_TOO_LARGE, "more than 2^31 rungs in one batch");
+    const int first = b->n_reads;
+    b->n_reads += n_reads;
+    b->n_out = (size_t)b->rung_off.back();
+    const int64_t* roff = b->rung_off.data() + first;
+    int rc;
+    if (b->ladder) {
+        // shared sweeps (nr_kernels.cuh, ladder_kernel): the pool holds left + motif^khi once and reverse(right) once
+        nr::LadderRegion lr = {};
+        lr.n_left = n_left; lr.n_right = n_right; lr.m = motif_len;
+        std::string fwd(left ? left : "", (size_t)n_left);
+        for (int u = 0; u < std::max(khi, 0); ++u) fwd.append(motif, (size_t)motif_len);
+        std::string rev(right ? right : "", (size_t)n_right);
+        std::reverse(rev.begin(), rev.end());
+        if ((rc = add_seq(b, fwd.data(), (int)fwd.size(), "ladder prefix", 0, &lr.fwd_word))) return rc;
+        if ((rc = add_seq(b, rev.data(), (int)rev.size(), "right anchor", 0, &lr.rev_word))) return rc;
+        const int lreg = (int)b->lregs.size();
+        b->lregs.push_back(lr);
+        for (int r = 0; r < n_reads; ++r) {
+            if (roff[r + 1] == roff[r]) continue;
+            const long long len = src.len(r);
+            if (len < 0 || len > 0x7fffffffLL) return fail(NR_ERR_ARG, "core %d has a bad length", r);
+            if (len == 0) continue;     // every rung scores 0: d_out is zero-filled
+            nr::LadderTask t = {};
+            if ((rc = add_seq(b, src.ptr(r), (int)len, "core", r, &t.q_word))) return rc;
+            t.q_len = (int)len;
+            t.kmin = kmin[r];
+            t.kmax = kmax[r];
+            t.out_off = (int32_t)roff[r];
+            t.region = lreg;
+            b->ltasks.push_back(t);
+        }
+        return NR_OK;
+    }
+    // independent rectangles: left + motif*k + right, one template per distinct k that any read of the region uses
+    // (nanoRepeat_bam.py:478-479)
+    std::vector<uint32_t> tpl_word;
+    if (khi >= klo) {
+        std::vector<uint8_t> used(khi - klo + 1, 0);
+        for (int r = 0; r < n_reads; ++r)
+            for (int k = kmin[r]; k <= kmax[r]; ++k) used[k - klo] = 1;
+        tpl_word.assign(khi - klo + 1, 0);
+        std::string tpl;
+        for (int k = klo; k <= khi; ++k) {
+            if (!used[k - klo]) continue;
+            tpl.assign(left ? left : "", (size_t)n_left);
+            for (int u = 0; u < k; ++u) tpl.append(motif, (size_t)motif_len);
+            tpl.append(right ? right : "", (size_t)n_right);
+            if ((rc = add_seq(b, tpl.data(), (int)tpl.size(), "ladder template", k, &tpl_word[k - klo]))) return rc;
+        }
+    }
+    b->tasks.resize(b->n_out);
+    for (int r = 0; r < n_reads; ++r) {
+        if (roff[r + 1] == roff[r]) continue;
+        const long long len = src.len(r);
+        if (len < 0 || len > 0x7fffffffLL) return fail(NR_ERR_ARG, "core %d has a bad length", r);
+        uint32_t qw;
+        if ((rc = add_seq(b, src.ptr(r), (int)len, "core", r, &qw))) return rc;
+        for (int k = kmin[r]; k <= kmax[r]; ++k) {
+            nr::Task& t = b->tasks[(size_t)(roff[r] + (k - kmin[r]))];
+            t.q_word = qw;
+            t.q_len = (int)len;
+            t.t_word = tpl_word[k - klo];
+            t.t_len = n_left + motif_len * k + n_right;
+        }
+    }
+    return NR_OK;
+}
+
+nr_batch* new_batch(const nr_scoring_t* sc, BatchKind kind) {
+    if (check_scoring(sc)) return nullptr;
+    if (ensure_init(-1)) return nullptr;
+    nr_batch* b = new (std::nothrow) nr_batch();
+    if (!b) { fail(NR_ERR_NOMEM, "out of host memory"); return nullptr; }
+    b->kind = kind;
+    b->sc = *sc;
+    b->ladder = kind == KIND_ROUND3 && g_ladder_mode.load() != 0;
+    return b;
+}
+
 }  // namespace
 
 // ---- exported C ABI --------------------------------------------------------------------------------------------
@@ -402,6 +617,8 @@ int nr_init(int device) { return ensure_init(device); }
 int nr_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_ctx_mu);
     if (g_ctx.ready) {
+        for (auto& kv : g_ctx.cache.free_dev) for (void* p : kv.second) cudaFree(p);
+        for (auto& kv : g_ctx.cache.free_pin) for (void* p : kv.second) cudaFreeHost(p);
         cudaStreamDestroy(g_ctx.stream);
         g_ctx = Context();
     }
@@ -433,29 +650,51 @@ int nr_limits(int32_t* max_score, int32_t* max_tlen) {
 
 void nr_batch_destroy(nr_batch_t* b) {
     if (!b) return;
-    cudaFree(b->d_tasks);
-    cudaFree(b->d_ltasks);
-    cudaFree(b->d_order);
-    cudaFree(b->d_pool);
-    cudaFree(b->d_counters);
-    cudaFree(b->d_out);
-    cudaFree(b->d_scratch);
-    if (b->h_out) cudaFreeHost(b->h_out);
+    if (b->ran && b->run_stream) cudaStreamSynchronize(b->run_stream);   // buffers return to the cache: kernels must be done
+    cached_free(b->d_blob, b->blob_bytes, false);
+    cached_free(b->h_blob, b->blob_bytes, true);
+    cached_free(b->d_out, b->out_bytes, false);
+    cached_free(b->h_out, b->out_bytes, true);
+    cached_free(b->d_scratch, b->scratch_bytes, false);
     delete b;
+}
+
+nr_batch_t* nr_batch_begin(const nr_scoring_t* sc, int32_t kind) {
+    if (kind != NR_KIND_ROUND2 && kind != NR_KIND_ROUND3) {
+        fail(NR_ERR_ARG, "nr_batch_begin: kind must be NR_KIND_ROUND2 or NR_KIND_ROUND3");
+        return nullptr;
+    }
+    return new_batch(sc, (BatchKind)kind);
+}
+
+int nr_batch_add_round2(nr_batch_t* b, const char* left, int32_t n_left, const char* motif, int32_t motif_len,
+                        int32_t T, int32_t n_reads, const char* cores_concat, const int64_t* core_off) {
+    if (n_reads > 0 && (!cores_concat || !core_off)) return fail(NR_ERR_ARG, "nr_batch_add_round2: NULL reads");
+    ReadSrc src = {nullptr, nullptr, cores_concat, core_off};
+    return add_round2(b, left, n_left, motif, motif_len, T, n_reads, src);
+}
+
+int nr_batch_add_round3(nr_batch_t* b, const char* left, int32_t n_left, const char* right, int32_t n_right,
+                        const char* motif, int32_t motif_len, int32_t n_reads, const char* cores_concat,
+                        const int64_t* core_off, const int32_t* kmin, const int32_t* kmax) {
+    if (n_reads > 0 && (!cores_concat || !core_off)) return fail(NR_ERR_ARG, "nr_batch_add_round3: NULL reads");
+    ReadSrc src = {nullptr, nullptr, cores_concat, core_off};
+    return add_round3(b, left, n_left, right, n_right, motif, motif_len, n_reads, src, kmin, kmax);
+}
+
+int nr_batch_commit(nr_batch_t* b) {
+    if (!b || b->committed) return fail(NR_ERR_ARG, "nr_batch_commit: NULL or already committed batch");
+    return plan_batch(b);
 }
 
 nr_batch_t* nr_batch_create_tasks(const nr_scoring_t* sc, int32_t n_tasks, const char* const* queries,
                                   const int32_t* qlen, const char* const* targets, const int32_t* tlen) {
-    if (check_scoring(sc)) return nullptr;
     if (n_tasks < 0 || (n_tasks > 0 && (!queries || !qlen || !targets || !tlen))) {
         fail(NR_ERR_ARG, "nr_batch_create_tasks: bad arguments");
         return nullptr;
     }
-    if (ensure_init(-1)) return nullptr;
-    nr_batch* b = new (std::nothrow) nr_batch();
-    if (!b) { fail(NR_ERR_NOMEM, "out of host memory"); return nullptr; }
-    b->kind = KIND_TASKS;
-    b->sc = *sc;
+    nr_batch* b = new_batch(sc, KIND_TASKS);
+    if (!b) return nullptr;
     b->tasks.resize(n_tasks);
     std::unordered_map<const char*, std::pair<int, uint32_t>> seen;   // pointer -> (len, word): callers often
     for (int i = 0; i < n_tasks; ++i) {                                // pass one template for many reads
@@ -481,32 +720,11 @@ nr_batch_t* nr_batch_create_tasks(const nr_scoring_t* sc, int32_t n_tasks, const
 nr_batch_t* nr_batch_create_round2(const nr_scoring_t* sc, const char* left, int32_t n_left, const char* motif,
                                    int32_t motif_len, int32_t T, int32_t n_reads, const char* const* cores,
                                    const int32_t* core_len) {
-    if (check_scoring(sc)) return nullptr;
-    if (n_left < 0 || motif_len <= 0 || T < 0 || n_reads < 0 || !motif || (n_left > 0 && !left) ||
-        (n_reads > 0 && (!cores || !core_len))) {
-        fail(NR_ERR_ARG, "nr_batch_create_round2: bad arguments");
-        return nullptr;
-    }
-    if (ensure_init(-1)) return nullptr;
-    nr_batch* b = new (std::nothrow) nr_batch();
-    if (!b) { fail(NR_ERR_NOMEM, "out of host memory"); return nullptr; }
-    b->kind = KIND_ROUND2;
-    b->sc = *sc;
-    // template = left + motif * T   (nanoRepeat_bam.py:352-354)
-    std::string tpl(left ? left : "", (size_t)n_left);
-    tpl.reserve((size_t)n_left + (size_t)motif_len * T);
-    for (int k = 0; k < T; ++k) tpl.append(motif, (size_t)motif_len);
-    uint32_t tw;
-    if (add_seq(b, tpl.data(), (int)tpl.size(), "round-2 template", 0, &tw)) { nr_batch_destroy(b); return nullptr; }
-    b->tasks.resize(n_reads);
-    for (int r = 0; r < n_reads; ++r) {
-        nr::Task& t = b->tasks[r];
-        if (add_seq(b, cores[r], core_len[r], "core", r, &t.q_word)) { nr_batch_destroy(b); return nullptr; }
-        t.q_len = core_len[r];
-        t.t_word = tw;
-        t.t_len = (int)tpl.size();
-    }
-    if (plan_batch(b)) { nr_batch_destroy(b); return nullptr; }
+    if (n_reads > 0 && (!cores || !core_len)) { fail(NR_ERR_ARG, "nr_batch_create_round2: NULL reads"); return nullptr; }
+    nr_batch* b = new_batch(sc, KIND_ROUND2);
+    if (!b) return nullptr;
+    ReadSrc src = {cores, core_len, nullptr, nullptr};
+    if (add_round2(b, left, n_left, motif, motif_len, T, n_reads, src) || plan_batch(b)) { nr_batch_destroy(b); return nullptr; }
     return b;
 }
 
@@ -514,101 +732,14 @@ nr_batch_t* nr_batch_create_round3(const nr_scoring_t* sc, const char* left, int
                                    int32_t n_right, const char* motif, int32_t motif_len, int32_t n_reads,
                                    const char* const* cores, const int32_t* core_len, const int32_t* kmin,
                                    const int32_t* kmax) {
-    if (check_scoring(sc)) return nullptr;
-    if (n_left < 0 || n_right < 0 || motif_len <= 0 || n_reads < 0 || !motif || (n_left > 0 && !left) ||
-        (n_right > 0 && !right) || (n_reads > 0 && (!cores || !core_len || !kmin || !kmax))) {
-        fail(NR_ERR_ARG, "nr_batch_create_round3: bad arguments");
-        return nullptr;
-    }
-    if (ensure_init(-1)) return nullptr;
-    nr_batch* b = new (std::nothrow) nr_batch();
-    if (!b) { fail(NR_ERR_NOMEM, "out of host memory"); return nullptr; }
-    b->kind = KIND_ROUND3;
-    b->sc = *sc;
-    b->n_reads = n_reads;
-    b->n_left = n_left;
-    b->n_right = n_right;
-    b->motif_len = motif_len;
-    b->kmin.assign(kmin, kmin + n_reads);
-    b->kmax.assign(kmax, kmax + n_reads);
-    b->rung_off.assign(n_reads + 1, 0);
-    int klo = INT32_MAX, khi = -1;
-    for (int r = 0; r < n_reads; ++r) {
-        if (kmin[r] < 0) { fail(NR_ERR_ARG, "kmin[%d] < 0", r); nr_batch_destroy(b); return nullptr; }
-        long long n = kmax[r] >= kmin[r] ? (long long)kmax[r] - kmin[r] + 1 : 0;
-        b->rung_off[r + 1] = b->rung_off[r] + n;
-        if (n) { klo = std::min(klo, kmin[r]); khi = std::max(khi, kmax[r]); }
-    }
-    if (b->rung_off[n_reads] > 0x7fffffffLL) {
-        fail(NR_ERR_TOO_LARGE, "more than 2^31 rungs in one call");
+    if (n_reads > 0 && (!cores || !core_len)) { fail(NR_ERR_ARG, "nr_batch_create_round3: NULL reads"); return nullptr; }
+    nr_batch* b = new_batch(sc, KIND_ROUND3);
+    if (!b) return nullptr;
+    ReadSrc src = {cores, core_len, nullptr, nullptr};
+    if (add_round3(b, left, n_left, right, n_right, motif, motif_len, n_reads, src, kmin, kmax) || plan_batch(b)) {
         nr_batch_destroy(b);
         return nullptr;
     }
-    b->n_out = (size_t)b->rung_off[n_reads];
-    if (g_ladder_mode.load() != 0) {
-        // shared sweeps (nr_kernels.cuh, ladder_kernel): the pool holds left + motif^khi once and reverse(right) once
-        b->ladder = true;
-        b->lreg.n_left = n_left;
-        b->lreg.n_right = n_right;
-        b->lreg.m = motif_len;
-        std::string fwd(left ? left : "", (size_t)n_left);
-        for (int u = 0; u < std::max(khi, 0); ++u) fwd.append(motif, (size_t)motif_len);
-        std::string rev(right ? right : "", (size_t)n_right);
-        std::reverse(rev.begin(), rev.end());
-        if (add_seq(b, fwd.data(), (int)fwd.size(), "ladder prefix", 0, &b->lreg.fwd_word) ||
-            add_seq(b, rev.data(), (int)rev.size(), "right anchor", 0, &b->lreg.rev_word)) {
-            nr_batch_destroy(b);
-            return nullptr;
-        }
-        for (int r = 0; r < n_reads; ++r) {
-            if (b->rung_off[r + 1] == b->rung_off[r]) continue;
-            if (core_len[r] < 0) { fail(NR_ERR_ARG, "core %d has negative length", r); nr_batch_destroy(b); return nullptr; }
-            if (core_len[r] == 0) continue;     // every rung scores 0: d_out is zero-filled
-            nr::LadderTask t = {};
-            if (add_seq(b, cores[r], core_len[r], "core", r, &t.q_word)) { nr_batch_destroy(b); return nullptr; }
-            t.q_len = core_len[r];
-            t.kmin = kmin[r];
-            t.kmax = kmax[r];
-            t.out_off = (int32_t)b->rung_off[r];
-            b->ltasks.push_back(t);
-        }
-        if (plan_batch(b)) { nr_batch_destroy(b); return nullptr; }
-        return b;
-    }
-    // ladder templates left + motif*k + right, one per distinct k that any read uses (nanoRepeat_bam.py:478-479)
-    std::vector<uint32_t> tpl_word;
-    std::vector<uint8_t> used;
-    if (khi >= klo) {
-        used.assign(khi - klo + 1, 0);
-        for (int r = 0; r < n_reads; ++r)
-            for (int k = kmin[r]; k <= kmax[r]; ++k) used[k - klo] = 1;
-        tpl_word.assign(khi - klo + 1, 0);
-        std::string tpl;
-        for (int k = klo; k <= khi; ++k) {
-            if (!used[k - klo]) continue;
-            tpl.assign(left ? left : "", (size_t)n_left);
-            for (int u = 0; u < k; ++u) tpl.append(motif, (size_t)motif_len);
-            tpl.append(right ? right : "", (size_t)n_right);
-            if (add_seq(b, tpl.data(), (int)tpl.size(), "ladder template", k, &tpl_word[k - klo])) {
-                nr_batch_destroy(b);
-                return nullptr;
-            }
-        }
-    }
-    b->tasks.resize((size_t)b->rung_off[n_reads]);
-    for (int r = 0; r < n_reads; ++r) {
-        if (b->rung_off[r + 1] == b->rung_off[r]) continue;
-        uint32_t qw;
-        if (add_seq(b, cores[r], core_len[r], "core", r, &qw)) { nr_batch_destroy(b); return nullptr; }
-        for (int k = kmin[r]; k <= kmax[r]; ++k) {
-            nr::Task& t = b->tasks[(size_t)(b->rung_off[r] + (k - kmin[r]))];
-            t.q_word = qw;
-            t.q_len = core_len[r];
-            t.t_word = tpl_word[k - klo];
-            t.t_len = n_left + motif_len * k + n_right;
-        }
-    }
-    if (plan_batch(b)) { nr_batch_destroy(b); return nullptr; }
     return b;
 }
 
@@ -638,6 +769,7 @@ int nr_batch_fetch_round3(nr_batch_t* b, const int64_t* rung_offset, nr_rung_t* 
     if (rc) return rc;
     const int min_score = std::max(1, b->sc.min_dp_score);
     for (int r = 0; r < b->n_reads; ++r) {
+        const RegionInfo& g = b->regions[b->read_region[r]];
         const int64_t o = b->rung_off[r];
         const int n = (int)(b->rung_off[r + 1] - o);
         int top = 0;
@@ -650,15 +782,15 @@ int nr_batch_fetch_round3(nr_batch_t* b, const int64_t* rung_offset, nr_rung_t* 
         for (int i = 0; i < n; ++i) {
             const int4 a = b->h_out[o + i];
             const int k = b->kmin[r] + i;
-            const int tlen = b->n_left + b->motif_len * k + b->n_right;
-            const bool in_left = a.x > 0 && a.y < b->n_left;               // tstart < |left|  (:427)
-            const bool in_right = a.x > 0 && tlen - a.z < b->n_right;      // tlen - tend < |right|
+            const int tlen = g.n_left + g.motif_len * k + g.n_right;
+            const bool in_left = a.x > 0 && a.y < g.n_left;               // tstart < |left|  (:427)
+            const bool in_right = a.x > 0 && tlen - a.z < g.n_right;      // tlen - tend < |right|
             if (rungs) {
-                nr_rung_t& g = rungs[rung_offset[r] + i];
-                g.score = a.x;
-                g.starts_in_left = in_left;
-                g.ends_in_right = in_right;
-                g.pad[0] = g.pad[1] = 0;
+                nr_rung_t& rg = rungs[rung_offset[r] + i];
+                rg.score = a.x;
+                rg.starts_in_left = in_left;
+                rg.ends_in_right = in_right;
+                rg.pad[0] = rg.pad[1] = 0;
             }
             if (top > 0 && a.x == top && in_left && in_right) { sum += k; ++cnt; }
         }

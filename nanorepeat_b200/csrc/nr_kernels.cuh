@@ -43,10 +43,11 @@ struct LadderTask {    // 32 bytes, one per read of a round-3 region
     int32_t  q_len;
     int32_t  kmin, kmax;   // rungs of this read (kmax >= kmin >= 0)
     int32_t  out_off;      // index of rung kmin in out[]
-    int32_t  pad[3];
+    int32_t  region;       // index into the launch's LadderRegion table
+    int32_t  pad[2];
 };
 
-struct LadderRegion {  // region constants of a ladder launch
+struct LadderRegion {  // per-region constants of a ladder launch (20 bytes)
     uint32_t fwd_word;     // L + motif^K, K >= every kmax of the launch
     uint32_t rev_word;     // reverse(R)
     int32_t  n_left, n_right, m;
@@ -524,7 +525,8 @@ __device__ __forceinline__ void ladder_dispatch(int r, const LadderTask& tk, con
 template <bool MULTI>
 __global__ void __launch_bounds__(128, 4)
 ladder_kernel(const LadderTask* __restrict__ tasks, const int32_t* __restrict__ order, int n_order,
-              const uint32_t* __restrict__ pool, LadderRegion reg, ScoreW sc, int* counter, int smem_stride,
+              const uint32_t* __restrict__ pool, const LadderRegion* __restrict__ regs, ScoreW sc, int* counter,
+              int smem_stride,
               int4* scratch, long long bnd_stride, long long b_stride, long long tok_stride, int4* out) {
     extern __shared__ int4 smem[];
     const int lane = threadIdx.x & 31;
@@ -543,6 +545,7 @@ ladder_kernel(const LadderTask* __restrict__ tasks, const int32_t* __restrict__ 
         oi = __shfl_sync(kFull, oi, 0);
         if (oi >= n_order) break;
         const LadderTask tk = tasks[order[oi]];
+        const LadderRegion reg = regs[tk.region];
         int R, n_stripes;
         stripe_shape(tk.q_len, kMaxRLadder, R, n_stripes);
         ladder_dispatch<kMinR, MULTI>(R, tk, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out);

@@ -68,6 +68,13 @@ SYMBOLS = {
     "nr_batch_create_round3": (ctypes.c_void_p, [_scp, ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p,
                                                  ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
                                                  _cpp, _i32p, _i32p, _i32p]),
+    "nr_batch_begin": (ctypes.c_void_p, [_scp, ctypes.c_int32]),
+    "nr_batch_add_round2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p,
+                                           ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_char_p, _i64p]),
+    "nr_batch_add_round3": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p,
+                                           ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
+                                           ctypes.c_char_p, _i64p, _i32p, _i32p]),
+    "nr_batch_commit": (ctypes.c_int, [ctypes.c_void_p]),
     "nr_batch_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "nr_batch_fetch_alns": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "nr_batch_fetch_round3": (ctypes.c_int, [ctypes.c_void_p, _i64p, ctypes.c_void_p, _i64p, _i32p, _i32p]),
@@ -135,6 +142,22 @@ def _cstrs(seqs):
     return bs, arr, lens
 
 
+def _concat(seqs):
+    """list of str / bytes -> (one bytes buffer, int64 offsets[n + 1]): how reads cross the C ABI in bulk."""
+    n = len(seqs)
+    off = np.zeros(n + 1, dtype=np.int64)
+    if n == 0:
+        return b"", off
+    if isinstance(seqs[0], str):
+        buf = "".join(seqs).encode("ascii", "replace")     # a non-ASCII character becomes '?': NR_ERR_BAD_BASE
+    else:
+        buf = b"".join(seqs)
+    np.cumsum(np.fromiter(map(len, seqs), dtype=np.int64, count=n), out=off[1:])
+    if off[-1] != len(buf):
+        raise ValueError("mixed str / bytes reads")
+    return buf, off
+
+
 def _b(s):
     return s.encode() if isinstance(s, str) else s
 
@@ -152,16 +175,6 @@ def score_tasks(queries, targets, sc):
     return out
 
 
-def round2_region(sc, left, motif, T, cores):
-    n = len(cores)
-    out = np.zeros(n, dtype=ALN_DTYPE)
-    _cb, ca, cl = _cstrs(cores)
-    lb, mb = _b(left), _b(motif)
-    _check(lib().nr_round2_region(ctypes.byref(sc), lb, len(lb), mb, len(mb), int(T), n, ca,
-                                  cl.ctypes.data_as(_i32p), out.ctypes.data))
-    return out
-
-
 def rung_offsets(kmin, kmax):
     n_rungs = np.maximum(kmax.astype(np.int64) - kmin.astype(np.int64) + 1, 0)
     off = np.zeros(len(kmin) + 1, dtype=np.int64)
@@ -169,68 +182,74 @@ def rung_offsets(kmin, kmax):
     return off
 
 
-def round3_region(sc, left, right, motif, cores, kmin, kmax, want_rungs=False):
-    """-> (sum_k, n_k, top_score[, rungs, rung_offset])."""
-    n = len(cores)
-    kmin = np.ascontiguousarray(kmin, dtype=np.int32)
-    kmax = np.ascontiguousarray(kmax, dtype=np.int32)
-    sum_k = np.zeros(n, dtype=np.int64)
-    n_k = np.zeros(n, dtype=np.int32)
-    top = np.zeros(n, dtype=np.int32)
-    off = rung_offsets(kmin, kmax)
-    rungs = np.zeros(int(off[-1]), dtype=RUNG_DTYPE) if want_rungs else None
-    _cb, ca, cl = _cstrs(cores)
-    lb, rb, mb = _b(left), _b(right), _b(motif)
-    _check(lib().nr_round3_region(ctypes.byref(sc), lb, len(lb), rb, len(rb), mb, len(mb), n, ca,
-                                  cl.ctypes.data_as(_i32p), kmin.ctypes.data_as(_i32p), kmax.ctypes.data_as(_i32p),
-                                  off.ctypes.data_as(_i64p) if want_rungs else None,
-                                  rungs.ctypes.data if want_rungs else None,
-                                  sum_k.ctypes.data_as(_i64p), n_k.ctypes.data_as(_i32p), top.ctypes.data_as(_i32p)))
-    if want_rungs:
-        return sum_k, n_k, top, rungs, off
-    return sum_k, n_k, top
+NR_KIND_ROUND2, NR_KIND_ROUND3 = 1, 2
 
 
 class Batch:
-    """Device-resident batch: inputs packed and uploaded at construction, run() launches kernels only."""
+    """Device-resident batch over one or more regions: reads are packed and uploaded by commit(), run() launches
+    kernels only (asynchronously), fetch_*() synchronises and copies the records back."""
 
-    def __init__(self, handle, kind, n_items, keep):
+    def __init__(self, handle, kind):
         if not handle:
             raise NanoRepeatB200Error(-2, lib().nr_last_error().decode(errors="replace"))
         self._h = ctypes.c_void_p(handle)
         self.kind = kind
-        self.n_items = n_items
-        self._keep = keep
+        self.n_items = 0          # reads (round 2 / 3) or tasks
+        self._kmin, self._kmax = [], []
+
+    # ---- construction -------------------------------------------------------------------------------------
+    @classmethod
+    def begin(cls, sc, kind):
+        return cls(lib().nr_batch_begin(ctypes.byref(sc), {"round2": NR_KIND_ROUND2, "round3": NR_KIND_ROUND3}[kind]), kind)
+
+    def add_round2(self, left, motif, T, cores):
+        buf, off = _concat(cores)
+        lb, mb = _b(left), _b(motif)
+        _check(lib().nr_batch_add_round2(self._h, lb, len(lb), mb, len(mb), int(T), len(cores), buf,
+                                         off.ctypes.data_as(_i64p)))
+        self.n_items += len(cores)
+        return self
+
+    def add_round3(self, left, right, motif, cores, kmin, kmax):
+        kmin = np.ascontiguousarray(kmin, dtype=np.int32)
+        kmax = np.ascontiguousarray(kmax, dtype=np.int32)
+        if len(kmin) != len(cores) or len(kmax) != len(cores):
+            raise ValueError("kmin / kmax / cores differ in length")
+        buf, off = _concat(cores)
+        lb, rb, mb = _b(left), _b(right), _b(motif)
+        _check(lib().nr_batch_add_round3(self._h, lb, len(lb), rb, len(rb), mb, len(mb), len(cores), buf,
+                                         off.ctypes.data_as(_i64p), kmin.ctypes.data_as(_i32p),
+                                         kmax.ctypes.data_as(_i32p)))
+        self.n_items += len(cores)
+        self._kmin.append(kmin)
+        self._kmax.append(kmax)
+        return self
+
+    def commit(self):
+        _check(lib().nr_batch_commit(self._h))
+        return self
 
     @classmethod
     def tasks(cls, sc, queries, targets):
         _qb, qa, ql = _cstrs(queries)
         _tb, ta, tl = _cstrs(targets)
-        h = lib().nr_batch_create_tasks(ctypes.byref(sc), len(queries), qa, ql.ctypes.data_as(_i32p), ta,
-                                        tl.ctypes.data_as(_i32p))
-        return cls(h, "tasks", len(queries), None)
+        b = cls(lib().nr_batch_create_tasks(ctypes.byref(sc), len(queries), qa, ql.ctypes.data_as(_i32p), ta,
+                                            tl.ctypes.data_as(_i32p)), "tasks")
+        b.n_items = len(queries)
+        return b
 
     @classmethod
     def round2(cls, sc, left, motif, T, cores):
-        _cb, ca, cl = _cstrs(cores)
-        lb, mb = _b(left), _b(motif)
-        h = lib().nr_batch_create_round2(ctypes.byref(sc), lb, len(lb), mb, len(mb), int(T), len(cores), ca,
-                                         cl.ctypes.data_as(_i32p))
-        return cls(h, "round2", len(cores), None)
+        return cls.begin(sc, "round2").add_round2(left, motif, T, cores).commit()
 
     @classmethod
     def round3(cls, sc, left, right, motif, cores, kmin, kmax):
-        kmin = np.ascontiguousarray(kmin, dtype=np.int32)
-        kmax = np.ascontiguousarray(kmax, dtype=np.int32)
-        _cb, ca, cl = _cstrs(cores)
-        lb, rb, mb = _b(left), _b(right), _b(motif)
-        h = lib().nr_batch_create_round3(ctypes.byref(sc), lb, len(lb), rb, len(rb), mb, len(mb), len(cores), ca,
-                                         cl.ctypes.data_as(_i32p), kmin.ctypes.data_as(_i32p),
-                                         kmax.ctypes.data_as(_i32p))
-        return cls(h, "round3", len(cores), (kmin, kmax))
+        return cls.begin(sc, "round3").add_round3(left, right, motif, cores, kmin, kmax).commit()
 
+    # ---- execution ----------------------------------------------------------------------------------------
     def run(self, stream=None):
         _check(lib().nr_batch_run(self._h, ctypes.c_void_p(stream) if stream else None))
+        return self
 
     def fetch_alns(self):
         st = self.stats()
@@ -239,12 +258,13 @@ class Batch:
         return out
 
     def fetch_round3(self, want_rungs=False):
-        kmin, kmax = self._keep
         n = self.n_items
+        kmin = np.concatenate(self._kmin) if self._kmin else np.zeros(0, np.int32)
+        kmax = np.concatenate(self._kmax) if self._kmax else np.zeros(0, np.int32)
         sum_k = np.zeros(n, dtype=np.int64)
         n_k = np.zeros(n, dtype=np.int32)
         top = np.zeros(n, dtype=np.int32)
-        off = rung_offsets(kmin, kmax)
+        off = rung_offsets(kmin, kmax) if want_rungs else None
         rungs = np.zeros(int(off[-1]), dtype=RUNG_DTYPE) if want_rungs else None
         _check(lib().nr_batch_fetch_round3(self._h, off.ctypes.data_as(_i64p) if want_rungs else None,
                                            rungs.ctypes.data if want_rungs else None,
@@ -264,8 +284,40 @@ class Batch:
             lib().nr_batch_destroy(self._h)
             self._h = None
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
     def __del__(self):
         try:
             self.close()
         except Exception:
             pass
+
+
+def round2_regions(sc, regions):
+    """regions: iterable of (left, motif, T, cores) -> one ALN_DTYPE array over all reads, in order."""
+    with Batch.begin(sc, "round2") as b:
+        for left, motif, T, cores in regions:
+            b.add_round2(left, motif, T, cores)
+        return b.commit().run().fetch_alns()
+
+
+def round3_regions(sc, regions, want_rungs=False):
+    """regions: iterable of (left, right, motif, cores, kmin, kmax) -> (sum_k, n_k, top_score[, rungs, rung_offset])
+    over all reads, in order."""
+    with Batch.begin(sc, "round3") as b:
+        for left, right, motif, cores, kmin, kmax in regions:
+            b.add_round3(left, right, motif, cores, kmin, kmax)
+        return b.commit().run().fetch_round3(want_rungs)
+
+
+def round2_region(sc, left, motif, T, cores):
+    return round2_regions(sc, [(left, motif, T, cores)])
+
+
+def round3_region(sc, left, right, motif, cores, kmin, kmax, want_rungs=False):
+    """-> (sum_k, n_k, top_score[, rungs, rung_offset])."""
+    return round3_regions(sc, [(left, right, motif, cores, kmin, kmax)], want_rungs)

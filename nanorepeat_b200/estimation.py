@@ -20,39 +20,50 @@ def _scoring_for(data_type):
     return engine.get_preset(data_type)
 
 
+def _round2_many(data_type, repeat_regions):
+    """Rounds 1 and 2 (reference nanoRepeat_bam.py:334-393) for a list of regions, one engine launch for all."""
+    sc = _scoring_for(data_type)
+    min_score = max(1, sc.min_dp_score)
+    specs, todo = [], []
+    for rr in repeat_regions:
+        if len(rr.read_dict) == 0:
+            continue                                                            # :336
+        motif_len = len(rr.repeat_unit_seq)
+        reads = rr.read_dict
+        round1_repeat_size_list = []
+        for read in reads.values():                                             # :339-342
+            read.round1_repeat_size = r1 = float(read.dist_between_anchors) / motif_len
+            round1_repeat_size_list.append(r1)
+        max_r1 = max(round1_repeat_size_list)
+        template_repeat_size = int(max_r1 * 1.5) + 1                            # :344
+        if template_repeat_size < max_r1 + 10:                                  # :346-347
+            template_repeat_size = int(max_r1 + 10)
+        # reads come from read_core_seq_dict, which is what the reference wrote to core_sequences.fastq (:311-321)
+        core_dict = rr.read_core_seq_dict
+        qnames = [n for n in reads if n in core_dict]
+        cores = [core_dict[n].strip() for n in qnames]
+        specs.append((rr.left_anchor_seq, rr.repeat_unit_seq, template_repeat_size, cores))
+        todo.append((rr, qnames))
+    if not specs:
+        return
+    alns = engine.round2_regions(sc, specs)                                     # was pymm2.main at :362
+    pos = 0
+    for (rr, qnames), (left, motif, _T, _cores) in zip(todo, specs):
+        n, n_left = len(qnames), len(left)
+        a = alns[pos:pos + n]
+        pos += n
+        score, tstart, tend = a["score"], a["tstart"], a["tend"]
+        ok = (score >= min_score) & (tstart <= n_left) & (tend >= n_left)       # no PAF line below -s; span test :373
+        r2 = ((tend - n_left).astype(np.float64) / np.float64(len(motif))).tolist()   # :375
+        reads = rr.read_dict
+        for name, good, v in zip(qnames, ok.tolist(), r2):
+            if good:
+                reads[name].round2_repeat_size = v
+
+
 def round1_and_round2_estimation(data_type, repeat_region, num_cpu=1):
     """Rounds 1 and 2 for one region (reference nanoRepeat_bam.py:334-393)."""
-    if len(repeat_region.read_dict) == 0:
-        return                                                                  # :336
-    sc = _scoring_for(data_type)
-    motif = repeat_region.repeat_unit_seq
-    left = repeat_region.left_anchor_seq
-    names = list(repeat_region.read_dict)
-
-    round1_repeat_size_list = []
-    for read_name in names:                                                     # :339-342
-        read = repeat_region.read_dict[read_name]
-        read.round1_repeat_size = float(read.dist_between_anchors) / len(motif)
-        round1_repeat_size_list.append(read.round1_repeat_size)
-
-    template_repeat_size = int(max(round1_repeat_size_list) * 1.5) + 1           # :344
-    if template_repeat_size < max(round1_repeat_size_list) + 10:                # :346-347
-        template_repeat_size = int(max(round1_repeat_size_list) + 10)
-
-    # one engine call for the region (was pymm2.main at :362); reads come from read_core_seq_dict, which is what
-    # the reference wrote to core_sequences.fastq (:311-321)
-    qnames = [n for n in names if n in repeat_region.read_core_seq_dict]
-    cores = [repeat_region.read_core_seq_dict[n].strip() for n in qnames]
-    alns = engine.round2_region(sc, left, motif, template_repeat_size, cores)
-
-    n_left = len(left)
-    min_score = max(1, sc.min_dp_score)
-    for read_name, a in zip(qnames, alns):
-        score, tstart, tend = int(a["score"]), int(a["tstart"]), int(a["tend"])
-        if score < min_score:
-            continue                                                            # minimap2 prints no line
-        if tstart <= n_left and tend >= n_left:                                 # :373
-            repeat_region.read_dict[read_name].round2_repeat_size = float(tend - n_left) / len(motif)   # :375
+    _round2_many(data_type, [repeat_region])
     return
 
 
@@ -70,6 +81,19 @@ def ladder_bounds(round2_repeat_size, fast_mode):
     return min_template_repeat_size, max_template_repeat_size
 
 
+def ladder_bounds_array(r2, fast_mode):
+    """ladder_bounds over a float64 array.  Same IEEE double arithmetic; np.trunc + cast is Python's int() for these
+    magnitudes (tests/test_host.py checks equality with the scalar form)."""
+    r2 = np.asarray(r2, dtype=np.float64)
+    buf = np.maximum(15, np.trunc(r2 * 0.05).astype(np.int64))
+    buf = np.minimum(buf, 150)
+    if fast_mode:
+        buf = np.full_like(buf, 15)
+    kmax = np.trunc(r2 + buf).astype(np.int64)
+    kmin = np.maximum(np.trunc(r2 - buf).astype(np.int64), 0)
+    return kmin.astype(np.int32), kmax.astype(np.int32)
+
+
 def round3_estimation_for1read(read, n_k, sum_k, top_score, best_k_list=None):
     """Reference nanoRepeat_bam.py:408-434 on the binary record instead of PAF text."""
     if top_score <= 0:
@@ -83,46 +107,60 @@ def round3_estimation_for1read(read, n_k, sum_k, top_score, best_k_list=None):
         read.round3_repeat_size = read.round2_repeat_size                       # :433
 
 
-def round3_estimation(data_type, fast_mode, repeat_region, num_cpu=1):
-    """Round 3 for one region (reference nanoRepeat_bam.py:446-450)."""
+def _round3_many(data_type, fast_mode, repeat_regions):
+    """Round 3 (reference nanoRepeat_bam.py:446-500 + :408-434) for a list of regions, one engine launch for all."""
     sc = _scoring_for(data_type)
-    names, cores, kmin, kmax = [], [], [], []
-    for read_name in repeat_region.read_dict:                                   # :457-472
-        read = repeat_region.read_dict[read_name]
-        if read.round2_repeat_size is None:
+    specs, todo = [], []
+    for rr in repeat_regions:
+        reads, r2, cores = [], [], []
+        core_dict = rr.read_core_seq_dict
+        for read_name, read in rr.read_dict.items():                            # :457-461
+            if read.round2_repeat_size is None:
+                continue
+            reads.append(read)
+            r2.append(read.round2_repeat_size)
+            cores.append(core_dict[read_name].strip())                          # :487-491
+        if not reads:
             continue
-        lo, hi = ladder_bounds(read.round2_repeat_size, fast_mode)
-        names.append(read_name)
-        cores.append(repeat_region.read_core_seq_dict[read_name].strip())
-        kmin.append(lo)
-        kmax.append(hi)
-    if not names:
+        kmin, kmax = ladder_bounds_array(r2, fast_mode)                         # :463-472
+        specs.append((rr.left_anchor_seq, rr.right_anchor_seq, rr.repeat_unit_seq, cores, kmin, kmax))
+        todo.append(reads)
+    if not specs:
         return
-    sum_k, n_k, top = engine.round3_region(
-        sc, repeat_region.left_anchor_seq, repeat_region.right_anchor_seq, repeat_region.repeat_unit_seq,
-        cores, np.asarray(kmin, dtype=np.int32), np.asarray(kmax, dtype=np.int32))
+    sum_k, n_k, top = engine.round3_regions(sc, specs)                          # was pymm2.main per read at :497
     # np.mean(list of k) == float64(sum k) / n exactly: the k are small integers, so every partial sum is an
     # exactly representable float64 and numpy's pairwise summation cannot round (tests/test_host.py checks it)
     with np.errstate(invalid="ignore", divide="ignore"):
         mean_k = sum_k.astype(np.float64) / n_k.astype(np.float64)
-    for i, read_name in enumerate(names):
-        read = repeat_region.read_dict[read_name]
-        if top[i] <= 0:
-            continue                                                            # no PAF line at all (:421)
-        if n_k[i] > 0:
-            read.round3_repeat_size = mean_k[i]                                 # :431
-        else:
-            read.round3_repeat_size = read.round2_repeat_size                   # :433
+    state = np.where(top <= 0, 0, np.where(n_k > 0, 1, 2)).tolist()
+    pos = 0
+    for reads in todo:
+        for i, read in enumerate(reads, pos):
+            s = state[i]
+            if s == 1:
+                read.round3_repeat_size = mean_k[i]                             # :431 (np.float64, like np.mean)
+            elif s == 2:
+                read.round3_repeat_size = read.round2_repeat_size               # :433
+            # s == 0: no PAF line at all (:421) -> untouched
+        pos += len(reads)
+
+
+def round3_estimation(data_type, fast_mode, repeat_region, num_cpu=1):
+    """Round 3 for one region (reference nanoRepeat_bam.py:446-450)."""
+    _round3_many(data_type, fast_mode, [repeat_region])
     return
 
 
 def estimate_regions(regions, data_type=None, fast_mode=False):
-    """Convenience driver: rounds 1-3 over a list of RepeatRegion-like objects (the reference runs this per
-    region inside quantify1repeat_from_bam, nanoRepeat_bam.py:675-679)."""
+    """Rounds 1-3 over a list of RepeatRegion-like objects with ONE engine launch per round for all of them (the
+    reference runs the two operators per region inside quantify1repeat_from_bam, nanoRepeat_bam.py:675-679).
+    Regions may carry their own .data_type; regions of one data type are batched together."""
+    groups = {}
     for rr in regions:
-        dt = data_type or getattr(rr, "data_type", "ont")
-        round1_and_round2_estimation(dt, rr, 1)
-        round3_estimation(dt, fast_mode, rr, 1)
+        groups.setdefault(data_type or getattr(rr, "data_type", None) or "ont", []).append(rr)
+    for dt, rrs in groups.items():
+        _round2_many(dt, rrs)
+        _round3_many(dt, fast_mode, rrs)
     return regions
 
 

@@ -197,6 +197,29 @@ def test_ladder_shared_sweeps_equal_independent_rectangles(engine, oracle, seed,
     _assert_same(got[1], ref, f"shared sweeps, seed {seed}")
 
 
+def test_multi_region_batches_equal_per_region_calls(engine):
+    """estimate_regions (one launch per round over all regions) == the two operators called region by region."""
+    import nanorepeat_b200 as nrb
+    from nanorepeat_b200 import synth
+    regs = synth.config1(seed=11, n_regions=6, reads_per_region=12) + synth.config3(seed=12, n_loci=5, reads_per_locus=9)
+    one = [nrb.RepeatRegion.from_synth(r) for r in regs]
+    for reg, rr in zip(regs, one):
+        nrb.round1_and_round2_estimation(reg.data_type, rr, 1)
+        nrb.round3_estimation(reg.data_type, False, rr, 1)
+    many = [nrb.RepeatRegion.from_synth(r) for r in regs]
+    for reg, rr in zip(regs, many):
+        rr.data_type = reg.data_type
+    nrb.estimate_regions(many)
+    n_r3 = 0
+    for a, b in zip(one, many):
+        for name in a.read_dict:
+            ra, rb = a.read_dict[name], b.read_dict[name]
+            assert (ra.round1_repeat_size, ra.round2_repeat_size) == (rb.round1_repeat_size, rb.round2_repeat_size)
+            assert ra.round3_repeat_size == rb.round3_repeat_size and type(ra.round3_repeat_size) is type(rb.round3_repeat_size)
+            n_r3 += ra.round3_repeat_size is not None
+    assert n_r3 > 100
+
+
 def test_ladder_long_expanded_allele(engine, oracle):
     """cfg4-like FMR1 shape: multi-stripe read, 1000-bp anchors, a +/-25 ladder around 500 units."""
     from nanorepeat_b200 import synth

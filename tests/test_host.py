@@ -43,6 +43,29 @@ def test_ladder_bounds_equal_oracle_restatement():
             assert ladder_bounds(float(v), fast) == selection.ladder_bounds(float(v), fast)
 
 
+def test_vectorised_ladder_bounds_equal_scalar_form():
+    from nanorepeat_b200.estimation import ladder_bounds, ladder_bounds_array
+    rng = np.random.default_rng(1)
+    vals = np.concatenate([rng.uniform(-1, 3300, size=20000), np.arange(0, 3200, 1 / 3.0),
+                           np.array([0.0, 14.999999999999998, 15.0, 299.99999999999994, 300.0, 3000.0, 3019.9999999999995])])
+    for fast in (False, True):
+        lo, hi = ladder_bounds_array(vals, fast)
+        exp = [ladder_bounds(float(v), fast) for v in vals]
+        assert lo.tolist() == [e[0] for e in exp] and hi.tolist() == [e[1] for e in exp]
+
+
+def test_concat_reads_layout():
+    from nanorepeat_b200 import engine
+    buf, off = engine._concat(["ACG", "", "TTGA"])
+    assert buf == b"ACGTTGA" and off.tolist() == [0, 3, 3, 7]
+    buf, off = engine._concat([b"AC", b"G"])
+    assert buf == b"ACG" and off.tolist() == [0, 2, 3]
+    buf, off = engine._concat([])
+    assert buf == b"" and off.tolist() == [0]
+    buf, off = engine._concat(["AC\u00e9T"])
+    assert buf == b"AC?T" and off.tolist() == [0, 4]
+
+
 def test_empty_region_is_a_no_op():
     import nanorepeat_b200 as nrb
     rr = nrb.RepeatRegion()
