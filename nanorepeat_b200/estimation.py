@@ -35,6 +35,8 @@ def _round2_many(data_type, repeat_regions):
             read.round1_repeat_size = r1 = float(read.dist_between_anchors) / motif_len
             round1_repeat_size_list.append(r1)
         max_r1 = max(round1_repeat_size_list)
+        if getattr(rr, "round1_max_dist", None) is not None:                    # a piece of a split region
+            max_r1 = max(max_r1, float(rr.round1_max_dist) / motif_len)         # (sharding.split_region): T is region-wide
         template_repeat_size = int(max_r1 * 1.5) + 1                            # :344
         if template_repeat_size < max_r1 + 10:                                  # :346-347
             template_repeat_size = int(max_r1 + 10)

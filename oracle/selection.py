@@ -10,10 +10,13 @@ import numpy as np
 from . import nr_oracle
 
 
-def round1(dist_between_anchors, motif_len):
-    """nanoRepeat_bam.py:338-347 -> (r1 list of float, template_repeat_size T)."""
+def round1(dist_between_anchors, motif_len, max_dist=None):
+    """nanoRepeat_bam.py:338-347 -> (r1 list of float, template_repeat_size T).
+    max_dist: the whole region's longest dist_between_anchors when the reads are one piece of a split region."""
     r1 = [float(d) / motif_len for d in dist_between_anchors]
     mx = max(r1)
+    if max_dist is not None:
+        mx = max(mx, float(max_dist) / motif_len)
     T = int(mx * 1.5) + 1
     if T < mx + 10:
         T = int(mx + 10)
@@ -67,14 +70,14 @@ def round3_select(rungs, kmin, n_left, n_right, motif_len, r2, min_dp_score):
     return r2
 
 
-def estimate_region(left, right, motif, cores, dists, fast_mode=False, sc=None, n_threads=1):
+def estimate_region(left, right, motif, cores, dists, fast_mode=False, sc=None, n_threads=1, max_dist=None):
     """Rounds 1-3 for one region -> dict of per-read lists r1, r2, r3, plus T and the ladders."""
     sc = sc or nr_oracle.scoring()
     n = len(cores)
     if n == 0:
         return dict(r1=[], r2=[], r3=[], T=None, kmin=[], kmax=[])
     m = len(motif)
-    r1, T = round1(dists, m)
+    r1, T = round1(dists, m, max_dist)
     tpl = left + motif * T
     a2 = nr_oracle.align_batch(cores, [tpl] * n, sc, n_threads)
     r2 = [round2_select(a2[i], len(left), m, sc.min_dp_score) for i in range(n)]

@@ -220,6 +220,27 @@ def test_multi_region_batches_equal_per_region_calls(engine):
     assert n_r3 > 100
 
 
+def test_sharded_pieces_equal_unsharded(engine):
+    """Region splitting + dealing to 4 ranks (run one after the other here) gives every read the same numbers as the
+    unsharded call: T is pinned region-wide, results do not depend on batch composition."""
+    import nanorepeat_b200 as nrb
+    from nanorepeat_b200 import synth, sharding
+    regs = synth.config1(seed=21, n_regions=4, reads_per_region=11) + synth.config2(seed=22, n_reads=23)
+    whole = [nrb.RepeatRegion.from_synth(r) for r in regs]
+    nrb.estimate_regions(whole, "ont", False)
+    parts = [nrb.RepeatRegion.from_synth(r) for r in regs]
+    seen = []
+    for rank in range(4):
+        seen += sharding.estimate_regions_sharded(parts, "ont", False, max_reads_per_piece=5, rank=rank, world_size=4,
+                                                  gather=False)
+    assert sorted(seen) == list(range(len(seen))) and len(seen) > len(regs)
+    for a, b in zip(whole, parts):
+        for name in a.read_dict:
+            ra, rb = a.read_dict[name], b.read_dict[name]
+            assert (ra.round1_repeat_size, ra.round2_repeat_size, ra.round3_repeat_size) == \
+                   (rb.round1_repeat_size, rb.round2_repeat_size, rb.round3_repeat_size), name
+
+
 def test_ladder_long_expanded_allele(engine, oracle):
     """cfg4-like FMR1 shape: multi-stripe read, 1000-bp anchors, a +/-25 ladder around 500 units."""
     from nanorepeat_b200 import synth
