@@ -47,8 +47,8 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 constexpr int kMaxScore = 32767;   // signed 16-bit score field of the packed DP word
-constexpr int kMaxTlen = 65535;    // unsigned 16-bit span field
-constexpr int kWarpsPerBlock = 4;
+constexpr int kMaxTlen = 65535 - 64; // unsigned 16-bit span field, minus the wavefront skew (step counters share it)
+using nr::kWarpsPerBlock;
 
 // ---- context + caching allocator -----------------------------------------------------------------------------
 // Batches come and go once per region (or per group of regions); cudaMalloc / cudaMallocHost / cudaFree cost far
@@ -67,11 +67,7 @@ struct Context {
     int device = -1;
     int sm_count = 0;
     int clock_khz = 0;
-    int blocks_per_sm = 4;
-    bool fork_long = true;
     cudaStream_t stream = nullptr;
-    cudaStream_t side = nullptr;          // the multi-stripe (long task) launch runs here, beside the main launch
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     BufCache cache;
 };
 Context g_ctx;
@@ -99,14 +95,9 @@ int ensure_init(int device) {
         return fail(NR_ERR_CUDA, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 part", device, prop.name,
                     prop.major, prop.minor);
     CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.side, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreateWithFlags(&g_ctx.ev_fork, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&g_ctx.ev_join, cudaEventDisableTiming));
     g_ctx.device = device;
     g_ctx.sm_count = prop.multiProcessorCount;
     g_ctx.clock_khz = prop.clockRate;
-    if (const char* e = getenv("NR_FORK_LONG")) g_ctx.fork_long = atoi(e) != 0;
-    if (const char* e = getenv("NR_BLOCKS_PER_SM")) g_ctx.blocks_per_sm = std::max(1, std::min(4, atoi(e)));
     g_ctx.ready = true;
     return NR_OK;
 }
@@ -142,7 +133,7 @@ struct CodeTable {
 };
 const CodeTable g_codes;
 
-// Sequence pool: 16 bases per 32-bit word, base i of a sequence at bits 2*(i%16) of word i/16.  Every sequence
+// Sequence pool: 16 bases per 32-bit word, MSB first: base i of a sequence at bits 30 - 2*(i%16) of word i/16.  Every sequence
 // starts on a word boundary and is followed by one zero slack word (kernels prefetch one word ahead).
 struct Pool {
     std::vector<uint32_t> words;
@@ -160,7 +151,7 @@ struct Pool {
             for (int j = 0; j < 16; ++j) {
                 const unsigned c = g_codes.t[u[i + j]];
                 bad |= c;
-                v |= (c & 3u) << (2 * j);
+                v |= (c & 3u) << (30 - 2 * j);
             }
             w[i >> 4] = v;
         }
@@ -169,7 +160,7 @@ struct Pool {
             for (int j = 0; i + j < len; ++j) {
                 const unsigned c = g_codes.t[u[i + j]];
                 bad |= c;
-                v |= (c & 3u) << (2 * j);
+                v |= (c & 3u) << (30 - 2 * j);
             }
             w[i >> 4] = v;
         }
@@ -178,17 +169,16 @@ struct Pool {
     }
 };
 
-struct Bucket {
-    bool multi;      // tasks with several stripes (boundary rows through L2 scratch)
+struct Launch {      // one persistent launch per batch
     bool ladder;     // ladder_kernel over nr_batch::ltasks instead of exact_kernel over nr_batch::tasks
     int R;           // tallest stripe of the launch: sizes the shared memory per warp
-    int order_off;   // offset into the order array
     int count;
+    int n_excl;      // leading multi-stripe tasks that get a scheduler each (nr_kernels.cuh, TaskCursor)
     int blocks;
-    long long scratch_stride;   // int4 per boundary row (multi only)
-    long long b_stride;         // ladder + multi: int4 of backward junction vectors per warp
-    long long tok_stride;       // ladder + multi: ulonglong2 per token row
-    size_t scratch_off;         // int4 offset into d_scratch
+    bool fixed;      // scoring == map-ont: kernels with immediate constants
+    long long scratch_stride;   // int4 per boundary row (multi-stripe tasks only; 0: the batch has none)
+    long long b_stride;         // ladder: int4 of backward junction vectors per warp
+    long long tok_stride;       // ladder: ulonglong2 per token row
 };
 
 struct RegionInfo {   // one add_round2 / add_round3 call
@@ -210,7 +200,7 @@ struct nr_batch {
     bool ladder = false;
     size_t n_out = 0;                         // records in d_out / h_out
     std::vector<int32_t> order;
-    std::vector<Bucket> buckets;
+    Launch launch = {};
     Pool pool;
     // per-read bookkeeping (rounds 2 and 3)
     std::vector<RegionInfo> regions;
@@ -239,11 +229,6 @@ struct nr_batch {
 };
 
 namespace {
-
-typedef void (*ExactKernel)(const nr::Task*, const int32_t*, int, const uint32_t*, nr::ScoreW, int*, int, int4*,
-                            long long, int4*);
-typedef void (*LadderKernel)(const nr::LadderTask*, const int32_t*, int, const uint32_t*, const nr::LadderRegion*,
-                             nr::ScoreW, int*, int, int4*, long long, long long, long long, int4*);
 
 // shared memory per warp, in int4: query profile (+ backward junction vectors for the ladder kernel)
 int exact_smem_int4(int R) { return 4 * ((R + 3) / 4) * 32; }
@@ -274,6 +259,9 @@ nr::ScoreW score_words(const nr_scoring_t& sc) {
     k.v_ext2 = -(sc.gap_ext2 << 16);
     k.refund1 = sc.gap_open1 << 16;
     k.refund2 = sc.gap_open2 << 16;
+    k.one = 1;
+    k.mone = -1;
+    k.four = 4u;
     return k;
 }
 
@@ -286,11 +274,11 @@ int plan_batch(nr_batch* b) {
     if (b->kind != KIND_ROUND3) b->n_out = b->tasks.size();
     b->stats = {};
     b->stats.n_tasks = (int64_t)b->n_out;
-    std::vector<uint8_t> shapeM(n);
     std::vector<long long> cost(n);
     const int max_r = ladder ? nr::kMaxRLadder : nr::kMaxRExact;
+    int rmax = 0, tmax = 0, qmax = 0, rungs_max = 0;      // tmax, qmax, rungs_max: over multi-stripe tasks only
     int n_multi = 0;
-    int rmax[2] = {0, 0}, tmax[2] = {0, 0}, qmax[2] = {0, 0}, rungs_max[2] = {0, 0};
+    long long min_multi_cost = 0, max_single_cost = 0;
     for (int i = 0; i < n; ++i) {
         int q_len, t_len, t_sweep, rungs = 0;
         if (ladder) {
@@ -316,46 +304,46 @@ int plan_batch(nr_batch* b) {
                         q_len, t_len, kMaxScore, kMaxTlen);
         int R, ns;
         nr::stripe_shape(q_len, max_r, R, ns);
-        const int mi = ns > 1;
-        shapeM[i] = (uint8_t)mi;
-        n_multi += mi;
-        rmax[mi] = std::max(rmax[mi], R);
-        tmax[mi] = std::max(tmax[mi], t_sweep);
-        qmax[mi] = std::max(qmax[mi], ns * 32 * R);
-        rungs_max[mi] = std::max(rungs_max[mi], rungs);
+        rmax = std::max(rmax, R);
         cost[i] = (long long)ns * 32 * R * t_len;
+        if (ns > 1) {
+            tmax = std::max(tmax, t_sweep);
+            qmax = std::max(qmax, ns * 32 * R);
+            rungs_max = std::max(rungs_max, rungs);
+            min_multi_cost = n_multi ? std::min(min_multi_cost, cost[i]) : cost[i];
+            ++n_multi;
+        } else {
+            max_single_cost = std::max(max_single_cost, cost[i]);
+        }
         b->stats.executed_cells += cost[i];
     }
-    // one launch per (single-stripe | multi-stripe) group, tasks in decreasing cost so the tail is short
+    // one persistent launch; tasks in decreasing cost (long multi-stripe tasks first) so the tail is short
     b->order.resize(n);
-    b->buckets.clear();
+    for (int i = 0; i < n; ++i) b->order[i] = i;
+    std::sort(b->order.begin(), b->order.end(),
+              [&](int x, int y) { return cost[x] != cost[y] ? cost[x] > cost[y] : x < y; });
+    Launch& L = b->launch;
+    L = {};
+    L.ladder = ladder;
+    L.R = rmax;
+    L.count = n;
+    L.blocks = std::max(1, std::min(g_ctx.sm_count, n));       // one persistent block per SM; a small batch still spreads
+    // the long tasks run alone on a scheduler when they are few and really lead the cost order
+    L.n_excl = (n_multi > 0 && n_multi < n && n_multi <= nr::kExclusiveWarps * L.blocks && min_multi_cost >= max_single_cost)
+                   ? n_multi : 0;
     {
-        int fill[2] = {0, n - n_multi};
-        for (int i = 0; i < n; ++i) b->order[fill[shapeM[i]]++] = i;
+        const nr_scoring_t& c = b->sc;
+        L.fixed = c.match == 2 && c.mismatch == 4 && c.gap_open1 == 4 && c.gap_ext1 == 2 && c.gap_open2 == 24 &&
+                  c.gap_ext2 == 1;
     }
     size_t scratch_total = 0;
-    for (int mi = 0; mi < 2; ++mi) {
-        Bucket bk = {};
-        bk.ladder = ladder;
-        bk.multi = mi == 1;
-        bk.R = rmax[mi];
-        bk.order_off = mi ? n - n_multi : 0;
-        bk.count = mi ? n_multi : n - n_multi;
-        if (!bk.count) continue;
-        std::sort(b->order.begin() + bk.order_off, b->order.begin() + bk.order_off + bk.count,
-                  [&](int x, int y) { return cost[x] != cost[y] ? cost[x] > cost[y] : x < y; });
-        bk.blocks = std::min(g_ctx.sm_count * g_ctx.blocks_per_sm, (bk.count + kWarpsPerBlock - 1) / kWarpsPerBlock);
-        if (bk.multi) {
-            bk.scratch_stride = ((long long)tmax[mi] + 63) / 32 * 32;
-            if (ladder) {
-                bk.b_stride = qmax[mi];
-                bk.tok_stride = rungs_max[mi];
-            }
-            bk.scratch_off = scratch_total;
-            scratch_total += (size_t)bk.blocks * kWarpsPerBlock *
-                             (size_t)(2 * bk.scratch_stride + bk.b_stride + 2 * bk.tok_stride);
+    if (tmax > 0) {
+        L.scratch_stride = ((long long)tmax + 63) / 32 * 32;
+        if (ladder) {
+            L.b_stride = qmax;
+            L.tok_stride = rungs_max;
         }
-        b->buckets.push_back(bk);
+        scratch_total = (size_t)L.blocks * kWarpsPerBlock * (size_t)(2 * L.scratch_stride + L.b_stride + 2 * L.tok_stride);
     }
     // ---- one device blob: [tasks | regions | order | pool (+4 slack words) | counters], staged in pinned memory ----
     const size_t task_bytes = ladder ? sizeof(nr::LadderTask) * n : sizeof(nr::Task) * n;
@@ -402,52 +390,28 @@ int plan_batch(nr_batch* b) {
 int run_batch(nr_batch* b, cudaStream_t st) {
     if (!b->committed) return fail(NR_ERR_ARG, "batch was not committed");
     b->run_stream = st;
-    if (b->buckets.empty()) { b->ran = true; return NR_OK; }
+    const Launch& L = b->launch;
+    if (!L.count) { b->ran = true; return NR_OK; }
     const nr::ScoreW k = score_words(b->sc);
-    CUDA_TRY(cudaMemsetAsync(b->d_counters, 0, sizeof(int) * b->buckets.size(), st));
-    int launches = 0;
-    // a few long multi-stripe tasks next to many short ones: the long-task launch goes to a side stream (forked from
-    // and joined back into `st`) so its tail hides behind the main launch
-    const bool fork = b->buckets.size() == 2 && g_ctx.fork_long;
-    if (fork) {
-        CUDA_TRY(cudaEventRecord(g_ctx.ev_fork, st));
-        CUDA_TRY(cudaStreamWaitEvent(g_ctx.side, g_ctx.ev_fork, 0));
+    CUDA_TRY(cudaMemsetAsync(b->d_counters, 0, sizeof(int), st));
+    if (L.ladder) {
+        auto fn = L.fixed ? nr::ladder_kernel<true> : nr::ladder_kernel<false>;
+        const int stride = ladder_smem_int4(L.R);
+        const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
+        CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fn<<<L.blocks, kWarpsPerBlock * 32, smem, st>>>(b->d_ltasks, b->d_order, L.count, L.n_excl, b->d_pool, b->d_lregs, k,
+                                                       b->d_counters, stride, b->d_scratch, L.scratch_stride,
+                                                       L.b_stride, L.tok_stride, b->d_out);
+    } else {
+        auto fn = L.fixed ? nr::exact_kernel<true> : nr::exact_kernel<false>;
+        const int stride = exact_smem_int4(L.R);
+        const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
+        CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fn<<<L.blocks, kWarpsPerBlock * 32, smem, st>>>(b->d_tasks, b->d_order, L.count, L.n_excl, b->d_pool, k,
+                                                       b->d_counters, stride, b->d_scratch, L.scratch_stride, b->d_out);
     }
-    cudaStream_t main_st = st;
-    for (size_t i = b->buckets.size(); i-- > 0;) {      // multi-stripe bucket (last) first
-        const Bucket& bk = b->buckets[i];
-        st = (fork && bk.multi) ? g_ctx.side : main_st;
-        int4* scratch = bk.multi ? b->d_scratch + bk.scratch_off : nullptr;
-        if (bk.ladder) {
-            LadderKernel fn = bk.multi ? (LadderKernel)nr::ladder_kernel<true> : (LadderKernel)nr::ladder_kernel<false>;
-            const int stride = ladder_smem_int4(bk.R);
-            const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
-            CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                          cudaSharedmemCarveoutMaxShared));
-            fn<<<bk.blocks, kWarpsPerBlock * 32, smem, st>>>(b->d_ltasks, b->d_order + bk.order_off, bk.count,
-                                                            b->d_pool, b->d_lregs, k, b->d_counters + i, stride,
-                                                            scratch, bk.scratch_stride, bk.b_stride, bk.tok_stride,
-                                                            b->d_out);
-        } else {
-            ExactKernel fn = bk.multi ? (ExactKernel)nr::exact_kernel<true> : (ExactKernel)nr::exact_kernel<false>;
-            const int stride = exact_smem_int4(bk.R);
-            const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
-            CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                          cudaSharedmemCarveoutMaxShared));
-            fn<<<bk.blocks, kWarpsPerBlock * 32, smem, st>>>(b->d_tasks, b->d_order + bk.order_off, bk.count,
-                                                            b->d_pool, k, b->d_counters + i, stride, scratch,
-                                                            bk.scratch_stride, b->d_out);
-        }
-        CUDA_TRY(cudaGetLastError());
-        ++launches;
-    }
-    if (fork) {
-        CUDA_TRY(cudaEventRecord(g_ctx.ev_join, g_ctx.side));
-        CUDA_TRY(cudaStreamWaitEvent(main_st, g_ctx.ev_join, 0));
-    }
-    b->stats.kernel_launches = launches;
+    CUDA_TRY(cudaGetLastError());
+    b->stats.kernel_launches = 1;
     b->ran = true;
     return NR_OK;
 }
@@ -640,9 +604,6 @@ int nr_shutdown(void) {
         for (auto& kv : g_ctx.cache.free_dev) for (void* p : kv.second) cudaFree(p);
         for (auto& kv : g_ctx.cache.free_pin) for (void* p : kv.second) cudaFreeHost(p);
         cudaStreamDestroy(g_ctx.stream);
-        cudaStreamDestroy(g_ctx.side);
-        cudaEventDestroy(g_ctx.ev_fork);
-        cudaEventDestroy(g_ctx.ev_join);
         g_ctx = Context();
     }
     return NR_OK;

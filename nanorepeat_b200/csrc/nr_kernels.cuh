@@ -58,6 +58,26 @@ struct ScoreW {        // scoring constants as W32 increments
     int h_open1, h_ext1, h_open2, h_ext2;    // horizontal gap: -((q + e) << 16) - 1, -(e << 16) - 1
     int v_open1, v_ext1, v_open2, v_ext2;    // vertical gap:   -((q + e) << 16),     -(e << 16)
     int refund1, refund2;                    // q << 16, q2 << 16: a gap that spans a junction pays its opening once
+    int one, mone;                           // 1, -1 and 4, passed as kernel parameters so that ptxas cannot fold them:
+    unsigned four;                           // adds written as a * one + b issue as IMAD on the FMA pipe, beside the DPX pipe
+};
+
+// Device-side view of the scoring constants.  FIXED = the reference's only scoring (tk.py:502-517: all five data types
+// map to minimap2's map-ont: +2 / -4 / 4,2 / 24,1): the constants become immediates of the DPX instructions, which
+// frees the register-operand slots (measured +7 %, tools/microbench/cell_chain.cu).  Otherwise they come from the
+// kernel parameter.
+template <bool FIXED> struct ScoreView;
+template <> struct ScoreView<false> : ScoreW {
+    __device__ __forceinline__ explicit ScoreView(const ScoreW& w) : ScoreW(w) {}
+};
+template <> struct ScoreView<true> {
+    static constexpr int sub_match = (2 << 16) - 1, sub_mismatch = -(4 << 16) - 1;
+    static constexpr int h_open1 = -(6 << 16) - 1, h_ext1 = -(2 << 16) - 1, h_open2 = -(25 << 16) - 1, h_ext2 = -(1 << 16) - 1;
+    static constexpr int v_open1 = -(6 << 16), v_ext1 = -(2 << 16), v_open2 = -(25 << 16), v_ext2 = -(1 << 16);
+    static constexpr int refund1 = 4 << 16, refund2 = 24 << 16;
+    int one, mone;
+    unsigned four;
+    __device__ __forceinline__ explicit ScoreView(const ScoreW& w) : one(w.one), mone(w.mone), four(w.four) {}
 };
 
 constexpr int kPadScore = -(16384 << 16);   // substitution score of rows below the query's end / void junction state
@@ -67,24 +87,42 @@ typedef unsigned long long u64;
 
 __device__ __forceinline__ int w_cap(int w) { return (w + 0xffff) & (int)0xffff0000; }   // score(w) << 16, any sign
 
-// One DP cell.  hd: H(i-1, j-1); s: substitution increment; e1/e2: E(i, j); f1/f2: F(i, j).
+// a * mul + b as one IMAD (FMA pipe).  The DPX instructions (VIMNMX3, VIADDMNMX) issue on the ALU pipe at 64 lanes
+// per clock per SM and so would plain integer adds; with the adds on the other pipe the cell is 6 ALU + 5 FMA slots.
+__device__ __forceinline__ int madd(int a, int mul, int b) {
+    int d;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(mul), "r"(b));
+    return d;
+}
+
+// One DP cell.  hd: H(i-1, j-1), taken times dmul (1, or 0 for the first row of a lane whose upper neighbour is the
+// matrix border); s: substitution increment; e1/e2: E(i, j); f1/f2: F(i, j).
 // On return h = H(i, j), e1/e2 = E(i, j+1), f1/f2 = F(i+1, j).
-__device__ __forceinline__ void cell_w32(int hd, int s, const ScoreW& sc, int& h, int& e1, int& e2, int& f1, int& f2) {
-    const int t = __vimax3_s32(hd + s, e1, e2);
+template <class SC>
+__device__ __forceinline__ void cell_w32(int hd, int dmul, int s, const SC& sc, int& h, int& e1, int& e2, int& f1,
+                                         int& f2) {
+    const int t = __vimax3_s32(madd(hd, dmul, s), e1, e2);
     h = __vimax3_s32_relu(t, f1, f2);        // vertical gaps last: they carry the row-to-row dependency
-    e1 = __viaddmax_s32(h, sc.h_open1, e1 + sc.h_ext1);
-    e2 = __viaddmax_s32(h, sc.h_open2, e2 + sc.h_ext2);
-    f1 = __viaddmax_s32(h, sc.v_open1, f1 + sc.v_ext1);
-    f2 = __viaddmax_s32(h, sc.v_open2, f2 + sc.v_ext2);
+    e1 = __viaddmax_s32(h, sc.h_open1, madd(e1, sc.one, sc.h_ext1));
+    e2 = __viaddmax_s32(h, sc.h_open2, madd(e2, sc.one, sc.h_ext2));
+    f1 = __viaddmax_s32(h, sc.v_open1, madd(f1, sc.one, sc.v_ext1));
+    f2 = __viaddmax_s32(h, sc.v_open2, madd(f2, sc.one, sc.v_ext2));
 }
 
 // Junction candidate: forward word wf (score_f, span) joined with backward word wb (score_b, ext).
-// (bhi, blo) keeps the lexicographic best of (score_f + score_b, -ext, -span).
-__device__ __forceinline__ void jcand(int wf, int wb, int& bhi, int& blo) {
-    const int sfs = w_cap(wf);
-    const int klo = wf - sfs;      // -span
-    const int khi = sfs + wb;      // (score_f + score_b) << 16 - ext
-    if (khi > bhi || (khi == bhi && klo > blo)) { bhi = khi; blo = klo; }
+// (bhi, blo) keeps the lexicographic best of (score_f + score_b, -ext, -span), both biased by a constant
+// (bhi by -1, blo by +1: the cap is taken as (wf - 1) | 0xffff = cap - 1, one LOP3); junction_unbias() undoes it.
+template <class SC>
+__device__ __forceinline__ void jcand(int wf, int wb, const SC& sc, int& bhi, int& blo) {
+    const int cf = madd(wf, sc.one, -1) | 0xffff;       // (score_f << 16) - 1
+    const int khi = madd(cf, sc.one, wb);                // ((score_f + score_b) << 16) - ext - 1
+    const int klo = madd(cf, sc.mone, wf);               // -span + 1
+    if (khi > bhi) { bhi = khi; blo = klo; }
+    else if (khi == bhi) blo = max(blo, klo);
+}
+constexpr int kJuncNone = (int)0x80000000;              // bhi of "no candidate yet"
+__device__ __forceinline__ void junction_unbias(int& bhi, int& blo) {
+    if (bhi == kJuncNone) { bhi = 0; blo = 0; } else { bhi += 1; blo -= 1; }
 }
 
 // (best word, its column) -> 64-bit key ordered like the contract: score desc, tend asc, tstart desc.
@@ -146,9 +184,9 @@ struct StripeCfg {
 
 // Build the stripe's query profile: prof[(c * CH + chunk) * 32 + lane].{x,y,z,w} = substitution increment of rows
 // 4*chunk..+3 of this lane against target code c.  reverse: the stripe's rows index the reversed query.
-template <int R>
+template <int R, class SC>
 __device__ __forceinline__ void build_profile(int4* prof, const uint32_t* __restrict__ qwords, int q_len,
-                                              int row0, int lane, const ScoreW& sc, bool reverse) {
+                                              int row0, int lane, const SC& sc, bool reverse) {
     constexpr int CH = StripeCfg<R>::CH;
     int* p = reinterpret_cast<int*>(prof);
 #pragma unroll
@@ -157,7 +195,7 @@ __device__ __forceinline__ void build_profile(int4* prof, const uint32_t* __rest
         int code = 4;
         if (r < R && i < q_len) {
             const int qi = reverse ? q_len - 1 - i : i;
-            code = (qwords[qi >> 4] >> (2 * (qi & 15))) & 3;
+            code = (qwords[qi >> 4] >> (30 - 2 * (qi & 15))) & 3;
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -181,6 +219,13 @@ __device__ __forceinline__ int bvec_pos(int idx0) {
 //   kFwd:   read x L + motif^kmax with junction tokens (see the file header).
 // MULTI: the task has several stripes; `top` = this stripe has a predecessor (read bnd_in), `bot` = it has a
 // successor (lane 31 writes bnd_out).  Boundary entry for column j: (H(last row, j), F1(next row, j), F2(next row, j)).
+//
+// Step kinds.  Lane l works on column st - l, so for 31 <= st < t_len every lane is inside the matrix: those steps
+// run the FAST body (no guards, no junction logic), in blocks of 16 with one uniform refill of the target stream per
+// block.  The first 32 steps, the tail and (kFwd) the junction zone run the guarded body.
+// Target stream: every lane reads the target through its own 32-bit window, MSB first, pre-shifted by the lane's
+// skew, so that all lanes refill at the same step; taking the next base is one IMAD.WIDE (window * 4: the base
+// falls out of the top), and the profile row address one more IMAD -- both off the DPX pipe.
 template <int R, int MODE, bool MULTI>
 struct Sweep {
     // inputs
@@ -198,30 +243,60 @@ struct Sweep {
     const ulonglong2* tok_in;
     ulonglong2* tok_out;
     int4* out;
-    int jnext, m, kcnt;
+    int jnext, m, kcnt, zone_start;
     int r_score, r_end, r_start;
     // state
     int H[R], E1[R], E2[R];
     int hup_prev, h_out, f1_out, f2_out;
-    int best, bestcap, bestj, best_rs;
-    uint32_t tw, tw_next;
+    int best, bestor, bestst;      // kExact / kFwd: best word, best | 0xffff (its score class), step it was found at
+    int nz;                        // 0 on lane 0, else 1: multiplier that blanks what lane 0 "receives" from SHFL.UP
+    uint32_t twl, w0, w1;          // target window (MSB first) and the two words the next window is cut from
+    int wi, wmax, wsh;
+    const char* prof_lane;
     int4 bcur, bnxt;
     u64 tokP, tokJ;
 
-    __device__ __forceinline__ void init(const ScoreW& sc) {
+    __device__ __forceinline__ uint32_t tword(int i) const { return __ldg(&twords[min(max(i, 0), wmax)]); }
+
+    template <class SC>
+    __device__ __forceinline__ void init(const SC& sc) {
 #pragma unroll
         for (int r = 0; r < R; ++r) { H[r] = 0; E1[r] = sc.h_open1; E2[r] = sc.h_open2; }
         hup_prev = 0;                       // H(row0 - 1, j - 1); column 0 is the word 0
         h_out = 0; f1_out = 0; f2_out = 0;  // bottom-row outputs of the previous step
-        best = 0; bestcap = 0; bestj = 0; best_rs = 0x7fffffff;
-        tw = 0; tw_next = twords[0];
+        best = 0; bestor = MODE == kBwd ? 0 : 0xffff; bestst = 0;
+        nz = lane != 0;
+        wmax = (t_len + 15) >> 4;           // the zero slack word behind the sequence
+        wi = (-lane) >> 4;                  // word of column -lane (floor)
+        wsh = 2 * ((-lane) & 15);
+        w0 = tword(wi); w1 = tword(wi + 1);
+        twl = 0;
+        prof_lane = reinterpret_cast<const char*>(prof + lane);
         bcur = make_int4(0, 0, 0, 0); bnxt = make_int4(0, 0, 0, 0);
         if (MULTI && top) bnxt = __ldcg(&bnd_in[lane < t_len ? lane : t_len - 1]);
         tokP = 0; tokJ = 0;
     }
 
-    template <bool JUNC>
-    __device__ __forceinline__ int cells(const int4* pp, int hd, int& f1, int& f2, const ScoreW& sc, int& jhi, int& jlo) {
+    // every 16 steps, all lanes together: next 16 columns of this lane's skewed view of the target
+    __device__ __forceinline__ void refill() {
+        twl = __funnelshift_l(w1, w0, wsh);
+        w0 = w1;
+        ++wi;
+        w1 = tword(wi + 1);
+    }
+
+    template <class SC>
+    __device__ __forceinline__ unsigned next_base(const SC& sc) {
+        unsigned lo, hi;
+        asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(lo), "=r"(hi) : "r"(twl), "r"(sc.four));
+        twl = lo;
+        return hi;
+    }
+
+    __device__ __forceinline__ int best_col() const { return bestst - lane + 1; }   // 1-based column of `best`
+
+    template <bool JUNC, class SC>
+    __device__ __forceinline__ int cells(const int4* pp, int hd, int mul0, int& f1, int& f2, const SC& sc, int& jhi, int& jlo) {
         constexpr int CH = StripeCfg<R>::CH;
         int cm = 0;
 #pragma unroll
@@ -235,12 +310,12 @@ struct Sweep {
                     const int hleft = H[r];
                     const int e1pre = E1[r], e2pre = E2[r];
                     int h;
-                    cell_w32(hd, s4[u], sc, h, E1[r], E2[r], f1, f2);
+                    cell_w32(hd, r == 0 ? mul0 : sc.one, s4[u], sc, h, E1[r], E2[r], f1, f2);
                     if (JUNC) {
                         const int4 b = bsm[r * 32 + lane];
-                        jcand(h, b.x, jhi, jlo);
-                        jcand(e1pre, b.y, jhi, jlo);
-                        jcand(e2pre, b.z, jhi, jlo);
+                        jcand(h, b.x, sc, jhi, jlo);
+                        jcand(e1pre, b.y, sc, jhi, jlo);
+                        jcand(e2pre, b.z, sc, jhi, jlo);
                     }
                     hd = hleft;
                     H[r] = h;
@@ -252,40 +327,47 @@ struct Sweep {
         return cm;
     }
 
-    // ZONE (kFwd only): some lane may be at a junction column, tokens are moving.
-    template <bool ZONE>
-    __device__ __forceinline__ void step(int st, const ScoreW& sc) {
+    // FAST: every lane is inside the matrix and (kFwd) no lane is at a junction column.
+    // Otherwise the guarded body; kFwd from zone_start on: some lane may be at a junction column, tokens are moving.
+    // A step in which any lane is at a junction evaluates the junction candidates on every lane (one code path for
+    // the warp; the lanes that are not at a junction drop theirs).
+    template <bool FAST, class SC>
+    __device__ __forceinline__ void step(int st, const SC& sc) {
+        const bool zone = !FAST && MODE == kFwd && st >= zone_start;     // uniform
         constexpr int CH = StripeCfg<R>::CH;
-        const int jj = st - lane;           // 0-based target column of this lane
         int hup = __shfl_up_sync(kFull, h_out, 1);
         int f1 = __shfl_up_sync(kFull, f1_out, 1);
         int f2 = __shfl_up_sync(kFull, f2_out, 1);
         u64 tP = 0, tJ = 0;
-        if (MODE == kFwd && ZONE) { tP = shfl_up64(tokP); tJ = shfl_up64(tokJ); }
-        int bh = 0, bf1 = 0, bf2 = 0;
+        if (zone) { tP = shfl_up64(tokP); tJ = shfl_up64(tokJ); }
+        int mul0;
         if (MULTI && top) {                 // uniform branch
             if ((st & 31) == 0) {
                 bcur = bnxt;
                 const int nj = st + 32 + lane;
                 bnxt = __ldcg(&bnd_in[nj < t_len ? nj : t_len - 1]);
             }
-            bh = __shfl_sync(kFull, bcur.x, st & 31);
-            bf1 = __shfl_sync(kFull, bcur.y, st & 31);
-            bf2 = __shfl_sync(kFull, bcur.z, st & 31);
+            const int bh = __shfl_sync(kFull, bcur.x, st & 31);
+            const int bf1 = __shfl_sync(kFull, bcur.y, st & 31);
+            const int bf2 = __shfl_sync(kFull, bcur.z, st & 31);
+            if (lane == 0) { hup = bh; f1 = bf1; f2 = bf2; }
+            mul0 = sc.one;
+        } else {
+            // matrix border above lane 0: H = 0 and any F <= 0 (the floor of H makes every non-positive F equivalent);
+            // the diagonal is blanked where it is used
+            f1 = madd(f1, nz, 0);
+            f2 = madd(f2, nz, 0);
+            mul0 = nz;
         }
-        if (jj >= 0 && jj < t_len) {
-            if (lane == 0) {
-                if (MULTI && top) { hup = bh; f1 = bf1; f2 = bf2; }
-                else { hup = 0; f1 = sc.v_open1; f2 = sc.v_open2; }
-            }
-            if ((jj & 15) == 0) { tw = tw_next; tw_next = twords[(jj >> 4) + 1]; }
-            const int tb = tw & 3;
-            tw >>= 2;
-            const int4* pp = prof + tb * (CH * 32) + lane;
+        const unsigned tb = next_base(sc);  // unconditional: the window advances one column per step
+        const int jj = st - lane;           // 0-based target column of this lane
+        const bool anyj = zone && __any_sync(kFull, jj + 1 == jnext && jj < t_len);
+        if (FAST || (jj >= 0 && jj < t_len)) {
+            const int4* pp = reinterpret_cast<const int4*>(prof_lane + tb * (unsigned)(CH * 512));
             const int hd = hup_prev;
             hup_prev = hup;
-            const bool last_col = (MODE == kBwd) && jj == t_len - 1;
-            if (MODE == kBwd) {
+            const bool last_col = !FAST && (MODE == kBwd) && jj == t_len - 1;
+            if (MODE == kBwd && !FAST) {
                 if (last_col) {             // E(i', n_right): the state entering the last column
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
@@ -298,18 +380,17 @@ struct Sweep {
                     }
                 }
             }
-            int cm, jhi = 0, jlo = 0;
-            bool junc = false;
-            if (MODE == kFwd && ZONE) junc = (jj + 1 == jnext);
-            if (MODE == kFwd && ZONE && junc) cm = cells<true>(pp, hd, f1, f2, sc, jhi, jlo);
-            else cm = cells<false>(pp, hd, f1, f2, sc, jhi, jlo);
+            int cm, jhi = kJuncNone, jlo = 0;
+            const bool junc = zone && (jj + 1 == jnext);
+            if (zone && anyj) cm = cells<true>(pp, hd, mul0, f1, f2, sc, jhi, jlo);
+            else cm = cells<false>(pp, hd, mul0, f1, f2, sc, jhi, jlo);
             h_out = H[R - 1]; f1_out = f1; f2_out = f2;
             if (MODE == kBwd) {
                 // R-only ordering in forward coordinates: score desc, end asc (= reversed start desc), start desc
-                // (= reversed end asc: keep the earlier column on a full tie)
-                const int cap = w_cap(cm);
-                const int rs = jj + 1 + cm - cap;          // reversed start of the column's best cell
-                if (cap > bestcap || (cap == bestcap && cap > 0 && rs > best_rs)) { bestcap = cap; best_rs = rs; bestj = jj + 1; }
+                // (= reversed end asc: keep the earlier column on a full tie).  cm + column = (score << 16) + reversed
+                // start of the column's best cell; within a lane column = st + const, so compare cm + st.
+                const int key = madd(cm, sc.one, st);
+                if (key > bestor) { bestor = key; bestst = st; }
                 if (last_col) {
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
@@ -318,14 +399,16 @@ struct Sweep {
                     }
                 }
             } else {
-                if (cm > bestcap) { best = cm; bestcap = w_cap(cm); bestj = jj + 1; }
+                // a strictly higher score (span is below 65536, so cm > best | 0xffff compares the score fields)
+                if (cm > bestor) { best = cm; bestor = cm | 0xffff; bestst = st; }
             }
-            if (MODE == kFwd && ZONE && junc) {
+            if (junc) {
+                junction_unbias(jhi, jlo);
                 if (lane == 0) {
                     if (MULTI && top) { const ulonglong2 t = __ldcg(&tok_in[kcnt]); tP = t.x; tJ = t.y; }
                     else { tP = 0; tJ = 0; }
                 }
-                const u64 myP = key_of_best(best, bestj), myJ = key_of_junction(jhi, jlo);
+                const u64 myP = key_of_best(best, best_col()), myJ = key_of_junction(jhi, jlo);
                 tokP = myP > tP ? myP : tP;
                 tokJ = myJ > tJ ? myJ : tJ;
                 if (lane == 31) {
@@ -339,15 +422,38 @@ struct Sweep {
         }
     }
 
-    __device__ __forceinline__ void run(const ScoreW& sc, int zone_start) {
-        const int nsteps = t_len + 31;
-        int st = 0;
-        if (MODE == kFwd) {
-            for (; st < zone_start && st < nsteps; ++st) step<false>(st, sc);
-            for (; st < nsteps; ++st) step<true>(st, sc);
-        } else {
-            for (; st < nsteps; ++st) step<false>(st, sc);
+    template <class SC>
+    __device__ __forceinline__ void slow_until(int& st, int end, const SC& sc) {
+#pragma unroll 1
+        for (; st < end; ++st) {
+            if ((st & 15) == 0) refill();
+            step<false>(st, sc);
         }
+    }
+
+    template <class SC>
+    __device__ __forceinline__ void run(const SC& sc, int zone_start_) {
+        zone_start = zone_start_;
+        const int nsteps = t_len + 31;
+        int fast_end = ((t_len - 1) >> 4) << 4;       // steps below it: every lane's column is < t_len - 1
+        if (MODE == kFwd) fast_end = min(fast_end, (zone_start >> 4) << 4);
+        int st = 0;
+        slow_until(st, min(32, nsteps), sc);
+        for (; st + 16 <= fast_end; st += 16) {
+            refill();
+#pragma unroll 1
+            for (int b = 0; b < 16; b += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) step<true>(st + b + u, sc);
+            }
+        }
+        slow_until(st, nsteps, sc);
+    }
+
+    // kBwd result: (score << 16) + reversed start, and the 1-based reversed end column
+    __device__ __forceinline__ void bwd_best(int& cap, int& rs, int& col) const {
+        const int key = bestor - lane + 1;            // cm + column
+        cap = key & (int)0xffff0000; rs = key & 0xffff; col = best_col();
     }
 };
 
@@ -367,8 +473,8 @@ __host__ __device__ __forceinline__ void stripe_shape(int q_len, int max_r, int&
     }
 }
 
-template <int R, bool MULTI>
-__device__ __forceinline__ u64 exact_task(const Task& tk, const uint32_t* __restrict__ pool, const ScoreW& sc,
+template <int R, bool MULTI, class SC>
+__device__ __forceinline__ u64 exact_task(const Task& tk, const uint32_t* __restrict__ pool, const SC& sc,
                                           int4* prof, int lane, int n_stripes, int4* bnd_a, int4* bnd_b) {
     const uint32_t* qwords = pool + tk.q_word;
     const int rows_per_stripe = 32 * R;
@@ -383,55 +489,110 @@ __device__ __forceinline__ u64 exact_task(const Task& tk, const uint32_t* __rest
         sw.bnd_in = (s & 1) ? bnd_a : bnd_b; sw.bnd_out = (s & 1) ? bnd_b : bnd_a;
         sw.init(sc);
         sw.run(sc, 0);
-        const u64 k = key_of_best(sw.best, sw.bestj);
+        const u64 k = key_of_best(sw.best, sw.best_col());
         key = k > key ? k : key;
     }
     return key;
 }
 
-template <int R, bool MULTI>
+template <int R, bool MULTI, class SC>
 __device__ __forceinline__ u64 exact_dispatch(int r, const Task& tk, const uint32_t* __restrict__ pool,
-                                              const ScoreW& sc, int4* prof, int lane, int n_stripes, int4* bnd_a,
+                                              const SC& sc, int4* prof, int lane, int n_stripes, int4* bnd_a,
                                               int4* bnd_b) {
     if (r == R) return exact_task<R, MULTI>(tk, pool, sc, prof, lane, n_stripes, bnd_a, bnd_b);
     if constexpr (R < kMaxRExact) return exact_dispatch<R + 1, MULTI>(r, tk, pool, sc, prof, lane, n_stripes, bnd_a, bnd_b);
     return 0ull;
 }
 
-// Exact (score, tstart, tend) kernel.  Persistent: every warp pulls task indices from *counter; the stripe
-// height is picked per task (warp-uniform dispatch), so one launch covers a whole batch.
-// order[] lists the tasks of this launch (host sorts them by decreasing cost); out[] is indexed by task id.
-// smem_stride: int4 of shared memory per warp.  scratch: MULTI only; per warp 2 rows of scratch_stride int4.
-template <bool MULTI>
-__global__ void __launch_bounds__(128, 4)
-exact_kernel(const Task* __restrict__ tasks, const int32_t* __restrict__ order, int n_order,
-             const uint32_t* __restrict__ pool, ScoreW sc, int* counter, int smem_stride,
+// A query that needs several stripes has at least max_r / 2 + 1 rows per lane (stripe_shape).
+constexpr int kMinRMultiExact = kMaxRExact / 2 + 1;
+constexpr int kMinRMultiLadder = kMaxRLadder / 2 + 1;
+
+constexpr int kWarpsPerBlock = 16;     // one persistent 512-thread block per SM: 4 warps per scheduler
+constexpr int kExclusiveWarps = 4;     // warps 0..3 sit on the four schedulers of the SM (warp id % 4)
+
+// Task scheduling shared by both kernels.  order[] lists the tasks by decreasing cost.
+//   1. Exclusive phase: the first n_excl tasks are the few long multi-stripe ones.  Each gets a scheduler of its own:
+//      warp g (g < 4) of a block takes it and the three warps that share its scheduler (g + 4, g + 8, g + 12) wait on
+//      a named barrier.  A lone warp runs at ~80 % of a full scheduler's rate, so the long tasks finish early instead
+//      of crawling at a quarter of the speed and becoming the kernel's tail; the other schedulers work on.
+//   2. One static round, slot-major (task = warp * gridDim + block), so that a small batch spreads over all SMs.
+//   3. Dynamic: warps pull the remaining tasks from *counter.
+struct TaskCursor {
+    int n_excl, n_order, lane, warp;
+    int* counter;
+    int round;      // 0: exclusive, 1: static round, 2: dynamic
+    bool group_wait;
+    __device__ __forceinline__ TaskCursor(int n_excl_, int n_order_, int* counter_)
+        : n_excl(n_excl_), n_order(n_order_), lane(threadIdx.x & 31), warp(threadIdx.x >> 5), counter(counter_),
+          round(n_excl_ > 0 ? 0 : 1), group_wait(false) {}
+    // next index into order[], -1: nothing this round (call again), -2: done
+    __device__ __forceinline__ int next() {
+        if (round == 0) {
+            round = 1;
+            const int g = warp & (kExclusiveWarps - 1);
+            const int i = g * (int)gridDim.x + (int)blockIdx.x;     // the long task of this warp's scheduler, if any
+            group_wait = i < n_excl;
+            return (group_wait && warp == g) ? i : -1;
+        }
+        if (round == 1) {
+            round = 2;
+            const int oi = n_excl + warp * (int)gridDim.x + (int)blockIdx.x;
+            return oi < n_order ? oi : -2;
+        }
+        int oi = 0;
+        if (lane == 0) oi = atomicAdd(counter, 1);
+        oi = __shfl_sync(kFull, oi, 0) + n_excl + kWarpsPerBlock * (int)gridDim.x;
+        return oi < n_order ? oi : -2;
+    }
+    // after the task of a round: the warps of a scheduler that hosted a long task meet here
+    __device__ __forceinline__ void done() {
+        if (group_wait) {
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & (kExclusiveWarps - 1))), "r"(32 * kWarpsPerBlock / kExclusiveWarps) : "memory");
+            group_wait = false;
+        }
+    }
+};
+
+// Exact (score, tstart, tend) kernel.  Persistent: the stripe height and the single- / multi-stripe path are picked
+// per task (warp-uniform dispatch), so one launch covers a whole batch, long expanded alleles included.
+// out[] is indexed by task id.  smem_stride: int4 of shared memory per warp.  scratch: per warp 2 boundary rows of
+// scratch_stride int4 (only touched by multi-stripe tasks; null when the batch has none).
+template <bool FIXED>
+__global__ void __launch_bounds__(32 * kWarpsPerBlock, 1)
+exact_kernel(const Task* __restrict__ tasks, const int32_t* __restrict__ order, int n_order, int n_excl,
+             const uint32_t* __restrict__ pool, ScoreW scw, int* counter, int smem_stride,
              int4* scratch, long long scratch_stride, int4* out) {
     extern __shared__ int4 smem[];
+    const ScoreView<FIXED> sc(scw);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     int4* prof = smem + warp * smem_stride;
-    const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-    int4* bnd_a = MULTI ? scratch + gwarp * 2 * scratch_stride : nullptr;
-    int4* bnd_b = MULTI ? bnd_a + scratch_stride : nullptr;
+    const long long gwarp = (long long)blockIdx.x * kWarpsPerBlock + warp;
+    int4* bnd_a = scratch + gwarp * 2 * scratch_stride;
+    int4* bnd_b = bnd_a + scratch_stride;
+    TaskCursor cur(n_excl, n_order, counter);
     for (;;) {
-        int oi = 0;
-        if (lane == 0) oi = atomicAdd(counter, 1);
-        oi = __shfl_sync(kFull, oi, 0);
-        if (oi >= n_order) break;
-        const int tid = order[oi];
-        const Task tk = tasks[tid];
-        int R, n_stripes;
-        stripe_shape(tk.q_len, kMaxRExact, R, n_stripes);
-        u64 key = exact_dispatch<kMinR, MULTI>(R, tk, pool, sc, prof, lane, n_stripes, bnd_a, bnd_b);
-        key = warp_max64(key);
-        if (lane == 0) out[tid] = finalize_rung(key, 0ull, 0, 0, 0, 0);
+        const int oi = cur.next();
+        if (oi == -2) break;
+        if (oi >= 0) {
+            const int tid = order[oi];
+            const Task tk = tasks[tid];
+            int R, n_stripes;
+            stripe_shape(tk.q_len, kMaxRExact, R, n_stripes);
+            u64 key;
+            if (n_stripes > 1) key = exact_dispatch<kMinRMultiExact, true>(R, tk, pool, sc, prof, lane, n_stripes, bnd_a, bnd_b);
+            else key = exact_dispatch<kMinR, false>(R, tk, pool, sc, prof, lane, n_stripes, bnd_a, bnd_b);
+            key = warp_max64(key);
+            if (lane == 0) out[tid] = finalize_rung(key, 0ull, 0, 0, 0, 0);
+        }
+        cur.done();
     }
 }
 
-template <int R, bool MULTI>
+template <int R, bool MULTI, class SC>
 __device__ __forceinline__ void ladder_task(const LadderTask& tk, const uint32_t* __restrict__ pool,
-                                            const LadderRegion& reg, const ScoreW& sc, int4* prof, int lane,
+                                            const LadderRegion& reg, const SC& sc, int4* prof, int lane,
                                             int n_stripes, int4* bnd_a, int4* bnd_b, int4* bglob, ulonglong2* tok_a,
                                             ulonglong2* tok_b, int4* out) {
     int4* bsm = prof + StripeCfg<R>::PROF_INT4;
@@ -465,9 +626,10 @@ __device__ __forceinline__ void ladder_task(const LadderTask& tk, const uint32_t
             sw.init(sc);
             sw.run(sc, 0);
             u64 k = 0;
-            if (sw.bestcap > 0)
-                k = ((u64)((unsigned)sw.bestcap >> 16) << 32) | ((u64)(unsigned)sw.best_rs << 16) |
-                    (u64)(0xffffu - (unsigned)sw.bestj);
+            int cap, rs, col;
+            sw.bwd_best(cap, rs, col);
+            if (cap > 0)
+                k = ((u64)((unsigned)cap >> 16) << 32) | ((u64)(unsigned)rs << 16) | (u64)(0xffffu - (unsigned)col);
             rkey = k > rkey ? k : rkey;
         }
         rkey = warp_max64(rkey);
@@ -509,9 +671,9 @@ __device__ __forceinline__ void ladder_task(const LadderTask& tk, const uint32_t
     if (c_first == 0 && lane == 0) outp[0] = finalize_rung(0ull, 0ull, 0, r_score, r_end, r_start);
 }
 
-template <int R, bool MULTI>
+template <int R, bool MULTI, class SC>
 __device__ __forceinline__ void ladder_dispatch(int r, const LadderTask& tk, const uint32_t* __restrict__ pool,
-                                                const LadderRegion& reg, const ScoreW& sc, int4* prof, int lane,
+                                                const LadderRegion& reg, const SC& sc, int4* prof, int lane,
                                                 int n_stripes, int4* bnd_a, int4* bnd_b, int4* bglob,
                                                 ulonglong2* tok_a, ulonglong2* tok_b, int4* out) {
     if (r == R) { ladder_task<R, MULTI>(tk, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out); return; }
@@ -520,35 +682,41 @@ __device__ __forceinline__ void ladder_dispatch(int r, const LadderTask& tk, con
 }
 
 // Round-3 ladder kernel: one warp per read, all rungs kmin..kmax from one backward and one forward sweep.
-// scratch (MULTI only), per warp: 2 boundary rows of bnd_stride int4, b_stride int4 of backward vectors,
-// 2 token rows of tok_stride ulonglong2.
-template <bool MULTI>
-__global__ void __launch_bounds__(128, 4)
-ladder_kernel(const LadderTask* __restrict__ tasks, const int32_t* __restrict__ order, int n_order,
-              const uint32_t* __restrict__ pool, const LadderRegion* __restrict__ regs, ScoreW sc, int* counter,
+// scratch (multi-stripe reads only), per warp: 2 boundary rows of bnd_stride int4, b_stride int4 of backward
+// vectors, 2 token rows of tok_stride ulonglong2.
+template <bool FIXED>
+__global__ void __launch_bounds__(32 * kWarpsPerBlock, 1)
+ladder_kernel(const LadderTask* __restrict__ tasks, const int32_t* __restrict__ order, int n_order, int n_excl,
+              const uint32_t* __restrict__ pool, const LadderRegion* __restrict__ regs, ScoreW scw, int* counter,
               int smem_stride,
               int4* scratch, long long bnd_stride, long long b_stride, long long tok_stride, int4* out) {
     extern __shared__ int4 smem[];
+    const ScoreView<FIXED> sc(scw);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     int4* prof = smem + warp * smem_stride;
-    const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    const long long gwarp = (long long)blockIdx.x * kWarpsPerBlock + warp;
     const long long per_warp = 2 * bnd_stride + b_stride + 2 * tok_stride;
-    int4* bnd_a = MULTI ? scratch + gwarp * per_warp : nullptr;
-    int4* bnd_b = MULTI ? bnd_a + bnd_stride : nullptr;
-    int4* bglob = MULTI ? bnd_b + bnd_stride : nullptr;
-    ulonglong2* tok_a = MULTI ? reinterpret_cast<ulonglong2*>(bglob + b_stride) : nullptr;
-    ulonglong2* tok_b = MULTI ? tok_a + tok_stride : nullptr;
+    int4* bnd_a = scratch + gwarp * per_warp;
+    int4* bnd_b = bnd_a + bnd_stride;
+    int4* bglob = bnd_b + bnd_stride;
+    ulonglong2* tok_a = reinterpret_cast<ulonglong2*>(bglob + b_stride);
+    ulonglong2* tok_b = tok_a + tok_stride;
+    TaskCursor cur(n_excl, n_order, counter);
     for (;;) {
-        int oi = 0;
-        if (lane == 0) oi = atomicAdd(counter, 1);
-        oi = __shfl_sync(kFull, oi, 0);
-        if (oi >= n_order) break;
-        const LadderTask tk = tasks[order[oi]];
-        const LadderRegion reg = regs[tk.region];
-        int R, n_stripes;
-        stripe_shape(tk.q_len, kMaxRLadder, R, n_stripes);
-        ladder_dispatch<kMinR, MULTI>(R, tk, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out);
+        const int oi = cur.next();
+        if (oi == -2) break;
+        if (oi >= 0) {
+            const LadderTask tk = tasks[order[oi]];
+            const LadderRegion reg = regs[tk.region];
+            int R, n_stripes;
+            stripe_shape(tk.q_len, kMaxRLadder, R, n_stripes);
+            if (n_stripes > 1)
+                ladder_dispatch<kMinRMultiLadder, true>(R, tk, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out);
+            else
+                ladder_dispatch<kMinR, false>(R, tk, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out);
+        }
+        cur.done();
     }
 }
 
