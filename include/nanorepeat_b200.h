@@ -58,8 +58,8 @@ typedef struct nr_aln_t { int32_t score, tstart, tend; } nr_aln_t;
 /* Per-rung summary produced by the round-3 ladder kernel: everything nanoRepeat_bam.py:423-431 looks at. */
 typedef struct nr_rung_t {
     int32_t score;        /* AS:i of core vs left + motif*k + right */
-    uint8_t starts_in_left;  /* tstart < |left|            (nanoRepeat_bam.py:427, strict) */
-    uint8_t ends_in_right;   /* tlen - tend < |right|      (nanoRepeat_bam.py:427, strict) */
+    uint8_t starts_in_left;  /* ends_in_right && tstart < |left|: the reference only ever tests the conjunction (:427) */
+    uint8_t ends_in_right;   /* tlen - tend < |right|                      (nanoRepeat_bam.py:427, strict) */
     uint8_t pad[2];
 } nr_rung_t;
 
@@ -87,9 +87,12 @@ int nr_device_info(int32_t* device, int32_t* sm_count, int32_t* clock_khz);
 int nr_limits(int32_t* max_score, int32_t* max_tlen);
 
 /*
- * How round 3 is computed (results are identical, bit for bit; tests run both):
- *   1 (default)  one backward sweep over the right anchor and one forward sweep over left + motif*kmax per read,
- *                joined at every junction column |left| + k*|motif| (the rungs share their prefix and suffix);
+ * How round 3 is computed (scores, predicates and selection are identical, bit for bit; tests run all three):
+ *   2 (default)  flag ladder: one backward sweep over the right anchor and one forward sweep over left + motif*kmax
+ *                per read, joined at every junction column |left| + k*|motif| (the rungs share prefix and suffix);
+ *                the DP words carry the score and the two span predicates only, no coordinates
+ *                (nr_batch_fetch_alns is not available on such a batch; |right| <= 32767);
+ *   1            the same two sweeps on (score, span) words: every rung also gets its exact (tstart, tend);
  *   0            every rung left + motif*k + right scored as its own full rectangle (what the reference hands its
  *                aligner, nanoRepeat_bam.py:474-497).
  */

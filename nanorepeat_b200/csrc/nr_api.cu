@@ -72,7 +72,7 @@ struct Context {
 };
 Context g_ctx;
 std::mutex g_ctx_mu;
-std::atomic<int> g_ladder_mode{1};   // 1: round 3 shares sweeps across the ladder; 0: every rung its own rectangle
+std::atomic<int> g_ladder_mode{2};   // 2: flag ladder, 1: shared sweeps with full records, 0: every rung its own rectangle
 
 int ensure_init(int device) {
     std::lock_guard<std::mutex> lk(g_ctx_mu);
@@ -198,6 +198,7 @@ struct nr_batch {
     std::vector<nr::LadderTask> ltasks;       // round 3 in ladder mode (tasks stays empty)
     std::vector<nr::LadderRegion> lregs;
     bool ladder = false;
+    bool flag = false;                        // ladder on flag words: d_out holds (score, spans both, ends in right)
     size_t n_out = 0;                         // records in d_out / h_out
     std::vector<int32_t> order;
     Launch launch = {};
@@ -395,7 +396,8 @@ int run_batch(nr_batch* b, cudaStream_t st) {
     const nr::ScoreW k = score_words(b->sc);
     CUDA_TRY(cudaMemsetAsync(b->d_counters, 0, sizeof(int), st));
     if (L.ladder) {
-        auto fn = L.fixed ? nr::ladder_kernel<true> : nr::ladder_kernel<false>;
+        auto fn = b->flag ? (L.fixed ? nr::ladder_kernel<true, true> : nr::ladder_kernel<false, true>)
+                          : (L.fixed ? nr::ladder_kernel<true, false> : nr::ladder_kernel<false, false>);
         const int stride = ladder_smem_int4(L.R);
         const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
         CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -503,6 +505,8 @@ int add_round3(nr_batch* b, const char* left, int32_t n_left, const char* right,
     b->n_out = (size_t)b->rung_off.back();
     const int64_t* roff = b->rung_off.data() + first;
     int rc;
+    if (b->flag && 2 * (long long)n_right > 65534)
+        return fail(NR_ERR_TOO_LARGE, "right anchor of %d bases exceeds the flag ladder's range (32767); use nr_set_ladder_mode(1)", n_right);
     if (b->ladder) {
         // shared sweeps (nr_kernels.cuh, ladder_kernel): the pool holds left + motif^khi once and reverse(right) once
         nr::LadderRegion lr = {};
@@ -574,6 +578,7 @@ nr_batch* new_batch(const nr_scoring_t* sc, BatchKind kind) {
     b->kind = kind;
     b->sc = *sc;
     b->ladder = kind == KIND_ROUND3 && g_ladder_mode.load() != 0;
+    b->flag = kind == KIND_ROUND3 && g_ladder_mode.load() == 2;
     return b;
 }
 
@@ -621,7 +626,7 @@ int nr_device_info(int32_t* device, int32_t* sm_count, int32_t* clock_khz) {
 }
 
 int nr_set_ladder_mode(int mode) {
-    if (mode != 0 && mode != 1) return fail(NR_ERR_ARG, "nr_set_ladder_mode: mode must be 0 or 1");
+    if (mode < 0 || mode > 2) return fail(NR_ERR_ARG, "nr_set_ladder_mode: mode must be 0, 1 or 2");
     g_ladder_mode.store(mode);
     return NR_OK;
 }
@@ -734,6 +739,7 @@ int nr_batch_run(nr_batch_t* b, void* stream) {
 
 int nr_batch_fetch_alns(nr_batch_t* b, nr_aln_t* out) {
     if (!b || (!out && b->n_out)) return fail(NR_ERR_ARG, "nr_batch_fetch_alns: NULL argument");
+    if (b->flag) return fail(NR_ERR_ARG, "nr_batch_fetch_alns: a flag-ladder batch has no (tstart, tend) records; use nr_batch_fetch_round3 or nr_set_ladder_mode(1)");
     int rc = fetch_raw(b);
     if (rc) return rc;
     for (size_t i = 0; i < b->n_out; ++i) {
@@ -767,8 +773,14 @@ int nr_batch_fetch_round3(nr_batch_t* b, const int64_t* rung_offset, nr_rung_t* 
             const int4 a = b->h_out[o + i];
             const int k = b->kmin[r] + i;
             const int tlen = g.n_left + g.motif_len * k + g.n_right;
-            const bool in_left = a.x > 0 && a.y < g.n_left;               // tstart < |left|  (:427)
-            const bool in_right = a.x > 0 && tlen - a.z < g.n_right;      // tlen - tend < |right|
+            bool in_left, in_right;
+            if (b->flag) {
+                in_right = a.z != 0;
+                in_left = a.y != 0;
+            } else {
+                in_right = a.x > 0 && tlen - a.z < g.n_right;             // tlen - tend < |right|  (:427)
+                in_left = in_right && a.y < g.n_left;                     // tstart < |left|; reported only with in_right
+            }
             if (rungs) {
                 nr_rung_t& rg = rungs[rung_offset[r] + i];
                 rg.score = a.x;

@@ -120,7 +120,7 @@ __device__ __forceinline__ void jcand(int wf, int wb, const SC& sc, int& bhi, in
     if (khi > bhi) { bhi = khi; blo = klo; }
     else if (khi == bhi) blo = max(blo, klo);
 }
-constexpr int kJuncNone = (int)0x80000000;              // bhi of "no candidate yet"
+constexpr int kJuncNone = -(3 << 29);                   // "no candidate yet": below every real candidate, room to subtract
 __device__ __forceinline__ void junction_unbias(int& bhi, int& blo) {
     if (bhi == kJuncNone) { bhi = 0; blo = 0; } else { bhi += 1; blo -= 1; }
 }
@@ -175,6 +175,17 @@ __device__ __forceinline__ int4 finalize_rung(u64 P, u64 J, int c, int r_score, 
     return make_int4(bs, bst, be, 0);
 }
 
+// Flag ladder: rung record from the prefix-class best word P, the junction-class best key J and the R-only candidate key
+// (keys: (score << 16) - 2 * ext - mark).  Output: (score, starts_in_left && ends_in_right, ends_in_right, 0).
+// An alignment that ends at or before the junction column has the smaller tend, so the prefix class wins ties.
+__device__ __forceinline__ int4 finalize_flag_rung(int P, int J, int rcand) {
+    const int np = max(J, rcand);
+    const int s_np = np > 0 ? w_cap(np) : 0;
+    const int s_p = w_cap(P);
+    const int in_right = s_np > s_p;
+    return make_int4(max(s_p, s_np) >> 16, in_right & np & 1, in_right, 0);
+}
+
 template <int R>
 struct StripeCfg {
     static constexpr int CH = (R + 3) / 4;             // LDS.128 per column step
@@ -212,22 +223,41 @@ __device__ __forceinline__ int bvec_pos(int idx0) {
     return stripe * (32 * R) + (in % R) * 32 + in / R;
 }
 
+// Per-sweep view of the scoring words.  DEC = what a move that consumes a target column subtracts from the word's
+// low half: 1 for span words (tstart = column - span), 2 for the backward sweep of the flag ladder (2 * ext, leaving
+// bit 0 for the forward mark), 0 for the forward sweep of the flag ladder (the low half holds only the mark).
+template <class SC, int DEC>
+struct ModeScore {
+    int sub_match, sub_mismatch, h_open1, h_ext1, h_open2, h_ext2, v_open1, v_ext1, v_open2, v_ext2, one;
+    __device__ __forceinline__ explicit ModeScore(const SC& sc)
+        : sub_match(sc.sub_match + 1 - DEC), sub_mismatch(sc.sub_mismatch + 1 - DEC), h_open1(sc.h_open1 + 1 - DEC),
+          h_ext1(sc.h_ext1 + 1 - DEC), h_open2(sc.h_open2 + 1 - DEC), h_ext2(sc.h_ext2 + 1 - DEC), v_open1(sc.v_open1),
+          v_ext1(sc.v_ext1), v_open2(sc.v_open2), v_ext2(sc.v_ext2), one(sc.one) {}
+};
+
+constexpr int kBwdF = 3, kFwdF = 4;     // flag ladder (see ladder_task)
+
 // One stripe of one sweep.
 //   kExact: plain task, running best per the contract.
 //   kBwd:   reversed read x reversed right flank; best per the R-only ordering; the final column's junction
 //           state (H, E1 + refund1, E2 + refund2) is written to bdst in the forward layout.
 //   kFwd:   read x L + motif^kmax with junction tokens (see the file header).
+//   kBwdF / kFwdF: the same two sweeps on flag words (ladder_task, FLAG).
 // MULTI: the task has several stripes; `top` = this stripe has a predecessor (read bnd_in), `bot` = it has a
 // successor (lane 31 writes bnd_out).  Boundary entry for column j: (H(last row, j), F1(next row, j), F2(next row, j)).
 //
 // Step kinds.  Lane l works on column st - l, so for 31 <= st < t_len every lane is inside the matrix: those steps
 // run the FAST body (no guards, no junction logic), in blocks of 16 with one uniform refill of the target stream per
-// block.  The first 32 steps, the tail and (kFwd) the junction zone run the guarded body.
+// block.  The first 32 steps, the tail, (kFwd) the junction zone and (kFwdF) the 32 steps in which the lanes pass
+// the end of the left flank run the guarded body.
 // Target stream: every lane reads the target through its own 32-bit window, MSB first, pre-shifted by the lane's
 // skew, so that all lanes refill at the same step; taking the next base is one IMAD.WIDE (window * 4: the base
 // falls out of the top), and the profile row address one more IMAD -- both off the DPX pipe.
 template <int R, int MODE, bool MULTI>
 struct Sweep {
+    static constexpr bool kIsFwd = MODE == kFwd || MODE == kFwdF;
+    static constexpr bool kIsBwd = MODE == kBwd || MODE == kBwdF;
+    static constexpr int DEC = MODE == kFwdF ? 0 : MODE == kBwdF ? 2 : 1;
     // inputs
     const int4* prof;
     const uint32_t* twords;
@@ -235,36 +265,38 @@ struct Sweep {
     bool top, bot;
     const int4* bnd_in;
     int4* bnd_out;
-    // kBwd
+    // backward sweeps
     int4* bdst;
     int q_len, brow0;
-    // kFwd
+    // forward sweeps
     const int4* bsm;
     const ulonglong2* tok_in;
     ulonglong2* tok_out;
     int4* out;
     int jnext, m, kcnt, zone_start;
-    int r_score, r_end, r_start;
+    int r_score, r_end, r_start;   // kFwd: the R-only optimum
+    int rcand, mark_col;           // kFwdF: the R-only candidate key; last column of the left flank (-1: none)
     // state
     int H[R], E1[R], E2[R];
     int hup_prev, h_out, f1_out, f2_out;
     int best, bestor, bestst;      // kExact / kFwd: best word, best | 0xffff (its score class), step it was found at
+                                   // backward: bestor = best key; kFwdF: best = running maximum word
     int nz;                        // 0 on lane 0, else 1: multiplier that blanks what lane 0 "receives" from SHFL.UP
     uint32_t twl, w0, w1;          // target window (MSB first) and the two words the next window is cut from
     int wi, wmax, wsh;
     const char* prof_lane;
     int4 bcur, bnxt;
-    u64 tokP, tokJ;
+    u64 tokP, tokJ;                // kFwd: 64-bit keys; kFwdF: 32-bit words in the low halves
 
     __device__ __forceinline__ uint32_t tword(int i) const { return __ldg(&twords[min(max(i, 0), wmax)]); }
 
-    template <class SC>
-    __device__ __forceinline__ void init(const SC& sc) {
+    template <class MS>
+    __device__ __forceinline__ void init(const MS& sc) {
 #pragma unroll
         for (int r = 0; r < R; ++r) { H[r] = 0; E1[r] = sc.h_open1; E2[r] = sc.h_open2; }
         hup_prev = 0;                       // H(row0 - 1, j - 1); column 0 is the word 0
         h_out = 0; f1_out = 0; f2_out = 0;  // bottom-row outputs of the previous step
-        best = 0; bestor = MODE == kBwd ? 0 : 0xffff; bestst = 0;
+        best = 0; bestor = kIsBwd ? 0 : 0xffff; bestst = 0;
         nz = lane != 0;
         wmax = (t_len + 15) >> 4;           // the zero slack word behind the sequence
         wi = (-lane) >> 4;                  // word of column -lane (floor)
@@ -285,20 +317,20 @@ struct Sweep {
         w1 = tword(wi + 1);
     }
 
-    template <class SC>
-    __device__ __forceinline__ unsigned next_base(const SC& sc) {
+    __device__ __forceinline__ unsigned next_base(unsigned four) {
         unsigned lo, hi;
-        asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(lo), "=r"(hi) : "r"(twl), "r"(sc.four));
+        asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(lo), "=r"(hi) : "r"(twl), "r"(four));
         twl = lo;
         return hi;
     }
 
     __device__ __forceinline__ int best_col() const { return bestst - lane + 1; }   // 1-based column of `best`
 
-    template <bool JUNC, class SC>
-    __device__ __forceinline__ int cells(const int4* pp, int hd, int mul0, int& f1, int& f2, const SC& sc, int& jhi, int& jlo) {
+    // JUNC: also evaluate the junction candidates of this column.  kFwd: lexicographic (jhi, jlo); kFwdF: one key jhi.
+    template <bool JUNC, class MS, class SC>
+    __device__ __forceinline__ int cells(const int4* pp, int hd, int mul0, int cm, int& f1, int& f2, const MS& ms,
+                                         const SC& sc, int& jhi, int& jlo) {
         constexpr int CH = StripeCfg<R>::CH;
-        int cm = 0;
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
             const int4 sv = pp[c * 32];
@@ -310,12 +342,18 @@ struct Sweep {
                     const int hleft = H[r];
                     const int e1pre = E1[r], e2pre = E2[r];
                     int h;
-                    cell_w32(hd, r == 0 ? mul0 : sc.one, s4[u], sc, h, E1[r], E2[r], f1, f2);
+                    cell_w32(hd, r == 0 ? mul0 : ms.one, s4[u], ms, h, E1[r], E2[r], f1, f2);
                     if (JUNC) {
                         const int4 b = bsm[r * 32 + lane];
-                        jcand(h, b.x, sc, jhi, jlo);
-                        jcand(e1pre, b.y, sc, jhi, jlo);
-                        jcand(e2pre, b.z, sc, jhi, jlo);
+                        if (MODE == kFwdF) {
+                            jhi = __viaddmax_s32(h, b.x, jhi);
+                            jhi = __viaddmax_s32(e1pre, b.y, jhi);
+                            jhi = __viaddmax_s32(e2pre, b.z, jhi);
+                        } else {
+                            jcand(h, b.x, sc, jhi, jlo);
+                            jcand(e1pre, b.y, sc, jhi, jlo);
+                            jcand(e2pre, b.z, sc, jhi, jlo);
+                        }
                     }
                     hd = hleft;
                     H[r] = h;
@@ -327,19 +365,37 @@ struct Sweep {
         return cm;
     }
 
-    // FAST: every lane is inside the matrix and (kFwd) no lane is at a junction column.
-    // Otherwise the guarded body; kFwd from zone_start on: some lane may be at a junction column, tokens are moving.
-    // A step in which any lane is at a junction evaluates the junction candidates on every lane (one code path for
-    // the warp; the lanes that are not at a junction drop theirs).
-    template <bool FAST, class SC>
-    __device__ __forceinline__ void step(int st, const SC& sc) {
-        const bool zone = !FAST && MODE == kFwd && st >= zone_start;     // uniform
+    // kFwdF, once per lane: everything alive after the last column of the left flank started inside the flank
+    __device__ __forceinline__ void mark_started_in_left() {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            H[r] = __viaddmax_s32(H[r], -1, 0);
+            E1[r] -= E1[r] > 0;
+            E2[r] -= E2[r] > 0;
+        }
+        hup_prev = __viaddmax_s32(hup_prev, -1, 0);
+    }
+
+    // FAST: every lane is inside the matrix and (forward sweeps) no lane is at a junction or mark column.
+    // Otherwise the guarded body; forward sweeps from zone_start on: some lane may be at a junction column, tokens
+    // are moving.  A step in which any lane is at a junction evaluates the junction candidates on every lane (one
+    // code path for the warp; the lanes that are not at a junction drop theirs).
+    template <bool FAST, class MS, class SC>
+    __device__ __forceinline__ void step(int st, const MS& ms, const SC& sc) {
+        const bool zone = !FAST && kIsFwd && st >= zone_start;     // uniform
         constexpr int CH = StripeCfg<R>::CH;
         int hup = __shfl_up_sync(kFull, h_out, 1);
         int f1 = __shfl_up_sync(kFull, f1_out, 1);
         int f2 = __shfl_up_sync(kFull, f2_out, 1);
         u64 tP = 0, tJ = 0;
-        if (zone) { tP = shfl_up64(tokP); tJ = shfl_up64(tokJ); }
+        if (zone) {
+            if (MODE == kFwdF) {
+                tP = (unsigned)__shfl_up_sync(kFull, (int)tokP, 1);
+                tJ = (unsigned)__shfl_up_sync(kFull, (int)tokJ, 1);
+            } else {
+                tP = shfl_up64(tokP); tJ = shfl_up64(tokJ);
+            }
+        }
         int mul0;
         if (MULTI && top) {                 // uniform branch
             if ((st & 31) == 0) {
@@ -351,7 +407,7 @@ struct Sweep {
             const int bf1 = __shfl_sync(kFull, bcur.y, st & 31);
             const int bf2 = __shfl_sync(kFull, bcur.z, st & 31);
             if (lane == 0) { hup = bh; f1 = bf1; f2 = bf2; }
-            mul0 = sc.one;
+            mul0 = ms.one;
         } else {
             // matrix border above lane 0: H = 0 and any F <= 0 (the floor of H makes every non-positive F equivalent);
             // the diagonal is blanked where it is used
@@ -359,15 +415,15 @@ struct Sweep {
             f2 = madd(f2, nz, 0);
             mul0 = nz;
         }
-        const unsigned tb = next_base(sc);  // unconditional: the window advances one column per step
+        const unsigned tb = next_base(sc.four);  // unconditional: the window advances one column per step
         const int jj = st - lane;           // 0-based target column of this lane
         const bool anyj = zone && __any_sync(kFull, jj + 1 == jnext && jj < t_len);
         if (FAST || (jj >= 0 && jj < t_len)) {
             const int4* pp = reinterpret_cast<const int4*>(prof_lane + tb * (unsigned)(CH * 512));
             const int hd = hup_prev;
             hup_prev = hup;
-            const bool last_col = !FAST && (MODE == kBwd) && jj == t_len - 1;
-            if (MODE == kBwd && !FAST) {
+            const bool last_col = !FAST && kIsBwd && jj == t_len - 1;
+            if (kIsBwd && !FAST) {
                 if (last_col) {             // E(i', n_right): the state entering the last column
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
@@ -382,14 +438,16 @@ struct Sweep {
             }
             int cm, jhi = kJuncNone, jlo = 0;
             const bool junc = zone && (jj + 1 == jnext);
-            if (zone && anyj) cm = cells<true>(pp, hd, mul0, f1, f2, sc, jhi, jlo);
-            else cm = cells<false>(pp, hd, mul0, f1, f2, sc, jhi, jlo);
+            const int cm0 = MODE == kFwdF ? best : 0;      // flag ladder: only the running maximum matters
+            if (zone && anyj) cm = cells<true>(pp, hd, mul0, cm0, f1, f2, ms, sc, jhi, jlo);
+            else cm = cells<false>(pp, hd, mul0, cm0, f1, f2, ms, sc, jhi, jlo);
             h_out = H[R - 1]; f1_out = f1; f2_out = f2;
-            if (MODE == kBwd) {
+            if (kIsBwd) {
                 // R-only ordering in forward coordinates: score desc, end asc (= reversed start desc), start desc
-                // (= reversed end asc: keep the earlier column on a full tie).  cm + column = (score << 16) + reversed
-                // start of the column's best cell; within a lane column = st + const, so compare cm + st.
-                const int key = madd(cm, sc.one, st);
+                // (= reversed end asc: keep the earlier column on a full tie).  cm + DEC * column = (score << 16) +
+                // DEC * reversed start of the column's best cell; within a lane column = st + const, so compare
+                // cm + DEC * st.
+                const int key = madd(cm, ms.one, DEC * st);
                 if (key > bestor) { bestor = key; bestst = st; }
                 if (last_col) {
 #pragma unroll
@@ -398,22 +456,41 @@ struct Sweep {
                         if (idx0 >= 0) reinterpret_cast<int*>(&bdst[bvec_pos<R>(idx0)])[0] = H[r];
                     }
                 }
+            } else if (MODE == kFwdF) {
+                best = cm;
+                if (!FAST && jj == mark_col) mark_started_in_left();
             } else {
                 // a strictly higher score (span is below 65536, so cm > best | 0xffff compares the score fields)
                 if (cm > bestor) { best = cm; bestor = cm | 0xffff; bestst = st; }
             }
             if (junc) {
-                junction_unbias(jhi, jlo);
-                if (lane == 0) {
-                    if (MULTI && top) { const ulonglong2 t = __ldcg(&tok_in[kcnt]); tP = t.x; tJ = t.y; }
-                    else { tP = 0; tJ = 0; }
-                }
-                const u64 myP = key_of_best(best, best_col()), myJ = key_of_junction(jhi, jlo);
-                tokP = myP > tP ? myP : tP;
-                tokJ = myJ > tJ ? myJ : tJ;
-                if (lane == 31) {
-                    if (MULTI && bot) __stcg(&tok_out[kcnt], make_ulonglong2(tokP, tokJ));
-                    else out[kcnt] = finalize_rung(tokP, tokJ, jj + 1, r_score, r_end, r_start);
+                if (MODE == kFwdF) {
+                    if (lane == 0) {
+                        if (MULTI && top) { const ulonglong2 t = __ldcg(&tok_in[kcnt]); tP = t.x; tJ = t.y; }
+                        else { tP = 0; tJ = (unsigned)kJuncNone; }
+                    }
+                    // rung 0's junction column is the left flank's last column: every forward part that scores has
+                    // started inside the flank but is marked only after this step (the candidates with an empty
+                    // forward part are the R-only class again, so the blanket -1 cannot lose anything)
+                    const int myP = max((int)tP, best), myJ = max((int)tJ, jj == mark_col ? jhi - 1 : jhi);
+                    tokP = (unsigned)myP; tokJ = (unsigned)myJ;
+                    if (lane == 31) {
+                        if (MULTI && bot) __stcg(&tok_out[kcnt], make_ulonglong2(tokP, tokJ));
+                        else out[kcnt] = finalize_flag_rung(myP, myJ, rcand);
+                    }
+                } else {
+                    junction_unbias(jhi, jlo);
+                    if (lane == 0) {
+                        if (MULTI && top) { const ulonglong2 t = __ldcg(&tok_in[kcnt]); tP = t.x; tJ = t.y; }
+                        else { tP = 0; tJ = 0; }
+                    }
+                    const u64 myP = key_of_best(best, best_col()), myJ = key_of_junction(jhi, jlo);
+                    tokP = myP > tP ? myP : tP;
+                    tokJ = myJ > tJ ? myJ : tJ;
+                    if (lane == 31) {
+                        if (MULTI && bot) __stcg(&tok_out[kcnt], make_ulonglong2(tokP, tokJ));
+                        else out[kcnt] = finalize_rung(tokP, tokJ, jj + 1, r_score, r_end, r_start);
+                    }
                 }
                 jnext += m;
                 ++kcnt;
@@ -422,38 +499,51 @@ struct Sweep {
         }
     }
 
-    template <class SC>
-    __device__ __forceinline__ void slow_until(int& st, int end, const SC& sc) {
+    template <class MS, class SC>
+    __device__ __forceinline__ void slow_until(int& st, int end, const MS& ms, const SC& sc) {
 #pragma unroll 1
         for (; st < end; ++st) {
             if ((st & 15) == 0) refill();
-            step<false>(st, sc);
+            step<false>(st, ms, sc);
         }
     }
 
-    template <class SC>
-    __device__ __forceinline__ void run(const SC& sc, int zone_start_) {
-        zone_start = zone_start_;
-        const int nsteps = t_len + 31;
-        int fast_end = ((t_len - 1) >> 4) << 4;       // steps below it: every lane's column is < t_len - 1
-        if (MODE == kFwd) fast_end = min(fast_end, (zone_start >> 4) << 4);
-        int st = 0;
-        slow_until(st, min(32, nsteps), sc);
-        for (; st + 16 <= fast_end; st += 16) {
+    template <class MS, class SC>
+    __device__ __forceinline__ void fast_until(int& st, int end, const MS& ms, const SC& sc) {
+        for (; st + 16 <= end; st += 16) {       // st is a multiple of 16 here
             refill();
 #pragma unroll 1
             for (int b = 0; b < 16; b += 4) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) step<true>(st + b + u, sc);
+                for (int u = 0; u < 4; ++u) step<true>(st + b + u, ms, sc);
             }
         }
-        slow_until(st, nsteps, sc);
     }
 
-    // kBwd result: (score << 16) + reversed start, and the 1-based reversed end column
-    __device__ __forceinline__ void bwd_best(int& cap, int& rs, int& col) const {
-        const int key = bestor - lane + 1;            // cm + column
-        cap = key & (int)0xffff0000; rs = key & 0xffff; col = best_col();
+    // zone_start_: forward sweeps, first step at which a lane can be at a junction column
+    template <class SC>
+    __device__ __forceinline__ void run(const SC& sc, int zone_start_) {
+        const ModeScore<SC, DEC> ms(sc);
+        init(ms);
+        zone_start = zone_start_;
+        const int nsteps = t_len + 31;
+        int fast_end = ((t_len - 1) >> 4) << 4;       // steps below it: every lane's column is < t_len - 1
+        if (kIsFwd) fast_end = min(fast_end, (zone_start >> 4) << 4);
+        int st = 0;
+        slow_until(st, min(32, nsteps), ms, sc);
+        if (MODE == kFwdF && mark_col >= 0) {
+            // the lanes pass the end of the left flank at steps mark_col .. mark_col + 31: guarded steps
+            fast_until(st, min(fast_end, (mark_col >> 4) << 4), ms, sc);
+            slow_until(st, min(nsteps, ((mark_col + 32 + 15) >> 4) << 4), ms, sc);
+        }
+        fast_until(st, fast_end, ms, sc);
+        slow_until(st, nsteps, ms, sc);
+    }
+
+    // backward sweeps: (score << 16) + DEC * reversed start, and the 1-based reversed end column
+    __device__ __forceinline__ void bwd_best(int& key, int& col) const {
+        key = bestor - DEC * (lane - 1);              // cm + DEC * column
+        col = best_col();
     }
 };
 
@@ -481,13 +571,12 @@ __device__ __forceinline__ u64 exact_task(const Task& tk, const uint32_t* __rest
     u64 key = 0;
     for (int s = 0; s < n_stripes; ++s) {
         __syncwarp();
-        build_profile<R>(prof, qwords, tk.q_len, s * rows_per_stripe + lane * R, lane, sc, false);
+        build_profile<R>(prof, qwords, tk.q_len, s * rows_per_stripe + lane * R, lane, ModeScore<SC, 1>(sc), false);
         __syncwarp();
         Sweep<R, kExact, MULTI> sw;
         sw.prof = prof; sw.twords = pool + tk.t_word; sw.t_len = tk.t_len; sw.lane = lane;
         sw.top = s > 0; sw.bot = s + 1 < n_stripes;
         sw.bnd_in = (s & 1) ? bnd_a : bnd_b; sw.bnd_out = (s & 1) ? bnd_b : bnd_a;
-        sw.init(sc);
         sw.run(sc, 0);
         const u64 k = key_of_best(sw.best, sw.best_col());
         key = k > key ? k : key;
@@ -590,11 +679,23 @@ exact_kernel(const Task* __restrict__ tasks, const int32_t* __restrict__ order, 
     }
 }
 
-template <int R, bool MULTI, class SC>
+// Round 3 for one read: all rungs kmin..kmax from one backward and one forward sweep (file header).
+//
+// FLAG = false: span words everywhere; every rung gets its exact (score, tstart, tend).
+// FLAG = true ("flag ladder", the production path): what the reference looks at per rung is the score and the two span
+// predicates (nanoRepeat_bam.py:423-427), so the words carry just that.  Forward words are (score << 16) - mark, mark =
+// the alignment started inside the left flank (set once, when a lane passes the flank's last column; a later fresh
+// start is unmarked and, being the larger word, wins ties like the larger tstart does).  Backward words are
+// (score << 16) - 2 * ext.  A junction candidate is then ONE VIADDMNMX: forward + backward = (total << 16) - 2 * ext -
+// mark, whose integer order is the contract's (score, smallest tend, largest tstart); the prefix class needs only its
+// best score, so the forward sweep has no per-step best tracking at all.  Output per rung: (score, spans both flanks,
+// ends in right flank).  Needs 2 * |R| < 65536.
+template <int R, bool MULTI, bool FLAG, class SC>
 __device__ __forceinline__ void ladder_task(const LadderTask& tk, const uint32_t* __restrict__ pool,
                                             const LadderRegion& reg, const SC& sc, int4* prof, int lane,
                                             int n_stripes, int4* bnd_a, int4* bnd_b, int4* bglob, ulonglong2* tok_a,
                                             ulonglong2* tok_b, int4* out) {
+    constexpr int BWD = FLAG ? kBwdF : kBwd, FWD = FLAG ? kFwdF : kFwd;
     int4* bsm = prof + StripeCfg<R>::PROF_INT4;
     const int rows_per_stripe = 32 * R;
     const uint32_t* qwords = pool + tk.q_word;
@@ -612,33 +713,38 @@ __device__ __forceinline__ void ladder_task(const LadderTask& tk, const uint32_t
         }
     __syncwarp();
     // ---- backward sweep: reversed read x reversed right flank ----
-    u64 rkey = 0;
+    u64 rkey = 0;       // FLAG: the best (score << 16) + 2 * reversed start, biased by 1 so that 0 means none
     if (reg.n_right > 0) {
         for (int s = 0; s < n_stripes; ++s) {
             __syncwarp();
-            build_profile<R>(prof, qwords, q_len, s * rows_per_stripe + lane * R, lane, sc, true);
+            build_profile<R>(prof, qwords, q_len, s * rows_per_stripe + lane * R, lane, ModeScore<SC, Sweep<R, BWD, MULTI>::DEC>(sc), true);
             __syncwarp();
-            Sweep<R, kBwd, MULTI> sw;
+            Sweep<R, BWD, MULTI> sw;
             sw.prof = prof; sw.twords = pool + reg.rev_word; sw.t_len = reg.n_right; sw.lane = lane;
             sw.top = s > 0; sw.bot = s + 1 < n_stripes;
             sw.bnd_in = (s & 1) ? bnd_a : bnd_b; sw.bnd_out = (s & 1) ? bnd_b : bnd_a;
             sw.bdst = bdst; sw.q_len = q_len; sw.brow0 = s * rows_per_stripe + lane * R;
-            sw.init(sc);
             sw.run(sc, 0);
+            int key, col;
+            sw.bwd_best(key, col);
             u64 k = 0;
-            int cap, rs, col;
-            sw.bwd_best(cap, rs, col);
-            if (cap > 0)
-                k = ((u64)((unsigned)cap >> 16) << 32) | ((u64)(unsigned)rs << 16) | (u64)(0xffffu - (unsigned)col);
+            if (key >= 65536) {     // a positive score
+                if (FLAG) k = (u64)(unsigned)key;
+                else k = ((u64)((unsigned)key >> 16) << 32) | ((u64)((unsigned)key & 0xffffu) << 16) | (u64)(0xffffu - (unsigned)col);
+            }
             rkey = k > rkey ? k : rkey;
         }
         rkey = warp_max64(rkey);
     }
-    int r_score = 0, r_end = 0, r_start = 0;
+    int r_score = 0, r_end = 0, r_start = 0, rcand = kJuncNone;
     if (rkey) {
-        r_score = (int)(rkey >> 32);
-        r_end = reg.n_right - (int)((rkey >> 16) & 0xffffu);             // forward end inside R (exclusive)
-        r_start = reg.n_right - (0xffff - (int)(rkey & 0xffffu));        // forward start inside R
+        if (FLAG) {
+            rcand = (int)(unsigned)rkey - 2 * reg.n_right;                   // (score << 16) - 2 * (forward end inside R)
+        } else {
+            r_score = (int)(rkey >> 32);
+            r_end = reg.n_right - (int)((rkey >> 16) & 0xffffu);             // forward end inside R (exclusive)
+            r_start = reg.n_right - (0xffff - (int)(rkey & 0xffffu));        // forward start inside R
+        }
     }
     // ---- forward sweep over L + motif^kmax with junction tokens ----
     const int c_first = reg.n_left + reg.m * tk.kmin;
@@ -647,13 +753,13 @@ __device__ __forceinline__ void ladder_task(const LadderTask& tk, const uint32_t
     if (t_len > 0) {
         for (int s = 0; s < n_stripes; ++s) {
             __syncwarp();
-            build_profile<R>(prof, qwords, q_len, s * rows_per_stripe + lane * R, lane, sc, false);
+            build_profile<R>(prof, qwords, q_len, s * rows_per_stripe + lane * R, lane, ModeScore<SC, Sweep<R, FWD, MULTI>::DEC>(sc), false);
             if (MULTI) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) bsm[r * 32 + lane] = __ldcg(&bglob[s * rows_per_stripe + r * 32 + lane]);
             }
             __syncwarp();
-            Sweep<R, kFwd, MULTI> sw;
+            Sweep<R, FWD, MULTI> sw;
             sw.prof = prof; sw.twords = pool + reg.fwd_word; sw.t_len = t_len; sw.lane = lane;
             sw.top = s > 0; sw.bot = s + 1 < n_stripes;
             sw.bnd_in = (s & 1) ? bnd_a : bnd_b; sw.bnd_out = (s & 1) ? bnd_b : bnd_a;
@@ -664,27 +770,28 @@ __device__ __forceinline__ void ladder_task(const LadderTask& tk, const uint32_t
             sw.jnext = c_first > 0 ? c_first : reg.m;     // a junction at column 0 has no forward part
             sw.kcnt = c_first > 0 ? 0 : 1;
             sw.r_score = r_score; sw.r_end = r_end; sw.r_start = r_start;
-            sw.init(sc);
+            sw.rcand = rcand; sw.mark_col = reg.n_left - 1;
             sw.run(sc, sw.jnext - 1);
         }
     }
-    if (c_first == 0 && lane == 0) outp[0] = finalize_rung(0ull, 0ull, 0, r_score, r_end, r_start);
+    if (c_first == 0 && lane == 0)
+        outp[0] = FLAG ? finalize_flag_rung(0, kJuncNone, rcand) : finalize_rung(0ull, 0ull, 0, r_score, r_end, r_start);
 }
 
-template <int R, bool MULTI, class SC>
+template <int R, bool MULTI, bool FLAG, class SC>
 __device__ __forceinline__ void ladder_dispatch(int r, const LadderTask& tk, const uint32_t* __restrict__ pool,
                                                 const LadderRegion& reg, const SC& sc, int4* prof, int lane,
                                                 int n_stripes, int4* bnd_a, int4* bnd_b, int4* bglob,
                                                 ulonglong2* tok_a, ulonglong2* tok_b, int4* out) {
-    if (r == R) { ladder_task<R, MULTI>(tk, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out); return; }
+    if (r == R) { ladder_task<R, MULTI, FLAG>(tk, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out); return; }
     if constexpr (R < kMaxRLadder)
-        ladder_dispatch<R + 1, MULTI>(r, tk, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out);
+        ladder_dispatch<R + 1, MULTI, FLAG>(r, tk, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out);
 }
 
 // Round-3 ladder kernel: one warp per read, all rungs kmin..kmax from one backward and one forward sweep.
 // scratch (multi-stripe reads only), per warp: 2 boundary rows of bnd_stride int4, b_stride int4 of backward
 // vectors, 2 token rows of tok_stride ulonglong2.
-template <bool FIXED>
+template <bool FIXED, bool FLAG>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock, 1)
 ladder_kernel(const LadderTask* __restrict__ tasks, const int32_t* __restrict__ order, int n_order, int n_excl,
               const uint32_t* __restrict__ pool, const LadderRegion* __restrict__ regs, ScoreW scw, int* counter,
@@ -712,9 +819,9 @@ ladder_kernel(const LadderTask* __restrict__ tasks, const int32_t* __restrict__ 
             int R, n_stripes;
             stripe_shape(tk.q_len, kMaxRLadder, R, n_stripes);
             if (n_stripes > 1)
-                ladder_dispatch<kMinRMultiLadder, true>(R, tk, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out);
+                ladder_dispatch<kMinRMultiLadder, true, FLAG>(R, tk, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out);
             else
-                ladder_dispatch<kMinR, false>(R, tk, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out);
+                ladder_dispatch<kMinR, false, FLAG>(R, tk, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out);
         }
         cur.done();
     }

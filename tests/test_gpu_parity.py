@@ -148,8 +148,30 @@ def test_round3_rungs_match_oracle(engine, oracle):
             k = int(kmin[r]) + i - int(off[r])
             a = ref[i]
             assert int(rungs[i]["score"]) == int(a["score"])
-            assert bool(rungs[i]["starts_in_left"]) == (a["score"] > 0 and a["tstart"] < nl)
-            assert bool(rungs[i]["ends_in_right"]) == (a["score"] > 0 and (nl + m * k + nr_) - a["tend"] < nr_)
+            in_right = bool(a["score"] > 0 and (nl + m * k + nr_) - a["tend"] < nr_)
+            assert bool(rungs[i]["ends_in_right"]) == in_right
+            assert bool(rungs[i]["starts_in_left"]) == bool(in_right and a["tstart"] < nl)     # conjunction (:427)
+
+
+def _assert_flag_ladder(b, ref, roff, kmin, n_left, n_right, m, min_score, ctx):
+    """Flag ladder (mode 2) == oracle on what the reference reads per rung (score, span predicates, :423-427) and on
+    the selection (top score, tied rungs that span both flanks)."""
+    sum_k, n_k, top, rungs, off = b.fetch_round3(want_rungs=True)
+    assert np.array_equal(off, roff), ctx
+    assert np.array_equal(rungs["score"], ref["score"]), ctx
+    for r in range(len(kmin)):
+        lo, hi = int(off[r]), int(off[r + 1])
+        ks = np.arange(hi - lo) + int(kmin[r])
+        a = ref[lo:hi]
+        tlen = n_left + m * ks + n_right
+        in_right = (a["score"] > 0) & (tlen - a["tend"] < n_right)
+        in_left = in_right & (a["tstart"] < n_left)
+        assert np.array_equal(rungs["ends_in_right"][lo:hi].astype(bool), in_right), (ctx, r)
+        assert np.array_equal(rungs["starts_in_left"][lo:hi].astype(bool), in_left), (ctx, r)
+        ok = a["score"] >= max(1, min_score)
+        t = int(a["score"][ok].max()) if ok.any() else 0
+        sel = ks[(a["score"] == t) & in_left] if t > 0 else ks[:0]
+        assert (int(top[r]), int(n_k[r]), int(sum_k[r])) == (t, len(sel), int(sel.sum())), (ctx, r)
 
 
 def _ladder_case(rng, n_left, n_right, m, n_reads, kspan, qmode):
@@ -185,14 +207,19 @@ def test_ladder_shared_sweeps_equal_independent_rectangles(engine, oracle, seed,
     ref, roff = oracle.align_ladders(cores, left, right, motif, kmin, kmax, n_threads=oracle.max_threads())
     got = {}
     try:
-        for mode in (1, 0):
+        for mode in (2, 1, 0):
             engine.set_ladder_mode(mode)
             b = engine.Batch.round3(sc, left, right, motif, cores, kmin, kmax)
             b.run()
-            got[mode] = b.fetch_alns()
+            if mode == 2:
+                _assert_flag_ladder(b, ref, roff, kmin, n_left, n_right, m, sc.min_dp_score, f"flag ladder, seed {seed}")
+                with pytest.raises(engine.NanoRepeatB200Error):
+                    b.fetch_alns()                      # no coordinates on flag words
+            else:
+                got[mode] = b.fetch_alns()
             b.close()
     finally:
-        engine.set_ladder_mode(1)
+        engine.set_ladder_mode(2)
     _assert_same(got[0], ref, f"independent rectangles, seed {seed}")
     _assert_same(got[1], ref, f"shared sweeps, seed {seed}")
 
@@ -250,13 +277,21 @@ def test_ladder_long_expanded_allele(engine, oracle):
     kmin = np.array([470, 490, 515], np.int32)
     kmax = np.array([486, 506, 530], np.int32)
     sc = engine.get_preset("ont")
-    ref, _ = oracle.align_ladders(cores, L, R, "CGG", kmin, kmax, n_threads=oracle.max_threads())
-    b = engine.Batch.round3(sc, L, R, "CGG", cores, kmin, kmax)
-    b.run()
-    _assert_same(b.fetch_alns(), ref, "long ladder")
-    st = b.stats()
-    assert st["executed_cells"] * 5 < st["algorithmic_cells"]
-    b.close()
+    ref, roff = oracle.align_ladders(cores, L, R, "CGG", kmin, kmax, n_threads=oracle.max_threads())
+    try:
+        for mode in (2, 1):
+            engine.set_ladder_mode(mode)
+            b = engine.Batch.round3(sc, L, R, "CGG", cores, kmin, kmax)
+            b.run()
+            if mode == 2:
+                _assert_flag_ladder(b, ref, roff, kmin, 1000, 1000, 3, sc.min_dp_score, "long flag ladder")
+            else:
+                _assert_same(b.fetch_alns(), ref, "long ladder")
+            st = b.stats()
+            assert st["executed_cells"] * 5 < st["algorithmic_cells"]
+            b.close()
+    finally:
+        engine.set_ladder_mode(2)
 
 
 @pytest.mark.parametrize("name", GOLDEN_SETS)
