@@ -159,6 +159,16 @@ int nr_batch_add_round2(nr_batch_t* b, const char* left, int32_t n_left, const c
 int nr_batch_add_round3(nr_batch_t* b, const char* left, int32_t n_left, const char* right, int32_t n_right,
                         const char* motif, int32_t motif_len, int32_t n_reads, const char* cores_concat,
                         const int64_t* core_off, const int32_t* kmin, const int32_t* kmax);
+/*
+ * Round 3 over the reads of a committed round-2 batch: the reads stay packed in HBM, only templates and per-read ladder
+ * bounds are uploaded (the reference writes every core to disk twice, nanoRepeat_bam.py:311-321 and :487-493).
+ * region_index = position of the region among the round-2 batch's nr_batch_add_round2 calls; kmin / kmax cover all
+ * reads of that region in order, kmax < kmin skips a read (round 2 gave it no size, :460).  The round-2 batch may be
+ * destroyed at any time; its device buffers live until the last batch that reads them is destroyed.
+ */
+nr_batch_t* nr_batch_begin_round3_from(nr_batch_t* round2);
+int nr_batch_add_round3_reuse(nr_batch_t* b, int32_t region_index, const char* right, int32_t n_right,
+                              const int32_t* kmin, const int32_t* kmax);
 int nr_batch_commit(nr_batch_t* b);
 int nr_batch_run(nr_batch_t* b, void* stream);
 int nr_batch_fetch_alns(nr_batch_t* b, nr_aln_t* out);                      /* tasks / round2 batches */

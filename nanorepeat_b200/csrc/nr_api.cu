@@ -18,6 +18,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -121,20 +122,74 @@ void cached_free(void* p, size_t bytes, bool pinned) {
 }
 
 // ---- 2-bit packing -------------------------------------------------------------------------------------------
-struct CodeTable {
+// 2-bit code of a base: (c >> 1) & 3  ->  A/a 0, C/c 1, T/t 2, G/g 3 (any bijection does: queries and targets go
+// through the same packer).  Validity comes from a table.
+struct BadTable {
     uint8_t t[256];
-    CodeTable() {
-        memset(t, 0x80, sizeof t);     // bit 7 = not ACGT
-        t[(int)'A'] = t[(int)'a'] = 0;
-        t[(int)'C'] = t[(int)'c'] = 1;
-        t[(int)'G'] = t[(int)'g'] = 2;
-        t[(int)'T'] = t[(int)'t'] = 3;
+    BadTable() {
+        memset(t, 1, sizeof t);
+        for (const char* p = "ACGTacgt"; *p; ++p) t[(unsigned char)*p] = 0;
     }
 };
-const CodeTable g_codes;
+const BadTable g_bad;
 
-// Sequence pool: 16 bases per 32-bit word, MSB first: base i of a sequence at bits 30 - 2*(i%16) of word i/16.  Every sequence
-// starts on a word boundary and is followed by one zero slack word (kernels prefetch one word ahead).
+#if defined(__x86_64__)
+__attribute__((target("bmi2"))) uint32_t pack16_bmi2(const unsigned char* u) {
+    uint64_t a, c;
+    memcpy(&a, u, 8);
+    memcpy(&c, u + 8, 8);
+    a = __builtin_bswap64(a);                         // first base -> highest byte -> highest bit pair
+    c = __builtin_bswap64(c);
+    return ((uint32_t)__builtin_ia32_pext_di(a, 0x0606060606060606ull) << 16) |
+           (uint32_t)__builtin_ia32_pext_di(c, 0x0606060606060606ull);
+}
+const bool g_have_bmi2 = __builtin_cpu_supports("bmi2");
+#else
+const bool g_have_bmi2 = false;
+#endif
+
+// Pack one sequence: 16 bases per 32-bit word, MSB first (base i at bits 30 - 2*(i%16) of word i/16).
+// w must hold (len + 15) / 16 words.  Returns false on a character other than ACGTacgt.
+bool pack_seq(const char* s, int len, uint32_t* w) {
+    const unsigned char* u = reinterpret_cast<const unsigned char*>(s);
+    unsigned bad = 0;
+    int i = 0;
+    for (; i + 16 <= len; i += 16) {
+        for (int j = 0; j < 16; ++j) bad |= g_bad.t[u[i + j]];
+#if defined(__x86_64__)
+        if (g_have_bmi2) { w[i >> 4] = pack16_bmi2(u + i); continue; }
+#endif
+        uint32_t v = 0;
+        for (int j = 0; j < 16; ++j) v |= ((u[i + j] >> 1) & 3u) << (30 - 2 * j);
+        w[i >> 4] = v;
+    }
+    if (i < len) {
+        uint32_t v = 0;
+        for (int j = 0; i + j < len; ++j) {
+            bad |= g_bad.t[u[i + j]];
+            v |= ((u[i + j] >> 1) & 3u) << (30 - 2 * j);
+        }
+        w[i >> 4] = v;
+    }
+    return bad == 0;
+}
+
+// fn(i) for i in [0, n) on a few host threads (packing thousands of reads is the host's largest cost per call)
+template <class F>
+void parallel_for(int n, int grain, F fn) {
+    int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u);
+    nt = std::min(nt, std::max(1, n / std::max(1, grain)));
+    if (nt <= 1) { for (int i = 0; i < n; ++i) fn(i); return; }
+    std::vector<std::thread> th;
+    th.reserve(nt - 1);
+    auto body = [&](int t) { for (int i = (int)((long long)n * t / nt), e = (int)((long long)n * (t + 1) / nt); i < e; ++i) fn(i); };
+    for (int t = 1; t < nt; ++t) th.emplace_back(body, t);
+    body(0);
+    for (auto& x : th) x.join();
+}
+
+// Sequence pool.  Every sequence starts on a word boundary and is followed by one zero slack word (kernels prefetch
+// one word ahead).
 struct Pool {
     std::vector<uint32_t> words;
     // append; returns first word index, or -1 on a non-ACGT character
@@ -142,29 +197,7 @@ struct Pool {
         const size_t w0 = words.size();
         const size_t nw = (size_t)(len + 15) / 16 + 1;
         words.resize(w0 + nw, 0u);
-        uint32_t* w = words.data() + w0;
-        const unsigned char* u = reinterpret_cast<const unsigned char*>(s);
-        unsigned bad = 0;
-        int i = 0;
-        for (; i + 16 <= len; i += 16) {
-            uint32_t v = 0;
-            for (int j = 0; j < 16; ++j) {
-                const unsigned c = g_codes.t[u[i + j]];
-                bad |= c;
-                v |= (c & 3u) << (30 - 2 * j);
-            }
-            w[i >> 4] = v;
-        }
-        if (i < len) {
-            uint32_t v = 0;
-            for (int j = 0; i + j < len; ++j) {
-                const unsigned c = g_codes.t[u[i + j]];
-                bad |= c;
-                v |= (c & 3u) << (30 - 2 * j);
-            }
-            w[i >> 4] = v;
-        }
-        if (bad & 0x80u) { words.resize(w0); return -1; }
+        if (!pack_seq(s, len, words.data() + w0)) { words.resize(w0); return -1; }
         return (long long)w0;
     }
 };
@@ -184,6 +217,7 @@ struct Launch {      // one persistent launch per batch
 struct RegionInfo {   // one add_round2 / add_round3 call
     int n_left = 0, n_right = 0, motif_len = 0;
     int first_read = 0, n_reads = 0;
+    std::string left, motif;      // round 2 keeps them for a round-3 batch built over the same reads
 };
 
 }  // namespace
@@ -224,9 +258,15 @@ struct nr_batch {
     int4* d_scratch = nullptr;
     size_t scratch_bytes = 0;
     int4* h_out = nullptr;                    // pinned
+    int4* d_sel = nullptr;                    // flag ladder: per read (top score, n tied, sum k lo, sum k hi)
+    int4* h_sel = nullptr;                    // pinned
+    size_t sel_bytes = 0;
     nr_stats_t stats = {};
     bool ran = false;
     cudaStream_t run_stream = nullptr;        // stream of the last nr_batch_run: fetch orders itself behind it
+    cudaEvent_t ev_uploaded = nullptr;        // recorded behind the upload on the library's stream
+    int refs = 1;                             // the owner + round-3 batches that read this batch's packed reads
+    nr_batch* qsrc = nullptr;                 // round 3: the committed round-2 batch whose reads are reused
 };
 
 namespace {
@@ -263,6 +303,7 @@ nr::ScoreW score_words(const nr_scoring_t& sc) {
     k.one = 1;
     k.mone = -1;
     k.four = 4u;
+    k.min_score = std::max(1, sc.min_dp_score);
     return k;
 }
 
@@ -364,6 +405,11 @@ int plan_batch(nr_batch* b) {
     if ((rc = cached_alloc((void**)&b->d_out, b->out_bytes, false))) return rc;
     if ((rc = cached_alloc((void**)&b->h_out, b->out_bytes, true))) return rc;
     if (scratch_total && (rc = cached_alloc((void**)&b->d_scratch, b->scratch_bytes, false))) return rc;
+    if (b->flag) {
+        b->sel_bytes = sizeof(int4) * std::max<size_t>((size_t)b->n_reads, 1);
+        if ((rc = cached_alloc((void**)&b->d_sel, b->sel_bytes, false))) return rc;
+        if ((rc = cached_alloc((void**)&b->h_sel, b->sel_bytes, true))) return rc;
+    }
     char* h = static_cast<char*>(b->h_blob);
     char* d = static_cast<char*>(b->d_blob);
     if (task_bytes) memcpy(h, ladder ? (const void*)b->ltasks.data() : (const void*)b->tasks.data(), task_bytes);
@@ -381,9 +427,10 @@ int plan_batch(nr_batch* b) {
     cudaStream_t st = g_ctx.stream;
     CUDA_TRY(cudaMemcpyAsync(d, h, b->blob_bytes, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(b->d_out, 0, b->out_bytes, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    if (b->d_sel) CUDA_TRY(cudaMemsetAsync(b->d_sel, 0, b->sel_bytes, st));
+    CUDA_TRY(cudaEventRecord(b->ev_uploaded, st));      // nr_batch_run on another stream waits for it; no host sync here
     b->stats.h2d_bytes = (int64_t)(task_bytes + reg_bytes + order_bytes + pool_bytes);
-    b->stats.d2h_bytes = (int64_t)sizeof(int4) * (int64_t)b->n_out;
+    b->stats.d2h_bytes = (int64_t)sizeof(int4) * (b->flag ? (int64_t)b->n_reads : (int64_t)b->n_out);
     b->committed = true;
     return NR_OK;
 }
@@ -394,6 +441,10 @@ int run_batch(nr_batch* b, cudaStream_t st) {
     const Launch& L = b->launch;
     if (!L.count) { b->ran = true; return NR_OK; }
     const nr::ScoreW k = score_words(b->sc);
+    if (st != g_ctx.stream) {                 // the upload (and the reused round-2 pool's) ran on the library's stream
+        CUDA_TRY(cudaStreamWaitEvent(st, b->ev_uploaded, 0));
+        if (b->qsrc) CUDA_TRY(cudaStreamWaitEvent(st, b->qsrc->ev_uploaded, 0));
+    }
     CUDA_TRY(cudaMemsetAsync(b->d_counters, 0, sizeof(int), st));
     if (L.ladder) {
         auto fn = b->flag ? (L.fixed ? nr::ladder_kernel<true, true> : nr::ladder_kernel<false, true>)
@@ -401,9 +452,10 @@ int run_batch(nr_batch* b, cudaStream_t st) {
         const int stride = ladder_smem_int4(L.R);
         const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
         CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fn<<<L.blocks, kWarpsPerBlock * 32, smem, st>>>(b->d_ltasks, b->d_order, L.count, L.n_excl, b->d_pool, b->d_lregs, k,
+        fn<<<L.blocks, kWarpsPerBlock * 32, smem, st>>>(b->d_ltasks, b->d_order, L.count, L.n_excl,
+                                                       b->qsrc ? b->qsrc->d_pool : b->d_pool, b->d_pool, b->d_lregs, k,
                                                        b->d_counters, stride, b->d_scratch, L.scratch_stride,
-                                                       L.b_stride, L.tok_stride, b->d_out);
+                                                       L.b_stride, L.tok_stride, b->d_out, b->d_sel);
     } else {
         auto fn = L.fixed ? nr::exact_kernel<true> : nr::exact_kernel<false>;
         const int stride = exact_smem_int4(L.R);
@@ -448,11 +500,41 @@ struct ReadSrc {
     long long len(int r) const { return cores ? (long long)core_len[r] : (long long)(off[r + 1] - off[r]); }
 };
 
+// Pack n_reads reads into the pool (in parallel); q_word[r] = first word of read r.
+int add_reads(nr_batch* b, const ReadSrc& src, int n_reads, std::vector<uint32_t>& q_word) {
+    q_word.resize(n_reads);
+    size_t w = b->pool.words.size();
+    const size_t w0 = w;
+    for (int r = 0; r < n_reads; ++r) {
+        const long long len = src.len(r);
+        if (len < 0 || len > 0x7fffffffLL) return fail(NR_ERR_ARG, "core %d has a bad length", r);
+        if (len > 0 && !src.ptr(r)) return fail(NR_ERR_ARG, "core %d is NULL", r);
+        if (w > 0xfffffff0ULL) return fail(NR_ERR_TOO_LARGE, "sequence pool exceeds 2^32 words");
+        q_word[r] = (uint32_t)w;
+        w += (size_t)(len + 15) / 16 + 1;
+    }
+    b->pool.words.resize(w, 0u);
+    uint32_t* words = b->pool.words.data();
+    std::atomic<int> bad{-1};
+    parallel_for(n_reads, 512, [&](int r) {
+        if (!pack_seq(src.ptr(r), (int)src.len(r), words + q_word[r])) {
+            int expect = -1;
+            bad.compare_exchange_strong(expect, r);
+        }
+    });
+    if (bad.load() >= 0) {
+        b->pool.words.resize(w0);
+        return fail(NR_ERR_BAD_BASE, "core %d contains a character other than ACGT", bad.load());
+    }
+    return NR_OK;
+}
+
 int add_round2(nr_batch* b, const char* left, int32_t n_left, const char* motif, int32_t motif_len, int32_t T,
                int32_t n_reads, const ReadSrc& src) {
     if (!b || b->kind != KIND_ROUND2 || b->committed) return fail(NR_ERR_ARG, "not an open round-2 batch");
     if (n_left < 0 || motif_len <= 0 || T < 0 || n_reads < 0 || !motif || (n_left > 0 && !left))
         return fail(NR_ERR_ARG, "nr_batch_add_round2: bad arguments");
+    const size_t pool0 = b->pool.words.size();
     // template = left + motif * T   (nanoRepeat_bam.py:352-354)
     std::string tpl(left ? left : "", (size_t)n_left);
     tpl.reserve((size_t)n_left + (size_t)motif_len * T);
@@ -462,15 +544,22 @@ int add_round2(nr_batch* b, const char* left, int32_t n_left, const char* motif,
     if ((rc = add_seq(b, tpl.data(), (int)tpl.size(), "round-2 template", 0, &tw))) return rc;
     RegionInfo g;
     g.n_left = n_left; g.motif_len = motif_len; g.first_read = b->n_reads; g.n_reads = n_reads;
+    g.left.assign(left ? left : "", (size_t)n_left);
+    g.motif.assign(motif, (size_t)motif_len);
     b->regions.push_back(g);
     const size_t base = b->tasks.size();
     b->tasks.resize(base + n_reads);
+    std::vector<uint32_t> qw;
+    if ((rc = add_reads(b, src, n_reads, qw))) {     // leave the batch as it was: the caller may retry this region
+        b->tasks.resize(base);
+        b->regions.pop_back();
+        b->pool.words.resize(pool0);
+        return rc;
+    }
     for (int r = 0; r < n_reads; ++r) {
         nr::Task& t = b->tasks[base + r];
-        const long long len = src.len(r);
-        if (len < 0 || len > 0x7fffffffLL) return fail(NR_ERR_ARG, "core %d has a bad length", r);
-        if ((rc = add_seq(b, src.ptr(r), (int)len, "core", r, &t.q_word))) return rc;
-        t.q_len = (int)len;
+        t.q_word = qw[r];
+        t.q_len = (int)src.len(r);
         t.t_word = tw;
         t.t_len = (int)tpl.size();
     }
@@ -478,8 +567,10 @@ int add_round2(nr_batch* b, const char* left, int32_t n_left, const char* motif,
     return NR_OK;
 }
 
+// reuse != NULL: the reads are tasks of the round-2 batch b->qsrc (already packed, already in HBM)
 int add_round3(nr_batch* b, const char* left, int32_t n_left, const char* right, int32_t n_right, const char* motif,
-               int32_t motif_len, int32_t n_reads, const ReadSrc& src, const int32_t* kmin, const int32_t* kmax) {
+               int32_t motif_len, int32_t n_reads, const ReadSrc& src, const int32_t* kmin, const int32_t* kmax,
+               const nr::Task* reuse = nullptr) {
     if (!b || b->kind != KIND_ROUND3 || b->committed) return fail(NR_ERR_ARG, "not an open round-3 batch");
     if (n_left < 0 || n_right < 0 || motif_len <= 0 || n_reads < 0 || !motif || (n_left > 0 && !left) ||
         (n_right > 0 && !right) || (n_reads > 0 && (!kmin || !kmax)))
@@ -519,22 +610,24 @@ int add_round3(nr_batch* b, const char* left, int32_t n_left, const char* right,
         if ((rc = add_seq(b, rev.data(), (int)rev.size(), "right anchor", 0, &lr.rev_word))) return rc;
         const int lreg = (int)b->lregs.size();
         b->lregs.push_back(lr);
+        std::vector<uint32_t> qw;
+        if (!reuse && (rc = add_reads(b, src, n_reads, qw))) return rc;
         for (int r = 0; r < n_reads; ++r) {
             if (roff[r + 1] == roff[r]) continue;
-            const long long len = src.len(r);
-            if (len < 0 || len > 0x7fffffffLL) return fail(NR_ERR_ARG, "core %d has a bad length", r);
-            if (len == 0) continue;     // every rung scores 0: d_out is zero-filled
             nr::LadderTask t = {};
-            if ((rc = add_seq(b, src.ptr(r), (int)len, "core", r, &t.q_word))) return rc;
-            t.q_len = (int)len;
+            if (reuse) { t.q_word = reuse[r].q_word; t.q_len = reuse[r].q_len; }
+            else { t.q_word = qw[r]; t.q_len = (int)src.len(r); }
+            if (t.q_len == 0) continue;     // every rung scores 0: the outputs are zero-filled
             t.kmin = kmin[r];
             t.kmax = kmax[r];
             t.out_off = (int32_t)roff[r];
             t.region = lreg;
+            t.read = first + r;
             b->ltasks.push_back(t);
         }
         return NR_OK;
     }
+    if (reuse) return fail(NR_ERR_ARG, "reads of a round-2 batch can only be reused by the ladder kernels (nr_set_ladder_mode 1 or 2)");
     // independent rectangles: left + motif*k + right, one template per distinct k that any read of the region uses
     // (nanoRepeat_bam.py:478-479)
     std::vector<uint32_t> tpl_word;
@@ -575,6 +668,11 @@ nr_batch* new_batch(const nr_scoring_t* sc, BatchKind kind) {
     if (ensure_init(-1)) return nullptr;
     nr_batch* b = new (std::nothrow) nr_batch();
     if (!b) { fail(NR_ERR_NOMEM, "out of host memory"); return nullptr; }
+    if (cudaEventCreateWithFlags(&b->ev_uploaded, cudaEventDisableTiming) != cudaSuccess) {
+        fail(NR_ERR_CUDA, "cudaEventCreate failed");
+        delete b;
+        return nullptr;
+    }
     b->kind = kind;
     b->sc = *sc;
     b->ladder = kind == KIND_ROUND3 && g_ladder_mode.load() != 0;
@@ -639,13 +737,50 @@ int nr_limits(int32_t* max_score, int32_t* max_tlen) {
 
 void nr_batch_destroy(nr_batch_t* b) {
     if (!b) return;
-    if (b->ran && b->run_stream) cudaStreamSynchronize(b->run_stream);   // buffers return to the cache: kernels must be done
+    if (--b->refs > 0) return;           // a round-3 batch still reads this batch's packed reads: freed with it
+    if (b->committed && b->ev_uploaded) cudaEventSynchronize(b->ev_uploaded);   // buffers return to the cache: the upload
+    if (b->ran && b->run_stream) cudaStreamSynchronize(b->run_stream);          // and the kernels must be done
     cached_free(b->d_blob, b->blob_bytes, false);
     cached_free(b->h_blob, b->blob_bytes, true);
     cached_free(b->d_out, b->out_bytes, false);
     cached_free(b->h_out, b->out_bytes, true);
     cached_free(b->d_scratch, b->scratch_bytes, false);
+    cached_free(b->d_sel, b->sel_bytes, false);
+    cached_free(b->h_sel, b->sel_bytes, true);
+    nr_batch* src = b->qsrc;
+    if (b->ev_uploaded) cudaEventDestroy(b->ev_uploaded);
     delete b;
+    if (src) nr_batch_destroy(src);
+}
+
+nr_batch_t* nr_batch_begin_round3_from(nr_batch_t* round2) {
+    if (!round2 || round2->kind != KIND_ROUND2 || !round2->committed) {
+        fail(NR_ERR_ARG, "nr_batch_begin_round3_from: needs a committed round-2 batch");
+        return nullptr;
+    }
+    nr_batch* b = new_batch(&round2->sc, KIND_ROUND3);
+    if (!b) return nullptr;
+    if (!b->ladder) {
+        fail(NR_ERR_ARG, "nr_batch_begin_round3_from: needs a ladder mode (nr_set_ladder_mode 1 or 2)");
+        cudaEventDestroy(b->ev_uploaded);
+        delete b;
+        return nullptr;
+    }
+    b->qsrc = round2;
+    ++round2->refs;
+    return b;
+}
+
+int nr_batch_add_round3_reuse(nr_batch_t* b, int32_t region_index, const char* right, int32_t n_right,
+                              const int32_t* kmin, const int32_t* kmax) {
+    if (!b || !b->qsrc) return fail(NR_ERR_ARG, "nr_batch_add_round3_reuse: batch was not begun with nr_batch_begin_round3_from");
+    const nr_batch* src = b->qsrc;
+    if (region_index < 0 || region_index >= (int)src->regions.size())
+        return fail(NR_ERR_ARG, "nr_batch_add_round3_reuse: region %d is not in the round-2 batch", region_index);
+    const RegionInfo& g = src->regions[region_index];
+    ReadSrc none = {nullptr, nullptr, nullptr, nullptr};
+    return add_round3(b, g.left.data(), g.n_left, right, n_right, g.motif.data(), g.motif_len, g.n_reads, none, kmin, kmax,
+                      src->tasks.data() + g.first_read);
 }
 
 nr_batch_t* nr_batch_begin(const nr_scoring_t* sc, int32_t kind) {
@@ -667,6 +802,7 @@ int nr_batch_add_round3(nr_batch_t* b, const char* left, int32_t n_left, const c
                         const char* motif, int32_t motif_len, int32_t n_reads, const char* cores_concat,
                         const int64_t* core_off, const int32_t* kmin, const int32_t* kmax) {
     if (n_reads > 0 && (!cores_concat || !core_off)) return fail(NR_ERR_ARG, "nr_batch_add_round3: NULL reads");
+    if (b && b->qsrc) return fail(NR_ERR_ARG, "nr_batch_add_round3: this batch reuses a round-2 batch's reads (nr_batch_add_round3_reuse)");
     ReadSrc src = {nullptr, nullptr, cores_concat, core_off};
     return add_round3(b, left, n_left, right, n_right, motif, motif_len, n_reads, src, kmin, kmax);
 }
@@ -755,6 +891,36 @@ int nr_batch_fetch_round3(nr_batch_t* b, const int64_t* rung_offset, nr_rung_t* 
     if (!b || b->kind != KIND_ROUND3) return fail(NR_ERR_ARG, "nr_batch_fetch_round3: not a round-3 batch");
     if (b->n_reads > 0 && (!sum_k || !n_k || !top_score)) return fail(NR_ERR_ARG, "nr_batch_fetch_round3: NULL output");
     if (rungs && !rung_offset) return fail(NR_ERR_ARG, "rungs given without rung_offset");
+    if (b->flag) {
+        // the kernel selected per read (nr_kernels.cuh, Sweep::select_rung); the rung records cross the bus only on request
+        if (!b->ran) return fail(NR_ERR_ARG, "batch was not run");
+        cudaStream_t st = b->run_stream ? b->run_stream : g_ctx.stream;
+        if (b->n_reads) CUDA_TRY(cudaMemcpyAsync(b->h_sel, b->d_sel, sizeof(int4) * b->n_reads, cudaMemcpyDeviceToHost, st));
+        if (rungs && b->n_out) CUDA_TRY(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(int4) * b->n_out, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        for (int r = 0; r < b->n_reads; ++r) {
+            const int4 v = b->h_sel[r];
+            top_score[r] = v.x;
+            n_k[r] = v.y;
+            sum_k[r] = (int64_t)(((uint64_t)(uint32_t)v.w << 32) | (uint32_t)v.z);
+        }
+        if (rungs) {
+            for (int r = 0; r < b->n_reads; ++r) {
+                const int64_t o = b->rung_off[r];
+                const int n = (int)(b->rung_off[r + 1] - o);
+                for (int i = 0; i < n; ++i) {
+                    const int4 a = b->h_out[o + i];
+                    nr_rung_t& rg = rungs[rung_offset[r] + i];
+                    rg.score = a.x;
+                    rg.starts_in_left = a.y != 0;
+                    rg.ends_in_right = a.z != 0;
+                    rg.pad[0] = rg.pad[1] = 0;
+                }
+            }
+        }
+        b->stats.d2h_bytes = (int64_t)sizeof(int4) * (b->n_reads + (rungs ? (int64_t)b->n_out : 0));
+        return NR_OK;
+    }
     int rc = fetch_raw(b);
     if (rc) return rc;
     const int min_score = std::max(1, b->sc.min_dp_score);
@@ -773,14 +939,8 @@ int nr_batch_fetch_round3(nr_batch_t* b, const int64_t* rung_offset, nr_rung_t* 
             const int4 a = b->h_out[o + i];
             const int k = b->kmin[r] + i;
             const int tlen = g.n_left + g.motif_len * k + g.n_right;
-            bool in_left, in_right;
-            if (b->flag) {
-                in_right = a.z != 0;
-                in_left = a.y != 0;
-            } else {
-                in_right = a.x > 0 && tlen - a.z < g.n_right;             // tlen - tend < |right|  (:427)
-                in_left = in_right && a.y < g.n_left;                     // tstart < |left|; reported only with in_right
-            }
+            const bool in_right = a.x > 0 && tlen - a.z < g.n_right;     // tlen - tend < |right|  (:427)
+            const bool in_left = in_right && a.y < g.n_left;             // tstart < |left|; reported only with in_right
             if (rungs) {
                 nr_rung_t& rg = rungs[rung_offset[r] + i];
                 rg.score = a.x;
@@ -788,7 +948,7 @@ int nr_batch_fetch_round3(nr_batch_t* b, const int64_t* rung_offset, nr_rung_t* 
                 rg.ends_in_right = in_right;
                 rg.pad[0] = rg.pad[1] = 0;
             }
-            if (top > 0 && a.x == top && in_left && in_right) { sum += k; ++cnt; }
+            if (top > 0 && a.x == top && in_left) { sum += k; ++cnt; }
         }
         sum_k[r] = sum;
         n_k[r] = cnt;

@@ -44,7 +44,8 @@ struct LadderTask {    // 32 bytes, one per read of a round-3 region
     int32_t  kmin, kmax;   // rungs of this read (kmax >= kmin >= 0)
     int32_t  out_off;      // index of rung kmin in out[]
     int32_t  region;       // index into the launch's LadderRegion table
-    int32_t  pad[2];
+    int32_t  read;         // index of the read in the batch (row of the selection output)
+    int32_t  pad;
 };
 
 struct LadderRegion {  // per-region constants of a ladder launch (20 bytes)
@@ -60,6 +61,7 @@ struct ScoreW {        // scoring constants as W32 increments
     int refund1, refund2;                    // q << 16, q2 << 16: a gap that spans a junction pays its opening once
     int one, mone;                           // 1, -1 and 4, passed as kernel parameters so that ptxas cannot fold them:
     unsigned four;                           // adds written as a * one + b issue as IMAD on the FMA pipe, beside the DPX pipe
+    int min_score;                           // minimap2 -s: rungs scoring below it do not exist for the selection (>= 1)
 };
 
 // Device-side view of the scoring constants.  FIXED = the reference's only scoring (tk.py:502-517: all five data types
@@ -77,7 +79,8 @@ template <> struct ScoreView<true> {
     static constexpr int refund1 = 4 << 16, refund2 = 24 << 16;
     int one, mone;
     unsigned four;
-    __device__ __forceinline__ explicit ScoreView(const ScoreW& w) : one(w.one), mone(w.mone), four(w.four) {}
+    int min_score;
+    __device__ __forceinline__ explicit ScoreView(const ScoreW& w) : one(w.one), mone(w.mone), four(w.four), min_score(w.min_score) {}
 };
 
 constexpr int kPadScore = -(16384 << 16);   // substitution score of rows below the query's end / void junction state
@@ -276,6 +279,9 @@ struct Sweep {
     int jnext, m, kcnt, zone_start;
     int r_score, r_end, r_start;   // kFwd: the R-only optimum
     int rcand, mark_col;           // kFwdF: the R-only candidate key; last column of the left flank (-1: none)
+    int k0, min_score;             // kFwdF: first rung of the read; selection threshold
+    int sel_top, sel_n;            // kFwdF, lane 31: round-3 selection over the rungs finalised so far
+    long long sel_sum;             //   (nanoRepeat_bam.py:423-431: top score, tied rungs that span both flanks)
     // state
     int H[R], E1[R], E2[R];
     int hup_prev, h_out, f1_out, f2_out;
@@ -363,6 +369,14 @@ struct Sweep {
             }
         }
         return cm;
+    }
+
+    // kFwdF: the reference's per-read selection, rung by rung in increasing k (only the lane that finalises rungs)
+    __device__ __forceinline__ void select_rung(const int4& rec, int k) {
+        if (rec.x >= min_score) {
+            if (rec.x > sel_top) { sel_top = rec.x; sel_n = 0; sel_sum = 0; }
+            if (rec.x == sel_top && rec.y) { ++sel_n; sel_sum += k; }
+        }
     }
 
     // kFwdF, once per lane: everything alive after the last column of the left flank started inside the flank
@@ -476,7 +490,11 @@ struct Sweep {
                     tokP = (unsigned)myP; tokJ = (unsigned)myJ;
                     if (lane == 31) {
                         if (MULTI && bot) __stcg(&tok_out[kcnt], make_ulonglong2(tokP, tokJ));
-                        else out[kcnt] = finalize_flag_rung(myP, myJ, rcand);
+                        else {
+                            const int4 rec = finalize_flag_rung(myP, myJ, rcand);
+                            out[kcnt] = rec;
+                            select_rung(rec, k0 + kcnt);
+                        }
                     }
                 } else {
                     junction_unbias(jhi, jlo);
@@ -691,14 +709,14 @@ exact_kernel(const Task* __restrict__ tasks, const int32_t* __restrict__ order, 
 // best score, so the forward sweep has no per-step best tracking at all.  Output per rung: (score, spans both flanks,
 // ends in right flank).  Needs 2 * |R| < 65536.
 template <int R, bool MULTI, bool FLAG, class SC>
-__device__ __forceinline__ void ladder_task(const LadderTask& tk, const uint32_t* __restrict__ pool,
-                                            const LadderRegion& reg, const SC& sc, int4* prof, int lane,
+__device__ __forceinline__ void ladder_task(const LadderTask& tk, const uint32_t* __restrict__ qpool,
+                                            const uint32_t* __restrict__ pool, const LadderRegion& reg, const SC& sc, int4* prof, int lane,
                                             int n_stripes, int4* bnd_a, int4* bnd_b, int4* bglob, ulonglong2* tok_a,
-                                            ulonglong2* tok_b, int4* out) {
+                                            ulonglong2* tok_b, int4* out, int4* sel) {
     constexpr int BWD = FLAG ? kBwdF : kBwd, FWD = FLAG ? kFwdF : kFwd;
     int4* bsm = prof + StripeCfg<R>::PROF_INT4;
     const int rows_per_stripe = 32 * R;
-    const uint32_t* qwords = pool + tk.q_word;
+    const uint32_t* qwords = qpool + tk.q_word;      // reads may live in the round-2 batch's pool
     const int q_len = tk.q_len;
     int4* bdst = MULTI ? bglob : bsm;
     // junction vectors: corner i (1-based) lives at forward cell row idx0 = i - 1.  Defaults: right part empty
@@ -750,6 +768,12 @@ __device__ __forceinline__ void ladder_task(const LadderTask& tk, const uint32_t
     const int c_first = reg.n_left + reg.m * tk.kmin;
     const int t_len = reg.n_left + reg.m * tk.kmax;
     int4* outp = out + tk.out_off;
+    int sel_top = 0, sel_n = 0;
+    long long sel_sum = 0;
+    if (FLAG && c_first == 0) {        // rung 0 of a region without a left flank: the R-only class alone
+        const int4 rec = finalize_flag_rung(0, kJuncNone, rcand);
+        if (rec.x >= sc.min_score) { sel_top = rec.x; sel_n = rec.y ? 1 : 0; }
+    }
     if (t_len > 0) {
         for (int s = 0; s < n_stripes; ++s) {
             __syncwarp();
@@ -771,21 +795,28 @@ __device__ __forceinline__ void ladder_task(const LadderTask& tk, const uint32_t
             sw.kcnt = c_first > 0 ? 0 : 1;
             sw.r_score = r_score; sw.r_end = r_end; sw.r_start = r_start;
             sw.rcand = rcand; sw.mark_col = reg.n_left - 1;
+            sw.k0 = tk.kmin; sw.min_score = sc.min_score;
+            sw.sel_top = sel_top; sw.sel_n = sel_n; sw.sel_sum = sel_sum;
             sw.run(sc, sw.jnext - 1);
+            sel_top = sw.sel_top; sel_n = sw.sel_n; sel_sum = sw.sel_sum;
         }
+    }
+    if (FLAG) {
+        // rungs are finalised by lane 31 (of the last stripe); without a sweep every lane holds rung 0's selection
+        if (lane == 31) sel[tk.read] = make_int4(sel_top, sel_n, (int)(unsigned)sel_sum, (int)(sel_sum >> 32));
     }
     if (c_first == 0 && lane == 0)
         outp[0] = FLAG ? finalize_flag_rung(0, kJuncNone, rcand) : finalize_rung(0ull, 0ull, 0, r_score, r_end, r_start);
 }
 
 template <int R, bool MULTI, bool FLAG, class SC>
-__device__ __forceinline__ void ladder_dispatch(int r, const LadderTask& tk, const uint32_t* __restrict__ pool,
-                                                const LadderRegion& reg, const SC& sc, int4* prof, int lane,
+__device__ __forceinline__ void ladder_dispatch(int r, const LadderTask& tk, const uint32_t* __restrict__ qpool,
+                                                const uint32_t* __restrict__ pool, const LadderRegion& reg, const SC& sc, int4* prof, int lane,
                                                 int n_stripes, int4* bnd_a, int4* bnd_b, int4* bglob,
-                                                ulonglong2* tok_a, ulonglong2* tok_b, int4* out) {
-    if (r == R) { ladder_task<R, MULTI, FLAG>(tk, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out); return; }
+                                                ulonglong2* tok_a, ulonglong2* tok_b, int4* out, int4* sel) {
+    if (r == R) { ladder_task<R, MULTI, FLAG>(tk, qpool, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out, sel); return; }
     if constexpr (R < kMaxRLadder)
-        ladder_dispatch<R + 1, MULTI, FLAG>(r, tk, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out);
+        ladder_dispatch<R + 1, MULTI, FLAG>(r, tk, qpool, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out, sel);
 }
 
 // Round-3 ladder kernel: one warp per read, all rungs kmin..kmax from one backward and one forward sweep.
@@ -794,9 +825,9 @@ __device__ __forceinline__ void ladder_dispatch(int r, const LadderTask& tk, con
 template <bool FIXED, bool FLAG>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock, 1)
 ladder_kernel(const LadderTask* __restrict__ tasks, const int32_t* __restrict__ order, int n_order, int n_excl,
-              const uint32_t* __restrict__ pool, const LadderRegion* __restrict__ regs, ScoreW scw, int* counter,
+              const uint32_t* __restrict__ qpool, const uint32_t* __restrict__ pool, const LadderRegion* __restrict__ regs, ScoreW scw, int* counter,
               int smem_stride,
-              int4* scratch, long long bnd_stride, long long b_stride, long long tok_stride, int4* out) {
+              int4* scratch, long long bnd_stride, long long b_stride, long long tok_stride, int4* out, int4* sel) {
     extern __shared__ int4 smem[];
     const ScoreView<FIXED> sc(scw);
     const int lane = threadIdx.x & 31;
@@ -819,9 +850,9 @@ ladder_kernel(const LadderTask* __restrict__ tasks, const int32_t* __restrict__ 
             int R, n_stripes;
             stripe_shape(tk.q_len, kMaxRLadder, R, n_stripes);
             if (n_stripes > 1)
-                ladder_dispatch<kMinRMultiLadder, true, FLAG>(R, tk, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out);
+                ladder_dispatch<kMinRMultiLadder, true, FLAG>(R, tk, qpool, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out, sel);
             else
-                ladder_dispatch<kMinR, false, FLAG>(R, tk, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out);
+                ladder_dispatch<kMinR, false, FLAG>(R, tk, qpool, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out, sel);
         }
         cur.done();
     }

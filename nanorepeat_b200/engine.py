@@ -74,6 +74,9 @@ SYMBOLS = {
     "nr_batch_add_round3": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p,
                                            ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
                                            ctypes.c_char_p, _i64p, _i32p, _i32p]),
+    "nr_batch_begin_round3_from": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "nr_batch_add_round3_reuse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32,
+                                                 _i32p, _i32p]),
     "nr_batch_commit": (ctypes.c_int, [ctypes.c_void_p]),
     "nr_batch_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "nr_batch_fetch_alns": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
@@ -123,10 +126,19 @@ def device_info():
     return dict(device=d.value, sm_count=s.value, clock_khz=c.value)
 
 
+_ladder_mode = 2
+
+
 def set_ladder_mode(mode):
-    """1 (default): round 3 shares one backward + one forward sweep across a read's ladder; 0: every rung is its
-    own full rectangle.  Same results either way."""
+    """2 (default): flag ladder (score + span predicates per rung); 1: shared sweeps with exact (tstart, tend) per rung;
+    0: every rung is its own full rectangle.  Same scores, predicates and selection either way."""
+    global _ladder_mode
     _check(lib().nr_set_ladder_mode(int(mode)))
+    _ladder_mode = int(mode)
+
+
+def ladder_mode():
+    return _ladder_mode
 
 
 def last_stats():
@@ -196,17 +208,41 @@ class Batch:
         self.kind = kind
         self.n_items = 0          # reads (round 2 / 3) or tasks
         self._kmin, self._kmax = [], []
+        self._region_reads = []   # round 2: reads per region, in add order
 
     # ---- construction -------------------------------------------------------------------------------------
     @classmethod
     def begin(cls, sc, kind):
         return cls(lib().nr_batch_begin(ctypes.byref(sc), {"round2": NR_KIND_ROUND2, "round3": NR_KIND_ROUND3}[kind]), kind)
 
+    @classmethod
+    def begin_round3_from(cls, round2_batch):
+        """Round-3 batch over the reads of a committed round-2 batch (they stay packed on the device)."""
+        b = cls(lib().nr_batch_begin_round3_from(round2_batch._h), "round3")
+        b._region_reads = list(round2_batch._region_reads)
+        return b
+
+    def add_round3_reuse(self, region_index, right, kmin, kmax):
+        """kmin / kmax over ALL reads of that round-2 region, kmax < kmin skips a read."""
+        kmin = np.ascontiguousarray(kmin, dtype=np.int32)
+        kmax = np.ascontiguousarray(kmax, dtype=np.int32)
+        n = self._region_reads[region_index]
+        if len(kmin) != n or len(kmax) != n:
+            raise ValueError("kmin / kmax must cover every read of the round-2 region")
+        rb = _b(right)
+        _check(lib().nr_batch_add_round3_reuse(self._h, int(region_index), rb, len(rb), kmin.ctypes.data_as(_i32p),
+                                               kmax.ctypes.data_as(_i32p)))
+        self.n_items += n
+        self._kmin.append(kmin)
+        self._kmax.append(kmax)
+        return self
+
     def add_round2(self, left, motif, T, cores):
         buf, off = _concat(cores)
         lb, mb = _b(left), _b(motif)
         _check(lib().nr_batch_add_round2(self._h, lb, len(lb), mb, len(mb), int(T), len(cores), buf,
                                          off.ctypes.data_as(_i64p)))
+        self._region_reads.append(len(cores))
         self.n_items += len(cores)
         return self
 

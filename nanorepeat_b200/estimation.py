@@ -20,21 +20,28 @@ def _scoring_for(data_type):
     return engine.get_preset(data_type)
 
 
+def _cores_of(rr, qnames):
+    core_dict = rr.read_core_seq_dict
+    return [core_dict[n] for n in qnames]
+
+
 def _round2_many(data_type, repeat_regions):
-    """Rounds 1 and 2 (reference nanoRepeat_bam.py:334-393) for a list of regions, one engine launch for all."""
+    """Rounds 1 and 2 (reference nanoRepeat_bam.py:334-393) for a list of regions, one engine launch for all.
+    The committed batch stays attached to the regions (rr._nr_round2) so that round 3 can reuse the packed reads."""
     sc = _scoring_for(data_type)
     min_score = max(1, sc.min_dp_score)
     specs, todo = [], []
     for rr in repeat_regions:
-        if len(rr.read_dict) == 0:
+        reads = rr.read_dict
+        if len(reads) == 0:
             continue                                                            # :336
         motif_len = len(rr.repeat_unit_seq)
-        reads = rr.read_dict
-        round1_repeat_size_list = []
-        for read in reads.values():                                             # :339-342
-            read.round1_repeat_size = r1 = float(read.dist_between_anchors) / motif_len
-            round1_repeat_size_list.append(r1)
-        max_r1 = max(round1_repeat_size_list)
+        read_list = list(reads.values())
+        # :339-342  r1 = float(dist) / len(motif): the same IEEE division, done on the whole array
+        r1 = (np.array([rd.dist_between_anchors for rd in read_list], dtype=np.float64) / np.float64(motif_len)).tolist()
+        for rd, v in zip(read_list, r1):
+            rd.round1_repeat_size = v
+        max_r1 = max(r1)
         if getattr(rr, "round1_max_dist", None) is not None:                    # a piece of a split region
             max_r1 = max(max_r1, float(rr.round1_max_dist) / motif_len)         # (sharding.split_region): T is region-wide
         template_repeat_size = int(max_r1 * 1.5) + 1                            # :344
@@ -42,15 +49,24 @@ def _round2_many(data_type, repeat_regions):
             template_repeat_size = int(max_r1 + 10)
         # reads come from read_core_seq_dict, which is what the reference wrote to core_sequences.fastq (:311-321)
         core_dict = rr.read_core_seq_dict
-        qnames = [n for n in reads if n in core_dict]
-        cores = [core_dict[n].strip() for n in qnames]
-        specs.append((rr.left_anchor_seq, rr.repeat_unit_seq, template_repeat_size, cores))
+        qnames = list(reads) if len(core_dict) == len(reads) and all(n in core_dict for n in reads) \
+            else [n for n in reads if n in core_dict]
+        specs.append((rr.left_anchor_seq, rr.repeat_unit_seq, template_repeat_size))
         todo.append((rr, qnames))
     if not specs:
         return
-    alns = engine.round2_regions(sc, specs)                                     # was pymm2.main at :362
+    b = engine.Batch.begin(sc, "round2")
+    for (left, motif, T), (rr, qnames) in zip(specs, todo):
+        cores = _cores_of(rr, qnames)
+        try:
+            b.add_round2(left, motif, T, cores)
+        except engine.NanoRepeatB200Error as e:
+            if e.code != -3:                                                    # NR_ERR_BAD_BASE: maybe just whitespace,
+                raise                                                           # which the reference's FASTQ round trip drops
+            b.add_round2(left, motif, T, [c.strip() for c in cores])         # a failed add leaves the batch untouched
+    alns = b.commit().run().fetch_alns()                                        # was pymm2.main at :362
     pos = 0
-    for (rr, qnames), (left, motif, _T, _cores) in zip(todo, specs):
+    for idx, ((rr, qnames), (left, motif, _T)) in enumerate(zip(todo, specs)):
         n, n_left = len(qnames), len(left)
         a = alns[pos:pos + n]
         pos += n
@@ -61,6 +77,7 @@ def _round2_many(data_type, repeat_regions):
         for name, good, v in zip(qnames, ok.tolist(), r2):
             if good:
                 reads[name].round2_repeat_size = v
+        rr._nr_round2 = (b, idx, qnames)
 
 
 def round1_and_round2_estimation(data_type, repeat_region, num_cpu=1):
@@ -109,11 +126,59 @@ def round3_estimation_for1read(read, n_k, sum_k, top_score, best_k_list=None):
         read.round3_repeat_size = read.round2_repeat_size                       # :433
 
 
+def _assign_round3(reads, sum_k, n_k, top):
+    # np.mean(list of k) == float64(sum k) / n exactly: the k are small integers, so every partial sum is an
+    # exactly representable float64 and numpy's pairwise summation cannot round (tests/test_host.py checks it)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mean_k = sum_k.astype(np.float64) / n_k.astype(np.float64)
+    state = np.where(top <= 0, 0, np.where(n_k > 0, 1, 2)).tolist()
+    for read, s, v in zip(reads, state, mean_k):
+        if read is None:
+            continue
+        if s == 1:
+            read.round3_repeat_size = v                                         # :431 (np.float64, like np.mean)
+        elif s == 2:
+            read.round3_repeat_size = read.round2_repeat_size                   # :433
+        # s == 0: no PAF line at all (:421) -> untouched
+
+
+def _round3_reuse(fast_mode, batch, rrs):
+    """Round 3 over the reads a committed round-2 batch already holds on the device."""
+    b3 = engine.Batch.begin_round3_from(batch)
+    all_reads = []
+    for rr in rrs:
+        _b, idx, qnames = rr._nr_round2
+        reads = rr.read_dict
+        rl = [reads[n] for n in qnames]
+        r2 = [rd.round2_repeat_size for rd in rl]
+        valid = np.array([v is not None for v in r2], dtype=bool)               # :460
+        kmin = np.zeros(len(rl), dtype=np.int32)
+        kmax = np.full(len(rl), -1, dtype=np.int32)
+        if valid.any():
+            lo, hi = ladder_bounds_array([v for v in r2 if v is not None], fast_mode)   # :463-472
+            kmin[valid], kmax[valid] = lo, hi
+        b3.add_round3_reuse(idx, rr.right_anchor_seq, kmin, kmax)
+        all_reads.extend(rd if ok else None for rd, ok in zip(rl, valid.tolist()))
+        del rr._nr_round2
+    with b3:
+        sum_k, n_k, top = b3.commit().run().fetch_round3()                      # was pymm2.main per read at :497
+    _assign_round3(all_reads, sum_k, n_k, top)
+
+
 def _round3_many(data_type, fast_mode, repeat_regions):
     """Round 3 (reference nanoRepeat_bam.py:446-500 + :408-434) for a list of regions, one engine launch for all."""
     sc = _scoring_for(data_type)
-    specs, todo = [], []
+    fresh, by_batch = [], {}
     for rr in repeat_regions:
+        cached = getattr(rr, "_nr_round2", None)
+        if cached is not None and engine.ladder_mode() != 0 and cached[0]._h:
+            by_batch.setdefault(id(cached[0]), (cached[0], []))[1].append(rr)
+        else:
+            fresh.append(rr)
+    for batch, rrs in by_batch.values():
+        _round3_reuse(fast_mode, batch, rrs)
+    specs, todo = [], []
+    for rr in fresh:
         reads, r2, cores = [], [], []
         core_dict = rr.read_core_seq_dict
         for read_name, read in rr.read_dict.items():                            # :457-461
@@ -126,25 +191,11 @@ def _round3_many(data_type, fast_mode, repeat_regions):
             continue
         kmin, kmax = ladder_bounds_array(r2, fast_mode)                         # :463-472
         specs.append((rr.left_anchor_seq, rr.right_anchor_seq, rr.repeat_unit_seq, cores, kmin, kmax))
-        todo.append(reads)
+        todo.extend(reads)
     if not specs:
         return
     sum_k, n_k, top = engine.round3_regions(sc, specs)                          # was pymm2.main per read at :497
-    # np.mean(list of k) == float64(sum k) / n exactly: the k are small integers, so every partial sum is an
-    # exactly representable float64 and numpy's pairwise summation cannot round (tests/test_host.py checks it)
-    with np.errstate(invalid="ignore", divide="ignore"):
-        mean_k = sum_k.astype(np.float64) / n_k.astype(np.float64)
-    state = np.where(top <= 0, 0, np.where(n_k > 0, 1, 2)).tolist()
-    pos = 0
-    for reads in todo:
-        for i, read in enumerate(reads, pos):
-            s = state[i]
-            if s == 1:
-                read.round3_repeat_size = mean_k[i]                             # :431 (np.float64, like np.mean)
-            elif s == 2:
-                read.round3_repeat_size = read.round2_repeat_size               # :433
-            # s == 0: no PAF line at all (:421) -> untouched
-        pos += len(reads)
+    _assign_round3(todo, sum_k, n_k, top)
 
 
 def round3_estimation(data_type, fast_mode, repeat_region, num_cpu=1):

@@ -347,3 +347,56 @@ def test_long_expanded_allele_shape(engine, oracle):
     assert tuple(int(v) for v in got[0]) == (2 * len(perfect), 900, 1000 + 3 * k + 100)
     ref = oracle.align_batch([perfect, noisy], [tpl, tpl], n_threads=2)
     _assert_same(got, ref, "long allele")
+
+
+@pytest.mark.gpu
+def test_round3_over_reused_round2_reads_equals_fresh_batches(engine):
+    """nr_batch_begin_round3_from / add_round3_reuse (reads stay packed on the device) == a fresh round-3 batch."""
+    from nanorepeat_b200 import synth
+    regs = synth.config1(seed=11, n_regions=3, reads_per_region=12)
+    sc = engine.get_preset("ont")
+    b2 = engine.Batch.begin(sc, "round2")
+    for reg in regs:
+        b2.add_round2(reg.left_anchor_seq, reg.repeat_unit_seq, 60, reg.core_seqs)
+    b2.commit().run().fetch_alns()
+    rng = np.random.default_rng(5)
+    b3 = engine.Batch.begin_round3_from(b2)
+    fresh = engine.Batch.begin(sc, "round3")
+    skip_all = []
+    for i in (2, 0, 1):                                   # any order
+        reg = regs[i]
+        n = len(reg.core_seqs)
+        kmin = np.array([max(0, k - 15) for k in reg.true_sizes], np.int32)
+        kmax = np.array([k + 15 for k in reg.true_sizes], np.int32)
+        skip = rng.random(n) < 0.25
+        kmin[skip], kmax[skip] = 0, -1
+        skip_all.append(skip)
+        b3.add_round3_reuse(i, reg.right_anchor_seq, kmin, kmax)
+        keep = np.flatnonzero(~skip)
+        fresh.add_round3(reg.left_anchor_seq, reg.right_anchor_seq, reg.repeat_unit_seq,
+                         [reg.core_seqs[j] for j in keep], kmin[keep], kmax[keep])
+    b2.close()                                            # the device pool must outlive its owner
+    got = b3.commit().run().fetch_round3()
+    exp = fresh.commit().run().fetch_round3()
+    keep_all = ~np.concatenate(skip_all)
+    for g, e in zip(got, exp):
+        assert np.array_equal(g[keep_all], e)
+        assert not g[~keep_all].any()
+    b3.close(); fresh.close()
+
+
+@pytest.mark.gpu
+def test_operator_layer_drops_whitespace_like_the_fastq_round_trip(engine):
+    import nanorepeat_b200 as nrb
+    from nanorepeat_b200 import synth
+    reg = synth.config1(seed=12, n_regions=1, reads_per_region=6)[0]
+    clean = nrb.RepeatRegion.from_synth(reg)
+    dirty = nrb.RepeatRegion.from_synth(reg)
+    for n in list(dirty.read_core_seq_dict)[::2]:
+        dirty.read_core_seq_dict[n] = dirty.read_core_seq_dict[n] + "\n"
+    for rr in (clean, dirty):
+        nrb.round1_and_round2_estimation("ont", rr, 1)
+        nrb.round3_estimation("ont", False, rr, 1)
+    for n in clean.read_dict:
+        a, b = clean.read_dict[n], dirty.read_dict[n]
+        assert (a.round2_repeat_size, a.round3_repeat_size) == (b.round2_repeat_size, b.round3_repeat_size)
