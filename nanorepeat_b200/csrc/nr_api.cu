@@ -265,6 +265,7 @@ struct nr_batch {
     bool ran = false;
     cudaStream_t run_stream = nullptr;        // stream of the last nr_batch_run: fetch orders itself behind it
     cudaEvent_t ev_uploaded = nullptr;        // recorded behind the upload on the library's stream
+    cudaEvent_t ev_done = nullptr;            // recorded behind the kernel and the result copy of nr_batch_run
     int refs = 1;                             // the owner + round-3 batches that read this batch's packed reads
     nr_batch* qsrc = nullptr;                 // round 3: the committed round-2 batch whose reads are reused
 };
@@ -439,14 +440,15 @@ int run_batch(nr_batch* b, cudaStream_t st) {
     if (!b->committed) return fail(NR_ERR_ARG, "batch was not committed");
     b->run_stream = st;
     const Launch& L = b->launch;
-    if (!L.count) { b->ran = true; return NR_OK; }
     const nr::ScoreW k = score_words(b->sc);
     if (st != g_ctx.stream) {                 // the upload (and the reused round-2 pool's) ran on the library's stream
         CUDA_TRY(cudaStreamWaitEvent(st, b->ev_uploaded, 0));
         if (b->qsrc) CUDA_TRY(cudaStreamWaitEvent(st, b->qsrc->ev_uploaded, 0));
     }
     CUDA_TRY(cudaMemsetAsync(b->d_counters, 0, sizeof(int), st));
-    if (L.ladder) {
+    if (!L.count) {
+        // nothing to score: the zero-filled outputs still travel back below
+    } else if (L.ladder) {
         auto fn = b->flag ? (L.fixed ? nr::ladder_kernel<true, true> : nr::ladder_kernel<false, true>)
                           : (L.fixed ? nr::ladder_kernel<true, false> : nr::ladder_kernel<false, false>);
         const int stride = ladder_smem_int4(L.R);
@@ -465,18 +467,22 @@ int run_batch(nr_batch* b, cudaStream_t st) {
                                                        b->d_counters, stride, b->d_scratch, L.scratch_stride, b->d_out);
     }
     CUDA_TRY(cudaGetLastError());
-    b->stats.kernel_launches = 1;
+    // results start their way back as soon as the kernel is done (a fetch issued later would queue behind whatever
+    // was launched on the stream in between): 16 B per task / per read; flag-ladder rung records only on request
+    if (b->flag) {
+        if (b->n_reads) CUDA_TRY(cudaMemcpyAsync(b->h_sel, b->d_sel, sizeof(int4) * b->n_reads, cudaMemcpyDeviceToHost, st));
+    } else if (b->n_out) {
+        CUDA_TRY(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(int4) * b->n_out, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaEventRecord(b->ev_done, st));
+    b->stats.kernel_launches = L.count ? 1 : 0;
     b->ran = true;
     return NR_OK;
 }
 
 int fetch_raw(nr_batch* b) {
     if (!b->ran) return fail(NR_ERR_ARG, "batch was not run");
-    const size_t n = b->n_out;
-    if (!n) return NR_OK;
-    cudaStream_t st = b->run_stream ? b->run_stream : g_ctx.stream;
-    CUDA_TRY(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(int4) * n, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaEventSynchronize(b->ev_done));         // kernel + the copy nr_batch_run queued behind it
     return NR_OK;
 }
 
@@ -668,7 +674,8 @@ nr_batch* new_batch(const nr_scoring_t* sc, BatchKind kind) {
     if (ensure_init(-1)) return nullptr;
     nr_batch* b = new (std::nothrow) nr_batch();
     if (!b) { fail(NR_ERR_NOMEM, "out of host memory"); return nullptr; }
-    if (cudaEventCreateWithFlags(&b->ev_uploaded, cudaEventDisableTiming) != cudaSuccess) {
+    if (cudaEventCreateWithFlags(&b->ev_uploaded, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming) != cudaSuccess) {
         fail(NR_ERR_CUDA, "cudaEventCreate failed");
         delete b;
         return nullptr;
@@ -749,6 +756,7 @@ void nr_batch_destroy(nr_batch_t* b) {
     cached_free(b->h_sel, b->sel_bytes, true);
     nr_batch* src = b->qsrc;
     if (b->ev_uploaded) cudaEventDestroy(b->ev_uploaded);
+    if (b->ev_done) cudaEventDestroy(b->ev_done);
     delete b;
     if (src) nr_batch_destroy(src);
 }
@@ -763,6 +771,7 @@ nr_batch_t* nr_batch_begin_round3_from(nr_batch_t* round2) {
     if (!b->ladder) {
         fail(NR_ERR_ARG, "nr_batch_begin_round3_from: needs a ladder mode (nr_set_ladder_mode 1 or 2)");
         cudaEventDestroy(b->ev_uploaded);
+        cudaEventDestroy(b->ev_done);
         delete b;
         return nullptr;
     }
@@ -894,10 +903,12 @@ int nr_batch_fetch_round3(nr_batch_t* b, const int64_t* rung_offset, nr_rung_t* 
     if (b->flag) {
         // the kernel selected per read (nr_kernels.cuh, Sweep::select_rung); the rung records cross the bus only on request
         if (!b->ran) return fail(NR_ERR_ARG, "batch was not run");
-        cudaStream_t st = b->run_stream ? b->run_stream : g_ctx.stream;
-        if (b->n_reads) CUDA_TRY(cudaMemcpyAsync(b->h_sel, b->d_sel, sizeof(int4) * b->n_reads, cudaMemcpyDeviceToHost, st));
-        if (rungs && b->n_out) CUDA_TRY(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(int4) * b->n_out, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaEventSynchronize(b->ev_done));
+        if (rungs && b->n_out) {
+            cudaStream_t st = b->run_stream ? b->run_stream : g_ctx.stream;
+            CUDA_TRY(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(int4) * b->n_out, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
         for (int r = 0; r < b->n_reads; ++r) {
             const int4 v = b->h_sel[r];
             top_score[r] = v.x;

@@ -25,9 +25,9 @@ def _cores_of(rr, qnames):
     return [core_dict[n] for n in qnames]
 
 
-def _round2_many(data_type, repeat_regions):
-    """Rounds 1 and 2 (reference nanoRepeat_bam.py:334-393) for a list of regions, one engine launch for all.
-    The committed batch stays attached to the regions (rr._nr_round2) so that round 3 can reuse the packed reads."""
+def _round2_launch(data_type, repeat_regions):
+    """Round 1 and the launch of round 2 (reference nanoRepeat_bam.py:334-362) for a list of regions, one engine launch
+    for all.  Returns the context _round2_finish() needs, or None when there is nothing to align."""
     sc = _scoring_for(data_type)
     min_score = max(1, sc.min_dp_score)
     specs, todo = [], []
@@ -54,7 +54,7 @@ def _round2_many(data_type, repeat_regions):
         specs.append((rr.left_anchor_seq, rr.repeat_unit_seq, template_repeat_size))
         todo.append((rr, qnames))
     if not specs:
-        return
+        return None
     b = engine.Batch.begin(sc, "round2")
     for (left, motif, T), (rr, qnames) in zip(specs, todo):
         cores = _cores_of(rr, qnames)
@@ -64,7 +64,17 @@ def _round2_many(data_type, repeat_regions):
             if e.code != -3:                                                    # NR_ERR_BAD_BASE: maybe just whitespace,
                 raise                                                           # which the reference's FASTQ round trip drops
             b.add_round2(left, motif, T, [c.strip() for c in cores])         # a failed add leaves the batch untouched
-    alns = b.commit().run().fetch_alns()                                        # was pymm2.main at :362
+    b.commit().run()                                                            # was pymm2.main at :362; asynchronous
+    return b, todo, specs, min_score
+
+
+def _round2_finish(ctx):
+    """Round-2 selection (reference nanoRepeat_bam.py:364-384).  The committed batch stays attached to the regions
+    (rr._nr_round2) so that round 3 can reuse the packed reads."""
+    if ctx is None:
+        return
+    b, todo, specs, min_score = ctx
+    alns = b.fetch_alns()
     pos = 0
     for idx, ((rr, qnames), (left, motif, _T)) in enumerate(zip(todo, specs)):
         n, n_left = len(qnames), len(left)
@@ -78,6 +88,10 @@ def _round2_many(data_type, repeat_regions):
             if good:
                 reads[name].round2_repeat_size = v
         rr._nr_round2 = (b, idx, qnames)
+
+
+def _round2_many(data_type, repeat_regions):
+    _round2_finish(_round2_launch(data_type, repeat_regions))
 
 
 def round1_and_round2_estimation(data_type, repeat_region, num_cpu=1):
@@ -142,8 +156,8 @@ def _assign_round3(reads, sum_k, n_k, top):
         # s == 0: no PAF line at all (:421) -> untouched
 
 
-def _round3_reuse(fast_mode, batch, rrs):
-    """Round 3 over the reads a committed round-2 batch already holds on the device."""
+def _round3_reuse_launch(fast_mode, batch, rrs):
+    """Launch of round 3 over the reads a committed round-2 batch already holds on the device."""
     b3 = engine.Batch.begin_round3_from(batch)
     all_reads = []
     for rr in rrs:
@@ -160,8 +174,14 @@ def _round3_reuse(fast_mode, batch, rrs):
         b3.add_round3_reuse(idx, rr.right_anchor_seq, kmin, kmax)
         all_reads.extend(rd if ok else None for rd, ok in zip(rl, valid.tolist()))
         del rr._nr_round2
+    b3.commit().run()                                                           # was pymm2.main per read at :497
+    return b3, all_reads
+
+
+def _round3_reuse_finish(ctx):
+    b3, all_reads = ctx
     with b3:
-        sum_k, n_k, top = b3.commit().run().fetch_round3()                      # was pymm2.main per read at :497
+        sum_k, n_k, top = b3.fetch_round3()
     _assign_round3(all_reads, sum_k, n_k, top)
 
 
@@ -175,8 +195,9 @@ def _round3_many(data_type, fast_mode, repeat_regions):
             by_batch.setdefault(id(cached[0]), (cached[0], []))[1].append(rr)
         else:
             fresh.append(rr)
-    for batch, rrs in by_batch.values():
-        _round3_reuse(fast_mode, batch, rrs)
+    pending = [_round3_reuse_launch(fast_mode, batch, rrs) for batch, rrs in by_batch.values()]
+    for ctx in pending:
+        _round3_reuse_finish(ctx)
     specs, todo = [], []
     for rr in fresh:
         reads, r2, cores = [], [], []
@@ -204,16 +225,50 @@ def round3_estimation(data_type, fast_mode, repeat_region, num_cpu=1):
     return
 
 
+PIPELINE_MIN_READS = 4096     # reads per pipeline group: enough tasks to fill 148 SMs x 16 warps about twice
+
+
+def _pipeline_groups(rrs):
+    """Cut a region list into a few contiguous groups of at least PIPELINE_MIN_READS reads (at most 8 groups)."""
+    total = sum(len(rr.read_dict) for rr in rrs)
+    n_groups = max(1, min(8, total // PIPELINE_MIN_READS))
+    if n_groups == 1:
+        return [rrs]
+    target, groups, cur, acc = total / n_groups, [], [], 0
+    for rr in rrs:
+        cur.append(rr)
+        acc += len(rr.read_dict)
+        if acc >= target * (len(groups) + 1) and len(groups) < n_groups - 1:
+            groups.append(cur)
+            cur = []
+    if cur:
+        groups.append(cur)
+    return groups
+
+
 def estimate_regions(regions, data_type=None, fast_mode=False):
-    """Rounds 1-3 over a list of RepeatRegion-like objects with ONE engine launch per round for all of them (the
+    """Rounds 1-3 over a list of RepeatRegion-like objects with one engine launch per round and group of regions (the
     reference runs the two operators per region inside quantify1repeat_from_bam, nanoRepeat_bam.py:675-679).
-    Regions may carry their own .data_type; regions of one data type are batched together."""
-    groups = {}
+    The groups are software-pipelined: while the GPU scores one group the host packs the next and selects the
+    previous, so most of the host work hides behind the kernels.  Per-region semantics (T per region, ladder per read)
+    are untouched.  Regions may carry their own .data_type; regions of one data type are batched together."""
+    by_type = {}
     for rr in regions:
-        groups.setdefault(data_type or getattr(rr, "data_type", None) or "ont", []).append(rr)
-    for dt, rrs in groups.items():
-        _round2_many(dt, rrs)
-        _round3_many(dt, fast_mode, rrs)
+        by_type.setdefault(data_type or getattr(rr, "data_type", None) or "ont", []).append(rr)
+    for dt, rrs in by_type.items():
+        groups = _pipeline_groups(rrs)
+        r2 = [_round2_launch(dt, g) for g in groups]                # GPU: round 2 of every group, back to back
+        r3 = []
+        for g, ctx in zip(groups, r2):
+            _round2_finish(ctx)                                     # waits for this group's round 2 only
+            _scoring_for(dt)
+            live = [rr for rr in g if getattr(rr, "_nr_round2", None) is not None]
+            if live and engine.ladder_mode() != 0:
+                r3.append(_round3_reuse_launch(fast_mode, live[0]._nr_round2[0], live))
+            else:
+                _round3_many(dt, fast_mode, g)
+        for ctx in r3:
+            _round3_reuse_finish(ctx)
     return regions
 
 
