@@ -87,8 +87,13 @@ int nr_device_info(int32_t* device, int32_t* sm_count, int32_t* clock_khz);
 int nr_limits(int32_t* max_score, int32_t* max_tlen);
 
 /*
- * How round 3 is computed (scores, predicates and selection are identical, bit for bit; tests run all three):
- *   2 (default)  flag ladder: one backward sweep over the right anchor and one forward sweep over left + motif*kmax
+ * How round 3 is computed (scores, predicates and selection are identical, bit for bit; tests run all four):
+ *   3 (default)  paired flag ladder: as mode 2, but two reads of a region share a warp, one per 16-bit half of every DP
+ *                word (VIADDMNMX.U16x2 / VIMNMX3.U16x2: two cells per DPX instruction).  Reads longer than 384 bases,
+ *                regions without a left or right anchor and other scorings than map-ont take mode 2's kernel; so does,
+ *                in a second launch, any read whose selection hinges on a tie that 16-bit words cannot order.  No rung
+ *                records (nr_batch_fetch_round3 with rungs != NULL fails);
+ *   2            flag ladder: one backward sweep over the right anchor and one forward sweep over left + motif*kmax
  *                per read, joined at every junction column |left| + k*|motif| (the rungs share prefix and suffix);
  *                the DP words carry the score and the two span predicates only, no coordinates
  *                (nr_batch_fetch_alns is not available on such a batch; |right| <= 32767);
@@ -153,6 +158,10 @@ nr_batch_t* nr_batch_create_round3(const nr_scoring_t* sc,
  */
 #define NR_KIND_ROUND2 1
 #define NR_KIND_ROUND3 2
+/* Round 2 with (score, tend, tstart <= |left|) records instead of (score, tstart, tend): all the selection of
+ * nanoRepeat_bam.py:364-384 reads.  Lets reads up to 512 bases run on the paired u16x2 kernel; fetch with
+ * nr_batch_fetch_round2.  Usable as the source of nr_batch_begin_round3_from like NR_KIND_ROUND2. */
+#define NR_KIND_ROUND2_FLAGS 3
 nr_batch_t* nr_batch_begin(const nr_scoring_t* sc, int32_t kind);
 int nr_batch_add_round2(nr_batch_t* b, const char* left, int32_t n_left, const char* motif, int32_t motif_len,
                         int32_t T, int32_t n_reads, const char* cores_concat, const int64_t* core_off);
@@ -172,6 +181,8 @@ int nr_batch_add_round3_reuse(nr_batch_t* b, int32_t region_index, const char* r
 int nr_batch_commit(nr_batch_t* b);
 int nr_batch_run(nr_batch_t* b, void* stream);
 int nr_batch_fetch_alns(nr_batch_t* b, nr_aln_t* out);                      /* tasks / round2 batches */
+/* round-2 batches of either kind: per read AS, tend and the predicate tstart <= |left| (nanoRepeat_bam.py:373) */
+int nr_batch_fetch_round2(nr_batch_t* b, int32_t* score, int32_t* tend, uint8_t* starts_by_left);
 int nr_batch_fetch_round3(nr_batch_t* b, const int64_t* rung_offset, nr_rung_t* rungs,
                           int64_t* sum_k, int32_t* n_k, int32_t* top_score);  /* round3 batches */
 int nr_batch_stats(const nr_batch_t* b, nr_stats_t* out);

@@ -8,6 +8,7 @@
 // There is no CPU compute fallback: without a CUDA device every compute call fails with NR_ERR_CUDA.
 #include "../../include/nanorepeat_b200.h"
 #include "nr_kernels.cuh"
+#include "nr_pair_kernels.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -69,11 +70,14 @@ struct Context {
     int sm_count = 0;
     int clock_khz = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;      // the few tasks the paired kernels do not take run here, beside the paired launch
     BufCache cache;
 };
 Context g_ctx;
 std::mutex g_ctx_mu;
-std::atomic<int> g_ladder_mode{2};   // 2: flag ladder, 1: shared sweeps with full records, 0: every rung its own rectangle
+// 3: paired flag ladder (two reads per warp, u16x2 words), 2: flag ladder, 1: shared sweeps with full records,
+// 0: every rung its own rectangle
+std::atomic<int> g_ladder_mode{3};
 
 int ensure_init(int device) {
     std::lock_guard<std::mutex> lk(g_ctx_mu);
@@ -96,6 +100,7 @@ int ensure_init(int device) {
         return fail(NR_ERR_CUDA, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 part", device, prop.name,
                     prop.major, prop.minor);
     CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.side, cudaStreamNonBlocking));
     g_ctx.device = device;
     g_ctx.sm_count = prop.multiProcessorCount;
     g_ctx.clock_khz = prop.clockRate;
@@ -212,6 +217,11 @@ struct Launch {      // one persistent launch per batch
     long long scratch_stride;   // int4 per boundary row (multi-stripe tasks only; 0: the batch has none)
     long long b_stride;         // ladder: int4 of backward junction vectors per warp
     long long tok_stride;       // ladder: ulonglong2 per token row
+    // paired launch (nr_pair_kernels.cuh): two reads of one region per warp
+    int n_pairs;
+    int pair_R;
+    int pair_blocks;
+    int redo_R;                 // tallest stripe among the paired round-3 reads: sizes the redo launch
 };
 
 struct RegionInfo {   // one add_round2 / add_round3 call
@@ -233,6 +243,16 @@ struct nr_batch {
     std::vector<nr::LadderRegion> lregs;
     bool ladder = false;
     bool flag = false;                        // ladder on flag words: d_out holds (score, spans both, ends in right)
+    bool pair = false;                        // paired u16x2 kernels where a task is eligible (round 2: flags kind; round 3: mode 3)
+    bool r2flags = false;                     // round 2: records are (score, span predicate, tend); no tstart
+    std::vector<nr::pr::Pair2> pairs2;
+    std::vector<nr::pr::Pair3> pairs3;
+    void* d_pairs = nullptr;                  // inside the blob
+    uint2* d_prung = nullptr;                 // round 3 pairs: (P, J) tokens per rung of a pair's ladder
+    size_t prung_bytes = 0;
+    int32_t* d_redo = nullptr;                // round 3 pairs: reads to rescore on 32-bit flag words
+    size_t redo_bytes = 0;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     size_t n_out = 0;                         // records in d_out / h_out
     std::vector<int32_t> order;
     Launch launch = {};
@@ -310,7 +330,20 @@ nr::ScoreW score_words(const nr_scoring_t& sc) {
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// Sort tasks (single-stripe | multi-stripe groups, each by decreasing cost), size the launches, upload.
+bool is_map_ont(const nr_scoring_t& c) {
+    return c.match == 2 && c.mismatch == 4 && c.gap_open1 == 4 && c.gap_ext1 == 2 && c.gap_open2 == 24 && c.gap_ext2 == 1;
+}
+
+// Pair up the eligible tasks of one region (ids[]: task indices, all of the same template): neighbours in read length
+// share a warp, one per 16-bit half of the DP words (nr_pair_kernels.cuh).  key(i) orders the tasks.
+template <class Key, class Emit>
+void make_pairs(std::vector<int>& ids, Key key, Emit emit) {
+    std::sort(ids.begin(), ids.end(), [&](int x, int y) { return key(x) != key(y) ? key(x) > key(y) : x < y; });
+    for (size_t i = 0; i < ids.size(); i += 2) emit(ids[i], i + 1 < ids.size() ? ids[i + 1] : -1);
+}
+
+// Pair the eligible tasks, sort the rest (single-stripe | multi-stripe groups, each by decreasing cost), size the
+// launches, upload.
 int plan_batch(nr_batch* b) {
     const bool ladder = b->ladder;
     const int n = ladder ? (int)b->ltasks.size() : (int)b->tasks.size();
@@ -318,12 +351,11 @@ int plan_batch(nr_batch* b) {
     b->stats = {};
     b->stats.n_tasks = (int64_t)b->n_out;
     std::vector<long long> cost(n);
+    std::vector<int> task_R(n), task_ns(n), task_sweep(n), task_rungs(n, 0);
     const int max_r = ladder ? nr::kMaxRLadder : nr::kMaxRExact;
-    int rmax = 0, tmax = 0, qmax = 0, rungs_max = 0;      // tmax, qmax, rungs_max: over multi-stripe tasks only
-    int n_multi = 0;
-    long long min_multi_cost = 0, max_single_cost = 0;
+    const bool fixed = is_map_ont(b->sc);
     for (int i = 0; i < n; ++i) {
-        int q_len, t_len, t_sweep, rungs = 0;
+        int q_len, t_len, t_sweep;
         if (ladder) {
             const nr::LadderTask& t = b->ltasks[i];
             const nr::LadderRegion& g = b->lregs[t.region];
@@ -331,7 +363,8 @@ int plan_batch(nr_batch* b) {
             q_len = t.q_len;
             t_len = flank + g.m * t.kmax;                 // longest rung = columns swept (|R| backward, rest forward)
             t_sweep = std::max(g.n_left + g.m * t.kmax, g.n_right);
-            rungs = t.kmax - t.kmin + 1;
+            const int rungs = t.kmax - t.kmin + 1;
+            task_rungs[i] = rungs;
             b->stats.algorithmic_cells +=
                 (long long)q_len * ((long long)rungs * flank + (long long)g.m * (t.kmin + t.kmax) * rungs / 2);
         } else {
@@ -345,14 +378,85 @@ int plan_batch(nr_batch* b) {
             return fail(NR_ERR_TOO_LARGE,
                         "task %d (query %d x target %d) exceeds the packed range (score <= %d, target <= %d)", i,
                         q_len, t_len, kMaxScore, kMaxTlen);
-        int R, ns;
-        nr::stripe_shape(q_len, max_r, R, ns);
-        rmax = std::max(rmax, R);
-        cost[i] = (long long)ns * 32 * R * t_len;
-        if (ns > 1) {
-            tmax = std::max(tmax, t_sweep);
-            qmax = std::max(qmax, ns * 32 * R);
-            rungs_max = std::max(rungs_max, rungs);
+        nr::stripe_shape(q_len, max_r, task_R[i], task_ns[i]);
+        task_sweep[i] = t_sweep;
+        cost[i] = (long long)task_ns[i] * 32 * task_R[i] * t_len;
+    }
+    // ---- paired launch: two reads of one region per warp ----
+    std::vector<char> paired(n, 0);
+    std::vector<long long> pair_cost;
+    Launch& L = b->launch;
+    L = {};
+    if (b->pair && fixed && !ladder && b->kind == KIND_ROUND2) {
+        for (const RegionInfo& g : b->regions) {
+            std::vector<int> ids;
+            for (int r = g.first_read; r < g.first_read + g.n_reads; ++r) {
+                const nr::Task& t = b->tasks[r];
+                if (t.q_len >= 1 && t.q_len <= 32 * nr::pr::kMaxRPair2 && t.t_len >= 1) ids.push_back(r);
+            }
+            make_pairs(ids, [&](int i) { return b->tasks[i].q_len; }, [&](int x, int y) {
+                nr::pr::Pair2 p = {x, y, g.n_left, 0};
+                b->pairs2.push_back(p);
+                paired[x] = 1;
+                if (y >= 0) paired[y] = 1;
+                const int R = nr::pr::pair_rows(b->tasks[x].q_len);      // x is the longer read
+                L.pair_R = std::max(L.pair_R, R);
+                pair_cost.push_back((long long)32 * R * b->tasks[x].t_len);
+            });
+        }
+    } else if (b->pair && fixed && ladder && b->flag) {
+        long long rung_off = 0;
+        for (int i0 = 0; i0 < n;) {
+            int i1 = i0;
+            while (i1 < n && b->ltasks[i1].region == b->ltasks[i0].region) ++i1;
+            const nr::LadderRegion& g = b->lregs[b->ltasks[i0].region];
+            std::vector<int> ids;
+            if (g.n_left > 0 && g.n_right > 0)
+                for (int i = i0; i < i1; ++i)
+                    if (b->ltasks[i].q_len >= 1 && b->ltasks[i].q_len <= 32 * nr::pr::kMaxRPair3) ids.push_back(i);
+            make_pairs(ids, [&](int i) { return ((long long)b->ltasks[i].q_len << 20) + b->ltasks[i].kmax; }, [&](int x, int y) {
+                const nr::LadderTask& tx = b->ltasks[x];
+                int kmin = tx.kmin, kmax = tx.kmax;
+                if (y >= 0) { kmin = std::min(kmin, b->ltasks[y].kmin); kmax = std::max(kmax, b->ltasks[y].kmax); }
+                nr::pr::Pair3 p = {x, y, (int32_t)rung_off, 0};
+                rung_off += kmax - kmin + 1;
+                b->pairs3.push_back(p);
+                paired[x] = 1;
+                if (y >= 0) paired[y] = 1;
+                const int R = nr::pr::pair_rows(tx.q_len);
+                L.pair_R = std::max(L.pair_R, R);
+                pair_cost.push_back((long long)32 * R * (g.n_right + g.n_left + (long long)g.m * kmax));
+            });
+            i0 = i1;
+        }
+        if (rung_off > 0x7fffffffLL) return fail(NR_ERR_TOO_LARGE, "more than 2^31 rungs in one batch");
+        b->prung_bytes = sizeof(uint2) * (size_t)std::max<long long>(rung_off, 1);
+        L.redo_R = L.pair_R;
+    }
+    L.n_pairs = (int)pair_cost.size();
+    if (L.n_pairs) {            // pairs in decreasing cost: the tail of the persistent launch is made of the cheap ones
+        std::vector<int> po(L.n_pairs);
+        for (int i = 0; i < L.n_pairs; ++i) po[i] = i;
+        std::sort(po.begin(), po.end(), [&](int x, int y) { return pair_cost[x] != pair_cost[y] ? pair_cost[x] > pair_cost[y] : x < y; });
+        if (!b->pairs2.empty()) { std::vector<nr::pr::Pair2> t(L.n_pairs); for (int i = 0; i < L.n_pairs; ++i) t[i] = b->pairs2[po[i]]; b->pairs2.swap(t); }
+        else { std::vector<nr::pr::Pair3> t(L.n_pairs); for (int i = 0; i < L.n_pairs; ++i) t[i] = b->pairs3[po[i]]; b->pairs3.swap(t); }
+        for (long long c : pair_cost) b->stats.executed_cells += 2 * c;      // both halves of every word
+        L.pair_blocks = std::max(1, std::min(g_ctx.sm_count, L.n_pairs));
+    }
+    // ---- the rest: one persistent launch of the 32-bit kernels; tasks in decreasing cost (long multi-stripe tasks
+    // first) so the tail is short ----
+    int rmax = 0, tmax = 0, qmax = 0, rungs_max = 0;      // tmax, qmax, rungs_max: over multi-stripe tasks only
+    int n_multi = 0;
+    long long min_multi_cost = 0, max_single_cost = 0;
+    b->order.clear();
+    for (int i = 0; i < n; ++i) {
+        if (paired[i]) continue;
+        b->order.push_back(i);
+        rmax = std::max(rmax, task_R[i]);
+        if (task_ns[i] > 1) {
+            tmax = std::max(tmax, task_sweep[i]);
+            qmax = std::max(qmax, task_ns[i] * 32 * task_R[i]);
+            rungs_max = std::max(rungs_max, task_rungs[i]);
             min_multi_cost = n_multi ? std::min(min_multi_cost, cost[i]) : cost[i];
             ++n_multi;
         } else {
@@ -360,25 +464,17 @@ int plan_batch(nr_batch* b) {
         }
         b->stats.executed_cells += cost[i];
     }
-    // one persistent launch; tasks in decreasing cost (long multi-stripe tasks first) so the tail is short
-    b->order.resize(n);
-    for (int i = 0; i < n; ++i) b->order[i] = i;
+    const int n_rest = (int)b->order.size();
     std::sort(b->order.begin(), b->order.end(),
               [&](int x, int y) { return cost[x] != cost[y] ? cost[x] > cost[y] : x < y; });
-    Launch& L = b->launch;
-    L = {};
     L.ladder = ladder;
     L.R = rmax;
-    L.count = n;
-    L.blocks = std::max(1, std::min(g_ctx.sm_count, n));       // one persistent block per SM; a small batch still spreads
+    L.count = n_rest;
+    L.blocks = std::max(1, std::min(g_ctx.sm_count, n_rest));  // one persistent block per SM; a small batch still spreads
     // the long tasks run alone on a scheduler when they are few and really lead the cost order
-    L.n_excl = (n_multi > 0 && n_multi < n && n_multi <= nr::kExclusiveWarps * L.blocks && min_multi_cost >= max_single_cost)
+    L.n_excl = (n_multi > 0 && n_multi < n_rest && n_multi <= nr::kExclusiveWarps * L.blocks && min_multi_cost >= max_single_cost)
                    ? n_multi : 0;
-    {
-        const nr_scoring_t& c = b->sc;
-        L.fixed = c.match == 2 && c.mismatch == 4 && c.gap_open1 == 4 && c.gap_ext1 == 2 && c.gap_open2 == 24 &&
-                  c.gap_ext2 == 1;
-    }
+    L.fixed = fixed;
     size_t scratch_total = 0;
     if (tmax > 0) {
         L.scratch_stride = ((long long)tmax + 63) / 32 * 32;
@@ -388,14 +484,16 @@ int plan_batch(nr_batch* b) {
         }
         scratch_total = (size_t)L.blocks * kWarpsPerBlock * (size_t)(2 * L.scratch_stride + L.b_stride + 2 * L.tok_stride);
     }
-    // ---- one device blob: [tasks | regions | order | pool (+4 slack words) | counters], staged in pinned memory ----
+    // ---- one device blob: [tasks | regions | order | pairs | pool (+4 slack words) | counters], staged in pinned memory ----
     const size_t task_bytes = ladder ? sizeof(nr::LadderTask) * n : sizeof(nr::Task) * n;
     const size_t reg_bytes = sizeof(nr::LadderRegion) * b->lregs.size();
-    const size_t order_bytes = sizeof(int32_t) * n;
+    const size_t order_bytes = sizeof(int32_t) * n_rest;
+    const size_t pair_bytes = b->pairs2.empty() ? sizeof(nr::pr::Pair3) * b->pairs3.size() : sizeof(nr::pr::Pair2) * b->pairs2.size();
     const size_t pool_bytes = sizeof(uint32_t) * (b->pool.words.size() + 4);
     const size_t off_reg = align_up(task_bytes, 256);
     const size_t off_order = off_reg + align_up(reg_bytes, 256);
-    const size_t off_pool = off_order + align_up(order_bytes, 256);
+    const size_t off_pair = off_order + align_up(order_bytes, 256);
+    const size_t off_pool = off_pair + align_up(pair_bytes, 256);
     const size_t off_cnt = off_pool + align_up(pool_bytes, 256);
     b->blob_bytes = off_cnt + 256;
     b->out_bytes = sizeof(int4) * std::max<size_t>(b->n_out, 1);
@@ -411,11 +509,17 @@ int plan_batch(nr_batch* b) {
         if ((rc = cached_alloc((void**)&b->d_sel, b->sel_bytes, false))) return rc;
         if ((rc = cached_alloc((void**)&b->h_sel, b->sel_bytes, true))) return rc;
     }
+    if (!b->pairs3.empty()) {
+        b->redo_bytes = sizeof(int32_t) * (size_t)n;
+        if ((rc = cached_alloc((void**)&b->d_prung, b->prung_bytes, false))) return rc;
+        if ((rc = cached_alloc((void**)&b->d_redo, b->redo_bytes, false))) return rc;
+    }
     char* h = static_cast<char*>(b->h_blob);
     char* d = static_cast<char*>(b->d_blob);
     if (task_bytes) memcpy(h, ladder ? (const void*)b->ltasks.data() : (const void*)b->tasks.data(), task_bytes);
     if (reg_bytes) memcpy(h + off_reg, b->lregs.data(), reg_bytes);
     if (order_bytes) memcpy(h + off_order, b->order.data(), order_bytes);
+    if (pair_bytes) memcpy(h + off_pair, b->pairs2.empty() ? (const void*)b->pairs3.data() : (const void*)b->pairs2.data(), pair_bytes);
     if (!b->pool.words.empty()) memcpy(h + off_pool, b->pool.words.data(), pool_bytes - 16);
     memset(h + off_pool + pool_bytes - 16, 0, 16);
     memset(h + off_cnt, 0, 256);
@@ -423,6 +527,7 @@ int plan_batch(nr_batch* b) {
     b->d_ltasks = reinterpret_cast<nr::LadderTask*>(d);
     b->d_lregs = reinterpret_cast<nr::LadderRegion*>(d + off_reg);
     b->d_order = reinterpret_cast<int32_t*>(d + off_order);
+    b->d_pairs = d + off_pair;
     b->d_pool = reinterpret_cast<uint32_t*>(d + off_pool);
     b->d_counters = reinterpret_cast<int*>(d + off_cnt);
     cudaStream_t st = g_ctx.stream;
@@ -430,9 +535,35 @@ int plan_batch(nr_batch* b) {
     CUDA_TRY(cudaMemsetAsync(b->d_out, 0, b->out_bytes, st));
     if (b->d_sel) CUDA_TRY(cudaMemsetAsync(b->d_sel, 0, b->sel_bytes, st));
     CUDA_TRY(cudaEventRecord(b->ev_uploaded, st));      // nr_batch_run on another stream waits for it; no host sync here
-    b->stats.h2d_bytes = (int64_t)(task_bytes + reg_bytes + order_bytes + pool_bytes);
+    b->stats.h2d_bytes = (int64_t)(task_bytes + reg_bytes + order_bytes + pair_bytes + pool_bytes);
     b->stats.d2h_bytes = (int64_t)sizeof(int4) * (b->flag ? (int64_t)b->n_reads : (int64_t)b->n_out);
     b->committed = true;
+    return NR_OK;
+}
+
+// launch of the 32-bit kernels over order[0, count) (count_dev != NULL: the count is read on the device)
+int launch_rest(nr_batch* b, cudaStream_t st, const nr::ScoreW& k, const int32_t* order, int count, int n_excl,
+                int blocks, int R, const int* count_dev, int* counter) {
+    const Launch& L = b->launch;
+    if (L.ladder) {
+        auto fn = b->flag ? (L.fixed ? nr::ladder_kernel<true, true> : nr::ladder_kernel<false, true>)
+                          : (L.fixed ? nr::ladder_kernel<true, false> : nr::ladder_kernel<false, false>);
+        const int stride = ladder_smem_int4(R);
+        const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
+        CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fn<<<blocks, kWarpsPerBlock * 32, smem, st>>>(b->d_ltasks, order, count, n_excl, count_dev,
+                                                     b->qsrc ? b->qsrc->d_pool : b->d_pool, b->d_pool, b->d_lregs, k,
+                                                     counter, stride, b->d_scratch, L.scratch_stride,
+                                                     L.b_stride, L.tok_stride, b->d_out, b->d_sel);
+    } else {
+        auto fn = L.fixed ? nr::exact_kernel<true> : nr::exact_kernel<false>;
+        const int stride = exact_smem_int4(R);
+        const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
+        CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fn<<<blocks, kWarpsPerBlock * 32, smem, st>>>(b->d_tasks, order, count, n_excl, b->d_pool, k,
+                                                     counter, stride, b->d_scratch, L.scratch_stride, b->d_out);
+    }
+    CUDA_TRY(cudaGetLastError());
     return NR_OK;
 }
 
@@ -445,28 +576,50 @@ int run_batch(nr_batch* b, cudaStream_t st) {
         CUDA_TRY(cudaStreamWaitEvent(st, b->ev_uploaded, 0));
         if (b->qsrc) CUDA_TRY(cudaStreamWaitEvent(st, b->qsrc->ev_uploaded, 0));
     }
-    CUDA_TRY(cudaMemsetAsync(b->d_counters, 0, sizeof(int), st));
-    if (!L.count) {
-        // nothing to score: the zero-filled outputs still travel back below
-    } else if (L.ladder) {
-        auto fn = b->flag ? (L.fixed ? nr::ladder_kernel<true, true> : nr::ladder_kernel<false, true>)
-                          : (L.fixed ? nr::ladder_kernel<true, false> : nr::ladder_kernel<false, false>);
-        const int stride = ladder_smem_int4(L.R);
-        const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
-        CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fn<<<L.blocks, kWarpsPerBlock * 32, smem, st>>>(b->d_ltasks, b->d_order, L.count, L.n_excl,
-                                                       b->qsrc ? b->qsrc->d_pool : b->d_pool, b->d_pool, b->d_lregs, k,
-                                                       b->d_counters, stride, b->d_scratch, L.scratch_stride,
-                                                       L.b_stride, L.tok_stride, b->d_out, b->d_sel);
-    } else {
-        auto fn = L.fixed ? nr::exact_kernel<true> : nr::exact_kernel<false>;
-        const int stride = exact_smem_int4(L.R);
-        const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
-        CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fn<<<L.blocks, kWarpsPerBlock * 32, smem, st>>>(b->d_tasks, b->d_order, L.count, L.n_excl, b->d_pool, k,
-                                                       b->d_counters, stride, b->d_scratch, L.scratch_stride, b->d_out);
+    // counters: [0] 32-bit kernels, [1] paired kernel, [2] length of the redo list, [3] redo launch
+    CUDA_TRY(cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(int), st));
+    int launches = 0;
+    int rc;
+    if (L.n_pairs) {
+        // the tasks the paired kernels do not take (long reads, odd scoring ranges) run beside them on a second stream
+        cudaStream_t rest_st = st;
+        if (L.count) {
+            rest_st = g_ctx.side;
+            CUDA_TRY(cudaEventRecord(b->ev_fork, st));
+            CUDA_TRY(cudaStreamWaitEvent(rest_st, b->ev_fork, 0));
+            if ((rc = launch_rest(b, rest_st, k, b->d_order, L.count, L.n_excl, L.blocks, L.R, nullptr, b->d_counters))) return rc;
+            CUDA_TRY(cudaEventRecord(b->ev_join, rest_st));
+            ++launches;
+        }
+        if (!b->pairs2.empty()) {
+            const int stride = exact_smem_int4(L.pair_R);
+            const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
+            CUDA_TRY(cudaFuncSetAttribute((const void*)nr::pr::pair_round2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            nr::pr::pair_round2_kernel<<<L.pair_blocks, kWarpsPerBlock * 32, smem, st>>>(
+                static_cast<const nr::pr::Pair2*>(b->d_pairs), L.n_pairs, b->d_tasks, b->d_pool, 1u, 4u, b->d_counters + 1,
+                stride, b->d_out);
+        } else {
+            const int stride = ladder_smem_int4(L.pair_R);
+            const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
+            CUDA_TRY(cudaFuncSetAttribute((const void*)nr::pr::pair_ladder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            nr::pr::pair_ladder_kernel<<<L.pair_blocks, kWarpsPerBlock * 32, smem, st>>>(
+                static_cast<const nr::pr::Pair3*>(b->d_pairs), L.n_pairs, b->d_ltasks, b->qsrc ? b->qsrc->d_pool : b->d_pool,
+                b->d_pool, b->d_lregs, 1u, 4u, k.min_score, b->d_counters + 1, stride, b->d_prung, b->d_sel,
+                b->d_counters + 2, b->d_redo);
+        }
+        CUDA_TRY(cudaGetLastError());
+        ++launches;
+        if (L.count) CUDA_TRY(cudaStreamWaitEvent(st, b->ev_join, 0));
+        if (!b->pairs3.empty()) {
+            // reads whose selection hinges on a tie the 16-bit words cannot order: 32-bit flag ladder, count on the device
+            if ((rc = launch_rest(b, st, k, b->d_redo, 0, 0, std::min(g_ctx.sm_count, 2 * L.n_pairs), L.redo_R,
+                                  b->d_counters + 2, b->d_counters + 3))) return rc;
+            ++launches;
+        }
+    } else if (L.count) {
+        if ((rc = launch_rest(b, st, k, b->d_order, L.count, L.n_excl, L.blocks, L.R, nullptr, b->d_counters))) return rc;
+        ++launches;
     }
-    CUDA_TRY(cudaGetLastError());
     // results start their way back as soon as the kernel is done (a fetch issued later would queue behind whatever
     // was launched on the stream in between): 16 B per task / per read; flag-ladder rung records only on request
     if (b->flag) {
@@ -475,7 +628,7 @@ int run_batch(nr_batch* b, cudaStream_t st) {
         CUDA_TRY(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(int4) * b->n_out, cudaMemcpyDeviceToHost, st));
     }
     CUDA_TRY(cudaEventRecord(b->ev_done, st));
-    b->stats.kernel_launches = L.count ? 1 : 0;
+    b->stats.kernel_launches = launches;
     b->ran = true;
     return NR_OK;
 }
@@ -669,21 +822,30 @@ int add_round3(nr_batch* b, const char* left, int32_t n_left, const char* right,
     return NR_OK;
 }
 
+void free_events(nr_batch* b) {
+    for (cudaEvent_t* e : {&b->ev_uploaded, &b->ev_done, &b->ev_fork, &b->ev_join})
+        if (*e) { cudaEventDestroy(*e); *e = nullptr; }
+}
+
 nr_batch* new_batch(const nr_scoring_t* sc, BatchKind kind) {
     if (check_scoring(sc)) return nullptr;
     if (ensure_init(-1)) return nullptr;
     nr_batch* b = new (std::nothrow) nr_batch();
     if (!b) { fail(NR_ERR_NOMEM, "out of host memory"); return nullptr; }
     if (cudaEventCreateWithFlags(&b->ev_uploaded, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming) != cudaSuccess) {
         fail(NR_ERR_CUDA, "cudaEventCreate failed");
+        free_events(b);
         delete b;
         return nullptr;
     }
     b->kind = kind;
     b->sc = *sc;
     b->ladder = kind == KIND_ROUND3 && g_ladder_mode.load() != 0;
-    b->flag = kind == KIND_ROUND3 && g_ladder_mode.load() == 2;
+    b->flag = kind == KIND_ROUND3 && g_ladder_mode.load() >= 2;
+    b->pair = kind == KIND_ROUND3 && g_ladder_mode.load() == 3;
     return b;
 }
 
@@ -714,6 +876,7 @@ int nr_shutdown(void) {
         for (auto& kv : g_ctx.cache.free_dev) for (void* p : kv.second) cudaFree(p);
         for (auto& kv : g_ctx.cache.free_pin) for (void* p : kv.second) cudaFreeHost(p);
         cudaStreamDestroy(g_ctx.stream);
+        cudaStreamDestroy(g_ctx.side);
         g_ctx = Context();
     }
     return NR_OK;
@@ -731,7 +894,7 @@ int nr_device_info(int32_t* device, int32_t* sm_count, int32_t* clock_khz) {
 }
 
 int nr_set_ladder_mode(int mode) {
-    if (mode < 0 || mode > 2) return fail(NR_ERR_ARG, "nr_set_ladder_mode: mode must be 0, 1 or 2");
+    if (mode < 0 || mode > 3) return fail(NR_ERR_ARG, "nr_set_ladder_mode: mode must be 0, 1, 2 or 3");
     g_ladder_mode.store(mode);
     return NR_OK;
 }
@@ -754,9 +917,10 @@ void nr_batch_destroy(nr_batch_t* b) {
     cached_free(b->d_scratch, b->scratch_bytes, false);
     cached_free(b->d_sel, b->sel_bytes, false);
     cached_free(b->h_sel, b->sel_bytes, true);
+    cached_free(b->d_prung, b->prung_bytes, false);
+    cached_free(b->d_redo, b->redo_bytes, false);
     nr_batch* src = b->qsrc;
-    if (b->ev_uploaded) cudaEventDestroy(b->ev_uploaded);
-    if (b->ev_done) cudaEventDestroy(b->ev_done);
+    free_events(b);
     delete b;
     if (src) nr_batch_destroy(src);
 }
@@ -770,8 +934,7 @@ nr_batch_t* nr_batch_begin_round3_from(nr_batch_t* round2) {
     if (!b) return nullptr;
     if (!b->ladder) {
         fail(NR_ERR_ARG, "nr_batch_begin_round3_from: needs a ladder mode (nr_set_ladder_mode 1 or 2)");
-        cudaEventDestroy(b->ev_uploaded);
-        cudaEventDestroy(b->ev_done);
+        free_events(b);
         delete b;
         return nullptr;
     }
@@ -793,11 +956,13 @@ int nr_batch_add_round3_reuse(nr_batch_t* b, int32_t region_index, const char* r
 }
 
 nr_batch_t* nr_batch_begin(const nr_scoring_t* sc, int32_t kind) {
-    if (kind != NR_KIND_ROUND2 && kind != NR_KIND_ROUND3) {
-        fail(NR_ERR_ARG, "nr_batch_begin: kind must be NR_KIND_ROUND2 or NR_KIND_ROUND3");
+    if (kind != NR_KIND_ROUND2 && kind != NR_KIND_ROUND3 && kind != NR_KIND_ROUND2_FLAGS) {
+        fail(NR_ERR_ARG, "nr_batch_begin: kind must be NR_KIND_ROUND2, NR_KIND_ROUND2_FLAGS or NR_KIND_ROUND3");
         return nullptr;
     }
-    return new_batch(sc, (BatchKind)kind);
+    nr_batch* b = new_batch(sc, kind == NR_KIND_ROUND3 ? KIND_ROUND3 : KIND_ROUND2);
+    if (b && kind == NR_KIND_ROUND2_FLAGS) b->r2flags = b->pair = true;
+    return b;
 }
 
 int nr_batch_add_round2(nr_batch_t* b, const char* left, int32_t n_left, const char* motif, int32_t motif_len,
@@ -885,6 +1050,7 @@ int nr_batch_run(nr_batch_t* b, void* stream) {
 int nr_batch_fetch_alns(nr_batch_t* b, nr_aln_t* out) {
     if (!b || (!out && b->n_out)) return fail(NR_ERR_ARG, "nr_batch_fetch_alns: NULL argument");
     if (b->flag) return fail(NR_ERR_ARG, "nr_batch_fetch_alns: a flag-ladder batch has no (tstart, tend) records; use nr_batch_fetch_round3 or nr_set_ladder_mode(1)");
+    if (b->r2flags) return fail(NR_ERR_ARG, "nr_batch_fetch_alns: a NR_KIND_ROUND2_FLAGS batch has no tstart; use nr_batch_fetch_round2");
     int rc = fetch_raw(b);
     if (rc) return rc;
     for (size_t i = 0; i < b->n_out; ++i) {
@@ -895,11 +1061,27 @@ int nr_batch_fetch_alns(nr_batch_t* b, nr_aln_t* out) {
     return NR_OK;
 }
 
+int nr_batch_fetch_round2(nr_batch_t* b, int32_t* score, int32_t* tend, uint8_t* starts_by_left) {
+    if (!b || b->kind != KIND_ROUND2) return fail(NR_ERR_ARG, "nr_batch_fetch_round2: not a round-2 batch");
+    if (b->n_out && (!score || !tend || !starts_by_left)) return fail(NR_ERR_ARG, "nr_batch_fetch_round2: NULL output");
+    int rc = fetch_raw(b);
+    if (rc) return rc;
+    for (const RegionInfo& g : b->regions)
+        for (int r = g.first_read; r < g.first_read + g.n_reads; ++r) {
+            const int4 a = b->h_out[r];
+            score[r] = a.x;
+            tend[r] = a.z;
+            starts_by_left[r] = a.y <= g.n_left;      // tstart <= |left| (nanoRepeat_bam.py:373); paired records hold 0 or |left| + 1
+        }
+    return NR_OK;
+}
+
 int nr_batch_fetch_round3(nr_batch_t* b, const int64_t* rung_offset, nr_rung_t* rungs, int64_t* sum_k,
                           int32_t* n_k, int32_t* top_score) {
     if (!b || b->kind != KIND_ROUND3) return fail(NR_ERR_ARG, "nr_batch_fetch_round3: not a round-3 batch");
     if (b->n_reads > 0 && (!sum_k || !n_k || !top_score)) return fail(NR_ERR_ARG, "nr_batch_fetch_round3: NULL output");
     if (rungs && !rung_offset) return fail(NR_ERR_ARG, "rungs given without rung_offset");
+    if (rungs && b->pair) return fail(NR_ERR_ARG, "nr_batch_fetch_round3: the paired ladder (mode 3) keeps no rung records; use nr_set_ladder_mode(2)");
     if (b->flag) {
         // the kernel selected per read (nr_kernels.cuh, Sweep::select_rung); the rung records cross the bus only on request
         if (!b->ran) return fail(NR_ERR_ARG, "batch was not run");

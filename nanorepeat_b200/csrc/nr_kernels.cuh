@@ -825,6 +825,7 @@ __device__ __forceinline__ void ladder_dispatch(int r, const LadderTask& tk, con
 template <bool FIXED, bool FLAG>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock, 1)
 ladder_kernel(const LadderTask* __restrict__ tasks, const int32_t* __restrict__ order, int n_order, int n_excl,
+              const int* __restrict__ n_order_dev,      // non-null: order[] was filled on the device (redo list), its length is here
               const uint32_t* __restrict__ qpool, const uint32_t* __restrict__ pool, const LadderRegion* __restrict__ regs, ScoreW scw, int* counter,
               int smem_stride,
               int4* scratch, long long bnd_stride, long long b_stride, long long tok_stride, int4* out, int4* sel) {
@@ -840,6 +841,7 @@ ladder_kernel(const LadderTask* __restrict__ tasks, const int32_t* __restrict__ 
     int4* bglob = bnd_b + bnd_stride;
     ulonglong2* tok_a = reinterpret_cast<ulonglong2*>(bglob + b_stride);
     ulonglong2* tok_b = tok_a + tok_stride;
+    if (n_order_dev) n_order = *n_order_dev;
     TaskCursor cur(n_excl, n_order, counter);
     for (;;) {
         const int oi = cur.next();

@@ -1,0 +1,545 @@
+// nr_pair_kernels.cuh -- paired DP kernels: TWO reads per warp, one per 16-bit half of every DP word (u16x2).
+//
+// Same contract as nr_kernels.cuh (oracle/nr_oracle.c), same wavefront mapping (one warp per task, lane l owns R rows,
+// skewed column sweep, query profile in shared memory); what changes is the DP word.  Rounds 2 and 3 of the reference
+// (nanoRepeat_bam.py:349-384, :408-434, :452-500) read, per alignment, the score, tend (round 2) and two span
+// predicates -- never a coordinate that needs 16 bits of its own -- so a cell fits 16 bits and a DPX instruction
+// (VIADDMNMX.U16x2 / VIMNMX3.U16x2) updates one cell of each of two reads of the same region (same template):
+//
+//     w = 2 * score + u + 64        u = 1: the alignment did NOT start in the marked prefix of the template
+//                                          (round 2: columns <= |left|, :373; round 3: columns < |left|, :427)
+//
+// * unsigned halves with a bias of 64: no half ever goes below 0 (the deepest value is floor - open2 - ext2 = 13), so a
+//   plain 32-bit add of a two-half constant cannot borrow across the halves and the five adds of the cell stay IMADs
+//   on the FMA pipe, beside the DPX pipe;
+// * a fresh start is the word 65 (score 0, unmarked); it enters as the third operand of the diagonal's VIADDMNMX, so the
+//   cell is 7 DPX-class instructions + 4 IMAD per PAIR of cells (3.5 DPX per cell against 6 for the 32-bit word);
+// * when a lane has finished the last marked column, every live state with a positive score loses 1 (becomes "started
+//   inside"); integer max then prefers the unmarked word among equal scores, which is the contract's "largest tstart".
+//
+// Round 3 (pair_ladder_kernel) shares prefix and suffix over the rungs exactly like ladder_kernel: one backward sweep
+// over reverse(right), one forward sweep over left + motif^kmax, junction candidates forward + backward at every column
+// |left| + k * |motif|.  The backward words carry the score only, so among candidates of equal total the contract's
+// order (smallest tend, then largest tstart) is not decidable when a marked and an unmarked candidate tie for a rung
+// that ties for the read's top score: those reads (none in the five configs' synthetic data, a few in the crafted
+// tests) are appended to a redo list and rescored by the 32-bit flag ladder right behind this kernel.  Everything
+// else -- scores, the "ends in right" predicate, the selection -- is exact as computed here.
+#pragma once
+#include "nr_kernels.cuh"
+
+namespace nr {
+namespace pr {
+
+typedef unsigned u32;
+constexpr int kBias = 64;
+__host__ __device__ constexpr u32 pk2(int hi, int lo) { return ((u32)(hi & 0xffff) << 16) | (u32)(lo & 0xffff); }
+__host__ __device__ constexpr u32 pk(int v) { return pk2(v, v); }
+// 32-bit addend that subtracts v from both halves (valid while both halves stay >= v)
+__host__ __device__ constexpr u32 sub2(int v) { return 0u - (((u32)v << 16) | (u32)v); }
+
+// map-ont (the reference's only scoring, tk.py:502-517) in doubled units: bit 0 of a word is the mark
+constexpr int kMatch = 4, kMismatch = 8, kOpen1 = 12, kExt1 = 4, kOpen2 = 50, kExt2 = 2, kRefund1 = 8, kRefund2 = 48;
+constexpr u32 kFloorFwd = pk(kBias + 1);     // score 0, unmarked
+constexpr u32 kFloorBwd = pk(kBias);         // backward words: bit 0 stays clear, so forward + backward keeps the mark
+constexpr u32 kOnes = 0x00010001u;
+
+__device__ __forceinline__ u32 pmadd(u32 a, u32 mul, u32 b) {
+    u32 d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(mul), "r"(b));
+    return d;
+}
+
+// One cell of both reads.  hd: H(i-1, j-1); s: substitution increment per half (two's complement halves).
+template <u32 FLOOR>
+__device__ __forceinline__ void cell(u32 hd, u32 s, u32 one, u32& h, u32& e1, u32& e2, u32& f1, u32& f2) {
+    const u32 d = __viaddmax_u16x2(hd, s, FLOOR);
+    const u32 t = __vimax3_u16x2(d, e1, e2);
+    h = __vimax3_u16x2(t, f1, f2);
+    e1 = __viaddmax_u16x2(h, pk(-kOpen1), pmadd(e1, one, sub2(kExt1)));
+    e2 = __viaddmax_u16x2(h, pk(-kOpen2), pmadd(e2, one, sub2(kExt2)));
+    f1 = __viaddmax_u16x2(h, pk(-kOpen1), pmadd(f1, one, sub2(kExt1)));
+    f2 = __viaddmax_u16x2(h, pk(-kOpen2), pmadd(f2, one, sub2(kExt2)));
+}
+
+struct Pair2 {         // round 2: two tasks of one region (same template); b < 0: no partner
+    int32_t a, b;
+    int32_t mark_col;  // |left|: an alignment that starts at a column <= mark_col passes the span test (:373)
+    int32_t pad;
+};
+
+struct Pair3 {         // round 3: two LadderTasks of one region; b < 0: no partner
+    int32_t a, b;
+    int32_t rung_off;  // first (P, J) token pair of this pair in the rung buffer
+    int32_t pad;
+};
+
+// Query profile of a pair: prof[(c * CH + chunk) * 32 + lane].{x,y,z,w} = increments of rows 4*chunk..+3 of this lane
+// against target code c, read A in the high half, read B in the low half.  Rows past a read's end score as mismatches:
+// they lie below every real row, nothing flows upwards, and whatever they hold is below a real cell of the same or an
+// earlier column, so they can neither set nor tie a maximum.
+template <int R>
+__device__ __forceinline__ void build_profile(uint4* prof, const uint32_t* __restrict__ qa, int q_a,
+                                              const uint32_t* __restrict__ qb, int q_b, int row0, int lane, bool reverse) {
+    constexpr int CH = StripeCfg<R>::CH;
+    u32* p = reinterpret_cast<u32*>(prof);
+#pragma unroll
+    for (int r = 0; r < 4 * CH; ++r) {
+        const int i = row0 + r;
+        int ca = 4, cb = 4;
+        if (r < R && i < q_a) {
+            const int qi = reverse ? q_a - 1 - i : i;
+            ca = (qa[qi >> 4] >> (30 - 2 * (qi & 15))) & 3;
+        }
+        if (r < R && i < q_b) {
+            const int qi = reverse ? q_b - 1 - i : i;
+            cb = (qb[qi >> 4] >> (30 - 2 * (qi & 15))) & 3;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            p[((c * CH + (r >> 2)) * 32 + lane) * 4 + (r & 3)] = pk2(ca == c ? kMatch : -kMismatch, cb == c ? kMatch : -kMismatch);
+    }
+}
+
+constexpr int kP2 = 0, kPB = 1, kPF = 2;
+
+// One sweep of one pair (single stripe).
+//   kP2: round 2, read x left + motif^T; marks after column mark_col; per half the first column that reaches the
+//        best score (tend) and the mark of the best word there.
+//   kPB: reversed reads x reverse(right), score only; running maximum (the R-only class); the final column's junction
+//        state (H, E1 + refund1, E2 + refund2) goes to bvec in the forward layout, each half at its own read's rows.
+//   kPF: reads x left + motif^kmax; marks after column |left| - 1; junction candidates and (P, J) tokens as in
+//        nr_kernels.cuh; the last lane stores every rung's token pair.
+template <int R, int MODE>
+struct Sweep {
+    static constexpr u32 FLOOR = MODE == kPB ? kFloorBwd : kFloorFwd;
+    static constexpr bool kMarks = MODE != kPB;
+    // inputs
+    const uint4* prof;
+    const uint32_t* twords;
+    int t_len, lane;
+    int mark_col;
+    uint4* bvec;                   // kPB
+    int q_a, q_b;
+    const uint4* bsm;              // kPF
+    uint2* rung_out;
+    int jnext, m, kcnt, zone_start;
+    // state
+    u32 H[R], E1[R], E2[R];
+    u32 hup_prev, h_out, f1_out, f2_out;
+    u32 best;                      // kPB / kPF: running maximum word per half
+    u32 bestc, raw_hi, raw_lo;     // kP2: best score class per half ((word | 1)); the best word itself (its mark)
+    int st_hi, st_lo;              // kP2: step at which each half's class was first reached
+    u32 nz, bz;                    // lane 0: what SHFL.UP "delivers" is replaced by the matrix border (x * nz + bz)
+    uint32_t twl, w0, w1;
+    int wi, wmax, wsh;
+    const char* prof_lane;
+    u32 tokP, tokJ;
+
+    __device__ __forceinline__ uint32_t tword(int i) const { return __ldg(&twords[min(max(i, 0), wmax)]); }
+
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int r = 0; r < R; ++r) { H[r] = FLOOR; E1[r] = FLOOR + sub2(kOpen1); E2[r] = FLOOR + sub2(kOpen2); }
+        hup_prev = FLOOR; h_out = FLOOR; f1_out = FLOOR; f2_out = FLOOR;
+        best = 0; bestc = FLOOR | kOnes; raw_hi = 0; raw_lo = 0; st_hi = 0; st_lo = 0;
+        nz = lane != 0; bz = lane != 0 ? 0u : FLOOR;
+        wmax = (t_len + 15) >> 4;
+        wi = (-lane) >> 4;
+        wsh = 2 * ((-lane) & 15);
+        w0 = tword(wi); w1 = tword(wi + 1);
+        twl = 0;
+        prof_lane = reinterpret_cast<const char*>(prof + lane);
+        tokP = 0; tokJ = 0;
+    }
+
+    __device__ __forceinline__ void refill() {
+        twl = __funnelshift_l(w1, w0, wsh);
+        w0 = w1;
+        ++wi;
+        w1 = tword(wi + 1);
+    }
+
+    __device__ __forceinline__ unsigned next_base(unsigned four) {
+        unsigned lo, hi;
+        asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(lo), "=r"(hi) : "r"(twl), "r"(four));
+        twl = lo;
+        return hi;
+    }
+
+    template <bool JUNC>
+    __device__ __forceinline__ u32 cells(const uint4* pp, u32 hd, u32 cm, u32& f1, u32& f2, u32 one, u32& jhi) {
+        constexpr int CH = StripeCfg<R>::CH;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const uint4 sv = pp[c * 32];
+            const u32 s4[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = 4 * c + u;
+                if (r < R) {
+                    const u32 hleft = H[r];
+                    const u32 e1pre = E1[r], e2pre = E2[r];
+                    u32 h;
+                    cell<FLOOR>(hd, s4[u], one, h, E1[r], E2[r], f1, f2);
+                    if (JUNC) {
+                        const uint4 b = bsm[r * 32 + lane];
+                        jhi = __viaddmax_u16x2(h, b.x, jhi);
+                        jhi = __viaddmax_u16x2(e1pre, b.y, jhi);
+                        jhi = __viaddmax_u16x2(e2pre, b.z, jhi);
+                    }
+                    hd = hleft;
+                    H[r] = h;
+                    if (r & 1) cm = __vimax3_u16x2(cm, h, H[r - 1]);
+                    else if (r == R - 1) cm = __vmaxu2(cm, h);
+                }
+            }
+        }
+        return cm;
+    }
+
+    // once per lane, after the last marked column: every live state with a positive score started inside
+    __device__ __forceinline__ void mark_started_inside() {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            H[r] = __viaddmax_u16x2(H[r], pk(-1), FLOOR);
+            E1[r] = __viaddmax_u16x2(E1[r], pk(-1), __vminu2(E1[r], FLOOR));
+            E2[r] = __viaddmax_u16x2(E2[r], pk(-1), __vminu2(E2[r], FLOOR));
+        }
+        hup_prev = __viaddmax_u16x2(hup_prev, pk(-1), FLOOR);
+    }
+
+    // kPB, last column: half h of junction vector component comp of forward row idx0
+    __device__ __forceinline__ void put_half(int idx0, int comp, int hi, u32 v) {
+        unsigned short* p = reinterpret_cast<unsigned short*>(&bvec[bvec_pos<R>(idx0)]) + 2 * comp + hi;
+        *p = (unsigned short)v;
+    }
+
+    template <bool FAST>
+    __device__ __forceinline__ void step(int st, u32 one, unsigned four) {
+        const bool zone = !FAST && MODE == kPF && st >= zone_start;     // uniform
+        constexpr int CH = StripeCfg<R>::CH;
+        u32 hup = __shfl_up_sync(kFull, h_out, 1);
+        u32 f1 = __shfl_up_sync(kFull, f1_out, 1);
+        u32 f2 = __shfl_up_sync(kFull, f2_out, 1);
+        u32 tP = 0, tJ = 0;
+        if (zone) {
+            tP = __shfl_up_sync(kFull, tokP, 1);
+            tJ = __shfl_up_sync(kFull, tokJ, 1);
+        }
+        hup = pmadd(hup, nz, bz);
+        f1 = pmadd(f1, nz, bz);
+        f2 = pmadd(f2, nz, bz);
+        const unsigned tb = next_base(four);
+        const int jj = st - lane;
+        const bool anyj = zone && __any_sync(kFull, jj + 1 == jnext && jj < t_len);
+        if (FAST || (jj >= 0 && jj < t_len)) {
+            const uint4* pp = reinterpret_cast<const uint4*>(prof_lane + tb * (unsigned)(CH * 512));
+            const u32 hd = hup_prev;
+            hup_prev = hup;
+            const bool last_col = !FAST && MODE == kPB && jj == t_len - 1;
+            if (MODE == kPB && !FAST && last_col) {      // E(i', n_right): the gap states entering the last column
+                const int brow0 = lane * R;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int ia = q_a - 2 - (brow0 + r), ib = q_b - 2 - (brow0 + r);
+                    if (ia >= 0) { put_half(ia, 1, 1, (E1[r] >> 16) + kRefund1); put_half(ia, 2, 1, (E2[r] >> 16) + kRefund2); }
+                    if (ib >= 0) { put_half(ib, 1, 0, (E1[r] & 0xffffu) + kRefund1); put_half(ib, 2, 0, (E2[r] & 0xffffu) + kRefund2); }
+                }
+            }
+            u32 cm, jhi = 0;
+            const u32 cm0 = MODE == kP2 ? 0u : best;
+            if (zone && anyj) cm = cells<true>(pp, hd, cm0, f1, f2, one, jhi);
+            else cm = cells<false>(pp, hd, cm0, f1, f2, one, jhi);
+            h_out = H[R - 1]; f1_out = f1; f2_out = f2;
+            if (MODE == kP2) {
+                // per half: a strictly higher score class (the mark bit forced on both sides); the first column wins
+                // (not __vibmax_u16x2: its inline asm re-reads an input after writing its output without an early clobber,
+                // so "best = __vibmax(best, ...)" may alias the two and report "kept" for ever)
+                const u32 nb = __vmaxu2(bestc, cm | kOnes);
+                const u32 x = nb ^ bestc;
+                bestc = nb;
+                if (x > 0xffffu) { st_hi = st; raw_hi = cm; }
+                if (x & 0xffffu) { st_lo = st; raw_lo = cm; }
+            } else {
+                best = cm;
+                if (last_col) {
+                    const int brow0 = lane * R;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int ia = q_a - 2 - (brow0 + r), ib = q_b - 2 - (brow0 + r);
+                        if (ia >= 0) put_half(ia, 0, 1, H[r] >> 16);
+                        if (ib >= 0) put_half(ib, 0, 0, H[r] & 0xffffu);
+                    }
+                }
+            }
+            if (zone && jj + 1 == jnext) {
+                if (lane == 0) { tP = 0; tJ = 0; }
+                // rung 0's junction column is the last marked column: every forward part that scores started inside
+                // but is marked only after this step (candidates with an empty forward part are the R-only class again)
+                const u32 jv = jj == mark_col ? jhi - kOnes : jhi;
+                tokP = __vmaxu2(tP, best);
+                tokJ = __vmaxu2(tJ, jv);
+                if (lane == 31) rung_out[kcnt] = make_uint2(tokP, tokJ);
+                jnext += m;
+                ++kcnt;
+            }
+            if (kMarks && !FAST && jj == mark_col) mark_started_inside();
+        }
+    }
+
+    __device__ __forceinline__ void slow_until(int& st, int end, u32 one, unsigned four) {
+#pragma unroll 1
+        for (; st < end; ++st) {
+            if ((st & 15) == 0) refill();
+            step<false>(st, one, four);
+        }
+    }
+
+    __device__ __forceinline__ void fast_until(int& st, int end, u32 one, unsigned four) {
+        for (; st + 16 <= end; st += 16) {       // st is a multiple of 16 here
+            refill();
+#pragma unroll 1
+            for (int b = 0; b < 16; b += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) step<true>(st + b + u, one, four);
+            }
+        }
+    }
+
+    __device__ __forceinline__ void run(u32 one, unsigned four, int zone_start_) {
+        init();
+        zone_start = zone_start_;
+        const int nsteps = t_len + 31;
+        int fast_end = ((t_len - 1) >> 4) << 4;
+        if (MODE == kPF) fast_end = min(fast_end, (zone_start >> 4) << 4);
+        int st = 0;
+        slow_until(st, min(32, nsteps), one, four);
+        if (kMarks && mark_col >= 0) {
+            fast_until(st, min(fast_end, (mark_col >> 4) << 4), one, four);
+            slow_until(st, min(nsteps, ((mark_col + 32 + 15) >> 4) << 4), one, four);
+        }
+        fast_until(st, fast_end, one, four);
+        slow_until(st, nsteps, one, four);
+    }
+};
+
+constexpr int kMaxRPair2 = 16;    // round 2: reads up to 512 bases
+constexpr int kMaxRPair3 = 12;    // round 3: 384 bases (profile + junction vectors: 12 KB of shared memory per warp)
+
+__host__ __device__ __forceinline__ int pair_rows(int q_len) {
+    int R = (q_len + 31) / 32;
+    return R < kMinR ? kMinR : R;
+}
+
+// Static first round (slot-major, so a small batch spreads over the SMs), then dynamic pulls.
+struct Cursor {
+    int n, lane, warp, wpb;
+    int* counter;
+    bool first;
+    __device__ __forceinline__ Cursor(int n_, int* counter_)
+        : n(n_), lane(threadIdx.x & 31), warp(threadIdx.x >> 5), wpb(blockDim.x >> 5), counter(counter_), first(true) {}
+    __device__ __forceinline__ int next() {
+        if (first) {
+            first = false;
+            const int i = warp * (int)gridDim.x + (int)blockIdx.x;
+            return i < n ? i : -1;
+        }
+        int i = 0;
+        if (lane == 0) i = atomicAdd(counter, 1);
+        i = __shfl_sync(kFull, i, 0) + wpb * (int)gridDim.x;
+        return i < n ? i : -1;
+    }
+};
+
+// ---- round 2 -------------------------------------------------------------------------------------------------------
+template <int R>
+__device__ __forceinline__ void pair2_task(const Pair2& pt, const Task* __restrict__ tasks, const uint32_t* __restrict__ pool,
+                                           uint4* prof, int lane, u32 one, unsigned four, int4* out) {
+    const Task ta = tasks[pt.a];
+    Task tb = ta;
+    int q_b = 0;
+    if (pt.b >= 0) { tb = tasks[pt.b]; q_b = tb.q_len; }
+    __syncwarp();
+    build_profile<R>(prof, pool + ta.q_word, ta.q_len, pool + tb.q_word, q_b, lane * R, lane, false);
+    __syncwarp();
+    Sweep<R, kP2> sw;
+    sw.prof = prof; sw.twords = pool + ta.t_word; sw.t_len = ta.t_len; sw.lane = lane;
+    sw.mark_col = pt.mark_col;
+    sw.run(one, four, 0);
+    // per half: (score, smallest end column, mark of the best word there) -> one 32-bit key, warp maximum
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const u32 cls = half ? (sw.bestc & 0xffffu) : (sw.bestc >> 16);
+        const u32 raw = half ? (sw.raw_lo & 0xffffu) : (sw.raw_hi >> 16);
+        const int st = half ? sw.st_lo : sw.st_hi;
+        const int score = (int)(cls - (kBias + 1)) >> 1;
+        const int col = st - lane;
+        unsigned key = 0;
+        if (score > 0) key = ((unsigned)score << 17) | ((0xffffu - (unsigned)col) << 1) | (raw & 1u);
+        key = __reduce_max_sync(kFull, key);
+        const int tid = half ? pt.b : pt.a;
+        if (lane == 0 && tid >= 0) {
+            int4 rec = make_int4(0, 0, 0, 0);
+            if (key) {
+                const int c = 0xffff - (int)((key >> 1) & 0xffffu);
+                const bool inside = c <= pt.mark_col || !(key & 1u);
+                rec = make_int4((int)(key >> 17), inside ? 0 : pt.mark_col + 1, c + 1, 0);
+            }
+            out[tid] = rec;
+        }
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void pair2_dispatch(int r, const Pair2& pt, const Task* __restrict__ tasks,
+                                               const uint32_t* __restrict__ pool, uint4* prof, int lane, u32 one,
+                                               unsigned four, int4* out) {
+    if (r == R) { pair2_task<R>(pt, tasks, pool, prof, lane, one, four, out); return; }
+    if constexpr (R < kMaxRPair2) pair2_dispatch<R + 1>(r, pt, tasks, pool, prof, lane, one, four, out);
+}
+
+// Round 2 on pairs: out[task] = (score, 0 if the alignment starts at a column <= |left| else |left| + 1, tend, 0).
+__global__ void __launch_bounds__(32 * kWarpsPerBlock, 1)
+pair_round2_kernel(const Pair2* __restrict__ pairs, int n_pairs, const Task* __restrict__ tasks,
+                   const uint32_t* __restrict__ pool, u32 one, unsigned four, int* counter, int smem_stride, int4* out) {
+    extern __shared__ uint4 psmem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4* prof = psmem + warp * smem_stride;
+    Cursor cur(n_pairs, counter);
+    for (;;) {
+        const int i = cur.next();
+        if (i < 0) break;
+        const Pair2 pt = pairs[i];
+        int q = tasks[pt.a].q_len;
+        if (pt.b >= 0) q = max(q, tasks[pt.b].q_len);
+        pair2_dispatch<kMinR>(pair_rows(q), pt, tasks, pool, prof, lane, one, four, out);
+    }
+}
+
+// ---- round 3 -------------------------------------------------------------------------------------------------------
+// One rung of one read from the (P, J) tokens: score, "ends in right", and the mark of the best non-prefix candidate.
+__device__ __forceinline__ void rung_of(u32 P, u32 J, u32 rc, int& score, bool& in_right, bool& unmarked) {
+    const u32 np = max(J, rc);
+    const int s_p = (int)(P - kBias) >> 1;
+    const int s_np = (int)(np - 2 * kBias) >> 1;
+    in_right = s_np > s_p;
+    score = max(s_p, s_np);
+    unmarked = np & 1u;
+}
+
+template <int R>
+__device__ __forceinline__ void pair3_task(const Pair3& pt, const LadderTask* __restrict__ tasks,
+                                           const uint32_t* __restrict__ qpool, const uint32_t* __restrict__ pool,
+                                           const LadderRegion* __restrict__ regs, uint4* prof, int lane, u32 one,
+                                           unsigned four, int min_score, uint2* prung, int4* sel, int* redo_count,
+                                           int32_t* redo) {
+    const LadderTask ta = tasks[pt.a];
+    LadderTask tb = ta;
+    int q_b = 0;
+    if (pt.b >= 0) { tb = tasks[pt.b]; q_b = tb.q_len; }
+    const LadderRegion reg = regs[ta.region];
+    const int q_a = ta.q_len;
+    const int kmin = pt.b >= 0 ? min(ta.kmin, tb.kmin) : ta.kmin;
+    const int kmax = pt.b >= 0 ? max(ta.kmax, tb.kmax) : ta.kmax;
+    uint4* bsm = prof + StripeCfg<R>::PROF_INT4;
+    uint2* rungs = prung + pt.rung_off;
+    // junction vectors, defaults: right part empty (score 0, no gap state) for rows of the read, void below it
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int idx0 = lane * R + r;
+        bsm[r * 32 + lane] = make_uint4(pk2(idx0 < q_a ? kBias : 0, idx0 < q_b ? kBias : 0), 0u, 0u, 0u);
+    }
+    build_profile<R>(prof, qpool + ta.q_word, q_a, qpool + tb.q_word, q_b, lane * R, lane, true);
+    __syncwarp();
+    u32 rcand;
+    {
+        Sweep<R, kPB> sw;
+        sw.prof = prof; sw.twords = pool + reg.rev_word; sw.t_len = reg.n_right; sw.lane = lane;
+        sw.mark_col = -1; sw.bvec = bsm; sw.q_a = q_a; sw.q_b = q_b;
+        sw.run(one, four, 0);
+        const u32 ra = __reduce_max_sync(kFull, sw.best >> 16), rb = __reduce_max_sync(kFull, sw.best & 0xffffu);
+        rcand = pk2((int)ra + kBias + 1, (int)rb + kBias + 1);      // forward part empty: score 0, unmarked
+    }
+    __syncwarp();
+    build_profile<R>(prof, qpool + ta.q_word, q_a, qpool + tb.q_word, q_b, lane * R, lane, false);
+    __syncwarp();
+    {
+        Sweep<R, kPF> sw;
+        sw.prof = prof; sw.twords = pool + reg.fwd_word; sw.t_len = reg.n_left + reg.m * kmax; sw.lane = lane;
+        sw.mark_col = reg.n_left - 1; sw.bsm = bsm; sw.rung_out = rungs;
+        sw.m = reg.m; sw.jnext = reg.n_left + reg.m * kmin; sw.kcnt = 0;
+        sw.run(one, four, sw.jnext - 1);
+    }
+    __syncwarp();
+    // selection per read (nanoRepeat_bam.py:423-431) over its own rungs
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int tid = half ? pt.b : pt.a;
+        if (tid < 0) continue;
+        const LadderTask& tk = half ? tb : ta;
+        const u32 rc = half ? (rcand & 0xffffu) : (rcand >> 16);
+        int top = 0;
+        for (int k = tk.kmin + lane; k <= tk.kmax; k += 32) {
+            const uint2 t = rungs[k - kmin];
+            int s; bool ir, um;
+            rung_of(half ? (t.x & 0xffffu) : (t.x >> 16), half ? (t.y & 0xffffu) : (t.y >> 16), rc, s, ir, um);
+            if (s >= min_score) top = max(top, s);
+        }
+        top = __reduce_max_sync(kFull, top);
+        int n = 0, sum = 0, unsure = 0;
+        if (top > 0) {
+            for (int k = tk.kmin + lane; k <= tk.kmax; k += 32) {
+                const uint2 t = rungs[k - kmin];
+                int s; bool ir, um;
+                rung_of(half ? (t.x & 0xffffu) : (t.x >> 16), half ? (t.y & 0xffffu) : (t.y >> 16), rc, s, ir, um);
+                if (s == top && ir) {
+                    if (um) unsure = 1;
+                    else { ++n; sum += k; }
+                }
+            }
+        }
+        n = __reduce_add_sync(kFull, n);
+        sum = __reduce_add_sync(kFull, sum);
+        unsure = __any_sync(kFull, unsure);
+        if (lane == 0) {
+            sel[tk.read] = make_int4(top, n, sum, 0);
+            if (unsure) redo[atomicAdd(redo_count, 1)] = tid;
+        }
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void pair3_dispatch(int r, const Pair3& pt, const LadderTask* __restrict__ tasks,
+                                               const uint32_t* __restrict__ qpool, const uint32_t* __restrict__ pool,
+                                               const LadderRegion* __restrict__ regs, uint4* prof, int lane, u32 one,
+                                               unsigned four, int min_score, uint2* prung, int4* sel, int* redo_count,
+                                               int32_t* redo) {
+    if (r == R) { pair3_task<R>(pt, tasks, qpool, pool, regs, prof, lane, one, four, min_score, prung, sel, redo_count, redo); return; }
+    if constexpr (R < kMaxRPair3)
+        pair3_dispatch<R + 1>(r, pt, tasks, qpool, pool, regs, prof, lane, one, four, min_score, prung, sel, redo_count, redo);
+}
+
+// Round 3 on pairs: sel[read] = (top score, n tied rungs that span both flanks, sum of their k, 0); reads whose
+// selection hinges on an undecidable tie go to redo[] (indices into tasks[]).
+__global__ void __launch_bounds__(32 * kWarpsPerBlock, 1)
+pair_ladder_kernel(const Pair3* __restrict__ pairs, int n_pairs, const LadderTask* __restrict__ tasks,
+                   const uint32_t* __restrict__ qpool, const uint32_t* __restrict__ pool,
+                   const LadderRegion* __restrict__ regs, u32 one, unsigned four, int min_score, int* counter,
+                   int smem_stride, uint2* prung, int4* sel, int* redo_count, int32_t* redo) {
+    extern __shared__ uint4 psmem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4* prof = psmem + warp * smem_stride;
+    Cursor cur(n_pairs, counter);
+    for (;;) {
+        const int i = cur.next();
+        if (i < 0) break;
+        const Pair3 pt = pairs[i];
+        int q = tasks[pt.a].q_len;
+        if (pt.b >= 0) q = max(q, tasks[pt.b].q_len);
+        pair3_dispatch<kMinR>(pair_rows(q), pt, tasks, qpool, pool, regs, prof, lane, one, four, min_score, prung, sel, redo_count, redo);
+    }
+}
+
+}  // namespace pr
+}  // namespace nr

@@ -80,6 +80,7 @@ SYMBOLS = {
     "nr_batch_commit": (ctypes.c_int, [ctypes.c_void_p]),
     "nr_batch_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "nr_batch_fetch_alns": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "nr_batch_fetch_round2": (ctypes.c_int, [ctypes.c_void_p, _i32p, _i32p, ctypes.c_void_p]),
     "nr_batch_fetch_round3": (ctypes.c_int, [ctypes.c_void_p, _i64p, ctypes.c_void_p, _i64p, _i32p, _i32p]),
     "nr_batch_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Stats)]),
     "nr_batch_destroy": (None, [ctypes.c_void_p]),
@@ -126,12 +127,13 @@ def device_info():
     return dict(device=d.value, sm_count=s.value, clock_khz=c.value)
 
 
-_ladder_mode = 2
+_ladder_mode = 3
 
 
 def set_ladder_mode(mode):
-    """2 (default): flag ladder (score + span predicates per rung); 1: shared sweeps with exact (tstart, tend) per rung;
-    0: every rung is its own full rectangle.  Same scores, predicates and selection either way."""
+    """3 (default): paired flag ladder (two reads per warp on u16x2 words); 2: flag ladder (score + span predicates per
+    rung); 1: shared sweeps with exact (tstart, tend) per rung; 0: every rung is its own full rectangle.  Same scores,
+    predicates and selection either way."""
     global _ladder_mode
     _check(lib().nr_set_ladder_mode(int(mode)))
     _ladder_mode = int(mode)
@@ -194,7 +196,8 @@ def rung_offsets(kmin, kmax):
     return off
 
 
-NR_KIND_ROUND2, NR_KIND_ROUND3 = 1, 2
+NR_KIND_ROUND2, NR_KIND_ROUND3, NR_KIND_ROUND2_FLAGS = 1, 2, 3
+_KINDS = {"round2": NR_KIND_ROUND2, "round3": NR_KIND_ROUND3, "round2_flags": NR_KIND_ROUND2_FLAGS}
 
 
 class Batch:
@@ -213,7 +216,9 @@ class Batch:
     # ---- construction -------------------------------------------------------------------------------------
     @classmethod
     def begin(cls, sc, kind):
-        return cls(lib().nr_batch_begin(ctypes.byref(sc), {"round2": NR_KIND_ROUND2, "round3": NR_KIND_ROUND3}[kind]), kind)
+        """kind: "round2" (exact (score, tstart, tend) records), "round2_flags" (score, tend and the span predicate
+        tstart <= |left|: what nanoRepeat_bam.py:364-384 reads; paired u16x2 kernel) or "round3"."""
+        return cls(lib().nr_batch_begin(ctypes.byref(sc), _KINDS[kind]), kind)
 
     @classmethod
     def begin_round3_from(cls, round2_batch):
@@ -292,6 +297,16 @@ class Batch:
         out = np.zeros(st["n_tasks"], dtype=ALN_DTYPE)
         _check(lib().nr_batch_fetch_alns(self._h, out.ctypes.data))
         return out
+
+    def fetch_round2(self):
+        """-> (score, tend, starts_by_left) per read; starts_by_left = tstart <= |left| (nanoRepeat_bam.py:373)."""
+        n = self.n_items
+        score = np.zeros(n, dtype=np.int32)
+        tend = np.zeros(n, dtype=np.int32)
+        inside = np.zeros(n, dtype=np.uint8)
+        _check(lib().nr_batch_fetch_round2(self._h, score.ctypes.data_as(_i32p), tend.ctypes.data_as(_i32p),
+                                           inside.ctypes.data))
+        return score, tend, inside.astype(bool)
 
     def fetch_round3(self, want_rungs=False):
         n = self.n_items

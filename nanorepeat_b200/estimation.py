@@ -55,7 +55,7 @@ def _round2_launch(data_type, repeat_regions):
         todo.append((rr, qnames))
     if not specs:
         return None
-    b = engine.Batch.begin(sc, "round2")
+    b = engine.Batch.begin(sc, "round2_flags")      # the selection reads AS, tend and tstart <= |left| only (:373-384)
     for (left, motif, T), (rr, qnames) in zip(specs, todo):
         cores = _cores_of(rr, qnames)
         try:
@@ -74,14 +74,13 @@ def _round2_finish(ctx):
     if ctx is None:
         return
     b, todo, specs, min_score = ctx
-    alns = b.fetch_alns()
+    all_score, all_tend, all_inside = b.fetch_round2()
     pos = 0
     for idx, ((rr, qnames), (left, motif, _T)) in enumerate(zip(todo, specs)):
         n, n_left = len(qnames), len(left)
-        a = alns[pos:pos + n]
+        score, tend, inside = all_score[pos:pos + n], all_tend[pos:pos + n], all_inside[pos:pos + n]
         pos += n
-        score, tstart, tend = a["score"], a["tstart"], a["tend"]
-        ok = (score >= min_score) & (tstart <= n_left) & (tend >= n_left)       # no PAF line below -s; span test :373
+        ok = (score >= min_score) & inside & (tend >= n_left)                   # no PAF line below -s; span test :373
         r2 = ((tend - n_left).astype(np.float64) / np.float64(len(motif))).tolist()   # :375
         reads = rr.read_dict
         for name, good, v in zip(qnames, ok.tolist(), r2):

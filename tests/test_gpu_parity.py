@@ -137,8 +137,12 @@ def test_round3_rungs_match_oracle(engine, oracle):
     n = len(reg.core_seqs)
     kmin = np.array([max(0, k - 15) for k in reg.true_sizes], dtype=np.int32)
     kmax = np.array([k + 15 for k in reg.true_sizes], dtype=np.int32)
-    sum_k, n_k, top, rungs, off = engine.round3_region(sc, reg.left_anchor_seq, reg.right_anchor_seq,
-                                                       reg.repeat_unit_seq, reg.core_seqs, kmin, kmax, want_rungs=True)
+    engine.set_ladder_mode(2)            # the paired ladder (mode 3) keeps no rung records
+    try:
+        sum_k, n_k, top, rungs, off = engine.round3_region(sc, reg.left_anchor_seq, reg.right_anchor_seq,
+                                                           reg.repeat_unit_seq, reg.core_seqs, kmin, kmax, want_rungs=True)
+    finally:
+        engine.set_ladder_mode(3)
     ref, roff = oracle.align_ladders(reg.core_seqs, reg.left_anchor_seq, reg.right_anchor_seq, reg.repeat_unit_seq,
                                      kmin, kmax, n_threads=oracle.max_threads())
     assert np.array_equal(off, roff)
@@ -153,12 +157,16 @@ def test_round3_rungs_match_oracle(engine, oracle):
             assert bool(rungs[i]["starts_in_left"]) == bool(in_right and a["tstart"] < nl)     # conjunction (:427)
 
 
-def _assert_flag_ladder(b, ref, roff, kmin, n_left, n_right, m, min_score, ctx):
-    """Flag ladder (mode 2) == oracle on what the reference reads per rung (score, span predicates, :423-427) and on
-    the selection (top score, tied rungs that span both flanks)."""
-    sum_k, n_k, top, rungs, off = b.fetch_round3(want_rungs=True)
-    assert np.array_equal(off, roff), ctx
-    assert np.array_equal(rungs["score"], ref["score"]), ctx
+def _assert_flag_ladder(b, ref, roff, kmin, n_left, n_right, m, min_score, ctx, rungs_too=True):
+    """Flag ladder (modes 2 and 3) == oracle on what the reference reads per rung (score, span predicates, :423-427;
+    mode 2 only: mode 3 keeps no rung records) and on the selection (top score, tied rungs that span both flanks)."""
+    if rungs_too:
+        sum_k, n_k, top, rungs, off = b.fetch_round3(want_rungs=True)
+        assert np.array_equal(off, roff), ctx
+        assert np.array_equal(rungs["score"], ref["score"]), ctx
+    else:
+        sum_k, n_k, top = b.fetch_round3()
+        off = roff
     for r in range(len(kmin)):
         lo, hi = int(off[r]), int(off[r + 1])
         ks = np.arange(hi - lo) + int(kmin[r])
@@ -166,8 +174,9 @@ def _assert_flag_ladder(b, ref, roff, kmin, n_left, n_right, m, min_score, ctx):
         tlen = n_left + m * ks + n_right
         in_right = (a["score"] > 0) & (tlen - a["tend"] < n_right)
         in_left = in_right & (a["tstart"] < n_left)
-        assert np.array_equal(rungs["ends_in_right"][lo:hi].astype(bool), in_right), (ctx, r)
-        assert np.array_equal(rungs["starts_in_left"][lo:hi].astype(bool), in_left), (ctx, r)
+        if rungs_too:
+            assert np.array_equal(rungs["ends_in_right"][lo:hi].astype(bool), in_right), (ctx, r)
+            assert np.array_equal(rungs["starts_in_left"][lo:hi].astype(bool), in_left), (ctx, r)
         ok = a["score"] >= max(1, min_score)
         t = int(a["score"][ok].max()) if ok.any() else 0
         sel = ks[(a["score"] == t) & in_left] if t > 0 else ks[:0]
@@ -207,19 +216,23 @@ def test_ladder_shared_sweeps_equal_independent_rectangles(engine, oracle, seed,
     ref, roff = oracle.align_ladders(cores, left, right, motif, kmin, kmax, n_threads=oracle.max_threads())
     got = {}
     try:
-        for mode in (2, 1, 0):
+        for mode in (3, 2, 1, 0):
             engine.set_ladder_mode(mode)
             b = engine.Batch.round3(sc, left, right, motif, cores, kmin, kmax)
             b.run()
-            if mode == 2:
-                _assert_flag_ladder(b, ref, roff, kmin, n_left, n_right, m, sc.min_dp_score, f"flag ladder, seed {seed}")
+            if mode >= 2:
+                _assert_flag_ladder(b, ref, roff, kmin, n_left, n_right, m, sc.min_dp_score,
+                                    f"flag ladder mode {mode}, seed {seed}", rungs_too=mode == 2)
                 with pytest.raises(engine.NanoRepeatB200Error):
                     b.fetch_alns()                      # no coordinates on flag words
+                if mode == 3:
+                    with pytest.raises(engine.NanoRepeatB200Error):
+                        b.fetch_round3(want_rungs=True)  # no rung records from the paired kernel
             else:
                 got[mode] = b.fetch_alns()
             b.close()
     finally:
-        engine.set_ladder_mode(2)
+        engine.set_ladder_mode(3)
     _assert_same(got[0], ref, f"independent rectangles, seed {seed}")
     _assert_same(got[1], ref, f"shared sweeps, seed {seed}")
 
@@ -279,19 +292,19 @@ def test_ladder_long_expanded_allele(engine, oracle):
     sc = engine.get_preset("ont")
     ref, roff = oracle.align_ladders(cores, L, R, "CGG", kmin, kmax, n_threads=oracle.max_threads())
     try:
-        for mode in (2, 1):
+        for mode in (3, 2, 1):
             engine.set_ladder_mode(mode)
             b = engine.Batch.round3(sc, L, R, "CGG", cores, kmin, kmax)
             b.run()
-            if mode == 2:
-                _assert_flag_ladder(b, ref, roff, kmin, 1000, 1000, 3, sc.min_dp_score, "long flag ladder")
+            if mode >= 2:
+                _assert_flag_ladder(b, ref, roff, kmin, 1000, 1000, 3, sc.min_dp_score, "long flag ladder", rungs_too=mode == 2)
             else:
                 _assert_same(b.fetch_alns(), ref, "long ladder")
             st = b.stats()
             assert st["executed_cells"] * 5 < st["algorithmic_cells"]
             b.close()
     finally:
-        engine.set_ladder_mode(2)
+        engine.set_ladder_mode(3)
 
 
 @pytest.mark.parametrize("name", GOLDEN_SETS)
@@ -400,3 +413,100 @@ def test_operator_layer_drops_whitespace_like_the_fastq_round_trip(engine):
     for n in clean.read_dict:
         a, b = clean.read_dict[n], dirty.read_dict[n]
         assert (a.round2_repeat_size, a.round3_repeat_size) == (b.round2_repeat_size, b.round3_repeat_size)
+
+
+@pytest.mark.parametrize("seed,n_left,m,T,n_reads,qmax", [(1, 40, 3, 30, 41, 200), (2, 0, 2, 12, 30, 90), (3, 300, 5, 40, 64, 520),
+                                                          (4, 25, 4, 0, 17, 60), (5, 1000, 3, 80, 33, 700), (6, 5, 1, 7, 50, 40)])
+def test_round2_flags_kind_equals_oracle(engine, oracle, seed, n_left, m, T, n_reads, qmax):
+    """NR_KIND_ROUND2_FLAGS (paired u16x2 kernel for reads up to 512 bases, 32-bit kernel beside it for the rest):
+    AS, tend and the span predicate tstart <= |left| (nanoRepeat_bam.py:373) against the oracle's records, and against
+    the exact-record kind."""
+    rng = random.Random(2000 + seed)
+    left, motif = _rand_seq(rng, n_left), _rand_seq(rng, m)
+    tpl = left + motif * T
+    cores = []
+    for i in range(n_reads):
+        k = rng.randint(0, T + 3)
+        kind = i % 5
+        if kind == 0:
+            core = _rand_seq(rng, rng.randint(1, min(qmax, 80)))                  # unrelated
+        elif kind == 1:
+            core = motif * max(1, k)                                              # no flank at all: starts past |left|
+        elif kind == 2:
+            core = _mutate(rng, left[-rng.randint(0, min(n_left, 100)):] if n_left else "", 0.05) + motif * k
+        elif kind == 3:
+            core = left[-1:] + motif * k if n_left else motif * k               # one flank base: ties on tstart
+        else:
+            core = _mutate(rng, (left[-60:] if n_left else "") + motif * k + _rand_seq(rng, 30), rng.choice([0.0, 0.1]))
+        cores.append((core or "A")[:qmax])
+    sc = engine.get_preset("ont")
+    ref = oracle.align_batch(cores, [tpl] * n_reads, n_threads=oracle.max_threads())
+    with engine.Batch.begin(sc, "round2_flags") as b:
+        b.add_round2(left, motif, T, cores)
+        score, tend, inside = b.commit().run().fetch_round2()
+        with pytest.raises(engine.NanoRepeatB200Error):
+            b.fetch_alns()
+    with engine.Batch.begin(sc, "round2") as b:
+        b.add_round2(left, motif, T, cores)
+        exact = b.commit().run().fetch_alns()
+    _assert_same(exact, ref, f"round-2 exact kind, seed {seed}")
+    assert np.array_equal(score, ref["score"]), seed
+    assert np.array_equal(tend, ref["tend"]), seed
+    live = ref["score"] > 0
+    assert np.array_equal(inside[live], (ref["tstart"] <= n_left)[live]), seed
+
+
+def test_paired_ladder_undecidable_ties_are_rescored(engine, oracle):
+    """Reads built so that a marked and an unmarked alignment tie for the top rung (no left-flank bases, one base, a
+    mismatching flank): the paired kernel must hand them to the 32-bit ladder and the results must equal mode 2."""
+    rng = random.Random(77)
+    left, right, motif = _rand_seq(rng, 50), _rand_seq(rng, 60), "CAG"
+    cores, kmin, kmax = [], [], []
+    for i in range(48):
+        k = rng.randint(1, 12)
+        lf = ["", left[-1:], left[-2:], _rand_seq(rng, 3), left[-30:]][i % 5]
+        rf = [right[:20], right[:1], "", right[:40]][i % 4]
+        cores.append(lf + motif * k + rf)
+        kmin.append(max(0, k - rng.randint(0, 4))); kmax.append(k + rng.randint(0, 4))
+    kmin, kmax = np.array(kmin, np.int32), np.array(kmax, np.int32)
+    sc = engine.get_preset("ont")
+    sc.min_dp_score = 1
+    ref, roff = oracle.align_ladders(cores, left, right, motif, kmin, kmax, n_threads=oracle.max_threads())
+    try:
+        for mode in (3, 2):
+            engine.set_ladder_mode(mode)
+            with engine.Batch.round3(sc, left, right, motif, cores, kmin, kmax) as b:
+                b.run()
+                _assert_flag_ladder(b, ref, roff, kmin, 50, 60, 3, 1, f"tie cases, mode {mode}", rungs_too=mode == 2)
+    finally:
+        engine.set_ladder_mode(3)
+
+
+def test_paired_and_long_reads_in_one_batch(engine, oracle):
+    """cfg2-like mix: most reads pair up (q <= 384), a few expanded alleles take the 32-bit kernels on the side stream;
+    several regions in one batch; odd read counts leave a single read without a partner."""
+    from nanorepeat_b200 import synth
+    rng = np.random.default_rng(8)
+    sc = engine.get_preset("ont")
+    specs, refs = [], []
+    for motif, ks in (("CAG", [17, 17, 55, 120, 150, 18, 54]), ("CCG", [7, 10, 7, 10, 9]), ("GGGGCC", [3, 80, 4])):
+        L, R = synth.random_seq(rng, 1000), synth.random_seq(rng, 1000)
+        cores = [synth.simulate_core(rng, L, R, motif, k, "ont")[0] for k in ks]
+        kmin = np.array([max(0, k - 15) for k in ks], np.int32)
+        kmax = np.array([k + 15 for k in ks], np.int32)
+        specs.append((L, R, motif, cores, kmin, kmax))
+        refs.append(oracle.align_ladders(cores, L, R, motif, kmin, kmax, n_threads=oracle.max_threads()))
+    got = engine.round3_regions(sc, specs)
+    pos = 0
+    for (L, R, motif, cores, kmin, kmax), (ref, roff) in zip(specs, refs):
+        for r in range(len(cores)):
+            lo, hi = int(roff[r]), int(roff[r + 1])
+            ks = np.arange(hi - lo) + int(kmin[r])
+            a = ref[lo:hi]
+            tlen = len(L) + len(motif) * ks + len(R)
+            spans = (a["score"] > 0) & (tlen - a["tend"] < len(R)) & (a["tstart"] < len(L))
+            ok = a["score"] >= sc.min_dp_score
+            t = int(a["score"][ok].max()) if ok.any() else 0
+            sel = ks[(a["score"] == t) & spans] if t > 0 else ks[:0]
+            assert (int(got[2][pos]), int(got[1][pos]), int(got[0][pos])) == (t, len(sel), int(sel.sum())), (motif, r)
+            pos += 1
