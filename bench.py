@@ -9,8 +9,10 @@ against its round-2 template and its round-3 ladder (31+ rungs).
          resident in HBM, CUDA-event time of the kernel launches only, summed over K steps, max over ranks.
   e2e    same metric through the operator API (round1_and_round2_estimation + round3_estimation) with host
          strings in, Python attributes out: packing, H2D, kernels, D2H, selection all inside the timed region.
-  roofline  DPX/integer-pipe bound: executed cells / device time against
-         SMs x sm_max_mhz x 64 DPX lanes/clk/SM x 1 cell per lane-instr / 6 DPX instr per cell.
+  roofline  DPX/integer-pipe bound: executed cells / device time of the dominant kernel (the paired round-3 ladder,
+         CUDA events around the launch on its stream) against
+         SMs x sm_max_mhz x 64 DPX lanes/clk/SM x 2 cells per lane-instr / 7 DPX instr per cell pair
+         (32-bit kernels beside it: 1 cell per lane-instr / 6 DPX instr per cell).
   cpu_baseline / --impl reference  the CPU oracle port (oracle/nr_oracle.c) on the host cores, bounded sample.
 
 N > 1 (torchrun): every rank runs its own batch (seed + rank) -- weak scaling, no data-path collective; NCCL is
@@ -32,8 +34,11 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 DPX_LANES_PER_CLK_PER_SM = 64       # measured: tools/microbench/pipe_rates.cu -> profiles/pipe_rates_r01.jsonl
-DPX_INSTR_PER_CELL = 6              # irreducible for the 5-state cell: 2 (five-way max + floor for H) + 4 (E1, E2,
-                                    # F1, F2 updates); the running-max op (0.5/cell) counts against the kernel
+DPX_INSTR_PER_CELL = 6              # 32-bit word: 2 (five-way max + floor for H) + 4 (E1, E2, F1, F2 updates); the
+                                    # running-max op (0.5/cell) counts against the kernel
+PAIR_LADDER_TRAFFIC = None          # bytes per launch from ncu --set full (profiles/); None until captured
+DPX_INSTR_PER_CELL_PAIR = 7         # u16x2 words (two cells per instruction): the floor needs an operand of its own
+                                    # (no .RELU on unsigned halves): 3 for H + 4 -> 3.5 per cell
 
 
 def load_peaks():
@@ -250,10 +255,10 @@ def main():
         r3_reuse.append((reg.right_anchor_seq, np.where(okm, lo, 0).astype(np.int32), np.where(okm, hi, -1).astype(np.int32)))
 
     def cabi_step():
-        b2c = engine.Batch.begin(sc, "round2")
+        b2c = engine.Batch.begin(sc, "round2_flags")
         for spec in r2_specs:
             b2c.add_round2(*spec)
-        a = b2c.commit().run().fetch_alns()
+        a = b2c.commit().run().fetch_round2()
         b3c = engine.Batch.begin_round3_from(b2c)        # the reads stay packed in HBM between the rounds
         for i, (right, lo, hi) in enumerate(r3_reuse):
             b3c.add_round3_reuse(i, right, lo, hi)
@@ -262,7 +267,7 @@ def main():
         return a, s
 
     # ---- resident batches: one per round over both regions ----
-    b2 = engine.Batch.begin(sc, "round2")
+    b2 = engine.Batch.begin(sc, "round2_flags")
     for spec in r2_specs:
         b2.add_round2(*spec)
     b3 = engine.Batch.begin(sc, "round3")
@@ -293,10 +298,12 @@ def main():
     torch.cuda.synchronize()
     launches_step = sum(b.stats()["kernel_launches"] for b in batches)
 
+    engine.set_timing(True)             # CUDA events around every kernel, on the stream it is launched on
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
     dev_ms, r2_ms, r3_ms = [], [], []
+    kern_ms = [dict(paired_ms=0.0, rest_ms=0.0, redo_ms=0.0) for _ in batches]
     wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush.fill_(1)                                  # evict L2 between timed iterations (untimed)
@@ -310,7 +317,13 @@ def main():
             e1.record(stream)
         e1.synchronize()
         dev_ms.append(e0.elapsed_time(e1)); r2_ms.append(e0.elapsed_time(em)); r3_ms.append(em.elapsed_time(e1))
+        for acc, b in zip(kern_ms, batches):
+            li = b.launch_info()
+            for key in acc:
+                acc[key] += li[key]
     barrier()
+    engine.set_timing(False)
+    linfo = [b.launch_info() for b in batches]
     wall = time.perf_counter() - wall0
     total_ms = float(sum(dev_ms))
 
@@ -357,17 +370,34 @@ def main():
         value = cells_all * K / (total_ms * 1e-3) / 1e9
         e2e_val = cells_all * K / e2e_s / 1e9
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
-        peak_gcups = info["sm_count"] * sm_max * 1e6 * DPX_LANES_PER_CLK_PER_SM / DPX_INSTR_PER_CELL / 1e9
-        step_achieved = executed_step * K / (float(sum(dev_ms)) * 1e-3) / 1e9      # this rank's kernels, both rounds
-        # the dominant kernel: ladder_kernel (round 3), one launch per step
-        lad_ms = float(sum(r3_ms)) / K
-        achieved = stats[1]["executed_cells"] / (lad_ms * 1e-3) / 1e9
-        ex_ms = float(sum(r2_ms)) / K
+        peak32 = info["sm_count"] * sm_max * 1e6 * DPX_LANES_PER_CLK_PER_SM / DPX_INSTR_PER_CELL / 1e9
+        peak16 = info["sm_count"] * sm_max * 1e6 * DPX_LANES_PER_CLK_PER_SM * 2 / DPX_INSTR_PER_CELL_PAIR / 1e9
+
+        def kern(cells, ms, peak):
+            if not cells or ms <= 0:
+                return None
+            a = cells / (ms / K * 1e-3) / 1e9
+            return {"achieved": a, "peak": peak, "frac": a / peak, "ms_per_launch": ms / K, "executed_cells_per_launch": cells}
+
+        kernels = {
+            "pair_round2_kernel (round 2, u16x2)": kern(linfo[0]["paired_cells"], kern_ms[0]["paired_ms"], peak16),
+            "exact_kernel<fixed scoring> (round 2, reads > 512 bases, side stream)": kern(linfo[0]["rest_cells"], kern_ms[0]["rest_ms"], peak32),
+            "pair_ladder_kernel (round 3, u16x2)": kern(linfo[1]["paired_cells"], kern_ms[1]["paired_ms"], peak16),
+            "ladder_kernel<fixed scoring, flag words> (round 3, reads > 384 bases, side stream)": kern(linfo[1]["rest_cells"], kern_ms[1]["rest_ms"], peak32),
+        }
+        kernels = {k: v for k, v in kernels.items() if v}
+        # the step against the roofline: time the DPX pipe needs for the executed cells of every kernel / time taken
+        ideal_ms = sum((li["paired_cells"] / peak16 + li["rest_cells"] / peak32) / 1e9 * 1e3 for li in linfo)
+        step_ms = float(sum(dev_ms)) / K
+        dom = kernels.get("pair_ladder_kernel (round 3, u16x2)") or next(iter(kernels.values()))
+        dom_name = "pair_ladder_kernel (round 3, u16x2)" if "pair_ladder_kernel (round 3, u16x2)" in kernels else next(iter(kernels))
         algo_bytes = h2d + d2h
         line = {
             "metric": "GCUPS", "value": value, "unit": "GCUPS (1e9 DP cells/s, full rectangles)", "n_gpus": world,
             "steps": K, "warmup": args.warmup, "ms_per_step": total_ms / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "s32 (score*65536 - span packed word)", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "u16x2 (2*score + mark + 64 per half, two reads per word); s32 (score*65536 - span) for reads > 384 bases",
+            "data": "synthetic",
             "reads_per_s": units_all * K / (total_ms * 1e-3),
             "config": {"workload": "config 2: HTT CAG/CCG amplicon, 5k ONT reads, two BED rows, rounds 2+3",
                        "reads": args.reads, "units_per_step_per_gpu": units_step,
@@ -382,22 +412,21 @@ def main():
                               "path": "nr_batch_begin/add/commit/run/fetch with host byte buffers in, records out"}},
             "gpu_launches": int(launches_all * K),
             "clocks": clocks,
-            "roofline": {"bound": "dpx", "kernel": "ladder_kernel<fixed scoring, flag words> (round 3)",
-                         "achieved": achieved, "peak": peak_gcups, "unit": "GCUPS",
-                         "frac": achieved / peak_gcups, "ms_per_launch": lad_ms,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel, ncu --set full:
-                         # profiles/r01_ncu_ladder_kernel_v12_summary.txt (1.84 MB + 1.34 MB)
-                         "traffic": 3175424, "traffic_unit": "bytes per launch (ncu)",
+            "roofline": {"bound": "dpx", "kernel": dom_name,
+                         "achieved": dom["achieved"], "peak": dom["peak"], "unit": "GCUPS",
+                         "frac": dom["frac"], "ms_per_launch": dom["ms_per_launch"],
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel, ncu --set full
+                         "traffic": PAIR_LADDER_TRAFFIC, "traffic_unit": "bytes per launch (ncu)",
                          "algorithmic_bytes_per_launch": stats[1]["h2d_bytes"] + stats[1]["d2h_bytes"],
-                         "other_kernels": {"exact_kernel<fixed scoring> (round 2)": {
-                             "achieved": stats[0]["executed_cells"] / (ex_ms * 1e-3) / 1e9,
-                             "frac": stats[0]["executed_cells"] / (ex_ms * 1e-3) / 1e9 / peak_gcups, "ms_per_launch": ex_ms}},
-                         "step": {"achieved": step_achieved, "frac": step_achieved / peak_gcups},
-                         "practical_ceiling": "2128-2282 GCUPS (0.69-0.74) for this cell with the wavefront machinery, "
-                                              "tools/microbench/cell_chain.cu (profiles/r01_cell_chain.jsonl)",
+                         "kernels": kernels,
+                         "step": {"frac": ideal_ms / step_ms, "ms": step_ms, "dpx_ideal_ms": ideal_ms,
+                                  "executed_gcups": executed_step / (step_ms * 1e-3) / 1e9,
+                                  "def": "sum over kernels of executed cells / that kernel's DPX peak, over the step's device time"},
+                         "redo_reads_per_step": linfo[1]["n_redo"],
                          "peak_def": f"{info['sm_count']} SMs x {sm_max:.0f} MHz ({peak_src}) x "
-                                     f"{DPX_LANES_PER_CLK_PER_SM} DPX lanes/clk/SM (measured) / "
-                                     f"{DPX_INSTR_PER_CELL} DPX instr per cell, 1 cell per lane-instr",
+                                     f"{DPX_LANES_PER_CLK_PER_SM} DPX lanes/clk/SM (measured) x 2 cells per lane-instr / "
+                                     f"{DPX_INSTR_PER_CELL_PAIR} DPX instr per cell pair (u16x2 kernels); "
+                                     f"x 1 / {DPX_INSTR_PER_CELL} for the 32-bit kernels ({peak32:.0f} GCUPS)",
                          "executed_cells_per_step": executed_step, "algorithmic_cells_per_step": cells_step,
                          "hbm_gbs_algorithmic": algo_bytes / (total_ms / K * 1e-3) / 1e9,
                          "hbm_peak_gbs": peaks.get("hbm_gbs")},

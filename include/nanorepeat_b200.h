@@ -74,6 +74,18 @@ typedef struct nr_stats_t {
     int64_t d2h_bytes;
 } nr_stats_t;
 
+/* How the last nr_batch_run split its work (bench.py: one roofline per kernel). */
+typedef struct nr_launch_info_t {
+    int64_t paired_cells;   /* DP cells the paired u16x2 launch updates (both halves of every word, padding included) */
+    int64_t rest_cells;     /* DP cells of the 32-bit launch beside it (long reads, other scorings, ...) */
+    int32_t n_pairs;        /* warps' worth of paired tasks */
+    int32_t n_rest;         /* tasks of the 32-bit launch */
+    int32_t n_redo;         /* paired round 3: reads rescored on 32-bit words because of an undecidable tie */
+    int32_t reserved;
+    float paired_ms, rest_ms, redo_ms;   /* CUDA-event durations on the launching streams; 0 unless nr_set_timing(1) */
+    float reserved2;
+} nr_launch_info_t;
+
 /* Data-type preset table (reference tk.py:502-517: ont, ont_sup, ont_q20, clr, hifi -- all map-ont). */
 int nr_get_preset(const char* data_type, nr_scoring_t* out);
 
@@ -186,6 +198,9 @@ int nr_batch_fetch_round2(nr_batch_t* b, int32_t* score, int32_t* tend, uint8_t*
 int nr_batch_fetch_round3(nr_batch_t* b, const int64_t* rung_offset, nr_rung_t* rungs,
                           int64_t* sum_k, int32_t* n_k, int32_t* top_score);  /* round3 batches */
 int nr_batch_stats(const nr_batch_t* b, nr_stats_t* out);
+/* nr_set_timing(1): nr_batch_run brackets every kernel with CUDA events; nr_batch_launch_info waits for the run. */
+int nr_set_timing(int on);
+int nr_batch_launch_info(nr_batch_t* b, nr_launch_info_t* out);
 void nr_batch_destroy(nr_batch_t* b);
 
 /* Counters of the last nr_score_tasks / nr_round2_region / nr_round3_region call on this thread. */

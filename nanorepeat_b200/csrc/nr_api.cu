@@ -78,6 +78,7 @@ std::mutex g_ctx_mu;
 // 3: paired flag ladder (two reads per warp, u16x2 words), 2: flag ladder, 1: shared sweeps with full records,
 // 0: every rung its own rectangle
 std::atomic<int> g_ladder_mode{3};
+std::atomic<int> g_timing{0};        // nr_set_timing: CUDA events around every kernel of nr_batch_run
 
 int ensure_init(int device) {
     std::lock_guard<std::mutex> lk(g_ctx_mu);
@@ -253,6 +254,10 @@ struct nr_batch {
     int32_t* d_redo = nullptr;                // round 3 pairs: reads to rescore on 32-bit flag words
     size_t redo_bytes = 0;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_t[6] = {};                 // nr_set_timing(1): start / end of the 32-bit, paired and redo launches
+    bool timed[3] = {};
+    int* h_redo_count = nullptr;              // pinned
+    long long paired_cells = 0, rest_cells = 0;
     size_t n_out = 0;                         // records in d_out / h_out
     std::vector<int32_t> order;
     Launch launch = {};
@@ -440,7 +445,8 @@ int plan_batch(nr_batch* b) {
         std::sort(po.begin(), po.end(), [&](int x, int y) { return pair_cost[x] != pair_cost[y] ? pair_cost[x] > pair_cost[y] : x < y; });
         if (!b->pairs2.empty()) { std::vector<nr::pr::Pair2> t(L.n_pairs); for (int i = 0; i < L.n_pairs; ++i) t[i] = b->pairs2[po[i]]; b->pairs2.swap(t); }
         else { std::vector<nr::pr::Pair3> t(L.n_pairs); for (int i = 0; i < L.n_pairs; ++i) t[i] = b->pairs3[po[i]]; b->pairs3.swap(t); }
-        for (long long c : pair_cost) b->stats.executed_cells += 2 * c;      // both halves of every word
+        for (long long c : pair_cost) b->paired_cells += 2 * c;             // both halves of every word
+        b->stats.executed_cells += b->paired_cells;
         L.pair_blocks = std::max(1, std::min(g_ctx.sm_count, L.n_pairs));
     }
     // ---- the rest: one persistent launch of the 32-bit kernels; tasks in decreasing cost (long multi-stripe tasks
@@ -462,8 +468,9 @@ int plan_batch(nr_batch* b) {
         } else {
             max_single_cost = std::max(max_single_cost, cost[i]);
         }
-        b->stats.executed_cells += cost[i];
+        b->rest_cells += cost[i];
     }
+    b->stats.executed_cells += b->rest_cells;
     const int n_rest = (int)b->order.size();
     std::sort(b->order.begin(), b->order.end(),
               [&](int x, int y) { return cost[x] != cost[y] ? cost[x] > cost[y] : x < y; });
@@ -513,6 +520,8 @@ int plan_batch(nr_batch* b) {
         b->redo_bytes = sizeof(int32_t) * (size_t)n;
         if ((rc = cached_alloc((void**)&b->d_prung, b->prung_bytes, false))) return rc;
         if ((rc = cached_alloc((void**)&b->d_redo, b->redo_bytes, false))) return rc;
+        if ((rc = cached_alloc((void**)&b->h_redo_count, 64, true))) return rc;
+        *b->h_redo_count = 0;
     }
     char* h = static_cast<char*>(b->h_blob);
     char* d = static_cast<char*>(b->d_blob);
@@ -580,6 +589,12 @@ int run_batch(nr_batch* b, cudaStream_t st) {
     CUDA_TRY(cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(int), st));
     int launches = 0;
     int rc;
+    const bool timing = g_timing.load() != 0;
+    if (timing)
+        for (cudaEvent_t& e : b->ev_t)
+            if (!e) CUDA_TRY(cudaEventCreate(&e));
+    b->timed[0] = b->timed[1] = b->timed[2] = false;
+    auto mark = [&](int i, cudaStream_t s) { return timing ? cudaEventRecord(b->ev_t[i], s) : cudaSuccess; };
     if (L.n_pairs) {
         // the tasks the paired kernels do not take (long reads, odd scoring ranges) run beside them on a second stream
         cudaStream_t rest_st = st;
@@ -587,10 +602,14 @@ int run_batch(nr_batch* b, cudaStream_t st) {
             rest_st = g_ctx.side;
             CUDA_TRY(cudaEventRecord(b->ev_fork, st));
             CUDA_TRY(cudaStreamWaitEvent(rest_st, b->ev_fork, 0));
+            CUDA_TRY(mark(0, rest_st));
             if ((rc = launch_rest(b, rest_st, k, b->d_order, L.count, L.n_excl, L.blocks, L.R, nullptr, b->d_counters))) return rc;
+            CUDA_TRY(mark(1, rest_st));
+            b->timed[0] = timing;
             CUDA_TRY(cudaEventRecord(b->ev_join, rest_st));
             ++launches;
         }
+        CUDA_TRY(mark(2, st));
         if (!b->pairs2.empty()) {
             const int stride = exact_smem_int4(L.pair_R);
             const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
@@ -608,16 +627,25 @@ int run_batch(nr_batch* b, cudaStream_t st) {
                 b->d_counters + 2, b->d_redo);
         }
         CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(mark(3, st));
+        b->timed[1] = timing;
         ++launches;
         if (L.count) CUDA_TRY(cudaStreamWaitEvent(st, b->ev_join, 0));
         if (!b->pairs3.empty()) {
+            CUDA_TRY(mark(4, st));
             // reads whose selection hinges on a tie the 16-bit words cannot order: 32-bit flag ladder, count on the device
             if ((rc = launch_rest(b, st, k, b->d_redo, 0, 0, std::min(g_ctx.sm_count, 2 * L.n_pairs), L.redo_R,
                                   b->d_counters + 2, b->d_counters + 3))) return rc;
+            CUDA_TRY(mark(5, st));
+            b->timed[2] = timing;
+            CUDA_TRY(cudaMemcpyAsync(b->h_redo_count, b->d_counters + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
             ++launches;
         }
     } else if (L.count) {
+        CUDA_TRY(mark(0, st));
         if ((rc = launch_rest(b, st, k, b->d_order, L.count, L.n_excl, L.blocks, L.R, nullptr, b->d_counters))) return rc;
+        CUDA_TRY(mark(1, st));
+        b->timed[0] = timing;
         ++launches;
     }
     // results start their way back as soon as the kernel is done (a fetch issued later would queue behind whatever
@@ -823,7 +851,8 @@ int add_round3(nr_batch* b, const char* left, int32_t n_left, const char* right,
 }
 
 void free_events(nr_batch* b) {
-    for (cudaEvent_t* e : {&b->ev_uploaded, &b->ev_done, &b->ev_fork, &b->ev_join})
+    for (cudaEvent_t* e : {&b->ev_uploaded, &b->ev_done, &b->ev_fork, &b->ev_join, &b->ev_t[0], &b->ev_t[1], &b->ev_t[2],
+                           &b->ev_t[3], &b->ev_t[4], &b->ev_t[5]})
         if (*e) { cudaEventDestroy(*e); *e = nullptr; }
 }
 
@@ -919,6 +948,7 @@ void nr_batch_destroy(nr_batch_t* b) {
     cached_free(b->h_sel, b->sel_bytes, true);
     cached_free(b->d_prung, b->prung_bytes, false);
     cached_free(b->d_redo, b->redo_bytes, false);
+    cached_free(b->h_redo_count, 64, true);
     nr_batch* src = b->qsrc;
     free_events(b);
     delete b;
@@ -1146,6 +1176,29 @@ int nr_batch_fetch_round3(nr_batch_t* b, const int64_t* rung_offset, nr_rung_t* 
         sum_k[r] = sum;
         n_k[r] = cnt;
         top_score[r] = top;
+    }
+    return NR_OK;
+}
+
+int nr_set_timing(int on) {
+    g_timing.store(on ? 1 : 0);
+    return NR_OK;
+}
+
+int nr_batch_launch_info(nr_batch_t* b, nr_launch_info_t* out) {
+    if (!b || !out) return fail(NR_ERR_ARG, "nr_batch_launch_info: NULL argument");
+    if (!b->committed) return fail(NR_ERR_ARG, "nr_batch_launch_info: batch was not committed");
+    *out = {};
+    out->paired_cells = b->paired_cells;
+    out->rest_cells = b->rest_cells;
+    out->n_pairs = b->launch.n_pairs;
+    out->n_rest = b->launch.count;
+    if (b->ran) {
+        CUDA_TRY(cudaEventSynchronize(b->ev_done));
+        if (b->h_redo_count) out->n_redo = *b->h_redo_count;
+        if (b->timed[0]) CUDA_TRY(cudaEventElapsedTime(&out->rest_ms, b->ev_t[0], b->ev_t[1]));
+        if (b->timed[1]) CUDA_TRY(cudaEventElapsedTime(&out->paired_ms, b->ev_t[2], b->ev_t[3]));
+        if (b->timed[2]) CUDA_TRY(cudaEventElapsedTime(&out->redo_ms, b->ev_t[4], b->ev_t[5]));
     }
     return NR_OK;
 }

@@ -30,6 +30,16 @@ class Stats(ctypes.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
 
 
+class LaunchInfo(ctypes.Structure):
+    _fields_ = [("paired_cells", ctypes.c_int64), ("rest_cells", ctypes.c_int64), ("n_pairs", ctypes.c_int32),
+                ("n_rest", ctypes.c_int32), ("n_redo", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("paired_ms", ctypes.c_float), ("rest_ms", ctypes.c_float), ("redo_ms", ctypes.c_float),
+                ("reserved2", ctypes.c_float)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}
+
+
 ALN_DTYPE = np.dtype([("score", "<i4"), ("tstart", "<i4"), ("tend", "<i4")])
 RUNG_DTYPE = np.dtype([("score", "<i4"), ("starts_in_left", "u1"), ("ends_in_right", "u1"), ("pad", "u1", (2,))])
 
@@ -83,6 +93,8 @@ SYMBOLS = {
     "nr_batch_fetch_round2": (ctypes.c_int, [ctypes.c_void_p, _i32p, _i32p, ctypes.c_void_p]),
     "nr_batch_fetch_round3": (ctypes.c_int, [ctypes.c_void_p, _i64p, ctypes.c_void_p, _i64p, _i32p, _i32p]),
     "nr_batch_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Stats)]),
+    "nr_set_timing": (ctypes.c_int, [ctypes.c_int]),
+    "nr_batch_launch_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(LaunchInfo)]),
     "nr_batch_destroy": (None, [ctypes.c_void_p]),
     "nr_last_stats": (ctypes.c_int, [ctypes.POINTER(Stats)]),
 }
@@ -141,6 +153,11 @@ def set_ladder_mode(mode):
 
 def ladder_mode():
     return _ladder_mode
+
+
+def set_timing(on):
+    """Bracket every kernel of Batch.run() with CUDA events (read back through Batch.launch_info())."""
+    _check(lib().nr_set_timing(int(bool(on))))
 
 
 def last_stats():
@@ -329,6 +346,12 @@ class Batch:
         st = Stats()
         _check(lib().nr_batch_stats(self._h, ctypes.byref(st)))
         return st.as_dict()
+
+    def launch_info(self):
+        """How the last run() split its work between the paired and the 32-bit kernels (+ event times, set_timing)."""
+        li = LaunchInfo()
+        _check(lib().nr_batch_launch_info(self._h, ctypes.byref(li)))
+        return li.as_dict()
 
     def close(self):
         if self._h:
