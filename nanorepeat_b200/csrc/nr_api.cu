@@ -101,7 +101,11 @@ int ensure_init(int device) {
         return fail(NR_ERR_CUDA, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 part", device, prop.name,
                     prop.major, prop.minor);
     CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.side, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&g_ctx.side, cudaStreamNonBlocking, hi));   // its blocks are placed first
+    }
     g_ctx.device = device;
     g_ctx.sm_count = prop.multiProcessorCount;
     g_ctx.clock_khz = prop.clockRate;
@@ -212,12 +216,10 @@ struct Launch {      // one persistent launch per batch
     bool ladder;     // ladder_kernel over nr_batch::ltasks instead of exact_kernel over nr_batch::tasks
     int R;           // tallest stripe of the launch: sizes the shared memory per warp
     int count;
-    int n_excl;      // leading multi-stripe tasks that get a scheduler each (nr_kernels.cuh, TaskCursor)
+    int wpb;         // warps per block of the 32-bit launch: 16, or 4 when it runs beside the paired launch (both resident)
     int blocks;
     bool fixed;      // scoring == map-ont: kernels with immediate constants
-    long long scratch_stride;   // int4 per boundary row (multi-stripe tasks only; 0: the batch has none)
-    long long b_stride;         // ladder: int4 of backward junction vectors per warp
-    long long tok_stride;       // ladder: ulonglong2 per token row
+    int pair_wpb;    // warps per block of the paired launch
     // paired launch (nr_pair_kernels.cuh): two reads of one region per warp
     int n_pairs;
     int pair_R;
@@ -259,7 +261,13 @@ struct nr_batch {
     int* h_redo_count = nullptr;              // pinned
     long long paired_cells = 0, rest_cells = 0;
     size_t n_out = 0;                         // records in d_out / h_out
-    std::vector<int32_t> order;
+    std::vector<int32_t> order;               // entries of the 32-bit launch: (task << 7) | code (nr_kernels.cuh)
+    std::vector<nr::CoopInfo> coop;           // scratch of the multi-stripe tasks
+    std::vector<int32_t> coop_idx;            // exact tasks: index into coop, -1 for single-stripe tasks
+    nr::CoopInfo* d_coop = nullptr;
+    int32_t* d_coop_idx = nullptr;
+    int* d_flags = nullptr;                   // progress flags of the multi-stripe tasks, zeroed before every run
+    size_t flags_bytes = 0;
     Launch launch = {};
     Pool pool;
     // per-read bookkeeping (rounds 2 and 3)
@@ -449,58 +457,107 @@ int plan_batch(nr_batch* b) {
         b->stats.executed_cells += b->paired_cells;
         L.pair_blocks = std::max(1, std::min(g_ctx.sm_count, L.n_pairs));
     }
-    // ---- the rest: one persistent launch of the 32-bit kernels; tasks in decreasing cost (long multi-stripe tasks
-    // first) so the tail is short ----
-    int rmax = 0, tmax = 0, qmax = 0, rungs_max = 0;      // tmax, qmax, rungs_max: over multi-stripe tasks only
-    int n_multi = 0;
-    long long min_multi_cost = 0, max_single_cost = 0;
-    b->order.clear();
+    // ---- the rest: one persistent launch of the 32-bit kernels.  Long reads are cut into stripes that run on
+    // different warps at the same time (nr_kernels.cuh, CoopInfo); their entries come first, by decreasing cost, every
+    // entry behind what it waits for; then the single-stripe tasks by decreasing cost ----
+    std::vector<int> singles, multis;
+    long long multi_rows = 0;
     for (int i = 0; i < n; ++i) {
         if (paired[i]) continue;
-        b->order.push_back(i);
-        rmax = std::max(rmax, task_R[i]);
-        if (task_ns[i] > 1) {
-            tmax = std::max(tmax, task_sweep[i]);
-            qmax = std::max(qmax, task_ns[i] * 32 * task_R[i]);
-            rungs_max = std::max(rungs_max, task_rungs[i]);
-            min_multi_cost = n_multi ? std::min(min_multi_cost, cost[i]) : cost[i];
-            ++n_multi;
-        } else {
-            max_single_cost = std::max(max_single_cost, cost[i]);
+        (task_ns[i] > 1 ? multis : singles).push_back(i);
+        if (task_ns[i] > 1) multi_rows += ladder ? b->ltasks[i].q_len : b->tasks[i].q_len;
+    }
+    if (!multis.empty()) {
+        // stripe height of the long tasks: the shortest that does not cut them into more stripes than there are warps
+        // to run them side by side (a stripe is one warp's work; the ladder's two sweeps overlap)
+        const long long warps = (long long)(L.n_pairs ? 4 : kWarpsPerBlock) * g_ctx.sm_count;
+        int cap = max_r;
+        const char* force = getenv("NR_COOP_ROWS");       // tuning / debugging: fixed stripe height of the long tasks
+        if (force && atoi(force) >= nr::kMinR && atoi(force) <= max_r) cap = atoi(force);
+        else for (int r : {4, 6, 8}) {
+            if (r >= max_r) break;
+            const long long stripes = (multi_rows / (32 * r) + (long long)multis.size()) * (ladder ? 2 : 1);
+            if (stripes <= warps) { cap = r; break; }
         }
+        for (int i : multis) {
+            const int q_len = ladder ? b->ltasks[i].q_len : b->tasks[i].q_len;
+            int ns = (q_len + 32 * cap - 1) / (32 * cap);
+            ns = std::min(ns, nr::kCodeFwd - 2);
+            const int R = nr::coop_rows(q_len, ns);
+            if (R > max_r)
+                return fail(NR_ERR_TOO_LARGE, "task %d: a query of %d bases needs more than %d stripes", i, q_len, nr::kCodeFwd - 2);
+            cost[i] = cost[i] / ((long long)task_ns[i] * task_R[i]) * ((long long)ns * R);
+            task_ns[i] = ns;
+            task_R[i] = R;
+        }
+    }
+    int rmax = 0;
+    for (int i = 0; i < n; ++i) {
+        if (paired[i]) continue;
+        rmax = std::max(rmax, task_R[i]);
         b->rest_cells += cost[i];
     }
     b->stats.executed_cells += b->rest_cells;
+    auto by_cost = [&](int x, int y) { return cost[x] != cost[y] ? cost[x] > cost[y] : x < y; };
+    std::sort(singles.begin(), singles.end(), by_cost);
+    std::sort(multis.begin(), multis.end(), by_cost);
+    if (n > (1 << (31 - nr::kCodeBits))) return fail(NR_ERR_TOO_LARGE, "more than 2^24 tasks in one batch");
+    b->order.clear();
+    b->coop.clear();
+    if (!ladder) b->coop_idx.assign(n, -1);
+    long long data_off = 0, flag_off = 0;
+    for (int i : multis) {
+        nr::CoopInfo ci = {};
+        ci.n_stripes = task_ns[i];
+        ci.data_off = data_off;
+        ci.flag_off = (int)flag_off;
+        ci.bnd_stride = (task_sweep[i] + 63) / 32 * 32;
+        if (ladder) {
+            ci.b_stride = task_ns[i] * 32 * task_R[i];
+            ci.tok_stride = (task_rungs[i] + 1) / 2 * 2;
+        }
+        data_off += (ladder ? 4LL : 2LL) * ci.bnd_stride + ci.b_stride + 2LL * ci.tok_stride;
+        flag_off += nr::kCoopFlagInts(task_ns[i]);
+        if (flag_off > 0x7fffffffLL) return fail(NR_ERR_TOO_LARGE, "too many long tasks in one batch");
+        if (ladder) b->ltasks[i].pad = (int32_t)b->coop.size();
+        else b->coop_idx[i] = (int32_t)b->coop.size();
+        b->coop.push_back(ci);
+    }
+    for (int i : multis) {                                  // first sweep of every long task (ladder: backward)
+        if (ladder && b->lregs[b->ltasks[i].region].n_right == 0) continue;
+        for (int st = 0; st < task_ns[i]; ++st) b->order.push_back((i << nr::kCodeBits) | (1 + st));
+    }
+    if (ladder)
+        for (int i : multis)
+            for (int st = 0; st < task_ns[i]; ++st) b->order.push_back((i << nr::kCodeBits) | (nr::kCodeFwd + st));
+    for (int i : singles) b->order.push_back(i << nr::kCodeBits);
     const int n_rest = (int)b->order.size();
-    std::sort(b->order.begin(), b->order.end(),
-              [&](int x, int y) { return cost[x] != cost[y] ? cost[x] > cost[y] : x < y; });
     L.ladder = ladder;
     L.R = rmax;
     L.count = n_rest;
-    L.blocks = std::max(1, std::min(g_ctx.sm_count, n_rest));  // one persistent block per SM; a small batch still spreads
-    // the long tasks run alone on a scheduler when they are few and really lead the cost order
-    L.n_excl = (n_multi > 0 && n_multi < n_rest && n_multi <= nr::kExclusiveWarps * L.blocks && min_multi_cost >= max_single_cost)
-                   ? n_multi : 0;
+    // both launches resident on every SM at the same time: 16 warps x 128 registers between them, the larger share of
+    // the work gets 12
+    L.wpb = !L.n_pairs ? kWarpsPerBlock : (b->rest_cells > b->paired_cells ? kWarpsPerBlock - 4 : 4);
+    L.pair_wpb = n_rest ? kWarpsPerBlock - L.wpb : kWarpsPerBlock;
+    // one persistent block per SM (every block resident: entries may wait for each other); a small batch still spreads
+    L.blocks = std::max(1, std::min(g_ctx.sm_count, n_rest));
     L.fixed = fixed;
-    size_t scratch_total = 0;
-    if (tmax > 0) {
-        L.scratch_stride = ((long long)tmax + 63) / 32 * 32;
-        if (ladder) {
-            L.b_stride = qmax;
-            L.tok_stride = rungs_max;
-        }
-        scratch_total = (size_t)L.blocks * kWarpsPerBlock * (size_t)(2 * L.scratch_stride + L.b_stride + 2 * L.tok_stride);
-    }
+    const size_t scratch_total = (size_t)data_off;
+    b->flags_bytes = sizeof(int) * (size_t)flag_off;
     // ---- one device blob: [tasks | regions | order | pairs | pool (+4 slack words) | counters], staged in pinned memory ----
     const size_t task_bytes = ladder ? sizeof(nr::LadderTask) * n : sizeof(nr::Task) * n;
     const size_t reg_bytes = sizeof(nr::LadderRegion) * b->lregs.size();
     const size_t order_bytes = sizeof(int32_t) * n_rest;
     const size_t pair_bytes = b->pairs2.empty() ? sizeof(nr::pr::Pair3) * b->pairs3.size() : sizeof(nr::pr::Pair2) * b->pairs2.size();
     const size_t pool_bytes = sizeof(uint32_t) * (b->pool.words.size() + 4);
+    const size_t coop_bytes = sizeof(nr::CoopInfo) * b->coop.size();
+    const size_t cidx_bytes = b->coop.empty() ? 0 : sizeof(int32_t) * b->coop_idx.size();
     const size_t off_reg = align_up(task_bytes, 256);
     const size_t off_order = off_reg + align_up(reg_bytes, 256);
     const size_t off_pair = off_order + align_up(order_bytes, 256);
-    const size_t off_pool = off_pair + align_up(pair_bytes, 256);
+    const size_t off_coop = off_pair + align_up(pair_bytes, 256);
+    const size_t off_cidx = off_coop + align_up(coop_bytes, 256);
+    const size_t off_pool = off_cidx + align_up(cidx_bytes, 256);
     const size_t off_cnt = off_pool + align_up(pool_bytes, 256);
     b->blob_bytes = off_cnt + 256;
     b->out_bytes = sizeof(int4) * std::max<size_t>(b->n_out, 1);
@@ -511,6 +568,7 @@ int plan_batch(nr_batch* b) {
     if ((rc = cached_alloc((void**)&b->d_out, b->out_bytes, false))) return rc;
     if ((rc = cached_alloc((void**)&b->h_out, b->out_bytes, true))) return rc;
     if (scratch_total && (rc = cached_alloc((void**)&b->d_scratch, b->scratch_bytes, false))) return rc;
+    if (b->flags_bytes && (rc = cached_alloc((void**)&b->d_flags, b->flags_bytes, false))) return rc;
     if (b->flag) {
         b->sel_bytes = sizeof(int4) * std::max<size_t>((size_t)b->n_reads, 1);
         if ((rc = cached_alloc((void**)&b->d_sel, b->sel_bytes, false))) return rc;
@@ -528,6 +586,8 @@ int plan_batch(nr_batch* b) {
     if (task_bytes) memcpy(h, ladder ? (const void*)b->ltasks.data() : (const void*)b->tasks.data(), task_bytes);
     if (reg_bytes) memcpy(h + off_reg, b->lregs.data(), reg_bytes);
     if (order_bytes) memcpy(h + off_order, b->order.data(), order_bytes);
+    if (coop_bytes) memcpy(h + off_coop, b->coop.data(), coop_bytes);
+    if (cidx_bytes) memcpy(h + off_cidx, b->coop_idx.data(), cidx_bytes);
     if (pair_bytes) memcpy(h + off_pair, b->pairs2.empty() ? (const void*)b->pairs3.data() : (const void*)b->pairs2.data(), pair_bytes);
     if (!b->pool.words.empty()) memcpy(h + off_pool, b->pool.words.data(), pool_bytes - 16);
     memset(h + off_pool + pool_bytes - 16, 0, 16);
@@ -537,6 +597,8 @@ int plan_batch(nr_batch* b) {
     b->d_lregs = reinterpret_cast<nr::LadderRegion*>(d + off_reg);
     b->d_order = reinterpret_cast<int32_t*>(d + off_order);
     b->d_pairs = d + off_pair;
+    b->d_coop = reinterpret_cast<nr::CoopInfo*>(d + off_coop);
+    b->d_coop_idx = reinterpret_cast<int32_t*>(d + off_cidx);
     b->d_pool = reinterpret_cast<uint32_t*>(d + off_pool);
     b->d_counters = reinterpret_cast<int*>(d + off_cnt);
     cudaStream_t st = g_ctx.stream;
@@ -544,33 +606,42 @@ int plan_batch(nr_batch* b) {
     CUDA_TRY(cudaMemsetAsync(b->d_out, 0, b->out_bytes, st));
     if (b->d_sel) CUDA_TRY(cudaMemsetAsync(b->d_sel, 0, b->sel_bytes, st));
     CUDA_TRY(cudaEventRecord(b->ev_uploaded, st));      // nr_batch_run on another stream waits for it; no host sync here
-    b->stats.h2d_bytes = (int64_t)(task_bytes + reg_bytes + order_bytes + pair_bytes + pool_bytes);
+    b->stats.h2d_bytes = (int64_t)(task_bytes + reg_bytes + order_bytes + pair_bytes + coop_bytes + cidx_bytes + pool_bytes);
     b->stats.d2h_bytes = (int64_t)sizeof(int4) * (b->flag ? (int64_t)b->n_reads : (int64_t)b->n_out);
     b->committed = true;
     return NR_OK;
 }
 
+// dynamic shared memory up to max_bytes, and the SM's L1 / shared split all the way to shared: a paired and a 32-bit
+// block must fit one SM together
+int prepare_kernel(const void* fn, size_t max_bytes) {
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    return NR_OK;
+}
+
 // launch of the 32-bit kernels over order[0, count) (count_dev != NULL: the count is read on the device)
-int launch_rest(nr_batch* b, cudaStream_t st, const nr::ScoreW& k, const int32_t* order, int count, int n_excl,
-                int blocks, int R, const int* count_dev, int* counter) {
+int launch_rest(nr_batch* b, cudaStream_t st, const nr::ScoreW& k, const int32_t* order, int count, int blocks, int wpb,
+                int R, const int* count_dev, int* counter) {
     const Launch& L = b->launch;
     if (L.ladder) {
         auto fn = b->flag ? (L.fixed ? nr::ladder_kernel<true, true> : nr::ladder_kernel<false, true>)
                           : (L.fixed ? nr::ladder_kernel<true, false> : nr::ladder_kernel<false, false>);
         const int stride = ladder_smem_int4(R);
-        const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
-        CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fn<<<blocks, kWarpsPerBlock * 32, smem, st>>>(b->d_ltasks, order, count, n_excl, count_dev,
-                                                     b->qsrc ? b->qsrc->d_pool : b->d_pool, b->d_pool, b->d_lregs, k,
-                                                     counter, stride, b->d_scratch, L.scratch_stride,
-                                                     L.b_stride, L.tok_stride, b->d_out, b->d_sel);
+        const size_t smem = (size_t)wpb * stride * sizeof(int4);
+        int rc = prepare_kernel((const void*)fn, kWarpsPerBlock * ladder_smem_int4(nr::kMaxRLadder) * sizeof(int4));
+        if (rc) return rc;
+        fn<<<blocks, wpb * 32, smem, st>>>(b->d_ltasks, order, count, count_dev,
+                                          b->qsrc ? b->qsrc->d_pool : b->d_pool, b->d_pool, b->d_lregs, k,
+                                          counter, stride, b->d_scratch, b->d_coop, b->d_flags, b->d_out, b->d_sel);
     } else {
         auto fn = L.fixed ? nr::exact_kernel<true> : nr::exact_kernel<false>;
         const int stride = exact_smem_int4(R);
-        const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
-        CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fn<<<blocks, kWarpsPerBlock * 32, smem, st>>>(b->d_tasks, order, count, n_excl, b->d_pool, k,
-                                                     counter, stride, b->d_scratch, L.scratch_stride, b->d_out);
+        const size_t smem = (size_t)wpb * stride * sizeof(int4);
+        int rc = prepare_kernel((const void*)fn, kWarpsPerBlock * exact_smem_int4(nr::kMaxRExact) * sizeof(int4));
+        if (rc) return rc;
+        fn<<<blocks, wpb * 32, smem, st>>>(b->d_tasks, order, count, b->d_pool, k,
+                                          counter, stride, b->d_scratch, b->d_coop, b->d_coop_idx, b->d_flags, b->d_out);
     }
     CUDA_TRY(cudaGetLastError());
     return NR_OK;
@@ -587,6 +658,7 @@ int run_batch(nr_batch* b, cudaStream_t st) {
     }
     // counters: [0] 32-bit kernels, [1] paired kernel, [2] length of the redo list, [3] redo launch
     CUDA_TRY(cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(int), st));
+    if (b->flags_bytes) CUDA_TRY(cudaMemsetAsync(b->d_flags, 0, b->flags_bytes, st));
     int launches = 0;
     int rc;
     const bool timing = g_timing.load() != 0;
@@ -603,7 +675,7 @@ int run_batch(nr_batch* b, cudaStream_t st) {
             CUDA_TRY(cudaEventRecord(b->ev_fork, st));
             CUDA_TRY(cudaStreamWaitEvent(rest_st, b->ev_fork, 0));
             CUDA_TRY(mark(0, rest_st));
-            if ((rc = launch_rest(b, rest_st, k, b->d_order, L.count, L.n_excl, L.blocks, L.R, nullptr, b->d_counters))) return rc;
+            if ((rc = launch_rest(b, rest_st, k, b->d_order, L.count, L.blocks, L.wpb, L.R, nullptr, b->d_counters))) return rc;
             CUDA_TRY(mark(1, rest_st));
             b->timed[0] = timing;
             CUDA_TRY(cudaEventRecord(b->ev_join, rest_st));
@@ -612,16 +684,16 @@ int run_batch(nr_batch* b, cudaStream_t st) {
         CUDA_TRY(mark(2, st));
         if (!b->pairs2.empty()) {
             const int stride = exact_smem_int4(L.pair_R);
-            const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
-            CUDA_TRY(cudaFuncSetAttribute((const void*)nr::pr::pair_round2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            nr::pr::pair_round2_kernel<<<L.pair_blocks, kWarpsPerBlock * 32, smem, st>>>(
+            const size_t smem = (size_t)L.pair_wpb * stride * sizeof(int4);
+            if ((rc = prepare_kernel((const void*)nr::pr::pair_round2_kernel, kWarpsPerBlock * exact_smem_int4(nr::pr::kMaxRPair2) * sizeof(int4)))) return rc;
+            nr::pr::pair_round2_kernel<<<L.pair_blocks, L.pair_wpb * 32, smem, st>>>(
                 static_cast<const nr::pr::Pair2*>(b->d_pairs), L.n_pairs, b->d_tasks, b->d_pool, 1u, 4u, b->d_counters + 1,
                 stride, b->d_out);
         } else {
             const int stride = ladder_smem_int4(L.pair_R);
-            const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
-            CUDA_TRY(cudaFuncSetAttribute((const void*)nr::pr::pair_ladder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            nr::pr::pair_ladder_kernel<<<L.pair_blocks, kWarpsPerBlock * 32, smem, st>>>(
+            const size_t smem = (size_t)L.pair_wpb * stride * sizeof(int4);
+            if ((rc = prepare_kernel((const void*)nr::pr::pair_ladder_kernel, kWarpsPerBlock * ladder_smem_int4(nr::pr::kMaxRPair3) * sizeof(int4)))) return rc;
+            nr::pr::pair_ladder_kernel<<<L.pair_blocks, L.pair_wpb * 32, smem, st>>>(
                 static_cast<const nr::pr::Pair3*>(b->d_pairs), L.n_pairs, b->d_ltasks, b->qsrc ? b->qsrc->d_pool : b->d_pool,
                 b->d_pool, b->d_lregs, 1u, 4u, k.min_score, b->d_counters + 1, stride, b->d_prung, b->d_sel,
                 b->d_counters + 2, b->d_redo);
@@ -634,7 +706,7 @@ int run_batch(nr_batch* b, cudaStream_t st) {
         if (!b->pairs3.empty()) {
             CUDA_TRY(mark(4, st));
             // reads whose selection hinges on a tie the 16-bit words cannot order: 32-bit flag ladder, count on the device
-            if ((rc = launch_rest(b, st, k, b->d_redo, 0, 0, std::min(g_ctx.sm_count, 2 * L.n_pairs), L.redo_R,
+            if ((rc = launch_rest(b, st, k, b->d_redo, 0, std::min(g_ctx.sm_count, 2 * L.n_pairs), kWarpsPerBlock, L.redo_R,
                                   b->d_counters + 2, b->d_counters + 3))) return rc;
             CUDA_TRY(mark(5, st));
             b->timed[2] = timing;
@@ -643,7 +715,7 @@ int run_batch(nr_batch* b, cudaStream_t st) {
         }
     } else if (L.count) {
         CUDA_TRY(mark(0, st));
-        if ((rc = launch_rest(b, st, k, b->d_order, L.count, L.n_excl, L.blocks, L.R, nullptr, b->d_counters))) return rc;
+        if ((rc = launch_rest(b, st, k, b->d_order, L.count, L.blocks, L.wpb, L.R, nullptr, b->d_counters))) return rc;
         CUDA_TRY(mark(1, st));
         b->timed[0] = timing;
         ++launches;
@@ -944,6 +1016,7 @@ void nr_batch_destroy(nr_batch_t* b) {
     cached_free(b->d_out, b->out_bytes, false);
     cached_free(b->h_out, b->out_bytes, true);
     cached_free(b->d_scratch, b->scratch_bytes, false);
+    cached_free(b->d_flags, b->flags_bytes, false);
     cached_free(b->d_sel, b->sel_bytes, false);
     cached_free(b->h_sel, b->sel_bytes, true);
     cached_free(b->d_prung, b->prung_bytes, false);

@@ -144,6 +144,23 @@ __device__ __forceinline__ u64 key_of_junction(int khi, int klo) {
     return ((u64)(cap >> 16) << 32) | ((u64)(0xffffu - ext) << 16) | (u64)(0xffffu - (unsigned)(-klo));
 }
 
+// Stripes of one long task run on different warps (any SM) at the same time, each a few dozen columns behind the one
+// above it: the producer's last lane stores its bottom row (and junction tokens) with .cg stores and then releases the
+// number of finished columns; the consumer acquires it before it prefetches the next 32 columns.
+__device__ __forceinline__ void publish_cols(int* flag, int cols) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(cols) : "memory");
+}
+__device__ __forceinline__ int peek_cols(const int* flag) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    return v;
+}
+__device__ __forceinline__ void wait_cols(const int* flag, int need, int lane) {
+    if (lane == 0)
+        while (peek_cols(flag) < need) __nanosleep(100);
+    __syncwarp();
+}
+
 __device__ __forceinline__ u64 shfl_up64(u64 v) {
     unsigned lo = __shfl_up_sync(kFull, (unsigned)v, 1);
     unsigned hi = __shfl_up_sync(kFull, (unsigned)(v >> 32), 1);
@@ -268,11 +285,20 @@ struct Sweep {
     bool top, bot;
     const int4* bnd_in;
     int4* bnd_out;
+    const int* prog_in;            // MULTI: columns the stripe above has finished (its boundary row / tokens are in L2)
+    int* prog_out;                 //        columns this stripe has finished
     // backward sweeps
     int4* bdst;
     int q_len, brow0;
     // forward sweeps
     const int4* bsm;
+    // MULTI forward sweeps: the junction vectors (and the R-only optimum) are fetched when the sweep reaches its first
+    // junction column, so that the stripes of the forward sweep run beside those of the backward sweep
+    int4* bsm_w;
+    const int4* bglob_rows;        // this stripe's rows of the backward vectors (forward layout), null: no backward sweep
+    const int* bdone;              // backward stripes that are done
+    int bdone_need, n_right;
+    bool late_pending;
     const ulonglong2* tok_in;
     ulonglong2* tok_out;
     int4* out;
@@ -311,7 +337,10 @@ struct Sweep {
         twl = 0;
         prof_lane = reinterpret_cast<const char*>(prof + lane);
         bcur = make_int4(0, 0, 0, 0); bnxt = make_int4(0, 0, 0, 0);
-        if (MULTI && top) bnxt = __ldcg(&bnd_in[lane < t_len ? lane : t_len - 1]);
+        if (MULTI && top) {
+            wait_cols(prog_in, min(32, t_len), lane);
+            bnxt = __ldcg(&bnd_in[lane < t_len ? lane : t_len - 1]);
+        }
         tokP = 0; tokJ = 0;
     }
 
@@ -414,6 +443,7 @@ struct Sweep {
         if (MULTI && top) {                 // uniform branch
             if ((st & 31) == 0) {
                 bcur = bnxt;
+                wait_cols(prog_in, min(st + 64, t_len), lane);
                 const int nj = st + 32 + lane;
                 bnxt = __ldcg(&bnd_in[nj < t_len ? nj : t_len - 1]);
             }
@@ -513,14 +543,42 @@ struct Sweep {
                 jnext += m;
                 ++kcnt;
             }
-            if (MULTI && bot && lane == 31) __stcg(&bnd_out[jj], make_int4(h_out, f1_out, f2_out, 0));
+            if (MULTI && bot && lane == 31) {
+                __stcg(&bnd_out[jj], make_int4(h_out, f1_out, f2_out, 0));
+                if ((jj & 31) == 31 || jj == t_len - 1) publish_cols(prog_out, jj + 1);
+            }
         }
+    }
+
+    __device__ __forceinline__ void late_load() {
+        u64 rkey = 0;
+        if (bglob_rows) {
+            wait_cols(bdone, bdone_need, lane);
+            rkey = __ldcg(reinterpret_cast<const u64*>(bdone + 2));
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            bsm_w[r * 32 + lane] = (bglob_rows && brow0 + r < q_len - 1) ? __ldcg(&bglob_rows[r * 32 + lane])
+                                   : (brow0 + r < q_len ? make_int4(0, kPadScore, kPadScore, 0) : make_int4(kPadScore, kPadScore, kPadScore, 0));
+        r_score = 0; r_end = 0; r_start = 0; rcand = kJuncNone;
+        if (rkey) {
+            if (MODE == kFwdF) {
+                rcand = (int)(unsigned)rkey - 2 * n_right;
+            } else {
+                r_score = (int)(rkey >> 32);
+                r_end = n_right - (int)((rkey >> 16) & 0xffffu);
+                r_start = n_right - (0xffff - (int)(rkey & 0xffffu));
+            }
+        }
+        __syncwarp();
+        late_pending = false;
     }
 
     template <class MS, class SC>
     __device__ __forceinline__ void slow_until(int& st, int end, const MS& ms, const SC& sc) {
 #pragma unroll 1
         for (; st < end; ++st) {
+            if (MULTI && kIsFwd && late_pending && st >= zone_start) late_load();
             if ((st & 15) == 0) refill();
             step<false>(st, ms, sc);
         }
@@ -581,126 +639,147 @@ __host__ __device__ __forceinline__ void stripe_shape(int q_len, int max_r, int&
     }
 }
 
-template <int R, bool MULTI, class SC>
-__device__ __forceinline__ u64 exact_task(const Task& tk, const uint32_t* __restrict__ pool, const SC& sc,
-                                          int4* prof, int lane, int n_stripes, int4* bnd_a, int4* bnd_b) {
-    const uint32_t* qwords = pool + tk.q_word;
-    const int rows_per_stripe = 32 * R;
-    u64 key = 0;
-    for (int s = 0; s < n_stripes; ++s) {
-        __syncwarp();
-        build_profile<R>(prof, qwords, tk.q_len, s * rows_per_stripe + lane * R, lane, ModeScore<SC, 1>(sc), false);
-        __syncwarp();
-        Sweep<R, kExact, MULTI> sw;
-        sw.prof = prof; sw.twords = pool + tk.t_word; sw.t_len = tk.t_len; sw.lane = lane;
-        sw.top = s > 0; sw.bot = s + 1 < n_stripes;
-        sw.bnd_in = (s & 1) ? bnd_a : bnd_b; sw.bnd_out = (s & 1) ? bnd_b : bnd_a;
-        sw.run(sc, 0);
-        const u64 k = key_of_best(sw.best, sw.best_col());
-        key = k > key ? k : key;
-    }
-    return key;
+// Scratch of one multi-stripe task.  flags (ints, zeroed before every run) at flag_off (even):
+//   [0, S) columns finished by stripe s of the first sweep (exact: the only sweep; ladder: backward)
+//   [S, 2S) the same for the ladder's forward sweep        [2S] stripes of the first sweep that are done
+//   [2S + 2, 2S + 4) 64-bit key: exact: the task's best; ladder: the R-only optimum of the backward sweep
+struct CoopInfo {
+    long long data_off;     // int4 index into scratch: [boundary rows a, b of the first sweep | (ladder) boundary rows a, b of the
+                            // forward sweep | backward vectors | token row a | token row b]: the ladder's two sweeps overlap
+    int flag_off;
+    int bnd_stride, b_stride, tok_stride;   // int4, int4, ulonglong2
+    int n_stripes, pad;
+};
+constexpr int kCoopFlagInts(int S) { return 2 * S + 4; }
+
+template <int R, class SC>
+__device__ __forceinline__ u64 exact_task(const Task& tk, const uint32_t* __restrict__ pool, const SC& sc, int4* prof, int lane) {
+    __syncwarp();
+    build_profile<R>(prof, pool + tk.q_word, tk.q_len, lane * R, lane, ModeScore<SC, 1>(sc), false);
+    __syncwarp();
+    Sweep<R, kExact, false> sw;
+    sw.prof = prof; sw.twords = pool + tk.t_word; sw.t_len = tk.t_len; sw.lane = lane;
+    sw.top = false; sw.bot = false;
+    sw.run(sc, 0);
+    return key_of_best(sw.best, sw.best_col());
 }
 
-template <int R, bool MULTI, class SC>
-__device__ __forceinline__ u64 exact_dispatch(int r, const Task& tk, const uint32_t* __restrict__ pool,
-                                              const SC& sc, int4* prof, int lane, int n_stripes, int4* bnd_a,
-                                              int4* bnd_b) {
-    if (r == R) return exact_task<R, MULTI>(tk, pool, sc, prof, lane, n_stripes, bnd_a, bnd_b);
-    if constexpr (R < kMaxRExact) return exact_dispatch<R + 1, MULTI>(r, tk, pool, sc, prof, lane, n_stripes, bnd_a, bnd_b);
+template <int R, class SC>
+__device__ __forceinline__ u64 exact_dispatch(int r, const Task& tk, const uint32_t* __restrict__ pool, const SC& sc,
+                                              int4* prof, int lane) {
+    if (r == R) return exact_task<R>(tk, pool, sc, prof, lane);
+    if constexpr (R < kMaxRExact) return exact_dispatch<R + 1>(r, tk, pool, sc, prof, lane);
     return 0ull;
 }
 
-// A query that needs several stripes has at least max_r / 2 + 1 rows per lane (stripe_shape).
-constexpr int kMinRMultiExact = kMaxRExact / 2 + 1;
-constexpr int kMinRMultiLadder = kMaxRLadder / 2 + 1;
-
-constexpr int kWarpsPerBlock = 16;     // one persistent 512-thread block per SM: 4 warps per scheduler
-constexpr int kExclusiveWarps = 4;     // warps 0..3 sit on the four schedulers of the SM (warp id % 4)
-
-// Task scheduling shared by both kernels.  order[] lists the tasks by decreasing cost.
-//   1. Exclusive phase: the first n_excl tasks are the few long multi-stripe ones.  Each gets a scheduler of its own:
-//      warp g (g < 4) of a block takes it and the three warps that share its scheduler (g + 4, g + 8, g + 12) wait on
-//      a named barrier.  A lone warp runs at ~80 % of a full scheduler's rate, so the long tasks finish early instead
-//      of crawling at a quarter of the speed and becoming the kernel's tail; the other schedulers work on.
-//   2. One static round, slot-major (task = warp * gridDim + block), so that a small batch spreads over all SMs.
-//   3. Dynamic: warps pull the remaining tasks from *counter.
-struct TaskCursor {
-    int n_excl, n_order, lane, warp;
-    int* counter;
-    int round;      // 0: exclusive, 1: static round, 2: dynamic
-    bool group_wait;
-    __device__ __forceinline__ TaskCursor(int n_excl_, int n_order_, int* counter_)
-        : n_excl(n_excl_), n_order(n_order_), lane(threadIdx.x & 31), warp(threadIdx.x >> 5), counter(counter_),
-          round(n_excl_ > 0 ? 0 : 1), group_wait(false) {}
-    // next index into order[], -1: nothing this round (call again), -2: done
-    __device__ __forceinline__ int next() {
-        if (round == 0) {
-            round = 1;
-            const int g = warp & (kExclusiveWarps - 1);
-            const int i = g * (int)gridDim.x + (int)blockIdx.x;     // the long task of this warp's scheduler, if any
-            group_wait = i < n_excl;
-            return (group_wait && warp == g) ? i : -1;
+// One stripe of a multi-stripe task; the stripe that finishes last writes the record.
+template <int R, class SC>
+__device__ __forceinline__ void exact_stripe(const Task& tk, int tid, int s, const CoopInfo& ci, int4* scratch, int* flags,
+                                             const uint32_t* __restrict__ pool, const SC& sc, int4* prof, int lane, int4* out) {
+    const int S = ci.n_stripes;
+    int* F = flags + ci.flag_off;
+    int4* bnd_a = scratch + ci.data_off;
+    int4* bnd_b = bnd_a + ci.bnd_stride;
+    __syncwarp();
+    build_profile<R>(prof, pool + tk.q_word, tk.q_len, s * 32 * R + lane * R, lane, ModeScore<SC, 1>(sc), false);
+    __syncwarp();
+    Sweep<R, kExact, true> sw;
+    sw.prof = prof; sw.twords = pool + tk.t_word; sw.t_len = tk.t_len; sw.lane = lane;
+    sw.top = s > 0; sw.bot = s + 1 < S;
+    sw.bnd_in = (s & 1) ? bnd_a : bnd_b; sw.bnd_out = (s & 1) ? bnd_b : bnd_a;
+    sw.prog_in = F + s - 1; sw.prog_out = F + s;
+    sw.run(sc, 0);
+    const u64 key = warp_max64(key_of_best(sw.best, sw.best_col()));
+    if (lane == 0) {
+        u64* K = reinterpret_cast<u64*>(F + 2 * S + 2);
+        atomicMax(K, key);
+        __threadfence();
+        if (atomicAdd(F + 2 * S, 1) == S - 1) {
+            __threadfence();
+            out[tid] = finalize_rung(atomicMax(K, 0ull), 0ull, 0, 0, 0, 0);
         }
-        if (round == 1) {
-            round = 2;
-            const int oi = n_excl + warp * (int)gridDim.x + (int)blockIdx.x;
-            return oi < n_order ? oi : -2;
+    }
+}
+
+template <int R, class SC>
+__device__ __forceinline__ void exact_stripe_dispatch(int r, const Task& tk, int tid, int s, const CoopInfo& ci, int4* scratch,
+                                                      int* flags, const uint32_t* __restrict__ pool, const SC& sc, int4* prof,
+                                                      int lane, int4* out) {
+    if (r == R) { exact_stripe<R>(tk, tid, s, ci, scratch, flags, pool, sc, prof, lane, out); return; }
+    if constexpr (R < kMaxRExact) exact_stripe_dispatch<R + 1>(r, tk, tid, s, ci, scratch, flags, pool, sc, prof, lane, out);
+}
+
+// Rows per lane of a long task that the host cut into n_stripes stripes (few long tasks: short stripes, so that more
+// warps work on each; many: tall ones, which cost less per cell).
+__host__ __device__ __forceinline__ int coop_rows(int q_len, int n_stripes) {
+    const int R = (q_len + 32 * n_stripes - 1) / (32 * n_stripes);
+    return R < kMinR ? kMinR : R;
+}
+
+constexpr int kWarpsPerBlock = 16;     // one persistent 512-thread block per SM: 4 warps per scheduler (the host may launch fewer)
+
+// order[] entries: (task << 7) | code.  code 0: the whole (single-stripe) task; 1 + s: stripe s of the first sweep of a
+// multi-stripe task (exact: the only sweep; ladder: backward); 64 + s: stripe s of the ladder's forward sweep.
+// Entries are listed so that whatever an entry waits for comes before it; warps take them in that order (one static
+// round, slot-major, so that a small batch spreads over all SMs; then dynamic pulls from *counter), every block of the
+// grid is resident (host: at most one block per SM), so whatever an entry waits for is running or done.
+constexpr int kCodeBits = 7, kCodeFwd = 64;
+struct TaskCursor {
+    int n_order, lane, warp, wpb;
+    int* counter;
+    bool first;
+    __device__ __forceinline__ TaskCursor(int n_order_, int* counter_)
+        : n_order(n_order_), lane(threadIdx.x & 31), warp(threadIdx.x >> 5), wpb(blockDim.x >> 5), counter(counter_), first(true) {}
+    // next index into order[], -1: done
+    __device__ __forceinline__ int next() {
+        if (first) {
+            first = false;
+            const int oi = warp * (int)gridDim.x + (int)blockIdx.x;
+            return oi < n_order ? oi : -1;
         }
         int oi = 0;
         if (lane == 0) oi = atomicAdd(counter, 1);
-        oi = __shfl_sync(kFull, oi, 0) + n_excl + kWarpsPerBlock * (int)gridDim.x;
-        return oi < n_order ? oi : -2;
-    }
-    // after the task of a round: the warps of a scheduler that hosted a long task meet here
-    __device__ __forceinline__ void done() {
-        if (group_wait) {
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & (kExclusiveWarps - 1))), "r"(32 * kWarpsPerBlock / kExclusiveWarps) : "memory");
-            group_wait = false;
-        }
+        oi = __shfl_sync(kFull, oi, 0) + wpb * (int)gridDim.x;
+        return oi < n_order ? oi : -1;
     }
 };
 
 // Exact (score, tstart, tend) kernel.  Persistent: the stripe height and the single- / multi-stripe path are picked
-// per task (warp-uniform dispatch), so one launch covers a whole batch, long expanded alleles included.
-// out[] is indexed by task id.  smem_stride: int4 of shared memory per warp.  scratch: per warp 2 boundary rows of
-// scratch_stride int4 (only touched by multi-stripe tasks; null when the batch has none).
+// per entry (warp-uniform dispatch), so one launch covers a whole batch, long expanded alleles included.
+// out[] is indexed by task id.  smem_stride: int4 of shared memory per warp.
 template <bool FIXED>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock, 1)
-exact_kernel(const Task* __restrict__ tasks, const int32_t* __restrict__ order, int n_order, int n_excl,
+exact_kernel(const Task* __restrict__ tasks, const int32_t* __restrict__ order, int n_order,
              const uint32_t* __restrict__ pool, ScoreW scw, int* counter, int smem_stride,
-             int4* scratch, long long scratch_stride, int4* out) {
+             int4* scratch, const CoopInfo* __restrict__ coop, const int32_t* __restrict__ coop_idx, int* flags, int4* out) {
     extern __shared__ int4 smem[];
     const ScoreView<FIXED> sc(scw);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     int4* prof = smem + warp * smem_stride;
-    const long long gwarp = (long long)blockIdx.x * kWarpsPerBlock + warp;
-    int4* bnd_a = scratch + gwarp * 2 * scratch_stride;
-    int4* bnd_b = bnd_a + scratch_stride;
-    TaskCursor cur(n_excl, n_order, counter);
+    TaskCursor cur(n_order, counter);
     for (;;) {
         const int oi = cur.next();
-        if (oi == -2) break;
-        if (oi >= 0) {
-            const int tid = order[oi];
-            const Task tk = tasks[tid];
+        if (oi < 0) break;
+        const int e = order[oi];
+        const int tid = e >> kCodeBits, code = e & ((1 << kCodeBits) - 1);
+        const Task tk = tasks[tid];
+        if (code == 0) {
             int R, n_stripes;
             stripe_shape(tk.q_len, kMaxRExact, R, n_stripes);
-            u64 key;
-            if (n_stripes > 1) key = exact_dispatch<kMinRMultiExact, true>(R, tk, pool, sc, prof, lane, n_stripes, bnd_a, bnd_b);
-            else key = exact_dispatch<kMinR, false>(R, tk, pool, sc, prof, lane, n_stripes, bnd_a, bnd_b);
-            key = warp_max64(key);
+            const u64 key = warp_max64(exact_dispatch<kMinR>(R, tk, pool, sc, prof, lane));
             if (lane == 0) out[tid] = finalize_rung(key, 0ull, 0, 0, 0, 0);
+        } else {
+            const CoopInfo ci = coop[coop_idx[tid]];
+            exact_stripe_dispatch<kMinR>(coop_rows(tk.q_len, ci.n_stripes), tk, tid, code - 1, ci, scratch, flags, pool, sc, prof, lane, out);
         }
-        cur.done();
     }
 }
 
 // Round 3 for one read: all rungs kmin..kmax from one backward and one forward sweep (file header).
 //
 // FLAG = false: span words everywhere; every rung gets its exact (score, tstart, tend).
-// FLAG = true ("flag ladder", the production path): what the reference looks at per rung is the score and the two span
+// FLAG = true ("flag ladder"): what the reference looks at per rung is the score and the two span
 // predicates (nanoRepeat_bam.py:423-427), so the words carry just that.  Forward words are (score << 16) - mark, mark =
 // the alignment started inside the left flank (set once, when a lane passes the flank's last column; a later fresh
 // start is unmarked and, being the larger word, wins ties like the larger tstart does).  Backward words are
@@ -708,155 +787,240 @@ exact_kernel(const Task* __restrict__ tasks, const int32_t* __restrict__ order, 
 // mark, whose integer order is the contract's (score, smallest tend, largest tstart); the prefix class needs only its
 // best score, so the forward sweep has no per-step best tracking at all.  Output per rung: (score, spans both flanks,
 // ends in right flank).  Needs 2 * |R| < 65536.
-template <int R, bool MULTI, bool FLAG, class SC>
-__device__ __forceinline__ void ladder_task(const LadderTask& tk, const uint32_t* __restrict__ qpool,
-                                            const uint32_t* __restrict__ pool, const LadderRegion& reg, const SC& sc, int4* prof, int lane,
-                                            int n_stripes, int4* bnd_a, int4* bnd_b, int4* bglob, ulonglong2* tok_a,
-                                            ulonglong2* tok_b, int4* out, int4* sel) {
-    constexpr int BWD = FLAG ? kBwdF : kBwd, FWD = FLAG ? kFwdF : kFwd;
-    int4* bsm = prof + StripeCfg<R>::PROF_INT4;
-    const int rows_per_stripe = 32 * R;
-    const uint32_t* qwords = qpool + tk.q_word;      // reads may live in the round-2 batch's pool
-    const int q_len = tk.q_len;
-    int4* bdst = MULTI ? bglob : bsm;
-    // junction vectors: corner i (1-based) lives at forward cell row idx0 = i - 1.  Defaults: right part empty
-    // (H = 0, no gap state) for corners inside the read, void below it; the backward sweep overwrites idx0 <= q-2.
-    __syncwarp();
-    for (int s = 0; s < n_stripes; ++s)
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int idx0 = s * rows_per_stripe + lane * R + r;
-            bdst[s * rows_per_stripe + r * 32 + lane] =
-                idx0 < q_len ? make_int4(0, kPadScore, kPadScore, 0) : make_int4(kPadScore, kPadScore, kPadScore, 0);
-        }
-    __syncwarp();
-    // ---- backward sweep: reversed read x reversed right flank ----
-    u64 rkey = 0;       // FLAG: the best (score << 16) + 2 * reversed start, biased by 1 so that 0 means none
-    if (reg.n_right > 0) {
-        for (int s = 0; s < n_stripes; ++s) {
-            __syncwarp();
-            build_profile<R>(prof, qwords, q_len, s * rows_per_stripe + lane * R, lane, ModeScore<SC, Sweep<R, BWD, MULTI>::DEC>(sc), true);
-            __syncwarp();
-            Sweep<R, BWD, MULTI> sw;
-            sw.prof = prof; sw.twords = pool + reg.rev_word; sw.t_len = reg.n_right; sw.lane = lane;
-            sw.top = s > 0; sw.bot = s + 1 < n_stripes;
-            sw.bnd_in = (s & 1) ? bnd_a : bnd_b; sw.bnd_out = (s & 1) ? bnd_b : bnd_a;
-            sw.bdst = bdst; sw.q_len = q_len; sw.brow0 = s * rows_per_stripe + lane * R;
-            sw.run(sc, 0);
-            int key, col;
-            sw.bwd_best(key, col);
-            u64 k = 0;
-            if (key >= 65536) {     // a positive score
-                if (FLAG) k = (u64)(unsigned)key;
-                else k = ((u64)((unsigned)key >> 16) << 32) | ((u64)((unsigned)key & 0xffffu) << 16) | (u64)(0xffffu - (unsigned)col);
-            }
-            rkey = k > rkey ? k : rkey;
-        }
-        rkey = warp_max64(rkey);
+//
+// ladder_task: single-stripe read, both sweeps on one warp, junction vectors in shared memory.
+// ladder_bwd_stripe / ladder_fwd_stripe: one stripe of a long read; the stripes of a sweep run on different warps at the
+// same time (CoopInfo), the forward stripes start when the last backward stripe is done.
+struct LadderCtx {
+    const uint32_t* qwords;
+    const uint32_t* pool;
+    LadderRegion reg;
+    int q_len;
+};
+
+template <bool FLAG>
+__device__ __forceinline__ u64 bwd_key(int key, int col) {
+    if (key < 65536) return 0ull;     // no positive score
+    if (FLAG) return (u64)(unsigned)key;
+    return ((u64)((unsigned)key >> 16) << 32) | ((u64)((unsigned)key & 0xffffu) << 16) | (u64)(0xffffu - (unsigned)col);
+}
+
+// R-only class from the backward sweep's best key
+template <bool FLAG>
+__device__ __forceinline__ void r_only(u64 rkey, int n_right, int& r_score, int& r_end, int& r_start, int& rcand) {
+    r_score = 0; r_end = 0; r_start = 0; rcand = kJuncNone;
+    if (!rkey) return;
+    if (FLAG) {
+        rcand = (int)(unsigned)rkey - 2 * n_right;                       // (score << 16) - 2 * (forward end inside R)
+    } else {
+        r_score = (int)(rkey >> 32);
+        r_end = n_right - (int)((rkey >> 16) & 0xffffu);                 // forward end inside R (exclusive)
+        r_start = n_right - (0xffff - (int)(rkey & 0xffffu));            // forward start inside R
     }
-    int r_score = 0, r_end = 0, r_start = 0, rcand = kJuncNone;
-    if (rkey) {
-        if (FLAG) {
-            rcand = (int)(unsigned)rkey - 2 * reg.n_right;                   // (score << 16) - 2 * (forward end inside R)
-        } else {
-            r_score = (int)(rkey >> 32);
-            r_end = reg.n_right - (int)((rkey >> 16) & 0xffffu);             // forward end inside R (exclusive)
-            r_start = reg.n_right - (0xffff - (int)(rkey & 0xffffu));        // forward start inside R
-        }
-    }
-    // ---- forward sweep over L + motif^kmax with junction tokens ----
-    const int c_first = reg.n_left + reg.m * tk.kmin;
-    const int t_len = reg.n_left + reg.m * tk.kmax;
-    int4* outp = out + tk.out_off;
-    int sel_top = 0, sel_n = 0;
-    long long sel_sum = 0;
+}
+
+// junction vector of forward row idx0 when the backward sweep did not write it: right part empty (H = 0, no gap state)
+// for rows of the read, void below it
+__device__ __forceinline__ int4 bvec_default(int idx0, int q_len) {
+    return idx0 < q_len ? make_int4(0, kPadScore, kPadScore, 0) : make_int4(kPadScore, kPadScore, kPadScore, 0);
+}
+
+template <int R, bool MULTI, bool FLAG, class SW, class SC>
+__device__ __forceinline__ void setup_fwd(SW& sw, const LadderTask& tk, const LadderCtx& cx, const SC& sc, int4* prof,
+                                          const int4* bsm, int lane, int4* out, int r_score, int r_end, int r_start, int rcand) {
+    const int c_first = cx.reg.n_left + cx.reg.m * tk.kmin;
+    sw.prof = prof; sw.twords = cx.pool + cx.reg.fwd_word; sw.t_len = cx.reg.n_left + cx.reg.m * tk.kmax; sw.lane = lane;
+    sw.bsm = bsm;
+    sw.out = out + tk.out_off;
+    sw.m = cx.reg.m;
+    sw.jnext = c_first > 0 ? c_first : cx.reg.m;     // a junction at column 0 has no forward part
+    sw.kcnt = c_first > 0 ? 0 : 1;
+    sw.r_score = r_score; sw.r_end = r_end; sw.r_start = r_start;
+    sw.rcand = rcand; sw.mark_col = cx.reg.n_left - 1;
+    sw.k0 = tk.kmin; sw.min_score = sc.min_score;
+    sw.sel_top = 0; sw.sel_n = 0; sw.sel_sum = 0;
     if (FLAG && c_first == 0) {        // rung 0 of a region without a left flank: the R-only class alone
         const int4 rec = finalize_flag_rung(0, kJuncNone, rcand);
-        if (rec.x >= sc.min_score) { sel_top = rec.x; sel_n = rec.y ? 1 : 0; }
+        if (rec.x >= sc.min_score) { sw.sel_top = rec.x; sw.sel_n = rec.y ? 1 : 0; }
     }
-    if (t_len > 0) {
-        for (int s = 0; s < n_stripes; ++s) {
-            __syncwarp();
-            build_profile<R>(prof, qwords, q_len, s * rows_per_stripe + lane * R, lane, ModeScore<SC, Sweep<R, FWD, MULTI>::DEC>(sc), false);
-            if (MULTI) {
+}
+
+// what the warp that holds the last rows writes when the forward sweep is over
+template <bool FLAG, class SW>
+__device__ __forceinline__ void finish_read(const SW& sw, const LadderTask& tk, const LadderCtx& cx, int lane, int4* out, int4* sel,
+                                            int r_score, int r_end, int r_start, int rcand) {
+    if (FLAG) {
+        // rungs are finalised by lane 31; without a sweep every lane holds rung 0's selection
+        if (lane == 31) sel[tk.read] = make_int4(sw.sel_top, sw.sel_n, (int)(unsigned)sw.sel_sum, (int)(sw.sel_sum >> 32));
+    }
+    if (cx.reg.n_left + cx.reg.m * tk.kmin == 0 && lane == 0)
+        out[tk.out_off] = FLAG ? finalize_flag_rung(0, kJuncNone, rcand) : finalize_rung(0ull, 0ull, 0, r_score, r_end, r_start);
+}
+
+template <int R, bool FLAG, class SC>
+__device__ __forceinline__ void ladder_task(const LadderTask& tk, const LadderCtx& cx, const SC& sc, int4* prof, int lane,
+                                            int4* out, int4* sel) {
+    constexpr int BWD = FLAG ? kBwdF : kBwd, FWD = FLAG ? kFwdF : kFwd;
+    int4* bsm = prof + StripeCfg<R>::PROF_INT4;
+    const int q_len = cx.q_len;
+    __syncwarp();
 #pragma unroll
-                for (int r = 0; r < R; ++r) bsm[r * 32 + lane] = __ldcg(&bglob[s * rows_per_stripe + r * 32 + lane]);
-            }
-            __syncwarp();
-            Sweep<R, FWD, MULTI> sw;
-            sw.prof = prof; sw.twords = pool + reg.fwd_word; sw.t_len = t_len; sw.lane = lane;
-            sw.top = s > 0; sw.bot = s + 1 < n_stripes;
-            sw.bnd_in = (s & 1) ? bnd_a : bnd_b; sw.bnd_out = (s & 1) ? bnd_b : bnd_a;
-            sw.bsm = bsm;
-            sw.tok_in = (s & 1) ? tok_a : tok_b; sw.tok_out = (s & 1) ? tok_b : tok_a;
-            sw.out = outp;
-            sw.m = reg.m;
-            sw.jnext = c_first > 0 ? c_first : reg.m;     // a junction at column 0 has no forward part
-            sw.kcnt = c_first > 0 ? 0 : 1;
-            sw.r_score = r_score; sw.r_end = r_end; sw.r_start = r_start;
-            sw.rcand = rcand; sw.mark_col = reg.n_left - 1;
-            sw.k0 = tk.kmin; sw.min_score = sc.min_score;
-            sw.sel_top = sel_top; sw.sel_n = sel_n; sw.sel_sum = sel_sum;
-            sw.run(sc, sw.jnext - 1);
-            sel_top = sw.sel_top; sel_n = sw.sel_n; sel_sum = sw.sel_sum;
+    for (int r = 0; r < R; ++r) bsm[r * 32 + lane] = bvec_default(lane * R + r, q_len);
+    __syncwarp();
+    // ---- backward sweep: reversed read x reversed right flank ----
+    u64 rkey = 0;
+    if (cx.reg.n_right > 0) {
+        build_profile<R>(prof, cx.qwords, q_len, lane * R, lane, ModeScore<SC, Sweep<R, BWD, false>::DEC>(sc), true);
+        __syncwarp();
+        Sweep<R, BWD, false> sw;
+        sw.prof = prof; sw.twords = cx.pool + cx.reg.rev_word; sw.t_len = cx.reg.n_right; sw.lane = lane;
+        sw.top = false; sw.bot = false;
+        sw.bdst = bsm; sw.q_len = q_len; sw.brow0 = lane * R;
+        sw.run(sc, 0);
+        int key, col;
+        sw.bwd_best(key, col);
+        rkey = warp_max64(bwd_key<FLAG>(key, col));
+    }
+    int r_score, r_end, r_start, rcand;
+    r_only<FLAG>(rkey, cx.reg.n_right, r_score, r_end, r_start, rcand);
+    // ---- forward sweep over L + motif^kmax with junction tokens ----
+    Sweep<R, FWD, false> sw;
+    setup_fwd<R, false, FLAG>(sw, tk, cx, sc, prof, bsm, lane, out, r_score, r_end, r_start, rcand);
+    sw.top = false; sw.bot = false;
+    if (sw.t_len > 0) {
+        __syncwarp();
+        build_profile<R>(prof, cx.qwords, q_len, lane * R, lane, ModeScore<SC, Sweep<R, FWD, false>::DEC>(sc), false);
+        __syncwarp();
+        sw.run(sc, sw.jnext - 1);
+    }
+    finish_read<FLAG>(sw, tk, cx, lane, out, sel, r_score, r_end, r_start, rcand);
+}
+
+template <int R, bool FLAG, class SC>
+__device__ __forceinline__ void ladder_bwd_stripe(const LadderTask& tk, const LadderCtx& cx, int s, const CoopInfo& ci,
+                                                  int4* scratch, int* flags, const SC& sc, int4* prof, int lane) {
+    constexpr int BWD = FLAG ? kBwdF : kBwd;
+    const int S = ci.n_stripes;
+    int* F = flags + ci.flag_off;
+    int4* bnd_a = scratch + ci.data_off;
+    int4* bnd_b = bnd_a + ci.bnd_stride;
+    int4* bglob = bnd_b + 3 * ci.bnd_stride;
+    __syncwarp();
+    build_profile<R>(prof, cx.qwords, cx.q_len, s * 32 * R + lane * R, lane, ModeScore<SC, Sweep<R, BWD, true>::DEC>(sc), true);
+    __syncwarp();
+    Sweep<R, BWD, true> sw;
+    sw.prof = prof; sw.twords = cx.pool + cx.reg.rev_word; sw.t_len = cx.reg.n_right; sw.lane = lane;
+    sw.top = s > 0; sw.bot = s + 1 < S;
+    sw.bnd_in = (s & 1) ? bnd_a : bnd_b; sw.bnd_out = (s & 1) ? bnd_b : bnd_a;
+    sw.prog_in = F + s - 1; sw.prog_out = F + s;
+    sw.bdst = bglob; sw.q_len = cx.q_len; sw.brow0 = s * 32 * R + lane * R;
+    sw.run(sc, 0);
+    int key, col;
+    sw.bwd_best(key, col);
+    const u64 rkey = warp_max64(bwd_key<FLAG>(key, col));
+    __syncwarp();                       // every lane's junction vectors are stored
+    if (lane == 0) {
+        atomicMax(reinterpret_cast<u64*>(F + 2 * S + 2), rkey);
+        __threadfence();
+        atomicAdd(F + 2 * S, 1);
+    }
+}
+
+template <int R, bool FLAG, class SC>
+__device__ __forceinline__ void ladder_fwd_stripe(const LadderTask& tk, const LadderCtx& cx, int s, const CoopInfo& ci,
+                                                  int4* scratch, int* flags, const SC& sc, int4* prof, int lane, int4* out,
+                                                  int4* sel) {
+    constexpr int FWD = FLAG ? kFwdF : kFwd;
+    const int S = ci.n_stripes;
+    int* F = flags + ci.flag_off;
+    int4* bnd_a = scratch + ci.data_off + 2 * ci.bnd_stride;
+    int4* bnd_b = bnd_a + ci.bnd_stride;
+    int4* bglob = bnd_b + ci.bnd_stride;
+    ulonglong2* tok_a = reinterpret_cast<ulonglong2*>(bglob + ci.b_stride);
+    ulonglong2* tok_b = tok_a + ci.tok_stride;
+    int4* bsm = prof + StripeCfg<R>::PROF_INT4;
+    Sweep<R, FWD, true> sw;
+    setup_fwd<R, true, FLAG>(sw, tk, cx, sc, prof, bsm, lane, out, 0, 0, 0, kJuncNone);
+    sw.top = s > 0; sw.bot = s + 1 < S;
+    sw.bsm_w = bsm;
+    sw.bglob_rows = cx.reg.n_right > 0 ? bglob + s * 32 * R : nullptr;
+    sw.bdone = F + 2 * S; sw.bdone_need = S; sw.n_right = cx.reg.n_right;
+    sw.q_len = cx.q_len; sw.brow0 = s * 32 * R + lane * R;
+    sw.late_pending = true;
+    __syncwarp();
+    if (sw.t_len == 0 || cx.reg.n_left + cx.reg.m * tk.kmin == 0) {
+        // no sweep, or rung 0 of a region without a left flank (its record is the R-only class alone): needs the
+        // backward sweep's result up front
+        sw.late_load();
+        if (FLAG && cx.reg.n_left + cx.reg.m * tk.kmin == 0) {
+            const int4 rec = finalize_flag_rung(0, kJuncNone, sw.rcand);
+            sw.sel_top = 0; sw.sel_n = 0;
+            if (rec.x >= sc.min_score) { sw.sel_top = rec.x; sw.sel_n = rec.y ? 1 : 0; }
         }
     }
-    if (FLAG) {
-        // rungs are finalised by lane 31 (of the last stripe); without a sweep every lane holds rung 0's selection
-        if (lane == 31) sel[tk.read] = make_int4(sel_top, sel_n, (int)(unsigned)sel_sum, (int)(sel_sum >> 32));
+    if (sw.t_len > 0) {
+        build_profile<R>(prof, cx.qwords, cx.q_len, s * 32 * R + lane * R, lane, ModeScore<SC, Sweep<R, FWD, true>::DEC>(sc), false);
+        __syncwarp();
+        sw.bnd_in = (s & 1) ? bnd_a : bnd_b; sw.bnd_out = (s & 1) ? bnd_b : bnd_a;
+        sw.tok_in = (s & 1) ? tok_a : tok_b; sw.tok_out = (s & 1) ? tok_b : tok_a;
+        sw.prog_in = F + S + s - 1; sw.prog_out = F + S + s;
+        sw.run(sc, sw.jnext - 1);
     }
-    if (c_first == 0 && lane == 0)
-        outp[0] = FLAG ? finalize_flag_rung(0, kJuncNone, rcand) : finalize_rung(0ull, 0ull, 0, r_score, r_end, r_start);
+    if (s == S - 1) finish_read<FLAG>(sw, tk, cx, lane, out, sel, sw.r_score, sw.r_end, sw.r_start, sw.rcand);
 }
 
-template <int R, bool MULTI, bool FLAG, class SC>
-__device__ __forceinline__ void ladder_dispatch(int r, const LadderTask& tk, const uint32_t* __restrict__ qpool,
-                                                const uint32_t* __restrict__ pool, const LadderRegion& reg, const SC& sc, int4* prof, int lane,
-                                                int n_stripes, int4* bnd_a, int4* bnd_b, int4* bglob,
-                                                ulonglong2* tok_a, ulonglong2* tok_b, int4* out, int4* sel) {
-    if (r == R) { ladder_task<R, MULTI, FLAG>(tk, qpool, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out, sel); return; }
-    if constexpr (R < kMaxRLadder)
-        ladder_dispatch<R + 1, MULTI, FLAG>(r, tk, qpool, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out, sel);
+template <int R, bool FLAG, class SC>
+__device__ __forceinline__ void ladder_dispatch(int r, const LadderTask& tk, const LadderCtx& cx, const SC& sc, int4* prof,
+                                                int lane, int4* out, int4* sel) {
+    if (r == R) { ladder_task<R, FLAG>(tk, cx, sc, prof, lane, out, sel); return; }
+    if constexpr (R < kMaxRLadder) ladder_dispatch<R + 1, FLAG>(r, tk, cx, sc, prof, lane, out, sel);
 }
 
-// Round-3 ladder kernel: one warp per read, all rungs kmin..kmax from one backward and one forward sweep.
-// scratch (multi-stripe reads only), per warp: 2 boundary rows of bnd_stride int4, b_stride int4 of backward
-// vectors, 2 token rows of tok_stride ulonglong2.
+template <int R, bool FLAG, class SC>
+__device__ __forceinline__ void ladder_stripe_dispatch(int r, const LadderTask& tk, const LadderCtx& cx, int code, const CoopInfo& ci,
+                                                       int4* scratch, int* flags, const SC& sc, int4* prof, int lane, int4* out,
+                                                       int4* sel) {
+    if (r == R) {
+        if (code < kCodeFwd) ladder_bwd_stripe<R, FLAG>(tk, cx, code - 1, ci, scratch, flags, sc, prof, lane);
+        else ladder_fwd_stripe<R, FLAG>(tk, cx, code - kCodeFwd, ci, scratch, flags, sc, prof, lane, out, sel);
+        return;
+    }
+    if constexpr (R < kMaxRLadder) ladder_stripe_dispatch<R + 1, FLAG>(r, tk, cx, code, ci, scratch, flags, sc, prof, lane, out, sel);
+}
+
+// Round-3 ladder kernel: one warp per read (single stripe) or per stripe of a long read.
 template <bool FIXED, bool FLAG>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock, 1)
-ladder_kernel(const LadderTask* __restrict__ tasks, const int32_t* __restrict__ order, int n_order, int n_excl,
+ladder_kernel(const LadderTask* __restrict__ tasks, const int32_t* __restrict__ order, int n_order,
               const int* __restrict__ n_order_dev,      // non-null: order[] was filled on the device (redo list), its length is here
               const uint32_t* __restrict__ qpool, const uint32_t* __restrict__ pool, const LadderRegion* __restrict__ regs, ScoreW scw, int* counter,
-              int smem_stride,
-              int4* scratch, long long bnd_stride, long long b_stride, long long tok_stride, int4* out, int4* sel) {
+              int smem_stride, int4* scratch, const CoopInfo* __restrict__ coop, int* flags, int4* out, int4* sel) {
     extern __shared__ int4 smem[];
     const ScoreView<FIXED> sc(scw);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     int4* prof = smem + warp * smem_stride;
-    const long long gwarp = (long long)blockIdx.x * kWarpsPerBlock + warp;
-    const long long per_warp = 2 * bnd_stride + b_stride + 2 * tok_stride;
-    int4* bnd_a = scratch + gwarp * per_warp;
-    int4* bnd_b = bnd_a + bnd_stride;
-    int4* bglob = bnd_b + bnd_stride;
-    ulonglong2* tok_a = reinterpret_cast<ulonglong2*>(bglob + b_stride);
-    ulonglong2* tok_b = tok_a + tok_stride;
     if (n_order_dev) n_order = *n_order_dev;
-    TaskCursor cur(n_excl, n_order, counter);
+    TaskCursor cur(n_order, counter);
     for (;;) {
         const int oi = cur.next();
-        if (oi == -2) break;
-        if (oi >= 0) {
-            const LadderTask tk = tasks[order[oi]];
-            const LadderRegion reg = regs[tk.region];
+        if (oi < 0) break;
+        const int e = order[oi];
+        const int tid = e >> kCodeBits, code = e & ((1 << kCodeBits) - 1);
+        const LadderTask tk = tasks[tid];
+        LadderCtx cx;
+        cx.qwords = qpool + tk.q_word;      // reads may live in the round-2 batch's pool
+        cx.pool = pool;
+        cx.reg = regs[tk.region];
+        cx.q_len = tk.q_len;
+        if (code == 0) {
             int R, n_stripes;
             stripe_shape(tk.q_len, kMaxRLadder, R, n_stripes);
-            if (n_stripes > 1)
-                ladder_dispatch<kMinRMultiLadder, true, FLAG>(R, tk, qpool, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out, sel);
-            else
-                ladder_dispatch<kMinR, false, FLAG>(R, tk, qpool, pool, reg, sc, prof, lane, n_stripes, bnd_a, bnd_b, bglob, tok_a, tok_b, out, sel);
+            ladder_dispatch<kMinR, FLAG>(R, tk, cx, sc, prof, lane, out, sel);
+        } else {
+            const CoopInfo ci = coop[tk.pad];
+            ladder_stripe_dispatch<kMinR, FLAG>(coop_rows(tk.q_len, ci.n_stripes), tk, cx, code, ci, scratch, flags, sc, prof, lane, out, sel);
         }
-        cur.done();
     }
 }
 

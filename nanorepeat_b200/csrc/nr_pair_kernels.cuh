@@ -504,7 +504,7 @@ __device__ __forceinline__ void pair3_task(const Pair3& pt, const LadderTask* __
         unsure = __any_sync(kFull, unsure);
         if (lane == 0) {
             sel[tk.read] = make_int4(top, n, sum, 0);
-            if (unsure) redo[atomicAdd(redo_count, 1)] = tid;
+            if (unsure) redo[atomicAdd(redo_count, 1)] = tid << kCodeBits;     // an entry of ladder_kernel's order[]
         }
     }
 }
