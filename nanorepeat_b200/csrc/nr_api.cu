@@ -78,6 +78,7 @@ std::mutex g_ctx_mu;
 // 3: paired flag ladder (two reads per warp, u16x2 words), 2: flag ladder, 1: shared sweeps with full records,
 // 0: every rung its own rectangle
 std::atomic<int> g_ladder_mode{3};
+std::atomic<int> g_epoch{0};         // runs of the 32-bit kernels, process-wide: tags the boundary entries of the long tasks
 std::atomic<int> g_timing{0};        // nr_set_timing: CUDA events around every kernel of nr_batch_run
 
 int ensure_init(int device) {
@@ -624,6 +625,7 @@ int prepare_kernel(const void* fn, size_t max_bytes) {
 int launch_rest(nr_batch* b, cudaStream_t st, const nr::ScoreW& k, const int32_t* order, int count, int blocks, int wpb,
                 int R, const int* count_dev, int* counter) {
     const Launch& L = b->launch;
+    const int epoch = (g_epoch.fetch_add(1) & 0x1ffffff) + 1;
     if (L.ladder) {
         auto fn = b->flag ? (L.fixed ? nr::ladder_kernel<true, true> : nr::ladder_kernel<false, true>)
                           : (L.fixed ? nr::ladder_kernel<true, false> : nr::ladder_kernel<false, false>);
@@ -633,7 +635,7 @@ int launch_rest(nr_batch* b, cudaStream_t st, const nr::ScoreW& k, const int32_t
         if (rc) return rc;
         fn<<<blocks, wpb * 32, smem, st>>>(b->d_ltasks, order, count, count_dev,
                                           b->qsrc ? b->qsrc->d_pool : b->d_pool, b->d_pool, b->d_lregs, k,
-                                          counter, stride, b->d_scratch, b->d_coop, b->d_flags, b->d_out, b->d_sel);
+                                          counter, stride, b->d_scratch, b->d_coop, b->d_flags, epoch, b->d_out, b->d_sel);
     } else {
         auto fn = L.fixed ? nr::exact_kernel<true> : nr::exact_kernel<false>;
         const int stride = exact_smem_int4(R);
@@ -641,7 +643,7 @@ int launch_rest(nr_batch* b, cudaStream_t st, const nr::ScoreW& k, const int32_t
         int rc = prepare_kernel((const void*)fn, kWarpsPerBlock * exact_smem_int4(nr::kMaxRExact) * sizeof(int4));
         if (rc) return rc;
         fn<<<blocks, wpb * 32, smem, st>>>(b->d_tasks, order, count, b->d_pool, k,
-                                          counter, stride, b->d_scratch, b->d_coop, b->d_coop_idx, b->d_flags, b->d_out);
+                                          counter, stride, b->d_scratch, b->d_coop, b->d_coop_idx, b->d_flags, epoch, b->d_out);
     }
     CUDA_TRY(cudaGetLastError());
     return NR_OK;

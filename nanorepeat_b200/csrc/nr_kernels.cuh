@@ -145,10 +145,18 @@ __device__ __forceinline__ u64 key_of_junction(int khi, int klo) {
 }
 
 // Stripes of one long task run on different warps (any SM) at the same time, each a few dozen columns behind the one
-// above it: the producer's last lane stores its bottom row (and junction tokens) with .cg stores and then releases the
-// number of finished columns; the consumer acquires it before it prefetches the next 32 columns.
-__device__ __forceinline__ void publish_cols(int* flag, int cols) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(cols) : "memory");
+// above it.  No flags and no fences on the column path: a boundary entry is ONE 16-byte store (H, F1, F2, tag) and one
+// 16-byte load, tag = (run epoch, stripe), so an entry that is not there yet (or is left over from the stripe that used
+// the row before, or from an earlier run) is recognised by its tag and simply read again.
+__device__ __forceinline__ int4 load_bnd(const int4* p) {
+    int4 v;
+    asm volatile("ld.volatile.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ ulonglong2 load_tok(const ulonglong2* p) {
+    ulonglong2 v;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ int peek_cols(const int* flag) {
     int v;
@@ -285,8 +293,7 @@ struct Sweep {
     bool top, bot;
     const int4* bnd_in;
     int4* bnd_out;
-    const int* prog_in;            // MULTI: columns the stripe above has finished (its boundary row / tokens are in L2)
-    int* prog_out;                 //        columns this stripe has finished
+    int tag_in, tag_out;           // MULTI: what marks an entry written by the stripe above / by this stripe in this run
     // backward sweeps
     int4* bdst;
     int q_len, brow0;
@@ -337,10 +344,7 @@ struct Sweep {
         twl = 0;
         prof_lane = reinterpret_cast<const char*>(prof + lane);
         bcur = make_int4(0, 0, 0, 0); bnxt = make_int4(0, 0, 0, 0);
-        if (MULTI && top) {
-            wait_cols(prog_in, min(32, t_len), lane);
-            bnxt = __ldcg(&bnd_in[lane < t_len ? lane : t_len - 1]);
-        }
+        if (MULTI && top) bnxt = load_bnd(&bnd_in[lane < t_len ? lane : t_len - 1]);   // checked when it is taken over
         tokP = 0; tokJ = 0;
     }
 
@@ -443,9 +447,13 @@ struct Sweep {
         if (MULTI && top) {                 // uniform branch
             if ((st & 31) == 0) {
                 bcur = bnxt;
-                wait_cols(prog_in, min(st + 64, t_len), lane);
+                const int cj = st + lane;       // the column this lane's entry stands for
+                while (!__all_sync(kFull, bcur.w == tag_in || cj >= t_len)) {
+                    __nanosleep(64);
+                    bcur = load_bnd(&bnd_in[cj < t_len ? cj : t_len - 1]);
+                }
                 const int nj = st + 32 + lane;
-                bnxt = __ldcg(&bnd_in[nj < t_len ? nj : t_len - 1]);
+                bnxt = load_bnd(&bnd_in[nj < t_len ? nj : t_len - 1]);      // in flight for the next 32 steps
             }
             const int bh = __shfl_sync(kFull, bcur.x, st & 31);
             const int bf1 = __shfl_sync(kFull, bcur.y, st & 31);
@@ -510,8 +518,11 @@ struct Sweep {
             if (junc) {
                 if (MODE == kFwdF) {
                     if (lane == 0) {
-                        if (MULTI && top) { const ulonglong2 t = __ldcg(&tok_in[kcnt]); tP = t.x; tJ = t.y; }
-                        else { tP = 0; tJ = (unsigned)kJuncNone; }
+                        if (MULTI && top) {     // the token carries its tag in the upper half of x
+                            ulonglong2 t = load_tok(&tok_in[kcnt]);
+                            while ((int)(t.x >> 32) != tag_in) { __nanosleep(64); t = load_tok(&tok_in[kcnt]); }
+                            tP = (unsigned)t.x; tJ = t.y;
+                        } else { tP = 0; tJ = (unsigned)kJuncNone; }
                     }
                     // rung 0's junction column is the left flank's last column: every forward part that scores has
                     // started inside the flank but is marked only after this step (the candidates with an empty
@@ -519,7 +530,7 @@ struct Sweep {
                     const int myP = max((int)tP, best), myJ = max((int)tJ, jj == mark_col ? jhi - 1 : jhi);
                     tokP = (unsigned)myP; tokJ = (unsigned)myJ;
                     if (lane == 31) {
-                        if (MULTI && bot) __stcg(&tok_out[kcnt], make_ulonglong2(tokP, tokJ));
+                        if (MULTI && bot) __stcg(&tok_out[kcnt], make_ulonglong2(tokP | ((u64)(unsigned)tag_out << 32), tokJ));
                         else {
                             const int4 rec = finalize_flag_rung(myP, myJ, rcand);
                             out[kcnt] = rec;
@@ -529,24 +540,22 @@ struct Sweep {
                 } else {
                     junction_unbias(jhi, jlo);
                     if (lane == 0) {
-                        if (MULTI && top) { const ulonglong2 t = __ldcg(&tok_in[kcnt]); tP = t.x; tJ = t.y; }
+                        // (its store was fenced before the boundary entry of this column, which this stripe has seen)
+                        if (MULTI && top) { const ulonglong2 t = load_tok(&tok_in[kcnt]); tP = t.x; tJ = t.y; }
                         else { tP = 0; tJ = 0; }
                     }
                     const u64 myP = key_of_best(best, best_col()), myJ = key_of_junction(jhi, jlo);
                     tokP = myP > tP ? myP : tP;
                     tokJ = myJ > tJ ? myJ : tJ;
                     if (lane == 31) {
-                        if (MULTI && bot) __stcg(&tok_out[kcnt], make_ulonglong2(tokP, tokJ));
+                        if (MULTI && bot) { __stcg(&tok_out[kcnt], make_ulonglong2(tokP, tokJ)); __threadfence(); }
                         else out[kcnt] = finalize_rung(tokP, tokJ, jj + 1, r_score, r_end, r_start);
                     }
                 }
                 jnext += m;
                 ++kcnt;
             }
-            if (MULTI && bot && lane == 31) {
-                __stcg(&bnd_out[jj], make_int4(h_out, f1_out, f2_out, 0));
-                if ((jj & 31) == 31 || jj == t_len - 1) publish_cols(prog_out, jj + 1);
-            }
+            if (MULTI && bot && lane == 31) __stcg(&bnd_out[jj], make_int4(h_out, f1_out, f2_out, tag_out));
         }
     }
 
@@ -640,8 +649,7 @@ __host__ __device__ __forceinline__ void stripe_shape(int q_len, int max_r, int&
 }
 
 // Scratch of one multi-stripe task.  flags (ints, zeroed before every run) at flag_off (even):
-//   [0, S) columns finished by stripe s of the first sweep (exact: the only sweep; ladder: backward)
-//   [S, 2S) the same for the ladder's forward sweep        [2S] stripes of the first sweep that are done
+//   [0, 2S) unused        [2S] stripes of the first sweep (exact: the only sweep; ladder: backward) that are done
 //   [2S + 2, 2S + 4) 64-bit key: exact: the task's best; ladder: the R-only optimum of the backward sweep
 struct CoopInfo {
     long long data_off;     // int4 index into scratch: [boundary rows a, b of the first sweep | (ladder) boundary rows a, b of the
@@ -651,6 +659,8 @@ struct CoopInfo {
     int n_stripes, pad;
 };
 constexpr int kCoopFlagInts(int S) { return 2 * S + 4; }
+// tag of the entries stripe s writes in the run with this epoch (the host counts runs; never 0)
+__device__ __forceinline__ int stripe_tag(int epoch, int s) { return (epoch << 6) | (s & 63); }
 
 template <int R, class SC>
 __device__ __forceinline__ u64 exact_task(const Task& tk, const uint32_t* __restrict__ pool, const SC& sc, int4* prof, int lane) {
@@ -674,7 +684,7 @@ __device__ __forceinline__ u64 exact_dispatch(int r, const Task& tk, const uint3
 
 // One stripe of a multi-stripe task; the stripe that finishes last writes the record.
 template <int R, class SC>
-__device__ __forceinline__ void exact_stripe(const Task& tk, int tid, int s, const CoopInfo& ci, int4* scratch, int* flags,
+__device__ __forceinline__ void exact_stripe(const Task& tk, int tid, int s, const CoopInfo& ci, int epoch, int4* scratch, int* flags,
                                              const uint32_t* __restrict__ pool, const SC& sc, int4* prof, int lane, int4* out) {
     const int S = ci.n_stripes;
     int* F = flags + ci.flag_off;
@@ -687,7 +697,7 @@ __device__ __forceinline__ void exact_stripe(const Task& tk, int tid, int s, con
     sw.prof = prof; sw.twords = pool + tk.t_word; sw.t_len = tk.t_len; sw.lane = lane;
     sw.top = s > 0; sw.bot = s + 1 < S;
     sw.bnd_in = (s & 1) ? bnd_a : bnd_b; sw.bnd_out = (s & 1) ? bnd_b : bnd_a;
-    sw.prog_in = F + s - 1; sw.prog_out = F + s;
+    sw.tag_in = stripe_tag(epoch, s - 1); sw.tag_out = stripe_tag(epoch, s);
     sw.run(sc, 0);
     const u64 key = warp_max64(key_of_best(sw.best, sw.best_col()));
     if (lane == 0) {
@@ -702,11 +712,11 @@ __device__ __forceinline__ void exact_stripe(const Task& tk, int tid, int s, con
 }
 
 template <int R, class SC>
-__device__ __forceinline__ void exact_stripe_dispatch(int r, const Task& tk, int tid, int s, const CoopInfo& ci, int4* scratch,
+__device__ __forceinline__ void exact_stripe_dispatch(int r, const Task& tk, int tid, int s, const CoopInfo& ci, int epoch, int4* scratch,
                                                       int* flags, const uint32_t* __restrict__ pool, const SC& sc, int4* prof,
                                                       int lane, int4* out) {
-    if (r == R) { exact_stripe<R>(tk, tid, s, ci, scratch, flags, pool, sc, prof, lane, out); return; }
-    if constexpr (R < kMaxRExact) exact_stripe_dispatch<R + 1>(r, tk, tid, s, ci, scratch, flags, pool, sc, prof, lane, out);
+    if (r == R) { exact_stripe<R>(tk, tid, s, ci, epoch, scratch, flags, pool, sc, prof, lane, out); return; }
+    if constexpr (R < kMaxRExact) exact_stripe_dispatch<R + 1>(r, tk, tid, s, ci, epoch, scratch, flags, pool, sc, prof, lane, out);
 }
 
 // Rows per lane of a long task that the host cut into n_stripes stripes (few long tasks: short stripes, so that more
@@ -751,7 +761,7 @@ template <bool FIXED>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock, 1)
 exact_kernel(const Task* __restrict__ tasks, const int32_t* __restrict__ order, int n_order,
              const uint32_t* __restrict__ pool, ScoreW scw, int* counter, int smem_stride,
-             int4* scratch, const CoopInfo* __restrict__ coop, const int32_t* __restrict__ coop_idx, int* flags, int4* out) {
+             int4* scratch, const CoopInfo* __restrict__ coop, const int32_t* __restrict__ coop_idx, int* flags, int epoch, int4* out) {
     extern __shared__ int4 smem[];
     const ScoreView<FIXED> sc(scw);
     const int lane = threadIdx.x & 31;
@@ -771,7 +781,7 @@ exact_kernel(const Task* __restrict__ tasks, const int32_t* __restrict__ order, 
             if (lane == 0) out[tid] = finalize_rung(key, 0ull, 0, 0, 0, 0);
         } else {
             const CoopInfo ci = coop[coop_idx[tid]];
-            exact_stripe_dispatch<kMinR>(coop_rows(tk.q_len, ci.n_stripes), tk, tid, code - 1, ci, scratch, flags, pool, sc, prof, lane, out);
+            exact_stripe_dispatch<kMinR>(coop_rows(tk.q_len, ci.n_stripes), tk, tid, code - 1, ci, epoch, scratch, flags, pool, sc, prof, lane, out);
         }
     }
 }
@@ -897,7 +907,7 @@ __device__ __forceinline__ void ladder_task(const LadderTask& tk, const LadderCt
 }
 
 template <int R, bool FLAG, class SC>
-__device__ __forceinline__ void ladder_bwd_stripe(const LadderTask& tk, const LadderCtx& cx, int s, const CoopInfo& ci,
+__device__ __forceinline__ void ladder_bwd_stripe(const LadderTask& tk, const LadderCtx& cx, int s, const CoopInfo& ci, int epoch,
                                                   int4* scratch, int* flags, const SC& sc, int4* prof, int lane) {
     constexpr int BWD = FLAG ? kBwdF : kBwd;
     const int S = ci.n_stripes;
@@ -912,7 +922,7 @@ __device__ __forceinline__ void ladder_bwd_stripe(const LadderTask& tk, const La
     sw.prof = prof; sw.twords = cx.pool + cx.reg.rev_word; sw.t_len = cx.reg.n_right; sw.lane = lane;
     sw.top = s > 0; sw.bot = s + 1 < S;
     sw.bnd_in = (s & 1) ? bnd_a : bnd_b; sw.bnd_out = (s & 1) ? bnd_b : bnd_a;
-    sw.prog_in = F + s - 1; sw.prog_out = F + s;
+    sw.tag_in = stripe_tag(epoch, s - 1); sw.tag_out = stripe_tag(epoch, s);
     sw.bdst = bglob; sw.q_len = cx.q_len; sw.brow0 = s * 32 * R + lane * R;
     sw.run(sc, 0);
     int key, col;
@@ -927,7 +937,7 @@ __device__ __forceinline__ void ladder_bwd_stripe(const LadderTask& tk, const La
 }
 
 template <int R, bool FLAG, class SC>
-__device__ __forceinline__ void ladder_fwd_stripe(const LadderTask& tk, const LadderCtx& cx, int s, const CoopInfo& ci,
+__device__ __forceinline__ void ladder_fwd_stripe(const LadderTask& tk, const LadderCtx& cx, int s, const CoopInfo& ci, int epoch,
                                                   int4* scratch, int* flags, const SC& sc, int4* prof, int lane, int4* out,
                                                   int4* sel) {
     constexpr int FWD = FLAG ? kFwdF : kFwd;
@@ -963,7 +973,7 @@ __device__ __forceinline__ void ladder_fwd_stripe(const LadderTask& tk, const La
         __syncwarp();
         sw.bnd_in = (s & 1) ? bnd_a : bnd_b; sw.bnd_out = (s & 1) ? bnd_b : bnd_a;
         sw.tok_in = (s & 1) ? tok_a : tok_b; sw.tok_out = (s & 1) ? tok_b : tok_a;
-        sw.prog_in = F + S + s - 1; sw.prog_out = F + S + s;
+        sw.tag_in = stripe_tag(epoch, s - 1); sw.tag_out = stripe_tag(epoch, s);
         sw.run(sc, sw.jnext - 1);
     }
     if (s == S - 1) finish_read<FLAG>(sw, tk, cx, lane, out, sel, sw.r_score, sw.r_end, sw.r_start, sw.rcand);
@@ -977,15 +987,15 @@ __device__ __forceinline__ void ladder_dispatch(int r, const LadderTask& tk, con
 }
 
 template <int R, bool FLAG, class SC>
-__device__ __forceinline__ void ladder_stripe_dispatch(int r, const LadderTask& tk, const LadderCtx& cx, int code, const CoopInfo& ci,
+__device__ __forceinline__ void ladder_stripe_dispatch(int r, const LadderTask& tk, const LadderCtx& cx, int code, const CoopInfo& ci, int epoch,
                                                        int4* scratch, int* flags, const SC& sc, int4* prof, int lane, int4* out,
                                                        int4* sel) {
     if (r == R) {
-        if (code < kCodeFwd) ladder_bwd_stripe<R, FLAG>(tk, cx, code - 1, ci, scratch, flags, sc, prof, lane);
-        else ladder_fwd_stripe<R, FLAG>(tk, cx, code - kCodeFwd, ci, scratch, flags, sc, prof, lane, out, sel);
+        if (code < kCodeFwd) ladder_bwd_stripe<R, FLAG>(tk, cx, code - 1, ci, epoch, scratch, flags, sc, prof, lane);
+        else ladder_fwd_stripe<R, FLAG>(tk, cx, code - kCodeFwd, ci, epoch, scratch, flags, sc, prof, lane, out, sel);
         return;
     }
-    if constexpr (R < kMaxRLadder) ladder_stripe_dispatch<R + 1, FLAG>(r, tk, cx, code, ci, scratch, flags, sc, prof, lane, out, sel);
+    if constexpr (R < kMaxRLadder) ladder_stripe_dispatch<R + 1, FLAG>(r, tk, cx, code, ci, epoch, scratch, flags, sc, prof, lane, out, sel);
 }
 
 // Round-3 ladder kernel: one warp per read (single stripe) or per stripe of a long read.
@@ -994,7 +1004,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock, 1)
 ladder_kernel(const LadderTask* __restrict__ tasks, const int32_t* __restrict__ order, int n_order,
               const int* __restrict__ n_order_dev,      // non-null: order[] was filled on the device (redo list), its length is here
               const uint32_t* __restrict__ qpool, const uint32_t* __restrict__ pool, const LadderRegion* __restrict__ regs, ScoreW scw, int* counter,
-              int smem_stride, int4* scratch, const CoopInfo* __restrict__ coop, int* flags, int4* out, int4* sel) {
+              int smem_stride, int4* scratch, const CoopInfo* __restrict__ coop, int* flags, int epoch, int4* out, int4* sel) {
     extern __shared__ int4 smem[];
     const ScoreView<FIXED> sc(scw);
     const int lane = threadIdx.x & 31;
@@ -1019,7 +1029,7 @@ ladder_kernel(const LadderTask* __restrict__ tasks, const int32_t* __restrict__ 
             ladder_dispatch<kMinR, FLAG>(R, tk, cx, sc, prof, lane, out, sel);
         } else {
             const CoopInfo ci = coop[tk.pad];
-            ladder_stripe_dispatch<kMinR, FLAG>(coop_rows(tk.q_len, ci.n_stripes), tk, cx, code, ci, scratch, flags, sc, prof, lane, out, sel);
+            ladder_stripe_dispatch<kMinR, FLAG>(coop_rows(tk.q_len, ci.n_stripes), tk, cx, code, ci, epoch, scratch, flags, sc, prof, lane, out, sel);
         }
     }
 }
