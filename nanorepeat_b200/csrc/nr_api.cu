@@ -70,7 +70,6 @@ struct Context {
     int sm_count = 0;
     int clock_khz = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t side = nullptr;      // the few tasks the paired kernels do not take run here, beside the paired launch
     BufCache cache;
 };
 Context g_ctx;
@@ -102,11 +101,6 @@ int ensure_init(int device) {
         return fail(NR_ERR_CUDA, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 part", device, prop.name,
                     prop.major, prop.minor);
     CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
-    {
-        int lo = 0, hi = 0;
-        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CUDA_TRY(cudaStreamCreateWithPriority(&g_ctx.side, cudaStreamNonBlocking, hi));   // its blocks are placed first
-    }
     g_ctx.device = device;
     g_ctx.sm_count = prop.multiProcessorCount;
     g_ctx.clock_khz = prop.clockRate;
@@ -217,10 +211,8 @@ struct Launch {      // one persistent launch per batch
     bool ladder;     // ladder_kernel over nr_batch::ltasks instead of exact_kernel over nr_batch::tasks
     int R;           // tallest stripe of the launch: sizes the shared memory per warp
     int count;
-    int wpb;         // warps per block of the 32-bit launch: 16, or 4 when it runs beside the paired launch (both resident)
     int blocks;
     bool fixed;      // scoring == map-ont: kernels with immediate constants
-    int pair_wpb;    // warps per block of the paired launch
     // paired launch (nr_pair_kernels.cuh): two reads of one region per warp
     int n_pairs;
     int pair_R;
@@ -471,7 +463,7 @@ int plan_batch(nr_batch* b) {
     if (!multis.empty()) {
         // stripe height of the long tasks: the shortest that does not cut them into more stripes than there are warps
         // to run them side by side (a stripe is one warp's work; the ladder's two sweeps overlap)
-        const long long warps = (long long)(L.n_pairs ? 4 : kWarpsPerBlock) * g_ctx.sm_count;
+        const long long warps = (long long)kWarpsPerBlock * g_ctx.sm_count;
         int cap = max_r;
         const char* force = getenv("NR_COOP_ROWS");       // tuning / debugging: fixed stripe height of the long tasks
         if (force && atoi(force) >= nr::kMinR && atoi(force) <= max_r) cap = atoi(force);
@@ -536,10 +528,6 @@ int plan_batch(nr_batch* b) {
     L.ladder = ladder;
     L.R = rmax;
     L.count = n_rest;
-    // both launches resident on every SM at the same time: 16 warps x 128 registers between them, the larger share of
-    // the work gets 12
-    L.wpb = !L.n_pairs ? kWarpsPerBlock : (b->rest_cells > b->paired_cells ? kWarpsPerBlock - 4 : 4);
-    L.pair_wpb = n_rest ? kWarpsPerBlock - L.wpb : kWarpsPerBlock;
     // one persistent block per SM (every block resident: entries may wait for each other); a small batch still spreads
     L.blocks = std::max(1, std::min(g_ctx.sm_count, n_rest));
     L.fixed = fixed;
@@ -621,29 +609,34 @@ int prepare_kernel(const void* fn, size_t max_bytes) {
     return NR_OK;
 }
 
+nr::RestArgs rest_args(const nr_batch* b, const int32_t* order, int count) {
+    nr::RestArgs ra;
+    ra.order = order; ra.n_order = count;
+    ra.scratch = b->d_scratch; ra.coop = b->d_coop; ra.coop_idx = b->d_coop_idx; ra.flags = b->d_flags;
+    ra.epoch = (g_epoch.fetch_add(1) & 0x1ffffff) + 1;
+    return ra;
+}
+
 // launch of the 32-bit kernels over order[0, count) (count_dev != NULL: the count is read on the device)
-int launch_rest(nr_batch* b, cudaStream_t st, const nr::ScoreW& k, const int32_t* order, int count, int blocks, int wpb,
+int launch_rest(nr_batch* b, cudaStream_t st, const nr::ScoreW& k, const int32_t* order, int count, int blocks,
                 int R, const int* count_dev, int* counter) {
     const Launch& L = b->launch;
-    const int epoch = (g_epoch.fetch_add(1) & 0x1ffffff) + 1;
+    const nr::RestArgs ra = rest_args(b, order, count);
+    int rc;
     if (L.ladder) {
         auto fn = b->flag ? (L.fixed ? nr::ladder_kernel<true, true> : nr::ladder_kernel<false, true>)
                           : (L.fixed ? nr::ladder_kernel<true, false> : nr::ladder_kernel<false, false>);
         const int stride = ladder_smem_int4(R);
-        const size_t smem = (size_t)wpb * stride * sizeof(int4);
-        int rc = prepare_kernel((const void*)fn, kWarpsPerBlock * ladder_smem_int4(nr::kMaxRLadder) * sizeof(int4));
-        if (rc) return rc;
-        fn<<<blocks, wpb * 32, smem, st>>>(b->d_ltasks, order, count, count_dev,
-                                          b->qsrc ? b->qsrc->d_pool : b->d_pool, b->d_pool, b->d_lregs, k,
-                                          counter, stride, b->d_scratch, b->d_coop, b->d_flags, epoch, b->d_out, b->d_sel);
+        const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
+        if ((rc = prepare_kernel((const void*)fn, smem))) return rc;
+        fn<<<blocks, kWarpsPerBlock * 32, smem, st>>>(b->d_ltasks, ra, count_dev, b->qsrc ? b->qsrc->d_pool : b->d_pool, b->d_pool,
+                                                     b->d_lregs, k, counter, stride, b->d_out, b->d_sel);
     } else {
         auto fn = L.fixed ? nr::exact_kernel<true> : nr::exact_kernel<false>;
         const int stride = exact_smem_int4(R);
-        const size_t smem = (size_t)wpb * stride * sizeof(int4);
-        int rc = prepare_kernel((const void*)fn, kWarpsPerBlock * exact_smem_int4(nr::kMaxRExact) * sizeof(int4));
-        if (rc) return rc;
-        fn<<<blocks, wpb * 32, smem, st>>>(b->d_tasks, order, count, b->d_pool, k,
-                                          counter, stride, b->d_scratch, b->d_coop, b->d_coop_idx, b->d_flags, epoch, b->d_out);
+        const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
+        if ((rc = prepare_kernel((const void*)fn, smem))) return rc;
+        fn<<<blocks, kWarpsPerBlock * 32, smem, st>>>(b->d_tasks, ra, b->d_pool, k, counter, stride, b->d_out);
     }
     CUDA_TRY(cudaGetLastError());
     return NR_OK;
@@ -658,7 +651,7 @@ int run_batch(nr_batch* b, cudaStream_t st) {
         CUDA_TRY(cudaStreamWaitEvent(st, b->ev_uploaded, 0));
         if (b->qsrc) CUDA_TRY(cudaStreamWaitEvent(st, b->qsrc->ev_uploaded, 0));
     }
-    // counters: [0] 32-bit kernels, [1] paired kernel, [2] length of the redo list, [3] redo launch
+    // counters: [0] main launch, [2] length of the redo list, [3] redo launch
     CUDA_TRY(cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(int), st));
     if (b->flags_bytes) CUDA_TRY(cudaMemsetAsync(b->d_flags, 0, b->flags_bytes, st));
     int launches = 0;
@@ -670,45 +663,34 @@ int run_batch(nr_batch* b, cudaStream_t st) {
     b->timed[0] = b->timed[1] = b->timed[2] = false;
     auto mark = [&](int i, cudaStream_t s) { return timing ? cudaEventRecord(b->ev_t[i], s) : cudaSuccess; };
     if (L.n_pairs) {
-        // the tasks the paired kernels do not take (long reads, odd scoring ranges) run beside them on a second stream
-        cudaStream_t rest_st = st;
-        if (L.count) {
-            rest_st = g_ctx.side;
-            CUDA_TRY(cudaEventRecord(b->ev_fork, st));
-            CUDA_TRY(cudaStreamWaitEvent(rest_st, b->ev_fork, 0));
-            CUDA_TRY(mark(0, rest_st));
-            if ((rc = launch_rest(b, rest_st, k, b->d_order, L.count, L.blocks, L.wpb, L.R, nullptr, b->d_counters))) return rc;
-            CUDA_TRY(mark(1, rest_st));
-            b->timed[0] = timing;
-            CUDA_TRY(cudaEventRecord(b->ev_join, rest_st));
-            ++launches;
-        }
+        // one persistent launch: the batch's 32-bit entries (long reads cut into stripes, ...) first, then its pairs
+        const nr::RestArgs ra = rest_args(b, b->d_order, L.count);
+        const int blocks = std::max(1, std::min(g_ctx.sm_count, L.count + L.n_pairs));
+        nr::pr::Deal deal = nr::pr::make_deal(L.count, L.n_pairs, kWarpsPerBlock, blocks);
+        if (getenv("NR_PLAIN_DEAL")) deal.nb_long = -1;      // tuning / debugging
         CUDA_TRY(mark(2, st));
         if (!b->pairs2.empty()) {
-            const int stride = exact_smem_int4(L.pair_R);
-            const size_t smem = (size_t)L.pair_wpb * stride * sizeof(int4);
-            if ((rc = prepare_kernel((const void*)nr::pr::pair_round2_kernel, kWarpsPerBlock * exact_smem_int4(nr::pr::kMaxRPair2) * sizeof(int4)))) return rc;
-            nr::pr::pair_round2_kernel<<<L.pair_blocks, L.pair_wpb * 32, smem, st>>>(
-                static_cast<const nr::pr::Pair2*>(b->d_pairs), L.n_pairs, b->d_tasks, b->d_pool, 1u, 4u, b->d_counters + 1,
-                stride, b->d_out);
+            const int stride = exact_smem_int4(std::max(L.pair_R, L.R));
+            const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
+            if ((rc = prepare_kernel((const void*)nr::pr::pair_round2_kernel, smem))) return rc;
+            nr::pr::pair_round2_kernel<<<blocks, kWarpsPerBlock * 32, smem, st>>>(
+                static_cast<const nr::pr::Pair2*>(b->d_pairs), deal, b->d_tasks, ra, b->d_pool, k, b->d_counters, stride, b->d_out);
         } else {
-            const int stride = ladder_smem_int4(L.pair_R);
-            const size_t smem = (size_t)L.pair_wpb * stride * sizeof(int4);
-            if ((rc = prepare_kernel((const void*)nr::pr::pair_ladder_kernel, kWarpsPerBlock * ladder_smem_int4(nr::pr::kMaxRPair3) * sizeof(int4)))) return rc;
-            nr::pr::pair_ladder_kernel<<<L.pair_blocks, L.pair_wpb * 32, smem, st>>>(
-                static_cast<const nr::pr::Pair3*>(b->d_pairs), L.n_pairs, b->d_ltasks, b->qsrc ? b->qsrc->d_pool : b->d_pool,
-                b->d_pool, b->d_lregs, 1u, 4u, k.min_score, b->d_counters + 1, stride, b->d_prung, b->d_sel,
-                b->d_counters + 2, b->d_redo);
+            const int stride = ladder_smem_int4(std::max(L.pair_R, L.R));
+            const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
+            if ((rc = prepare_kernel((const void*)nr::pr::pair_ladder_kernel, smem))) return rc;
+            nr::pr::pair_ladder_kernel<<<blocks, kWarpsPerBlock * 32, smem, st>>>(
+                static_cast<const nr::pr::Pair3*>(b->d_pairs), deal, b->d_ltasks, ra, b->qsrc ? b->qsrc->d_pool : b->d_pool,
+                b->d_pool, b->d_lregs, k, b->d_counters, stride, b->d_prung, b->d_out, b->d_sel, b->d_counters + 2, b->d_redo);
         }
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(mark(3, st));
         b->timed[1] = timing;
         ++launches;
-        if (L.count) CUDA_TRY(cudaStreamWaitEvent(st, b->ev_join, 0));
         if (!b->pairs3.empty()) {
-            CUDA_TRY(mark(4, st));
             // reads whose selection hinges on a tie the 16-bit words cannot order: 32-bit flag ladder, count on the device
-            if ((rc = launch_rest(b, st, k, b->d_redo, 0, std::min(g_ctx.sm_count, 2 * L.n_pairs), kWarpsPerBlock, L.redo_R,
+            CUDA_TRY(mark(4, st));
+            if ((rc = launch_rest(b, st, k, b->d_redo, 0, std::min(g_ctx.sm_count, 2 * L.n_pairs), L.redo_R,
                                   b->d_counters + 2, b->d_counters + 3))) return rc;
             CUDA_TRY(mark(5, st));
             b->timed[2] = timing;
@@ -717,7 +699,7 @@ int run_batch(nr_batch* b, cudaStream_t st) {
         }
     } else if (L.count) {
         CUDA_TRY(mark(0, st));
-        if ((rc = launch_rest(b, st, k, b->d_order, L.count, L.blocks, L.wpb, L.R, nullptr, b->d_counters))) return rc;
+        if ((rc = launch_rest(b, st, k, b->d_order, L.count, L.blocks, L.R, nullptr, b->d_counters))) return rc;
         CUDA_TRY(mark(1, st));
         b->timed[0] = timing;
         ++launches;
@@ -979,7 +961,6 @@ int nr_shutdown(void) {
         for (auto& kv : g_ctx.cache.free_dev) for (void* p : kv.second) cudaFree(p);
         for (auto& kv : g_ctx.cache.free_pin) for (void* p : kv.second) cudaFreeHost(p);
         cudaStreamDestroy(g_ctx.stream);
-        cudaStreamDestroy(g_ctx.side);
         g_ctx = Context();
     }
     return NR_OK;

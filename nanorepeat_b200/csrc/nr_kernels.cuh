@@ -448,8 +448,10 @@ struct Sweep {
             if ((st & 31) == 0) {
                 bcur = bnxt;
                 const int cj = st + lane;       // the column this lane's entry stands for
-                while (!__all_sync(kFull, bcur.w == tag_in || cj >= t_len)) {
-                    __nanosleep(64);
+                // a stripe right behind its producer finds the entries it asked for 32 steps ago not written yet: it reads
+                // them again (one L2 round trip), falls back a little, and from then on its prefetches arrive valid
+                for (int tries = 0; !__all_sync(kFull, bcur.w == tag_in || cj >= t_len); ++tries) {
+                    if (tries > 3) __nanosleep(32);
                     bcur = load_bnd(&bnd_in[cj < t_len ? cj : t_len - 1]);
                 }
                 const int nj = st + 32 + lane;
@@ -520,7 +522,10 @@ struct Sweep {
                     if (lane == 0) {
                         if (MULTI && top) {     // the token carries its tag in the upper half of x
                             ulonglong2 t = load_tok(&tok_in[kcnt]);
-                            while ((int)(t.x >> 32) != tag_in) { __nanosleep(64); t = load_tok(&tok_in[kcnt]); }
+                            for (int tries = 0; (int)(t.x >> 32) != tag_in; ++tries) {
+                                if (tries > 3) __nanosleep(32);
+                                t = load_tok(&tok_in[kcnt]);
+                            }
                             tP = (unsigned)t.x; tJ = t.y;
                         } else { tP = 0; tJ = (unsigned)kJuncNone; }
                     }
@@ -757,32 +762,47 @@ struct TaskCursor {
 // Exact (score, tstart, tend) kernel.  Persistent: the stripe height and the single- / multi-stripe path are picked
 // per entry (warp-uniform dispatch), so one launch covers a whole batch, long expanded alleles included.
 // out[] is indexed by task id.  smem_stride: int4 of shared memory per warp.
+// what the 32-bit kernels need beside the tasks (also handed to the fused kernels of nr_pair_kernels.cuh)
+struct RestArgs {
+    const int32_t* order;       // entries, (task << 7) | code
+    int n_order;
+    int4* scratch;
+    const CoopInfo* coop;
+    const int32_t* coop_idx;    // exact tasks only (ladder tasks carry theirs)
+    int* flags;
+    int epoch;
+};
+
+template <class SC>
+__device__ __forceinline__ void exact_entry(int e, const Task* __restrict__ tasks, const uint32_t* __restrict__ pool, const SC& sc,
+                                            const RestArgs& ra, int4* prof, int lane, int4* out) {
+    const int tid = e >> kCodeBits, code = e & ((1 << kCodeBits) - 1);
+    const Task tk = tasks[tid];
+    if (code == 0) {
+        int R, n_stripes;
+        stripe_shape(tk.q_len, kMaxRExact, R, n_stripes);
+        const u64 key = warp_max64(exact_dispatch<kMinR>(R, tk, pool, sc, prof, lane));
+        if (lane == 0) out[tid] = finalize_rung(key, 0ull, 0, 0, 0, 0);
+    } else {
+        const CoopInfo ci = ra.coop[ra.coop_idx[tid]];
+        exact_stripe_dispatch<kMinR>(coop_rows(tk.q_len, ci.n_stripes), tk, tid, code - 1, ci, ra.epoch, ra.scratch, ra.flags, pool, sc, prof, lane, out);
+    }
+}
+
 template <bool FIXED>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock, 1)
-exact_kernel(const Task* __restrict__ tasks, const int32_t* __restrict__ order, int n_order,
-             const uint32_t* __restrict__ pool, ScoreW scw, int* counter, int smem_stride,
-             int4* scratch, const CoopInfo* __restrict__ coop, const int32_t* __restrict__ coop_idx, int* flags, int epoch, int4* out) {
+exact_kernel(const Task* __restrict__ tasks, RestArgs ra, const uint32_t* __restrict__ pool, ScoreW scw, int* counter,
+             int smem_stride, int4* out) {
     extern __shared__ int4 smem[];
     const ScoreView<FIXED> sc(scw);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     int4* prof = smem + warp * smem_stride;
-    TaskCursor cur(n_order, counter);
+    TaskCursor cur(ra.n_order, counter);
     for (;;) {
         const int oi = cur.next();
         if (oi < 0) break;
-        const int e = order[oi];
-        const int tid = e >> kCodeBits, code = e & ((1 << kCodeBits) - 1);
-        const Task tk = tasks[tid];
-        if (code == 0) {
-            int R, n_stripes;
-            stripe_shape(tk.q_len, kMaxRExact, R, n_stripes);
-            const u64 key = warp_max64(exact_dispatch<kMinR>(R, tk, pool, sc, prof, lane));
-            if (lane == 0) out[tid] = finalize_rung(key, 0ull, 0, 0, 0, 0);
-        } else {
-            const CoopInfo ci = coop[coop_idx[tid]];
-            exact_stripe_dispatch<kMinR>(coop_rows(tk.q_len, ci.n_stripes), tk, tid, code - 1, ci, epoch, scratch, flags, pool, sc, prof, lane, out);
-        }
+        exact_entry(ra.order[oi], tasks, pool, sc, ra, prof, lane, out);
     }
 }
 
@@ -998,39 +1018,44 @@ __device__ __forceinline__ void ladder_stripe_dispatch(int r, const LadderTask& 
     if constexpr (R < kMaxRLadder) ladder_stripe_dispatch<R + 1, FLAG>(r, tk, cx, code, ci, epoch, scratch, flags, sc, prof, lane, out, sel);
 }
 
+template <bool FLAG, class SC>
+__device__ __forceinline__ void ladder_entry(int e, const LadderTask* __restrict__ tasks, const uint32_t* __restrict__ qpool,
+                                             const uint32_t* __restrict__ pool, const LadderRegion* __restrict__ regs, const SC& sc,
+                                             const RestArgs& ra, int4* prof, int lane, int4* out, int4* sel) {
+    const int tid = e >> kCodeBits, code = e & ((1 << kCodeBits) - 1);
+    const LadderTask tk = tasks[tid];
+    LadderCtx cx;
+    cx.qwords = qpool + tk.q_word;      // reads may live in the round-2 batch's pool
+    cx.pool = pool;
+    cx.reg = regs[tk.region];
+    cx.q_len = tk.q_len;
+    if (code == 0) {
+        int R, n_stripes;
+        stripe_shape(tk.q_len, kMaxRLadder, R, n_stripes);
+        ladder_dispatch<kMinR, FLAG>(R, tk, cx, sc, prof, lane, out, sel);
+    } else {
+        const CoopInfo ci = ra.coop[tk.pad];
+        ladder_stripe_dispatch<kMinR, FLAG>(coop_rows(tk.q_len, ci.n_stripes), tk, cx, code, ci, ra.epoch, ra.scratch, ra.flags, sc, prof, lane, out, sel);
+    }
+}
+
 // Round-3 ladder kernel: one warp per read (single stripe) or per stripe of a long read.
+// n_order_dev non-null: order[] was filled on the device (redo list), its length is there.
 template <bool FIXED, bool FLAG>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock, 1)
-ladder_kernel(const LadderTask* __restrict__ tasks, const int32_t* __restrict__ order, int n_order,
-              const int* __restrict__ n_order_dev,      // non-null: order[] was filled on the device (redo list), its length is here
+ladder_kernel(const LadderTask* __restrict__ tasks, RestArgs ra, const int* __restrict__ n_order_dev,
               const uint32_t* __restrict__ qpool, const uint32_t* __restrict__ pool, const LadderRegion* __restrict__ regs, ScoreW scw, int* counter,
-              int smem_stride, int4* scratch, const CoopInfo* __restrict__ coop, int* flags, int epoch, int4* out, int4* sel) {
+              int smem_stride, int4* out, int4* sel) {
     extern __shared__ int4 smem[];
     const ScoreView<FIXED> sc(scw);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     int4* prof = smem + warp * smem_stride;
-    if (n_order_dev) n_order = *n_order_dev;
-    TaskCursor cur(n_order, counter);
+    TaskCursor cur(n_order_dev ? *n_order_dev : ra.n_order, counter);
     for (;;) {
         const int oi = cur.next();
         if (oi < 0) break;
-        const int e = order[oi];
-        const int tid = e >> kCodeBits, code = e & ((1 << kCodeBits) - 1);
-        const LadderTask tk = tasks[tid];
-        LadderCtx cx;
-        cx.qwords = qpool + tk.q_word;      // reads may live in the round-2 batch's pool
-        cx.pool = pool;
-        cx.reg = regs[tk.region];
-        cx.q_len = tk.q_len;
-        if (code == 0) {
-            int R, n_stripes;
-            stripe_shape(tk.q_len, kMaxRLadder, R, n_stripes);
-            ladder_dispatch<kMinR, FLAG>(R, tk, cx, sc, prof, lane, out, sel);
-        } else {
-            const CoopInfo ci = coop[tk.pad];
-            ladder_stripe_dispatch<kMinR, FLAG>(coop_rows(tk.q_len, ci.n_stripes), tk, cx, code, ci, epoch, scratch, flags, sc, prof, lane, out, sel);
-        }
+        ladder_entry<FLAG>(ra.order[oi], tasks, qpool, pool, regs, sc, ra, prof, lane, out, sel);
     }
 }
 

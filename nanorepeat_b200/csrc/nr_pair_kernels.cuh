@@ -331,25 +331,59 @@ __host__ __device__ __forceinline__ int pair_rows(int q_len) {
     return R < kMinR ? kMinR : R;
 }
 
-// Static first round (slot-major, so a small batch spreads over the SMs), then dynamic pulls.
-struct Cursor {
-    int n, lane, warp, wpb;
-    int* counter;
-    bool first;
-    __device__ __forceinline__ Cursor(int n_, int* counter_)
-        : n(n_), lane(threadIdx.x & 31), warp(threadIdx.x >> 5), wpb(blockDim.x >> 5), counter(counter_), first(true) {}
-    __device__ __forceinline__ int next() {
+// Work distribution of the fused launches.  Items: the batch's 32-bit entries [0, n_rest) (in dependency order), then
+// its pairs.  A long-read stripe is a latency-bound chain; next to three warps that saturate the DPX pipe it crawls at
+// a fraction of its speed and becomes the kernel's tail.  So the 32-bit entries are dealt block-major: they fill whole
+// blocks (four such warps per scheduler overlap each other's latencies), the other blocks start on pairs at once
+// (slot-major, so a small batch spreads over the SMs), and everything left is pulled in order from *counter.
+struct Deal {          // computed by the host, read from the kernel's parameter bank (no registers held across a task)
+    int n_rest, n_pairs;
+    int static_rest;   // 32-bit entries dealt block-major to blocks [0, nb_long)
+    int nb_long;
+    int static_pairs;  // pairs dealt slot-major to the other blocks
+};
+__host__ __device__ inline Deal make_deal(int n_rest, int n_pairs, int wpb, int grid) {
+    Deal d;
+    d.n_rest = n_rest; d.n_pairs = n_pairs;
+    d.static_rest = n_rest < wpb * grid ? n_rest : wpb * grid;
+    d.nb_long = (d.static_rest + wpb - 1) / wpb;
+    const int room = wpb * (grid - d.nb_long);
+    d.static_pairs = n_pairs < room ? n_pairs : room;
+    return d;
+}
+// next item: < n_rest: entry of the 32-bit kernels; else pair (item - n_rest); -1: done
+__device__ __forceinline__ int next_item(const Deal& dl, bool& first, int* counter) {
+    if (dl.nb_long < 0) {       // plain dealing: one slot-major round over all items, then dynamic pulls
+        const int n = dl.n_rest + dl.n_pairs;
         if (first) {
             first = false;
-            const int i = warp * (int)gridDim.x + (int)blockIdx.x;
+            const int i = (threadIdx.x >> 5) * (int)gridDim.x + (int)blockIdx.x;
             return i < n ? i : -1;
         }
         int i = 0;
-        if (lane == 0) i = atomicAdd(counter, 1);
-        i = __shfl_sync(kFull, i, 0) + wpb * (int)gridDim.x;
+        if ((threadIdx.x & 31) == 0) i = atomicAdd(counter, 1);
+        i = __shfl_sync(kFull, i, 0) + (blockDim.x >> 5) * (int)gridDim.x;
         return i < n ? i : -1;
     }
-};
+    if (first) {
+        first = false;
+        const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, blk = (int)blockIdx.x;
+        if (blk < dl.nb_long) {
+            const int e = blk * wpb + warp;
+            if (e < dl.static_rest) return e;
+        } else {
+            const int p = warp * ((int)gridDim.x - dl.nb_long) + (blk - dl.nb_long);
+            if (p < dl.static_pairs) return dl.n_rest + p;
+        }
+    }
+    int d = 0;
+    if ((threadIdx.x & 31) == 0) d = atomicAdd(counter, 1);
+    d = __shfl_sync(kFull, d, 0);
+    const int rest_left = dl.n_rest - dl.static_rest;
+    if (d < rest_left) return dl.static_rest + d;
+    const int p = dl.static_pairs + d - rest_left;
+    return p < dl.n_pairs ? dl.n_rest + p : -1;
+}
 
 // ---- round 2 -------------------------------------------------------------------------------------------------------
 template <int R>
@@ -398,21 +432,28 @@ __device__ __forceinline__ void pair2_dispatch(int r, const Pair2& pt, const Tas
     if constexpr (R < kMaxRPair2) pair2_dispatch<R + 1>(r, pt, tasks, pool, prof, lane, one, four, out);
 }
 
-// Round 2 on pairs: out[task] = (score, 0 if the alignment starts at a column <= |left| else |left| + 1, tend, 0).
+// Round 2: the batch's 32-bit entries (stripes of long reads first: they are the critical path) and then its pairs, one
+// persistent launch.  out[task] = (score, 0 if the alignment starts at a column <= |left| else |left| + 1, tend, 0) for
+// paired tasks, the exact (score, tstart, tend, 0) for the others.
 __global__ void __launch_bounds__(32 * kWarpsPerBlock, 1)
-pair_round2_kernel(const Pair2* __restrict__ pairs, int n_pairs, const Task* __restrict__ tasks,
-                   const uint32_t* __restrict__ pool, u32 one, unsigned four, int* counter, int smem_stride, int4* out) {
+pair_round2_kernel(const Pair2* __restrict__ pairs, Deal dl, const Task* __restrict__ tasks, RestArgs ra,
+                   const uint32_t* __restrict__ pool, ScoreW scw, int* counter, int smem_stride, int4* out) {
     extern __shared__ uint4 psmem[];
+    const ScoreView<true> sc(scw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4* prof = psmem + warp * smem_stride;
-    Cursor cur(n_pairs, counter);
+    bool first = true;
     for (;;) {
-        const int i = cur.next();
+        const int i = next_item(dl, first, counter);
         if (i < 0) break;
-        const Pair2 pt = pairs[i];
+        if (i < ra.n_order) {
+            exact_entry(ra.order[i], tasks, pool, sc, ra, reinterpret_cast<int4*>(prof), lane, out);
+            continue;
+        }
+        const Pair2 pt = pairs[i - ra.n_order];
         int q = tasks[pt.a].q_len;
         if (pt.b >= 0) q = max(q, tasks[pt.b].q_len);
-        pair2_dispatch<kMinR>(pair_rows(q), pt, tasks, pool, prof, lane, one, four, out);
+        pair2_dispatch<kMinR>(pair_rows(q), pt, tasks, pool, prof, lane, (u32)sc.one, sc.four, out);
     }
 }
 
@@ -520,24 +561,30 @@ __device__ __forceinline__ void pair3_dispatch(int r, const Pair3& pt, const Lad
         pair3_dispatch<R + 1>(r, pt, tasks, qpool, pool, regs, prof, lane, one, four, min_score, prung, sel, redo_count, redo);
 }
 
-// Round 3 on pairs: sel[read] = (top score, n tied rungs that span both flanks, sum of their k, 0); reads whose
-// selection hinges on an undecidable tie go to redo[] (indices into tasks[]).
+// Round 3: the batch's 32-bit entries (stripes of long reads, reads without an anchor) and then its pairs, one
+// persistent launch.  sel[read] = (top score, n tied rungs that span both flanks, sum of their k, 0); paired reads
+// whose selection hinges on an undecidable tie go to redo[] (entries for ladder_kernel).
 __global__ void __launch_bounds__(32 * kWarpsPerBlock, 1)
-pair_ladder_kernel(const Pair3* __restrict__ pairs, int n_pairs, const LadderTask* __restrict__ tasks,
+pair_ladder_kernel(const Pair3* __restrict__ pairs, Deal dl, const LadderTask* __restrict__ tasks, RestArgs ra,
                    const uint32_t* __restrict__ qpool, const uint32_t* __restrict__ pool,
-                   const LadderRegion* __restrict__ regs, u32 one, unsigned four, int min_score, int* counter,
-                   int smem_stride, uint2* prung, int4* sel, int* redo_count, int32_t* redo) {
+                   const LadderRegion* __restrict__ regs, ScoreW scw, int* counter,
+                   int smem_stride, uint2* prung, int4* out, int4* sel, int* redo_count, int32_t* redo) {
     extern __shared__ uint4 psmem[];
+    const ScoreView<true> sc(scw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4* prof = psmem + warp * smem_stride;
-    Cursor cur(n_pairs, counter);
+    bool first = true;
     for (;;) {
-        const int i = cur.next();
+        const int i = next_item(dl, first, counter);
         if (i < 0) break;
-        const Pair3 pt = pairs[i];
+        if (i < ra.n_order) {
+            ladder_entry<true>(ra.order[i], tasks, qpool, pool, regs, sc, ra, reinterpret_cast<int4*>(prof), lane, out, sel);
+            continue;
+        }
+        const Pair3 pt = pairs[i - ra.n_order];
         int q = tasks[pt.a].q_len;
         if (pt.b >= 0) q = max(q, tasks[pt.b].q_len);
-        pair3_dispatch<kMinR>(pair_rows(q), pt, tasks, qpool, pool, regs, prof, lane, one, four, min_score, prung, sel, redo_count, redo);
+        pair3_dispatch<kMinR>(pair_rows(q), pt, tasks, qpool, pool, regs, prof, lane, (u32)sc.one, sc.four, sc.min_score, prung, sel, redo_count, redo);
     }
 }
 
