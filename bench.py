@@ -270,10 +270,11 @@ def main():
     b2 = engine.Batch.begin(sc, "round2_flags")
     for spec in r2_specs:
         b2.add_round2(*spec)
-    b3 = engine.Batch.begin(sc, "round3")
-    for spec in r3_specs:
-        b3.add_round3(*spec)
-    batches = [b2.commit(), b3.commit()]
+    b2.commit()
+    b3 = engine.Batch.begin_round3_from(b2)          # the production flow: round 3 over the reads round 2 left in HBM,
+    for i, (right, lo, hi) in enumerate(r3_reuse):   # resuming from the DP state round 2 kept at the end of the left anchor
+        b3.add_round3_reuse(i, right, lo, hi)
+    batches = [b2, b3.commit()]
     stats = [b.stats() for b in batches]
     executed_step = sum(s["executed_cells"] for s in stats)
     algorithmic_check = sum(s["algorithmic_cells"] for s in stats)
@@ -352,8 +353,14 @@ def main():
 
     # the resident path (valid reads only) and the C-ABI path (all reads, skipped ones zero) must give the same records
     s3 = batches[1].fetch_round3()
+    assert all(np.array_equal(x, y) for x, y in zip(s3, s3_cabi)), "resident and C-ABI round-3 results differ"
+    # ... and the same as a fresh round-3 batch (full forward sweeps, nothing taken over from round 2)
+    with engine.Batch.begin(sc, "round3") as fresh3:
+        for spec in r3_specs:
+            fresh3.add_round3(*spec)
+        s3_fresh = fresh3.commit().run().fetch_round3()
     vmask = np.concatenate([np.asarray(ok, bool) for ok in valid])
-    assert all(np.array_equal(x, y[vmask]) for x, y in zip(s3, s3_cabi)), "resident and C-ABI round-3 results differ"
+    assert all(np.array_equal(x[vmask], y) for x, y in zip(s3, s3_fresh)), "resumed and fresh round-3 results differ"
 
     if world > 1:
         t = torch.tensor([total_ms, e2e_s, cabi_s], dtype=torch.float64, device="cuda")

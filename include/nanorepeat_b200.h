@@ -172,7 +172,8 @@ nr_batch_t* nr_batch_create_round3(const nr_scoring_t* sc,
 #define NR_KIND_ROUND3 2
 /* Round 2 with (score, tend, tstart <= |left|) records instead of (score, tstart, tend): all the selection of
  * nanoRepeat_bam.py:364-384 reads.  Lets reads up to 512 bases run on the paired u16x2 kernel; fetch with
- * nr_batch_fetch_round2.  Usable as the source of nr_batch_begin_round3_from like NR_KIND_ROUND2. */
+ * nr_batch_fetch_round2.  As the source of nr_batch_begin_round3_from it also keeps every pair's DP state at the end of
+ * the left anchor on the device, and round 3 resumes from it instead of sweeping the left anchor again. */
 #define NR_KIND_ROUND2_FLAGS 3
 nr_batch_t* nr_batch_begin(const nr_scoring_t* sc, int32_t kind);
 int nr_batch_add_round2(nr_batch_t* b, const char* left, int32_t n_left, const char* motif, int32_t motif_len,
@@ -193,7 +194,9 @@ int nr_batch_add_round3_reuse(nr_batch_t* b, int32_t region_index, const char* r
 int nr_batch_commit(nr_batch_t* b);
 int nr_batch_run(nr_batch_t* b, void* stream);
 int nr_batch_fetch_alns(nr_batch_t* b, nr_aln_t* out);                      /* tasks / round2 batches */
-/* round-2 batches of either kind: per read AS, tend and the predicate tstart <= |left| (nanoRepeat_bam.py:373) */
+/* round-2 batches of either kind: per read AS, tend and the predicate tstart <= |left| (nanoRepeat_bam.py:373).
+ * NR_KIND_ROUND2_FLAGS: tend and the predicate are exact whenever tend >= |left| (the other half of the span test);
+ * an alignment that ends before the repeat is reported with some tend < |left| -- the reference drops such reads. */
 int nr_batch_fetch_round2(nr_batch_t* b, int32_t* score, int32_t* tend, uint8_t* starts_by_left);
 int nr_batch_fetch_round3(nr_batch_t* b, const int64_t* rung_offset, nr_rung_t* rungs,
                           int64_t* sum_k, int32_t* n_k, int32_t* top_score);  /* round3 batches */

@@ -259,6 +259,9 @@ struct nr_batch {
     std::vector<int32_t> coop_idx;            // exact tasks: index into coop, -1 for single-stripe tasks
     nr::CoopInfo* d_coop = nullptr;
     int32_t* d_coop_idx = nullptr;
+    std::vector<int32_t> lt_src;              // round 3 over a round-2 batch's reads: that batch's task of every ladder task
+    uint32_t* d_state = nullptr;              // round 2 pairs: DP state after column |left| - 2, kept for round 3
+    size_t state_bytes = 0;
     int* d_flags = nullptr;                   // progress flags of the multi-stripe tasks, zeroed before every run
     size_t flags_bytes = 0;
     Launch launch = {};
@@ -393,6 +396,7 @@ int plan_batch(nr_batch* b) {
     std::vector<long long> pair_cost;
     Launch& L = b->launch;
     L = {};
+    long long state_off = 0;
     if (b->pair && fixed && !ladder && b->kind == KIND_ROUND2) {
         for (const RegionInfo& g : b->regions) {
             std::vector<int> ids;
@@ -401,17 +405,49 @@ int plan_batch(nr_batch* b) {
                 if (t.q_len >= 1 && t.q_len <= 32 * nr::pr::kMaxRPair2 && t.t_len >= 1) ids.push_back(r);
             }
             make_pairs(ids, [&](int i) { return b->tasks[i].q_len; }, [&](int x, int y) {
-                nr::pr::Pair2 p = {x, y, g.n_left, 0};
+                const int R = nr::pr::pair_rows(b->tasks[x].q_len);      // x is the longer read
+                nr::pr::Pair2 p = {x, y, g.n_left, -1};
+                if (g.n_left >= 2 && state_off + nr::pr::state_words(R) < 0x7fffffffLL) {
+                    p.state_off = (int32_t)state_off;                    // round 3 resumes from here (nr_batch_begin_round3_from)
+                    state_off += nr::pr::state_words(R);
+                }
                 b->pairs2.push_back(p);
                 paired[x] = 1;
                 if (y >= 0) paired[y] = 1;
-                const int R = nr::pr::pair_rows(b->tasks[x].q_len);      // x is the longer read
                 L.pair_R = std::max(L.pair_R, R);
                 pair_cost.push_back((long long)32 * R * b->tasks[x].t_len);
             });
         }
     } else if (b->pair && fixed && ladder && b->flag) {
         long long rung_off = 0;
+        if (b->qsrc && !b->qsrc->pairs2.empty() && (int)b->lt_src.size() == n) {
+            // the reads were paired in round 2: same pairs, same halves, same rows per lane, so that the forward sweep
+            // can take over the DP state round 2 kept after column |left| - 2 instead of sweeping the left anchor again
+            const nr_batch* src = b->qsrc;
+            std::vector<int> src2lt(src->tasks.size(), -1);
+            for (int i = 0; i < n; ++i)
+                if (b->lt_src[i] >= 0) src2lt[b->lt_src[i]] = i;
+            for (const nr::pr::Pair2& p2 : src->pairs2) {
+                const int la = src2lt[p2.a], lb = p2.b >= 0 ? src2lt[p2.b] : -1;
+                if (la < 0 && lb < 0) continue;
+                const nr::LadderRegion& g = b->lregs[b->ltasks[la >= 0 ? la : lb].region];
+                if (g.n_left <= 0 || g.n_right <= 0) continue;
+                const int q = std::max(src->tasks[p2.a].q_len, p2.b >= 0 ? src->tasks[p2.b].q_len : 0);
+                const int R = nr::pr::pair_rows(q);
+                int kmin = INT32_MAX, kmax = -1;
+                for (int t : {la, lb})
+                    if (t >= 0) { kmin = std::min(kmin, b->ltasks[t].kmin); kmax = std::max(kmax, b->ltasks[t].kmax); }
+                nr::pr::Pair3 p = {la, lb, (int32_t)rung_off, -1, R, {0, 0, 0}};
+                if (p2.state_off >= 0 && src->d_state && g.n_left >= 2 && g.n_left == p2.mark_col) p.state_off = p2.state_off;
+                rung_off += kmax - kmin + 1;
+                b->pairs3.push_back(p);
+                if (la >= 0) paired[la] = 1;
+                if (lb >= 0) paired[lb] = 1;
+                L.pair_R = std::max(L.pair_R, R);
+                const long long cols = (long long)g.n_right + g.n_left + (long long)g.m * kmax - (p.state_off >= 0 ? g.n_left - 1 : 0);
+                pair_cost.push_back((long long)32 * R * cols);
+            }
+        }
         for (int i0 = 0; i0 < n;) {
             int i1 = i0;
             while (i1 < n && b->ltasks[i1].region == b->ltasks[i0].region) ++i1;
@@ -419,12 +455,12 @@ int plan_batch(nr_batch* b) {
             std::vector<int> ids;
             if (g.n_left > 0 && g.n_right > 0)
                 for (int i = i0; i < i1; ++i)
-                    if (b->ltasks[i].q_len >= 1 && b->ltasks[i].q_len <= 32 * nr::pr::kMaxRPair3) ids.push_back(i);
+                    if (!paired[i] && b->ltasks[i].q_len >= 1 && b->ltasks[i].q_len <= 32 * nr::pr::kMaxRPair3) ids.push_back(i);
             make_pairs(ids, [&](int i) { return ((long long)b->ltasks[i].q_len << 20) + b->ltasks[i].kmax; }, [&](int x, int y) {
                 const nr::LadderTask& tx = b->ltasks[x];
                 int kmin = tx.kmin, kmax = tx.kmax;
                 if (y >= 0) { kmin = std::min(kmin, b->ltasks[y].kmin); kmax = std::max(kmax, b->ltasks[y].kmax); }
-                nr::pr::Pair3 p = {x, y, (int32_t)rung_off, 0};
+                nr::pr::Pair3 p = {x, y, (int32_t)rung_off, -1, 0, {0, 0, 0}};
                 rung_off += kmax - kmin + 1;
                 b->pairs3.push_back(p);
                 paired[x] = 1;
@@ -439,6 +475,7 @@ int plan_batch(nr_batch* b) {
         b->prung_bytes = sizeof(uint2) * (size_t)std::max<long long>(rung_off, 1);
         L.redo_R = L.pair_R;
     }
+    b->state_bytes = sizeof(uint32_t) * 32 * (size_t)state_off;
     L.n_pairs = (int)pair_cost.size();
     if (L.n_pairs) {            // pairs in decreasing cost: the tail of the persistent launch is made of the cheap ones
         std::vector<int> po(L.n_pairs);
@@ -558,6 +595,7 @@ int plan_batch(nr_batch* b) {
     if ((rc = cached_alloc((void**)&b->h_out, b->out_bytes, true))) return rc;
     if (scratch_total && (rc = cached_alloc((void**)&b->d_scratch, b->scratch_bytes, false))) return rc;
     if (b->flags_bytes && (rc = cached_alloc((void**)&b->d_flags, b->flags_bytes, false))) return rc;
+    if (b->state_bytes && (rc = cached_alloc((void**)&b->d_state, b->state_bytes, false))) return rc;
     if (b->flag) {
         b->sel_bytes = sizeof(int4) * std::max<size_t>((size_t)b->n_reads, 1);
         if ((rc = cached_alloc((void**)&b->d_sel, b->sel_bytes, false))) return rc;
@@ -674,14 +712,16 @@ int run_batch(nr_batch* b, cudaStream_t st) {
             const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
             if ((rc = prepare_kernel((const void*)nr::pr::pair_round2_kernel, smem))) return rc;
             nr::pr::pair_round2_kernel<<<blocks, kWarpsPerBlock * 32, smem, st>>>(
-                static_cast<const nr::pr::Pair2*>(b->d_pairs), deal, b->d_tasks, ra, b->d_pool, k, b->d_counters, stride, b->d_out);
+                static_cast<const nr::pr::Pair2*>(b->d_pairs), deal, b->d_tasks, ra, b->d_pool, k, b->d_counters, stride, b->d_out,
+                b->d_state);
         } else {
             const int stride = ladder_smem_int4(std::max(L.pair_R, L.R));
             const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
             if ((rc = prepare_kernel((const void*)nr::pr::pair_ladder_kernel, smem))) return rc;
             nr::pr::pair_ladder_kernel<<<blocks, kWarpsPerBlock * 32, smem, st>>>(
                 static_cast<const nr::pr::Pair3*>(b->d_pairs), deal, b->d_ltasks, ra, b->qsrc ? b->qsrc->d_pool : b->d_pool,
-                b->d_pool, b->d_lregs, k, b->d_counters, stride, b->d_prung, b->d_out, b->d_sel, b->d_counters + 2, b->d_redo);
+                b->d_pool, b->d_lregs, k, b->d_counters, stride, b->d_prung, b->d_out, b->d_sel, b->d_counters + 2, b->d_redo,
+                b->qsrc ? b->qsrc->d_state : nullptr);
         }
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(mark(3, st));
@@ -867,6 +907,7 @@ int add_round3(nr_batch* b, const char* left, int32_t n_left, const char* right,
             t.region = lreg;
             t.read = first + r;
             b->ltasks.push_back(t);
+            b->lt_src.push_back(reuse ? (int32_t)(reuse - b->qsrc->tasks.data()) + r : -1);
         }
         return NR_OK;
     }
@@ -1000,6 +1041,7 @@ void nr_batch_destroy(nr_batch_t* b) {
     cached_free(b->h_out, b->out_bytes, true);
     cached_free(b->d_scratch, b->scratch_bytes, false);
     cached_free(b->d_flags, b->flags_bytes, false);
+    cached_free(b->d_state, b->state_bytes, false);
     cached_free(b->d_sel, b->sel_bytes, false);
     cached_free(b->h_sel, b->sel_bytes, true);
     cached_free(b->d_prung, b->prung_bytes, false);

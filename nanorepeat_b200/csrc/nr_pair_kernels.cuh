@@ -64,14 +64,19 @@ __device__ __forceinline__ void cell(u32 hd, u32 s, u32 one, u32& h, u32& e1, u3
 struct Pair2 {         // round 2: two tasks of one region (same template); b < 0: no partner
     int32_t a, b;
     int32_t mark_col;  // |left|: an alignment that starts at a column <= mark_col passes the span test (:373)
-    int32_t pad;
+    int32_t state_off; // where the pair's DP state after column |left| - 2 is kept for round 3 (units of 32 words), -1: not kept
 };
 
-struct Pair3 {         // round 3: two LadderTasks of one region; b < 0: no partner
+struct Pair3 {         // round 3: two LadderTasks of one region, either may be absent (< 0)
     int32_t a, b;
     int32_t rung_off;  // first (P, J) token pair of this pair in the rung buffer
-    int32_t pad;
+    int32_t state_off; // >= 0: the forward sweep resumes from the state round 2 kept (same pair, same halves, same R)
+    int32_t R;         // rows per lane (the pair's shape in round 2 when it resumes; 0: from the reads' lengths)
+    int32_t pad[3];
 };
+
+// words per lane of a kept state: H, E1, E2 of R rows and the lane's best prefix class
+__host__ __device__ constexpr int state_words(int R) { return 3 * R + 1; }
 
 // Query profile of a pair: prof[(c * CH + chunk) * 32 + lane].{x,y,z,w} = increments of rows 4*chunk..+3 of this lane
 // against target code c, read A in the high half, read B in the low half.  Rows past a read's end score as mismatches:
@@ -122,7 +127,11 @@ struct Sweep {
     int q_a, q_b;
     const uint4* bsm;              // kPF
     uint2* rung_out;
-    int jnext, m, kcnt, zone_start;
+    int jnext, m, kcnt, zone_start; // zone_start: in steps of this sweep
+    int col0;                      // first column of the sweep (kPF resuming from a kept state: |left| - 1; else 0)
+    const u32* resume;             // kPF: state kept by round 2, [word * 32 + lane]
+    u32* save;                     // kP2: where to keep the state after column save_col (null: nowhere)
+    int save_col;
     // state
     u32 H[R], E1[R], E2[R];
     u32 hup_prev, h_out, f1_out, f2_out;
@@ -138,14 +147,29 @@ struct Sweep {
     __device__ __forceinline__ uint32_t tword(int i) const { return __ldg(&twords[min(max(i, 0), wmax)]); }
 
     __device__ __forceinline__ void init() {
+        if (MODE == kPF && resume) {
+            // round 2 swept these reads over the same left anchor with the same pairing: take over where every live
+            // state is still unmarked in both rounds (after column |left| - 2)
 #pragma unroll
-        for (int r = 0; r < R; ++r) { H[r] = FLOOR; E1[r] = FLOOR + sub2(kOpen1); E2[r] = FLOOR + sub2(kOpen2); }
-        hup_prev = FLOOR; h_out = FLOOR; f1_out = FLOOR; f2_out = FLOOR;
-        best = 0; bestc = FLOOR | kOnes; raw_hi = 0; raw_lo = 0; st_hi = 0; st_lo = 0;
+            for (int r = 0; r < R; ++r) {
+                H[r] = __ldcg(&resume[r * 32 + lane]);
+                E1[r] = __ldcg(&resume[(R + r) * 32 + lane]);
+                E2[r] = __ldcg(&resume[(2 * R + r) * 32 + lane]);
+            }
+            hup_prev = lane ? __ldcg(&resume[(R - 1) * 32 + lane - 1]) : FLOOR;
+            best = __ldcg(&resume[3 * R * 32 + lane]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) { H[r] = FLOOR; E1[r] = FLOOR + sub2(kOpen1); E2[r] = FLOOR + sub2(kOpen2); }
+            hup_prev = FLOOR;
+            best = 0;
+        }
+        h_out = FLOOR; f1_out = FLOOR; f2_out = FLOOR;
+        bestc = FLOOR | kOnes; raw_hi = 0; raw_lo = 0; st_hi = 0; st_lo = 0;
         nz = lane != 0; bz = lane != 0 ? 0u : FLOOR;
         wmax = (t_len + 15) >> 4;
-        wi = (-lane) >> 4;
-        wsh = 2 * ((-lane) & 15);
+        wi = (col0 - lane) >> 4;
+        wsh = 2 * ((col0 - lane) & 15);
         w0 = tword(wi); w1 = tword(wi + 1);
         twl = 0;
         prof_lane = reinterpret_cast<const char*>(prof + lane);
@@ -214,7 +238,9 @@ struct Sweep {
         *p = (unsigned short)v;
     }
 
-    template <bool FAST>
+    // TRACK (kP2): per half the step of the last strict improvement of the score class; without it (the columns an
+    // alignment that passes the span test cannot end in) only the running maximum word.
+    template <bool FAST, bool TRACK>
     __device__ __forceinline__ void step(int st, u32 one, unsigned four) {
         const bool zone = !FAST && MODE == kPF && st >= zone_start;     // uniform
         constexpr int CH = StripeCfg<R>::CH;
@@ -230,9 +256,10 @@ struct Sweep {
         f1 = pmadd(f1, nz, bz);
         f2 = pmadd(f2, nz, bz);
         const unsigned tb = next_base(four);
-        const int jj = st - lane;
+        const int rel = st - lane;
+        const int jj = rel + col0;
         const bool anyj = zone && __any_sync(kFull, jj + 1 == jnext && jj < t_len);
-        if (FAST || (jj >= 0 && jj < t_len)) {
+        if (FAST || (rel >= 0 && jj < t_len)) {
             const uint4* pp = reinterpret_cast<const uint4*>(prof_lane + tb * (unsigned)(CH * 512));
             const u32 hd = hup_prev;
             hup_prev = hup;
@@ -247,11 +274,11 @@ struct Sweep {
                 }
             }
             u32 cm, jhi = 0;
-            const u32 cm0 = MODE == kP2 ? 0u : best;
+            const u32 cm0 = (MODE == kP2 && TRACK) ? 0u : best;
             if (zone && anyj) cm = cells<true>(pp, hd, cm0, f1, f2, one, jhi);
             else cm = cells<false>(pp, hd, cm0, f1, f2, one, jhi);
             h_out = H[R - 1]; f1_out = f1; f2_out = f2;
-            if (MODE == kP2) {
+            if (MODE == kP2 && TRACK) {
                 // per half: a strictly higher score class (the mark bit forced on both sides); the first column wins
                 // (not __vibmax_u16x2: its inline asm re-reads an input after writing its output without an early clobber,
                 // so "best = __vibmax(best, ...)" may alias the two and report "kept" for ever)
@@ -260,6 +287,15 @@ struct Sweep {
                 bestc = nb;
                 if (x > 0xffffu) { st_hi = st; raw_hi = cm; }
                 if (x & 0xffffu) { st_lo = st; raw_lo = cm; }
+                if (!FAST && save && jj == save_col) {      // the state round 3 resumes from
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        __stcg(&save[r * 32 + lane], H[r]);
+                        __stcg(&save[(R + r) * 32 + lane], E1[r]);
+                        __stcg(&save[(2 * R + r) * 32 + lane], E2[r]);
+                    }
+                    __stcg(&save[3 * R * 32 + lane], bestc);
+                }
             } else {
                 best = cm;
                 if (last_col) {
@@ -291,40 +327,61 @@ struct Sweep {
 #pragma unroll 1
         for (; st < end; ++st) {
             if ((st & 15) == 0) refill();
-            step<false>(st, one, four);
+            step<false, true>(st, one, four);
         }
     }
 
+    template <bool TRACK>
     __device__ __forceinline__ void fast_until(int& st, int end, u32 one, unsigned four) {
         for (; st + 16 <= end; st += 16) {       // st is a multiple of 16 here
             refill();
 #pragma unroll 1
             for (int b = 0; b < 16; b += 4) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) step<true>(st + b + u, one, four);
+                for (int u = 0; u < 4; ++u) step<true, TRACK>(st + b + u, one, four);
             }
         }
     }
 
+    // zone_start_: kPF, first step (of this sweep) at which a lane can be at a junction column
     __device__ __forceinline__ void run(u32 one, unsigned four, int zone_start_) {
         init();
         zone_start = zone_start_;
-        const int nsteps = t_len + 31;
-        int fast_end = ((t_len - 1) >> 4) << 4;
+        const int n = t_len - col0;              // columns swept
+        const int nsteps = n + 31;
+        int fast_end = ((n - 1) >> 4) << 4;
         if (MODE == kPF) fast_end = min(fast_end, (zone_start >> 4) << 4);
+        const int mc = mark_col - col0;          // the last marked column, in steps of lane 0
         int st = 0;
         slow_until(st, min(32, nsteps), one, four);
-        if (kMarks && mark_col >= 0) {
-            fast_until(st, min(fast_end, (mark_col >> 4) << 4), one, four);
-            slow_until(st, min(nsteps, ((mark_col + 32 + 15) >> 4) << 4), one, four);
+        if (kMarks && mc >= 0) {
+            // guarded steps while the lanes pass the last marked column (kP2: from two columns earlier on, where the
+            // state is kept for round 3 and the tracked columns begin)
+            const int zs = MODE == kP2 ? max(mc - 2, 0) : mc;
+            if (MODE == kP2) {
+                // columns below |left| - 2: an alignment ending there fails the span test whatever its tend, so only the
+                // running maximum matters; it is folded into the tracked class once, marked as "ended too early"
+                const int before = st;
+                fast_until<false>(st, min(fast_end, (zs >> 4) << 4), one, four);
+                if (st != before) {
+                    const u32 nb = __vmaxu2(bestc, best | kOnes);
+                    const u32 x = nb ^ bestc;
+                    bestc = nb;
+                    if (x > 0xffffu) { st_hi = lane; raw_hi = 0; }       // column 0: tend = 1
+                    if (x & 0xffffu) { st_lo = lane; raw_lo = 0; }
+                }
+            } else {
+                fast_until<true>(st, min(fast_end, (zs >> 4) << 4), one, four);
+            }
+            slow_until(st, min(nsteps, ((mc + 32 + 15) >> 4) << 4), one, four);
         }
-        fast_until(st, fast_end, one, four);
+        fast_until<true>(st, fast_end, one, four);
         slow_until(st, nsteps, one, four);
     }
 };
 
-constexpr int kMaxRPair2 = 16;    // round 2: reads up to 512 bases
 constexpr int kMaxRPair3 = 12;    // round 3: 384 bases (profile + junction vectors: 12 KB of shared memory per warp)
+constexpr int kMaxRPair2 = kMaxRPair3;   // round 2 pairs the same reads, so that round 3 can resume from its state
 
 __host__ __device__ __forceinline__ int pair_rows(int q_len) {
     int R = (q_len + 31) / 32;
@@ -388,7 +445,7 @@ __device__ __forceinline__ int next_item(const Deal& dl, bool& first, int* count
 // ---- round 2 -------------------------------------------------------------------------------------------------------
 template <int R>
 __device__ __forceinline__ void pair2_task(const Pair2& pt, const Task* __restrict__ tasks, const uint32_t* __restrict__ pool,
-                                           uint4* prof, int lane, u32 one, unsigned four, int4* out) {
+                                           uint4* prof, int lane, u32 one, unsigned four, int4* out, u32* state) {
     const Task ta = tasks[pt.a];
     Task tb = ta;
     int q_b = 0;
@@ -399,6 +456,9 @@ __device__ __forceinline__ void pair2_task(const Pair2& pt, const Task* __restri
     Sweep<R, kP2> sw;
     sw.prof = prof; sw.twords = pool + ta.t_word; sw.t_len = ta.t_len; sw.lane = lane;
     sw.mark_col = pt.mark_col;
+    sw.col0 = 0; sw.resume = nullptr;
+    sw.save_col = pt.mark_col - 2;
+    sw.save = (state && pt.state_off >= 0 && sw.save_col >= 0) ? state + (size_t)pt.state_off * 32 : nullptr;
     sw.run(one, four, 0);
     // per half: (score, smallest end column, mark of the best word there) -> one 32-bit key, warp maximum
 #pragma unroll
@@ -427,9 +487,9 @@ __device__ __forceinline__ void pair2_task(const Pair2& pt, const Task* __restri
 template <int R>
 __device__ __forceinline__ void pair2_dispatch(int r, const Pair2& pt, const Task* __restrict__ tasks,
                                                const uint32_t* __restrict__ pool, uint4* prof, int lane, u32 one,
-                                               unsigned four, int4* out) {
-    if (r == R) { pair2_task<R>(pt, tasks, pool, prof, lane, one, four, out); return; }
-    if constexpr (R < kMaxRPair2) pair2_dispatch<R + 1>(r, pt, tasks, pool, prof, lane, one, four, out);
+                                               unsigned four, int4* out, u32* state) {
+    if (r == R) { pair2_task<R>(pt, tasks, pool, prof, lane, one, four, out, state); return; }
+    if constexpr (R < kMaxRPair2) pair2_dispatch<R + 1>(r, pt, tasks, pool, prof, lane, one, four, out, state);
 }
 
 // Round 2: the batch's 32-bit entries (stripes of long reads first: they are the critical path) and then its pairs, one
@@ -437,7 +497,7 @@ __device__ __forceinline__ void pair2_dispatch(int r, const Pair2& pt, const Tas
 // paired tasks, the exact (score, tstart, tend, 0) for the others.
 __global__ void __launch_bounds__(32 * kWarpsPerBlock, 1)
 pair_round2_kernel(const Pair2* __restrict__ pairs, Deal dl, const Task* __restrict__ tasks, RestArgs ra,
-                   const uint32_t* __restrict__ pool, ScoreW scw, int* counter, int smem_stride, int4* out) {
+                   const uint32_t* __restrict__ pool, ScoreW scw, int* counter, int smem_stride, int4* out, u32* state) {
     extern __shared__ uint4 psmem[];
     const ScoreView<true> sc(scw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -453,7 +513,7 @@ pair_round2_kernel(const Pair2* __restrict__ pairs, Deal dl, const Task* __restr
         const Pair2 pt = pairs[i - ra.n_order];
         int q = tasks[pt.a].q_len;
         if (pt.b >= 0) q = max(q, tasks[pt.b].q_len);
-        pair2_dispatch<kMinR>(pair_rows(q), pt, tasks, pool, prof, lane, (u32)sc.one, sc.four, out);
+        pair2_dispatch<kMinR>(pair_rows(q), pt, tasks, pool, prof, lane, (u32)sc.one, sc.four, out, state);
     }
 }
 
@@ -473,15 +533,17 @@ __device__ __forceinline__ void pair3_task(const Pair3& pt, const LadderTask* __
                                            const uint32_t* __restrict__ qpool, const uint32_t* __restrict__ pool,
                                            const LadderRegion* __restrict__ regs, uint4* prof, int lane, u32 one,
                                            unsigned four, int min_score, uint2* prung, int4* sel, int* redo_count,
-                                           int32_t* redo) {
-    const LadderTask ta = tasks[pt.a];
-    LadderTask tb = ta;
-    int q_b = 0;
-    if (pt.b >= 0) { tb = tasks[pt.b]; q_b = tb.q_len; }
-    const LadderRegion reg = regs[ta.region];
-    const int q_a = ta.q_len;
-    const int kmin = pt.b >= 0 ? min(ta.kmin, tb.kmin) : ta.kmin;
-    const int kmax = pt.b >= 0 ? max(ta.kmax, tb.kmax) : ta.kmax;
+                                           int32_t* redo, const u32* __restrict__ qstate) {
+    // either half may be absent (a read round 2 gave no size keeps its place in a resumed pair)
+    const bool ha = pt.a >= 0, hb = pt.b >= 0;
+    const LadderTask tv = tasks[ha ? pt.a : pt.b];
+    LadderTask ta = tv, tb = tv;
+    int q_a = 0, q_b = 0;
+    if (ha) { ta = tasks[pt.a]; q_a = ta.q_len; }
+    if (hb) { tb = tasks[pt.b]; q_b = tb.q_len; }
+    const LadderRegion reg = regs[tv.region];
+    const int kmin = (ha && hb) ? min(ta.kmin, tb.kmin) : tv.kmin;
+    const int kmax = (ha && hb) ? max(ta.kmax, tb.kmax) : tv.kmax;
     uint4* bsm = prof + StripeCfg<R>::PROF_INT4;
     uint2* rungs = prung + pt.rung_off;
     // junction vectors, defaults: right part empty (score 0, no gap state) for rows of the read, void below it
@@ -498,6 +560,7 @@ __device__ __forceinline__ void pair3_task(const Pair3& pt, const LadderTask* __
         Sweep<R, kPB> sw;
         sw.prof = prof; sw.twords = pool + reg.rev_word; sw.t_len = reg.n_right; sw.lane = lane;
         sw.mark_col = -1; sw.bvec = bsm; sw.q_a = q_a; sw.q_b = q_b;
+        sw.col0 = 0; sw.resume = nullptr; sw.save = nullptr; sw.save_col = -1;
         sw.run(one, four, 0);
         const u32 ra = __reduce_max_sync(kFull, sw.best >> 16), rb = __reduce_max_sync(kFull, sw.best & 0xffffu);
         rcand = pk2((int)ra + kBias + 1, (int)rb + kBias + 1);      // forward part empty: score 0, unmarked
@@ -510,7 +573,11 @@ __device__ __forceinline__ void pair3_task(const Pair3& pt, const LadderTask* __
         sw.prof = prof; sw.twords = pool + reg.fwd_word; sw.t_len = reg.n_left + reg.m * kmax; sw.lane = lane;
         sw.mark_col = reg.n_left - 1; sw.bsm = bsm; sw.rung_out = rungs;
         sw.m = reg.m; sw.jnext = reg.n_left + reg.m * kmin; sw.kcnt = 0;
-        sw.run(one, four, sw.jnext - 1);
+        sw.save = nullptr; sw.save_col = -1;
+        const bool resumes = qstate && pt.state_off >= 0;
+        sw.col0 = resumes ? reg.n_left - 1 : 0;
+        sw.resume = resumes ? qstate + (size_t)pt.state_off * 32 : nullptr;
+        sw.run(one, four, sw.jnext - 1 - sw.col0);
     }
     __syncwarp();
     // selection per read (nanoRepeat_bam.py:423-431) over its own rungs
@@ -555,10 +622,10 @@ __device__ __forceinline__ void pair3_dispatch(int r, const Pair3& pt, const Lad
                                                const uint32_t* __restrict__ qpool, const uint32_t* __restrict__ pool,
                                                const LadderRegion* __restrict__ regs, uint4* prof, int lane, u32 one,
                                                unsigned four, int min_score, uint2* prung, int4* sel, int* redo_count,
-                                               int32_t* redo) {
-    if (r == R) { pair3_task<R>(pt, tasks, qpool, pool, regs, prof, lane, one, four, min_score, prung, sel, redo_count, redo); return; }
+                                               int32_t* redo, const u32* __restrict__ qstate) {
+    if (r == R) { pair3_task<R>(pt, tasks, qpool, pool, regs, prof, lane, one, four, min_score, prung, sel, redo_count, redo, qstate); return; }
     if constexpr (R < kMaxRPair3)
-        pair3_dispatch<R + 1>(r, pt, tasks, qpool, pool, regs, prof, lane, one, four, min_score, prung, sel, redo_count, redo);
+        pair3_dispatch<R + 1>(r, pt, tasks, qpool, pool, regs, prof, lane, one, four, min_score, prung, sel, redo_count, redo, qstate);
 }
 
 // Round 3: the batch's 32-bit entries (stripes of long reads, reads without an anchor) and then its pairs, one
@@ -568,7 +635,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock, 1)
 pair_ladder_kernel(const Pair3* __restrict__ pairs, Deal dl, const LadderTask* __restrict__ tasks, RestArgs ra,
                    const uint32_t* __restrict__ qpool, const uint32_t* __restrict__ pool,
                    const LadderRegion* __restrict__ regs, ScoreW scw, int* counter,
-                   int smem_stride, uint2* prung, int4* out, int4* sel, int* redo_count, int32_t* redo) {
+                   int smem_stride, uint2* prung, int4* out, int4* sel, int* redo_count, int32_t* redo,
+                   const u32* __restrict__ qstate) {
     extern __shared__ uint4 psmem[];
     const ScoreView<true> sc(scw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -582,9 +650,13 @@ pair_ladder_kernel(const Pair3* __restrict__ pairs, Deal dl, const LadderTask* _
             continue;
         }
         const Pair3 pt = pairs[i - ra.n_order];
-        int q = tasks[pt.a].q_len;
-        if (pt.b >= 0) q = max(q, tasks[pt.b].q_len);
-        pair3_dispatch<kMinR>(pair_rows(q), pt, tasks, qpool, pool, regs, prof, lane, (u32)sc.one, sc.four, sc.min_score, prung, sel, redo_count, redo);
+        int rows = pt.R;
+        if (rows <= 0) {
+            int q = pt.a >= 0 ? tasks[pt.a].q_len : 0;
+            if (pt.b >= 0) q = max(q, tasks[pt.b].q_len);
+            rows = pair_rows(q);
+        }
+        pair3_dispatch<kMinR>(rows, pt, tasks, qpool, pool, regs, prof, lane, (u32)sc.one, sc.four, sc.min_score, prung, sel, redo_count, redo, qstate);
     }
 }
 

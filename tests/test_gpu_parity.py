@@ -451,8 +451,12 @@ def test_round2_flags_kind_equals_oracle(engine, oracle, seed, n_left, m, T, n_r
         exact = b.commit().run().fetch_alns()
     _assert_same(exact, ref, f"round-2 exact kind, seed {seed}")
     assert np.array_equal(score, ref["score"]), seed
-    assert np.array_equal(tend, ref["tend"]), seed
-    live = ref["score"] > 0
+    # tend and the predicate are exact wherever the span test (:373) can pass, i.e. tend >= |left|; an alignment that
+    # ends before the repeat is reported as such (some tend < |left|), which is all the selection needs to drop it
+    spans = ref["tend"] >= n_left
+    assert np.array_equal(tend[spans], ref["tend"][spans]), seed
+    assert (tend[~spans] < max(n_left, 1)).all(), seed
+    live = (ref["score"] > 0) & spans
     assert np.array_equal(inside[live], (ref["tstart"] <= n_left)[live]), seed
 
 
@@ -510,3 +514,59 @@ def test_paired_and_long_reads_in_one_batch(engine, oracle):
             sel = ks[(a["score"] == t) & spans] if t > 0 else ks[:0]
             assert (int(got[2][pos]), int(got[1][pos]), int(got[0][pos])) == (t, len(sel), int(sel.sum())), (motif, r)
             pos += 1
+
+
+def test_round3_resumed_from_round2_state_equals_fresh(engine, oracle):
+    """The production flow (round 3 over a round-2 batch's reads, forward sweeps resumed from the DP state round 2 kept
+    at the end of the left anchor) == fresh round-3 batches == the oracle's selection; reads round 2 gave no size keep
+    their half of the pair empty."""
+    from nanorepeat_b200 import synth
+    rng = np.random.default_rng(17)
+    sc = engine.get_preset("ont")
+    regs = synth.config1(seed=31, n_regions=4, reads_per_region=15) + synth.config2(seed=32, n_reads=41)
+    b2 = engine.Batch.begin(sc, "round2_flags")
+    Ts = []
+    for reg in regs:
+        m = len(reg.repeat_unit_seq)
+        T = int(max(d / m for d in reg.dist_between_anchors) * 1.5) + 1
+        Ts.append(T)
+        b2.add_round2(reg.left_anchor_seq, reg.repeat_unit_seq, T, reg.core_seqs)
+    b2.commit().run().fetch_round2()
+    b3 = engine.Batch.begin_round3_from(b2)
+    fresh = engine.Batch.begin(sc, "round3")
+    keep_all, refs = [], []
+    for i, reg in enumerate(regs):
+        n = len(reg.core_seqs)
+        kmin = np.array([max(0, k - int(rng.integers(3, 16))) for k in reg.true_sizes], np.int32)
+        kmax = np.array([k + int(rng.integers(3, 16)) for k in reg.true_sizes], np.int32)
+        skip = rng.random(n) < 0.2
+        kmin[skip], kmax[skip] = 0, -1
+        b3.add_round3_reuse(i, reg.right_anchor_seq, kmin, kmax)
+        keep = np.flatnonzero(~skip)
+        keep_all.append(~skip)
+        cores = [reg.core_seqs[j] for j in keep]
+        fresh.add_round3(reg.left_anchor_seq, reg.right_anchor_seq, reg.repeat_unit_seq, cores, kmin[keep], kmax[keep])
+        refs.append((oracle.align_ladders(cores, reg.left_anchor_seq, reg.right_anchor_seq, reg.repeat_unit_seq,
+                                          kmin[keep], kmax[keep], n_threads=oracle.max_threads()), kmin[keep], reg))
+    li = b3.commit().launch_info()
+    assert li["n_pairs"] > 0
+    got = b3.run().fetch_round3()
+    exp = fresh.commit().run().fetch_round3()
+    keep_all = np.concatenate(keep_all)
+    for g, e in zip(got, exp):
+        assert np.array_equal(g[keep_all], e)
+        assert not g[~keep_all].any()
+    pos = 0
+    for (ref, roff), kmin, reg in refs:
+        nl, nr_, m = len(reg.left_anchor_seq), len(reg.right_anchor_seq), len(reg.repeat_unit_seq)
+        for r in range(len(kmin)):
+            lo, hi = int(roff[r]), int(roff[r + 1])
+            ks = np.arange(hi - lo) + int(kmin[r])
+            a = ref[lo:hi]
+            spans = (a["score"] > 0) & ((nl + m * ks + nr_) - a["tend"] < nr_) & (a["tstart"] < nl)
+            ok = a["score"] >= sc.min_dp_score
+            t = int(a["score"][ok].max()) if ok.any() else 0
+            sel = ks[(a["score"] == t) & spans] if t > 0 else ks[:0]
+            assert (int(exp[2][pos]), int(exp[1][pos]), int(exp[0][pos])) == (t, len(sel), int(sel.sum())), (reg.name, r)
+            pos += 1
+    b2.close(); b3.close(); fresh.close()
