@@ -662,8 +662,8 @@ int launch_rest(nr_batch* b, cudaStream_t st, const nr::ScoreW& k, const int32_t
     const nr::RestArgs ra = rest_args(b, order, count);
     int rc;
     if (L.ladder) {
-        auto fn = b->flag ? (L.fixed ? nr::ladder_kernel<true, true> : nr::ladder_kernel<false, true>)
-                          : (L.fixed ? nr::ladder_kernel<true, false> : nr::ladder_kernel<false, false>);
+        if (!L.fixed) return fail(NR_ERR_ARG, "the ladder kernels are built for map-ont scoring only");
+        auto fn = b->flag ? nr::ladder_kernel<true, true> : nr::ladder_kernel<true, false>;
         const int stride = ladder_smem_int4(R);
         const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
         if ((rc = prepare_kernel((const void*)fn, smem))) return rc;
@@ -689,6 +689,13 @@ int run_batch(nr_batch* b, cudaStream_t st) {
         CUDA_TRY(cudaStreamWaitEvent(st, b->ev_uploaded, 0));
         if (b->qsrc) CUDA_TRY(cudaStreamWaitEvent(st, b->qsrc->ev_uploaded, 0));
     }
+    bool resumes = false;
+    for (const nr::pr::Pair3& p : b->pairs3) resumes = resumes || p.state_off >= 0;
+    if (resumes) {
+        // forward sweeps take over the DP state the round-2 batch's kernel kept: it must have run, and be done first
+        if (!b->qsrc->ran) return fail(NR_ERR_ARG, "nr_batch_run: the round-2 batch this round-3 batch resumes from has not been run");
+        if (b->qsrc->run_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, b->qsrc->ev_done, 0));
+    }
     // counters: [0] main launch, [2] length of the redo list, [3] redo launch
     CUDA_TRY(cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(int), st));
     if (b->flags_bytes) CUDA_TRY(cudaMemsetAsync(b->d_flags, 0, b->flags_bytes, st));
@@ -703,22 +710,24 @@ int run_batch(nr_batch* b, cudaStream_t st) {
     if (L.n_pairs) {
         // one persistent launch: the batch's 32-bit entries (long reads cut into stripes, ...) first, then its pairs
         const nr::RestArgs ra = rest_args(b, b->d_order, L.count);
+        int wpb = kWarpsPerBlock;
+        if (const char* e = getenv("NR_WPB")) wpb = std::max(4, std::min(kWarpsPerBlock, atoi(e)));   // tuning
         const int blocks = std::max(1, std::min(g_ctx.sm_count, L.count + L.n_pairs));
-        nr::pr::Deal deal = nr::pr::make_deal(L.count, L.n_pairs, kWarpsPerBlock, blocks);
+        nr::pr::Deal deal = nr::pr::make_deal(L.count, L.n_pairs, wpb, blocks);
         if (getenv("NR_PLAIN_DEAL")) deal.nb_long = -1;      // tuning / debugging
         CUDA_TRY(mark(2, st));
         if (!b->pairs2.empty()) {
             const int stride = exact_smem_int4(std::max(L.pair_R, L.R));
-            const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
+            const size_t smem = (size_t)wpb * stride * sizeof(int4);
             if ((rc = prepare_kernel((const void*)nr::pr::pair_round2_kernel, smem))) return rc;
-            nr::pr::pair_round2_kernel<<<blocks, kWarpsPerBlock * 32, smem, st>>>(
+            nr::pr::pair_round2_kernel<<<blocks, wpb * 32, smem, st>>>(
                 static_cast<const nr::pr::Pair2*>(b->d_pairs), deal, b->d_tasks, ra, b->d_pool, k, b->d_counters, stride, b->d_out,
                 b->d_state);
         } else {
             const int stride = ladder_smem_int4(std::max(L.pair_R, L.R));
-            const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
+            const size_t smem = (size_t)wpb * stride * sizeof(int4);
             if ((rc = prepare_kernel((const void*)nr::pr::pair_ladder_kernel, smem))) return rc;
-            nr::pr::pair_ladder_kernel<<<blocks, kWarpsPerBlock * 32, smem, st>>>(
+            nr::pr::pair_ladder_kernel<<<blocks, wpb * 32, smem, st>>>(
                 static_cast<const nr::pr::Pair3*>(b->d_pairs), deal, b->d_ltasks, ra, b->qsrc ? b->qsrc->d_pool : b->d_pool,
                 b->d_pool, b->d_lregs, k, b->d_counters, stride, b->d_prung, b->d_out, b->d_sel, b->d_counters + 2, b->d_redo,
                 b->qsrc ? b->qsrc->d_state : nullptr);
@@ -969,9 +978,12 @@ nr_batch* new_batch(const nr_scoring_t* sc, BatchKind kind) {
     }
     b->kind = kind;
     b->sc = *sc;
-    b->ladder = kind == KIND_ROUND3 && g_ladder_mode.load() != 0;
-    b->flag = kind == KIND_ROUND3 && g_ladder_mode.load() >= 2;
-    b->pair = kind == KIND_ROUND3 && g_ladder_mode.load() == 3;
+    // the shared-sweep ladder kernels exist for the reference's scoring only (tk.py:502-517: every preset is map-ont);
+    // any other scoring scores every rung as its own rectangle (mode 0), which the 32-bit exact kernel does for any values
+    const int mode = is_map_ont(*sc) ? g_ladder_mode.load() : 0;
+    b->ladder = kind == KIND_ROUND3 && mode != 0;
+    b->flag = kind == KIND_ROUND3 && mode >= 2;
+    b->pair = kind == KIND_ROUND3 && mode == 3;
     return b;
 }
 
