@@ -182,7 +182,9 @@ bool pack_seq(const char* s, int len, uint32_t* w) {
 // fn(i) for i in [0, n) on a few host threads (packing thousands of reads is the host's largest cost per call)
 template <class F>
 void parallel_for(int n, int grain, F fn) {
-    int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u);
+    // one process per GPU shares the host cores with its siblings (torchrun exports LOCAL_WORLD_SIZE)
+    static const int share = [] { const char* e = getenv("LOCAL_WORLD_SIZE"); return e && atoi(e) > 0 ? atoi(e) : 1; }();
+    int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency() / (unsigned)share), 8u);
     nt = std::min(nt, std::max(1, n / std::max(1, grain)));
     if (nt <= 1) { for (int i = 0; i < n; ++i) fn(i); return; }
     std::vector<std::thread> th;

@@ -240,9 +240,11 @@ struct Sweep {
 
     // TRACK (kP2): per half the step of the last strict improvement of the score class; without it (the columns an
     // alignment that passes the span test cannot end in) only the running maximum word.
-    template <bool FAST, bool TRACK>
+    // FAST: every lane is inside the matrix, no bounds checks.  SPECIAL (with FAST): the step may still hold a lane at a
+    // junction, at the last marked column or at the column whose state is kept -- the guard-free body with those checks.
+    template <bool FAST, bool TRACK, bool SPECIAL = false>
     __device__ __forceinline__ void step(int st, u32 one, unsigned four) {
-        const bool zone = !FAST && MODE == kPF && st >= zone_start;     // uniform
+        const bool zone = MODE == kPF && (FAST ? SPECIAL : st >= zone_start);     // uniform
         constexpr int CH = StripeCfg<R>::CH;
         u32 hup = __shfl_up_sync(kFull, h_out, 1);
         u32 f1 = __shfl_up_sync(kFull, f1_out, 1);
@@ -263,6 +265,7 @@ struct Sweep {
             const uint4* pp = reinterpret_cast<const uint4*>(prof_lane + tb * (unsigned)(CH * 512));
             const u32 hd = hup_prev;
             hup_prev = hup;
+            constexpr bool kChecks = !FAST || SPECIAL;
             const bool last_col = !FAST && MODE == kPB && jj == t_len - 1;
             if (MODE == kPB && !FAST && last_col) {      // E(i', n_right): the gap states entering the last column
                 const int brow0 = lane * R;
@@ -287,7 +290,7 @@ struct Sweep {
                 bestc = nb;
                 if (x > 0xffffu) { st_hi = st; raw_hi = cm; }
                 if (x & 0xffffu) { st_lo = st; raw_lo = cm; }
-                if (!FAST && save && jj == save_col) {      // the state round 3 resumes from
+                if (kChecks && save && jj == save_col) {    // the state round 3 resumes from
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         __stcg(&save[r * 32 + lane], H[r]);
@@ -319,7 +322,7 @@ struct Sweep {
                 jnext += m;
                 ++kcnt;
             }
-            if (kMarks && !FAST && jj == mark_col) mark_started_inside();
+            if (kMarks && kChecks && jj == mark_col) mark_started_inside();
         }
     }
 
@@ -331,14 +334,14 @@ struct Sweep {
         }
     }
 
-    template <bool TRACK>
+    template <bool TRACK, bool SPECIAL = false>
     __device__ __forceinline__ void fast_until(int& st, int end, u32 one, unsigned four) {
         for (; st + 16 <= end; st += 16) {       // st is a multiple of 16 here
             refill();
 #pragma unroll 1
             for (int b = 0; b < 16; b += 4) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) step<true, TRACK>(st + b + u, one, four);
+                for (int u = 0; u < 4; ++u) step<true, TRACK, SPECIAL>(st + b + u, one, four);
             }
         }
     }
@@ -349,20 +352,19 @@ struct Sweep {
         zone_start = zone_start_;
         const int n = t_len - col0;              // columns swept
         const int nsteps = n + 31;
-        int fast_end = ((n - 1) >> 4) << 4;
-        if (MODE == kPF) fast_end = min(fast_end, (zone_start >> 4) << 4);
+        const int inside_end = ((n - 1) >> 4) << 4;     // steps 31 <= st < inside_end: every lane is inside the matrix
         const int mc = mark_col - col0;          // the last marked column, in steps of lane 0
         int st = 0;
         slow_until(st, min(32, nsteps), one, four);
-        if (kMarks && mc >= 0) {
-            // guarded steps while the lanes pass the last marked column (kP2: from two columns earlier on, where the
-            // state is kept for round 3 and the tracked columns begin)
-            const int zs = MODE == kP2 ? max(mc - 2, 0) : mc;
-            if (MODE == kP2) {
+        if (MODE == kPB) {
+            fast_until<true>(st, inside_end, one, four);
+        } else if (MODE == kP2) {
+            if (mc >= 0) {
                 // columns below |left| - 2: an alignment ending there fails the span test whatever its tend, so only the
                 // running maximum matters; it is folded into the tracked class once, marked as "ended too early"
+                const int zs = max(mc - 2, 0);
                 const int before = st;
-                fast_until<false>(st, min(fast_end, (zs >> 4) << 4), one, four);
+                fast_until<false>(st, min(inside_end, (zs >> 4) << 4), one, four);
                 if (st != before) {
                     const u32 nb = __vmaxu2(bestc, best | kOnes);
                     const u32 x = nb ^ bestc;
@@ -370,12 +372,17 @@ struct Sweep {
                     if (x > 0xffffu) { st_hi = lane; raw_hi = 0; }       // column 0: tend = 1
                     if (x & 0xffffu) { st_lo = lane; raw_lo = 0; }
                 }
-            } else {
-                fast_until<true>(st, min(fast_end, (zs >> 4) << 4), one, four);
+                // the lanes pass the kept column and the last marked column: guarded steps (the guard-free body with
+                // those two checks unrolled four times measured slower here, unlike in the junction zone below)
+                slow_until(st, min(nsteps, ((mc + 32 + 15) >> 4) << 4), one, four);
             }
-            slow_until(st, min(nsteps, ((mc + 32 + 15) >> 4) << 4), one, four);
+            fast_until<true>(st, inside_end, one, four);
+        } else {
+            // plain steps up to the first junction / marked column, then guard-free steps that look for both
+            const int first = min(zone_start, mc >= 0 ? mc : zone_start);
+            fast_until<true>(st, min(inside_end, (first >> 4) << 4), one, four);
+            fast_until<true, true>(st, inside_end, one, four);
         }
-        fast_until<true>(st, fast_end, one, four);
         slow_until(st, nsteps, one, four);
     }
 };

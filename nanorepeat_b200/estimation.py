@@ -81,12 +81,14 @@ def _round2_finish(ctx):
         score, tend, inside = all_score[pos:pos + n], all_tend[pos:pos + n], all_inside[pos:pos + n]
         pos += n
         ok = (score >= min_score) & inside & (tend >= n_left)                   # no PAF line below -s; span test :373
-        r2 = ((tend - n_left).astype(np.float64) / np.float64(len(motif))).tolist()   # :375
+        r2_arr = (tend - n_left).astype(np.float64) / np.float64(len(motif))    # :375
         reads = rr.read_dict
-        for name, good, v in zip(qnames, ok.tolist(), r2):
+        for name, good, v in zip(qnames, ok.tolist(), r2_arr.tolist()):
             if good:
                 reads[name].round2_repeat_size = v
-        rr._nr_round2 = (b, idx, qnames)
+        # the committed batch (round 3 reuses its packed reads and kept DP state) and what round 2 just decided, so that
+        # a round 3 issued right behind it (estimate_regions) need not read 5 000 attributes back
+        rr._nr_round2 = (b, idx, qnames, ok, r2_arr)
 
 
 def _round2_many(data_type, repeat_regions):
@@ -155,20 +157,27 @@ def _assign_round3(reads, sum_k, n_k, top):
         # s == 0: no PAF line at all (:421) -> untouched
 
 
-def _round3_reuse_launch(fast_mode, batch, rrs):
-    """Launch of round 3 over the reads a committed round-2 batch already holds on the device."""
+def _round3_reuse_launch(fast_mode, batch, rrs, trust_round2=False):
+    """Launch of round 3 over the reads a committed round-2 batch already holds on the device.
+    trust_round2: the caller ran round 2 itself just now (estimate_regions), so the sizes round 2 assigned are taken from
+    its arrays instead of being read back from the Read objects (which a caller of the two separate operators may
+    have edited in between, as the reference's attributes allow)."""
     b3 = engine.Batch.begin_round3_from(batch)
     all_reads = []
     for rr in rrs:
-        _b, idx, qnames = rr._nr_round2
+        _b, idx, qnames, ok2, r2_arr = rr._nr_round2
         reads = rr.read_dict
         rl = [reads[n] for n in qnames]
-        r2 = [rd.round2_repeat_size for rd in rl]
-        valid = np.array([v is not None for v in r2], dtype=bool)               # :460
+        if trust_round2:
+            valid, r2_valid = ok2, r2_arr[ok2]
+        else:
+            r2 = [rd.round2_repeat_size for rd in rl]
+            valid = np.array([v is not None for v in r2], dtype=bool)           # :460
+            r2_valid = [v for v in r2 if v is not None]
         kmin = np.zeros(len(rl), dtype=np.int32)
         kmax = np.full(len(rl), -1, dtype=np.int32)
         if valid.any():
-            lo, hi = ladder_bounds_array([v for v in r2 if v is not None], fast_mode)   # :463-472
+            lo, hi = ladder_bounds_array(r2_valid, fast_mode)                   # :463-472
             kmin[valid], kmax[valid] = lo, hi
         b3.add_round3_reuse(idx, rr.right_anchor_seq, kmin, kmax)
         all_reads.extend(rd if ok else None for rd, ok in zip(rl, valid.tolist()))
@@ -263,7 +272,7 @@ def estimate_regions(regions, data_type=None, fast_mode=False):
             _scoring_for(dt)
             live = [rr for rr in g if getattr(rr, "_nr_round2", None) is not None]
             if live and engine.ladder_mode() != 0:
-                r3.append(_round3_reuse_launch(fast_mode, live[0]._nr_round2[0], live))
+                r3.append(_round3_reuse_launch(fast_mode, live[0]._nr_round2[0], live, trust_round2=True))
             else:
                 _round3_many(dt, fast_mode, g)
         for ctx in r3:
