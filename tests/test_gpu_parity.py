@@ -570,3 +570,49 @@ def test_round3_resumed_from_round2_state_equals_fresh(engine, oracle):
             assert (int(exp[2][pos]), int(exp[1][pos]), int(exp[0][pos])) == (t, len(sel), int(sel.sum())), (reg.name, r)
             pos += 1
     b2.close(); b3.close(); fresh.close()
+
+
+@pytest.mark.parametrize("rows", ["4", "6", "12", ""])
+def test_many_long_reads_on_concurrent_stripes(engine, oracle, rows, monkeypatch):
+    """Stress for the cooperative long-read path: dozens of multi-stripe tasks in flight at once, at every stripe
+    height the host may pick (NR_COOP_ROWS pins it; "" = the host's own choice), exact records and ladders against the
+    oracle.  A lost or stale boundary entry / token would show up as a wrong score here."""
+    if rows:
+        monkeypatch.setenv("NR_COOP_ROWS", rows)
+    else:
+        monkeypatch.delenv("NR_COOP_ROWS", raising=False)
+    rng = random.Random(4242)
+    qs, ts = [], []
+    for i in range(48):
+        ql = rng.randint(520, 2600)
+        q = _rand_seq(rng, ql)
+        t = _rand_seq(rng, rng.randint(0, 300)) + _mutate(rng, q, rng.choice([0.02, 0.1])) + _rand_seq(rng, rng.randint(0, 300))
+        if i % 6 == 0:
+            t = _rand_seq(rng, rng.randint(600, 3000))       # unrelated
+        qs.append(q); ts.append(t)
+    sc = engine.get_preset("ont")
+    got = engine.score_tasks(qs, ts, sc)
+    ref = oracle.align_batch(qs, ts, n_threads=oracle.max_threads())
+    _assert_same(got, ref, f"long tasks, rows {rows!r}")
+    # ladders: long reads of one region, modes 3 (long reads take the 32-bit flag ladder inside the fused launch) and 1
+    left, right, motif = _rand_seq(rng, 300), _rand_seq(rng, 280), "GGGGCC"
+    cores, kmin, kmax = [], [], []
+    for i in range(20):
+        k = rng.randint(70, 330)
+        cores.append(_mutate(rng, left[-80:] + motif * k + right[:90], 0.06))
+        kmin.append(max(0, k - rng.randint(3, 20))); kmax.append(k + rng.randint(3, 20))
+    cores += [_mutate(rng, left[-50:] + motif * 9 + right[:60], 0.03) for _ in range(5)]      # short ones in the same batch
+    kmin += [2] * 5; kmax += [20] * 5
+    kmin, kmax = np.array(kmin, np.int32), np.array(kmax, np.int32)
+    ref, roff = oracle.align_ladders(cores, left, right, motif, kmin, kmax, n_threads=oracle.max_threads())
+    try:
+        for mode in (3, 1):
+            engine.set_ladder_mode(mode)
+            with engine.Batch.round3(sc, left, right, motif, cores, kmin, kmax) as b:
+                b.run()
+                if mode == 3:
+                    _assert_flag_ladder(b, ref, roff, kmin, 300, 280, 6, sc.min_dp_score, f"long ladders, rows {rows!r}", rungs_too=False)
+                else:
+                    _assert_same(b.fetch_alns(), ref, f"long ladders with coordinates, rows {rows!r}")
+    finally:
+        engine.set_ladder_mode(3)
