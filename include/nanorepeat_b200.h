@@ -178,6 +178,9 @@ nr_batch_t* nr_batch_create_round3(const nr_scoring_t* sc,
 nr_batch_t* nr_batch_begin(const nr_scoring_t* sc, int32_t kind);
 int nr_batch_add_round2(nr_batch_t* b, const char* left, int32_t n_left, const char* motif, int32_t motif_len,
                         int32_t T, int32_t n_reads, const char* cores_concat, const int64_t* core_off);
+/* The same with the reads as n_reads lines separated by '\n' (no offsets array: one pass less for a Python caller). */
+int nr_batch_add_round2_lines(nr_batch_t* b, const char* left, int32_t n_left, const char* motif, int32_t motif_len,
+                              int32_t T, int32_t n_reads, const char* lines, int64_t lines_len);
 int nr_batch_add_round3(nr_batch_t* b, const char* left, int32_t n_left, const char* right, int32_t n_right,
                         const char* motif, int32_t motif_len, int32_t n_reads, const char* cores_concat,
                         const int64_t* core_off, const int32_t* kmin, const int32_t* kmax);

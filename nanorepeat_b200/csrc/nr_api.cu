@@ -11,11 +11,16 @@
 #include "nr_pair_kernels.cuh"
 
 #include <algorithm>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <new>
 #include <string>
@@ -160,9 +165,16 @@ bool pack_seq(const char* s, int len, uint32_t* w) {
     unsigned bad = 0;
     int i = 0;
     for (; i + 16 <= len; i += 16) {
-        for (int j = 0; j < 16; ++j) bad |= g_bad.t[u[i + j]];
 #if defined(__x86_64__)
+        {   // 16 bases at a time: lower-case them, compare with 'a' 'c' 'g' 't'
+            const __m128i v = _mm_or_si128(_mm_loadu_si128(reinterpret_cast<const __m128i*>(u + i)), _mm_set1_epi8(0x20));
+            const __m128i ok = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(v, _mm_set1_epi8('a')), _mm_cmpeq_epi8(v, _mm_set1_epi8('c'))),
+                                            _mm_or_si128(_mm_cmpeq_epi8(v, _mm_set1_epi8('g')), _mm_cmpeq_epi8(v, _mm_set1_epi8('t'))));
+            bad |= (unsigned)_mm_movemask_epi8(ok) ^ 0xffffu;
+        }
         if (g_have_bmi2) { w[i >> 4] = pack16_bmi2(u + i); continue; }
+#else
+        for (int j = 0; j < 16; ++j) bad |= g_bad.t[u[i + j]];
 #endif
         uint32_t v = 0;
         for (int j = 0; j < 16; ++j) v |= ((u[i + j] >> 1) & 3u) << (30 - 2 * j);
@@ -250,7 +262,6 @@ struct nr_batch {
     size_t prung_bytes = 0;
     int32_t* d_redo = nullptr;                // round 3 pairs: reads to rescore on 32-bit flag words
     size_t redo_bytes = 0;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_t[6] = {};                 // nr_set_timing(1): start / end of the 32-bit, paired and redo launches
     bool timed[3] = {};
     int* h_redo_count = nullptr;              // pinned
@@ -341,6 +352,18 @@ nr::ScoreW score_words(const nr_scoring_t& sc) {
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// NR_TRACE=1: host-side phase times of plan_batch on stderr (where a commit's half millisecond goes)
+struct PhaseTrace {
+    const bool on = getenv("NR_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[nr trace] %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 bool is_map_ont(const nr_scoring_t& c) {
     return c.match == 2 && c.mismatch == 4 && c.gap_open1 == 4 && c.gap_ext1 == 2 && c.gap_open2 == 24 && c.gap_ext2 == 1;
 }
@@ -349,7 +372,11 @@ bool is_map_ont(const nr_scoring_t& c) {
 // share a warp, one per 16-bit half of the DP words (nr_pair_kernels.cuh).  key(i) orders the tasks.
 template <class Key, class Emit>
 void make_pairs(std::vector<int>& ids, Key key, Emit emit) {
-    std::sort(ids.begin(), ids.end(), [&](int x, int y) { return key(x) != key(y) ? key(x) > key(y) : x < y; });
+    // decreasing key, then increasing id: one 64-bit word per task, (key << 32) | ~id, sorted downwards
+    std::vector<uint64_t> w(ids.size());
+    for (size_t i = 0; i < ids.size(); ++i) w[i] = ((uint64_t)(uint32_t)key(ids[i]) << 32) | (uint32_t)~(uint32_t)ids[i];
+    std::sort(w.begin(), w.end(), std::greater<uint64_t>());
+    for (size_t i = 0; i < w.size(); ++i) ids[i] = (int)~(uint32_t)w[i];
     for (size_t i = 0; i < ids.size(); i += 2) emit(ids[i], i + 1 < ids.size() ? ids[i + 1] : -1);
 }
 
@@ -365,6 +392,7 @@ int plan_batch(nr_batch* b) {
     std::vector<int> task_R(n), task_ns(n), task_sweep(n), task_rungs(n, 0);
     const int max_r = ladder ? nr::kMaxRLadder : nr::kMaxRExact;
     const bool fixed = is_map_ont(b->sc);
+    PhaseTrace trace;
     for (int i = 0; i < n; ++i) {
         int q_len, t_len, t_sweep;
         if (ladder) {
@@ -393,6 +421,7 @@ int plan_batch(nr_batch* b) {
         task_sweep[i] = t_sweep;
         cost[i] = (long long)task_ns[i] * 32 * task_R[i] * t_len;
     }
+    trace.mark("task shapes");
     // ---- paired launch: two reads of one region per warp ----
     std::vector<char> paired(n, 0);
     std::vector<long long> pair_cost;
@@ -477,18 +506,24 @@ int plan_batch(nr_batch* b) {
         b->prung_bytes = sizeof(uint2) * (size_t)std::max<long long>(rung_off, 1);
         L.redo_R = L.pair_R;
     }
+    trace.mark("pairing");
     b->state_bytes = sizeof(uint32_t) * 32 * (size_t)state_off;
     L.n_pairs = (int)pair_cost.size();
     if (L.n_pairs) {            // pairs in decreasing cost: the tail of the persistent launch is made of the cheap ones
         std::vector<int> po(L.n_pairs);
-        for (int i = 0; i < L.n_pairs; ++i) po[i] = i;
-        std::sort(po.begin(), po.end(), [&](int x, int y) { return pair_cost[x] != pair_cost[y] ? pair_cost[x] > pair_cost[y] : x < y; });
+        {
+            std::vector<uint64_t> w(L.n_pairs);      // (cost << 24) | ~index: pair costs stay below 2^40, pairs below 2^24
+            for (int i = 0; i < L.n_pairs; ++i) w[i] = ((uint64_t)pair_cost[i] << 24) | (uint32_t)(0xffffff - i);
+            std::sort(w.begin(), w.end(), std::greater<uint64_t>());
+            for (int i = 0; i < L.n_pairs; ++i) po[i] = 0xffffff - (int)(w[i] & 0xffffff);
+        }
         if (!b->pairs2.empty()) { std::vector<nr::pr::Pair2> t(L.n_pairs); for (int i = 0; i < L.n_pairs; ++i) t[i] = b->pairs2[po[i]]; b->pairs2.swap(t); }
         else { std::vector<nr::pr::Pair3> t(L.n_pairs); for (int i = 0; i < L.n_pairs; ++i) t[i] = b->pairs3[po[i]]; b->pairs3.swap(t); }
         for (long long c : pair_cost) b->paired_cells += 2 * c;             // both halves of every word
         b->stats.executed_cells += b->paired_cells;
         L.pair_blocks = std::max(1, std::min(g_ctx.sm_count, L.n_pairs));
     }
+    trace.mark("pair order");
     // ---- the rest: one persistent launch of the 32-bit kernels.  Long reads are cut into stripes that run on
     // different warps at the same time (nr_kernels.cuh, CoopInfo); their entries come first, by decreasing cost, every
     // entry behind what it waits for; then the single-stripe tasks by decreasing cost ----
@@ -572,6 +607,7 @@ int plan_batch(nr_batch* b) {
     L.fixed = fixed;
     const size_t scratch_total = (size_t)data_off;
     b->flags_bytes = sizeof(int) * (size_t)flag_off;
+    trace.mark("32-bit entries");
     // ---- one device blob: [tasks | regions | order | pairs | pool (+4 slack words) | counters], staged in pinned memory ----
     const size_t task_bytes = ladder ? sizeof(nr::LadderTask) * n : sizeof(nr::Task) * n;
     const size_t reg_bytes = sizeof(nr::LadderRegion) * b->lregs.size();
@@ -610,6 +646,7 @@ int plan_batch(nr_batch* b) {
         if ((rc = cached_alloc((void**)&b->h_redo_count, 64, true))) return rc;
         *b->h_redo_count = 0;
     }
+    trace.mark("buffers (cached alloc)");
     char* h = static_cast<char*>(b->h_blob);
     char* d = static_cast<char*>(b->d_blob);
     if (task_bytes) memcpy(h, ladder ? (const void*)b->ltasks.data() : (const void*)b->tasks.data(), task_bytes);
@@ -630,6 +667,7 @@ int plan_batch(nr_batch* b) {
     b->d_coop_idx = reinterpret_cast<int32_t*>(d + off_cidx);
     b->d_pool = reinterpret_cast<uint32_t*>(d + off_pool);
     b->d_counters = reinterpret_cast<int*>(d + off_cnt);
+    trace.mark("blob staging (memcpy)");
     cudaStream_t st = g_ctx.stream;
     CUDA_TRY(cudaMemcpyAsync(d, h, b->blob_bytes, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(b->d_out, 0, b->out_bytes, st));
@@ -637,6 +675,7 @@ int plan_batch(nr_batch* b) {
     CUDA_TRY(cudaEventRecord(b->ev_uploaded, st));      // nr_batch_run on another stream waits for it; no host sync here
     b->stats.h2d_bytes = (int64_t)(task_bytes + reg_bytes + order_bytes + pair_bytes + coop_bytes + cidx_bytes + pool_bytes);
     b->stats.d2h_bytes = (int64_t)sizeof(int4) * (b->flag ? (int64_t)b->n_reads : (int64_t)b->n_out);
+    trace.mark("upload + memsets (async)");
     b->committed = true;
     return NR_OK;
 }
@@ -959,7 +998,7 @@ int add_round3(nr_batch* b, const char* left, int32_t n_left, const char* right,
 }
 
 void free_events(nr_batch* b) {
-    for (cudaEvent_t* e : {&b->ev_uploaded, &b->ev_done, &b->ev_fork, &b->ev_join, &b->ev_t[0], &b->ev_t[1], &b->ev_t[2],
+    for (cudaEvent_t* e : {&b->ev_uploaded, &b->ev_done, &b->ev_t[0], &b->ev_t[1], &b->ev_t[2],
                            &b->ev_t[3], &b->ev_t[4], &b->ev_t[5]})
         if (*e) { cudaEventDestroy(*e); *e = nullptr; }
 }
@@ -970,8 +1009,6 @@ nr_batch* new_batch(const nr_scoring_t* sc, BatchKind kind) {
     nr_batch* b = new (std::nothrow) nr_batch();
     if (!b) { fail(NR_ERR_NOMEM, "out of host memory"); return nullptr; }
     if (cudaEventCreateWithFlags(&b->ev_uploaded, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming) != cudaSuccess) {
         fail(NR_ERR_CUDA, "cudaEventCreate failed");
         free_events(b);
@@ -1111,6 +1148,36 @@ int nr_batch_add_round2(nr_batch_t* b, const char* left, int32_t n_left, const c
                         int32_t T, int32_t n_reads, const char* cores_concat, const int64_t* core_off) {
     if (n_reads > 0 && (!cores_concat || !core_off)) return fail(NR_ERR_ARG, "nr_batch_add_round2: NULL reads");
     ReadSrc src = {nullptr, nullptr, cores_concat, core_off};
+    return add_round2(b, left, n_left, motif, motif_len, T, n_reads, src);
+}
+
+// reads as one buffer of n_reads lines separated by '\n' (what "\n".join(cores) gives a Python caller without a second
+// pass for the lengths); a buffer with another number of lines is rejected like a bad base (a core held a newline)
+int nr_batch_add_round2_lines(nr_batch_t* b, const char* left, int32_t n_left, const char* motif, int32_t motif_len,
+                              int32_t T, int32_t n_reads, const char* lines, int64_t lines_len) {
+    if (n_reads < 0 || lines_len < 0 || (n_reads > 0 && !lines)) return fail(NR_ERR_ARG, "nr_batch_add_round2_lines: bad arguments");
+    std::vector<int64_t> off;
+    std::string flat;
+    if (n_reads > 0) {
+        off.reserve((size_t)n_reads + 1);
+        flat.resize((size_t)lines_len);
+        // offsets into the buffer with the separators squeezed out
+        int64_t out = 0, pos = 0;
+        off.push_back(0);
+        while (pos <= lines_len) {
+            const char* nl = pos < lines_len ? static_cast<const char*>(memchr(lines + pos, '\n', (size_t)(lines_len - pos))) : nullptr;
+            const int64_t end = nl ? nl - lines : lines_len;
+            memcpy(&flat[(size_t)out], lines + pos, (size_t)(end - pos));
+            out += end - pos;
+            off.push_back(out);
+            if (!nl) break;
+            pos = end + 1;
+        }
+        if ((int64_t)off.size() != (int64_t)n_reads + 1)
+            return fail(NR_ERR_BAD_BASE, "nr_batch_add_round2_lines: %lld lines for %d reads (a core holds a newline?)",
+                        (long long)off.size() - 1, n_reads);
+    }
+    ReadSrc src = {nullptr, nullptr, flat.data(), off.data()};
     return add_round2(b, left, n_left, motif, motif_len, T, n_reads, src);
 }
 

@@ -81,6 +81,9 @@ SYMBOLS = {
     "nr_batch_begin": (ctypes.c_void_p, [_scp, ctypes.c_int32]),
     "nr_batch_add_round2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p,
                                            ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_char_p, _i64p]),
+    "nr_batch_add_round2_lines": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p,
+                                                 ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                                 ctypes.c_int64]),
     "nr_batch_add_round3": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p,
                                            ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
                                            ctypes.c_char_p, _i64p, _i32p, _i32p]),
@@ -193,6 +196,13 @@ def _b(s):
     return s.encode() if isinstance(s, str) else s
 
 
+# const char* PyUnicode_AsUTF8AndSize(PyObject*, Py_ssize_t*): for an ASCII str this is its own buffer, valid while
+# the str is alive
+_utf8 = ctypes.pythonapi.PyUnicode_AsUTF8AndSize
+_utf8.restype = ctypes.c_void_p
+_utf8.argtypes = [ctypes.py_object, ctypes.POINTER(ctypes.c_ssize_t)]
+
+
 def score_tasks(queries, targets, sc):
     """Generic engine: (score, tstart, tend) for every (query, target) pair."""
     n = len(queries)
@@ -260,10 +270,19 @@ class Batch:
         return self
 
     def add_round2(self, left, motif, T, cores):
-        buf, off = _concat(cores)
         lb, mb = _b(left), _b(motif)
-        _check(lib().nr_batch_add_round2(self._h, lb, len(lb), mb, len(mb), int(T), len(cores), buf,
-                                         off.ctypes.data_as(_i64p)))
+        if cores and isinstance(cores[0], str):
+            # one join, no per-read lengths, no encode: the joined str's own (ASCII == UTF-8) buffer crosses the ABI
+            joined = "\n".join(cores)
+            size = ctypes.c_ssize_t()
+            ptr = _utf8(joined, ctypes.byref(size))
+            if not ptr:
+                raise ValueError("reads are not valid text")
+            _check(lib().nr_batch_add_round2_lines(self._h, lb, len(lb), mb, len(mb), int(T), len(cores), ptr, size.value))
+        else:
+            buf, off = _concat(cores)
+            _check(lib().nr_batch_add_round2(self._h, lb, len(lb), mb, len(mb), int(T), len(cores), buf,
+                                             off.ctypes.data_as(_i64p)))
         self._region_reads.append(len(cores))
         self.n_items += len(cores)
         return self

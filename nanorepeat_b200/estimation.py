@@ -21,8 +21,7 @@ def _scoring_for(data_type):
 
 
 def _cores_of(rr, qnames):
-    core_dict = rr.read_core_seq_dict
-    return [core_dict[n] for n in qnames]
+    return list(map(rr.read_core_seq_dict.__getitem__, qnames))
 
 
 def _round2_launch(data_type, repeat_regions):
@@ -49,8 +48,7 @@ def _round2_launch(data_type, repeat_regions):
             template_repeat_size = int(max_r1 + 10)
         # reads come from read_core_seq_dict, which is what the reference wrote to core_sequences.fastq (:311-321)
         core_dict = rr.read_core_seq_dict
-        qnames = list(reads) if len(core_dict) == len(reads) and all(n in core_dict for n in reads) \
-            else [n for n in reads if n in core_dict]
+        qnames = list(reads) if core_dict.keys() >= reads.keys() else [n for n in reads if n in core_dict]
         specs.append((rr.left_anchor_seq, rr.repeat_unit_seq, template_repeat_size))
         todo.append((rr, qnames))
     if not specs:
@@ -167,7 +165,7 @@ def _round3_reuse_launch(fast_mode, batch, rrs, trust_round2=False):
     for rr in rrs:
         _b, idx, qnames, ok2, r2_arr = rr._nr_round2
         reads = rr.read_dict
-        rl = [reads[n] for n in qnames]
+        rl = list(map(reads.__getitem__, qnames))
         if trust_round2:
             valid, r2_valid = ok2, r2_arr[ok2]
         else:
@@ -180,7 +178,7 @@ def _round3_reuse_launch(fast_mode, batch, rrs, trust_round2=False):
             lo, hi = ladder_bounds_array(r2_valid, fast_mode)                   # :463-472
             kmin[valid], kmax[valid] = lo, hi
         b3.add_round3_reuse(idx, rr.right_anchor_seq, kmin, kmax)
-        all_reads.extend(rd if ok else None for rd, ok in zip(rl, valid.tolist()))
+        all_reads += [rd if ok else None for rd, ok in zip(rl, valid.tolist())]
         del rr._nr_round2
     b3.commit().run()                                                           # was pymm2.main per read at :497
     return b3, all_reads
