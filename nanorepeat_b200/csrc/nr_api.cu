@@ -12,7 +12,7 @@
 
 #include <algorithm>
 #if defined(__x86_64__)
-#include <emmintrin.h>
+#include <tmmintrin.h>
 #endif
 #include <atomic>
 #include <chrono>
@@ -144,18 +144,23 @@ struct BadTable {
 const BadTable g_bad;
 
 #if defined(__x86_64__)
-__attribute__((target("bmi2"))) uint32_t pack16_bmi2(const unsigned char* u) {
-    uint64_t a, c;
-    memcpy(&a, u, 8);
-    memcpy(&c, u + 8, 8);
-    a = __builtin_bswap64(a);                         // first base -> highest byte -> highest bit pair
-    c = __builtin_bswap64(c);
-    return ((uint32_t)__builtin_ia32_pext_di(a, 0x0606060606060606ull) << 16) |
-           (uint32_t)__builtin_ia32_pext_di(c, 0x0606060606060606ull);
+// 16 bases -> one word, and their validity: lower-case and compare with "acgt"; (c >> 1) & 3 per byte; two multiply-adds
+// fold four codes into a byte (b0 * 64 + b1 * 16 + b2 * 4 + b3); a byte shuffle puts the four bytes MSB first.
+__attribute__((target("ssse3"))) inline uint32_t pack16_ssse3(const unsigned char* u, unsigned& bad) {
+    const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(u));
+    const __m128i l = _mm_or_si128(v, _mm_set1_epi8(0x20));
+    const __m128i ok = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(l, _mm_set1_epi8('a')), _mm_cmpeq_epi8(l, _mm_set1_epi8('c'))),
+                                    _mm_or_si128(_mm_cmpeq_epi8(l, _mm_set1_epi8('g')), _mm_cmpeq_epi8(l, _mm_set1_epi8('t'))));
+    bad |= (unsigned)_mm_movemask_epi8(ok) ^ 0xffffu;
+    const __m128i c = _mm_and_si128(_mm_srli_epi16(v, 1), _mm_set1_epi8(3));
+    const __m128i p = _mm_maddubs_epi16(c, _mm_set1_epi16(0x0104));
+    const __m128i q = _mm_madd_epi16(p, _mm_set1_epi32(0x00010010));
+    const __m128i r = _mm_shuffle_epi8(q, _mm_set_epi8(-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 0, 4, 8, 12));
+    return (uint32_t)_mm_cvtsi128_si32(r);
 }
-const bool g_have_bmi2 = __builtin_cpu_supports("bmi2");
+const bool g_have_ssse3 = __builtin_cpu_supports("ssse3");
 #else
-const bool g_have_bmi2 = false;
+const bool g_have_ssse3 = false;
 #endif
 
 // Pack one sequence: 16 bases per 32-bit word, MSB first (base i at bits 30 - 2*(i%16) of word i/16).
@@ -166,16 +171,9 @@ bool pack_seq(const char* s, int len, uint32_t* w) {
     int i = 0;
     for (; i + 16 <= len; i += 16) {
 #if defined(__x86_64__)
-        {   // 16 bases at a time: lower-case them, compare with 'a' 'c' 'g' 't'
-            const __m128i v = _mm_or_si128(_mm_loadu_si128(reinterpret_cast<const __m128i*>(u + i)), _mm_set1_epi8(0x20));
-            const __m128i ok = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(v, _mm_set1_epi8('a')), _mm_cmpeq_epi8(v, _mm_set1_epi8('c'))),
-                                            _mm_or_si128(_mm_cmpeq_epi8(v, _mm_set1_epi8('g')), _mm_cmpeq_epi8(v, _mm_set1_epi8('t'))));
-            bad |= (unsigned)_mm_movemask_epi8(ok) ^ 0xffffu;
-        }
-        if (g_have_bmi2) { w[i >> 4] = pack16_bmi2(u + i); continue; }
-#else
-        for (int j = 0; j < 16; ++j) bad |= g_bad.t[u[i + j]];
+        if (g_have_ssse3) { w[i >> 4] = pack16_ssse3(u + i, bad); continue; }
 #endif
+        for (int j = 0; j < 16; ++j) bad |= g_bad.t[u[i + j]];
         uint32_t v = 0;
         for (int j = 0; j < 16; ++j) v |= ((u[i + j] >> 1) & 3u) << (30 - 2 * j);
         w[i >> 4] = v;
@@ -829,8 +827,9 @@ struct ReadSrc {
     const int32_t* core_len;
     const char* concat;
     const int64_t* off;
+    int gap;        // bytes between two reads of `concat` that belong to neither (1: newline-separated lines)
     const char* ptr(int r) const { return cores ? cores[r] : concat + off[r]; }
-    long long len(int r) const { return cores ? (long long)core_len[r] : (long long)(off[r + 1] - off[r]); }
+    long long len(int r) const { return cores ? (long long)core_len[r] : (long long)(off[r + 1] - off[r] - gap); }
 };
 
 // Pack n_reads reads into the pool (in parallel); q_word[r] = first word of read r.
@@ -849,7 +848,8 @@ int add_reads(nr_batch* b, const ReadSrc& src, int n_reads, std::vector<uint32_t
     b->pool.words.resize(w, 0u);
     uint32_t* words = b->pool.words.data();
     std::atomic<int> bad{-1};
-    parallel_for(n_reads, 512, [&](int r) {
+    // ~0.1 us per read on one core: threads only pay for themselves from tens of thousands of reads on
+    parallel_for(n_reads, 8192, [&](int r) {
         if (!pack_seq(src.ptr(r), (int)src.len(r), words + q_word[r])) {
             int expect = -1;
             bad.compare_exchange_strong(expect, r);
@@ -1129,7 +1129,7 @@ int nr_batch_add_round3_reuse(nr_batch_t* b, int32_t region_index, const char* r
     if (region_index < 0 || region_index >= (int)src->regions.size())
         return fail(NR_ERR_ARG, "nr_batch_add_round3_reuse: region %d is not in the round-2 batch", region_index);
     const RegionInfo& g = src->regions[region_index];
-    ReadSrc none = {nullptr, nullptr, nullptr, nullptr};
+    ReadSrc none = {nullptr, nullptr, nullptr, nullptr, 0};
     return add_round3(b, g.left.data(), g.n_left, right, n_right, g.motif.data(), g.motif_len, g.n_reads, none, kmin, kmax,
                       src->tasks.data() + g.first_read);
 }
@@ -1147,7 +1147,7 @@ nr_batch_t* nr_batch_begin(const nr_scoring_t* sc, int32_t kind) {
 int nr_batch_add_round2(nr_batch_t* b, const char* left, int32_t n_left, const char* motif, int32_t motif_len,
                         int32_t T, int32_t n_reads, const char* cores_concat, const int64_t* core_off) {
     if (n_reads > 0 && (!cores_concat || !core_off)) return fail(NR_ERR_ARG, "nr_batch_add_round2: NULL reads");
-    ReadSrc src = {nullptr, nullptr, cores_concat, core_off};
+    ReadSrc src = {nullptr, nullptr, cores_concat, core_off, 0};
     return add_round2(b, left, n_left, motif, motif_len, T, n_reads, src);
 }
 
@@ -1156,28 +1156,22 @@ int nr_batch_add_round2(nr_batch_t* b, const char* left, int32_t n_left, const c
 int nr_batch_add_round2_lines(nr_batch_t* b, const char* left, int32_t n_left, const char* motif, int32_t motif_len,
                               int32_t T, int32_t n_reads, const char* lines, int64_t lines_len) {
     if (n_reads < 0 || lines_len < 0 || (n_reads > 0 && !lines)) return fail(NR_ERR_ARG, "nr_batch_add_round2_lines: bad arguments");
-    std::vector<int64_t> off;
-    std::string flat;
+    std::vector<int64_t> off;      // off[r] = start of line r, off[n_reads] = one past the last line's (virtual) newline
     if (n_reads > 0) {
         off.reserve((size_t)n_reads + 1);
-        flat.resize((size_t)lines_len);
-        // offsets into the buffer with the separators squeezed out
-        int64_t out = 0, pos = 0;
-        off.push_back(0);
-        while (pos <= lines_len) {
+        int64_t pos = 0;
+        for (;;) {
+            off.push_back(pos);
             const char* nl = pos < lines_len ? static_cast<const char*>(memchr(lines + pos, '\n', (size_t)(lines_len - pos))) : nullptr;
-            const int64_t end = nl ? nl - lines : lines_len;
-            memcpy(&flat[(size_t)out], lines + pos, (size_t)(end - pos));
-            out += end - pos;
-            off.push_back(out);
             if (!nl) break;
-            pos = end + 1;
+            pos = nl - lines + 1;
         }
+        off.push_back(lines_len + 1);
         if ((int64_t)off.size() != (int64_t)n_reads + 1)
             return fail(NR_ERR_BAD_BASE, "nr_batch_add_round2_lines: %lld lines for %d reads (a core holds a newline?)",
                         (long long)off.size() - 1, n_reads);
     }
-    ReadSrc src = {nullptr, nullptr, flat.data(), off.data()};
+    ReadSrc src = {nullptr, nullptr, lines, off.data(), 1};
     return add_round2(b, left, n_left, motif, motif_len, T, n_reads, src);
 }
 
@@ -1186,7 +1180,7 @@ int nr_batch_add_round3(nr_batch_t* b, const char* left, int32_t n_left, const c
                         const int64_t* core_off, const int32_t* kmin, const int32_t* kmax) {
     if (n_reads > 0 && (!cores_concat || !core_off)) return fail(NR_ERR_ARG, "nr_batch_add_round3: NULL reads");
     if (b && b->qsrc) return fail(NR_ERR_ARG, "nr_batch_add_round3: this batch reuses a round-2 batch's reads (nr_batch_add_round3_reuse)");
-    ReadSrc src = {nullptr, nullptr, cores_concat, core_off};
+    ReadSrc src = {nullptr, nullptr, cores_concat, core_off, 0};
     return add_round3(b, left, n_left, right, n_right, motif, motif_len, n_reads, src, kmin, kmax);
 }
 
@@ -1231,7 +1225,7 @@ nr_batch_t* nr_batch_create_round2(const nr_scoring_t* sc, const char* left, int
     if (n_reads > 0 && (!cores || !core_len)) { fail(NR_ERR_ARG, "nr_batch_create_round2: NULL reads"); return nullptr; }
     nr_batch* b = new_batch(sc, KIND_ROUND2);
     if (!b) return nullptr;
-    ReadSrc src = {cores, core_len, nullptr, nullptr};
+    ReadSrc src = {cores, core_len, nullptr, nullptr, 0};
     if (add_round2(b, left, n_left, motif, motif_len, T, n_reads, src) || plan_batch(b)) { nr_batch_destroy(b); return nullptr; }
     return b;
 }
@@ -1243,7 +1237,7 @@ nr_batch_t* nr_batch_create_round3(const nr_scoring_t* sc, const char* left, int
     if (n_reads > 0 && (!cores || !core_len)) { fail(NR_ERR_ARG, "nr_batch_create_round3: NULL reads"); return nullptr; }
     nr_batch* b = new_batch(sc, KIND_ROUND3);
     if (!b) return nullptr;
-    ReadSrc src = {cores, core_len, nullptr, nullptr};
+    ReadSrc src = {cores, core_len, nullptr, nullptr, 0};
     if (add_round3(b, left, n_left, right, n_right, motif, motif_len, n_reads, src, kmin, kmax) || plan_batch(b)) {
         nr_batch_destroy(b);
         return nullptr;
