@@ -616,3 +616,65 @@ def test_many_long_reads_on_concurrent_stripes(engine, oracle, rows, monkeypatch
                     _assert_same(b.fetch_alns(), ref, f"long ladders with coordinates, rows {rows!r}")
     finally:
         engine.set_ladder_mode(3)
+
+
+def test_config2_full_size_properties(engine, oracle):
+    """BASELINE.json's config 2 at full size (5 000 reads x 2 regions), through the operator API, by properties that do
+    not need the oracle on every read: (1) planted error-free reads recover their repeat count exactly and a core that
+    is its own template scores 2 * |core|; (2) the per-read results do not depend on the order of the reads (other
+    pairs, other warps, other pipeline groups); (3) a random sample agrees with the CPU oracle's full selection."""
+    import nanorepeat_b200 as nrb
+    from nanorepeat_b200 import synth
+    from oracle import selection
+    regs = synth.config2(seed=2, n_reads=5000)
+    rng = np.random.default_rng(99)
+    cag = regs[0]
+    planted = {}
+    for j, k in enumerate([5, 17, 18, 40, 55, 56, 90, 121, 150, 33] * 3):
+        name = f"perfect{j}"
+        core = cag.left_anchor_seq[-100:] + "CAG" * k + cag.right_anchor_seq[:100]
+        cag.read_names.append(name); cag.core_seqs.append(core); cag.dist_between_anchors.append(3 * k); cag.true_sizes.append(k)
+        planted[name] = (k, core)
+
+    def run(order_seed):
+        rrs = []
+        for reg in regs:
+            rr = nrb.RepeatRegion.from_synth(reg)
+            if order_seed is not None:
+                names = list(rr.read_dict)
+                np.random.default_rng(order_seed).shuffle(names)
+                rr.read_dict = {n: rr.read_dict[n] for n in names}
+            rrs.append(rr)
+        nrb.estimate_regions(rrs, "ont", False)
+        return rrs
+
+    a, b = run(None), run(7)
+    n_r3 = 0
+    for ra, rb in zip(a, b):
+        for name, rd in ra.read_dict.items():
+            other = rb.read_dict[name]
+            assert (rd.round1_repeat_size, rd.round2_repeat_size, rd.round3_repeat_size) == \
+                   (other.round1_repeat_size, other.round2_repeat_size, other.round3_repeat_size), name
+            n_r3 += rd.round3_repeat_size is not None
+    assert n_r3 > 9900
+    for name, (k, core) in planted.items():
+        rd = a[0].read_dict[name]
+        # round 2 has no right anchor to stop at (the first bases behind the repeat may extend it); round 3 is exact
+        assert k <= rd.round2_repeat_size <= k + 4 and float(rd.round3_repeat_size) == float(k), (name, k, rd.round2_repeat_size, rd.round3_repeat_size)
+    sc = engine.get_preset("ont")
+    cores = [c for _k, c in planted.values()]
+    tpls = [cag.left_anchor_seq + "CAG" * k + cag.right_anchor_seq for k, _c in planted.values()]
+    got = engine.score_tasks(cores, tpls, sc)
+    assert all(int(g["score"]) == 2 * len(c) and int(g["tstart"]) == 900 for g, c in zip(got, cores))
+    # a sample of 24 reads per region against the oracle's rounds 1-3
+    for reg, rr in zip(regs, a):
+        idx = rng.choice(len(reg.read_names), 24, replace=False)
+        # T is region-wide (nanoRepeat_bam.py:344): the oracle is told the region's longest distance between anchors
+        exp = selection.estimate_region(reg.left_anchor_seq, reg.right_anchor_seq, reg.repeat_unit_seq,
+                                        [reg.core_seqs[i] for i in idx], [reg.dist_between_anchors[i] for i in idx],
+                                        n_threads=oracle.max_threads(), max_dist=max(reg.dist_between_anchors))
+        for j, i in enumerate(idx):
+            rd = rr.read_dict[reg.read_names[i]]
+            g3 = rd.round3_repeat_size
+            assert rd.round2_repeat_size == exp["r2"][j], (reg.name, i)
+            assert (None if g3 is None else float(g3)) == (None if exp["r3"][j] is None else float(exp["r3"][j])), (reg.name, i)
