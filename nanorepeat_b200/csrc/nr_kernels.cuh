@@ -16,7 +16,10 @@
 // consecutive rows whose H / E1 / E2 state lives in registers.  The warp sweeps the target column by column as
 // a skewed wavefront (lane l works on column step - l); the bottom row's H, F1, F2 move to lane l + 1 by warp
 // shuffle.  Substitution scores come from a per-warp query profile in shared memory (one LDS.128 per four rows,
-// off the integer pipes).  Between stripes the bottom row goes through an L2-resident scratch row.
+// off the integer pipes).  A query longer than one stripe is cut into stripes that run on DIFFERENT warps at the same
+// time, each a few dozen columns behind the one above it; the bottom row travels through an L2-resident scratch row
+// as tagged 16-byte entries (CoopInfo, load_bnd below).  These 32-bit kernels are the second family beside the paired
+// u16x2 kernels of nr_pair_kernels.cuh: they take what needs coordinates, other scorings, or more than one stripe.
 //
 // Ladder kernel (round 3): all rungs k of one read share their prefix L + motif^k and their suffix R, so the warp
 // does ONE backward sweep (reversed read x reversed R, final column kept in shared memory) and ONE forward sweep
