@@ -1,0 +1,48 @@
+"""The joint path's rescoring / selection restatement (oracle/joint.py) against golden vectors
+produced by the reference's own functions (tests/golden/make_golden_joint.py)."""
+import json
+import os
+
+import pytest
+
+from oracle import joint
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def test_window_stats_equal_reference():
+    doc = _load("joint_window_cases.json")
+    assert len(doc["cases"]) > 400
+    for c in doc["cases"]:
+        got = joint.window_stats(c["cigar"], c["tstart"], c["tend"], c["a"], c["b"])
+        assert got == c["expected"], (c["cigar"], c["tstart"], c["a"], c["b"], c["note"], got, c["expected"])
+
+
+def test_known_window_answers():
+    # SURVEY.md section 4's probe and two hand-derived ones: +2 / -4 / gap -4 - 2 (l - 1), window edges as tk.py has them
+    assert joint.window_stats("100=", 0, 100, 10, 90)["score"] == 160
+    assert joint.window_stats("50=20D50=", 0, 120, 60, 100) == dict(num_match=30, num_mismatch=0, num_ins=0, num_del=10, score=60 - 4 - 2 * 9)
+    assert joint.window_stats("50=7I50=", 0, 100, 50, 100)["num_ins"] == 0          # insertion AT the window start: not counted
+    assert joint.window_stats("50=7I50=", 0, 100, 49, 100)["score"] == 2 * 51 - 4 - 2 * 6
+    with pytest.raises(ValueError):
+        joint.window_stats("", 0, 0, 0, 1)
+    with pytest.raises(ValueError):
+        joint.window_stats("10=3Q", 0, 10, 0, 5)
+
+
+def test_two_repeat_selection_equals_reference():
+    doc = _load("joint_selection_cases.json")
+    for c in doc["cases"]:
+        recs = []
+        for line in c["paf_lines"]:
+            col = line.split("\t")
+            k1, k2 = (int(x) for x in col[5].split("-"))
+            cigar = [x[5:] for x in col[12:] if x.startswith("cg:Z:")][0]
+            recs.append((col[0], k1, k2, int(col[6]), int(col[7]), int(col[8]), cigar))
+        got = joint.two_repeat_sizes(recs, c["left_len"], c["mid_len"], c["m1"], c["m2"])
+        assert {q: list(v) for q, v in got.items()} == c["expected"]
