@@ -678,11 +678,19 @@ int plan_batch(nr_batch* b) {
     return NR_OK;
 }
 
-// dynamic shared memory up to max_bytes, and the SM's L1 / shared split all the way to shared: a paired and a 32-bit
-// block must fit one SM together
-int prepare_kernel(const void* fn, size_t max_bytes) {
-    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_bytes));
+// Once per kernel: dynamic shared memory up to what a full block of the tallest stripes needs, and the SM's L1 / shared
+// split all the way to shared.  Set once to the maximum (not per launch to the launch's size): batches are launched
+// from several host threads, and a smaller value set by one thread would fail another thread's launch.
+int prepare_kernel(const void* fn, size_t launch_bytes) {
+    constexpr size_t kMaxDyn = (size_t)kWarpsPerBlock * 12 * 1024;      // 16 warps x (profile + junction vectors at R = 12)
+    if (launch_bytes > kMaxDyn) return fail(NR_ERR_ARG, "launch needs %zu bytes of shared memory", launch_bytes);
+    static std::mutex mu;
+    static std::vector<const void*> done;
+    std::lock_guard<std::mutex> lk(mu);
+    if (std::find(done.begin(), done.end(), fn) != done.end()) return NR_OK;
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    done.push_back(fn);
     return NR_OK;
 }
 

@@ -256,7 +256,8 @@ def estimate_regions(regions, data_type=None, fast_mode=False):
     """Rounds 1-3 over a list of RepeatRegion-like objects with one engine launch per round and group of regions (the
     reference runs the two operators per region inside quantify1repeat_from_bam, nanoRepeat_bam.py:675-679).
     The groups are software-pipelined: while the GPU scores one group the host packs the next and selects the
-    previous, so most of the host work hides behind the kernels.  Per-region semantics (T per region, ladder per read)
+    previous, so most of the host work hides behind the kernels (one host thread: a thread per group was measured and
+    is no faster, the Python passes serialise on the GIL).  Per-region semantics (T per region, ladder per read)
     are untouched.  Regions may carry their own .data_type; regions of one data type are batched together."""
     by_type = {}
     for rr in regions:
