@@ -263,6 +263,7 @@ struct nr_batch {
     cudaEvent_t ev_t[6] = {};                 // nr_set_timing(1): start / end of the 32-bit, paired and redo launches
     bool timed[3] = {};
     int* h_redo_count = nullptr;              // pinned
+    int* h_spin = nullptr;                    // pinned: the kernels' give-up flag after the run (long reads only)
     long long paired_cells = 0, rest_cells = 0;
     size_t n_out = 0;                         // records in d_out / h_out
     std::vector<int32_t> order;               // entries of the 32-bit launch: (task << 7) | code (nr_kernels.cuh)
@@ -745,6 +746,10 @@ int run_batch(nr_batch* b, cudaStream_t st) {
     }
     // counters: [0] main launch, [2] length of the redo list, [3] redo launch
     CUDA_TRY(cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(int), st));
+    if (b->flags_bytes) {          // long reads on concurrent stripes: clear the kernels' give-up flag (nr_kernels.cuh)
+        static const int zero = 0;
+        CUDA_TRY(cudaMemcpyToSymbolAsync(nr::g_spin_timeout, &zero, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+    }
     if (b->flags_bytes) CUDA_TRY(cudaMemsetAsync(b->d_flags, 0, b->flags_bytes, st));
     int launches = 0;
     int rc;
@@ -807,6 +812,10 @@ int run_batch(nr_batch* b, cudaStream_t st) {
     } else if (b->n_out) {
         CUDA_TRY(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(int4) * b->n_out, cudaMemcpyDeviceToHost, st));
     }
+    if (b->flags_bytes) {
+        if (!b->h_spin) { int rc2 = cached_alloc((void**)&b->h_spin, 64, true); if (rc2) return rc2; }
+        CUDA_TRY(cudaMemcpyFromSymbolAsync(b->h_spin, nr::g_spin_timeout, sizeof(int), 0, cudaMemcpyDeviceToHost, st));
+    }
     CUDA_TRY(cudaEventRecord(b->ev_done, st));
     b->stats.kernel_launches = launches;
     b->ran = true;
@@ -816,6 +825,8 @@ int run_batch(nr_batch* b, cudaStream_t st) {
 int fetch_raw(nr_batch* b) {
     if (!b->ran) return fail(NR_ERR_ARG, "batch was not run");
     CUDA_TRY(cudaEventSynchronize(b->ev_done));         // kernel + the copy nr_batch_run queued behind it
+    if (b->h_spin && *b->h_spin)
+        return fail(NR_ERR_CUDA, "a stripe of a long read gave up waiting for the stripe above it; the results of this batch are not valid");
     return NR_OK;
 }
 
@@ -1106,6 +1117,7 @@ void nr_batch_destroy(nr_batch_t* b) {
     cached_free(b->d_prung, b->prung_bytes, false);
     cached_free(b->d_redo, b->redo_bytes, false);
     cached_free(b->h_redo_count, 64, true);
+    cached_free(b->h_spin, 64, true);
     nr_batch* src = b->qsrc;
     free_events(b);
     delete b;
@@ -1295,8 +1307,8 @@ int nr_batch_fetch_round3(nr_batch_t* b, const int64_t* rung_offset, nr_rung_t* 
     if (rungs && b->pair) return fail(NR_ERR_ARG, "nr_batch_fetch_round3: the paired ladder (mode 3) keeps no rung records; use nr_set_ladder_mode(2)");
     if (b->flag) {
         // the kernel selected per read (nr_kernels.cuh, Sweep::select_rung); the rung records cross the bus only on request
-        if (!b->ran) return fail(NR_ERR_ARG, "batch was not run");
-        CUDA_TRY(cudaEventSynchronize(b->ev_done));
+        int rc0 = fetch_raw(b);
+        if (rc0) return rc0;
         if (rungs && b->n_out) {
             cudaStream_t st = b->run_stream ? b->run_stream : g_ctx.stream;
             CUDA_TRY(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(int4) * b->n_out, cudaMemcpyDeviceToHost, st));

@@ -166,9 +166,18 @@ __device__ __forceinline__ int peek_cols(const int* flag) {
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
     return v;
 }
+// Safety valve of every wait between stripes: what a stripe waits for is running or done (entries are dealt in
+// dependency order to resident blocks), so a wait ends within the producer's run time.  Should that ever not hold, the
+// warp gives up after a few seconds' worth of retries, raises this flag and runs on with what it has; the host turns
+// the flag into NR_ERR_CUDA instead of a hung GPU.
+__device__ int g_spin_timeout = 0;
+constexpr int kSpinLimit = 1 << 23;
 __device__ __forceinline__ void wait_cols(const int* flag, int need, int lane) {
     if (lane == 0)
-        while (peek_cols(flag) < need) __nanosleep(100);
+        for (int tries = 0; peek_cols(flag) < need; ++tries) {
+            if (tries > kSpinLimit) { g_spin_timeout = 1; break; }
+            __nanosleep(100);
+        }
     __syncwarp();
 }
 
@@ -454,6 +463,7 @@ struct Sweep {
                 // a stripe right behind its producer finds the entries it asked for 32 steps ago not written yet: it reads
                 // them again (one L2 round trip), falls back a little, and from then on its prefetches arrive valid
                 for (int tries = 0; !__all_sync(kFull, bcur.w == tag_in || cj >= t_len); ++tries) {
+                    if (tries > kSpinLimit) { g_spin_timeout = 1; break; }
                     if (tries > 3) __nanosleep(32);
                     bcur = load_bnd(&bnd_in[cj < t_len ? cj : t_len - 1]);
                 }
@@ -526,6 +536,7 @@ struct Sweep {
                         if (MULTI && top) {     // the token carries its tag in the upper half of x
                             ulonglong2 t = load_tok(&tok_in[kcnt]);
                             for (int tries = 0; (int)(t.x >> 32) != tag_in; ++tries) {
+                                if (tries > kSpinLimit) { g_spin_timeout = 1; break; }
                                 if (tries > 3) __nanosleep(32);
                                 t = load_tok(&tok_in[kcnt]);
                             }

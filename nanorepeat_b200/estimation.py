@@ -73,13 +73,18 @@ def _round2_finish(ctx):
         return
     b, todo, specs, min_score = ctx
     all_score, all_tend, all_inside = b.fetch_round2()
+    # selection over every read of every region at once: no PAF line below -s; span test :373; r2 :375 (the same IEEE
+    # division per element as the reference's float(tend - |left|) / |motif|)
+    counts = np.fromiter((len(q) for _rr, q in todo), dtype=np.int64, count=len(todo))
+    n_left_all = np.repeat(np.fromiter((len(left) for left, _m, _T in specs), dtype=np.int64, count=len(specs)), counts)
+    m_all = np.repeat(np.fromiter((len(motif) for _l, motif, _T in specs), dtype=np.float64, count=len(specs)), counts)
+    ok_all = (all_score >= min_score) & all_inside & (all_tend >= n_left_all)
+    r2_all = (all_tend - n_left_all).astype(np.float64) / m_all
     pos = 0
-    for idx, ((rr, qnames), (left, motif, _T)) in enumerate(zip(todo, specs)):
-        n, n_left = len(qnames), len(left)
-        score, tend, inside = all_score[pos:pos + n], all_tend[pos:pos + n], all_inside[pos:pos + n]
+    for idx, (rr, qnames) in enumerate(todo):
+        n = len(qnames)
+        ok, r2_arr = ok_all[pos:pos + n], r2_all[pos:pos + n]
         pos += n
-        ok = (score >= min_score) & inside & (tend >= n_left)                   # no PAF line below -s; span test :373
-        r2_arr = (tend - n_left).astype(np.float64) / np.float64(len(motif))    # :375
         reads = rr.read_dict
         for name, good, v in zip(qnames, ok.tolist(), r2_arr.tolist()):
             if good:
@@ -161,7 +166,7 @@ def _round3_reuse_launch(fast_mode, batch, rrs, trust_round2=False):
     its arrays instead of being read back from the Read objects (which a caller of the two separate operators may
     have edited in between, as the reference's attributes allow)."""
     b3 = engine.Batch.begin_round3_from(batch)
-    all_reads = []
+    per_region, valid_parts, r2_parts = [], [], []
     for rr in rrs:
         _b, idx, qnames, ok2, r2_arr = rr._nr_round2
         reads = rr.read_dict
@@ -171,13 +176,21 @@ def _round3_reuse_launch(fast_mode, batch, rrs, trust_round2=False):
         else:
             r2 = [rd.round2_repeat_size for rd in rl]
             valid = np.array([v is not None for v in r2], dtype=bool)           # :460
-            r2_valid = [v for v in r2 if v is not None]
-        kmin = np.zeros(len(rl), dtype=np.int32)
-        kmax = np.full(len(rl), -1, dtype=np.int32)
-        if valid.any():
-            lo, hi = ladder_bounds_array(r2_valid, fast_mode)                   # :463-472
-            kmin[valid], kmax[valid] = lo, hi
-        b3.add_round3_reuse(idx, rr.right_anchor_seq, kmin, kmax)
+            r2_valid = np.array([v for v in r2 if v is not None], dtype=np.float64)
+        per_region.append((rr, idx, rl, valid))
+        valid_parts.append(valid)
+        r2_parts.append(r2_valid)
+    # ladder bounds of every read of every region in one pass (:463-472)
+    valid_all = np.concatenate(valid_parts) if valid_parts else np.zeros(0, dtype=bool)
+    kmin_all = np.zeros(len(valid_all), dtype=np.int32)
+    kmax_all = np.full(len(valid_all), -1, dtype=np.int32)
+    if valid_all.any():
+        kmin_all[valid_all], kmax_all[valid_all] = ladder_bounds_array(np.concatenate(r2_parts), fast_mode)
+    all_reads, pos = [], 0
+    for rr, idx, rl, valid in per_region:
+        n = len(rl)
+        b3.add_round3_reuse(idx, rr.right_anchor_seq, kmin_all[pos:pos + n], kmax_all[pos:pos + n])
+        pos += n
         all_reads += [rd if ok else None for rd, ok in zip(rl, valid.tolist())]
         del rr._nr_round2
     b3.commit().run()                                                           # was pymm2.main per read at :497
