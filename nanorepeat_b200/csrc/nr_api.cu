@@ -545,11 +545,18 @@ int plan_batch(nr_batch* b) {
             const long long stripes = (multi_rows / (32 * r) + (long long)multis.size()) * (ladder ? 2 : 1);
             if (stripes <= warps) { cap = r; break; }
         }
+        // ONE stripe height for all long tasks of the batch.  Every height is its own unrolled code; long reads running
+        // at six different heights at once miss the instruction cache on most fetches (config 5: 4.7 stall cycles per
+        // issued instruction, round 3 in 183 ms with three heights in flight against 57 ms with one).  The last stripe of
+        // a task is padded up to the common height.
+        const int height = std::min(cap, 12);
         for (int i : multis) {
             const int q_len = ladder ? b->ltasks[i].q_len : b->tasks[i].q_len;
-            int ns = (q_len + 32 * cap - 1) / (32 * cap);
-            ns = std::min(ns, nr::kCodeFwd - 2);
-            const int R = nr::coop_rows(q_len, ns);
+            int R = height, ns = (q_len + 32 * height - 1) / (32 * height);
+            if (ns > nr::kCodeFwd - 2) {                            // too long for that many stripes: its own, taller ones
+                ns = nr::kCodeFwd - 2;
+                R = nr::coop_rows(q_len, ns);
+            }
             if (R > max_r)
                 return fail(NR_ERR_TOO_LARGE, "task %d: a query of %d bases needs more than %d stripes", i, q_len, nr::kCodeFwd - 2);
             cost[i] = cost[i] / ((long long)task_ns[i] * task_R[i]) * ((long long)ns * R);
@@ -575,6 +582,7 @@ int plan_batch(nr_batch* b) {
     for (int i : multis) {
         nr::CoopInfo ci = {};
         ci.n_stripes = task_ns[i];
+        ci.rows = task_R[i];
         ci.data_off = data_off;
         ci.flag_off = (int)flag_off;
         ci.bnd_stride = (task_sweep[i] + 63) / 32 * 32;

@@ -675,7 +675,8 @@ struct CoopInfo {
                             // forward sweep | backward vectors | token row a | token row b]: the ladder's two sweeps overlap
     int flag_off;
     int bnd_stride, b_stride, tok_stride;   // int4, int4, ulonglong2
-    int n_stripes, pad;
+    int n_stripes;
+    int rows;               // rows per lane of every stripe (the host picks from a short list, see plan_batch)
 };
 constexpr int kCoopFlagInts(int S) { return 2 * S + 4; }
 // tag of the entries stripe s writes in the run with this epoch (the host counts runs; never 0)
@@ -799,7 +800,7 @@ __device__ __forceinline__ void exact_entry(int e, const Task* __restrict__ task
         if (lane == 0) out[tid] = finalize_rung(key, 0ull, 0, 0, 0, 0);
     } else {
         const CoopInfo ci = ra.coop[ra.coop_idx[tid]];
-        exact_stripe_dispatch<kMinR>(coop_rows(tk.q_len, ci.n_stripes), tk, tid, code - 1, ci, ra.epoch, ra.scratch, ra.flags, pool, sc, prof, lane, out);
+        exact_stripe_dispatch<kMinR>(ci.rows, tk, tid, code - 1, ci, ra.epoch, ra.scratch, ra.flags, pool, sc, prof, lane, out);
     }
 }
 
@@ -1049,7 +1050,7 @@ __device__ __forceinline__ void ladder_entry(int e, const LadderTask* __restrict
         ladder_dispatch<kMinR, FLAG>(R, tk, cx, sc, prof, lane, out, sel);
     } else {
         const CoopInfo ci = ra.coop[tk.pad];
-        ladder_stripe_dispatch<kMinR, FLAG>(coop_rows(tk.q_len, ci.n_stripes), tk, cx, code, ci, ra.epoch, ra.scratch, ra.flags, sc, prof, lane, out, sel);
+        ladder_stripe_dispatch<kMinR, FLAG>(ci.rows, tk, cx, code, ci, ra.epoch, ra.scratch, ra.flags, sc, prof, lane, out, sel);
     }
 }
 
