@@ -539,7 +539,7 @@ int plan_batch(nr_batch* b) {
         const long long warps = (long long)kWarpsPerBlock * g_ctx.sm_count;
         int cap = max_r;
         const char* force = getenv("NR_COOP_ROWS");       // tuning / debugging: fixed stripe height of the long tasks
-        if (force && atoi(force) >= nr::kMinR && atoi(force) <= max_r) cap = atoi(force);
+        if (force && atoi(force) >= nr::kMinR && atoi(force) <= max_r) cap = std::min(nr::coop_height_at_least(atoi(force)), max_r);
         else for (int r : {4, 6, 8}) {
             if (r >= max_r) break;
             const long long stripes = (multi_rows / (32 * r) + (long long)multis.size()) * (ladder ? 2 : 1);
@@ -554,8 +554,8 @@ int plan_batch(nr_batch* b) {
             const int q_len = ladder ? b->ltasks[i].q_len : b->tasks[i].q_len;
             int R = height, ns = (q_len + 32 * height - 1) / (32 * height);
             if (ns > nr::kCodeFwd - 2) {                            // too long for that many stripes: its own, taller ones
-                ns = nr::kCodeFwd - 2;
-                R = nr::coop_rows(q_len, ns);
+                R = nr::coop_height_at_least(nr::coop_rows(q_len, nr::kCodeFwd - 2));
+                ns = (q_len + 32 * R - 1) / (32 * R);
             }
             if (R > max_r)
                 return fail(NR_ERR_TOO_LARGE, "task %d: a query of %d bases needs more than %d stripes", i, q_len, nr::kCodeFwd - 2);

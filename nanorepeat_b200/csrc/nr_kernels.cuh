@@ -735,9 +735,15 @@ template <int R, class SC>
 __device__ __forceinline__ void exact_stripe_dispatch(int r, const Task& tk, int tid, int s, const CoopInfo& ci, int epoch, int4* scratch,
                                                       int* flags, const uint32_t* __restrict__ pool, const SC& sc, int4* prof,
                                                       int lane, int4* out) {
-    if (r == R) { exact_stripe<R>(tk, tid, s, ci, epoch, scratch, flags, pool, sc, prof, lane, out); return; }
+    if constexpr (is_coop_height(R))
+        if (r == R) { exact_stripe<R>(tk, tid, s, ci, epoch, scratch, flags, pool, sc, prof, lane, out); return; }
     if constexpr (R < kMaxRExact) exact_stripe_dispatch<R + 1>(r, tk, tid, s, ci, epoch, scratch, flags, pool, sc, prof, lane, out);
 }
+
+// The stripe heights the multi-stripe code is built for (the host uses one per batch, plan_batch): every height is a
+// few hundred KB of unrolled code, and the ones in between would never run.
+__host__ __device__ constexpr bool is_coop_height(int R) { return R == 4 || R == 6 || R == 8 || R == 12 || R == 16; }
+__host__ __device__ constexpr int coop_height_at_least(int R) { return R <= 4 ? 4 : R <= 6 ? 6 : R <= 8 ? 8 : R <= 12 ? 12 : 16; }
 
 // Rows per lane of a long task that the host cut into n_stripes stripes (few long tasks: short stripes, so that more
 // warps work on each; many: tall ones, which cost less per cell).
@@ -1025,11 +1031,12 @@ template <int R, bool FLAG, class SC>
 __device__ __forceinline__ void ladder_stripe_dispatch(int r, const LadderTask& tk, const LadderCtx& cx, int code, const CoopInfo& ci, int epoch,
                                                        int4* scratch, int* flags, const SC& sc, int4* prof, int lane, int4* out,
                                                        int4* sel) {
-    if (r == R) {
-        if (code < kCodeFwd) ladder_bwd_stripe<R, FLAG>(tk, cx, code - 1, ci, epoch, scratch, flags, sc, prof, lane);
-        else ladder_fwd_stripe<R, FLAG>(tk, cx, code - kCodeFwd, ci, epoch, scratch, flags, sc, prof, lane, out, sel);
-        return;
-    }
+    if constexpr (is_coop_height(R))
+        if (r == R) {
+            if (code < kCodeFwd) ladder_bwd_stripe<R, FLAG>(tk, cx, code - 1, ci, epoch, scratch, flags, sc, prof, lane);
+            else ladder_fwd_stripe<R, FLAG>(tk, cx, code - kCodeFwd, ci, epoch, scratch, flags, sc, prof, lane, out, sel);
+            return;
+        }
     if constexpr (R < kMaxRLadder) ladder_stripe_dispatch<R + 1, FLAG>(r, tk, cx, code, ci, epoch, scratch, flags, sc, prof, lane, out, sel);
 }
 
