@@ -651,6 +651,11 @@ struct Sweep {
     }
 };
 
+// The stripe heights the multi-stripe code is built for (the host uses one per batch, plan_batch): every height is a
+// few hundred KB of unrolled code, and the ones in between would never run.
+__host__ __device__ constexpr bool is_coop_height(int R) { return R == 4 || R == 6 || R == 8 || R == 12 || R == 16; }
+__host__ __device__ constexpr int coop_height_at_least(int R) { return R <= 4 ? 4 : R <= 6 ? 6 : R <= 8 ? 8 : R <= 12 ? 12 : 16; }
+
 constexpr int kMinR = 4;
 constexpr int kMaxRExact = 16;    // single-stripe tasks up to 512 rows
 constexpr int kMaxRLadder = 12;   // 384 rows: profile + junction vectors stay within 12 KB of shared memory per warp
@@ -739,11 +744,6 @@ __device__ __forceinline__ void exact_stripe_dispatch(int r, const Task& tk, int
         if (r == R) { exact_stripe<R>(tk, tid, s, ci, epoch, scratch, flags, pool, sc, prof, lane, out); return; }
     if constexpr (R < kMaxRExact) exact_stripe_dispatch<R + 1>(r, tk, tid, s, ci, epoch, scratch, flags, pool, sc, prof, lane, out);
 }
-
-// The stripe heights the multi-stripe code is built for (the host uses one per batch, plan_batch): every height is a
-// few hundred KB of unrolled code, and the ones in between would never run.
-__host__ __device__ constexpr bool is_coop_height(int R) { return R == 4 || R == 6 || R == 8 || R == 12 || R == 16; }
-__host__ __device__ constexpr int coop_height_at_least(int R) { return R <= 4 ? 4 : R <= 6 ? 6 : R <= 8 ? 8 : R <= 12 ? 12 : 16; }
 
 // Rows per lane of a long task that the host cut into n_stripes stripes (few long tasks: short stripes, so that more
 // warps work on each; many: tall ones, which cost less per cell).
