@@ -36,7 +36,7 @@ import numpy as np  # noqa: E402
 DPX_LANES_PER_CLK_PER_SM = 64       # measured: tools/microbench/pipe_rates.cu -> profiles/pipe_rates_r01.jsonl
 DPX_INSTR_PER_CELL = 6              # 32-bit word: 2 (five-way max + floor for H) + 4 (E1, E2, F1, F2 updates); the
                                     # running-max op (0.5/cell) counts against the kernel
-PAIR_LADDER_TRAFFIC = 75080192      # bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_ncu_pair_ladder_kernel_v35_summary.txt); the writes include dirty lines of the L2 flush buffer that the launch evicts
+PAIR_LADDER_TRAFFIC = 74990848      # bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_ncu_pair_ladder_kernel_v41_summary.txt); the writes include dirty lines of the L2 flush buffer that the launch evicts
 DPX_INSTR_PER_CELL_PAIR = 7         # u16x2 words (two cells per instruction): the floor needs an operand of its own
                                     # (no .RELU on unsigned halves): 3 for H + 4 -> 3.5 per cell
 
