@@ -6,7 +6,8 @@ import nanorepeat_b200 as nrb
 from nanorepeat_b200 import synth, engine
 from nanorepeat_b200.estimation import ladder_bounds_array
 which = sys.argv[1] if len(sys.argv) > 1 else "5"
-regs = synth.config5(seed=5, n_reads=10000) if which == "5" else synth.config4(seed=4, reads_per_locus=40)
+regs = (synth.config5(seed=5, n_reads=10000) if which == "5" else synth.config3(seed=3, n_loci=2000) if which == "3"
+        else synth.config1(seed=1) if which == "1" else synth.config4(seed=4, reads_per_locus=40))
 engine.init(0)
 sc = engine.get_preset("ont")
 rrs = [nrb.RepeatRegion.from_synth(r) for r in regs]
