@@ -18,6 +18,14 @@
  * compute call (never at load time), so the library is safe to load before the reference's fork()
  * (nanoRepeat_bam.py:719-724); each worker process then owns its own context.
  *
+ * Sequences.  Reads may hold any character: ACGT / acgt are bases, anything else is an ambiguous base (minimap2's code 4,
+ * scored -ambiguous against every template base, as the reference's engine does with N); white space around a read is
+ * dropped, as the reference's FASTQ / FASTA round trip does (nanoRepeat_bam.py:311-321, :487-493).  Templates (anchors,
+ * motif, generic targets) must be ACGT: a region whose anchor holds another character is NOT SCORED -- its reads come back
+ * with score 0, i.e. "the aligner printed nothing" (round 2 leaves the size unset, nanoRepeat_bam.py:373; round 3 leaves
+ * it untouched, :421) -- and so is a single task beyond nr_limits (match * min(|query|, |template|) > 32767, or a template
+ * over 65471 bases).  Neither fails the call: nr_stats_t.n_skipped counts them, every other read is scored as usual.
+ *
  * Alignment contract (bit-exact with oracle/nr_oracle.c): exact local alignment, match +a, mismatch -b,
  * gap of length l costs min(q + l*e, q2 + l*e2);
  *   score  = best local score (0: nothing aligns),
@@ -36,8 +44,8 @@ extern "C" {
 #define NR_OK                0
 #define NR_ERR_CUDA         -1   /* CUDA runtime failure (no device, launch error, out of memory on device) */
 #define NR_ERR_ARG          -2   /* null pointer / negative size / inconsistent arguments */
-#define NR_ERR_BAD_BASE     -3   /* a sequence holds a character other than ACGTacgt (2-bit device encoding) */
-#define NR_ERR_TOO_LARGE    -4   /* a task exceeds the packed score/coordinate range (see nr_limits) */
+#define NR_ERR_BAD_BASE     -3   /* malformed read buffer (e.g. a line count that does not match n_reads) */
+#define NR_ERR_TOO_LARGE    -4   /* a batch exceeds an index range (2^31 rungs, 2^32 pool words, 2^24 tasks) */
 #define NR_ERR_NOMEM        -5   /* host allocation failure */
 #define NR_ERR_UNKNOWN_TYPE -6   /* nr_get_preset: data type not in the reference's table */
 
@@ -48,7 +56,7 @@ typedef struct nr_scoring_t {
     int32_t gap_ext1;     /* minimap2 -E first value (2) */
     int32_t gap_open2;    /* minimap2 -O second value (24) */
     int32_t gap_ext2;     /* minimap2 -E second value (1) */
-    int32_t ambiguous;    /* minimap2 --score-N (1); kept for ABI parity with the oracle, unused on device */
+    int32_t ambiguous;    /* minimap2 --score-N (1): a read base other than ACGT scores -ambiguous against any base */
     int32_t min_dp_score; /* minimap2 -s (80): alignments scoring below it are "not printed" by the selection */
 } nr_scoring_t;
 
@@ -69,7 +77,8 @@ typedef struct nr_stats_t {
     int64_t executed_cells;     /* DP cells the kernels actually updated (padding and shared prefixes accounted) */
     int64_t n_tasks;
     int32_t kernel_launches;    /* launches of this library's kernels */
-    int32_t reserved;
+    int32_t n_skipped;          /* tasks / reads left unscored: template with a base other than ACGT, or beyond nr_limits.
+                                   Their records are zero ("the aligner printed nothing"); everything else is unaffected */
     int64_t h2d_bytes;
     int64_t d2h_bytes;
 } nr_stats_t;
@@ -95,7 +104,8 @@ int nr_shutdown(void);
 const char* nr_last_error(void);
 int nr_device_info(int32_t* device, int32_t* sm_count, int32_t* clock_khz);
 
-/* Largest task the packed kernels accept: match * min(qlen, tlen) <= max_score and tlen <= max_tlen. */
+/* Largest task the packed kernels score: match * min(qlen, tlen) <= max_score and tlen <= max_tlen (larger ones are
+ * skipped, see "Sequences" above). */
 int nr_limits(int32_t* max_score, int32_t* max_tlen);
 
 /*

@@ -60,8 +60,14 @@ using nr::kWarpsPerBlock;
 // ---- context + caching allocator -----------------------------------------------------------------------------
 // Batches come and go once per region (or per group of regions); cudaMalloc / cudaMallocHost / cudaFree cost far
 // more than the copies they serve, so freed buffers are kept by power-of-two size class and handed out again.
+enum BufKind { BUF_DEV = 0, BUF_PIN = 1, BUF_SCRATCH = 2 };
 struct BufCache {
-    std::unordered_map<size_t, std::vector<void*>> free_dev, free_pin;
+    // free_scratch: device buffers that only ever serve as the long reads' boundary-row scratch.  They are zeroed when
+    // allocated and hold nothing but tagged entries of earlier launches afterwards, so a stale word can never pass for
+    // an entry of the running launch (nr_kernels.cuh, load_bnd); scratch_era[ptr] = era of the last launch that used it.
+    std::unordered_map<size_t, std::vector<void*>> free_dev, free_pin, free_scratch;
+    std::unordered_map<void*, long long> scratch_era;
+    std::unordered_map<size_t, std::vector<void*>>& of(int kind) { return kind == BUF_PIN ? free_pin : kind == BUF_SCRATCH ? free_scratch : free_dev; }
     static size_t klass(size_t bytes) {
         size_t c = 4096;
         while (c < bytes) c <<= 1;
@@ -82,12 +88,20 @@ std::mutex g_ctx_mu;
 // 3: paired flag ladder (two reads per warp, u16x2 words), 2: flag ladder, 1: shared sweeps with full records,
 // 0: every rung its own rectangle
 std::atomic<int> g_ladder_mode{3};
-std::atomic<int> g_epoch{0};         // runs of the 32-bit kernels, process-wide: tags the boundary entries of the long tasks
+// Launches of the 32-bit kernels, process-wide.  Launch number n tags the long reads' boundary entries with epoch
+// n % 1023 + 1 (10 bits of the 16-bit tag, never 0); n / 1023 is its era (see BufCache::scratch_era).
+std::atomic<long long> g_launch_no{0};
+constexpr long long kEpochs = 1023;
 std::atomic<int> g_timing{0};        // nr_set_timing: CUDA events around every kernel of nr_batch_run
 
 int ensure_init(int device) {
     std::lock_guard<std::mutex> lk(g_ctx_mu);
-    if (g_ctx.ready) return NR_OK;
+    if (g_ctx.ready) {
+        if (device >= 0 && device != g_ctx.device)
+            return fail(NR_ERR_ARG, "the library is already initialised on device %d (requested %d); call nr_shutdown() first",
+                        g_ctx.device, device);
+        return NR_OK;
+    }
     if (device < 0) {
         const char* e = getenv("NR_DEVICE");
         if (!e) e = getenv("LOCAL_RANK");
@@ -98,7 +112,8 @@ int ensure_init(int device) {
     if (err != cudaSuccess || n == 0)
         return fail(NR_ERR_CUDA, "no CUDA device available (%s); libnanorepeat_b200 has no CPU fallback",
                     err == cudaSuccess ? "device count 0" : cudaGetErrorString(err));
-    device %= n;
+    if (device >= n)       // two ranks must never end up on one GPU silently
+        return fail(NR_ERR_ARG, "device %d requested but only %d CUDA device(s) are visible", device, n);
     CUDA_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -113,22 +128,45 @@ int ensure_init(int device) {
     return NR_OK;
 }
 
-int cached_alloc(void** p, size_t bytes, bool pinned) {
+// give every cached free buffer back to the driver (called when an allocation fails, and by nr_shutdown)
+void trim_cache_locked() {
+    for (auto& kv : g_ctx.cache.free_dev) for (void* p : kv.second) cudaFree(p);
+    for (auto& kv : g_ctx.cache.free_scratch) for (void* p : kv.second) { cudaFree(p); g_ctx.cache.scratch_era.erase(p); }
+    for (auto& kv : g_ctx.cache.free_pin) for (void* p : kv.second) cudaFreeHost(p);
+    g_ctx.cache.free_dev.clear(); g_ctx.cache.free_scratch.clear(); g_ctx.cache.free_pin.clear();
+}
+
+int cached_alloc(void** p, size_t bytes, int kind) {
     const size_t k = BufCache::klass(bytes);
     {
         std::lock_guard<std::mutex> lk(g_ctx_mu);
-        auto& fl = (pinned ? g_ctx.cache.free_pin : g_ctx.cache.free_dev)[k];
+        auto& fl = g_ctx.cache.of(kind)[k];
         if (!fl.empty()) { *p = fl.back(); fl.pop_back(); return NR_OK; }
     }
-    if (pinned) CUDA_TRY(cudaMallocHost(p, k));
-    else CUDA_TRY(cudaMalloc(p, k));
+    auto raw = [&]() { return kind == BUF_PIN ? cudaMallocHost(p, k) : cudaMalloc(p, k); };
+    cudaError_t e = raw();
+    if (e != cudaSuccess) {        // out of memory while the cache may hold plenty: hand the cache back and try once more
+        cudaGetLastError();
+        { std::lock_guard<std::mutex> lk(g_ctx_mu); cudaDeviceSynchronize(); trim_cache_locked(); }
+        e = raw();
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(NR_ERR_CUDA, "%s of %zu bytes failed: %s", kind == BUF_PIN ? "cudaMallocHost" : "cudaMalloc", k, cudaGetErrorString(e));
+    }
+    if (kind == BUF_SCRATCH) {
+        CUDA_TRY(cudaMemsetAsync(*p, 0, k, g_ctx.stream));
+        CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        g_ctx.cache.scratch_era[*p] = g_launch_no.load() / kEpochs;
+    }
     return NR_OK;
 }
 
-void cached_free(void* p, size_t bytes, bool pinned) {
+void cached_free(void* p, size_t bytes, int kind) {
     if (!p) return;
     std::lock_guard<std::mutex> lk(g_ctx_mu);
-    (pinned ? g_ctx.cache.free_pin : g_ctx.cache.free_dev)[BufCache::klass(bytes)].push_back(p);
+    g_ctx.cache.of(kind)[BufCache::klass(bytes)].push_back(p);
 }
 
 // ---- 2-bit packing -------------------------------------------------------------------------------------------
@@ -205,17 +243,34 @@ void parallel_for(int n, int grain, F fn) {
     for (auto& x : th) x.join();
 }
 
-// Sequence pool.  Every sequence starts on a word boundary and is followed by one zero slack word (kernels prefetch
-// one word ahead).
+// Bit plane of the bases of s that are not ACGT (bit i & 31 of word i >> 5); m holds (len + 31) / 32 zeroed words.
+void ambiguity_plane(const char* s, int len, uint32_t* m) {
+    for (int i = 0; i < len; ++i)
+        if (g_bad.t[(unsigned char)s[i]]) m[i >> 5] |= 1u << (i & 31);
+}
+
+// Sequence pool.  Every sequence starts on a word boundary and is followed by one slack word (kernels prefetch one word
+// ahead).  For a READ the slack word doubles as the link to its ambiguity plane: 0 = ACGT only, otherwise the plane
+// starts that many words behind the read's first word (nr_kernels.cuh, read_has_ambiguous).  Templates must be ACGT.
 struct Pool {
     std::vector<uint32_t> words;
-    // append; returns first word index, or -1 on a non-ACGT character
-    long long add(const char* s, int len) {
+    // append; returns first word index, or -1 on a non-ACGT character (ambiguous_ok: append the plane instead)
+    long long add(const char* s, int len, bool ambiguous_ok = false) {
         const size_t w0 = words.size();
         const size_t nw = (size_t)(len + 15) / 16 + 1;
         words.resize(w0 + nw, 0u);
-        if (!pack_seq(s, len, words.data() + w0)) { words.resize(w0); return -1; }
+        if (!pack_seq(s, len, words.data() + w0)) {
+            if (!ambiguous_ok) { words.resize(w0); return -1; }
+            link_plane(w0, s, len);
+        }
         return (long long)w0;
+    }
+    // append the ambiguity plane of the read packed at word w0 and link it from the read's slack word
+    void link_plane(size_t w0, const char* s, int len) {
+        const size_t at = words.size();
+        words.resize(at + (size_t)(len + 31) / 32, 0u);
+        ambiguity_plane(s, len, words.data() + at);
+        words[w0 + (size_t)(len + 15) / 16] = (uint32_t)(at - w0);
     }
 };
 
@@ -281,6 +336,8 @@ struct nr_batch {
     // per-read bookkeeping (rounds 2 and 3)
     std::vector<RegionInfo> regions;
     int n_reads = 0;
+    int n_skipped = 0;                        // tasks / reads left unscored (template not ACGT, beyond the packed range)
+    int n_ambiguous_reads = 0;                // reads with a base other than ACGT (scored through an ambiguity plane)
     std::vector<int32_t> read_region;
     std::vector<int32_t> kmin, kmax;
     std::vector<int64_t> rung_off;            // n_reads + 1 (round 3)
@@ -322,6 +379,7 @@ int check_scoring(const nr_scoring_t* sc) {
     if (sc->match <= 0 || sc->mismatch < 0 || sc->gap_open1 < 0 || sc->gap_ext1 <= 0 || sc->gap_open2 < 0 ||
         sc->gap_ext2 <= 0)
         return fail(NR_ERR_ARG, "scoring values out of range");
+    if (sc->ambiguous < 0 || sc->ambiguous > 4096) return fail(NR_ERR_ARG, "scoring values out of range");
     if (sc->gap_open1 + sc->gap_ext1 > 4096 || sc->gap_open2 + sc->gap_ext2 > 4096 || sc->mismatch > 4096 ||
         sc->match > 4096)
         return fail(NR_ERR_ARG, "scoring values too large for the packed kernels");
@@ -332,6 +390,7 @@ nr::ScoreW score_words(const nr_scoring_t& sc) {
     nr::ScoreW k;
     k.sub_match = (sc.match << 16) - 1;
     k.sub_mismatch = -(sc.mismatch << 16) - 1;
+    k.sub_amb = -(sc.ambiguous << 16) - 1;
     k.h_open1 = -((sc.gap_open1 + sc.gap_ext1) << 16) - 1;
     k.h_ext1 = -(sc.gap_ext1 << 16) - 1;
     k.h_open2 = -((sc.gap_open2 + sc.gap_ext2) << 16) - 1;
@@ -364,7 +423,8 @@ struct PhaseTrace {
 };
 
 bool is_map_ont(const nr_scoring_t& c) {
-    return c.match == 2 && c.mismatch == 4 && c.gap_open1 == 4 && c.gap_ext1 == 2 && c.gap_open2 == 24 && c.gap_ext2 == 1;
+    return c.match == 2 && c.mismatch == 4 && c.gap_open1 == 4 && c.gap_ext1 == 2 && c.gap_open2 == 24 && c.gap_ext2 == 1 &&
+           c.ambiguous == 1;
 }
 
 // Pair up the eligible tasks of one region (ids[]: task indices, all of the same template): neighbours in read length
@@ -387,8 +447,12 @@ int plan_batch(nr_batch* b) {
     if (b->kind != KIND_ROUND3) b->n_out = b->tasks.size();
     b->stats = {};
     b->stats.n_tasks = (int64_t)b->n_out;
-    std::vector<long long> cost(n);
-    std::vector<int> task_R(n), task_ns(n), task_sweep(n), task_rungs(n, 0);
+    std::vector<long long> cost(n, 0);
+    std::vector<int> task_R(n, nr::kMinR), task_ns(n, 1), task_sweep(n, 0), task_rungs(n, 0);
+    // 1: runs on the paired kernels; 2: not scored -- an empty sequence, a template that is not ACGT (t_len < 0), or a
+    // task beyond the packed score / coordinate range: its record stays zero, which every caller reads as "the aligner
+    // printed nothing" (nanoRepeat_bam.py:421, :433); the rest of the batch is unaffected
+    std::vector<char> paired(n, 0);
     const int max_r = ladder ? nr::kMaxRLadder : nr::kMaxRExact;
     const bool fixed = is_map_ont(b->sc);
     PhaseTrace trace;
@@ -409,20 +473,25 @@ int plan_batch(nr_batch* b) {
             const nr::Task& t = b->tasks[i];
             q_len = t.q_len;
             t_len = t_sweep = t.t_len;
-            b->stats.algorithmic_cells += (long long)q_len * t_len;
+            if (t_len > 0) b->stats.algorithmic_cells += (long long)q_len * t_len;
+        }
+        if (q_len <= 0 || t_len <= 0) {
+            paired[i] = 2;
+            if (t_len < 0) ++b->n_skipped;
+            continue;
         }
         long long m = (long long)b->sc.match * std::min(q_len, t_len);
-        if (m > kMaxScore || t_len > kMaxTlen)
-            return fail(NR_ERR_TOO_LARGE,
-                        "task %d (query %d x target %d) exceeds the packed range (score <= %d, target <= %d)", i,
-                        q_len, t_len, kMaxScore, kMaxTlen);
+        if (m > kMaxScore || t_len > kMaxTlen) {        // (its cells stay in the count of what was asked for)
+            paired[i] = 2;
+            ++b->n_skipped;
+            continue;
+        }
         nr::stripe_shape(q_len, max_r, task_R[i], task_ns[i]);
         task_sweep[i] = t_sweep;
         cost[i] = (long long)task_ns[i] * 32 * task_R[i] * t_len;
     }
     trace.mark("task shapes");
     // ---- paired launch: two reads of one region per warp ----
-    std::vector<char> paired(n, 0);
     std::vector<long long> pair_cost;
     Launch& L = b->launch;
     L = {};
@@ -432,7 +501,7 @@ int plan_batch(nr_batch* b) {
             std::vector<int> ids;
             for (int r = g.first_read; r < g.first_read + g.n_reads; ++r) {
                 const nr::Task& t = b->tasks[r];
-                if (t.q_len >= 1 && t.q_len <= 32 * nr::pr::kMaxRPair2 && t.t_len >= 1) ids.push_back(r);
+                if (!paired[r] && t.q_len >= 1 && t.q_len <= 32 * nr::pr::kMaxRPair2 && t.t_len >= 1) ids.push_back(r);
             }
             make_pairs(ids, [&](int i) { return b->tasks[i].q_len; }, [&](int x, int y) {
                 const int R = nr::pr::pair_rows(b->tasks[x].q_len);      // x is the longer read
@@ -458,7 +527,9 @@ int plan_batch(nr_batch* b) {
             for (int i = 0; i < n; ++i)
                 if (b->lt_src[i] >= 0) src2lt[b->lt_src[i]] = i;
             for (const nr::pr::Pair2& p2 : src->pairs2) {
-                const int la = src2lt[p2.a], lb = p2.b >= 0 ? src2lt[p2.b] : -1;
+                int la = src2lt[p2.a], lb = p2.b >= 0 ? src2lt[p2.b] : -1;
+                if (la >= 0 && paired[la]) la = -1;        // (not scored: beyond the packed range)
+                if (lb >= 0 && paired[lb]) lb = -1;
                 if (la < 0 && lb < 0) continue;
                 const nr::LadderRegion& g = b->lregs[b->ltasks[la >= 0 ? la : lb].region];
                 if (g.n_left <= 0 || g.n_right <= 0) continue;
@@ -644,23 +715,23 @@ int plan_batch(nr_batch* b) {
     b->out_bytes = sizeof(int4) * std::max<size_t>(b->n_out, 1);
     b->scratch_bytes = sizeof(int4) * scratch_total;
     int rc;
-    if ((rc = cached_alloc(&b->d_blob, b->blob_bytes, false))) return rc;
-    if ((rc = cached_alloc(&b->h_blob, b->blob_bytes, true))) return rc;
-    if ((rc = cached_alloc((void**)&b->d_out, b->out_bytes, false))) return rc;
-    if ((rc = cached_alloc((void**)&b->h_out, b->out_bytes, true))) return rc;
-    if (scratch_total && (rc = cached_alloc((void**)&b->d_scratch, b->scratch_bytes, false))) return rc;
-    if (b->flags_bytes && (rc = cached_alloc((void**)&b->d_flags, b->flags_bytes, false))) return rc;
-    if (b->state_bytes && (rc = cached_alloc((void**)&b->d_state, b->state_bytes, false))) return rc;
+    if ((rc = cached_alloc(&b->d_blob, b->blob_bytes, BUF_DEV))) return rc;
+    if ((rc = cached_alloc(&b->h_blob, b->blob_bytes, BUF_PIN))) return rc;
+    if ((rc = cached_alloc((void**)&b->d_out, b->out_bytes, BUF_DEV))) return rc;
+    if ((rc = cached_alloc((void**)&b->h_out, b->out_bytes, BUF_PIN))) return rc;
+    if (scratch_total && (rc = cached_alloc((void**)&b->d_scratch, b->scratch_bytes, BUF_SCRATCH))) return rc;
+    if (b->flags_bytes && (rc = cached_alloc((void**)&b->d_flags, b->flags_bytes, BUF_DEV))) return rc;
+    if (b->state_bytes && (rc = cached_alloc((void**)&b->d_state, b->state_bytes, BUF_DEV))) return rc;
     if (b->flag) {
         b->sel_bytes = sizeof(int4) * std::max<size_t>((size_t)b->n_reads, 1);
-        if ((rc = cached_alloc((void**)&b->d_sel, b->sel_bytes, false))) return rc;
-        if ((rc = cached_alloc((void**)&b->h_sel, b->sel_bytes, true))) return rc;
+        if ((rc = cached_alloc((void**)&b->d_sel, b->sel_bytes, BUF_DEV))) return rc;
+        if ((rc = cached_alloc((void**)&b->h_sel, b->sel_bytes, BUF_PIN))) return rc;
     }
     if (!b->pairs3.empty()) {
         b->redo_bytes = sizeof(int32_t) * (size_t)n;
-        if ((rc = cached_alloc((void**)&b->d_prung, b->prung_bytes, false))) return rc;
-        if ((rc = cached_alloc((void**)&b->d_redo, b->redo_bytes, false))) return rc;
-        if ((rc = cached_alloc((void**)&b->h_redo_count, 64, true))) return rc;
+        if ((rc = cached_alloc((void**)&b->d_prung, b->prung_bytes, BUF_DEV))) return rc;
+        if ((rc = cached_alloc((void**)&b->d_redo, b->redo_bytes, BUF_DEV))) return rc;
+        if ((rc = cached_alloc((void**)&b->h_redo_count, 64, BUF_PIN))) return rc;
         *b->h_redo_count = 0;
     }
     trace.mark("buffers (cached alloc)");
@@ -692,6 +763,7 @@ int plan_batch(nr_batch* b) {
     CUDA_TRY(cudaEventRecord(b->ev_uploaded, st));      // nr_batch_run on another stream waits for it; no host sync here
     b->stats.h2d_bytes = (int64_t)(task_bytes + reg_bytes + order_bytes + pair_bytes + coop_bytes + cidx_bytes + pool_bytes);
     b->stats.d2h_bytes = (int64_t)sizeof(int4) * (b->flag ? (int64_t)b->n_reads : (int64_t)b->n_out);
+    b->stats.n_skipped = b->n_skipped;
     trace.mark("upload + memsets (async)");
     b->committed = true;
     return NR_OK;
@@ -713,20 +785,38 @@ int prepare_kernel(const void* fn, size_t launch_bytes) {
     return NR_OK;
 }
 
-nr::RestArgs rest_args(const nr_batch* b, const int32_t* order, int count) {
+constexpr int kSpinSlot = 16;        // d_counters[kSpinSlot]: the batch's give-up flag (nr_kernels.cuh, wait_cols)
+
+// Arguments of one launch of the 32-bit kernels.  Draws the launch's epoch; a scratch buffer that was last used in an
+// earlier era is zeroed first (on the launch's stream), so no tag left in it can equal one of this launch.
+int rest_args(nr_batch* b, const int32_t* order, int count, cudaStream_t st, nr::RestArgs* out) {
     nr::RestArgs ra;
     ra.order = order; ra.n_order = count;
     ra.scratch = b->d_scratch; ra.coop = b->d_coop; ra.coop_idx = b->d_coop_idx; ra.flags = b->d_flags;
-    ra.epoch = (g_epoch.fetch_add(1) & 0x1ffffff) + 1;
-    return ra;
+    ra.spin = b->d_counters + kSpinSlot;
+    const long long no = g_launch_no.fetch_add(1);
+    ra.epoch = (int)(no % kEpochs) + 1;
+    if (b->d_scratch) {
+        bool stale;
+        {
+            std::lock_guard<std::mutex> lk(g_ctx_mu);
+            long long& era = g_ctx.cache.scratch_era[b->d_scratch];
+            stale = era != no / kEpochs;
+            era = no / kEpochs;
+        }
+        if (stale) CUDA_TRY(cudaMemsetAsync(b->d_scratch, 0, b->scratch_bytes, st));
+    }
+    *out = ra;
+    return NR_OK;
 }
 
 // launch of the 32-bit kernels over order[0, count) (count_dev != NULL: the count is read on the device)
 int launch_rest(nr_batch* b, cudaStream_t st, const nr::ScoreW& k, const int32_t* order, int count, int blocks,
                 int R, const int* count_dev, int* counter) {
     const Launch& L = b->launch;
-    const nr::RestArgs ra = rest_args(b, order, count);
+    nr::RestArgs ra;
     int rc;
+    if ((rc = rest_args(b, order, count, st, &ra))) return rc;
     if (L.ladder) {
         if (!L.fixed) return fail(NR_ERR_ARG, "the ladder kernels are built for map-ont scoring only");
         auto fn = b->flag ? nr::ladder_kernel<true, true> : nr::ladder_kernel<true, false>;
@@ -762,12 +852,8 @@ int run_batch(nr_batch* b, cudaStream_t st) {
         if (!b->qsrc->ran) return fail(NR_ERR_ARG, "nr_batch_run: the round-2 batch this round-3 batch resumes from has not been run");
         if (b->qsrc->run_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, b->qsrc->ev_done, 0));
     }
-    // counters: [0] main launch, [2] length of the redo list, [3] redo launch
-    CUDA_TRY(cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(int), st));
-    if (b->flags_bytes) {          // long reads on concurrent stripes: clear the kernels' give-up flag (nr_kernels.cuh)
-        static const int zero = 0;
-        CUDA_TRY(cudaMemcpyToSymbolAsync(nr::g_spin_timeout, &zero, sizeof(int), 0, cudaMemcpyHostToDevice, st));
-    }
+    // counters: [0] main launch, [2] length of the redo list, [3] redo launch, [kSpinSlot] the long reads' give-up flag
+    CUDA_TRY(cudaMemsetAsync(b->d_counters, 0, 32 * sizeof(int), st));
     if (b->flags_bytes) CUDA_TRY(cudaMemsetAsync(b->d_flags, 0, b->flags_bytes, st));
     int launches = 0;
     int rc;
@@ -779,7 +865,8 @@ int run_batch(nr_batch* b, cudaStream_t st) {
     auto mark = [&](int i, cudaStream_t s) { return timing ? cudaEventRecord(b->ev_t[i], s) : cudaSuccess; };
     if (L.n_pairs) {
         // one persistent launch: the batch's 32-bit entries (long reads cut into stripes, ...) first, then its pairs
-        const nr::RestArgs ra = rest_args(b, b->d_order, L.count);
+        nr::RestArgs ra;
+        if ((rc = rest_args(b, b->d_order, L.count, st, &ra))) return rc;
         int wpb = kWarpsPerBlock;
         if (const char* e = getenv("NR_WPB")) wpb = std::max(4, std::min(kWarpsPerBlock, atoi(e)));   // tuning
         const int blocks = std::max(1, std::min(g_ctx.sm_count, L.count + L.n_pairs));
@@ -831,8 +918,8 @@ int run_batch(nr_batch* b, cudaStream_t st) {
         CUDA_TRY(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(int4) * b->n_out, cudaMemcpyDeviceToHost, st));
     }
     if (b->flags_bytes) {
-        if (!b->h_spin) { int rc2 = cached_alloc((void**)&b->h_spin, 64, true); if (rc2) return rc2; }
-        CUDA_TRY(cudaMemcpyFromSymbolAsync(b->h_spin, nr::g_spin_timeout, sizeof(int), 0, cudaMemcpyDeviceToHost, st));
+        if (!b->h_spin) { int rc2 = cached_alloc((void**)&b->h_spin, 64, BUF_PIN); if (rc2) return rc2; }
+        CUDA_TRY(cudaMemcpyAsync(b->h_spin, b->d_counters + kSpinSlot, sizeof(int), cudaMemcpyDeviceToHost, st));
     }
     CUDA_TRY(cudaEventRecord(b->ev_done, st));
     b->stats.kernel_launches = launches;
@@ -848,12 +935,15 @@ int fetch_raw(nr_batch* b) {
     return NR_OK;
 }
 
-int add_seq(nr_batch* b, const char* s, int len, const char* what, int idx, uint32_t* word) {
+// A template / generic sequence.  ambiguous_ok: a query of the generic engine (bases other than ACGT are scored
+// -sc_ambi through its ambiguity plane); templates must be ACGT: NR_ERR_BAD_BASE, which the region-level callers turn
+// into "this region is not scored" instead of failing the batch.
+int add_seq(nr_batch* b, const char* s, int len, const char* what, int idx, uint32_t* word, bool ambiguous_ok = false) {
     if (!s && len > 0) return fail(NR_ERR_ARG, "%s %d is NULL", what, idx);
     if (len < 0) return fail(NR_ERR_ARG, "%s %d has negative length", what, idx);
-    long long w = b->pool.add(s, len);
+    long long w = b->pool.add(s, len, ambiguous_ok);
     if (w < 0) return fail(NR_ERR_BAD_BASE, "%s %d contains a character other than ACGT", what, idx);
-    if (w > 0xfffffff0LL) return fail(NR_ERR_TOO_LARGE, "sequence pool exceeds 2^32 words");
+    if (w > 0xfffffff0LL || b->pool.words.size() > 0xfffffff0ULL) return fail(NR_ERR_TOO_LARGE, "sequence pool exceeds 2^32 words");
     *word = (uint32_t)w;
     return NR_OK;
 }
@@ -869,33 +959,43 @@ struct ReadSrc {
     long long len(int r) const { return cores ? (long long)core_len[r] : (long long)(off[r + 1] - off[r] - gap); }
 };
 
-// Pack n_reads reads into the pool (in parallel); q_word[r] = first word of read r.
-int add_reads(nr_batch* b, const ReadSrc& src, int n_reads, std::vector<uint32_t>& q_word) {
+inline bool is_blank(char c) { return c == ' ' || c == '\n' || c == '\r' || c == '\t'; }
+
+// Pack n_reads reads into the pool (in parallel); q_word[r] = first word of read r, q_len[r] its length.
+// * White space around a read is not part of it: the reference writes every core to a FASTQ / FASTA file and reads it
+//   back (nanoRepeat_bam.py:311-321, :487-493), which drops it.
+// * A base other than ACGT is kept as an ambiguous base (minimap2's code 4, scored -sc_ambi; the reference accepts such
+//   reads, only tk.rev_comp raises on them): the read gets an ambiguity plane behind the packed reads.
+int add_reads(nr_batch* b, const ReadSrc& src, int n_reads, std::vector<uint32_t>& q_word, std::vector<int32_t>& q_len) {
     q_word.resize(n_reads);
+    q_len.resize(n_reads);
+    std::vector<const char*> ptr(n_reads);
     size_t w = b->pool.words.size();
     const size_t w0 = w;
     for (int r = 0; r < n_reads; ++r) {
-        const long long len = src.len(r);
+        long long len = src.len(r);
         if (len < 0 || len > 0x7fffffffLL) return fail(NR_ERR_ARG, "core %d has a bad length", r);
-        if (len > 0 && !src.ptr(r)) return fail(NR_ERR_ARG, "core %d is NULL", r);
+        const char* p = src.ptr(r);
+        if (len > 0 && !p) return fail(NR_ERR_ARG, "core %d is NULL", r);
+        while (len > 0 && is_blank(p[len - 1])) --len;
+        while (len > 0 && is_blank(*p)) { ++p; --len; }
         if (w > 0xfffffff0ULL) return fail(NR_ERR_TOO_LARGE, "sequence pool exceeds 2^32 words");
+        ptr[r] = p;
+        q_len[r] = (int32_t)len;
         q_word[r] = (uint32_t)w;
         w += (size_t)(len + 15) / 16 + 1;
     }
     b->pool.words.resize(w, 0u);
     uint32_t* words = b->pool.words.data();
-    std::atomic<int> bad{-1};
+    std::vector<uint8_t> amb(n_reads, 0);
     // ~0.1 us per read on one core: threads only pay for themselves from tens of thousands of reads on
-    parallel_for(n_reads, 8192, [&](int r) {
-        if (!pack_seq(src.ptr(r), (int)src.len(r), words + q_word[r])) {
-            int expect = -1;
-            bad.compare_exchange_strong(expect, r);
+    parallel_for(n_reads, 8192, [&](int r) { amb[r] = !pack_seq(ptr[r], q_len[r], words + q_word[r]); });
+    for (int r = 0; r < n_reads; ++r)
+        if (amb[r]) {
+            b->pool.link_plane(q_word[r], ptr[r], q_len[r]);
+            ++b->n_ambiguous_reads;
         }
-    });
-    if (bad.load() >= 0) {
-        b->pool.words.resize(w0);
-        return fail(NR_ERR_BAD_BASE, "core %d contains a character other than ACGT", bad.load());
-    }
+    if (b->pool.words.size() > 0xfffffff0ULL) { b->pool.words.resize(w0); return fail(NR_ERR_TOO_LARGE, "sequence pool exceeds 2^32 words"); }
     return NR_OK;
 }
 
@@ -909,9 +1009,13 @@ int add_round2(nr_batch* b, const char* left, int32_t n_left, const char* motif,
     std::string tpl(left ? left : "", (size_t)n_left);
     tpl.reserve((size_t)n_left + (size_t)motif_len * T);
     for (int k = 0; k < T; ++k) tpl.append(motif, (size_t)motif_len);
-    uint32_t tw;
+    uint32_t tw = 0;
     int rc;
-    if ((rc = add_seq(b, tpl.data(), (int)tpl.size(), "round-2 template", 0, &tw))) return rc;
+    bool bad_template = false;
+    if ((rc = add_seq(b, tpl.data(), (int)tpl.size(), "round-2 template", 0, &tw))) {
+        if (rc != NR_ERR_BAD_BASE) return rc;
+        bad_template = true;       // an anchor with N: the region is not scored (no read gets a size), the batch lives on
+    }
     RegionInfo g;
     g.n_left = n_left; g.motif_len = motif_len; g.first_read = b->n_reads; g.n_reads = n_reads;
     g.left.assign(left ? left : "", (size_t)n_left);
@@ -920,7 +1024,8 @@ int add_round2(nr_batch* b, const char* left, int32_t n_left, const char* motif,
     const size_t base = b->tasks.size();
     b->tasks.resize(base + n_reads);
     std::vector<uint32_t> qw;
-    if ((rc = add_reads(b, src, n_reads, qw))) {     // leave the batch as it was: the caller may retry this region
+    std::vector<int32_t> ql;
+    if ((rc = add_reads(b, src, n_reads, qw, ql))) {     // leave the batch as it was: the caller may retry this region
         b->tasks.resize(base);
         b->regions.pop_back();
         b->pool.words.resize(pool0);
@@ -929,22 +1034,24 @@ int add_round2(nr_batch* b, const char* left, int32_t n_left, const char* motif,
     for (int r = 0; r < n_reads; ++r) {
         nr::Task& t = b->tasks[base + r];
         t.q_word = qw[r];
-        t.q_len = (int)src.len(r);
+        t.q_len = ql[r];
         t.t_word = tw;
-        t.t_len = (int)tpl.size();
+        t.t_len = bad_template ? -1 : (int)tpl.size();      // -1: not scored (plan_batch counts it as skipped)
     }
     b->n_reads += n_reads;
     return NR_OK;
 }
 
 // reuse != NULL: the reads are tasks of the round-2 batch b->qsrc (already packed, already in HBM)
-int add_round3(nr_batch* b, const char* left, int32_t n_left, const char* right, int32_t n_right, const char* motif,
-               int32_t motif_len, int32_t n_reads, const ReadSrc& src, const int32_t* kmin, const int32_t* kmax,
-               const nr::Task* reuse = nullptr) {
-    if (!b || b->kind != KIND_ROUND3 || b->committed) return fail(NR_ERR_ARG, "not an open round-3 batch");
-    if (n_left < 0 || n_right < 0 || motif_len <= 0 || n_reads < 0 || !motif || (n_left > 0 && !left) ||
-        (n_right > 0 && !right) || (n_reads > 0 && (!kmin || !kmax)))
-        return fail(NR_ERR_ARG, "nr_batch_add_round3: bad arguments");
+int add_round3_impl(nr_batch* b, const char* left, int32_t n_left, const char* right, int32_t n_right, const char* motif,
+                    int32_t motif_len, int32_t n_reads, const ReadSrc& src, const int32_t* kmin, const int32_t* kmax,
+                    const nr::Task* reuse) {
+    for (int r = 0; r < n_reads; ++r)
+        if (kmin[r] < 0) return fail(NR_ERR_ARG, "kmin[%d] < 0", r);
+    if (b->flag && 2 * (long long)n_right > 65534)
+        return fail(NR_ERR_TOO_LARGE, "right anchor of %d bases exceeds the flag ladder's range (32767); use nr_set_ladder_mode(1)", n_right);
+    if (reuse && !b->ladder)
+        return fail(NR_ERR_ARG, "reads of a round-2 batch can only be reused by the ladder kernels (nr_set_ladder_mode 1 or 2)");
     RegionInfo g;
     g.n_left = n_left; g.n_right = n_right; g.motif_len = motif_len; g.first_read = b->n_reads; g.n_reads = n_reads;
     const int region = (int)b->regions.size();
@@ -952,7 +1059,6 @@ int add_round3(nr_batch* b, const char* left, int32_t n_left, const char* right,
     if (b->rung_off.empty()) b->rung_off.push_back(0);
     int klo = INT32_MAX, khi = -1;
     for (int r = 0; r < n_reads; ++r) {
-        if (kmin[r] < 0) return fail(NR_ERR_ARG, "kmin[%d] < 0", r);
         const long long n = kmax[r] >= kmin[r] ? (long long)kmax[r] - kmin[r] + 1 : 0;
         b->rung_off.push_back(b->rung_off.back() + n);
         b->kmin.push_back(kmin[r]);
@@ -966,8 +1072,11 @@ int add_round3(nr_batch* b, const char* left, int32_t n_left, const char* right,
     b->n_out = (size_t)b->rung_off.back();
     const int64_t* roff = b->rung_off.data() + first;
     int rc;
-    if (b->flag && 2 * (long long)n_right > 65534)
-        return fail(NR_ERR_TOO_LARGE, "right anchor of %d bases exceeds the flag ladder's range (32767); use nr_set_ladder_mode(1)", n_right);
+    // a template with a base other than ACGT (an anchor with N): the region is not scored -- its reads come back with
+    // top_score 0 ("minimap2 printed nothing", nanoRepeat_bam.py:421) and count as skipped; the batch lives on
+    bool bad_template = false;
+    std::vector<uint32_t> qw;
+    std::vector<int32_t> ql;
     if (b->ladder) {
         // shared sweeps (nr_kernels.cuh, ladder_kernel): the pool holds left + motif^khi once and reverse(right) once
         nr::LadderRegion lr = {};
@@ -976,17 +1085,20 @@ int add_round3(nr_batch* b, const char* left, int32_t n_left, const char* right,
         for (int u = 0; u < std::max(khi, 0); ++u) fwd.append(motif, (size_t)motif_len);
         std::string rev(right ? right : "", (size_t)n_right);
         std::reverse(rev.begin(), rev.end());
-        if ((rc = add_seq(b, fwd.data(), (int)fwd.size(), "ladder prefix", 0, &lr.fwd_word))) return rc;
-        if ((rc = add_seq(b, rev.data(), (int)rev.size(), "right anchor", 0, &lr.rev_word))) return rc;
+        if ((rc = add_seq(b, fwd.data(), (int)fwd.size(), "ladder prefix", 0, &lr.fwd_word)) ||
+            (rc = add_seq(b, rev.data(), (int)rev.size(), "right anchor", 0, &lr.rev_word))) {
+            if (rc != NR_ERR_BAD_BASE) return rc;
+            bad_template = true;
+        }
         const int lreg = (int)b->lregs.size();
         b->lregs.push_back(lr);
-        std::vector<uint32_t> qw;
-        if (!reuse && (rc = add_reads(b, src, n_reads, qw))) return rc;
+        if (!reuse && (rc = add_reads(b, src, n_reads, qw, ql))) return rc;
         for (int r = 0; r < n_reads; ++r) {
             if (roff[r + 1] == roff[r]) continue;
+            if (bad_template) { ++b->n_skipped; continue; }
             nr::LadderTask t = {};
             if (reuse) { t.q_word = reuse[r].q_word; t.q_len = reuse[r].q_len; }
-            else { t.q_word = qw[r]; t.q_len = (int)src.len(r); }
+            else { t.q_word = qw[r]; t.q_len = ql[r]; }
             if (t.q_len == 0) continue;     // every rung scores 0: the outputs are zero-filled
             t.kmin = kmin[r];
             t.kmax = kmax[r];
@@ -998,7 +1110,6 @@ int add_round3(nr_batch* b, const char* left, int32_t n_left, const char* right,
         }
         return NR_OK;
     }
-    if (reuse) return fail(NR_ERR_ARG, "reads of a round-2 batch can only be reused by the ladder kernels (nr_set_ladder_mode 1 or 2)");
     // independent rectangles: left + motif*k + right, one template per distinct k that any read of the region uses
     // (nanoRepeat_bam.py:478-479)
     std::vector<uint32_t> tpl_word;
@@ -1008,30 +1119,52 @@ int add_round3(nr_batch* b, const char* left, int32_t n_left, const char* right,
             for (int k = kmin[r]; k <= kmax[r]; ++k) used[k - klo] = 1;
         tpl_word.assign(khi - klo + 1, 0);
         std::string tpl;
-        for (int k = klo; k <= khi; ++k) {
+        for (int k = klo; k <= khi && !bad_template; ++k) {
             if (!used[k - klo]) continue;
             tpl.assign(left ? left : "", (size_t)n_left);
             for (int u = 0; u < k; ++u) tpl.append(motif, (size_t)motif_len);
             tpl.append(right ? right : "", (size_t)n_right);
-            if ((rc = add_seq(b, tpl.data(), (int)tpl.size(), "ladder template", k, &tpl_word[k - klo]))) return rc;
+            if ((rc = add_seq(b, tpl.data(), (int)tpl.size(), "ladder template", k, &tpl_word[k - klo]))) {
+                if (rc != NR_ERR_BAD_BASE) return rc;
+                bad_template = true;
+            }
         }
     }
+    if ((rc = add_reads(b, src, n_reads, qw, ql))) return rc;
     b->tasks.resize(b->n_out);
     for (int r = 0; r < n_reads; ++r) {
-        if (roff[r + 1] == roff[r]) continue;
-        const long long len = src.len(r);
-        if (len < 0 || len > 0x7fffffffLL) return fail(NR_ERR_ARG, "core %d has a bad length", r);
-        uint32_t qw;
-        if ((rc = add_seq(b, src.ptr(r), (int)len, "core", r, &qw))) return rc;
         for (int k = kmin[r]; k <= kmax[r]; ++k) {
             nr::Task& t = b->tasks[(size_t)(roff[r] + (k - kmin[r]))];
-            t.q_word = qw;
-            t.q_len = (int)len;
-            t.t_word = tpl_word[k - klo];
-            t.t_len = n_left + motif_len * k + n_right;
+            t.q_word = qw[r];
+            t.q_len = ql[r];
+            t.t_word = bad_template ? 0u : tpl_word[k - klo];
+            t.t_len = bad_template ? -1 : n_left + motif_len * k + n_right;      // -1: not scored (plan_batch)
         }
     }
     return NR_OK;
+}
+
+// Validates first; a failure further down (pool overflow, too many rungs) restores the batch to what it was, so the
+// caller may go on adding other regions (like nr_batch_add_round2).
+int add_round3(nr_batch* b, const char* left, int32_t n_left, const char* right, int32_t n_right, const char* motif,
+               int32_t motif_len, int32_t n_reads, const ReadSrc& src, const int32_t* kmin, const int32_t* kmax,
+               const nr::Task* reuse = nullptr) {
+    if (!b || b->kind != KIND_ROUND3 || b->committed) return fail(NR_ERR_ARG, "not an open round-3 batch");
+    if (n_left < 0 || n_right < 0 || motif_len <= 0 || n_reads < 0 || !motif || (n_left > 0 && !left) ||
+        (n_right > 0 && !right) || (n_reads > 0 && (!kmin || !kmax)))
+        return fail(NR_ERR_ARG, "nr_batch_add_round3: bad arguments");
+    const size_t n_regions = b->regions.size(), n_roff = b->rung_off.size(), n_k = b->kmin.size(), n_rr = b->read_region.size(),
+                 n_lregs = b->lregs.size(), n_lt = b->ltasks.size(), n_src = b->lt_src.size(), n_tasks = b->tasks.size(),
+                 n_words = b->pool.words.size(), n_out = b->n_out;
+    const int n_reads0 = b->n_reads, n_skipped0 = b->n_skipped, n_amb0 = b->n_ambiguous_reads;
+    const int rc = add_round3_impl(b, left, n_left, right, n_right, motif, motif_len, n_reads, src, kmin, kmax, reuse);
+    if (rc) {
+        b->regions.resize(n_regions); b->rung_off.resize(n_roff); b->kmin.resize(n_k); b->kmax.resize(n_k);
+        b->read_region.resize(n_rr); b->lregs.resize(n_lregs); b->ltasks.resize(n_lt); b->lt_src.resize(n_src);
+        b->tasks.resize(n_tasks); b->pool.words.resize(n_words);
+        b->n_out = n_out; b->n_reads = n_reads0; b->n_skipped = n_skipped0; b->n_ambiguous_reads = n_amb0;
+    }
+    return rc;
 }
 
 void free_events(nr_batch* b) {
@@ -1087,8 +1220,7 @@ int nr_init(int device) { return ensure_init(device); }
 int nr_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_ctx_mu);
     if (g_ctx.ready) {
-        for (auto& kv : g_ctx.cache.free_dev) for (void* p : kv.second) cudaFree(p);
-        for (auto& kv : g_ctx.cache.free_pin) for (void* p : kv.second) cudaFreeHost(p);
+        trim_cache_locked();
         cudaStreamDestroy(g_ctx.stream);
         g_ctx = Context();
     }
@@ -1123,19 +1255,19 @@ void nr_batch_destroy(nr_batch_t* b) {
     if (--b->refs > 0) return;           // a round-3 batch still reads this batch's packed reads: freed with it
     if (b->committed && b->ev_uploaded) cudaEventSynchronize(b->ev_uploaded);   // buffers return to the cache: the upload
     if (b->ran && b->run_stream) cudaStreamSynchronize(b->run_stream);          // and the kernels must be done
-    cached_free(b->d_blob, b->blob_bytes, false);
-    cached_free(b->h_blob, b->blob_bytes, true);
-    cached_free(b->d_out, b->out_bytes, false);
-    cached_free(b->h_out, b->out_bytes, true);
-    cached_free(b->d_scratch, b->scratch_bytes, false);
-    cached_free(b->d_flags, b->flags_bytes, false);
-    cached_free(b->d_state, b->state_bytes, false);
-    cached_free(b->d_sel, b->sel_bytes, false);
-    cached_free(b->h_sel, b->sel_bytes, true);
-    cached_free(b->d_prung, b->prung_bytes, false);
-    cached_free(b->d_redo, b->redo_bytes, false);
-    cached_free(b->h_redo_count, 64, true);
-    cached_free(b->h_spin, 64, true);
+    cached_free(b->d_blob, b->blob_bytes, BUF_DEV);
+    cached_free(b->h_blob, b->blob_bytes, BUF_PIN);
+    cached_free(b->d_out, b->out_bytes, BUF_DEV);
+    cached_free(b->h_out, b->out_bytes, BUF_PIN);
+    cached_free(b->d_scratch, b->scratch_bytes, BUF_SCRATCH);
+    cached_free(b->d_flags, b->flags_bytes, BUF_DEV);
+    cached_free(b->d_state, b->state_bytes, BUF_DEV);
+    cached_free(b->d_sel, b->sel_bytes, BUF_DEV);
+    cached_free(b->h_sel, b->sel_bytes, BUF_PIN);
+    cached_free(b->d_prung, b->prung_bytes, BUF_DEV);
+    cached_free(b->d_redo, b->redo_bytes, BUF_DEV);
+    cached_free(b->h_redo_count, 64, BUF_PIN);
+    cached_free(b->h_spin, 64, BUF_PIN);
     nr_batch* src = b->qsrc;
     free_events(b);
     delete b;
@@ -1247,7 +1379,9 @@ nr_batch_t* nr_batch_create_tasks(const nr_scoring_t* sc, int32_t n_tasks, const
         for (int s = 0; s < 2; ++s) {
             auto it = seen.find(ptrs[s]);
             if (it != seen.end() && it->second.first == lens[s]) { words[s] = it->second.second; continue; }
-            if (add_seq(b, ptrs[s], lens[s], s ? "target" : "query", i, &words[s])) { nr_batch_destroy(b); return nullptr; }
+            const int rc = add_seq(b, ptrs[s], lens[s], s ? "target" : "query", i, &words[s], /*ambiguous_ok=*/s == 0);
+            if (rc == NR_ERR_BAD_BASE && s == 1) { words[1] = 0; t.t_len = -1; continue; }     // not scored, record (0, 0, 0)
+            if (rc) { nr_batch_destroy(b); return nullptr; }
             seen[ptrs[s]] = std::make_pair(lens[s], words[s]);
         }
         t.q_word = words[0];

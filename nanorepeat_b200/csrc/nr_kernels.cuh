@@ -59,6 +59,7 @@ struct LadderRegion {  // per-region constants of a ladder launch (20 bytes)
 
 struct ScoreW {        // scoring constants as W32 increments
     int sub_match, sub_mismatch;             // (a << 16) - 1, -(b << 16) - 1      (diagonal: one column consumed)
+    int sub_amb;                             // -(sc_ambi << 16) - 1: a read base other than ACGT against any template base
     int h_open1, h_ext1, h_open2, h_ext2;    // horizontal gap: -((q + e) << 16) - 1, -(e << 16) - 1
     int v_open1, v_ext1, v_open2, v_ext2;    // vertical gap:   -((q + e) << 16),     -(e << 16)
     int refund1, refund2;                    // q << 16, q2 << 16: a gap that spans a junction pays its opening once
@@ -76,7 +77,7 @@ template <> struct ScoreView<false> : ScoreW {
     __device__ __forceinline__ explicit ScoreView(const ScoreW& w) : ScoreW(w) {}
 };
 template <> struct ScoreView<true> {
-    static constexpr int sub_match = (2 << 16) - 1, sub_mismatch = -(4 << 16) - 1;
+    static constexpr int sub_match = (2 << 16) - 1, sub_mismatch = -(4 << 16) - 1, sub_amb = -(1 << 16) - 1;
     static constexpr int h_open1 = -(6 << 16) - 1, h_ext1 = -(2 << 16) - 1, h_open2 = -(25 << 16) - 1, h_ext2 = -(1 << 16) - 1;
     static constexpr int v_open1 = -(6 << 16), v_ext1 = -(2 << 16), v_open2 = -(25 << 16), v_ext2 = -(1 << 16);
     static constexpr int refund1 = 4 << 16, refund2 = 24 << 16;
@@ -148,13 +149,32 @@ __device__ __forceinline__ u64 key_of_junction(int khi, int klo) {
 }
 
 // Stripes of one long task run on different warps (any SM) at the same time, each a few dozen columns behind the one
-// above it.  No flags and no fences on the column path: a boundary entry is ONE 16-byte store (H, F1, F2, tag) and one
-// 16-byte load, tag = (run epoch, stripe), so an entry that is not there yet (or is left over from the stripe that used
-// the row before, or from an earlier run) is recognised by its tag and simply read again.
-__device__ __forceinline__ int4 load_bnd(const int4* p) {
-    int4 v;
-    asm volatile("ld.volatile.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+// above it.  No flags and no fences on the column path: a boundary entry (H, F1, F2 of one column) is one 16-byte store
+// and one 16-byte load of TWO 64-bit elements, each carrying 48 bits of the payload and its own 16-bit tag
+// (tag = (run epoch, stripe)).  PTX treats a vector access as independent accesses of its elements, and a 64-bit
+// element access is single-copy atomic: an element whose tag matches holds the payload bits that were stored with that
+// tag, so an entry is taken only when BOTH elements carry the expected tag; an entry that is not there yet (or is left
+// over from the stripe that used the row before, or from an earlier run) is recognised and simply read again.
+//   lo = H | (F1 & 0xffff) << 32 | tag << 48          hi = (F1 >> 16) | F2 << 16 | tag << 48
+// What keeps stale tags apart (host side, nr_api.cu): the scratch comes from a pool of its own that is zeroed when
+// allocated; every launch draws a fresh epoch from 1..1023; a buffer is zeroed again before its first launch in a new
+// "era" (every 1023 launches), so a tag left in it can never equal a tag of the running launch.
+__device__ __forceinline__ ulonglong2 load_bnd(const ulonglong2* p) {
+    ulonglong2 v;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void store_bnd(ulonglong2* p, int h, int f1, int f2, int tag) {
+    const unsigned long long t = (unsigned long long)(unsigned)tag << 48;
+    const unsigned long long lo = (unsigned long long)(unsigned)h | ((unsigned long long)((unsigned)f1 & 0xffffu) << 32) | t;
+    const unsigned long long hi = (unsigned long long)((unsigned)f1 >> 16) | ((unsigned long long)(unsigned)f2 << 16) | t;
+    asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(lo), "l"(hi) : "memory");
+}
+__device__ __forceinline__ bool bnd_valid(const ulonglong2& v, int tag) {
+    return (int)(v.x >> 48) == tag && (int)(v.y >> 48) == tag;
+}
+__device__ __forceinline__ int4 unpack_bnd(const ulonglong2& v) {
+    return make_int4((int)(unsigned)v.x, (int)((unsigned)(v.x >> 32) & 0xffffu) | (int)((unsigned)v.y << 16), (int)(unsigned)(v.y >> 16), 0);
 }
 __device__ __forceinline__ ulonglong2 load_tok(const ulonglong2* p) {
     ulonglong2 v;
@@ -169,13 +189,12 @@ __device__ __forceinline__ int peek_cols(const int* flag) {
 // Safety valve of every wait between stripes: what a stripe waits for is running or done (entries are dealt in
 // dependency order to resident blocks), so a wait ends within the producer's run time.  Should that ever not hold, the
 // warp gives up after a few seconds' worth of retries, raises this flag and runs on with what it has; the host turns
-// the flag into NR_ERR_CUDA instead of a hung GPU.
-__device__ int g_spin_timeout = 0;
+// the flag into NR_ERR_CUDA instead of a hung GPU.  The flag is a word of the batch's own counters (RestArgs::spin).
 constexpr int kSpinLimit = 1 << 23;
-__device__ __forceinline__ void wait_cols(const int* flag, int need, int lane) {
+__device__ __forceinline__ void wait_cols(const int* flag, int need, int lane, int* spin) {
     if (lane == 0)
         for (int tries = 0; peek_cols(flag) < need; ++tries) {
-            if (tries > kSpinLimit) { g_spin_timeout = 1; break; }
+            if (tries > kSpinLimit) { *spin = 1; break; }
             __nanosleep(100);
         }
     __syncwarp();
@@ -233,6 +252,17 @@ struct StripeCfg {
     static constexpr int BVEC_INT4 = R * 32;           // int4 entries per warp: backward junction vectors
 };
 
+// A read in the sequence pool: ceil(len / 16) words of 2-bit codes, then one word that is 0 for a read of ACGT only;
+// otherwise it is the distance (in words, from the read's first word) to a bit plane: bit i & 31 of word i >> 5 says
+// that base i is not ACGT -- minimap2's code 4, scored -sc_ambi against every template base (oracle/nr_oracle.c).
+// The plane costs nothing where there is no such base.
+__device__ __forceinline__ uint32_t read_ambiguity_plane(const uint32_t* __restrict__ qwords, int q_len) {
+    return qwords[(q_len + 15) >> 4];
+}
+__device__ __forceinline__ bool read_base_ambiguous(const uint32_t* __restrict__ qwords, uint32_t plane, int qi) {
+    return (qwords[plane + (qi >> 5)] >> (qi & 31)) & 1u;
+}
+
 // Build the stripe's query profile: prof[(c * CH + chunk) * 32 + lane].{x,y,z,w} = substitution increment of rows
 // 4*chunk..+3 of this lane against target code c.  reverse: the stripe's rows index the reversed query.
 template <int R, class SC>
@@ -240,6 +270,7 @@ __device__ __forceinline__ void build_profile(int4* prof, const uint32_t* __rest
                                               int row0, int lane, const SC& sc, bool reverse) {
     constexpr int CH = StripeCfg<R>::CH;
     int* p = reinterpret_cast<int*>(prof);
+    const uint32_t amb = q_len > 0 ? read_ambiguity_plane(qwords, q_len) : 0u;      // warp-uniform
 #pragma unroll
     for (int r = 0; r < 4 * CH; ++r) {
         const int i = row0 + r;
@@ -247,10 +278,11 @@ __device__ __forceinline__ void build_profile(int4* prof, const uint32_t* __rest
         if (r < R && i < q_len) {
             const int qi = reverse ? q_len - 1 - i : i;
             code = (qwords[qi >> 4] >> (30 - 2 * (qi & 15))) & 3;
+            if (amb && read_base_ambiguous(qwords, amb, qi)) code = 5;
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const int v = (code == 4) ? kPadScore : (code == c ? sc.sub_match : sc.sub_mismatch);
+            const int v = (code == 4) ? kPadScore : code == 5 ? sc.sub_amb : (code == c ? sc.sub_match : sc.sub_mismatch);
             p[((c * CH + (r >> 2)) * 32 + lane) * 4 + (r & 3)] = v;
         }
     }
@@ -268,9 +300,10 @@ __device__ __forceinline__ int bvec_pos(int idx0) {
 // bit 0 for the forward mark), 0 for the forward sweep of the flag ladder (the low half holds only the mark).
 template <class SC, int DEC>
 struct ModeScore {
-    int sub_match, sub_mismatch, h_open1, h_ext1, h_open2, h_ext2, v_open1, v_ext1, v_open2, v_ext2, one;
+    int sub_match, sub_mismatch, sub_amb, h_open1, h_ext1, h_open2, h_ext2, v_open1, v_ext1, v_open2, v_ext2, one;
     __device__ __forceinline__ explicit ModeScore(const SC& sc)
-        : sub_match(sc.sub_match + 1 - DEC), sub_mismatch(sc.sub_mismatch + 1 - DEC), h_open1(sc.h_open1 + 1 - DEC),
+        : sub_match(sc.sub_match + 1 - DEC), sub_mismatch(sc.sub_mismatch + 1 - DEC), sub_amb(sc.sub_amb + 1 - DEC),
+          h_open1(sc.h_open1 + 1 - DEC),
           h_ext1(sc.h_ext1 + 1 - DEC), h_open2(sc.h_open2 + 1 - DEC), h_ext2(sc.h_ext2 + 1 - DEC), v_open1(sc.v_open1),
           v_ext1(sc.v_ext1), v_open2(sc.v_open2), v_ext2(sc.v_ext2), one(sc.one) {}
 };
@@ -303,9 +336,10 @@ struct Sweep {
     const uint32_t* twords;
     int t_len, lane;
     bool top, bot;
-    const int4* bnd_in;
-    int4* bnd_out;
+    const ulonglong2* bnd_in;
+    ulonglong2* bnd_out;
     int tag_in, tag_out;           // MULTI: what marks an entry written by the stripe above / by this stripe in this run
+    int* spin;                     // MULTI: the batch's give-up flag (RestArgs::spin)
     // backward sweeps
     int4* bdst;
     int q_len, brow0;
@@ -336,7 +370,8 @@ struct Sweep {
     uint32_t twl, w0, w1;          // target window (MSB first) and the two words the next window is cut from
     int wi, wmax, wsh;
     const char* prof_lane;
-    int4 bcur, bnxt;
+    int4 bcur;                     // MULTI: boundary entries of the current 32 columns (lane l: column block + l), unpacked
+    ulonglong2 bnxt;               //        and of the next 32, as loaded (validated when they are taken over)
     u64 tokP, tokJ;                // kFwd: 64-bit keys; kFwdF: 32-bit words in the low halves
 
     __device__ __forceinline__ uint32_t tword(int i) const { return __ldg(&twords[min(max(i, 0), wmax)]); }
@@ -355,7 +390,7 @@ struct Sweep {
         w0 = tword(wi); w1 = tword(wi + 1);
         twl = 0;
         prof_lane = reinterpret_cast<const char*>(prof + lane);
-        bcur = make_int4(0, 0, 0, 0); bnxt = make_int4(0, 0, 0, 0);
+        bcur = make_int4(0, 0, 0, 0); bnxt = make_ulonglong2(0ull, 0ull);
         if (MULTI && top) bnxt = load_bnd(&bnd_in[lane < t_len ? lane : t_len - 1]);   // checked when it is taken over
         tokP = 0; tokJ = 0;
     }
@@ -458,15 +493,16 @@ struct Sweep {
         int mul0;
         if (MULTI && top) {                 // uniform branch
             if ((st & 31) == 0) {
-                bcur = bnxt;
+                ulonglong2 raw = bnxt;
                 const int cj = st + lane;       // the column this lane's entry stands for
                 // a stripe right behind its producer finds the entries it asked for 32 steps ago not written yet: it reads
                 // them again (one L2 round trip), falls back a little, and from then on its prefetches arrive valid
-                for (int tries = 0; !__all_sync(kFull, bcur.w == tag_in || cj >= t_len); ++tries) {
-                    if (tries > kSpinLimit) { g_spin_timeout = 1; break; }
+                for (int tries = 0; !__all_sync(kFull, bnd_valid(raw, tag_in) || cj >= t_len); ++tries) {
+                    if (tries > kSpinLimit) { *spin = 1; break; }
                     if (tries > 3) __nanosleep(32);
-                    bcur = load_bnd(&bnd_in[cj < t_len ? cj : t_len - 1]);
+                    raw = load_bnd(&bnd_in[cj < t_len ? cj : t_len - 1]);
                 }
+                bcur = unpack_bnd(raw);
                 const int nj = st + 32 + lane;
                 bnxt = load_bnd(&bnd_in[nj < t_len ? nj : t_len - 1]);      // in flight for the next 32 steps
             }
@@ -533,14 +569,14 @@ struct Sweep {
             if (junc) {
                 if (MODE == kFwdF) {
                     if (lane == 0) {
-                        if (MULTI && top) {     // the token carries its tag in the upper half of x
+                        if (MULTI && top) {     // both 64-bit elements of the token carry the tag in their upper half
                             ulonglong2 t = load_tok(&tok_in[kcnt]);
-                            for (int tries = 0; (int)(t.x >> 32) != tag_in; ++tries) {
-                                if (tries > kSpinLimit) { g_spin_timeout = 1; break; }
+                            for (int tries = 0; (int)(t.x >> 32) != tag_in || (int)(t.y >> 32) != tag_in; ++tries) {
+                                if (tries > kSpinLimit) { *spin = 1; break; }
                                 if (tries > 3) __nanosleep(32);
                                 t = load_tok(&tok_in[kcnt]);
                             }
-                            tP = (unsigned)t.x; tJ = t.y;
+                            tP = (unsigned)t.x; tJ = (unsigned)t.y;
                         } else { tP = 0; tJ = (unsigned)kJuncNone; }
                     }
                     // rung 0's junction column is the left flank's last column: every forward part that scores has
@@ -549,7 +585,7 @@ struct Sweep {
                     const int myP = max((int)tP, best), myJ = max((int)tJ, jj == mark_col ? jhi - 1 : jhi);
                     tokP = (unsigned)myP; tokJ = (unsigned)myJ;
                     if (lane == 31) {
-                        if (MULTI && bot) __stcg(&tok_out[kcnt], make_ulonglong2(tokP | ((u64)(unsigned)tag_out << 32), tokJ));
+                        if (MULTI && bot) __stcg(&tok_out[kcnt], make_ulonglong2(tokP | ((u64)(unsigned)tag_out << 32), tokJ | ((u64)(unsigned)tag_out << 32)));
                         else {
                             const int4 rec = finalize_flag_rung(myP, myJ, rcand);
                             out[kcnt] = rec;
@@ -559,8 +595,9 @@ struct Sweep {
                 } else {
                     junction_unbias(jhi, jlo);
                     if (lane == 0) {
-                        // (its store was fenced before the boundary entry of this column, which this stripe has seen)
-                        if (MULTI && top) { const ulonglong2 t = load_tok(&tok_in[kcnt]); tP = t.x; tJ = t.y; }
+                        // (its store was fenced before the boundary entry of this column, which this stripe has seen; the
+                        // fence on this side orders the token load behind that observation)
+                        if (MULTI && top) { __threadfence(); const ulonglong2 t = load_tok(&tok_in[kcnt]); tP = t.x; tJ = t.y; }
                         else { tP = 0; tJ = 0; }
                     }
                     const u64 myP = key_of_best(best, best_col()), myJ = key_of_junction(jhi, jlo);
@@ -574,14 +611,14 @@ struct Sweep {
                 jnext += m;
                 ++kcnt;
             }
-            if (MULTI && bot && lane == 31) __stcg(&bnd_out[jj], make_int4(h_out, f1_out, f2_out, tag_out));
+            if (MULTI && bot && lane == 31) store_bnd(&bnd_out[jj], h_out, f1_out, f2_out, tag_out);
         }
     }
 
     __device__ __forceinline__ void late_load() {
         u64 rkey = 0;
         if (bglob_rows) {
-            wait_cols(bdone, bdone_need, lane);
+            wait_cols(bdone, bdone_need, lane, spin);
             rkey = __ldcg(reinterpret_cast<const u64*>(bdone + 2));
         }
 #pragma unroll
@@ -684,8 +721,20 @@ struct CoopInfo {
     int rows;               // rows per lane of every stripe (the host picks from a short list, see plan_batch)
 };
 constexpr int kCoopFlagInts(int S) { return 2 * S + 4; }
-// tag of the entries stripe s writes in the run with this epoch (the host counts runs; never 0)
-__device__ __forceinline__ int stripe_tag(int epoch, int s) { return (epoch << 6) | (s & 63); }
+// 16-bit tag of the entries stripe s writes in the launch with this epoch (1..1023, drawn by the host; never 0)
+__device__ __forceinline__ int stripe_tag(int epoch, int s) { return ((epoch & 0x3ff) << 6) | (s & 63); }
+
+// what the 32-bit kernels need beside the tasks (also handed to the fused kernels of nr_pair_kernels.cuh)
+struct RestArgs {
+    const int32_t* order;       // entries, (task << 7) | code
+    int n_order;
+    int4* scratch;
+    const CoopInfo* coop;
+    const int32_t* coop_idx;    // exact tasks only (ladder tasks carry theirs)
+    int* flags;
+    int* spin;                  // set to 1 by a warp that gave up waiting for another stripe (see wait_cols)
+    int epoch;
+};
 
 template <int R, class SC>
 __device__ __forceinline__ u64 exact_task(const Task& tk, const uint32_t* __restrict__ pool, const SC& sc, int4* prof, int lane) {
@@ -709,12 +758,13 @@ __device__ __forceinline__ u64 exact_dispatch(int r, const Task& tk, const uint3
 
 // One stripe of a multi-stripe task; the stripe that finishes last writes the record.
 template <int R, class SC>
-__device__ __forceinline__ void exact_stripe(const Task& tk, int tid, int s, const CoopInfo& ci, int epoch, int4* scratch, int* flags,
+__device__ __forceinline__ void exact_stripe(const Task& tk, int tid, int s, const CoopInfo& ci, const RestArgs& ra,
                                              const uint32_t* __restrict__ pool, const SC& sc, int4* prof, int lane, int4* out) {
     const int S = ci.n_stripes;
-    int* F = flags + ci.flag_off;
-    int4* bnd_a = scratch + ci.data_off;
-    int4* bnd_b = bnd_a + ci.bnd_stride;
+    const int epoch = ra.epoch;
+    int* F = ra.flags + ci.flag_off;
+    ulonglong2* bnd_a = reinterpret_cast<ulonglong2*>(ra.scratch + ci.data_off);
+    ulonglong2* bnd_b = bnd_a + ci.bnd_stride;
     __syncwarp();
     build_profile<R>(prof, pool + tk.q_word, tk.q_len, s * 32 * R + lane * R, lane, ModeScore<SC, 1>(sc), false);
     __syncwarp();
@@ -722,7 +772,7 @@ __device__ __forceinline__ void exact_stripe(const Task& tk, int tid, int s, con
     sw.prof = prof; sw.twords = pool + tk.t_word; sw.t_len = tk.t_len; sw.lane = lane;
     sw.top = s > 0; sw.bot = s + 1 < S;
     sw.bnd_in = (s & 1) ? bnd_a : bnd_b; sw.bnd_out = (s & 1) ? bnd_b : bnd_a;
-    sw.tag_in = stripe_tag(epoch, s - 1); sw.tag_out = stripe_tag(epoch, s);
+    sw.tag_in = stripe_tag(epoch, s - 1); sw.tag_out = stripe_tag(epoch, s); sw.spin = ra.spin;
     sw.run(sc, 0);
     const u64 key = warp_max64(key_of_best(sw.best, sw.best_col()));
     if (lane == 0) {
@@ -737,12 +787,12 @@ __device__ __forceinline__ void exact_stripe(const Task& tk, int tid, int s, con
 }
 
 template <int R, class SC>
-__device__ __forceinline__ void exact_stripe_dispatch(int r, const Task& tk, int tid, int s, const CoopInfo& ci, int epoch, int4* scratch,
-                                                      int* flags, const uint32_t* __restrict__ pool, const SC& sc, int4* prof,
+__device__ __forceinline__ void exact_stripe_dispatch(int r, const Task& tk, int tid, int s, const CoopInfo& ci, const RestArgs& ra,
+                                                      const uint32_t* __restrict__ pool, const SC& sc, int4* prof,
                                                       int lane, int4* out) {
     if constexpr (is_coop_height(R))
-        if (r == R) { exact_stripe<R>(tk, tid, s, ci, epoch, scratch, flags, pool, sc, prof, lane, out); return; }
-    if constexpr (R < kMaxRExact) exact_stripe_dispatch<R + 1>(r, tk, tid, s, ci, epoch, scratch, flags, pool, sc, prof, lane, out);
+        if (r == R) { exact_stripe<R>(tk, tid, s, ci, ra, pool, sc, prof, lane, out); return; }
+    if constexpr (R < kMaxRExact) exact_stripe_dispatch<R + 1>(r, tk, tid, s, ci, ra, pool, sc, prof, lane, out);
 }
 
 // Rows per lane of a long task that the host cut into n_stripes stripes (few long tasks: short stripes, so that more
@@ -783,16 +833,6 @@ struct TaskCursor {
 // Exact (score, tstart, tend) kernel.  Persistent: the stripe height and the single- / multi-stripe path are picked
 // per entry (warp-uniform dispatch), so one launch covers a whole batch, long expanded alleles included.
 // out[] is indexed by task id.  smem_stride: int4 of shared memory per warp.
-// what the 32-bit kernels need beside the tasks (also handed to the fused kernels of nr_pair_kernels.cuh)
-struct RestArgs {
-    const int32_t* order;       // entries, (task << 7) | code
-    int n_order;
-    int4* scratch;
-    const CoopInfo* coop;
-    const int32_t* coop_idx;    // exact tasks only (ladder tasks carry theirs)
-    int* flags;
-    int epoch;
-};
 
 template <class SC>
 __device__ __forceinline__ void exact_entry(int e, const Task* __restrict__ tasks, const uint32_t* __restrict__ pool, const SC& sc,
@@ -806,7 +846,7 @@ __device__ __forceinline__ void exact_entry(int e, const Task* __restrict__ task
         if (lane == 0) out[tid] = finalize_rung(key, 0ull, 0, 0, 0, 0);
     } else {
         const CoopInfo ci = ra.coop[ra.coop_idx[tid]];
-        exact_stripe_dispatch<kMinR>(ci.rows, tk, tid, code - 1, ci, ra.epoch, ra.scratch, ra.flags, pool, sc, prof, lane, out);
+        exact_stripe_dispatch<kMinR>(ci.rows, tk, tid, code - 1, ci, ra, pool, sc, prof, lane, out);
     }
 }
 
@@ -948,14 +988,15 @@ __device__ __forceinline__ void ladder_task(const LadderTask& tk, const LadderCt
 }
 
 template <int R, bool FLAG, class SC>
-__device__ __forceinline__ void ladder_bwd_stripe(const LadderTask& tk, const LadderCtx& cx, int s, const CoopInfo& ci, int epoch,
-                                                  int4* scratch, int* flags, const SC& sc, int4* prof, int lane) {
+__device__ __forceinline__ void ladder_bwd_stripe(const LadderTask& tk, const LadderCtx& cx, int s, const CoopInfo& ci,
+                                                  const RestArgs& ra, const SC& sc, int4* prof, int lane) {
     constexpr int BWD = FLAG ? kBwdF : kBwd;
     const int S = ci.n_stripes;
-    int* F = flags + ci.flag_off;
-    int4* bnd_a = scratch + ci.data_off;
-    int4* bnd_b = bnd_a + ci.bnd_stride;
-    int4* bglob = bnd_b + 3 * ci.bnd_stride;
+    const int epoch = ra.epoch;
+    int* F = ra.flags + ci.flag_off;
+    ulonglong2* bnd_a = reinterpret_cast<ulonglong2*>(ra.scratch + ci.data_off);
+    ulonglong2* bnd_b = bnd_a + ci.bnd_stride;
+    int4* bglob = ra.scratch + ci.data_off + 4 * ci.bnd_stride;
     __syncwarp();
     build_profile<R>(prof, cx.qwords, cx.q_len, s * 32 * R + lane * R, lane, ModeScore<SC, Sweep<R, BWD, true>::DEC>(sc), true);
     __syncwarp();
@@ -963,7 +1004,7 @@ __device__ __forceinline__ void ladder_bwd_stripe(const LadderTask& tk, const La
     sw.prof = prof; sw.twords = cx.pool + cx.reg.rev_word; sw.t_len = cx.reg.n_right; sw.lane = lane;
     sw.top = s > 0; sw.bot = s + 1 < S;
     sw.bnd_in = (s & 1) ? bnd_a : bnd_b; sw.bnd_out = (s & 1) ? bnd_b : bnd_a;
-    sw.tag_in = stripe_tag(epoch, s - 1); sw.tag_out = stripe_tag(epoch, s);
+    sw.tag_in = stripe_tag(epoch, s - 1); sw.tag_out = stripe_tag(epoch, s); sw.spin = ra.spin;
     sw.bdst = bglob; sw.q_len = cx.q_len; sw.brow0 = s * 32 * R + lane * R;
     sw.run(sc, 0);
     int key, col;
@@ -978,15 +1019,16 @@ __device__ __forceinline__ void ladder_bwd_stripe(const LadderTask& tk, const La
 }
 
 template <int R, bool FLAG, class SC>
-__device__ __forceinline__ void ladder_fwd_stripe(const LadderTask& tk, const LadderCtx& cx, int s, const CoopInfo& ci, int epoch,
-                                                  int4* scratch, int* flags, const SC& sc, int4* prof, int lane, int4* out,
+__device__ __forceinline__ void ladder_fwd_stripe(const LadderTask& tk, const LadderCtx& cx, int s, const CoopInfo& ci,
+                                                  const RestArgs& ra, const SC& sc, int4* prof, int lane, int4* out,
                                                   int4* sel) {
     constexpr int FWD = FLAG ? kFwdF : kFwd;
     const int S = ci.n_stripes;
-    int* F = flags + ci.flag_off;
-    int4* bnd_a = scratch + ci.data_off + 2 * ci.bnd_stride;
-    int4* bnd_b = bnd_a + ci.bnd_stride;
-    int4* bglob = bnd_b + ci.bnd_stride;
+    const int epoch = ra.epoch;
+    int* F = ra.flags + ci.flag_off;
+    ulonglong2* bnd_a = reinterpret_cast<ulonglong2*>(ra.scratch + ci.data_off + 2 * ci.bnd_stride);
+    ulonglong2* bnd_b = bnd_a + ci.bnd_stride;
+    int4* bglob = ra.scratch + ci.data_off + 4 * ci.bnd_stride;
     ulonglong2* tok_a = reinterpret_cast<ulonglong2*>(bglob + ci.b_stride);
     ulonglong2* tok_b = tok_a + ci.tok_stride;
     int4* bsm = prof + StripeCfg<R>::PROF_INT4;
@@ -998,6 +1040,7 @@ __device__ __forceinline__ void ladder_fwd_stripe(const LadderTask& tk, const La
     sw.bdone = F + 2 * S; sw.bdone_need = S; sw.n_right = cx.reg.n_right;
     sw.q_len = cx.q_len; sw.brow0 = s * 32 * R + lane * R;
     sw.late_pending = true;
+    sw.spin = ra.spin;
     __syncwarp();
     if (sw.t_len == 0 || cx.reg.n_left + cx.reg.m * tk.kmin == 0) {
         // no sweep, or rung 0 of a region without a left flank (its record is the R-only class alone): needs the
@@ -1028,16 +1071,16 @@ __device__ __forceinline__ void ladder_dispatch(int r, const LadderTask& tk, con
 }
 
 template <int R, bool FLAG, class SC>
-__device__ __forceinline__ void ladder_stripe_dispatch(int r, const LadderTask& tk, const LadderCtx& cx, int code, const CoopInfo& ci, int epoch,
-                                                       int4* scratch, int* flags, const SC& sc, int4* prof, int lane, int4* out,
+__device__ __forceinline__ void ladder_stripe_dispatch(int r, const LadderTask& tk, const LadderCtx& cx, int code, const CoopInfo& ci,
+                                                       const RestArgs& ra, const SC& sc, int4* prof, int lane, int4* out,
                                                        int4* sel) {
     if constexpr (is_coop_height(R))
         if (r == R) {
-            if (code < kCodeFwd) ladder_bwd_stripe<R, FLAG>(tk, cx, code - 1, ci, epoch, scratch, flags, sc, prof, lane);
-            else ladder_fwd_stripe<R, FLAG>(tk, cx, code - kCodeFwd, ci, epoch, scratch, flags, sc, prof, lane, out, sel);
+            if (code < kCodeFwd) ladder_bwd_stripe<R, FLAG>(tk, cx, code - 1, ci, ra, sc, prof, lane);
+            else ladder_fwd_stripe<R, FLAG>(tk, cx, code - kCodeFwd, ci, ra, sc, prof, lane, out, sel);
             return;
         }
-    if constexpr (R < kMaxRLadder) ladder_stripe_dispatch<R + 1, FLAG>(r, tk, cx, code, ci, epoch, scratch, flags, sc, prof, lane, out, sel);
+    if constexpr (R < kMaxRLadder) ladder_stripe_dispatch<R + 1, FLAG>(r, tk, cx, code, ci, ra, sc, prof, lane, out, sel);
 }
 
 template <bool FLAG, class SC>
@@ -1057,7 +1100,7 @@ __device__ __forceinline__ void ladder_entry(int e, const LadderTask* __restrict
         ladder_dispatch<kMinR, FLAG>(R, tk, cx, sc, prof, lane, out, sel);
     } else {
         const CoopInfo ci = ra.coop[tk.pad];
-        ladder_stripe_dispatch<kMinR, FLAG>(ci.rows, tk, cx, code, ci, ra.epoch, ra.scratch, ra.flags, sc, prof, lane, out, sel);
+        ladder_stripe_dispatch<kMinR, FLAG>(ci.rows, tk, cx, code, ci, ra, sc, prof, lane, out, sel);
     }
 }
 

@@ -38,7 +38,7 @@ __host__ __device__ constexpr u32 pk(int v) { return pk2(v, v); }
 __host__ __device__ constexpr u32 sub2(int v) { return 0u - (((u32)v << 16) | (u32)v); }
 
 // map-ont (the reference's only scoring, tk.py:502-517) in doubled units: bit 0 of a word is the mark
-constexpr int kMatch = 4, kMismatch = 8, kOpen1 = 12, kExt1 = 4, kOpen2 = 50, kExt2 = 2, kRefund1 = 8, kRefund2 = 48;
+constexpr int kMatch = 4, kMismatch = 8, kAmbiguous = 2, kOpen1 = 12, kExt1 = 4, kOpen2 = 50, kExt2 = 2, kRefund1 = 8, kRefund2 = 48;
 constexpr u32 kFloorFwd = pk(kBias + 1);     // score 0, unmarked
 constexpr u32 kFloorBwd = pk(kBias);         // backward words: bit 0 stays clear, so forward + backward keeps the mark
 constexpr u32 kOnes = 0x00010001u;
@@ -87,6 +87,8 @@ __device__ __forceinline__ void build_profile(uint4* prof, const uint32_t* __res
                                               const uint32_t* __restrict__ qb, int q_b, int row0, int lane, bool reverse) {
     constexpr int CH = StripeCfg<R>::CH;
     u32* p = reinterpret_cast<u32*>(prof);
+    // a read base other than ACGT (code 5) scores -sc_ambi against every template base (nr_kernels.cuh, build_profile)
+    const uint32_t amb_a = q_a > 0 ? read_ambiguity_plane(qa, q_a) : 0u, amb_b = q_b > 0 ? read_ambiguity_plane(qb, q_b) : 0u;
 #pragma unroll
     for (int r = 0; r < 4 * CH; ++r) {
         const int i = row0 + r;
@@ -94,14 +96,17 @@ __device__ __forceinline__ void build_profile(uint4* prof, const uint32_t* __res
         if (r < R && i < q_a) {
             const int qi = reverse ? q_a - 1 - i : i;
             ca = (qa[qi >> 4] >> (30 - 2 * (qi & 15))) & 3;
+            if (amb_a && read_base_ambiguous(qa, amb_a, qi)) ca = 5;
         }
         if (r < R && i < q_b) {
             const int qi = reverse ? q_b - 1 - i : i;
             cb = (qb[qi >> 4] >> (30 - 2 * (qi & 15))) & 3;
+            if (amb_b && read_base_ambiguous(qb, amb_b, qi)) cb = 5;
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-            p[((c * CH + (r >> 2)) * 32 + lane) * 4 + (r & 3)] = pk2(ca == c ? kMatch : -kMismatch, cb == c ? kMatch : -kMismatch);
+            p[((c * CH + (r >> 2)) * 32 + lane) * 4 + (r & 3)] =
+                pk2(ca == 5 ? -kAmbiguous : ca == c ? kMatch : -kMismatch, cb == 5 ? -kAmbiguous : cb == c ? kMatch : -kMismatch);
     }
 }
 

@@ -23,7 +23,7 @@ class Scoring(ctypes.Structure):
 
 class Stats(ctypes.Structure):
     _fields_ = [("algorithmic_cells", ctypes.c_int64), ("executed_cells", ctypes.c_int64),
-                ("n_tasks", ctypes.c_int64), ("kernel_launches", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("n_tasks", ctypes.c_int64), ("kernel_launches", ctypes.c_int32), ("n_skipped", ctypes.c_int32),
                 ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64)]
 
     def as_dict(self):
@@ -183,7 +183,7 @@ def _concat(seqs):
     if n == 0:
         return b"", off
     if isinstance(seqs[0], str):
-        buf = "".join(seqs).encode("ascii", "replace")     # a non-ASCII character becomes '?': NR_ERR_BAD_BASE
+        buf = "".join(seqs).encode("ascii", "replace")     # a non-ASCII character becomes '?': an ambiguous base
     else:
         buf = b"".join(seqs)
     np.cumsum(np.fromiter(map(len, seqs), dtype=np.int64, count=n), out=off[1:])
@@ -269,9 +269,9 @@ class Batch:
         self._kmax.append(kmax)
         return self
 
-    def add_round2(self, left, motif, T, cores):
+    def add_round2(self, left, motif, T, cores, lines=True):
         lb, mb = _b(left), _b(motif)
-        if cores and isinstance(cores[0], str):
+        if lines and cores and isinstance(cores[0], str):
             # one join, no per-read lengths, no encode: the joined str's own (ASCII == UTF-8) buffer crosses the ABI
             joined = "\n".join(cores)
             size = ctypes.c_ssize_t()

@@ -55,13 +55,16 @@ def _round2_launch(data_type, repeat_regions):
         return None
     b = engine.Batch.begin(sc, "round2_flags")      # the selection reads AS, tend and tstart <= |left| only (:373-384)
     for (left, motif, T), (rr, qnames) in zip(specs, todo):
+        # white space around a core is dropped by the library (the reference's FASTQ round trip drops it, :311-321); a
+        # base other than ACGT is scored as minimap2 scores N; an anchor with such a base or a core beyond the packed
+        # range leaves its reads without a size instead of failing the call (include/nanorepeat_b200.h, "Sequences")
         cores = _cores_of(rr, qnames)
         try:
             b.add_round2(left, motif, T, cores)
         except engine.NanoRepeatB200Error as e:
-            if e.code != -3:                                                    # NR_ERR_BAD_BASE: maybe just whitespace,
-                raise                                                           # which the reference's FASTQ round trip drops
-            b.add_round2(left, motif, T, [c.strip() for c in cores])         # a failed add leaves the batch untouched
+            if e.code != -3:
+                raise
+            b.add_round2(left, motif, T, [c.strip() for c in cores], lines=False)      # a core with a newline inside
     b.commit().run()                                                            # was pymm2.main at :362; asynchronous
     return b, todo, specs, min_score
 

@@ -184,6 +184,7 @@ int nro_align(const nro_scoring_t* sc, const char* query, int32_t qlen,
 typedef struct {
     const nro_scoring_t* sc;
     int32_t n_items;
+    int32_t n_reads;            /* ladder mode: reads (n_items = rungs) */
     volatile int32_t next;      /* claimed with __sync_fetch_and_add */
     volatile int rc;
     /* batch mode */
@@ -208,10 +209,18 @@ static void* worker(void* arg) {
         int32_t t = __sync_fetch_and_add(&w->next, 1);
         if (t >= w->n_items) break;
         int r;
-        if (w->ladder)
-            r = nro_align_ladder(w->sc, w->cores[t], w->core_len[t], w->left, w->n_left, w->right, w->n_right,
-                                 w->motif, w->m, w->kmin[t], w->kmax[t], w->out + w->rung_offset[t]);
-        else
+        if (w->ladder) {
+            /* one work item per RUNG (a long expanded allele has up to 301 of them, 10^8 cells each): find the read
+               whose rung range holds item t, then score that one rung as its own rectangle */
+            int32_t lo = 0, hi = w->n_reads;             /* rung_offset[lo] <= t < rung_offset[hi] */
+            while (hi - lo > 1) {
+                int32_t mid = lo + (hi - lo) / 2;
+                if (w->rung_offset[mid] <= (int64_t)t) lo = mid; else hi = mid;
+            }
+            int32_t k = w->kmin[lo] + (int32_t)((int64_t)t - w->rung_offset[lo]);
+            r = nro_align_ladder(w->sc, w->cores[lo], w->core_len[lo], w->left, w->n_left, w->right, w->n_right,
+                                 w->motif, w->m, k, k, w->out + t);
+        } else
             r = nro_align(w->sc, w->queries[t], w->qlen[t], w->targets[t], w->tlen[t], &w->out[t]);
         if (r != 0) w->rc = -1;
     }
@@ -280,7 +289,9 @@ int nro_align_ladders(const nro_scoring_t* sc, int32_t n_reads,
                       nro_aln_t* out, int32_t n_threads)
 {
     work_t w; memset(&w, 0, sizeof w);
-    w.sc = sc; w.n_items = n_reads; w.cores = cores; w.core_len = core_len;
+    if (n_reads <= 0 || rung_offset[n_reads] <= 0) return 0;
+    if (rung_offset[n_reads] > 0x7fffffffLL) return -1;
+    w.sc = sc; w.n_items = (int32_t)rung_offset[n_reads]; w.n_reads = n_reads; w.cores = cores; w.core_len = core_len;
     w.left = left; w.n_left = n_left; w.right = right; w.n_right = n_right; w.motif = motif; w.m = m;
     w.kmin = kmin; w.kmax = kmax; w.rung_offset = rung_offset; w.out = out; w.ladder = 1;
     return run_pool(&w, n_threads);

@@ -20,7 +20,7 @@ def load_golden(name):
         return json.load(f)
 
 
-GOLDEN_SETS = ["cfg1_small", "cfg2_small", "cfg3_small", "cfg5_small_fast", "crafted"]
+GOLDEN_SETS = ["cfg1_small", "cfg2_small", "cfg3_small", "cfg4_small", "cfg5_small", "cfg5_small_fast", "crafted"]
 
 
 @pytest.fixture(scope="session")

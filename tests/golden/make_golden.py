@@ -10,7 +10,7 @@ prints PAF lines whose AS/tstart/tend come from the oracle DP (oracle/nr_oracle.
 everything the reference itself decides (task generation, int() truncations, span predicates, tie
 averaging, fall-backs) and record the oracle DP's numbers for the engine part (PARITY UNPINNED there).
 
-Usage: python tests/golden/make_golden.py        (rewrites the fixtures in place)
+Usage: python tests/golden/make_golden.py [name ...]   (rewrites the named fixtures, default all, in place)
 """
 import json
 import os
@@ -181,7 +181,14 @@ def main():
     fixtures["cfg3_small"] = (synth.config3(seed=3, n_loci=4, reads_per_locus=4), False)
     fixtures["cfg5_small_fast"] = (synth.config5(seed=5, n_reads=12, reads_per_region=3, k_max=120), True)
     fixtures["crafted"] = (crafted_regions(), False)
+    # the long shapes: config 4's expansions (C9orf72 ~6.4 kb core x 101 rungs, FMR1 ~1.7 kb x 51) and config 5 with the
+    # full ladder rule (cores up to 10.6 kb, up to 167 rungs) -- a minute of oracle time each
+    fixtures["cfg4_small"] = (synth.config4(seed=4, reads_per_locus=5), False)
+    fixtures["cfg5_small"] = (synth.config5(seed=8, n_reads=8, reads_per_region=2, k_max=2000), False)
+    only = set(sys.argv[1:])
     for name, (regs, fast_mode) in fixtures.items():
+        if only and name not in only:
+            continue
         doc = dict(fast_mode=fast_mode, scoring={n: getattr(SC, n) for n, _ in nr_oracle.Scoring._fields_},
                    generated_by="tests/golden/make_golden.py (reference functions from /root/reference, DP from oracle)",
                    regions=[])

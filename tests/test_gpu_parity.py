@@ -118,16 +118,132 @@ def test_empty_and_degenerate_inputs(engine):
 
 def test_errors_are_reported_not_fatal(engine):
     sc = engine.get_preset("ont")
-    with pytest.raises(engine.NanoRepeatB200Error) as ei:
-        engine.score_tasks(["ACGTN"], ["ACGT"], sc)
-    assert ei.value.code == -3
-    with pytest.raises(engine.NanoRepeatB200Error) as ei:
-        engine.score_tasks(["A" * 20000], ["A" * 20000], sc)
-    assert ei.value.code == -4
     with pytest.raises(ValueError):
         engine.get_preset("pacbio")
+    with pytest.raises(engine.NanoRepeatB200Error) as ei:
+        engine.Batch.begin(sc, "round3").add_round3("ACGT", "ACGT", "CAG", ["ACGT"], [-1], [3])
+    assert ei.value.code == -2
     # the library is still usable afterwards
     assert tuple(int(v) for v in engine.score_tasks(["ACGT"], ["ACGT"], sc)[0]) == (8, 0, 4)
+
+
+def test_unscorable_tasks_are_isolated_not_fatal(engine, oracle):
+    """One read beyond the packed range, one template with an N: their records are zero ("the aligner printed nothing"),
+    nr_stats_t.n_skipped counts them, and every other task of the same call is scored as usual."""
+    rng = random.Random(5)
+    sc = engine.get_preset("ont")
+    good_q = [_rand_seq(rng, rng.randint(30, 700)) for _ in range(6)]
+    good_t = [_rand_seq(rng, 20) + _mutate(rng, q, 0.05) + _rand_seq(rng, 20) for q in good_q]
+    qs = good_q[:3] + ["A" * 20000, "ACGTACGTAC"] + good_q[3:]
+    ts = good_t[:3] + ["A" * 20000, "ACGTNCGTAC"] + good_t[3:]
+    b = engine.Batch.tasks(sc, qs, ts)
+    got = b.run().fetch_alns()
+    assert b.stats()["n_skipped"] == 2
+    b.close()
+    ref = oracle.align_batch(good_q, good_t)
+    _assert_same(np.concatenate([got[:3], got[5:]]), ref, "tasks beside the skipped ones")
+    assert [tuple(int(v) for v in g) for g in got[3:5]] == [(0, 0, 0)] * 2
+    # operator layer: a region whose left anchor holds an N sits between two normal regions
+    import nanorepeat_b200 as nrb
+    from nanorepeat_b200 import synth
+    regs = synth.config1(seed=41, n_regions=3, reads_per_region=8)
+    plain = [nrb.RepeatRegion.from_synth(r) for r in regs]
+    nrb.estimate_regions(plain, "ont", False)
+    mixed = [nrb.RepeatRegion.from_synth(r) for r in regs]
+    mixed[1].left_anchor_seq = mixed[1].left_anchor_seq[:500] + "N" + mixed[1].left_anchor_seq[501:]
+    nrb.estimate_regions(mixed, "ont", False)
+    for i in (0, 2):
+        for name, rd in plain[i].read_dict.items():
+            o = mixed[i].read_dict[name]
+            assert (rd.round1_repeat_size, rd.round2_repeat_size, rd.round3_repeat_size) == \
+                   (o.round1_repeat_size, o.round2_repeat_size, o.round3_repeat_size)
+    for rd in mixed[1].read_dict.values():
+        assert rd.round1_repeat_size is not None and rd.round2_repeat_size is None and rd.round3_repeat_size is None
+
+
+def _with_ambiguous(rng, s, rate):
+    """Replace a fraction of the bases by N / other IUPAC letters / lower-case n."""
+    out = list(s)
+    for i in range(len(out)):
+        if rng.random() < rate:
+            out[i] = rng.choice("NNNnRYK")
+    return "".join(out)
+
+
+def test_ambiguous_read_bases_equal_oracle(engine, oracle):
+    """Reads with bases other than ACGT (the reference accepts them; minimap2 scores them -1 against anything):
+    exact records, round-2 flags kind, and every ladder mode, on paired, single and multi-stripe reads, next to clean
+    reads of the same region."""
+    rng = random.Random(606)
+    sc = engine.get_preset("ont")
+    qs, ts = [], []
+    for i in range(90):
+        q = _rand_seq(rng, rng.choice([5, 40, 130, 400, 700, 1500]))
+        t = _rand_seq(rng, rng.randint(0, 50)) + _mutate(rng, q, 0.06) + _rand_seq(rng, rng.randint(0, 50))
+        qs.append(_with_ambiguous(rng, q, rng.choice([0.0, 0.01, 0.2])) if i % 7 else "N" * len(q))
+        ts.append(t)
+    _assert_same(engine.score_tasks(qs, ts, sc), oracle.align_batch(qs, ts, n_threads=oracle.max_threads()), "ambiguous queries")
+    # round 2 + round 3 of one region: clean and ambiguous reads pair up with each other
+    left, right, motif = _rand_seq(rng, 200), _rand_seq(rng, 180), "CAG"
+    cores, kmin, kmax = [], [], []
+    for i in range(41):
+        k = rng.choice([4, 17, 55, 150, 300])          # up to ~1.1 kb: stripes
+        core = _mutate(rng, left[-70:] + motif * k + right[:80], 0.04)
+        if i % 3:
+            core = _with_ambiguous(rng, core, rng.choice([0.005, 0.05]))
+        cores.append(core + ("\n" if i % 5 == 0 else ""))      # white space around a read is not part of it
+        kmin.append(max(0, k - rng.randint(2, 9))); kmax.append(k + rng.randint(2, 9))
+    kmin, kmax = np.array(kmin, np.int32), np.array(kmax, np.int32)
+    stripped = [c.strip() for c in cores]
+    T = 320
+    ref2 = oracle.align_batch(stripped, [left + motif * T] * len(cores), n_threads=oracle.max_threads())
+    with engine.Batch.begin(sc, "round2_flags") as b:
+        b.add_round2(left, motif, T, cores)
+        score, tend, inside = b.commit().run().fetch_round2()
+        assert b.stats()["n_skipped"] == 0
+    assert np.array_equal(score, ref2["score"])
+    spans = ref2["tend"] >= len(left)
+    assert np.array_equal(tend[spans], ref2["tend"][spans])
+    live = (ref2["score"] > 0) & spans
+    assert np.array_equal(inside[live], (ref2["tstart"] <= len(left))[live])
+    ref, roff = oracle.align_ladders(stripped, left, right, motif, kmin, kmax, n_threads=oracle.max_threads())
+    try:
+        for mode in (3, 2, 1, 0):
+            engine.set_ladder_mode(mode)
+            with engine.Batch.round3(sc, left, right, motif, cores, kmin, kmax) as b:
+                b.run()
+                if mode >= 2:
+                    _assert_flag_ladder(b, ref, roff, kmin, len(left), len(right), 3, sc.min_dp_score,
+                                        f"ambiguous reads, mode {mode}", rungs_too=mode == 2)
+                else:
+                    _assert_same(b.fetch_alns(), ref, f"ambiguous reads, mode {mode}")
+    finally:
+        engine.set_ladder_mode(3)
+
+
+def test_scratch_reuse_across_launches_and_eras(engine, oracle):
+    """The long reads' boundary rows live in pooled scratch that still holds the tagged entries of earlier launches;
+    tags carry a 10-bit launch epoch, and a buffer is cleared when the epochs wrap (every 1023 launches).  Same batch
+    launched across an era boundary, and a different batch over the same pooled buffer: always the oracle's records."""
+    rng = random.Random(99)
+    sc = engine.get_preset("ont")
+
+    def make(n):
+        qs = [_rand_seq(rng, rng.randint(600, 1400)) for _ in range(n)]
+        ts = [_rand_seq(rng, 40) + _mutate(rng, q, 0.08) + _rand_seq(rng, 40) for q in qs]
+        return qs, ts
+
+    qa, ta = make(6)
+    ref_a = oracle.align_batch(qa, ta, n_threads=oracle.max_threads())
+    b = engine.Batch.tasks(sc, qa, ta)
+    for it in range(1100):                     # > 1023 launches: crosses an era boundary at least once
+        b.run()
+        if it % 97 == 0 or it > 1090:
+            _assert_same(b.fetch_alns(), ref_a, f"launch {it}")
+    b.close()                                  # its scratch returns to the pool, full of valid-looking entries
+    for _ in range(3):
+        qb, tb = make(6)
+        _assert_same(engine.score_tasks(qb, tb, sc), oracle.align_batch(qb, tb, n_threads=oracle.max_threads()), "reused scratch")
 
 
 def test_round3_rungs_match_oracle(engine, oracle):
