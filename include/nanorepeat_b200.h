@@ -219,6 +219,36 @@ int nr_set_timing(int on);
 int nr_batch_launch_info(nr_batch_t* b, nr_launch_info_t* out);
 void nr_batch_destroy(nr_batch_t* b);
 
+/*
+ * Rounds 1-3 of any number of regions in ONE call: what quantify1repeat_from_bam does per region with
+ * round1_and_round2_estimation + round3_estimation (nanoRepeat_bam.py:675-679), with no trip back to the caller between
+ * the rounds.  Host buffers in, per-read results out (concatenated in region order):
+ *   r1[i]       = float(dist_between_anchors) / len(motif)                               (:341)
+ *   r2[i]       = round-2 size, valid only where r2_valid[i] (Read.round2_repeat_size stays None otherwise, :373-384)
+ *   r3[i]       = round-3 size; r3_state[i]: 0 = untouched (None), 1 = mean of the tied top rungs (an np.float64 in the
+ *                 reference, :431), 2 = fell back to r2 (:433)
+ *   T_out[g]    = region g's round-2 template size (:344-347); may be NULL
+ * All deciding arithmetic (r1, T, r2, ladder bounds with their truncations, the mean) is done in IEEE doubles exactly as
+ * the reference's Python evaluates it.  Regions are grouped and software-pipelined so that packing, uploads and
+ * selection of one group overlap the kernels of another.  The reads of a region arrive as n_reads lines separated by
+ * '\n' (no trailing newline needed).  has_round1_max_dist: this "region" is one piece of a split region and
+ * round1_max_dist is the whole region's longest dist_between_anchors (T is region-wide, :344).
+ * Needs map-ont scoring (every preset of the reference) and nr_set_ladder_mode != 0.
+ */
+typedef struct nr_region_t {
+    const char* left;  int32_t n_left;      /* RepeatRegion.left_anchor_seq  */
+    const char* right; int32_t n_right;     /* RepeatRegion.right_anchor_seq */
+    const char* motif; int32_t motif_len;   /* RepeatRegion.repeat_unit_seq  */
+    int32_t n_reads;
+    const char* reads; int64_t reads_len;   /* read_core_seq_dict values, in read_dict order */
+    const int32_t* dist_between_anchors;    /* Read.dist_between_anchors */
+    int32_t has_round1_max_dist;
+    int64_t round1_max_dist;
+} nr_region_t;
+int nr_estimate_regions(const nr_scoring_t* sc, int32_t fast_mode, int32_t n_regions, const nr_region_t* regions,
+                        double* r1, double* r2, uint8_t* r2_valid, double* r3, uint8_t* r3_state, int32_t* T_out,
+                        nr_stats_t* stats /* nullable: summed over the batches of the call */);
+
 /* Counters of the last nr_score_tasks / nr_round2_region / nr_round3_region call on this thread. */
 int nr_last_stats(nr_stats_t* out);
 

@@ -1601,3 +1601,155 @@ int nr_round3_region(const nr_scoring_t* sc, const char* left, int32_t n_left, c
 }
 
 }  // extern "C"
+
+// ---- rounds 1-3 of any number of regions in one call --------------------------------------------------------------
+// The arithmetic that decides results is the reference's, in IEEE doubles exactly as Python evaluates it (a Python float
+// IS a C double; int() truncates toward zero like the casts below; no expression here can be contracted into an FMA):
+//   r1 = float(dist) / len(motif); T = int(max r1 * 1.5) + 1, raised to int(max r1 + 10)       nanoRepeat_bam.py:339-347
+//   r2 = float(tend - |left|) / len(motif) where tstart <= |left| <= tend                      :373-375
+//   buffer = max(15, int(r2 * 0.05)) <= 150 (fast mode: 15); k = int(r2 - buffer) .. int(r2 + buffer), kmin >= 0   :463-472
+//   r3 = mean of the tied top rungs that span both anchors (sum and count are exact integers, one division), else r2   :423-433
+namespace {
+
+struct Group { int r0, r1; nr_batch* b2 = nullptr; nr_batch* b3 = nullptr; std::vector<int> regs; };
+
+int estimate_regions(const nr_scoring_t* sc, int fast_mode, int n_regions, const nr_region_t* regs, double* r1, double* r2,
+                     uint8_t* r2_valid, double* r3, uint8_t* r3_state, int32_t* T_out, nr_stats_t* stats) {
+    std::vector<long long> first(n_regions + 1, 0);
+    for (int g = 0; g < n_regions; ++g) {
+        const nr_region_t& R = regs[g];
+        if (R.n_reads < 0 || R.motif_len <= 0 || !R.motif || (R.n_reads > 0 && (!R.reads || !R.dist_between_anchors)))
+            return fail(NR_ERR_ARG, "nr_estimate_regions: region %d has bad arguments", g);
+        first[g + 1] = first[g] + R.n_reads;
+    }
+    const long long total = first[n_regions];
+    for (long long i = 0; i < total; ++i) { r2_valid[i] = 0; r3_state[i] = 0; r2[i] = 0.0; r3[i] = 0.0; }
+    // ---- round 1 (host): r1 per read, T per region ----
+    std::vector<int32_t> T(n_regions, 0);
+    for (int g = 0; g < n_regions; ++g) {
+        const nr_region_t& R = regs[g];
+        if (R.n_reads == 0) continue;                                                   // :336
+        const double m = (double)R.motif_len;
+        double mx = 0.0;
+        for (int r = 0; r < R.n_reads; ++r) {
+            const double v = (double)R.dist_between_anchors[r] / m;                     // :341
+            r1[first[g] + r] = v;
+            if (r == 0 || v > mx) mx = v;
+        }
+        if (R.has_round1_max_dist) { const double v = (double)R.round1_max_dist / m; if (v > mx) mx = v; }
+        int t = (int)(mx * 1.5) + 1;                                                    // :344
+        if ((double)t < mx + 10.0) t = (int)(mx + 10.0);                                // :346-347
+        if (t < 0) t = 0;
+        T[g] = t;
+        if (T_out) T_out[g] = t;
+    }
+    // ---- groups of regions, software-pipelined: while the GPU scores one group the host packs the next ----
+    constexpr long long kMinReads = 4096;
+    const int n_groups = (int)std::max<long long>(1, std::min<long long>(8, total / kMinReads));
+    std::vector<Group> groups;
+    {
+        const double target = (double)total / n_groups;
+        long long acc = 0;
+        int start = 0;
+        for (int g = 0; g < n_regions; ++g) {
+            acc += regs[g].n_reads;
+            if (acc >= target * (double)(groups.size() + 1) && (int)groups.size() < n_groups - 1) {
+                Group G; G.r0 = start; G.r1 = g + 1; groups.push_back(G);
+                start = g + 1;
+            }
+        }
+        Group G; G.r0 = start; G.r1 = n_regions; groups.push_back(G);
+    }
+    int rc = NR_OK;
+    auto cleanup = [&]() { for (Group& G : groups) { if (G.b3) nr_batch_destroy(G.b3); if (G.b2) nr_batch_destroy(G.b2); G.b2 = G.b3 = nullptr; } };
+    auto add_stats = [&](const nr_batch* b) {
+        if (!stats) return;
+        stats->algorithmic_cells += b->stats.algorithmic_cells; stats->executed_cells += b->stats.executed_cells;
+        stats->n_tasks += b->stats.n_tasks; stats->kernel_launches += b->stats.kernel_launches;
+        stats->n_skipped += b->stats.n_skipped; stats->h2d_bytes += b->stats.h2d_bytes; stats->d2h_bytes += b->stats.d2h_bytes;
+    };
+    if (stats) *stats = {};
+    const int min_score = std::max(1, sc->min_dp_score);
+    // round 2 of every group, back to back (was pymm2.main at :362)
+    for (Group& G : groups) {
+        for (int g = G.r0; g < G.r1; ++g) {
+            const nr_region_t& R = regs[g];
+            if (R.n_reads == 0) continue;
+            if (!G.b2 && !(G.b2 = nr_batch_begin(sc, NR_KIND_ROUND2_FLAGS))) { cleanup(); return g_code; }
+            if ((rc = nr_batch_add_round2_lines(G.b2, R.left, R.n_left, R.motif, R.motif_len, T[g], R.n_reads, R.reads, R.reads_len))) { cleanup(); return rc; }
+            G.regs.push_back(g);
+        }
+        if (G.b2 && ((rc = nr_batch_commit(G.b2)) || (rc = nr_batch_run(G.b2, nullptr)))) { cleanup(); return rc; }
+    }
+    // round-2 selection and the launch of round 3 (was pymm2.main per read at :497), group by group
+    std::vector<int32_t> kmin, kmax;
+    for (Group& G : groups) {
+        if (!G.b2) continue;
+        if ((rc = fetch_raw(G.b2))) { cleanup(); return rc; }
+        if (!(G.b3 = nr_batch_begin_round3_from(G.b2))) { cleanup(); return g_code; }
+        for (size_t i = 0; i < G.regs.size(); ++i) {
+            const int g = G.regs[i];
+            const nr_region_t& R = regs[g];
+            const RegionInfo& info = G.b2->regions[i];
+            const double m = (double)R.motif_len;
+            kmin.assign(R.n_reads, 0);
+            kmax.assign(R.n_reads, -1);
+            for (int r = 0; r < R.n_reads; ++r) {
+                const int4 a = G.b2->h_out[info.first_read + r];          // (score, 0 or |left| + 1, tend)
+                if (a.x < min_score || a.y > R.n_left || a.z < R.n_left) continue;      // no PAF line below -s; span test :373
+                const double v = (double)(a.z - R.n_left) / m;                           // :375
+                r2[first[g] + r] = v;
+                r2_valid[first[g] + r] = 1;
+                int buffer = std::max(15, (int)(v * 0.05));                              // :463-467
+                if (buffer > 150) buffer = 150;
+                if (fast_mode) buffer = 15;
+                kmax[r] = (int)(v + (double)buffer);                                     // :469-472
+                kmin[r] = std::max((int)(v - (double)buffer), 0);
+            }
+            if ((rc = nr_batch_add_round3_reuse(G.b3, (int)i, R.right, R.n_right, kmin.data(), kmax.data()))) { cleanup(); return rc; }
+        }
+        if ((rc = nr_batch_commit(G.b3)) || (rc = nr_batch_run(G.b3, nullptr))) { cleanup(); return rc; }
+    }
+    // round-3 selection (:423-433)
+    for (Group& G : groups) {
+        if (!G.b3) continue;
+        if ((rc = fetch_raw(G.b3))) { cleanup(); return rc; }
+        for (size_t i = 0; i < G.regs.size(); ++i) {
+            const int g = G.regs[i];
+            const RegionInfo& info = G.b3->regions[i];
+            for (int r = 0; r < regs[g].n_reads; ++r) {
+                const long long o = first[g] + r;
+                if (!r2_valid[o]) continue;                                              // :460
+                const int4 v = G.b3->h_sel[info.first_read + r];                         // (top, n tied, sum k lo, hi)
+                if (v.x <= 0) continue;                                                  // no PAF line at all (:421)
+                if (v.y > 0) {
+                    const long long sum = (long long)(((unsigned long long)(unsigned)v.w << 32) | (unsigned)v.z);
+                    r3[o] = (double)sum / (double)v.y;                                   // np.mean of the tied k (:431)
+                    r3_state[o] = 1;
+                } else {
+                    r3[o] = r2[o];                                                       // :433
+                    r3_state[o] = 2;
+                }
+            }
+        }
+        add_stats(G.b2);
+        add_stats(G.b3);
+    }
+    cleanup();
+    return NR_OK;
+}
+
+}  // namespace
+
+extern "C" int nr_estimate_regions(const nr_scoring_t* sc, int32_t fast_mode, int32_t n_regions, const nr_region_t* regions,
+                                   double* r1, double* r2, uint8_t* r2_valid, double* r3, uint8_t* r3_state, int32_t* T_out,
+                                   nr_stats_t* stats) {
+    if (check_scoring(sc)) return g_code;
+    if (n_regions < 0 || (n_regions > 0 && !regions)) return fail(NR_ERR_ARG, "nr_estimate_regions: bad arguments");
+    long long total = 0;
+    for (int g = 0; g < n_regions; ++g) total += std::max(0, regions[g].n_reads);
+    if (total > 0 && (!r1 || !r2 || !r2_valid || !r3 || !r3_state)) return fail(NR_ERR_ARG, "nr_estimate_regions: NULL output");
+    if (!is_map_ont(*sc) || g_ladder_mode.load() == 0)
+        return fail(NR_ERR_ARG, "nr_estimate_regions needs map-ont scoring and a shared-sweep ladder mode (1-3)");
+    return estimate_regions(sc, fast_mode, n_regions, regions, r1, r2, r2_valid, r3, r3_state, T_out, stats);
+}

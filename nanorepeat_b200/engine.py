@@ -40,6 +40,15 @@ class LaunchInfo(ctypes.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}
 
 
+class RegionIn(ctypes.Structure):
+    """nr_region_t: one region of nr_estimate_regions."""
+    _fields_ = [("left", ctypes.c_char_p), ("n_left", ctypes.c_int32), ("right", ctypes.c_char_p), ("n_right", ctypes.c_int32),
+                ("motif", ctypes.c_char_p), ("motif_len", ctypes.c_int32), ("n_reads", ctypes.c_int32),
+                ("reads", ctypes.c_void_p), ("reads_len", ctypes.c_int64),
+                ("dist_between_anchors", ctypes.POINTER(ctypes.c_int32)),
+                ("has_round1_max_dist", ctypes.c_int32), ("round1_max_dist", ctypes.c_int64)]
+
+
 ALN_DTYPE = np.dtype([("score", "<i4"), ("tstart", "<i4"), ("tend", "<i4")])
 RUNG_DTYPE = np.dtype([("score", "<i4"), ("starts_in_left", "u1"), ("ends_in_right", "u1"), ("pad", "u1", (2,))])
 
@@ -100,6 +109,9 @@ SYMBOLS = {
     "nr_batch_launch_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(LaunchInfo)]),
     "nr_batch_destroy": (None, [ctypes.c_void_p]),
     "nr_last_stats": (ctypes.c_int, [ctypes.POINTER(Stats)]),
+    "nr_estimate_regions": (ctypes.c_int, [_scp, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(RegionIn),
+                                           ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.c_void_p,
+                                           ctypes.POINTER(ctypes.c_double), ctypes.c_void_p, _i32p, ctypes.POINTER(Stats)]),
 }
 
 
@@ -414,3 +426,42 @@ def round2_region(sc, left, motif, T, cores):
 def round3_region(sc, left, right, motif, cores, kmin, kmax, want_rungs=False):
     """-> (sum_k, n_k, top_score[, rungs, rung_offset])."""
     return round3_regions(sc, [(left, right, motif, cores, kmin, kmax)], want_rungs)
+
+
+def estimate_regions(sc, fast_mode, regions):
+    """nr_estimate_regions: rounds 1-3 of many regions in one call.
+    regions: list of (left, right, motif, cores (list of str), dists (sequence of int), round1_max_dist or None).
+    -> dict of arrays over all reads in order: r1, r2, r2_valid, r3, r3_state (0 None / 1 mean of rungs / 2 = r2),
+    plus T per region and the summed stats."""
+    n = len(regions)
+    arr = (RegionIn * max(n, 1))()
+    keep = []                                   # everything the structs point at stays alive until the call returns
+    total = 0
+    dists_all = np.fromiter((d for reg in regions for d in reg[4]), dtype=np.int32)
+    for g, (left, right, motif, cores, dists, max_dist) in enumerate(regions):
+        lb, rb, mb = _b(left), _b(right), _b(motif)
+        joined = "\n".join(cores) if cores and isinstance(cores[0], str) else b"\n".join(cores).decode("latin-1")
+        size = ctypes.c_ssize_t()
+        ptr = _utf8(joined, ctypes.byref(size))
+        if not ptr:
+            raise ValueError("reads are not valid text")
+        keep.append((lb, rb, mb, joined))
+        r = arr[g]
+        r.left, r.n_left, r.right, r.n_right, r.motif, r.motif_len = lb, len(lb), rb, len(rb), mb, len(mb)
+        r.n_reads, r.reads, r.reads_len = len(cores), ptr, size.value
+        r.dist_between_anchors = ctypes.cast(dists_all.ctypes.data + 4 * total, _i32p)
+        r.has_round1_max_dist = max_dist is not None
+        r.round1_max_dist = int(max_dist) if max_dist is not None else 0
+        total += len(cores)
+    if total != len(dists_all):
+        raise ValueError("cores and dist_between_anchors differ in length")
+    r1 = np.zeros(total, np.float64); r2 = np.zeros(total, np.float64); r3 = np.zeros(total, np.float64)
+    r2_valid = np.zeros(total, np.uint8); r3_state = np.zeros(total, np.uint8)
+    T = np.zeros(max(n, 1), np.int32)
+    st = Stats()
+    dp = ctypes.POINTER(ctypes.c_double)
+    _check(lib().nr_estimate_regions(ctypes.byref(sc), int(bool(fast_mode)), n, arr, r1.ctypes.data_as(dp), r2.ctypes.data_as(dp),
+                                     r2_valid.ctypes.data, r3.ctypes.data_as(dp), r3_state.ctypes.data, T.ctypes.data_as(_i32p),
+                                     ctypes.byref(st)))
+    del keep
+    return dict(r1=r1, r2=r2, r2_valid=r2_valid.astype(bool), r3=r3, r3_state=r3_state, T=T[:n], stats=st.as_dict())

@@ -9,10 +9,33 @@ libnanorepeat_b200.so per round instead of temp files + one minimap2 process per
 All float arithmetic that decides results (r1, T, r2, ladder bounds with int() truncation, np.mean of the tied
 rungs) stays here in Python/numpy float64, written exactly as the reference writes it.
 """
+import weakref
+
 import numpy as np
 
 from . import engine
 from .presets import get_preset_for_minimap2
+
+
+# What round1_and_round2_estimation leaves behind for round3_estimation on the same region: the committed round-2 batch
+# (its packed reads and kept DP state stay on the device) and what round 2 decided.  Kept HERE, keyed weakly by the
+# region object, never as an attribute of it: the reference pickles RepeatRegion objects through a multiprocessing
+# queue (nanoRepeat_bam.py:610) and a ctypes handle cannot be pickled.
+_ROUND2_CACHE = weakref.WeakKeyDictionary()
+
+
+def _cache_put(rr, value):
+    try:
+        _ROUND2_CACHE[rr] = value
+    except TypeError:           # not hashable / not weakly referenceable: round 3 packs the reads again
+        pass
+
+
+def _cache_pop(rr):
+    try:
+        return _ROUND2_CACHE.pop(rr, None)
+    except TypeError:
+        return None
 
 
 def _scoring_for(data_type):
@@ -70,8 +93,8 @@ def _round2_launch(data_type, repeat_regions):
 
 
 def _round2_finish(ctx):
-    """Round-2 selection (reference nanoRepeat_bam.py:364-384).  The committed batch stays attached to the regions
-    (rr._nr_round2) so that round 3 can reuse the packed reads."""
+    """Round-2 selection (reference nanoRepeat_bam.py:364-384).  The committed batch is remembered per region
+    (_ROUND2_CACHE) so that round 3 can reuse the packed reads."""
     if ctx is None:
         return
     b, todo, specs, min_score = ctx
@@ -94,7 +117,7 @@ def _round2_finish(ctx):
                 reads[name].round2_repeat_size = v
         # the committed batch (round 3 reuses its packed reads and kept DP state) and what round 2 just decided, so that
         # a round 3 issued right behind it (estimate_regions) need not read 5 000 attributes back
-        rr._nr_round2 = (b, idx, qnames, ok, r2_arr)
+        _cache_put(rr, (b, idx, qnames, ok, r2_arr))
 
 
 def _round2_many(data_type, repeat_regions):
@@ -163,23 +186,19 @@ def _assign_round3(reads, sum_k, n_k, top):
         # s == 0: no PAF line at all (:421) -> untouched
 
 
-def _round3_reuse_launch(fast_mode, batch, rrs, trust_round2=False):
-    """Launch of round 3 over the reads a committed round-2 batch already holds on the device.
-    trust_round2: the caller ran round 2 itself just now (estimate_regions), so the sizes round 2 assigned are taken from
-    its arrays instead of being read back from the Read objects (which a caller of the two separate operators may
-    have edited in between, as the reference's attributes allow)."""
+def _round3_reuse_launch(fast_mode, batch, items):
+    """Launch of round 3 over the reads a committed round-2 batch already holds on the device.  items: (region, what
+    round 2 cached for it).  The sizes are read back from the Read objects: a caller of the two separate operators may
+    have edited them in between, as the reference's attributes allow."""
     b3 = engine.Batch.begin_round3_from(batch)
     per_region, valid_parts, r2_parts = [], [], []
-    for rr in rrs:
-        _b, idx, qnames, ok2, r2_arr = rr._nr_round2
+    for rr, cached in items:
+        _b, idx, qnames, _ok2, _r2_arr = cached
         reads = rr.read_dict
-        rl = list(map(reads.__getitem__, qnames))
-        if trust_round2:
-            valid, r2_valid = ok2, r2_arr[ok2]
-        else:
-            r2 = [rd.round2_repeat_size for rd in rl]
-            valid = np.array([v is not None for v in r2], dtype=bool)           # :460
-            r2_valid = np.array([v for v in r2 if v is not None], dtype=np.float64)
+        rl = [reads.get(n) for n in qnames]                                     # a read dropped since round 2 is skipped
+        r2 = [None if rd is None else rd.round2_repeat_size for rd in rl]
+        valid = np.array([v is not None for v in r2], dtype=bool)               # :460
+        r2_valid = np.array([v for v in r2 if v is not None], dtype=np.float64)
         per_region.append((rr, idx, rl, valid))
         valid_parts.append(valid)
         r2_parts.append(r2_valid)
@@ -195,7 +214,6 @@ def _round3_reuse_launch(fast_mode, batch, rrs, trust_round2=False):
         b3.add_round3_reuse(idx, rr.right_anchor_seq, kmin_all[pos:pos + n], kmax_all[pos:pos + n])
         pos += n
         all_reads += [rd if ok else None for rd, ok in zip(rl, valid.tolist())]
-        del rr._nr_round2
     b3.commit().run()                                                           # was pymm2.main per read at :497
     return b3, all_reads
 
@@ -212,12 +230,12 @@ def _round3_many(data_type, fast_mode, repeat_regions):
     sc = _scoring_for(data_type)
     fresh, by_batch = [], {}
     for rr in repeat_regions:
-        cached = getattr(rr, "_nr_round2", None)
+        cached = _cache_pop(rr)
         if cached is not None and engine.ladder_mode() != 0 and cached[0]._h:
-            by_batch.setdefault(id(cached[0]), (cached[0], []))[1].append(rr)
+            by_batch.setdefault(id(cached[0]), (cached[0], []))[1].append((rr, cached))
         else:
             fresh.append(rr)
-    pending = [_round3_reuse_launch(fast_mode, batch, rrs) for batch, rrs in by_batch.values()]
+    pending = [_round3_reuse_launch(fast_mode, batch, items) for batch, items in by_batch.values()]
     for ctx in pending:
         _round3_reuse_finish(ctx)
     specs, todo = [], []
@@ -247,51 +265,70 @@ def round3_estimation(data_type, fast_mode, repeat_region, num_cpu=1):
     return
 
 
-PIPELINE_MIN_READS = 4096     # reads per pipeline group: enough tasks to fill 148 SMs x 16 warps about twice
-
-
-def _pipeline_groups(rrs):
-    """Cut a region list into a few contiguous groups of at least PIPELINE_MIN_READS reads (at most 8 groups)."""
-    total = sum(len(rr.read_dict) for rr in rrs)
-    n_groups = max(1, min(8, total // PIPELINE_MIN_READS))
-    if n_groups == 1:
-        return [rrs]
-    target, groups, cur, acc = total / n_groups, [], [], 0
+def _estimate_regions_fused(dt, fast_mode, rrs):
+    """Rounds 1-3 of a list of regions through nr_estimate_regions: one call into the library, which runs round 2,
+    derives every read's ladder from it and runs round 3 without coming back here in between; the attributes of
+    every Read are then assigned once from the returned arrays."""
+    sc = _scoring_for(dt)
+    specs, todo = [], []
     for rr in rrs:
-        cur.append(rr)
-        acc += len(rr.read_dict)
-        if acc >= target * (len(groups) + 1) and len(groups) < n_groups - 1:
-            groups.append(cur)
-            cur = []
-    if cur:
-        groups.append(cur)
-    return groups
+        reads = rr.read_dict
+        if len(reads) == 0:
+            continue                                                            # :336
+        core_dict = rr.read_core_seq_dict
+        # reads come from read_core_seq_dict, which is what the reference wrote to core_sequences.fastq (:311-321); a read
+        # without a core there gets round 1 only (it is not in the FASTQ the reference aligns)
+        if core_dict.keys() >= reads.keys():
+            qnames, extra = list(reads), ()
+        else:
+            qnames = [n for n in reads if n in core_dict]
+            extra = [n for n in reads if n not in core_dict]
+        read_list = list(map(reads.__getitem__, qnames))
+        max_dist = getattr(rr, "round1_max_dist", None)                         # a piece of a split region (sharding)
+        if extra:
+            m = len(rr.repeat_unit_seq)
+            for n in extra:
+                reads[n].round1_repeat_size = float(reads[n].dist_between_anchors) / m
+            far = max(reads[n].dist_between_anchors for n in extra)             # T is over ALL reads of the region (:344)
+            max_dist = far if max_dist is None else max(max_dist, far)
+        specs.append((rr.left_anchor_seq, rr.right_anchor_seq, rr.repeat_unit_seq, _cores_of(rr, qnames),
+                      [rd.dist_between_anchors for rd in read_list], max_dist))
+        todo.append(read_list)
+    if not specs:
+        return
+    res = engine.estimate_regions(sc, fast_mode, specs)
+    r1, r2, r3 = res["r1"].tolist(), res["r2"].tolist(), res["r3"]
+    ok2, st3 = res["r2_valid"].tolist(), res["r3_state"].tolist()
+    pos = 0
+    for read_list in todo:
+        for rd in read_list:
+            rd.round1_repeat_size = r1[pos]                                     # :341
+            if ok2[pos]:
+                v = r2[pos]
+                rd.round2_repeat_size = v                                       # :375-384
+                s = st3[pos]
+                if s == 1:
+                    rd.round3_repeat_size = r3[pos]                             # :431 (np.float64, like np.mean)
+                elif s == 2:
+                    rd.round3_repeat_size = v                                   # :433
+            pos += 1
 
 
 def estimate_regions(regions, data_type=None, fast_mode=False):
-    """Rounds 1-3 over a list of RepeatRegion-like objects with one engine launch per round and group of regions (the
-    reference runs the two operators per region inside quantify1repeat_from_bam, nanoRepeat_bam.py:675-679).
-    The groups are software-pipelined: while the GPU scores one group the host packs the next and selects the
-    previous, so most of the host work hides behind the kernels (one host thread: a thread per group was measured and
-    is no faster, the Python passes serialise on the GIL).  Per-region semantics (T per region, ladder per read)
-    are untouched.  Regions may carry their own .data_type; regions of one data type are batched together."""
+    """Rounds 1-3 over a list of RepeatRegion-like objects (the reference runs the two operators per region inside
+    quantify1repeat_from_bam, nanoRepeat_bam.py:675-679): one call into the library per data type, which batches the
+    regions into a few pipelined launches per round (nr_estimate_regions).  Per-region semantics (T per region, ladder
+    per read) are untouched.  Regions may carry their own .data_type; regions of one data type are batched together.
+    With nr_set_ladder_mode(0) (every rung its own rectangle: a checking mode) the two operators are run instead."""
     by_type = {}
     for rr in regions:
         by_type.setdefault(data_type or getattr(rr, "data_type", None) or "ont", []).append(rr)
     for dt, rrs in by_type.items():
-        groups = _pipeline_groups(rrs)
-        r2 = [_round2_launch(dt, g) for g in groups]                # GPU: round 2 of every group, back to back
-        r3 = []
-        for g, ctx in zip(groups, r2):
-            _round2_finish(ctx)                                     # waits for this group's round 2 only
-            _scoring_for(dt)
-            live = [rr for rr in g if getattr(rr, "_nr_round2", None) is not None]
-            if live and engine.ladder_mode() != 0:
-                r3.append(_round3_reuse_launch(fast_mode, live[0]._nr_round2[0], live, trust_round2=True))
-            else:
-                _round3_many(dt, fast_mode, g)
-        for ctx in r3:
-            _round3_reuse_finish(ctx)
+        if engine.ladder_mode() != 0:
+            _estimate_regions_fused(dt, fast_mode, rrs)
+            continue
+        _round2_many(dt, rrs)
+        _round3_many(dt, fast_mode, rrs)
     return regions
 
 

@@ -85,15 +85,15 @@ def estimate_region(left, right, motif, cores, dists, fast_mode=False, sc=None, 
     kmin = [None] * n
     kmax = [None] * n
     r3 = [None] * n
-    rungs = (None, None)
+    all_rungs = (None, None)
     if idx:
         kb = [ladder_bounds(r2[i], fast_mode) for i in idx]
         out, off = nr_oracle.align_ladders([cores[i] for i in idx], left, right, motif,
                                            [b[0] for b in kb], [b[1] for b in kb], sc, n_threads)
-        rungs = (out, off)          # records of read idx[j]'s rungs: out[off[j]:off[j + 1]]
+        all_rungs = (out, off)      # records of read idx[j]'s rungs: out[off[j]:off[j + 1]]
         for j, i in enumerate(idx):
             kmin[i], kmax[i] = kb[j]
             rungs = out[off[j]:off[j + 1]]
             r3[i] = round3_select([(r["score"], r["tstart"], r["tend"]) for r in rungs], kmin[i],
                                   len(left), len(right), m, r2[i], sc.min_dp_score)
-    return dict(r1=r1, r2=r2, r3=r3, T=T, kmin=kmin, kmax=kmax, round2_aln=a2, round3_idx=idx, round3_rungs=rungs)
+    return dict(r1=r1, r2=r2, r3=r3, T=T, kmin=kmin, kmax=kmax, round2_aln=a2, round3_idx=idx, round3_rungs=all_rungs)
