@@ -93,6 +93,8 @@ typedef struct nr_launch_info_t {
     int32_t reserved;
     float paired_ms, rest_ms, redo_ms;   /* CUDA-event durations on the launching streams; 0 unless nr_set_timing(1) */
     float reserved2;
+    int64_t paired_useful_cells;   /* the same counts without padding: only rows that belong to a read (a warp sweeps */
+    int64_t rest_useful_cells;     /* 32 * R rows per pair / stripe whatever the reads' lengths) */
 } nr_launch_info_t;
 
 /* Data-type preset table (reference tk.py:502-517: ont, ont_sup, ont_q20, clr, hifi -- all map-ont). */

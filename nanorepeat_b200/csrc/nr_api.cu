@@ -320,6 +320,7 @@ struct nr_batch {
     int* h_redo_count = nullptr;              // pinned
     int* h_spin = nullptr;                    // pinned: the kernels' give-up flag after the run (long reads only)
     long long paired_cells = 0, rest_cells = 0;
+    long long paired_useful = 0, rest_useful = 0;   // the same without padding: rows of real reads only
     size_t n_out = 0;                         // records in d_out / h_out
     std::vector<int32_t> order;               // entries of the 32-bit launch: (task << 7) | code (nr_kernels.cuh)
     std::vector<nr::CoopInfo> coop;           // scratch of the multi-stripe tasks
@@ -515,6 +516,7 @@ int plan_batch(nr_batch* b) {
                 if (y >= 0) paired[y] = 1;
                 L.pair_R = std::max(L.pair_R, R);
                 pair_cost.push_back((long long)32 * R * b->tasks[x].t_len);
+                b->paired_useful += (long long)(b->tasks[x].q_len + (y >= 0 ? b->tasks[y].q_len : 0)) * b->tasks[x].t_len;
             });
         }
     } else if (b->pair && fixed && ladder && b->flag) {
@@ -547,6 +549,7 @@ int plan_batch(nr_batch* b) {
                 L.pair_R = std::max(L.pair_R, R);
                 const long long cols = (long long)g.n_right + g.n_left + (long long)g.m * kmax - (p.state_off >= 0 ? g.n_left - 1 : 0);
                 pair_cost.push_back((long long)32 * R * cols);
+                b->paired_useful += (long long)((la >= 0 ? b->ltasks[la].q_len : 0) + (lb >= 0 ? b->ltasks[lb].q_len : 0)) * cols;
             }
         }
         for (int i0 = 0; i0 < n;) {
@@ -569,6 +572,7 @@ int plan_batch(nr_batch* b) {
                 const int R = nr::pr::pair_rows(tx.q_len);
                 L.pair_R = std::max(L.pair_R, R);
                 pair_cost.push_back((long long)32 * R * (g.n_right + g.n_left + (long long)g.m * kmax));
+                b->paired_useful += (long long)(tx.q_len + (y >= 0 ? b->ltasks[y].q_len : 0)) * (g.n_right + g.n_left + (long long)g.m * kmax);
             });
             i0 = i1;
         }
@@ -640,6 +644,7 @@ int plan_batch(nr_batch* b) {
         if (paired[i]) continue;
         rmax = std::max(rmax, task_R[i]);
         b->rest_cells += cost[i];
+        b->rest_useful += cost[i] / ((long long)task_ns[i] * 32 * task_R[i]) * (ladder ? b->ltasks[i].q_len : b->tasks[i].q_len);
     }
     b->stats.executed_cells += b->rest_cells;
     auto by_cost = [&](int x, int y) { return cost[x] != cost[y] ? cost[x] > cost[y] : x < y; };
@@ -1536,6 +1541,8 @@ int nr_batch_launch_info(nr_batch_t* b, nr_launch_info_t* out) {
     *out = {};
     out->paired_cells = b->paired_cells;
     out->rest_cells = b->rest_cells;
+    out->paired_useful_cells = b->paired_useful;
+    out->rest_useful_cells = b->rest_useful;
     out->n_pairs = b->launch.n_pairs;
     out->n_rest = b->launch.count;
     if (b->ran) {
