@@ -7,8 +7,7 @@
 // gather and the round-3 selection of nanoRepeat_bam.py:423-431.
 // There is no CPU compute fallback: without a CUDA device every compute call fails with NR_ERR_CUDA.
 #include "../../include/nanorepeat_b200.h"
-#include "nr_kernels.cuh"
-#include "nr_pair_kernels.cuh"
+#include "nr_launch.h"
 
 #include <algorithm>
 #if defined(__x86_64__)
@@ -774,22 +773,6 @@ int plan_batch(nr_batch* b) {
     return NR_OK;
 }
 
-// Once per kernel: dynamic shared memory up to what a full block of the tallest stripes needs, and the SM's L1 / shared
-// split all the way to shared.  Set once to the maximum (not per launch to the launch's size): batches are launched
-// from several host threads, and a smaller value set by one thread would fail another thread's launch.
-int prepare_kernel(const void* fn, size_t launch_bytes) {
-    constexpr size_t kMaxDyn = (size_t)kWarpsPerBlock * 12 * 1024;      // 16 warps x (profile + junction vectors at R = 12)
-    if (launch_bytes > kMaxDyn) return fail(NR_ERR_ARG, "launch needs %zu bytes of shared memory", launch_bytes);
-    static std::mutex mu;
-    static std::vector<const void*> done;
-    std::lock_guard<std::mutex> lk(mu);
-    if (std::find(done.begin(), done.end(), fn) != done.end()) return NR_OK;
-    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
-    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    done.push_back(fn);
-    return NR_OK;
-}
-
 constexpr int kSpinSlot = 16;        // d_counters[kSpinSlot]: the batch's give-up flag (nr_kernels.cuh, wait_cols)
 
 // Arguments of one launch of the 32-bit kernels.  Draws the launch's epoch; a scratch buffer that was last used in an
@@ -824,20 +807,17 @@ int launch_rest(nr_batch* b, cudaStream_t st, const nr::ScoreW& k, const int32_t
     if ((rc = rest_args(b, order, count, st, &ra))) return rc;
     if (L.ladder) {
         if (!L.fixed) return fail(NR_ERR_ARG, "the ladder kernels are built for map-ont scoring only");
-        auto fn = b->flag ? nr::ladder_kernel<true, true> : nr::ladder_kernel<true, false>;
         const int stride = ladder_smem_int4(R);
         const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
-        if ((rc = prepare_kernel((const void*)fn, smem))) return rc;
-        fn<<<blocks, kWarpsPerBlock * 32, smem, st>>>(b->d_ltasks, ra, count_dev, b->qsrc ? b->qsrc->d_pool : b->d_pool, b->d_pool,
-                                                     b->d_lregs, k, counter, stride, b->d_out, b->d_sel);
+        if (smem > nrl::kMaxDynShared) return fail(NR_ERR_ARG, "launch needs %zu bytes of shared memory", smem);
+        CUDA_TRY(nrl::launch_ladder(b->flag, blocks, kWarpsPerBlock * 32, smem, st, b->d_ltasks, ra, count_dev,
+                                    b->qsrc ? b->qsrc->d_pool : b->d_pool, b->d_pool, b->d_lregs, k, counter, stride, b->d_out, b->d_sel));
     } else {
-        auto fn = L.fixed ? nr::exact_kernel<true> : nr::exact_kernel<false>;
         const int stride = exact_smem_int4(R);
         const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
-        if ((rc = prepare_kernel((const void*)fn, smem))) return rc;
-        fn<<<blocks, kWarpsPerBlock * 32, smem, st>>>(b->d_tasks, ra, b->d_pool, k, counter, stride, b->d_out);
+        if (smem > nrl::kMaxDynShared) return fail(NR_ERR_ARG, "launch needs %zu bytes of shared memory", smem);
+        CUDA_TRY(nrl::launch_exact(L.fixed, blocks, kWarpsPerBlock * 32, smem, st, b->d_tasks, ra, b->d_pool, k, counter, stride, b->d_out));
     }
-    CUDA_TRY(cudaGetLastError());
     return NR_OK;
 }
 
@@ -881,18 +861,17 @@ int run_batch(nr_batch* b, cudaStream_t st) {
         if (!b->pairs2.empty()) {
             const int stride = exact_smem_int4(std::max(L.pair_R, L.R));
             const size_t smem = (size_t)wpb * stride * sizeof(int4);
-            if ((rc = prepare_kernel((const void*)nr::pr::pair_round2_kernel, smem))) return rc;
-            nr::pr::pair_round2_kernel<<<blocks, wpb * 32, smem, st>>>(
-                static_cast<const nr::pr::Pair2*>(b->d_pairs), deal, b->d_tasks, ra, b->d_pool, k, b->d_counters, stride, b->d_out,
-                b->d_state);
+            if (smem > nrl::kMaxDynShared) return fail(NR_ERR_ARG, "launch needs %zu bytes of shared memory", smem);
+            CUDA_TRY(nrl::launch_pair_round2(blocks, wpb * 32, smem, st, static_cast<const nr::pr::Pair2*>(b->d_pairs), deal, b->d_tasks,
+                                             ra, b->d_pool, k, b->d_counters, stride, b->d_out, b->d_state));
         } else {
             const int stride = ladder_smem_int4(std::max(L.pair_R, L.R));
             const size_t smem = (size_t)wpb * stride * sizeof(int4);
-            if ((rc = prepare_kernel((const void*)nr::pr::pair_ladder_kernel, smem))) return rc;
-            nr::pr::pair_ladder_kernel<<<blocks, wpb * 32, smem, st>>>(
-                static_cast<const nr::pr::Pair3*>(b->d_pairs), deal, b->d_ltasks, ra, b->qsrc ? b->qsrc->d_pool : b->d_pool,
-                b->d_pool, b->d_lregs, k, b->d_counters, stride, b->d_prung, b->d_out, b->d_sel, b->d_counters + 2, b->d_redo,
-                b->qsrc ? b->qsrc->d_state : nullptr);
+            if (smem > nrl::kMaxDynShared) return fail(NR_ERR_ARG, "launch needs %zu bytes of shared memory", smem);
+            CUDA_TRY(nrl::launch_pair_ladder(blocks, wpb * 32, smem, st, static_cast<const nr::pr::Pair3*>(b->d_pairs), deal, b->d_ltasks,
+                                             ra, b->qsrc ? b->qsrc->d_pool : b->d_pool, b->d_pool, b->d_lregs, k, b->d_counters, stride,
+                                             b->d_prung, b->d_out, b->d_sel, b->d_counters + 2, b->d_redo,
+                                             b->qsrc ? b->qsrc->d_state : nullptr));
         }
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(mark(3, st));
@@ -1677,6 +1656,8 @@ int estimate_regions(const nr_scoring_t* sc, int fast_mode, int n_regions, const
     };
     if (stats) *stats = {};
     const int min_score = std::max(1, sc->min_dp_score);
+    PhaseTrace trace;
+    trace.mark("estimate: round 1, grouping");
     // round 2 of every group, back to back (was pymm2.main at :362)
     for (Group& G : groups) {
         for (int g = G.r0; g < G.r1; ++g) {
@@ -1686,13 +1667,16 @@ int estimate_regions(const nr_scoring_t* sc, int fast_mode, int n_regions, const
             if ((rc = nr_batch_add_round2_lines(G.b2, R.left, R.n_left, R.motif, R.motif_len, T[g], R.n_reads, R.reads, R.reads_len))) { cleanup(); return rc; }
             G.regs.push_back(g);
         }
+        trace.mark("estimate: round-2 add (pack)");
         if (G.b2 && ((rc = nr_batch_commit(G.b2)) || (rc = nr_batch_run(G.b2, nullptr)))) { cleanup(); return rc; }
+        trace.mark("estimate: round-2 commit + run");
     }
     // round-2 selection and the launch of round 3 (was pymm2.main per read at :497), group by group
     std::vector<int32_t> kmin, kmax;
     for (Group& G : groups) {
         if (!G.b2) continue;
         if ((rc = fetch_raw(G.b2))) { cleanup(); return rc; }
+        trace.mark("estimate: wait for round 2");
         if (!(G.b3 = nr_batch_begin_round3_from(G.b2))) { cleanup(); return g_code; }
         for (size_t i = 0; i < G.regs.size(); ++i) {
             const int g = G.regs[i];
@@ -1715,12 +1699,15 @@ int estimate_regions(const nr_scoring_t* sc, int fast_mode, int n_regions, const
             }
             if ((rc = nr_batch_add_round3_reuse(G.b3, (int)i, R.right, R.n_right, kmin.data(), kmax.data()))) { cleanup(); return rc; }
         }
+        trace.mark("estimate: select 2 + round-3 add");
         if ((rc = nr_batch_commit(G.b3)) || (rc = nr_batch_run(G.b3, nullptr))) { cleanup(); return rc; }
+        trace.mark("estimate: round-3 commit + run");
     }
     // round-3 selection (:423-433)
     for (Group& G : groups) {
         if (!G.b3) continue;
         if ((rc = fetch_raw(G.b3))) { cleanup(); return rc; }
+        trace.mark("estimate: wait for round 3");
         for (size_t i = 0; i < G.regs.size(); ++i) {
             const int g = G.regs[i];
             const RegionInfo& info = G.b3->regions[i];
@@ -1742,7 +1729,9 @@ int estimate_regions(const nr_scoring_t* sc, int fast_mode, int n_regions, const
         add_stats(G.b2);
         add_stats(G.b3);
     }
+    trace.mark("estimate: select 3");
     cleanup();
+    trace.mark("estimate: destroy batches");
     return NR_OK;
 }
 

@@ -507,6 +507,7 @@ __device__ __forceinline__ void pair2_dispatch(int r, const Pair2& pt, const Tas
 // Round 2: the batch's 32-bit entries (stripes of long reads first: they are the critical path) and then its pairs, one
 // persistent launch.  out[task] = (score, 0 if the alignment starts at a column <= |left| else |left| + 1, tend, 0) for
 // paired tasks, the exact (score, tstart, tend, 0) for the others.
+#ifdef NR_DEFINE_PAIR_ROUND2_KERNEL      // defined by the one translation unit that owns this kernel (nr_launch_pair2.cu)
 __global__ void __launch_bounds__(32 * kWarpsPerBlock, 1)
 pair_round2_kernel(const Pair2* __restrict__ pairs, Deal dl, const Task* __restrict__ tasks, RestArgs ra,
                    const uint32_t* __restrict__ pool, ScoreW scw, int* counter, int smem_stride, int4* out, u32* state) {
@@ -528,6 +529,7 @@ pair_round2_kernel(const Pair2* __restrict__ pairs, Deal dl, const Task* __restr
         pair2_dispatch<kMinR>(pair_rows(q), pt, tasks, pool, prof, lane, (u32)sc.one, sc.four, out, state);
     }
 }
+#endif
 
 // ---- round 3 -------------------------------------------------------------------------------------------------------
 // One rung of one read from the (P, J) tokens: score, "ends in right", and the mark of the best non-prefix candidate.
@@ -643,6 +645,7 @@ __device__ __forceinline__ void pair3_dispatch(int r, const Pair3& pt, const Lad
 // Round 3: the batch's 32-bit entries (stripes of long reads, reads without an anchor) and then its pairs, one
 // persistent launch.  sel[read] = (top score, n tied rungs that span both flanks, sum of their k, 0); paired reads
 // whose selection hinges on an undecidable tie go to redo[] (entries for ladder_kernel).
+#ifdef NR_DEFINE_PAIR_LADDER_KERNEL      // defined by the one translation unit that owns this kernel (nr_launch_pair3.cu)
 __global__ void __launch_bounds__(32 * kWarpsPerBlock, 1)
 pair_ladder_kernel(const Pair3* __restrict__ pairs, Deal dl, const LadderTask* __restrict__ tasks, RestArgs ra,
                    const uint32_t* __restrict__ qpool, const uint32_t* __restrict__ pool,
@@ -671,6 +674,7 @@ pair_ladder_kernel(const Pair3* __restrict__ pairs, Deal dl, const LadderTask* _
         pair3_dispatch<kMinR>(rows, pt, tasks, qpool, pool, regs, prof, lane, (u32)sc.one, sc.four, sc.min_score, prung, sel, redo_count, redo, qstate);
     }
 }
+#endif
 
 }  // namespace pr
 }  // namespace nr
