@@ -99,6 +99,7 @@ int ensure_init(int device) {
         if (device >= 0 && device != g_ctx.device)
             return fail(NR_ERR_ARG, "the library is already initialised on device %d (requested %d); call nr_shutdown() first",
                         g_ctx.device, device);
+        cudaSetDevice(g_ctx.device);        // the current device is per host thread: a caller's new thread starts on device 0
         return NR_OK;
     }
     if (device < 0) {
@@ -1597,7 +1598,20 @@ int nr_round3_region(const nr_scoring_t* sc, const char* left, int32_t n_left, c
 //   r3 = mean of the tied top rungs that span both anchors (sum and count are exact integers, one division), else r2   :423-433
 namespace {
 
-struct Group { int r0, r1; nr_batch* b2 = nullptr; nr_batch* b3 = nullptr; std::vector<int> regs; };
+struct Group {
+    int r0, r1;
+    nr_batch* b2 = nullptr;
+    nr_batch* b3 = nullptr;
+    std::vector<int> regs;
+    int rc = NR_OK;            // of the thread that packed this group's reads
+    std::string err;
+};
+
+// host threads this process may use (one process per GPU shares the cores with its siblings)
+int host_threads() {
+    static const int share = [] { const char* e = getenv("LOCAL_WORLD_SIZE"); return e && atoi(e) > 0 ? atoi(e) : 1; }();
+    return (int)std::max(1u, std::thread::hardware_concurrency() / (unsigned)share);
+}
 
 int estimate_regions(const nr_scoring_t* sc, int fast_mode, int n_regions, const nr_region_t* regs, double* r1, double* r2,
                      uint8_t* r2_valid, double* r3, uint8_t* r3_state, int32_t* T_out, nr_stats_t* stats) {
@@ -1658,16 +1672,45 @@ int estimate_regions(const nr_scoring_t* sc, int fast_mode, int n_regions, const
     const int min_score = std::max(1, sc->min_dp_score);
     PhaseTrace trace;
     trace.mark("estimate: round 1, grouping");
-    // round 2 of every group, back to back (was pymm2.main at :362)
+    // round 2 of every group (was pymm2.main at :362).  The reads of the groups are packed side by side on host threads
+    // (pure CPU work on each group's own batch; batches are created here, on the thread that owns the CUDA context),
+    // then committed and launched back to back.
     for (Group& G : groups) {
-        for (int g = G.r0; g < G.r1; ++g) {
+        long long bases = 0;
+        for (int g = G.r0; g < G.r1; ++g)
+            if (regs[g].n_reads > 0) { G.regs.push_back(g); bases += regs[g].reads_len + regs[g].n_left + (long long)regs[g].motif_len * T[g]; }
+        if (G.regs.empty()) continue;
+        if (!(G.b2 = nr_batch_begin(sc, NR_KIND_ROUND2_FLAGS))) { cleanup(); return g_code; }
+        G.b2->pool.words.reserve((size_t)(bases / 16 + 2 * (long long)G.regs.size() + 64));
+        long long n_reads = 0;
+        for (int g : G.regs) n_reads += regs[g].n_reads;
+        G.b2->pool.words.reserve((size_t)(bases / 16 + 2 * n_reads + 4 * (long long)G.regs.size() + 64));
+        G.b2->tasks.reserve((size_t)n_reads);
+    }
+    auto pack_group = [&](Group& G) {
+        if (!G.b2) return;
+        for (int g : G.regs) {
             const nr_region_t& R = regs[g];
-            if (R.n_reads == 0) continue;
-            if (!G.b2 && !(G.b2 = nr_batch_begin(sc, NR_KIND_ROUND2_FLAGS))) { cleanup(); return g_code; }
-            if ((rc = nr_batch_add_round2_lines(G.b2, R.left, R.n_left, R.motif, R.motif_len, T[g], R.n_reads, R.reads, R.reads_len))) { cleanup(); return rc; }
-            G.regs.push_back(g);
+            const int rc1 = nr_batch_add_round2_lines(G.b2, R.left, R.n_left, R.motif, R.motif_len, T[g], R.n_reads, R.reads, R.reads_len);
+            if (rc1) { G.rc = rc1; G.err = g_err; return; }      // (the message lives in this thread's g_err)
         }
-        trace.mark("estimate: round-2 add (pack)");
+    };
+    {
+        const int nt = std::min<int>((int)groups.size(), host_threads());
+        if (nt <= 1) {
+            for (Group& G : groups) pack_group(G);
+        } else {
+            std::atomic<int> next{0};
+            auto work = [&]() { for (int i; (i = next.fetch_add(1)) < (int)groups.size();) pack_group(groups[i]); };
+            std::vector<std::thread> th;
+            for (int t = 1; t < nt; ++t) th.emplace_back(work);
+            work();
+            for (auto& x : th) x.join();
+        }
+    }
+    trace.mark("estimate: round-2 add (pack, threads)");
+    for (Group& G : groups) {
+        if (G.rc) { const int rc1 = G.rc; const std::string msg = G.err; cleanup(); return fail(rc1, "%s", msg.c_str()); }
         if (G.b2 && ((rc = nr_batch_commit(G.b2)) || (rc = nr_batch_run(G.b2, nullptr)))) { cleanup(); return rc; }
         trace.mark("estimate: round-2 commit + run");
     }

@@ -428,40 +428,73 @@ def round3_region(sc, left, right, motif, cores, kmin, kmax, want_rungs=False):
     return round3_regions(sc, [(left, right, motif, cores, kmin, kmax)], want_rungs)
 
 
-def estimate_regions(sc, fast_mode, regions):
-    """nr_estimate_regions: rounds 1-3 of many regions in one call.
-    regions: list of (left, right, motif, cores (list of str), dists (sequence of int), round1_max_dist or None).
-    -> dict of arrays over all reads in order: r1, r2, r2_valid, r3, r3_state (0 None / 1 mean of rungs / 2 = r2),
-    plus T per region and the summed stats."""
-    n = len(regions)
-    arr = (RegionIn * max(n, 1))()
-    keep = []                                   # everything the structs point at stays alive until the call returns
-    total = 0
-    dists_all = np.fromiter((d for reg in regions for d in reg[4]), dtype=np.int32)
-    for g, (left, right, motif, cores, dists, max_dist) in enumerate(regions):
-        lb, rb, mb = _b(left), _b(right), _b(motif)
-        joined = "\n".join(cores) if cores and isinstance(cores[0], str) else b"\n".join(cores).decode("latin-1")
-        size = ctypes.c_ssize_t()
-        ptr = _utf8(joined, ctypes.byref(size))
-        if not ptr:
-            raise ValueError("reads are not valid text")
-        keep.append((lb, rb, mb, joined))
-        r = arr[g]
-        r.left, r.n_left, r.right, r.n_right, r.motif, r.motif_len = lb, len(lb), rb, len(rb), mb, len(mb)
-        r.n_reads, r.reads, r.reads_len = len(cores), ptr, size.value
-        r.dist_between_anchors = ctypes.cast(dists_all.ctypes.data + 4 * total, _i32p)
-        r.has_round1_max_dist = max_dist is not None
-        r.round1_max_dist = int(max_dist) if max_dist is not None else 0
-        total += len(cores)
-    if total != len(dists_all):
+# nr_region_t as a numpy record (same layout: natural alignment), so that a table of regions is filled column by column
+REGION_DTYPE = np.dtype([("left", "<u8"), ("n_left", "<i4"), ("right", "<u8"), ("n_right", "<i4"), ("motif", "<u8"),
+                         ("motif_len", "<i4"), ("n_reads", "<i4"), ("reads", "<u8"), ("reads_len", "<i8"),
+                         ("dist_between_anchors", "<u8"), ("has_round1_max_dist", "<i4"), ("round1_max_dist", "<i8")],
+                        align=True)
+assert REGION_DTYPE.itemsize == ctypes.sizeof(RegionIn)
+
+
+def _joined(strings):
+    """list of str -> (one str, its buffer address, int64 start offsets[n + 1]); the str must outlive the pointer."""
+    big = "".join(strings)
+    size = ctypes.c_ssize_t()
+    ptr = _utf8(big, ctypes.byref(size))
+    off = np.zeros(len(strings) + 1, np.int64)
+    np.cumsum(np.fromiter(map(len, strings), np.int64, len(strings)), out=off[1:])
+    if not ptr or size.value != off[-1]:
+        raise ValueError("sequences must be ASCII text")
+    return big, ptr, off
+
+
+def estimate_regions(sc, fast_mode, lefts, rights, motifs, cores, dists, max_dists=None):
+    """nr_estimate_regions: rounds 1-3 of many regions in one call into the library.
+    lefts / rights / motifs: one str per region; cores: one list of str per region (at least one read each); dists: all
+    reads' dist_between_anchors, flat, in the same order; max_dists: per region None or the whole region's longest
+    distance when the region is a piece of a split one.
+    -> dict of arrays over all reads in order: r1, r2, r2_valid, r3, r3_state (0 None / 1 mean of rungs / 2 = r2), plus T
+    per region and the summed stats.  The table of regions is built column by column (no per-region ctypes work)."""
+    n = len(lefts)
+    dists = np.ascontiguousarray(dists, dtype=np.int32)
+    n_reads = np.fromiter(map(len, cores), np.int64, n)
+    total = int(n_reads.sum())
+    if total != len(dists):
         raise ValueError("cores and dist_between_anchors differ in length")
+    tab = np.zeros(max(n, 1), REGION_DTYPE)
+    keep = []
+    for name, seqs in (("left", lefts), ("right", rights), ("motif", motifs)):
+        big, ptr, off = _joined(seqs)
+        keep.append(big)
+        tab[name][:n] = ptr + off[:-1]
+        tab["n_" + name if name != "motif" else "motif_len"][:n] = off[1:] - off[:-1]
+    lines = ["\n".join(c) for c in cores]                 # a region's reads as lines
+    big = "\n".join(lines)
+    size = ctypes.c_ssize_t()
+    ptr = _utf8(big, ctypes.byref(size))
+    keep.append(big)
+    llen = np.fromiter(map(len, lines), np.int64, n)
+    start = np.zeros(n + 1, np.int64)
+    np.cumsum(llen + 1, out=start[1:])
+    if not ptr or (n and size.value != start[-1] - 1):
+        raise ValueError("reads must be ASCII text")
+    first = np.zeros(n + 1, np.int64)
+    np.cumsum(n_reads, out=first[1:])
+    tab["reads"][:n] = ptr + start[:-1]
+    tab["reads_len"][:n] = llen
+    tab["n_reads"][:n] = n_reads
+    tab["dist_between_anchors"][:n] = dists.ctypes.data + 4 * first[:-1]
+    if max_dists is not None:
+        has = np.fromiter((d is not None for d in max_dists), np.bool_, n)
+        tab["has_round1_max_dist"][:n] = has
+        tab["round1_max_dist"][:n] = np.fromiter((0 if d is None else d for d in max_dists), np.int64, n)
     r1 = np.zeros(total, np.float64); r2 = np.zeros(total, np.float64); r3 = np.zeros(total, np.float64)
     r2_valid = np.zeros(total, np.uint8); r3_state = np.zeros(total, np.uint8)
     T = np.zeros(max(n, 1), np.int32)
     st = Stats()
     dp = ctypes.POINTER(ctypes.c_double)
-    _check(lib().nr_estimate_regions(ctypes.byref(sc), int(bool(fast_mode)), n, arr, r1.ctypes.data_as(dp), r2.ctypes.data_as(dp),
-                                     r2_valid.ctypes.data, r3.ctypes.data_as(dp), r3_state.ctypes.data, T.ctypes.data_as(_i32p),
-                                     ctypes.byref(st)))
+    _check(lib().nr_estimate_regions(ctypes.byref(sc), int(bool(fast_mode)), n, ctypes.cast(tab.ctypes.data, ctypes.POINTER(RegionIn)),
+                                     r1.ctypes.data_as(dp), r2.ctypes.data_as(dp), r2_valid.ctypes.data, r3.ctypes.data_as(dp),
+                                     r3_state.ctypes.data, T.ctypes.data_as(_i32p), ctypes.byref(st)))
     del keep
     return dict(r1=r1, r2=r2, r2_valid=r2_valid.astype(bool), r3=r3, r3_state=r3_state, T=T[:n], stats=st.as_dict())

@@ -265,12 +265,10 @@ def round3_estimation(data_type, fast_mode, repeat_region, num_cpu=1):
     return
 
 
-def _estimate_regions_fused(dt, fast_mode, rrs):
-    """Rounds 1-3 of a list of regions through nr_estimate_regions: one call into the library, which runs round 2,
-    derives every read's ladder from it and runs round 3 without coming back here in between; the attributes of
-    every Read are then assigned once from the returned arrays."""
-    sc = _scoring_for(dt)
-    specs, todo = [], []
+def _gather_chunk(rrs):
+    """What nr_estimate_regions needs of a list of regions, column by column, plus the Read objects in result order."""
+    lefts, rights, motifs, cores, max_dists, todo = [], [], [], [], [], []
+    any_max = False
     for rr in rrs:
         reads = rr.read_dict
         if len(reads) == 0:
@@ -278,25 +276,45 @@ def _estimate_regions_fused(dt, fast_mode, rrs):
         core_dict = rr.read_core_seq_dict
         # reads come from read_core_seq_dict, which is what the reference wrote to core_sequences.fastq (:311-321); a read
         # without a core there gets round 1 only (it is not in the FASTQ the reference aligns)
-        if core_dict.keys() >= reads.keys():
-            qnames, extra = list(reads), ()
-        else:
-            qnames = [n for n in reads if n in core_dict]
-            extra = [n for n in reads if n not in core_dict]
-        read_list = list(map(reads.__getitem__, qnames))
         max_dist = getattr(rr, "round1_max_dist", None)                         # a piece of a split region (sharding)
-        if extra:
+        if core_dict.keys() >= reads.keys():
+            read_list = list(reads.values())
+            cores.append(list(map(core_dict.__getitem__, reads)))
+        else:
             m = len(rr.repeat_unit_seq)
-            for n in extra:
-                reads[n].round1_repeat_size = float(reads[n].dist_between_anchors) / m
-            far = max(reads[n].dist_between_anchors for n in extra)             # T is over ALL reads of the region (:344)
+            extra = [rd for n, rd in reads.items() if n not in core_dict]
+            for rd in extra:
+                rd.round1_repeat_size = float(rd.dist_between_anchors) / m
+            far = max(rd.dist_between_anchors for rd in extra)                  # T is over ALL reads of the region (:344)
             max_dist = far if max_dist is None else max(max_dist, far)
-        specs.append((rr.left_anchor_seq, rr.right_anchor_seq, rr.repeat_unit_seq, _cores_of(rr, qnames),
-                      [rd.dist_between_anchors for rd in read_list], max_dist))
+            qnames = [n for n in reads if n in core_dict]
+            if not qnames:
+                continue
+            read_list = list(map(reads.__getitem__, qnames))
+            cores.append(list(map(core_dict.__getitem__, qnames)))
+        any_max = any_max or max_dist is not None
+        lefts.append(rr.left_anchor_seq); rights.append(rr.right_anchor_seq); motifs.append(rr.repeat_unit_seq)
+        max_dists.append(max_dist)
         todo.append(read_list)
-    if not specs:
-        return
-    res = engine.estimate_regions(sc, fast_mode, specs)
+    dists = [rd.dist_between_anchors for read_list in todo for rd in read_list]
+    return (lefts, rights, motifs, cores, dists, max_dists if any_max else None), todo
+
+
+def _run_chunk(sc, fast_mode, cols):
+    """One call into the library (ctypes releases the GIL for its duration)."""
+    lefts, rights, motifs, cores, dists, max_dists = cols
+    try:
+        return engine.estimate_regions(sc, fast_mode, lefts, rights, motifs, cores, dists, max_dists)
+    except engine.NanoRepeatB200Error as e:
+        if e.code != -3:
+            raise
+        # a core with a line break inside or around it (the reads travel as lines): the reference's FASTQ round trip
+        # drops white space around a read (:311-321), so do that here and go again
+        cores = [[c.strip() for c in cl] for cl in cores]
+        return engine.estimate_regions(sc, fast_mode, lefts, rights, motifs, cores, dists, max_dists)
+
+
+def _assign_chunk(res, todo):
     r1, r2, r3 = res["r1"].tolist(), res["r2"].tolist(), res["r3"]
     ok2, st3 = res["r2_valid"].tolist(), res["r3_state"].tolist()
     pos = 0
@@ -312,6 +330,58 @@ def _estimate_regions_fused(dt, fast_mode, rrs):
                 elif s == 2:
                     rd.round3_repeat_size = v                                   # :433
             pos += 1
+
+
+CHUNK_MIN_READS = 4096      # reads per call into the library when a region list is cut into pipelined chunks
+_POOL = None
+
+
+def _chunks(rrs):
+    """Contiguous chunks of regions of at least CHUNK_MIN_READS reads each, at most 6."""
+    total = sum(len(rr.read_dict) for rr in rrs)
+    n = max(1, min(6, total // CHUNK_MIN_READS))
+    if n == 1:
+        return [rrs]
+    out, cur, acc = [], [], 0
+    for rr in rrs:
+        cur.append(rr)
+        acc += len(rr.read_dict)
+        if acc * n >= total * (len(out) + 1) and len(out) < n - 1:
+            out.append(cur)
+            cur = []
+    if cur:
+        out.append(cur)
+    return out
+
+
+def _estimate_regions_fused(dt, fast_mode, rrs):
+    """Rounds 1-3 of a list of regions through nr_estimate_regions: the library runs round 2, derives every read's ladder
+    from it and runs round 3 without coming back here in between; the attributes of every Read are then assigned once
+    from the returned arrays.  A long list is cut into a few chunks: while the library (GIL released) and the GPU work
+    on one chunk, this thread gathers the next chunk's strings and assigns the previous chunk's results, so that the
+    Python side of the boundary -- one attribute read and three attribute writes per Read object -- hides behind the
+    kernels."""
+    global _POOL
+    sc = _scoring_for(dt)
+    chunks = _chunks(rrs)
+    if len(chunks) == 1:
+        cols, todo = _gather_chunk(rrs)
+        if todo:
+            _assign_chunk(_run_chunk(sc, fast_mode, cols), todo)
+        return
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=2, thread_name_prefix="nanorepeat_b200")
+    pending = []
+    for ch in chunks:
+        cols, todo = _gather_chunk(ch)
+        if todo:
+            pending.append((_POOL.submit(_run_chunk, sc, fast_mode, cols), todo))
+        while pending and pending[0][0].done():
+            fut, td = pending.pop(0)
+            _assign_chunk(fut.result(), td)
+    for fut, td in pending:
+        _assign_chunk(fut.result(), td)
 
 
 def estimate_regions(regions, data_type=None, fast_mode=False):
