@@ -431,10 +431,9 @@ struct Sweep {
                     cell_w32(hd, r == 0 ? mul0 : ms.one, s4[u], ms, h, E1[r], E2[r], f1, f2);
                     if (JUNC) {
                         const int4 b = bsm[r * 32 + lane];
-                        if (MODE == kFwdF) {
-                            jhi = __viaddmax_s32(h, b.x, jhi);
-                            jhi = __viaddmax_s32(e1pre, b.y, jhi);
-                            jhi = __viaddmax_s32(e2pre, b.z, jhi);
+                        if (MODE == kFwdF) {       // the sums on the FMA pipe, two three-input maxima on the DPX pipe
+                            jhi = __vimax3_s32(jhi, madd(h, ms.one, b.x), madd(e1pre, ms.one, b.y));
+                            jhi = max(jhi, madd(e2pre, ms.one, b.z));
                         } else {
                             jcand(h, b.x, sc, jhi, jlo);
                             jcand(e1pre, b.y, sc, jhi, jlo);

@@ -195,9 +195,14 @@ struct Sweep {
         return hi;
     }
 
-    template <bool JUNC>
-    __device__ __forceinline__ u32 cells(const uint4* pp, u32 hd, u32 cm, u32& f1, u32& f2, u32 one, u32& jhi) {
+    // JUNC: junction candidates of this column (forward word + backward word per row and state; the sums are plain 32-bit
+    // adds -- both halves stay below 2^16 -- on the FMA pipe, the maxima three-input ones: 1.5 DPX-class instructions
+    // per row instead of 3).  KEEP_E (kPB, guarded steps): in the sweep's last column the gap states are left as they
+    // entered it, which is what the junction vectors hold (store_junction_vectors).
+    template <bool JUNC, bool KEEP_E = false>
+    __device__ __forceinline__ u32 cells(const uint4* pp, u32 hd, u32 cm, u32& f1, u32& f2, u32 one, u32& jhi, bool keep = false) {
         constexpr int CH = StripeCfg<R>::CH;
+        u32 jprev = 0;
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
             const uint4 sv = pp[c * 32];
@@ -210,11 +215,13 @@ struct Sweep {
                     const u32 e1pre = E1[r], e2pre = E2[r];
                     u32 h;
                     cell<FLOOR>(hd, s4[u], one, h, E1[r], E2[r], f1, f2);
+                    if (KEEP_E) { E1[r] = keep ? e1pre : E1[r]; E2[r] = keep ? e2pre : E2[r]; }
                     if (JUNC) {
                         const uint4 b = bsm[r * 32 + lane];
-                        jhi = __viaddmax_u16x2(h, b.x, jhi);
-                        jhi = __viaddmax_u16x2(e1pre, b.y, jhi);
-                        jhi = __viaddmax_u16x2(e2pre, b.z, jhi);
+                        const u32 t = __vimax3_u16x2(pmadd(h, one, b.x), pmadd(e1pre, one, b.y), pmadd(e2pre, one, b.z));
+                        if (r & 1) jhi = __vimax3_u16x2(jhi, jprev, t);
+                        else if (r == R - 1) jhi = __vmaxu2(jhi, t);
+                        jprev = t;
                     }
                     hd = hleft;
                     H[r] = h;
@@ -237,10 +244,35 @@ struct Sweep {
         hup_prev = __viaddmax_u16x2(hup_prev, pk(-1), FLOOR);
     }
 
-    // kPB, last column: half h of junction vector component comp of forward row idx0
-    __device__ __forceinline__ void put_half(int idx0, int comp, int hi, u32 v) {
-        unsigned short* p = reinterpret_cast<unsigned short*>(&bvec[bvec_pos<R>(idx0)]) + 2 * comp + hi;
-        *p = (unsigned short)v;
+    // kPB, after the sweep: the junction vectors.  Every lane still holds, for its R rows of the reversed reads, H of the
+    // last column and the gap states that entered it (cells<.., KEEP_E>).  They go to `stage` (the reversed profile's
+    // shared memory, dead by now) as they are, [state][row][lane]; then every lane gathers the vectors of ITS forward
+    // rows -- forward row i of read A is reversed row q_a - 2 - i (read B: q_b - 2 - i; the halves move apart) -- and
+    // writes them in the forward layout the junction columns read.  Rows the sweep has no value for: the right part is
+    // empty (score 0, no gap state) for the last row of a read, void below it.
+    __device__ __forceinline__ void store_junction_vectors(u32* stage, uint4* bvec_fwd) {
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            stage[(0 * R + r) * 32 + lane] = H[r];
+            stage[(1 * R + r) * 32 + lane] = E1[r] + pk(kRefund1);
+            stage[(2 * R + r) * 32 + lane] = E2[r] + pk(kRefund2);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int idx0 = lane * R + r;
+            const int ia = q_a - 2 - idx0, ib = q_b - 2 - idx0;
+            u32 v[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const u32 da = c == 0 ? (idx0 < q_a ? (u32)kBias : 0u) : 0u, db = c == 0 ? (idx0 < q_b ? (u32)kBias : 0u) : 0u;
+                const u32 a = ia >= 0 ? stage[(c * R + ia % R) * 32 + ia / R] >> 16 : da;
+                const u32 b = ib >= 0 ? stage[(c * R + ib % R) * 32 + ib / R] & 0xffffu : db;
+                v[c] = (a << 16) | b;
+            }
+            bvec_fwd[r * 32 + lane] = make_uint4(v[0], v[1], v[2], 0u);
+        }
     }
 
     // TRACK (kP2): per half the step of the last strict improvement of the score class; without it (the columns an
@@ -272,18 +304,10 @@ struct Sweep {
             hup_prev = hup;
             constexpr bool kChecks = !FAST || SPECIAL;
             const bool last_col = !FAST && MODE == kPB && jj == t_len - 1;
-            if (MODE == kPB && !FAST && last_col) {      // E(i', n_right): the gap states entering the last column
-                const int brow0 = lane * R;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int ia = q_a - 2 - (brow0 + r), ib = q_b - 2 - (brow0 + r);
-                    if (ia >= 0) { put_half(ia, 1, 1, (E1[r] >> 16) + kRefund1); put_half(ia, 2, 1, (E2[r] >> 16) + kRefund2); }
-                    if (ib >= 0) { put_half(ib, 1, 0, (E1[r] & 0xffffu) + kRefund1); put_half(ib, 2, 0, (E2[r] & 0xffffu) + kRefund2); }
-                }
-            }
             u32 cm, jhi = 0;
             const u32 cm0 = (MODE == kP2 && TRACK) ? 0u : best;
             if (zone && anyj) cm = cells<true>(pp, hd, cm0, f1, f2, one, jhi);
+            else if (MODE == kPB && !FAST) cm = cells<false, true>(pp, hd, cm0, f1, f2, one, jhi, last_col);
             else cm = cells<false>(pp, hd, cm0, f1, f2, one, jhi);
             h_out = H[R - 1]; f1_out = f1; f2_out = f2;
             if (MODE == kP2 && TRACK) {
@@ -306,15 +330,6 @@ struct Sweep {
                 }
             } else {
                 best = cm;
-                if (last_col) {
-                    const int brow0 = lane * R;
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const int ia = q_a - 2 - (brow0 + r), ib = q_b - 2 - (brow0 + r);
-                        if (ia >= 0) put_half(ia, 0, 1, H[r] >> 16);
-                        if (ib >= 0) put_half(ib, 0, 0, H[r] & 0xffffu);
-                    }
-                }
             }
             if (zone && jj + 1 == jnext) {
                 if (lane == 0) { tP = 0; tJ = 0; }
@@ -560,13 +575,7 @@ __device__ __forceinline__ void pair3_task(const Pair3& pt, const LadderTask* __
     const int kmax = (ha && hb) ? max(ta.kmax, tb.kmax) : tv.kmax;
     uint4* bsm = prof + StripeCfg<R>::PROF_INT4;
     uint2* rungs = prung + pt.rung_off;
-    // junction vectors, defaults: right part empty (score 0, no gap state) for rows of the read, void below it
     __syncwarp();
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int idx0 = lane * R + r;
-        bsm[r * 32 + lane] = make_uint4(pk2(idx0 < q_a ? kBias : 0, idx0 < q_b ? kBias : 0), 0u, 0u, 0u);
-    }
     build_profile<R>(prof, qpool + ta.q_word, q_a, qpool + tb.q_word, q_b, lane * R, lane, true);
     __syncwarp();
     u32 rcand;
@@ -578,6 +587,7 @@ __device__ __forceinline__ void pair3_task(const Pair3& pt, const LadderTask* __
         sw.run(one, four, 0);
         const u32 ra = __reduce_max_sync(kFull, sw.best >> 16), rb = __reduce_max_sync(kFull, sw.best & 0xffffu);
         rcand = pk2((int)ra + kBias + 1, (int)rb + kBias + 1);      // forward part empty: score 0, unmarked
+        sw.store_junction_vectors(reinterpret_cast<u32*>(prof), bsm);
     }
     __syncwarp();
     build_profile<R>(prof, qpool + ta.q_word, q_a, qpool + tb.q_word, q_b, lane * R, lane, false);
