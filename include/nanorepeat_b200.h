@@ -251,6 +251,31 @@ int nr_estimate_regions(const nr_scoring_t* sc, int32_t fast_mode, int32_t n_reg
                         double* r1, double* r2, uint8_t* r2_valid, double* r3, uint8_t* r3_state, int32_t* T_out,
                         nr_stats_t* stats /* nullable: summed over the batches of the call */);
 
+/*
+ * Joint path (nanoRepeat-joint: two neighbouring repeats quantified together).  The reference aligns every read against
+ * a grid of templates left + motif1*k1 + mid + motif2*k2 + right with `minimap2 -c --eqx` (nanoRepeat_joint.py:315-343,
+ * :397-419) and re-scores each alignment's CIGAR inside the window [|left| - 10, |left| + m1 k1 + |mid| + m2 k2 + 10)
+ * with tk.target_region_alignment_stats_from_cigar (tk.py:435-500); per read the grid point with the best window score
+ * wins (nanoRepeat_joint.py:457-476).  Here one DP returns both numbers per (read, template): the alignment score and the
+ * window score of the optimal alignment, carried through the DP as a payload -- no CIGAR, no text.  Among alignments of
+ * equal score the one with the highest window score is the alignment (the CPU checker under oracle/ states the same rule; its
+ * traceback's CIGAR re-scored by the reference's own function gives the same number: tests/golden/make_golden_window.py).
+ * A read is aligned as given and as its reverse complement when asked (the joint CLI feeds raw reads of either strand).
+ */
+typedef struct nr_window_t { int32_t score, window_score; } nr_window_t;
+/* n independent (query, target, window [a, b)) tasks; reverse (nullable): 1 = align the query's reverse complement. */
+int nr_window_tasks(const nr_scoring_t* sc, int32_t n_tasks, const char* const* queries, const int32_t* qlen,
+                    const char* const* targets, const int32_t* tlen, const int32_t* win_a, const int32_t* win_b,
+                    const uint8_t* reverse, nr_window_t* out);
+/* Grid points of one locus: point i = read point_read[i] against the template of (point_k1[i], point_k2[i]); every
+ * distinct template is built and packed once.  out[i] = the better strand's (score, window score), strand[i] (nullable)
+ * 0 for '+', 1 for '-'.  score 0: no alignment (the reference would have no PAF line). */
+int nr_joint_grid(const nr_scoring_t* sc, const char* left, int32_t n_left, const char* mid, int32_t n_mid,
+                  const char* right, int32_t n_right, const char* motif1, int32_t m1, const char* motif2, int32_t m2,
+                  int32_t n_reads, const char* const* reads, const int32_t* read_len, int32_t n_points,
+                  const int32_t* point_read, const int32_t* point_k1, const int32_t* point_k2, nr_window_t* out,
+                  uint8_t* strand);
+
 /* Counters of the last nr_score_tasks / nr_round2_region / nr_round3_region call on this thread. */
 int nr_last_stats(nr_stats_t* out);
 

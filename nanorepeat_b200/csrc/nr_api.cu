@@ -1792,3 +1792,18 @@ extern "C" int nr_estimate_regions(const nr_scoring_t* sc, int32_t fast_mode, in
         return fail(NR_ERR_ARG, "nr_estimate_regions needs map-ont scoring and a shared-sweep ladder mode (1-3)");
     return estimate_regions(sc, fast_mode, n_regions, regions, r1, r2, r2_valid, r3, r3_state, T_out, stats);
 }
+
+// ---- what the other host translation units (nr_joint.cu, nr_anchor.cu) share with this one ----------------------------
+#include "nr_internal.h"
+namespace nri {
+int ensure_init() { return ::ensure_init(-1); }
+cudaStream_t stream() { return g_ctx.stream; }
+int sm_count() { return g_ctx.sm_count; }
+int fail_msg(int code, const char* msg) { return fail(code, "%s", msg); }
+int last_code() { return g_code; }
+bool pack(const char* s, int len, uint32_t* w) { return pack_seq(s, len, w); }
+void ambiguity(const char* s, int len, uint32_t* m) { ambiguity_plane(s, len, m); }
+int alloc(void** p, size_t bytes, bool pinned) { return cached_alloc(p, bytes, pinned ? BUF_PIN : BUF_DEV); }
+void release(void* p, size_t bytes, bool pinned) { cached_free(p, bytes, pinned ? BUF_PIN : BUF_DEV); }
+int check(const nr_scoring_t* sc) { return check_scoring(sc); }
+}  // namespace nri

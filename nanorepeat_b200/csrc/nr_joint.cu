@@ -1,0 +1,190 @@
+// nr_joint.cu -- host side + launcher of the joint path (nanoRepeat-joint): alignment score and window score of every
+// (read, template) task in one DP (nr_window_kernel.cuh).  C ABI: nr_window_tasks, nr_joint_grid.
+#include "nr_internal.h"
+#include "nr_window_kernel.cuh"
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace {
+
+#define JTRY(expr)                                                                                       \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            char b__[256];                                                                               \
+            snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return nri::fail_msg(NR_ERR_CUDA, b__);                                                      \
+        }                                                                                                \
+    } while (0)
+
+struct SeqPool {
+    std::vector<uint32_t> words;
+    // read: bases other than ACGT get an ambiguity plane (linked from the slack word); template: must be ACGT (-1)
+    long long add(const char* s, int len, bool is_read) {
+        const size_t w0 = words.size();
+        words.resize(w0 + (size_t)(len + 15) / 16 + 1, 0u);
+        if (!nri::pack(s, len, words.data() + w0)) {
+            if (!is_read) { words.resize(w0); return -1; }
+            const size_t at = words.size();
+            words.resize(at + (size_t)(len + 31) / 32, 0u);
+            nri::ambiguity(s, len, words.data() + at);
+            words[w0 + (size_t)(len + 15) / 16] = (uint32_t)(at - w0);
+        }
+        return (long long)w0;
+    }
+};
+
+constexpr int kMaxScore = 32767, kMaxWindow = 8000, kMaxTlen = 1 << 20;
+
+// tasks[i].q_word / t_word index `pool`; out[i] = (score, window score); skipped tasks (outside the packed range) stay 0
+int run_window_tasks(const nr_scoring_t* sc, std::vector<nrw::WinTask>& tasks, const SeqPool& pool, nr_window_t* out, int* n_skipped) {
+    const int n = (int)tasks.size();
+    if (n == 0) return NR_OK;
+    int max_t = 1;
+    for (nrw::WinTask& t : tasks) {
+        const long long m = (long long)sc->match * std::min(t.q_len, t.t_len);
+        if (m > kMaxScore || t.win_b - t.win_a > kMaxWindow || t.t_len > kMaxTlen) { t.q_len = 0; if (n_skipped) ++*n_skipped; }
+        max_t = std::max(max_t, t.t_len);
+    }
+    // long tasks first: the tail of the launch is made of short ones
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int x, int y) {
+        const long long cx = (long long)tasks[x].q_len * tasks[x].t_len, cy = (long long)tasks[y].q_len * tasks[y].t_len;
+        return cx != cy ? cx > cy : x < y;
+    });
+    std::vector<nrw::WinTask> sorted(n);
+    for (int i = 0; i < n; ++i) sorted[i] = tasks[order[i]];
+    const int blocks = std::max(1, std::min(2 * nri::sm_count(), (n + nrw::kWarps - 1) / nrw::kWarps));
+    const int stride = 2 * ((max_t + 31) / 32 * 32);
+    const size_t task_bytes = sizeof(nrw::WinTask) * n, pool_bytes = sizeof(uint32_t) * (pool.words.size() + 4),
+                 out_bytes = sizeof(int2) * n, scratch_bytes = sizeof(int4) * (size_t)blocks * nrw::kWarps * stride;
+    void *d_tasks = nullptr, *d_pool = nullptr, *d_out = nullptr, *d_scratch = nullptr, *d_counter = nullptr, *h_out = nullptr;
+    int rc;
+    auto cleanup = [&]() {
+        nri::release(d_tasks, task_bytes, false); nri::release(d_pool, pool_bytes, false); nri::release(d_out, out_bytes, false);
+        nri::release(d_scratch, scratch_bytes, false); nri::release(d_counter, 256, false); nri::release(h_out, out_bytes, true);
+    };
+    if ((rc = nri::alloc(&d_tasks, task_bytes, false)) || (rc = nri::alloc(&d_pool, pool_bytes, false)) ||
+        (rc = nri::alloc(&d_out, out_bytes, false)) || (rc = nri::alloc(&d_scratch, scratch_bytes, false)) ||
+        (rc = nri::alloc(&d_counter, 256, false)) || (rc = nri::alloc(&h_out, out_bytes, true))) { cleanup(); return rc; }
+    cudaStream_t st = nri::stream();
+    nrw::WinScore k;
+    k.match = sc->match << 16; k.mismatch = -(sc->mismatch << 16); k.ambiguous = -(sc->ambiguous << 16);
+    k.open1 = -((sc->gap_open1 + sc->gap_ext1) << 16); k.ext1 = -(sc->gap_ext1 << 16);
+    k.open2 = -((sc->gap_open2 + sc->gap_ext2) << 16); k.ext2 = -(sc->gap_ext2 << 16);
+    const size_t smem = (size_t)nrw::kWarps * 8 * nrw::kRows * sizeof(int);
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&]() { attr_err = cudaFuncSetAttribute(nrw::window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+    cudaError_t e = attr_err;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_tasks, sorted.data(), task_bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_pool, pool.words.data(), sizeof(uint32_t) * pool.words.size(), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_counter, 0, 256, st);
+    if (e == cudaSuccess) {
+        nrw::window_kernel<<<blocks, 32 * nrw::kWarps, smem, st>>>(static_cast<const nrw::WinTask*>(d_tasks), n, static_cast<const uint32_t*>(d_pool), k,
+                                                                  static_cast<int4*>(d_scratch), stride, static_cast<int*>(d_counter),
+                                                                  static_cast<int2*>(d_out));
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cleanup(); cudaGetLastError(); return nri::fail_msg(NR_ERR_CUDA, cudaGetErrorString(e)); }
+    const int2* res = static_cast<const int2*>(h_out);
+    for (int i = 0; i < n; ++i) { out[order[i]].score = res[i].x; out[order[i]].window_score = res[i].y; }
+    cleanup();
+    return NR_OK;
+}
+
+}  // namespace
+
+extern "C" int nr_window_tasks(const nr_scoring_t* sc, int32_t n_tasks, const char* const* queries, const int32_t* qlen,
+                               const char* const* targets, const int32_t* tlen, const int32_t* win_a, const int32_t* win_b,
+                               const uint8_t* reverse, nr_window_t* out) {
+    if (nri::check(sc)) return nri::last_code();
+    if (n_tasks < 0 || (n_tasks > 0 && (!queries || !qlen || !targets || !tlen || !win_a || !win_b || !out)))
+        return nri::fail_msg(NR_ERR_ARG, "nr_window_tasks: bad arguments");
+    int rc = nri::ensure_init();
+    if (rc) return rc;
+    SeqPool pool;
+    std::vector<nrw::WinTask> tasks(n_tasks);
+    std::map<std::pair<const char*, int>, long long> seen_q, seen_t;
+    for (int i = 0; i < n_tasks; ++i) {
+        nrw::WinTask& t = tasks[i];
+        t = {};
+        out[i].score = out[i].window_score = 0;
+        if (qlen[i] < 0 || tlen[i] < 0) return nri::fail_msg(NR_ERR_ARG, "nr_window_tasks: negative length");
+        auto qk = std::make_pair(queries[i], (int)qlen[i]);
+        auto tk = std::make_pair(targets[i], (int)tlen[i]);
+        if (!seen_q.count(qk)) seen_q[qk] = pool.add(queries[i], qlen[i], true);
+        if (!seen_t.count(tk)) seen_t[tk] = pool.add(targets[i], tlen[i], false);
+        const long long tw = seen_t[tk];
+        t.q_word = (uint32_t)seen_q[qk]; t.q_len = qlen[i];
+        t.t_word = tw < 0 ? 0u : (uint32_t)tw; t.t_len = tw < 0 ? 0 : tlen[i];      // a template with N is not scored
+        t.win_a = std::max(0, win_a[i]); t.win_b = std::min(win_b[i], tlen[i]);
+        t.reverse = reverse ? reverse[i] != 0 : 0;
+    }
+    return run_window_tasks(sc, tasks, pool, out, nullptr);
+}
+
+extern "C" int nr_joint_grid(const nr_scoring_t* sc, const char* left, int32_t n_left, const char* mid, int32_t n_mid,
+                             const char* right, int32_t n_right, const char* motif1, int32_t m1, const char* motif2, int32_t m2,
+                             int32_t n_reads, const char* const* reads, const int32_t* read_len, int32_t n_points,
+                             const int32_t* point_read, const int32_t* point_k1, const int32_t* point_k2, nr_window_t* out,
+                             uint8_t* strand) {
+    if (nri::check(sc)) return nri::last_code();
+    if (n_left < 0 || n_mid < 0 || n_right < 0 || m1 <= 0 || m2 <= 0 || n_reads < 0 || n_points < 0 || !motif1 || !motif2 ||
+        (n_left > 0 && !left) || (n_mid > 0 && !mid) || (n_right > 0 && !right) || (n_reads > 0 && (!reads || !read_len)) ||
+        (n_points > 0 && (!point_read || !point_k1 || !point_k2 || !out)))
+        return nri::fail_msg(NR_ERR_ARG, "nr_joint_grid: bad arguments");
+    int rc = nri::ensure_init();
+    if (rc) return rc;
+    SeqPool pool;
+    std::vector<long long> read_word(n_reads);
+    for (int r = 0; r < n_reads; ++r) {
+        if (read_len[r] < 0) return nri::fail_msg(NR_ERR_ARG, "nr_joint_grid: negative read length");
+        read_word[r] = pool.add(reads[r], read_len[r], true);
+    }
+    // one template per distinct grid point: left + motif1 * k1 + mid + motif2 * k2 + right (nanoRepeat_joint.py:351-374)
+    std::map<std::pair<int, int>, std::pair<long long, int>> tpl;      // (k1, k2) -> (word, length)
+    std::vector<nrw::WinTask> tasks;
+    tasks.reserve((size_t)n_points * 2);
+    std::string s;
+    for (int i = 0; i < n_points; ++i) {
+        const int r = point_read[i], k1 = point_k1[i], k2 = point_k2[i];
+        if (r < 0 || r >= n_reads || k1 < 0 || k2 < 0) return nri::fail_msg(NR_ERR_ARG, "nr_joint_grid: bad grid point");
+        auto key = std::make_pair(k1, k2);
+        auto it = tpl.find(key);
+        if (it == tpl.end()) {
+            s.assign(left ? left : "", (size_t)n_left);
+            for (int u = 0; u < k1; ++u) s.append(motif1, (size_t)m1);
+            s.append(mid ? mid : "", (size_t)n_mid);
+            for (int u = 0; u < k2; ++u) s.append(motif2, (size_t)m2);
+            s.append(right ? right : "", (size_t)n_right);
+            it = tpl.emplace(key, std::make_pair(pool.add(s.data(), (int)s.size(), false), (int)s.size())).first;
+        }
+        const long long tw = it->second.first;
+        const int tl = it->second.second;
+        nrw::WinTask t = {};
+        t.q_word = (uint32_t)read_word[r]; t.q_len = read_len[r];
+        t.t_word = tw < 0 ? 0u : (uint32_t)tw; t.t_len = tw < 0 ? 0 : tl;
+        t.win_a = std::max(n_left - 10, 0);                                                   // nanoRepeat_joint.py:448-451
+        t.win_b = std::min(n_left + m1 * k1 + n_mid + m2 * k2 + 10, tl);
+        t.reverse = 0; tasks.push_back(t);
+        t.reverse = 1; tasks.push_back(t);
+    }
+    std::vector<nr_window_t> res(tasks.size());
+    if ((rc = run_window_tasks(sc, tasks, pool, res.data(), nullptr))) return rc;
+    for (int i = 0; i < n_points; ++i) {
+        const nr_window_t f = res[2 * (size_t)i], v = res[2 * (size_t)i + 1];
+        // the better strand by (score, window score); '+' on a full tie
+        const bool rev = v.score > f.score || (v.score == f.score && v.window_score > f.window_score);
+        out[i] = rev ? v : f;
+        if (strand) strand[i] = rev ? 1 : 0;
+    }
+    return NR_OK;
+}

@@ -109,6 +109,11 @@ SYMBOLS = {
     "nr_batch_launch_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(LaunchInfo)]),
     "nr_batch_destroy": (None, [ctypes.c_void_p]),
     "nr_last_stats": (ctypes.c_int, [ctypes.POINTER(Stats)]),
+    "nr_window_tasks": (ctypes.c_int, [_scp, ctypes.c_int32, _cpp, _i32p, _cpp, _i32p, _i32p, _i32p, ctypes.c_void_p, ctypes.c_void_p]),
+    "nr_joint_grid": (ctypes.c_int, [_scp, ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p,
+                                     ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32,
+                                     ctypes.c_int32, _cpp, _i32p, ctypes.c_int32, _i32p, _i32p, _i32p, ctypes.c_void_p,
+                                     ctypes.c_void_p]),
     "nr_estimate_regions": (ctypes.c_int, [_scp, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(RegionIn),
                                            ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.c_void_p,
                                            ctypes.POINTER(ctypes.c_double), ctypes.c_void_p, _i32p, ctypes.POINTER(Stats)]),
@@ -498,3 +503,42 @@ def estimate_regions(sc, fast_mode, lefts, rights, motifs, cores, dists, max_dis
                                      r3_state.ctypes.data, T.ctypes.data_as(_i32p), ctypes.byref(st)))
     del keep
     return dict(r1=r1, r2=r2, r2_valid=r2_valid.astype(bool), r3=r3, r3_state=r3_state, T=T[:n], stats=st.as_dict())
+
+
+WINDOW_DTYPE = np.dtype([("score", "<i4"), ("window_score", "<i4")])
+
+
+def window_tasks(queries, targets, win_a, win_b, sc, reverse=None):
+    """nr_window_tasks: (alignment score, window score of the optimal alignment inside [win_a, win_b)) per task."""
+    n = len(queries)
+    out = np.zeros(n, dtype=WINDOW_DTYPE)
+    _qb, qa, ql = _cstrs(queries)
+    _tb, ta, tl = _cstrs(targets)
+    a = np.ascontiguousarray(win_a, dtype=np.int32)
+    b = np.ascontiguousarray(win_b, dtype=np.int32)
+    rv = None if reverse is None else np.ascontiguousarray(reverse, dtype=np.uint8)
+    if len(targets) != n or len(a) != n or len(b) != n or (rv is not None and len(rv) != n):
+        raise ValueError("task arrays differ in length")
+    _check(lib().nr_window_tasks(ctypes.byref(sc), n, qa, ql.ctypes.data_as(_i32p), ta, tl.ctypes.data_as(_i32p),
+                                 a.ctypes.data_as(_i32p), b.ctypes.data_as(_i32p), rv.ctypes.data if rv is not None else None,
+                                 out.ctypes.data))
+    return out
+
+
+def joint_grid(sc, left, mid, right, motif1, motif2, reads, point_read, point_k1, point_k2):
+    """nr_joint_grid: read point_read[i] against left + motif1*k1 + mid + motif2*k2 + right for (k1, k2) = point i.
+    -> (records (score, window_score), strand (0 '+', 1 '-')), the better strand of every point."""
+    _rb, ra, rl = _cstrs(reads)
+    pr = np.ascontiguousarray(point_read, dtype=np.int32)
+    k1 = np.ascontiguousarray(point_k1, dtype=np.int32)
+    k2 = np.ascontiguousarray(point_k2, dtype=np.int32)
+    n = len(pr)
+    if len(k1) != n or len(k2) != n:
+        raise ValueError("grid point arrays differ in length")
+    out = np.zeros(n, dtype=WINDOW_DTYPE)
+    strand = np.zeros(n, dtype=np.uint8)
+    lb, mb, rb, m1b, m2b = _b(left), _b(mid), _b(right), _b(motif1), _b(motif2)
+    _check(lib().nr_joint_grid(ctypes.byref(sc), lb, len(lb), mb, len(mb), rb, len(rb), m1b, len(m1b), m2b, len(m2b), len(reads), ra,
+                               rl.ctypes.data_as(_i32p), n, pr.ctypes.data_as(_i32p), k1.ctypes.data_as(_i32p),
+                               k2.ctypes.data_as(_i32p), out.ctypes.data, strand.ctypes.data))
+    return out, strand

@@ -26,6 +26,7 @@
  * the largest start among the paths that reach it.
  */
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -300,4 +301,160 @@ int nro_align_ladders(const nro_scoring_t* sc, int32_t n_reads,
 int nro_max_threads(void) {
     long n = sysconf(_SC_NPROCESSORS_ONLN);
     return n > 0 ? (int)n : 1;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Joint path: alignment score AND the score of the alignment inside a template window, in one DP.
+ *
+ * The reference re-scores the CIGAR of every alignment inside the window [a, b) of the template with
+ * tk.target_region_alignment_stats_from_cigar (src/NanoRepeat/tk.py:435-500): '=' +2, 'X' -4 per base inside the
+ * window; a deletion by the part of it inside the window, -4 - 2 (part - 1); an insertion in full, -4 - 2 (len - 1),
+ * when its template position p satisfies a < p < b - 1.  Which of several optimal alignments minimap2 reports is not
+ * pinned by anything in the reference tree (PARITY UNPINNED, see the top of this file), so the contract names one:
+ * DP values are pairs (score, payload) compared lexicographically, payload = window score collected along the path, i.e.
+ * among all alignments of the best score the one with the HIGHEST window score is the alignment.  A move's payload:
+ *   diagonal into template position p:             +2 / -4 (bases equal / not) if a <= p < b
+ *   deletion step consuming template position p:   -4 if it opens the run or p == a, else -2, if a <= p < b
+ *   insertion step at template position p:         -4 if it opens the run, else -2, if a < p < b - 1
+ * nro_align_window returns (score, payload); nro_align_window_cigar also walks the chosen path back and writes its
+ * CIGAR (=, X, I, D), so that tests can hand it to the reference's own function: payload == its .score.
+ * reverse != 0: the reverse complement of the query is aligned (minimap2 reports '-' strand hits in template
+ * coordinates; the window arithmetic is the same).
+ */
+typedef struct { int32_t score, window_score, tstart, tend; } nro_win_t;
+
+static inline int comp_code(int c) { return c > 3 ? c : 3 - c; }      /* A0 C1 G2 T3 */
+
+typedef struct { int64_t h, e1, e2; } wcol_t;
+
+#define WV(s, p) ((int64_t)(s) * 4294967296LL + (int64_t)(p))
+static inline int64_t wmax(int64_t a, int64_t b) { return a > b ? a : b; }
+
+/* tb != NULL: one byte per cell (row-major, (qlen + 1) x (tlen + 1)):
+ * bits 0-2 source of H (0 fresh start, 1 diagonal, 2 E1, 3 E2, 4 F1, 5 F2), bit 3: E1 extended (else opened),
+ * bit 4: E2 extended, bit 5: F1 extended, bit 6: F2 extended -- for the states LEAVING this cell. */
+static int window_dp(const nro_scoring_t* sc, const uint8_t* qc, int32_t qlen, const uint8_t* tc, int32_t tlen,
+                     int32_t a, int32_t b, uint8_t* tb, nro_win_t* out, int32_t* best_i, int32_t* best_j)
+{
+    const int64_t qe1 = sc->gap_open1 + sc->gap_ext1, qe2 = sc->gap_open2 + sc->gap_ext2;
+    const int64_t x1 = sc->gap_ext1, x2 = sc->gap_ext2;
+    wcol_t* col = (wcol_t*)malloc(sizeof(wcol_t) * (size_t)(qlen + 1));
+    if (!col) return -1;
+    for (int32_t i = 0; i <= qlen; ++i) { col[i].h = 0; col[i].e1 = WV(-qe1, 0); col[i].e2 = WV(-qe2, 0); }
+    int64_t best = 0;
+    *best_i = 0; *best_j = 0;
+    for (int32_t j = 1; j <= tlen; ++j) {
+        const int32_t p = j - 1;                                  /* template position of this column */
+        const int in_diag = p >= a && p < b;
+        const int in_next = p + 1 >= a && p + 1 < b;              /* E leaving this column consumes position p + 1 */
+        const int in_ins = j > a && j < b - 1;                    /* insertions behind this column sit at position j */
+        const int64_t h_open_pay = in_next ? -4 : 0, h_ext_pay = in_next ? (p + 1 == a ? -4 : -2) : 0;
+        const int64_t v_open_pay = in_ins ? -4 : 0, v_ext_pay = in_ins ? -2 : 0;
+        int64_t hdiag = col[0].h;                                 /* H(0, j - 1) = 0 */
+        col[0].h = 0;
+        int64_t f1 = WV(-(1 << 28), 0), f2 = WV(-(1 << 28), 0);   /* nothing above row 1 */
+        for (int32_t i = 1; i <= qlen; ++i) {
+            const int q = qc[i - 1], t = tc[p];
+            int32_t s; int64_t pay = 0;
+            if (q > 3 || t > 3) s = -sc->ambiguous; else s = q == t ? sc->match : -sc->mismatch;
+            if (in_diag) pay = (q == t && q <= 3) ? 2 : -4;
+            int64_t cand[6] = {0, hdiag + WV(s, pay), col[i].e1, col[i].e2, f1, f2};
+            int src = 0; int64_t h = 0;
+            for (int k = 1; k < 6; ++k) if (cand[k] > h) { h = cand[k]; src = k; }
+            hdiag = col[i].h;
+            col[i].h = h;
+            const int64_t oe1 = h + WV(-qe1, h_open_pay), xe1 = col[i].e1 + WV(-x1, h_ext_pay);
+            const int64_t oe2 = h + WV(-qe2, h_open_pay), xe2 = col[i].e2 + WV(-x2, h_ext_pay);
+            const int64_t of1 = h + WV(-qe1, v_open_pay), xf1 = f1 + WV(-x1, v_ext_pay);
+            const int64_t of2 = h + WV(-qe2, v_open_pay), xf2 = f2 + WV(-x2, v_ext_pay);
+            col[i].e1 = wmax(oe1, xe1); col[i].e2 = wmax(oe2, xe2);
+            f1 = wmax(of1, xf1); f2 = wmax(of2, xf2);
+            if (tb) tb[(size_t)i * (size_t)(tlen + 1) + (size_t)j] =
+                (uint8_t)(src | ((xe1 > oe1) << 3) | ((xe2 > oe2) << 4) | ((xf1 > of1) << 5) | ((xf2 > of2) << 6));
+            if (h > best) { best = h; *best_i = i; *best_j = j; }
+        }
+    }
+    free(col);
+    int64_t s = (best + 2147483648LL) >> 32;                      /* payload is a signed 32-bit value around the score field */
+    out->score = (int32_t)s;
+    out->window_score = (int32_t)(best - s * 4294967296LL);
+    out->tstart = 0; out->tend = *best_j;
+    return 0;
+}
+
+static uint8_t* codes_of(const char* s, int32_t n, int reverse) {
+    uint8_t* c = (uint8_t*)malloc((size_t)(n > 0 ? n : 1));
+    if (!c) return NULL;
+    for (int32_t i = 0; i < n; ++i) c[i] = (uint8_t)(reverse ? comp_code(code_of(s[n - 1 - i])) : code_of(s[i]));
+    return c;
+}
+
+int nro_align_window(const nro_scoring_t* sc, const char* query, int32_t qlen, const char* target, int32_t tlen,
+                     int32_t win_a, int32_t win_b, int32_t reverse, nro_win_t* out)
+{
+    out->score = out->window_score = out->tstart = out->tend = 0;
+    if (qlen <= 0 || tlen <= 0) return 0;
+    uint8_t* qc = codes_of(query, qlen, reverse); uint8_t* tc = codes_of(target, tlen, 0);
+    int32_t bi, bj;
+    int rc = (qc && tc) ? window_dp(sc, qc, qlen, tc, tlen, win_a, win_b, NULL, out, &bi, &bj) : -1;
+    free(qc); free(tc);
+    return rc;
+}
+
+/* cigar: caller's buffer of cigar_cap bytes; returns 0, -1 out of memory, -2 buffer too small */
+int nro_align_window_cigar(const nro_scoring_t* sc, const char* query, int32_t qlen, const char* target, int32_t tlen,
+                           int32_t win_a, int32_t win_b, int32_t reverse, nro_win_t* out, char* cigar, int32_t cigar_cap)
+{
+    out->score = out->window_score = out->tstart = out->tend = 0;
+    if (cigar_cap > 0) cigar[0] = 0;
+    if (qlen <= 0 || tlen <= 0) return 0;
+    uint8_t* qc = codes_of(query, qlen, reverse); uint8_t* tc = codes_of(target, tlen, 0);
+    uint8_t* tb = (uint8_t*)calloc((size_t)(qlen + 1) * (size_t)(tlen + 1), 1);
+    int32_t bi = 0, bj = 0;
+    int rc = (qc && tc && tb) ? window_dp(sc, qc, qlen, tc, tlen, win_a, win_b, tb, out, &bi, &bj) : -1;
+    if (rc == 0 && out->score > 0) {
+        /* walk back from the best cell; ops are collected last-to-first */
+        size_t cap = (size_t)qlen + (size_t)tlen + 2, n = 0;
+        char* ops = (char*)malloc(cap);
+        if (!ops) rc = -1;
+        int32_t i = bi, j = bj;
+        int state = 0;                   /* 0: in H, 2/3: in E1/E2 (arrived at (i, j) by a deletion), 4/5: in F1/F2 */
+        while (rc == 0) {
+            const uint8_t c = tb[(size_t)i * (size_t)(tlen + 1) + (size_t)j];
+            if (state == 0) {
+                const int src = c & 7;
+                if (src == 0) break;                                          /* fresh start: the alignment begins here */
+                if (src == 1) { ops[n++] = (qc[i - 1] == tc[j - 1] && qc[i - 1] <= 3) ? '=' : 'X'; --i; --j; }
+                else state = src;                                             /* H(i, j) was taken from a gap state */
+            } else if (state == 2 || state == 3) {
+                /* E(i, j) came from cell (i, j - 1): opened from its H or extended from its E */
+                ops[n++] = 'D'; --j;
+                const uint8_t pc = tb[(size_t)i * (size_t)(tlen + 1) + (size_t)j];
+                if (j <= 0 || !((pc >> (state == 2 ? 3 : 4)) & 1)) state = 0;
+            } else {
+                /* F(i, j) came from cell (i - 1, j) */
+                ops[n++] = 'I'; --i;
+                const uint8_t pc = tb[(size_t)i * (size_t)(tlen + 1) + (size_t)j];
+                if (i <= 0 || !((pc >> (state == 4 ? 5 : 6)) & 1)) state = 0;
+            }
+            if (n + 1 >= cap) { rc = -1; break; }
+            if (i <= 0 || j <= 0) break;
+        }
+        if (rc == 0) {
+            out->tstart = j;
+            /* run-length encode, first-to-last */
+            int32_t w = 0;
+            for (size_t k = n; k > 0;) {
+                const char op = ops[k - 1];
+                size_t run = 0;
+                while (k > 0 && ops[k - 1] == op) { ++run; --k; }
+                int len = snprintf(cigar + w, (size_t)(cigar_cap - w), "%zu%c", run, op);
+                if (len < 0 || len >= cigar_cap - w) { rc = -2; break; }
+                w += len;
+            }
+        }
+        free(ops);
+    }
+    free(qc); free(tc); free(tb);
+    return rc;
 }

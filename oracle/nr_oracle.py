@@ -52,6 +52,9 @@ def lib():
                                         ctypes.c_char_p, ctypes.c_int32, i32p, i32p,
                                         ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p, ctypes.c_int32]
         L.nro_max_threads.restype = ctypes.c_int
+        L.nro_align_window.argtypes = [ctypes.POINTER(Scoring), ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32,
+                                       ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
+        L.nro_align_window_cigar.argtypes = L.nro_align_window.argtypes + [ctypes.c_char_p, ctypes.c_int32]
         _lib = L
     return _lib
 
@@ -122,6 +125,29 @@ def align_ladders(cores, left, right, motif, kmin, kmax, sc=None, n_threads=1):
     if rc != 0:
         raise MemoryError("nro_align_ladders failed")
     return out, off
+
+
+WIN_DTYPE = np.dtype([("score", "<i4"), ("window_score", "<i4"), ("tstart", "<i4"), ("tend", "<i4")])
+
+
+def align_window(query, target, win_a, win_b, reverse=False, sc=None, want_cigar=False):
+    """Joint path (nr_oracle.c, nro_align_window): -> (score, window_score[, tstart, tend, cigar]) of the canonical optimal
+    local alignment of query (its reverse complement when reverse) against target, window [win_a, win_b)."""
+    sc = sc or scoring()
+    out = np.zeros(1, dtype=WIN_DTYPE)
+    q = query.encode() if isinstance(query, str) else query
+    t = target.encode() if isinstance(target, str) else target
+    if not want_cigar:
+        rc = lib().nro_align_window(ctypes.byref(sc), q, len(q), t, len(t), int(win_a), int(win_b), int(bool(reverse)), out.ctypes.data)
+        if rc != 0:
+            raise MemoryError("nro_align_window failed")
+        return int(out["score"][0]), int(out["window_score"][0])
+    buf = ctypes.create_string_buffer(8 * (len(q) + len(t)) + 64)
+    rc = lib().nro_align_window_cigar(ctypes.byref(sc), q, len(q), t, len(t), int(win_a), int(win_b), int(bool(reverse)),
+                                      out.ctypes.data, buf, len(buf))
+    if rc != 0:
+        raise MemoryError(f"nro_align_window_cigar failed ({rc})")
+    return int(out["score"][0]), int(out["window_score"][0]), int(out["tstart"][0]), int(out["tend"][0]), buf.value.decode()
 
 
 def max_threads():

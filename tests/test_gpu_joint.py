@@ -1,0 +1,114 @@
+"""GPU parity of the joint path: nr_window_tasks / nr_joint_grid against the CPU oracle and the
+golden vectors whose window scores the reference's own CIGAR re-scoring confirmed (tests/golden/make_golden_window.py)."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+COMP = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+
+
+def _rs(rng, n):
+    return "".join(rng.choice("ACGT") for _ in range(n))
+
+
+def _mut(rng, s, rate):
+    out = []
+    for ch in s:
+        u = rng.random()
+        if u < rate / 3:
+            continue
+        if u < 2 * rate / 3:
+            out.append(rng.choice("ACGT")); continue
+        if u < rate:
+            out.append(rng.choice("ACGT"))
+        out.append(ch)
+    return "".join(out)
+
+
+def _revcomp(s):
+    return "".join(COMP[c] for c in reversed(s))
+
+
+def test_window_tasks_equal_golden_vectors(engine):
+    with open(os.path.join(GOLDEN, "joint_dp_cases.json")) as f:
+        cases = json.load(f)["cases"]
+    sc = engine.get_preset("ont")
+    got = engine.window_tasks([c["query"] for c in cases], [c["target"] for c in cases], [c["win_a"] for c in cases],
+                              [c["win_b"] for c in cases], sc, reverse=[c["reverse"] for c in cases])
+    bad = [i for i, c in enumerate(cases) if (int(got["score"][i]), int(got["window_score"][i])) != (c["score"], c["window_score"])]
+    assert not bad, (len(bad), bad[:5], [tuple(got[i]) for i in bad[:5]], [(cases[i]["score"], cases[i]["window_score"]) for i in bad[:5]])
+
+
+def test_window_tasks_equal_oracle_long_reads_both_strands(engine, oracle):
+    """Reads of many stripes (the joint CLI aligns whole amplicon reads, not cores), both strands, windows anywhere."""
+    rng = random.Random(31)
+    sc = engine.get_preset("ont")
+    qs, ts, aa, bb, rv = [], [], [], [], []
+    for it in range(60):
+        L, R = _rs(rng, rng.choice([200, 1000])), _rs(rng, rng.choice([200, 1000]))
+        m1, m2, mid = _rs(rng, 3), _rs(rng, 3), _rs(rng, 12)
+        k1, k2 = rng.randint(0, 60), rng.randint(0, 20)
+        tpl = L + m1 * k1 + mid + m2 * k2 + R
+        read = _mut(rng, _rs(rng, rng.randint(0, 1500)) + L + m1 * (k1 + rng.randint(-3, 3) if k1 > 3 else k1) + mid + m2 * k2 + R +
+                    _rs(rng, rng.randint(0, 1500)), rng.choice([0.02, 0.1]))
+        reverse = it % 2
+        qs.append(_revcomp(read) if reverse else read); ts.append(tpl); rv.append(reverse)
+        a = max(len(L) - 10, 0); b = min(len(L) + 3 * k1 + 12 + 3 * k2 + 10, len(tpl))
+        if it % 5 == 0:
+            a, b = rng.randint(0, 100), rng.randint(len(tpl) - 100, len(tpl))
+        aa.append(a); bb.append(b)
+    got = engine.window_tasks(qs, ts, aa, bb, sc, reverse=rv)
+    for i in range(len(qs)):
+        exp = oracle.align_window(qs[i], ts[i], aa[i], bb[i], reverse=rv[i])
+        assert (int(got["score"][i]), int(got["window_score"][i])) == exp, (i, tuple(got[i]), exp)
+    # degenerate inputs
+    z = engine.window_tasks(["", "ACGT"], ["ACGT", ""], [0, 0], [4, 0], sc)
+    assert [tuple(int(v) for v in r) for r in z] == [(0, 0), (0, 0)]
+
+
+def test_quantify_two_repeats_equals_oracle_driven_run(engine, oracle):
+    """nanoRepeat-joint's rounds 2 and 3 for an HTT-like locus (CAG / CCG, README.md:167) through nr_joint_grid ==
+    the same host logic fed by the CPU oracle, read by read; and the estimates land on the simulated alleles."""
+    from nanorepeat_b200 import joint
+    rng = random.Random(5)
+    left, right, mid = _rs(rng, 1000), _rs(rng, 1000), "CAACAGCCGCCA"
+    reads, truth, range1, range2 = [], [], [], []
+    for i in range(24):
+        k1, k2 = rng.choice([17, 55]), rng.choice([7, 10])
+        amp = left[-rng.randint(150, 400):] + "CAG" * k1 + mid + "CCG" * k2 + right[:rng.randint(150, 400)]
+        read = _mut(rng, amp, 0.05)
+        reads.append(_revcomp(read) if i % 3 == 0 else read)
+        truth.append((k1, k2))
+        range1.append((max(0, k1 - rng.randint(8, 20)), k1 + rng.randint(8, 20)))        # what the initial estimate would give
+        range2.append((max(0, k2 - rng.randint(4, 7)), k2 + rng.randint(4, 9)))
+    range1[5] = None                                                                       # a read the initial estimate dropped
+
+    def oracle_grid(sc, left, mid, right, motif1, motif2, reads_, pr, p1, p2):
+        rec = np.zeros(len(pr), dtype=engine.WINDOW_DTYPE)
+        strand = np.zeros(len(pr), dtype=np.uint8)
+        for i, (r, k1, k2) in enumerate(zip(pr, p1, p2)):
+            tpl = left + motif1 * k1 + mid + motif2 * k2 + right
+            a, b = max(len(left) - 10, 0), min(len(left) + len(motif1) * k1 + len(mid) + len(motif2) * k2 + 10, len(tpl))
+            f = oracle.align_window(reads_[r], tpl, a, b, reverse=False)
+            v = oracle.align_window(reads_[r], tpl, a, b, reverse=True)
+            best, strand[i] = (v, 1) if v > f else (f, 0)
+            rec[i] = best
+        return rec, strand
+
+    got = joint.quantify_two_repeats(reads, left, mid, right, "CAG", "CCG", range1, range2, 200, 50)
+    exp = joint.quantify_two_repeats(reads, left, mid, right, "CAG", "CCG", range1, range2, 200, 50, align=oracle_grid)
+    assert got["step1"] == exp["step1"] and got["step2"] == exp["step2"]
+    for i in range(len(reads)):
+        assert (got["size1"][i] is None) == (exp["size1"][i] is None)
+        if got["size1"][i] is not None:
+            assert float(got["size1"][i]) == float(exp["size1"][i]) and float(got["size2"][i]) == float(exp["size2"][i]), i
+    assert got["size1"][5] is None
+    close = sum(abs(float(got["size1"][i]) - truth[i][0]) <= 2 and abs(float(got["size2"][i]) - truth[i][1]) <= 2
+                for i in range(len(reads)) if got["size1"][i] is not None)
+    assert close >= 18

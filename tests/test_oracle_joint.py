@@ -46,3 +46,20 @@ def test_two_repeat_selection_equals_reference():
             recs.append((col[0], k1, k2, int(col[6]), int(col[7]), int(col[8]), cigar))
         got = joint.two_repeat_sizes(recs, c["left_len"], c["mid_len"], c["m1"], c["m2"])
         assert {q: list(v) for q, v in got.items()} == c["expected"]
+
+
+def test_window_dp_equals_golden_and_the_reference_rescoring_of_its_own_cigar():
+    """oracle/nr_oracle.c nro_align_window (score, window score carried through the DP) on the committed cases: equal to
+    the recorded values, equal with and without the traceback, and the recorded CIGAR re-scored by the restatement of
+    tk.target_region_alignment_stats_from_cigar (itself pinned above against the reference) gives the window score.
+    (At generation time the reference's own function was run on the same CIGARs: tests/golden/make_golden_window.py.)"""
+    from oracle import nr_oracle
+    nr_oracle.build()
+    doc = _load("joint_dp_cases.json")
+    assert len(doc["cases"]) >= 150
+    for c in doc["cases"]:
+        got = nr_oracle.align_window(c["query"], c["target"], c["win_a"], c["win_b"], reverse=c["reverse"], want_cigar=True)
+        assert got == (c["score"], c["window_score"], c["tstart"], c["tend"], c["cigar"])
+        assert nr_oracle.align_window(c["query"], c["target"], c["win_a"], c["win_b"], reverse=c["reverse"]) == (c["score"], c["window_score"])
+        if c["score"] > 0:
+            assert joint.window_stats(c["cigar"], c["tstart"], c["tend"], c["win_a"], c["win_b"])["score"] == c["window_score"]
