@@ -374,6 +374,9 @@ namespace {
 // shared memory per warp, in int4: query profile (+ backward junction vectors for the ladder kernel)
 int exact_smem_int4(int R) { return 4 * ((R + 3) / 4) * 32; }
 int ladder_smem_int4(int R) { return exact_smem_int4(R) + R * 32; }
+// paired ladder: the junction vectors are three 4-byte planes (nr_pair_kernels.cuh); the fused launch's 32-bit entries
+// (at most kMaxRLadder rows per lane) need the int4 layout
+int pair_ladder_smem_int4(int pair_R, int rest_R) { return std::max(exact_smem_int4(pair_R) + 3 * pair_R * 8, rest_R ? ladder_smem_int4(rest_R) : 0); }
 
 int check_scoring(const nr_scoring_t* sc) {
     if (!sc) return fail(NR_ERR_ARG, "scoring is NULL");
@@ -809,9 +812,12 @@ int launch_rest(nr_batch* b, cudaStream_t st, const nr::ScoreW& k, const int32_t
     if (L.ladder) {
         if (!L.fixed) return fail(NR_ERR_ARG, "the ladder kernels are built for map-ont scoring only");
         const int stride = ladder_smem_int4(R);
-        const size_t smem = (size_t)kWarpsPerBlock * stride * sizeof(int4);
+        // single stripes of more than 384 rows (the paired kernel's redo reads) need 16 KB per warp: fewer warps per block
+        int wpb = kWarpsPerBlock;
+        while (wpb > 4 && (size_t)wpb * stride * sizeof(int4) > nrl::kMaxDynShared) wpb -= 4;
+        const size_t smem = (size_t)wpb * stride * sizeof(int4);
         if (smem > nrl::kMaxDynShared) return fail(NR_ERR_ARG, "launch needs %zu bytes of shared memory", smem);
-        CUDA_TRY(nrl::launch_ladder(b->flag, blocks, kWarpsPerBlock * 32, smem, st, b->d_ltasks, ra, count_dev,
+        CUDA_TRY(nrl::launch_ladder(b->flag, blocks, wpb * 32, smem, st, b->d_ltasks, ra, count_dev,
                                     b->qsrc ? b->qsrc->d_pool : b->d_pool, b->d_pool, b->d_lregs, k, counter, stride, b->d_out, b->d_sel));
     } else {
         const int stride = exact_smem_int4(R);
@@ -866,7 +872,7 @@ int run_batch(nr_batch* b, cudaStream_t st) {
             CUDA_TRY(nrl::launch_pair_round2(blocks, wpb * 32, smem, st, static_cast<const nr::pr::Pair2*>(b->d_pairs), deal, b->d_tasks,
                                              ra, b->d_pool, k, b->d_counters, stride, b->d_out, b->d_state));
         } else {
-            const int stride = ladder_smem_int4(std::max(L.pair_R, L.R));
+            const int stride = pair_ladder_smem_int4(L.pair_R, L.R);
             const size_t smem = (size_t)wpb * stride * sizeof(int4);
             if (smem > nrl::kMaxDynShared) return fail(NR_ERR_ARG, "launch needs %zu bytes of shared memory", smem);
             CUDA_TRY(nrl::launch_pair_ladder(blocks, wpb * 32, smem, st, static_cast<const nr::pr::Pair3*>(b->d_pairs), deal, b->d_ltasks,

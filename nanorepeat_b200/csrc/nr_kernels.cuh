@@ -695,6 +695,9 @@ __host__ __device__ constexpr int coop_height_at_least(int R) { return R <= 4 ? 
 constexpr int kMinR = 4;
 constexpr int kMaxRExact = 16;    // single-stripe tasks up to 512 rows
 constexpr int kMaxRLadder = 12;   // 384 rows: profile + junction vectors stay within 12 KB of shared memory per warp
+// ladder_kernel launched on its own (the paired kernel's redo list, mode 2 / 1 batches) also takes single-stripe reads of
+// up to 512 rows -- the reads the paired kernels now pair -- at 16 KB per warp, i.e. with fewer warps per block
+constexpr int kMaxRLadderOwn = 16;
 
 // Stripe height for a query: single stripe when it fits max_r rows per lane, else the fewest equal stripes.
 __host__ __device__ __forceinline__ void stripe_shape(int q_len, int max_r, int& R, int& n_stripes) {
@@ -1062,11 +1065,11 @@ __device__ __forceinline__ void ladder_fwd_stripe(const LadderTask& tk, const La
     if (s == S - 1) finish_read<FLAG>(sw, tk, cx, lane, out, sel, sw.r_score, sw.r_end, sw.r_start, sw.rcand);
 }
 
-template <int R, bool FLAG, class SC>
+template <int R, bool FLAG, int MAXR, class SC>
 __device__ __forceinline__ void ladder_dispatch(int r, const LadderTask& tk, const LadderCtx& cx, const SC& sc, int4* prof,
                                                 int lane, int4* out, int4* sel) {
     if (r == R) { ladder_task<R, FLAG>(tk, cx, sc, prof, lane, out, sel); return; }
-    if constexpr (R < kMaxRLadder) ladder_dispatch<R + 1, FLAG>(r, tk, cx, sc, prof, lane, out, sel);
+    if constexpr (R < MAXR) ladder_dispatch<R + 1, FLAG, MAXR>(r, tk, cx, sc, prof, lane, out, sel);
 }
 
 template <int R, bool FLAG, class SC>
@@ -1082,7 +1085,9 @@ __device__ __forceinline__ void ladder_stripe_dispatch(int r, const LadderTask& 
     if constexpr (R < kMaxRLadder) ladder_stripe_dispatch<R + 1, FLAG>(r, tk, cx, code, ci, ra, sc, prof, lane, out, sel);
 }
 
-template <bool FLAG, class SC>
+// MAXR: tallest single stripe of a code-0 entry (the host cuts longer reads into cooperative stripes, except for the
+// redo list of the paired kernel, whose reads of up to 512 rows run as one stripe)
+template <bool FLAG, int MAXR, class SC>
 __device__ __forceinline__ void ladder_entry(int e, const LadderTask* __restrict__ tasks, const uint32_t* __restrict__ qpool,
                                              const uint32_t* __restrict__ pool, const LadderRegion* __restrict__ regs, const SC& sc,
                                              const RestArgs& ra, int4* prof, int lane, int4* out, int4* sel) {
@@ -1095,8 +1100,8 @@ __device__ __forceinline__ void ladder_entry(int e, const LadderTask* __restrict
     cx.q_len = tk.q_len;
     if (code == 0) {
         int R, n_stripes;
-        stripe_shape(tk.q_len, kMaxRLadder, R, n_stripes);
-        ladder_dispatch<kMinR, FLAG>(R, tk, cx, sc, prof, lane, out, sel);
+        stripe_shape(tk.q_len, MAXR, R, n_stripes);
+        ladder_dispatch<kMinR, FLAG, MAXR>(R, tk, cx, sc, prof, lane, out, sel);
     } else {
         const CoopInfo ci = ra.coop[tk.pad];
         ladder_stripe_dispatch<kMinR, FLAG>(ci.rows, tk, cx, code, ci, ra, sc, prof, lane, out, sel);
@@ -1119,7 +1124,7 @@ ladder_kernel(const LadderTask* __restrict__ tasks, RestArgs ra, const int* __re
     for (;;) {
         const int oi = cur.next();
         if (oi < 0) break;
-        ladder_entry<FLAG>(ra.order[oi], tasks, qpool, pool, regs, sc, ra, prof, lane, out, sel);
+        ladder_entry<FLAG, kMaxRLadderOwn>(ra.order[oi], tasks, qpool, pool, regs, sc, ra, prof, lane, out, sel);
     }
 }
 

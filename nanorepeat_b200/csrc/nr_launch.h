@@ -9,7 +9,7 @@
 
 namespace nrl {
 
-constexpr size_t kMaxDynShared = (size_t)nr::kWarpsPerBlock * 12 * 1024;   // 16 warps x (profile + junction vectors at R = 12)
+constexpr size_t kMaxDynShared = (size_t)nr::kWarpsPerBlock * 14 * 1024;   // 16 warps x 14 KB (paired ladder at R = 16): 224 of 227 KB
 
 cudaError_t launch_exact(bool fixed, int blocks, int threads, size_t smem, cudaStream_t st, const nr::Task* tasks,
                          const nr::RestArgs& ra, const uint32_t* pool, const nr::ScoreW& k, int* counter, int stride, int4* out);

@@ -128,9 +128,8 @@ struct Sweep {
     const uint32_t* twords;
     int t_len, lane;
     int mark_col;
-    uint4* bvec;                   // kPB
     int q_a, q_b;
-    const uint4* bsm;              // kPF
+    const u32* bsm;                // kPF: junction vectors, three planes [state][row][lane] of two-half words
     uint2* rung_out;
     int jnext, m, kcnt, zone_start; // zone_start: in steps of this sweep
     int col0;                      // first column of the sweep (kPF resuming from a kept state: |left| - 1; else 0)
@@ -217,8 +216,8 @@ struct Sweep {
                     cell<FLOOR>(hd, s4[u], one, h, E1[r], E2[r], f1, f2);
                     if (KEEP_E) { E1[r] = keep ? e1pre : E1[r]; E2[r] = keep ? e2pre : E2[r]; }
                     if (JUNC) {
-                        const uint4 b = bsm[r * 32 + lane];
-                        const u32 t = __vimax3_u16x2(pmadd(h, one, b.x), pmadd(e1pre, one, b.y), pmadd(e2pre, one, b.z));
+                        const u32 bx = bsm[(0 * R + r) * 32 + lane], by = bsm[(1 * R + r) * 32 + lane], bz = bsm[(2 * R + r) * 32 + lane];
+                        const u32 t = __vimax3_u16x2(pmadd(h, one, bx), pmadd(e1pre, one, by), pmadd(e2pre, one, bz));
                         if (r & 1) jhi = __vimax3_u16x2(jhi, jprev, t);
                         else if (r == R - 1) jhi = __vmaxu2(jhi, t);
                         jprev = t;
@@ -250,7 +249,7 @@ struct Sweep {
     // rows -- forward row i of read A is reversed row q_a - 2 - i (read B: q_b - 2 - i; the halves move apart) -- and
     // writes them in the forward layout the junction columns read.  Rows the sweep has no value for: the right part is
     // empty (score 0, no gap state) for the last row of a read, void below it.
-    __device__ __forceinline__ void store_junction_vectors(u32* stage, uint4* bvec_fwd) {
+    __device__ __forceinline__ void store_junction_vectors(u32* stage, u32* bvec_fwd) {
         __syncwarp();
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -263,15 +262,13 @@ struct Sweep {
         for (int r = 0; r < R; ++r) {
             const int idx0 = lane * R + r;
             const int ia = q_a - 2 - idx0, ib = q_b - 2 - idx0;
-            u32 v[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const u32 da = c == 0 ? (idx0 < q_a ? (u32)kBias : 0u) : 0u, db = c == 0 ? (idx0 < q_b ? (u32)kBias : 0u) : 0u;
                 const u32 a = ia >= 0 ? stage[(c * R + ia % R) * 32 + ia / R] >> 16 : da;
                 const u32 b = ib >= 0 ? stage[(c * R + ib % R) * 32 + ib / R] & 0xffffu : db;
-                v[c] = (a << 16) | b;
+                bvec_fwd[(c * R + r) * 32 + lane] = (a << 16) | b;
             }
-            bvec_fwd[r * 32 + lane] = make_uint4(v[0], v[1], v[2], 0u);
         }
     }
 
@@ -407,7 +404,9 @@ struct Sweep {
     }
 };
 
-constexpr int kMaxRPair3 = 12;    // round 3: 384 bases (profile + junction vectors: 12 KB of shared memory per warp)
+// round 3: 512 bases.  Shared memory per warp: the profile (2 KB per four rows) + the junction vectors as three 4-byte
+// planes (384 bytes per row): 14 KB at R = 16, 224 KB for the 16 warps of a block
+constexpr int kMaxRPair3 = 16;
 constexpr int kMaxRPair2 = kMaxRPair3;   // round 2 pairs the same reads, so that round 3 can resume from its state
 
 __host__ __device__ __forceinline__ int pair_rows(int q_len) {
@@ -573,7 +572,7 @@ __device__ __forceinline__ void pair3_task(const Pair3& pt, const LadderTask* __
     const LadderRegion reg = regs[tv.region];
     const int kmin = (ha && hb) ? min(ta.kmin, tb.kmin) : tv.kmin;
     const int kmax = (ha && hb) ? max(ta.kmax, tb.kmax) : tv.kmax;
-    uint4* bsm = prof + StripeCfg<R>::PROF_INT4;
+    u32* bsm = reinterpret_cast<u32*>(prof + StripeCfg<R>::PROF_INT4);
     uint2* rungs = prung + pt.rung_off;
     __syncwarp();
     build_profile<R>(prof, qpool + ta.q_word, q_a, qpool + tb.q_word, q_b, lane * R, lane, true);
@@ -582,7 +581,7 @@ __device__ __forceinline__ void pair3_task(const Pair3& pt, const LadderTask* __
     {
         Sweep<R, kPB> sw;
         sw.prof = prof; sw.twords = pool + reg.rev_word; sw.t_len = reg.n_right; sw.lane = lane;
-        sw.mark_col = -1; sw.bvec = bsm; sw.q_a = q_a; sw.q_b = q_b;
+        sw.mark_col = -1; sw.q_a = q_a; sw.q_b = q_b;
         sw.col0 = 0; sw.resume = nullptr; sw.save = nullptr; sw.save_col = -1;
         sw.run(one, four, 0);
         const u32 ra = __reduce_max_sync(kFull, sw.best >> 16), rb = __reduce_max_sync(kFull, sw.best & 0xffffu);
@@ -671,7 +670,7 @@ pair_ladder_kernel(const Pair3* __restrict__ pairs, Deal dl, const LadderTask* _
         const int i = next_item(dl, first, counter);
         if (i < 0) break;
         if (i < ra.n_order) {
-            ladder_entry<true>(ra.order[i], tasks, qpool, pool, regs, sc, ra, reinterpret_cast<int4*>(prof), lane, out, sel);
+            ladder_entry<true, kMaxRLadder>(ra.order[i], tasks, qpool, pool, regs, sc, ra, reinterpret_cast<int4*>(prof), lane, out, sel);
             continue;
         }
         const Pair3 pt = pairs[i - ra.n_order];

@@ -402,10 +402,22 @@ def estimate_regions(regions, data_type=None, fast_mode=False):
     return regions
 
 
-def install(nanoRepeat_bam_module):
+def install(nanoRepeat_bam_module, anchoring=False):
     """Patch the reference module in place so the unmodified CLI runs this path:
         import NanoRepeat.nanoRepeat_bam as m; nanorepeat_b200.install(m)
+    anchoring=True also replaces Step 1 (find_anchor_locations_in_reads, make_core_seq_fastq; nanoRepeat_bam.py:260-331)
+    by the GPU version -- opt-in, because minimap2's secondary-hit / mapq heuristics are replaced by a stated rule there
+    (nanorepeat_b200/anchoring.py).
     """
     nanoRepeat_bam_module.round1_and_round2_estimation = round1_and_round2_estimation
     nanoRepeat_bam_module.round3_estimation = round3_estimation
+    if anchoring:
+        from . import anchoring as _anchoring
+        read_class = getattr(nanoRepeat_bam_module, "Read", None)
+
+        def find_anchor_locations_in_reads(data_type, repeat_region, num_cpu):
+            return _anchoring.find_anchor_locations_in_reads(data_type, repeat_region, num_cpu, read_class=read_class)
+
+        nanoRepeat_bam_module.find_anchor_locations_in_reads = find_anchor_locations_in_reads
+        nanoRepeat_bam_module.make_core_seq_fastq = _anchoring.make_core_seq_fastq
     return nanoRepeat_bam_module

@@ -6,6 +6,7 @@ passed to nanorepeat_b200.round1_and_round2_estimation / round3_estimation uncha
 class Read:
     def __init__(self, read_name=None, dist_between_anchors=None):
         self.read_name = read_name
+        self.strand = None
         self.dist_between_anchors = dist_between_anchors
         self.round1_repeat_size = None
         self.round2_repeat_size = None

@@ -200,3 +200,33 @@ def algorithmic_cells(n_left, n_right, m, core_len, T, kmin, kmax):
     r2 = core_len * (n_left + m * T)
     r3 = core_len * (n * (n_left + n_right) + m * (kmin + kmax) * n // 2) if n > 0 else 0
     return r2, r3
+
+
+def region_reads(seed=6, n_reads=40, motif="CAG", alleles=(17, 55), profile="ont", flank=1000, outer=2000):
+    """What Step 1 of the reference starts from (nanoRepeat_bam.py:577-600): the raw reads overlapping one region, in
+    either orientation, some of them ending inside an anchor.  -> (SynthRegion without cores, names, sequences, truth):
+    truth[name] = (allele, strand) for reads that contain both anchors in full, None for truncated ones."""
+    rng = np.random.default_rng(seed)
+    sub, ins, dele, _ = ERROR_PROFILES[profile]
+    up, down = random_seq(rng, outer), random_seq(rng, outer)
+    reg = SynthRegion(f"reads_{motif}", random_seq(rng, flank), random_seq(rng, flank), motif, "ont")
+    comp = str.maketrans("ACGT", "TGCA")
+    names, seqs, truth = [], [], {}
+    for i in range(n_reads):
+        k = int(alleles[int(rng.integers(0, len(alleles)))])
+        genome = up + reg.left_anchor_seq + motif * k + reg.right_anchor_seq + down
+        lo = int(rng.integers(0, outer))
+        hi = len(genome) - int(rng.integers(0, outer))
+        full = True
+        if i % 7 == 3:                                   # starts inside the left anchor: no left hit worth the name
+            lo = outer + flank - int(rng.integers(5, 30)); full = False
+        if i % 11 == 5:                                  # ends in the repeat: no right anchor at all
+            hi = outer + flank + len(motif) * k // 2; full = False
+        read = mutate(rng, genome[lo:hi], sub, ins, dele)
+        strand = "+" if rng.random() < 0.5 else "-"
+        if strand == "-":
+            read = read.translate(comp)[::-1]
+        name = f"raw{i}"
+        names.append(name); seqs.append(read)
+        truth[name] = (k, strand) if full else None
+    return reg, names, seqs, truth
