@@ -68,7 +68,7 @@ def estimate_regions_sharded(regions, data_type=None, fast_mode=False, max_reads
 
     Every rank passes the same `regions` list (same order).  Rank r computes the pieces dealt to it on its own GPU
     (estimate_fn defaults to nanorepeat_b200.estimate_regions), then -- gather=True -- the per-read results are
-    exchanged on the host (all_gather_object: 3 numbers per read, no NCCL data path) and written into every rank's
+    exchanged on the host (all_gather_object of three float arrays per rank, no NCCL data path) and written into every rank's
     Read objects.  Returns the list of piece indices this rank computed."""
     import torch.distributed as dist
     if estimate_fn is None:
@@ -88,21 +88,26 @@ def estimate_regions_sharded(regions, data_type=None, fast_mode=False, max_reads
     mine = parts[rank]
     estimate_fn([pieces[i] for i in mine], data_type, fast_mode)
     if gather and world_size > 1:
-        payload = []
-        for i in mine:
-            rd = pieces[i].read_dict
-            payload.append((i, [(n, r.round1_repeat_size, r.round2_repeat_size,
-                                 None if r.round3_repeat_size is None else float(r.round3_repeat_size),
-                                 isinstance(r.round3_repeat_size, np.floating)) for n, r in rd.items()]))
+        # host-side gather: every rank holds the same pieces in the same order, so three float arrays (NaN = None) and a
+        # flag array per rank say everything -- no names, no per-read Python objects on the wire
+        reads = [rd for i in mine for rd in pieces[i].read_dict.values()]
+        nan = float("nan")
+        r1 = np.fromiter((nan if r.round1_repeat_size is None else r.round1_repeat_size for r in reads), np.float64, len(reads))
+        r2 = np.fromiter((nan if r.round2_repeat_size is None else r.round2_repeat_size for r in reads), np.float64, len(reads))
+        r3 = np.fromiter((nan if r.round3_repeat_size is None else r.round3_repeat_size for r in reads), np.float64, len(reads))
+        is_np = np.fromiter((isinstance(r.round3_repeat_size, np.floating) for r in reads), np.bool_, len(reads))
         gathered = [None] * world_size
-        dist.all_gather_object(gathered, payload)
-        for src, chunk in enumerate(gathered):
+        dist.all_gather_object(gathered, (mine, r1, r2, r3, is_np))
+        for src, (theirs, g1, g2, g3, gnp) in enumerate(gathered):
             if src == rank:
                 continue
-            for i, rows in chunk:
-                rd = pieces[i].read_dict
-                for n, r1, r2, r3, is_np in rows:
-                    read = rd[n]
-                    read.round1_repeat_size, read.round2_repeat_size = r1, r2
-                    read.round3_repeat_size = np.float64(r3) if (is_np and r3 is not None) else r3
+            v1, v2, v3, fl = g1.tolist(), g2.tolist(), g3.tolist(), gnp.tolist()
+            pos = 0
+            for i in theirs:
+                for read in pieces[i].read_dict.values():
+                    a, b, c = v1[pos], v2[pos], v3[pos]
+                    read.round1_repeat_size = None if a != a else a
+                    read.round2_repeat_size = None if b != b else b
+                    read.round3_repeat_size = None if c != c else (np.float64(c) if fl[pos] else c)
+                    pos += 1
     return mine
