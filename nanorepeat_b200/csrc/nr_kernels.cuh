@@ -473,9 +473,11 @@ struct Sweep {
     // Otherwise the guarded body; forward sweeps from zone_start on: some lane may be at a junction column, tokens
     // are moving.  A step in which any lane is at a junction evaluates the junction candidates on every lane (one
     // code path for the warp; the lanes that are not at a junction drop theirs).
-    template <bool FAST, class MS, class SC>
+    // ZONE (guarded body of forward sweeps): the caller knows on which side of zone_start the step lies, so each of the
+    // two guarded loops holds one copy of the cell code (with or without the junction candidates), not both.
+    template <bool FAST, bool ZONE, class MS, class SC>
     __device__ __forceinline__ void step(int st, const MS& ms, const SC& sc) {
-        const bool zone = !FAST && kIsFwd && st >= zone_start;     // uniform
+        constexpr bool zone = !FAST && kIsFwd && ZONE;
         constexpr int CH = StripeCfg<R>::CH;
         int hup = __shfl_up_sync(kFull, h_out, 1);
         int f1 = __shfl_up_sync(kFull, f1_out, 1);
@@ -519,7 +521,6 @@ struct Sweep {
         }
         const unsigned tb = next_base(sc.four);  // unconditional: the window advances one column per step
         const int jj = st - lane;           // 0-based target column of this lane
-        const bool anyj = zone && __any_sync(kFull, jj + 1 == jnext && jj < t_len);
         if (FAST || (jj >= 0 && jj < t_len)) {
             const int4* pp = reinterpret_cast<const int4*>(prof_lane + tb * (unsigned)(CH * 512));
             const int hd = hup_prev;
@@ -541,8 +542,9 @@ struct Sweep {
             int cm, jhi = kJuncNone, jlo = 0;
             const bool junc = zone && (jj + 1 == jnext);
             const int cm0 = MODE == kFwdF ? best : 0;      // flag ladder: only the running maximum matters
-            if (zone && anyj) cm = cells<true>(pp, hd, mul0, cm0, f1, f2, ms, sc, jhi, jlo);
-            else cm = cells<false>(pp, hd, mul0, cm0, f1, f2, ms, sc, jhi, jlo);
+            // in the zone the junction candidates are evaluated on every step (with 32 lanes a motif apart or less some
+            // lane is at a junction column on almost every one)
+            cm = cells<zone>(pp, hd, mul0, cm0, f1, f2, ms, sc, jhi, jlo);
             h_out = H[R - 1]; f1_out = f1; f2_out = f2;
             if (kIsBwd) {
                 // R-only ordering in forward coordinates: score desc, end asc (= reversed start desc), start desc
@@ -640,22 +642,35 @@ struct Sweep {
 
     template <class MS, class SC>
     __device__ __forceinline__ void slow_until(int& st, int end, const MS& ms, const SC& sc) {
+        const int pre = kIsFwd ? min(end, zone_start) : end;      // guarded steps before any lane can be at a junction
 #pragma unroll 1
-        for (; st < end; ++st) {
-            if (MULTI && kIsFwd && late_pending && st >= zone_start) late_load();
+        for (; st < pre; ++st) {
             if ((st & 15) == 0) refill();
-            step<false>(st, ms, sc);
+            step<false, false>(st, ms, sc);
+        }
+        if (kIsFwd) {
+#pragma unroll 1
+            for (; st < end; ++st) {
+                if (MULTI && late_pending) late_load();
+                if ((st & 15) == 0) refill();
+                step<false, true>(st, ms, sc);
+            }
         }
     }
 
+    // Steps per trip of the fast loop.  A single-stripe task runs four (loop overhead off the DPX pipe); the stripes of a
+    // long read run one: their warps are latency-bound (a stripe waits on the one above it) and sit on the same SM in
+    // different sweeps and phases, so what limits them is instruction fetch (`no_instruction` was the top stall of
+    // config 5's launches, 2.5 cycles per issue) and a loop body a quarter of the size is worth more than the saved branch.
+    static constexpr int kUnroll = (MULTI && MODE != kExact) ? 1 : 4;
     template <class MS, class SC>
     __device__ __forceinline__ void fast_until(int& st, int end, const MS& ms, const SC& sc) {
         for (; st + 16 <= end; st += 16) {       // st is a multiple of 16 here
             refill();
 #pragma unroll 1
-            for (int b = 0; b < 16; b += 4) {
+            for (int b = 0; b < 16; b += kUnroll) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) step<true>(st + b + u, ms, sc);
+                for (int u = 0; u < kUnroll; ++u) step<true, false>(st + b + u, ms, sc);
             }
         }
     }
@@ -739,7 +754,7 @@ struct RestArgs {
 };
 
 template <int R, class SC>
-__device__ __forceinline__ u64 exact_task(const Task& tk, const uint32_t* __restrict__ pool, const SC& sc, int4* prof, int lane) {
+__device__ __noinline__ u64 exact_task(const Task& tk, const uint32_t* __restrict__ pool, const SC& sc, int4* prof, int lane) {
     __syncwarp();
     build_profile<R>(prof, pool + tk.q_word, tk.q_len, lane * R, lane, ModeScore<SC, 1>(sc), false);
     __syncwarp();
@@ -760,7 +775,7 @@ __device__ __forceinline__ u64 exact_dispatch(int r, const Task& tk, const uint3
 
 // One stripe of a multi-stripe task; the stripe that finishes last writes the record.
 template <int R, class SC>
-__device__ __forceinline__ void exact_stripe(const Task& tk, int tid, int s, const CoopInfo& ci, const RestArgs& ra,
+__device__ __noinline__ void exact_stripe(const Task& tk, int tid, int s, const CoopInfo& ci, const RestArgs& ra,
                                              const uint32_t* __restrict__ pool, const SC& sc, int4* prof, int lane, int4* out) {
     const int S = ci.n_stripes;
     const int epoch = ra.epoch;
@@ -804,6 +819,10 @@ __host__ __device__ __forceinline__ int coop_rows(int q_len, int n_stripes) {
     return R < kMinR ? kMinR : R;
 }
 
+// The task-level functions of the 32-bit kernels above (one per stripe height and sweep kind) are NOT inlined into the
+// persistent kernels: each is compiled as a function of its own, so that ptxas allocates registers and decides on spills
+// per variant.  Inlined, the kernels were one 2 MB body whose allocation flipped between builds (with or without a
+// 1.5-3 KB stack frame, 5-8 % apart in speed) on edits to unrelated variants; a call per task costs nothing.
 constexpr int kWarpsPerBlock = 16;     // one persistent 512-thread block per SM: 4 warps per scheduler (the host may launch fewer)
 
 // order[] entries: (task << 7) | code.  code 0: the whole (single-stripe) task; 1 + s: stripe s of the first sweep of a
@@ -951,7 +970,7 @@ __device__ __forceinline__ void finish_read(const SW& sw, const LadderTask& tk, 
 }
 
 template <int R, bool FLAG, class SC>
-__device__ __forceinline__ void ladder_task(const LadderTask& tk, const LadderCtx& cx, const SC& sc, int4* prof, int lane,
+__device__ __noinline__ void ladder_task(const LadderTask& tk, const LadderCtx& cx, const SC& sc, int4* prof, int lane,
                                             int4* out, int4* sel) {
     constexpr int BWD = FLAG ? kBwdF : kBwd, FWD = FLAG ? kFwdF : kFwd;
     int4* bsm = prof + StripeCfg<R>::PROF_INT4;
@@ -990,7 +1009,7 @@ __device__ __forceinline__ void ladder_task(const LadderTask& tk, const LadderCt
 }
 
 template <int R, bool FLAG, class SC>
-__device__ __forceinline__ void ladder_bwd_stripe(const LadderTask& tk, const LadderCtx& cx, int s, const CoopInfo& ci,
+__device__ __noinline__ void ladder_bwd_stripe(const LadderTask& tk, const LadderCtx& cx, int s, const CoopInfo& ci,
                                                   const RestArgs& ra, const SC& sc, int4* prof, int lane) {
     constexpr int BWD = FLAG ? kBwdF : kBwd;
     const int S = ci.n_stripes;
@@ -1021,7 +1040,7 @@ __device__ __forceinline__ void ladder_bwd_stripe(const LadderTask& tk, const La
 }
 
 template <int R, bool FLAG, class SC>
-__device__ __forceinline__ void ladder_fwd_stripe(const LadderTask& tk, const LadderCtx& cx, int s, const CoopInfo& ci,
+__device__ __noinline__ void ladder_fwd_stripe(const LadderTask& tk, const LadderCtx& cx, int s, const CoopInfo& ci,
                                                   const RestArgs& ra, const SC& sc, int4* prof, int lane, int4* out,
                                                   int4* sel) {
     constexpr int FWD = FLAG ? kFwdF : kFwd;
