@@ -386,6 +386,53 @@ def measure_config(name, regs, torch, stream, flush, engine, peak16, peak32, ste
     return res
 
 
+def measure_joint(torch, engine, peak32, threads, n_reads=1000, n_check=48):
+    """Config 2 read as what BASELINE.json literally names -- HTT CAG/CCG JOINT quantification: nanoRepeat-joint's grid
+    rounds 2 and 3 (nanoRepeat_joint.py:234-273) for one locus through nr_joint_grid; every (read, grid point, strand) is
+    its own rectangle here (no ladder sharing yet), the window score comes out of the DP.  A sample of grid points is
+    checked against the CPU oracle."""
+    from nanorepeat_b200 import joint, synth
+    from oracle import nr_oracle
+    loc = synth.joint_locus(seed=7, n_reads=n_reads)
+    args = (loc["reads"], loc["left"], loc["mid"], loc["right"], "CAG", "CCG", loc["range1"], loc["range2"], 200, 50)
+    counted = {"points": 0, "cells": 0}
+
+    def counting_grid(sc, left, mid, right, m1, m2, reads, pr, p1, p2):
+        counted["points"] += len(pr)
+        counted["cells"] += sum(2 * len(reads[r]) * (len(left) + len(m1) * a + len(mid) + len(m2) * b + len(right)) for r, a, b in zip(pr, p1, p2))
+        counted["last"] = (pr, p1, p2)
+        rec, strand = engine.joint_grid(sc, left, mid, right, m1, m2, reads, pr, p1, p2)
+        counted["rec"], counted["strand"] = rec, strand
+        return rec, strand
+
+    joint.quantify_two_repeats(*args)                       # warm-up
+    counted.update(points=0, cells=0)
+    t0 = time.perf_counter()
+    res = joint.quantify_two_repeats(*args, align=counting_grid)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    # parity spot check on the last round's grid points
+    pr, p1, p2 = counted["last"]
+    rng = np.random.default_rng(3)
+    for i in rng.choice(len(pr), min(n_check, len(pr)), replace=False):
+        r, k1, k2 = pr[i], p1[i], p2[i]
+        tpl = loc["left"] + "CAG" * k1 + loc["mid"] + "CCG" * k2 + loc["right"]
+        a, b = max(len(loc["left"]) - 10, 0), min(len(loc["left"]) + 3 * k1 + len(loc["mid"]) + 3 * k2 + 10, len(tpl))
+        f = nr_oracle.align_window(loc["reads"][r], tpl, a, b, reverse=False)
+        v = nr_oracle.align_window(loc["reads"][r], tpl, a, b, reverse=True)
+        exp = v if v > f else f
+        got = (int(counted["rec"]["score"][i]), int(counted["rec"]["window_score"][i]))
+        assert got == exp, f"joint grid point {i}: {got} vs oracle {exp}"
+    good = sum(abs(float(a) - t[0]) <= 1 and abs(float(b) - t[1]) <= 1
+               for a, b, t in zip(res["size1"], res["size2"], loc["truth"]) if a is not None)
+    return {"workload": f"HTT-like locus, {n_reads} raw amplicon reads (either strand), grid rounds 2 and 3 of nanoRepeat-joint",
+            "reads": n_reads, "grid_points": counted["points"], "cells": counted["cells"], "s": dt, "reads_per_s": n_reads / dt,
+            "value": counted["cells"] / dt / 1e9, "unit": UNIT, "frac_of_32bit_peak_end_to_end": counted["cells"] / dt / 1e9 / peak32,
+            "oracle_checked_points": min(n_check, len(pr)), "reads_within_1_unit_of_both_simulated_counts": good,
+            "path": "joint.quantify_two_repeats -> nr_joint_grid (host strings in, sizes out; both strands of every grid point; "
+                    "time includes template building, packing, both launches and the selection)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -578,6 +625,8 @@ def main():
             cfgs[name] = measure_config(name, make(), torch, stream, flush, engine, peak16, peak32, steps, passes,
                                         e2e_passes_c, threads, check)
         line["configs"] = cfgs
+    if not args.no_configs and world == 1:
+        line["joint"] = measure_joint(torch, engine, peak32, threads)
     if not args.no_cpu_baseline:
         sample = synth.config2(seed=args.seed, n_reads=args.cpu_sample_reads)
         t0 = time.perf_counter()

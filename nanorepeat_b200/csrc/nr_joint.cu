@@ -4,6 +4,9 @@
 #include "nr_window_kernel.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
@@ -92,7 +95,11 @@ int run_window_tasks(const nr_scoring_t* sc, std::vector<nrw::WinTask>& tasks, c
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, st);
+    const auto t_launch = std::chrono::steady_clock::now();
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (getenv("NR_TRACE"))
+        fprintf(stderr, "[nr trace] window kernel: %d tasks, upload + kernel + download %.1f us\n", n,
+                std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_launch).count());
     if (e != cudaSuccess) { cleanup(); cudaGetLastError(); return nri::fail_msg(NR_ERR_CUDA, cudaGetErrorString(e)); }
     const int2* res = static_cast<const int2*>(h_out);
     for (int i = 0; i < n; ++i) { out[order[i]].score = res[i].x; out[order[i]].window_score = res[i].y; }

@@ -26,6 +26,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace nrw {
 
@@ -100,7 +101,9 @@ __device__ __forceinline__ int window_task(const WinTask& tk, const uint32_t* __
         int hup_prev = 0, h_out = 0, f1_out = 0, f2_out = 0;
         int4 bcur = make_int4(0, 0, 0, 0);
         const int nsteps = t_len + 31;
-        for (int st = 0; st < nsteps; ++st) {
+        // one column step of this lane; GUARD: the lane may be outside the matrix (the first 31 and the last 31 steps)
+        auto step = [&](int st, auto guard_tag) {
+            constexpr bool GUARD = decltype(guard_tag)::value;
             if (top && (st & 31) == 0) {
                 const int cj = st + lane;
                 bcur = cj < t_len ? __ldcg(&bin[cj]) : make_int4(0, 0, 0, 0);
@@ -108,39 +111,53 @@ __device__ __forceinline__ int window_task(const WinTask& tk, const uint32_t* __
             int hup = __shfl_up_sync(kFull, h_out, 1);
             int f1 = __shfl_up_sync(kFull, f1_out, 1);
             int f2 = __shfl_up_sync(kFull, f2_out, 1);
-            const int bh = __shfl_sync(kFull, bcur.x, st & 31), bf1 = __shfl_sync(kFull, bcur.y, st & 31), bf2 = __shfl_sync(kFull, bcur.z, st & 31);
-            if (lane == 0) { hup = top ? bh : 0; f1 = top ? bf1 : kPad; f2 = top ? bf2 : kPad; }
+            if (top) {        // (uniform)
+                const int bh = __shfl_sync(kFull, bcur.x, st & 31), bf1 = __shfl_sync(kFull, bcur.y, st & 31), bf2 = __shfl_sync(kFull, bcur.z, st & 31);
+                if (lane == 0) { hup = bh; f1 = bf1; f2 = bf2; }
+            } else if (lane == 0) { hup = 0; f1 = kPad; f2 = kPad; }
             const int p = st - lane;                 // template position of this lane's column
-            if (p >= 0 && p < t_len) {
+            if (!GUARD || (p >= 0 && p < t_len)) {
                 const int code = (tw[p >> 4] >> (30 - 2 * (p & 15))) & 3;
                 const bool in_diag = p >= a && p < b;                 // this column's base is inside the window
                 const bool in_next = p + 1 >= a && p + 1 < b;         // the next column's (a deletion step computed here consumes it)
                 const bool in_ins = p + 1 > a && p + 1 < b - 1;       // insertions behind this column (tk.py:477)
                 const int h_open_pay = in_next ? -4 : 0, h_ext_pay = in_next ? (p + 1 == a ? -4 : -2) : 0;
                 const int v_open_pay = in_ins ? -4 : 0, v_ext_pay = in_ins ? -2 : 0;
-                const int* pr = prof + ((in_diag ? 4 : 0) + code) * kRows + lane * kR;
+                const int ho1 = sc.open1 + h_open_pay, ho2 = sc.open2 + h_open_pay, he1 = sc.ext1 + h_ext_pay, he2 = sc.ext2 + h_ext_pay;
+                const int vo1 = sc.open1 + v_open_pay, vo2 = sc.open2 + v_open_pay, ve1 = sc.ext1 + v_ext_pay, ve2 = sc.ext2 + v_ext_pay;
+                const int4* pr = reinterpret_cast<const int4*>(prof + ((in_diag ? 4 : 0) + code) * kRows + lane * kR);
                 int hd = hup_prev;
                 hup_prev = hup;
-                // the first column's horizontal state: a deletion run that opens at position 0 (E was preset without window value)
                 int cm = best;
 #pragma unroll
-                for (int r = 0; r < kR; ++r) {
-                    const int hleft = H[r];
-                    const int t = __vimax3_s32(hd + pr[r], E1[r], E2[r]);
-                    const int h = __vimax3_s32_relu(t, f1, f2);
-                    E1[r] = __viaddmax_s32(h, sc.open1 + h_open_pay, E1[r] + sc.ext1 + h_ext_pay);
-                    E2[r] = __viaddmax_s32(h, sc.open2 + h_open_pay, E2[r] + sc.ext2 + h_ext_pay);
-                    f1 = __viaddmax_s32(h, sc.open1 + v_open_pay, f1 + sc.ext1 + v_ext_pay);
-                    f2 = __viaddmax_s32(h, sc.open2 + v_open_pay, f2 + sc.ext2 + v_ext_pay);
-                    hd = hleft;
-                    H[r] = h;
-                    cm = max(cm, h);
+                for (int c = 0; c < kR / 4; ++c) {
+                    const int4 sv = pr[c];
+                    const int s4[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = 4 * c + u;
+                        const int hleft = H[r];
+                        const int t = __vimax3_s32(hd + s4[u], E1[r], E2[r]);
+                        const int h = __vimax3_s32_relu(t, f1, f2);
+                        E1[r] = __viaddmax_s32(h, ho1, E1[r] + he1);
+                        E2[r] = __viaddmax_s32(h, ho2, E2[r] + he2);
+                        f1 = __viaddmax_s32(h, vo1, f1 + ve1);
+                        f2 = __viaddmax_s32(h, vo2, f2 + ve2);
+                        hd = hleft;
+                        H[r] = h;
+                        if (r & 1) cm = __vimax3_s32(cm, h, H[r - 1]);
+                    }
                 }
                 best = cm;
                 h_out = H[kR - 1]; f1_out = f1; f2_out = f2;
                 if (bot && lane == 31) __stcg(&bout[p], make_int4(h_out, f1_out, f2_out, 0));
             }
-        }
+        };
+        int st = 0;
+        for (; st < min(31, nsteps); ++st) step(st, std::true_type{});
+#pragma unroll 2
+        for (; st < t_len; ++st) step(st, std::false_type{});          // every lane's column is inside the matrix
+        for (; st < nsteps; ++st) step(st, std::true_type{});
         __syncwarp();
         __threadfence_block();
     }

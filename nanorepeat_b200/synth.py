@@ -230,3 +230,28 @@ def region_reads(seed=6, n_reads=40, motif="CAG", alleles=(17, 55), profile="ont
         names.append(name); seqs.append(read)
         truth[name] = (k, strand) if full else None
     return reg, names, seqs, truth
+
+
+def joint_locus(seed=7, n_reads=500, profile="ont", flank=1000, alleles=((17, 10), (55, 7)), amplicon_flank=(150, 600)):
+    """nanoRepeat-joint's input shape (reference README.md:167, nanoRepeat_joint.py:509-649): the HTT locus
+    (CAG)k1 CAACAGCCGCCA (CCG)k2 with 1000-bp anchors, raw amplicon reads of either strand, and per read the
+    (min, max) repeat-count ranges the initial estimate hands to the grid rounds (here: the simulated counts +- what the
+    reference's initial estimate typically leaves, :592-649).  -> dict(left, mid, right, motif1, motif2, reads, range1,
+    range2, truth)."""
+    rng = np.random.default_rng(seed)
+    sub, ins, dele, _ = ERROR_PROFILES[profile]
+    left, right, mid = random_seq(rng, flank), random_seq(rng, flank), "CAACAGCCGCCA"
+    comp = str.maketrans("ACGT", "TGCA")
+    reads, range1, range2, truth = [], [], [], []
+    for i in range(n_reads):
+        k1, k2 = alleles[int(rng.integers(0, len(alleles)))]
+        lo, hi = int(rng.integers(*amplicon_flank)), int(rng.integers(*amplicon_flank))
+        read = mutate(rng, left[-lo:] + "CAG" * k1 + mid + "CCG" * k2 + right[:hi], sub, ins, dele)
+        if rng.random() < 0.5:
+            read = read.translate(comp)[::-1]
+        reads.append(read)
+        truth.append((k1, k2))
+        range1.append((max(0, k1 - int(rng.integers(8, 16))), k1 + int(rng.integers(8, 16))))
+        range2.append((max(0, k2 - int(rng.integers(4, 7))), k2 + int(rng.integers(4, 7))))
+    return dict(left=left, mid=mid, right=right, motif1="CAG", motif2="CCG", reads=reads, range1=range1, range2=range2,
+                truth=truth)
