@@ -308,8 +308,10 @@ struct nr_batch {
     bool flag = false;                        // ladder on flag words: d_out holds (score, spans both, ends in right)
     bool pair = false;                        // paired u16x2 kernels where a task is eligible (round 2: flags kind; round 3: mode 3)
     bool r2flags = false;                     // round 2: records are (score, span predicate, tend); no tstart
-    std::vector<nr::pr::Pair2> pairs2;
+    std::vector<nr::pr::Pair2> pairs2;        // single-stripe pairs first (n_pairs2_single), then the pairs of long reads
     std::vector<nr::pr::Pair3> pairs3;
+    int n_pairs2_single = 0;
+    int n_long_pairs = 0;                     // pairs of long reads: their stripes are entries of order[] (nr::pr::kPairEntry)
     void* d_pairs = nullptr;                  // inside the blob
     uint2* d_prung = nullptr;                 // round 3 pairs: (P, J) tokens per rung of a pair's ladder
     size_t prung_bytes = 0;
@@ -531,7 +533,8 @@ int plan_batch(nr_batch* b) {
             std::vector<int> src2lt(src->tasks.size(), -1);
             for (int i = 0; i < n; ++i)
                 if (b->lt_src[i] >= 0) src2lt[b->lt_src[i]] = i;
-            for (const nr::pr::Pair2& p2 : src->pairs2) {
+            for (int pi = 0; pi < src->n_pairs2_single; ++pi) {
+                const nr::pr::Pair2& p2 = src->pairs2[pi];
                 int la = src2lt[p2.a], lb = p2.b >= 0 ? src2lt[p2.b] : -1;
                 if (la >= 0 && paired[la]) la = -1;        // (not scored: beyond the packed range)
                 if (lb >= 0 && paired[lb]) lb = -1;
@@ -601,6 +604,32 @@ int plan_batch(nr_batch* b) {
         L.pair_blocks = std::max(1, std::min(g_ctx.sm_count, L.n_pairs));
     }
     trace.mark("pair order");
+    b->n_pairs2_single = (int)b->pairs2.size();
+    // ---- pairs of LONG reads (round 2): two reads of a region that are longer than one paired stripe share the u16x2
+    // words stripe by stripe; their stripes are cooperative entries like the 32-bit ones.  A read pairs with the next
+    // shorter one of its region if that one is at least half as long (the pair sweeps the longer read's rows).
+    struct LongPair { int a, b, n_left; long long cost; };
+    std::vector<LongPair> long_pairs;
+    long long long_pair_rows = 0;
+    if (b->pair && fixed && !ladder && b->kind == KIND_ROUND2 && !getenv("NR_NO_LONG_PAIRS")) {
+        for (const RegionInfo& g : b->regions) {
+            std::vector<int> ids;
+            for (int r = g.first_read; r < g.first_read + g.n_reads; ++r)
+                if (!paired[r] && b->tasks[r].q_len > 32 * nr::pr::kMaxRPair2 && b->tasks[r].t_len >= 1) ids.push_back(r);
+            std::sort(ids.begin(), ids.end(), [&](int x, int y) { return b->tasks[x].q_len != b->tasks[y].q_len ? b->tasks[x].q_len > b->tasks[y].q_len : x < y; });
+            for (size_t i = 0; i + 1 < ids.size();) {
+                const int x = ids[i], y = ids[i + 1];
+                if (2 * b->tasks[y].q_len >= b->tasks[x].q_len) {
+                    long_pairs.push_back({x, y, g.n_left, 0});
+                    paired[x] = paired[y] = 3;
+                    long_pair_rows += b->tasks[x].q_len;
+                    i += 2;
+                } else {
+                    ++i;
+                }
+            }
+        }
+    }
     // ---- the rest: one persistent launch of the 32-bit kernels.  Long reads are cut into stripes that run on
     // different warps at the same time (nr_kernels.cuh, CoopInfo); their entries come first, by decreasing cost, every
     // entry behind what it waits for; then the single-stripe tasks by decreasing cost ----
@@ -611,7 +640,8 @@ int plan_batch(nr_batch* b) {
         (task_ns[i] > 1 ? multis : singles).push_back(i);
         if (task_ns[i] > 1) multi_rows += ladder ? b->ltasks[i].q_len : b->tasks[i].q_len;
     }
-    if (!multis.empty()) {
+    int coop_height = 12;
+    if (!multis.empty() || !long_pairs.empty()) {
         // stripe height of the long tasks: the shortest that does not cut them into more stripes than there are warps
         // to run them side by side (a stripe is one warp's work; the ladder's two sweeps overlap)
         const long long warps = (long long)kWarpsPerBlock * g_ctx.sm_count;
@@ -620,7 +650,7 @@ int plan_batch(nr_batch* b) {
         if (force && atoi(force) >= nr::kMinR && atoi(force) <= max_r) cap = std::min(nr::coop_height_at_least(atoi(force)), max_r);
         else for (int r : {4, 6, 8}) {
             if (r >= max_r) break;
-            const long long stripes = (multi_rows / (32 * r) + (long long)multis.size()) * (ladder ? 2 : 1);
+            const long long stripes = ((multi_rows + long_pair_rows) / (32 * r) + (long long)multis.size() + (long long)long_pairs.size()) * (ladder ? 2 : 1);
             if (stripes <= warps) { cap = r; break; }
         }
         // ONE stripe height for all long tasks of the batch.  Every height is its own unrolled code; long reads running
@@ -628,6 +658,7 @@ int plan_batch(nr_batch* b) {
         // issued instruction, round 3 in 183 ms with three heights in flight against 57 ms with one).  The last stripe of
         // a task is padded up to the common height.
         const int height = std::min(cap, 12);
+        coop_height = height;
         for (int i : multis) {
             const int q_len = ladder ? b->ltasks[i].q_len : b->tasks[i].q_len;
             int R = height, ns = (q_len + 32 * height - 1) / (32 * height);
@@ -641,6 +672,29 @@ int plan_batch(nr_batch* b) {
             task_ns[i] = ns;
             task_R[i] = R;
         }
+    }
+    // long pairs at the common height; one that would need more than 62 stripes goes back to the 32-bit kernels
+    {
+        std::vector<LongPair> keep;
+        for (LongPair& lp : long_pairs) {
+            const int q = b->tasks[lp.a].q_len, ns = (q + 32 * coop_height - 1) / (32 * coop_height);
+            if (ns > nr::kCodeFwd - 2 || b->pairs2.size() + keep.size() >= (1u << 22)) {
+                for (int t : {lp.a, lp.b}) {
+                    paired[t] = 0;
+                    multis.push_back(t);
+                    int R = nr::coop_height_at_least(nr::coop_rows(b->tasks[t].q_len, nr::kCodeFwd - 2));
+                    R = std::max(R, coop_height);
+                    const int ns1 = (b->tasks[t].q_len + 32 * R - 1) / (32 * R);
+                    cost[t] = cost[t] / ((long long)task_ns[t] * task_R[t]) * ((long long)ns1 * R);
+                    task_ns[t] = ns1; task_R[t] = R;
+                }
+                continue;
+            }
+            lp.cost = (long long)ns * 32 * coop_height * b->tasks[lp.a].t_len;
+            keep.push_back(lp);
+        }
+        long_pairs.swap(keep);
+        std::sort(long_pairs.begin(), long_pairs.end(), [](const LongPair& x, const LongPair& y) { return x.cost != y.cost ? x.cost > y.cost : x.a < y.a; });
     }
     int rmax = 0;
     for (int i = 0; i < n; ++i) {
@@ -676,6 +730,28 @@ int plan_batch(nr_batch* b) {
         else b->coop_idx[i] = (int32_t)b->coop.size();
         b->coop.push_back(ci);
     }
+    std::vector<int> long_pair_ns;
+    for (const LongPair& lp : long_pairs) {
+        const nr::Task& ta = b->tasks[lp.a];
+        nr::CoopInfo ci = {};
+        ci.n_stripes = (ta.q_len + 32 * coop_height - 1) / (32 * coop_height);
+        ci.rows = coop_height;
+        ci.data_off = data_off;
+        ci.flag_off = (int)flag_off;
+        ci.bnd_stride = (ta.t_len + 63) / 32 * 32;
+        data_off += 2LL * ci.bnd_stride;
+        flag_off += nr::kCoopFlagInts(ci.n_stripes);
+        if (flag_off > 0x7fffffffLL) return fail(NR_ERR_TOO_LARGE, "too many long tasks in one batch");
+        nr::pr::Pair2 p = {lp.a, lp.b, lp.n_left, (int32_t)b->coop.size()};      // state_off = the pair's CoopInfo
+        b->coop.push_back(ci);
+        b->pairs2.push_back(p);
+        long_pair_ns.push_back(ci.n_stripes);
+        L.pair_R = std::max(L.pair_R, coop_height);
+        b->paired_cells += 2 * lp.cost;
+        b->stats.executed_cells += 2 * lp.cost;
+        b->paired_useful += (long long)(ta.q_len + b->tasks[lp.b].q_len) * ta.t_len;
+    }
+    b->n_long_pairs = (int)long_pairs.size();
     // Stripe-major: stripe 0 of every long task, then stripe 1 of every long task, ...  A stripe waits for the one above
     // it; listed task by task, all stripes of a task would be picked up at the same moment and stripe s would spin for
     // s x (lag of ~95 columns) before its first column -- with 20 stripes over the 1000 columns of the right anchor
@@ -684,11 +760,16 @@ int plan_batch(nr_batch* b) {
     // from the tasks; with few long tasks all levels are in flight at once and the stripes pipeline as before.
     int max_ns = 0;
     for (int i : multis) max_ns = std::max(max_ns, task_ns[i]);
-    for (int st = 0; st < max_ns; ++st)                     // first sweep of every long task (ladder: backward)
+    for (int ns : long_pair_ns) max_ns = std::max(max_ns, ns);
+    for (int st = 0; st < max_ns; ++st) {                   // first sweep of every long task (ladder: backward)
+        for (size_t k = 0; k < long_pair_ns.size(); ++k)    // (pairs of long reads: entries point into pairs[])
+            if (st < long_pair_ns[k])
+                b->order.push_back(nr::pr::kPairEntry | ((b->n_pairs2_single + (int)k) << nr::kCodeBits) | (1 + st));
         for (int i : multis) {
             if (st >= task_ns[i] || (ladder && b->lregs[b->ltasks[i].region].n_right == 0)) continue;
             b->order.push_back((i << nr::kCodeBits) | (1 + st));
         }
+    }
     if (ladder)
         for (int st = 0; st < max_ns; ++st)
             for (int i : multis)
@@ -855,7 +936,7 @@ int run_batch(nr_batch* b, cudaStream_t st) {
             if (!e) CUDA_TRY(cudaEventCreate(&e));
     b->timed[0] = b->timed[1] = b->timed[2] = false;
     auto mark = [&](int i, cudaStream_t s) { return timing ? cudaEventRecord(b->ev_t[i], s) : cudaSuccess; };
-    if (L.n_pairs) {
+    if (L.n_pairs || b->n_long_pairs) {
         // one persistent launch: the batch's 32-bit entries (long reads cut into stripes, ...) first, then its pairs
         nr::RestArgs ra;
         if ((rc = rest_args(b, b->d_order, L.count, st, &ra))) return rc;

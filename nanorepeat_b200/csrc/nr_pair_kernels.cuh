@@ -119,11 +119,22 @@ constexpr int kP2 = 0, kPB = 1, kPF = 2;
 //        state (H, E1 + refund1, E2 + refund2) goes to bvec in the forward layout, each half at its own read's rows.
 //   kPF: reads x left + motif^kmax; marks after column |left| - 1; junction candidates and (P, J) tokens as in
 //        nr_kernels.cuh; the last lane stores every rung's token pair.
-template <int R, int MODE>
+// MULTI: one stripe of a pair of LONG reads (more than 512 bases): the stripes of the pair run on different warps at the
+// same time and hand their bottom rows down through tagged boundary entries exactly like the 32-bit stripes of
+// nr_kernels.cuh (load_bnd / store_bnd: a boundary entry holds H, F1, F2 as three 32-bit words -- here each is the two
+// halves of the pair).  `top`: a stripe above exists (lane 0 takes its upper neighbour from bnd_in); `bot`: one below.
+template <int R, int MODE, bool MULTI = false>
 struct Sweep {
     static constexpr u32 FLOOR = MODE == kPB ? kFloorBwd : kFloorFwd;
     static constexpr bool kMarks = MODE != kPB;
     // inputs
+    bool top, bot;
+    const ulonglong2* bnd_in;
+    ulonglong2* bnd_out;
+    int tag_in, tag_out;
+    int* spin;
+    int4 bcur;
+    ulonglong2 bnxt;
     const uint4* prof;
     const uint32_t* twords;
     int t_len, lane;
@@ -178,6 +189,10 @@ struct Sweep {
         twl = 0;
         prof_lane = reinterpret_cast<const char*>(prof + lane);
         tokP = 0; tokJ = 0;
+        if (MULTI) {
+            bcur = make_int4(0, 0, 0, 0); bnxt = make_ulonglong2(0ull, 0ull);
+            if (top) bnxt = load_bnd(&bnd_in[lane < t_len ? lane : t_len - 1]);      // validated when it is taken over
+        }
     }
 
     __device__ __forceinline__ void refill() {
@@ -288,9 +303,28 @@ struct Sweep {
             tP = __shfl_up_sync(kFull, tokP, 1);
             tJ = __shfl_up_sync(kFull, tokJ, 1);
         }
-        hup = pmadd(hup, nz, bz);
-        f1 = pmadd(f1, nz, bz);
-        f2 = pmadd(f2, nz, bz);
+        if (MULTI && top) {                 // uniform branch: lane 0's upper neighbour is the stripe above
+            if ((st & 31) == 0) {
+                ulonglong2 raw = bnxt;
+                const int cj = st + lane;
+                for (int tries = 0; !__all_sync(kFull, bnd_valid(raw, tag_in) || cj >= t_len); ++tries) {
+                    if (tries > kSpinLimit) { *spin = 1; break; }
+                    if (tries > 3) __nanosleep(32);
+                    raw = load_bnd(&bnd_in[cj < t_len ? cj : t_len - 1]);
+                }
+                bcur = unpack_bnd(raw);
+                const int nj = st + 32 + lane;
+                bnxt = load_bnd(&bnd_in[nj < t_len ? nj : t_len - 1]);      // in flight for the next 32 steps
+            }
+            const u32 bh = __shfl_sync(kFull, (u32)bcur.x, st & 31);
+            const u32 bf1 = __shfl_sync(kFull, (u32)bcur.y, st & 31);
+            const u32 bf2 = __shfl_sync(kFull, (u32)bcur.z, st & 31);
+            if (lane == 0) { hup = bh; f1 = bf1; f2 = bf2; }
+        } else {
+            hup = pmadd(hup, nz, bz);
+            f1 = pmadd(f1, nz, bz);
+            f2 = pmadd(f2, nz, bz);
+        }
         const unsigned tb = next_base(four);
         const int rel = st - lane;
         const int jj = rel + col0;
@@ -340,6 +374,7 @@ struct Sweep {
                 ++kcnt;
             }
             if (kMarks && kChecks && jj == mark_col) mark_started_inside();
+            if (MULTI && bot && lane == 31) store_bnd(&bnd_out[jj], (int)h_out, (int)f1_out, (int)f2_out, tag_out);
         }
     }
 
@@ -408,6 +443,7 @@ struct Sweep {
 // planes (384 bytes per row): 14 KB at R = 16, 224 KB for the 16 warps of a block
 constexpr int kMaxRPair3 = 16;
 constexpr int kMaxRPair2 = kMaxRPair3;   // round 2 pairs the same reads, so that round 3 can resume from its state
+constexpr int kPairEntry = 1 << 30;      // order[] entry of a long pair's stripe: (index into pairs[] << 7) | code, this bit set
 
 __host__ __device__ __forceinline__ int pair_rows(int q_len) {
     int R = (q_len + 31) / 32;
@@ -510,6 +546,75 @@ __device__ __forceinline__ void pair2_task(const Pair2& pt, const Task* __restri
     }
 }
 
+// One stripe of a pair of long reads in round 2.  pt.state_off = index of the pair's CoopInfo; the pair's flag words:
+// [2S] stripes done, [2S + 2] / [2S + 3] best key of read A / read B over the stripes done so far.
+template <int R>
+__device__ __noinline__ void pair2_stripe(const Pair2& pt, int s, const Task* __restrict__ tasks, const uint32_t* __restrict__ pool,
+                                          const RestArgs& ra, uint4* prof, int lane, u32 one, unsigned four, int4* out) {
+    const CoopInfo ci = ra.coop[pt.state_off];
+    const int S = ci.n_stripes;
+    int* F = ra.flags + ci.flag_off;
+    ulonglong2* bnd_a = reinterpret_cast<ulonglong2*>(ra.scratch + ci.data_off);
+    ulonglong2* bnd_b = bnd_a + ci.bnd_stride;
+    const Task ta = tasks[pt.a];
+    Task tb = ta;
+    int q_b = 0;
+    if (pt.b >= 0) { tb = tasks[pt.b]; q_b = tb.q_len; }
+    __syncwarp();
+    build_profile<R>(prof, pool + ta.q_word, ta.q_len, pool + tb.q_word, q_b, s * 32 * R + lane * R, lane, false);
+    __syncwarp();
+    Sweep<R, kP2, true> sw;
+    sw.prof = prof; sw.twords = pool + ta.t_word; sw.t_len = ta.t_len; sw.lane = lane;
+    sw.mark_col = pt.mark_col;
+    sw.col0 = 0; sw.resume = nullptr; sw.save = nullptr; sw.save_col = -1;
+    sw.top = s > 0; sw.bot = s + 1 < S;
+    sw.bnd_in = (s & 1) ? bnd_a : bnd_b; sw.bnd_out = (s & 1) ? bnd_b : bnd_a;
+    sw.tag_in = stripe_tag(ra.epoch, s - 1); sw.tag_out = stripe_tag(ra.epoch, s); sw.spin = ra.spin;
+    sw.run(one, four, 0);
+    unsigned keys[2];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const u32 cls = half ? (sw.bestc & 0xffffu) : (sw.bestc >> 16);
+        const u32 raw = half ? (sw.raw_lo & 0xffffu) : (sw.raw_hi >> 16);
+        const int st = half ? sw.st_lo : sw.st_hi;
+        const int score = (int)(cls - (kBias + 1)) >> 1;
+        unsigned key = 0;
+        if (score > 0) key = ((unsigned)score << 17) | ((0xffffu - (unsigned)(st - lane)) << 1) | (raw & 1u);
+        keys[half] = __reduce_max_sync(kFull, key);
+    }
+    if (lane == 0) {
+        unsigned* K = reinterpret_cast<unsigned*>(F + 2 * S + 2);
+        atomicMax(&K[0], keys[0]);
+        atomicMax(&K[1], keys[1]);
+        __threadfence();
+        if (atomicAdd(F + 2 * S, 1) == S - 1) {
+            __threadfence();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int tid = half ? pt.b : pt.a;
+                if (tid < 0) continue;
+                const unsigned key = atomicMax(&K[half], 0u);
+                int4 rec = make_int4(0, 0, 0, 0);
+                if (key) {
+                    const int c = 0xffff - (int)((key >> 1) & 0xffffu);
+                    const bool inside = c <= pt.mark_col || !(key & 1u);
+                    rec = make_int4((int)(key >> 17), inside ? 0 : pt.mark_col + 1, c + 1, 0);
+                }
+                out[tid] = rec;
+            }
+        }
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void pair2_stripe_dispatch(int r, const Pair2& pt, int s, const Task* __restrict__ tasks,
+                                                      const uint32_t* __restrict__ pool, const RestArgs& ra, uint4* prof, int lane,
+                                                      u32 one, unsigned four, int4* out) {
+    if constexpr (is_coop_height(R))
+        if (r == R) { pair2_stripe<R>(pt, s, tasks, pool, ra, prof, lane, one, four, out); return; }
+    if constexpr (R < kMaxRLadder) pair2_stripe_dispatch<R + 1>(r, pt, s, tasks, pool, ra, prof, lane, one, four, out);
+}
+
 template <int R>
 __device__ __forceinline__ void pair2_dispatch(int r, const Pair2& pt, const Task* __restrict__ tasks,
                                                const uint32_t* __restrict__ pool, uint4* prof, int lane, u32 one,
@@ -534,7 +639,14 @@ pair_round2_kernel(const Pair2* __restrict__ pairs, Deal dl, const Task* __restr
         const int i = next_item(dl, first, counter);
         if (i < 0) break;
         if (i < ra.n_order) {
-            exact_entry(ra.order[i], tasks, pool, sc, ra, reinterpret_cast<int4*>(prof), lane, out);
+            const int e = ra.order[i];
+            if (e & kPairEntry) {           // a stripe of a pair of long reads: (pair index << 7) | (1 + stripe)
+                const Pair2 mp = pairs[(e & ~kPairEntry) >> kCodeBits];
+                pair2_stripe_dispatch<kMinR>(ra.coop[mp.state_off].rows, mp, (e & ((1 << kCodeBits) - 1)) - 1, tasks, pool, ra, prof, lane,
+                                             (u32)sc.one, sc.four, out);
+            } else {
+                exact_entry(e, tasks, pool, sc, ra, reinterpret_cast<int4*>(prof), lane, out);
+            }
             continue;
         }
         const Pair2 pt = pairs[i - ra.n_order];

@@ -794,3 +794,54 @@ def test_config2_full_size_properties(engine, oracle):
             g3 = rd.round3_repeat_size
             assert rd.round2_repeat_size == exp["r2"][j], (reg.name, i)
             assert (None if g3 is None else float(g3)) == (None if exp["r3"][j] is None else float(exp["r3"][j])), (reg.name, i)
+
+
+@pytest.mark.parametrize("rows", ["4", "8", ""])
+def test_round2_pairs_of_long_reads_equal_oracle(engine, oracle, rows, monkeypatch):
+    """Round 2, flags kind, reads longer than one paired stripe (513 ... 3000 bases): two reads of a region share the
+    u16x2 words stripe by stripe (cooperative stripes on different warps).  Several regions, odd counts, partners of
+    very different lengths (those stay on the 32-bit kernels), short reads beside them; every stripe height."""
+    if rows:
+        monkeypatch.setenv("NR_COOP_ROWS", rows)
+    else:
+        monkeypatch.delenv("NR_COOP_ROWS", raising=False)
+    rng = random.Random(515)
+    sc = engine.get_preset("ont")
+    specs, refs = [], []
+    for g in range(4):
+        n_left, m = rng.choice([60, 400, 1000]), rng.randint(2, 6)
+        left, motif = _rand_seq(rng, n_left), _rand_seq(rng, m)
+        T = rng.randint(300, 700)
+        tpl = left + motif * T
+        cores = []
+        for i in range(rng.choice([7, 12, 15])):
+            k = rng.choice([rng.randint(90, T), rng.randint(90, T), rng.randint(5, 60)])
+            kind = i % 4
+            core = left[-rng.randint(20, min(n_left, 120)):] + motif * k + _rand_seq(rng, rng.randint(0, 80))
+            if kind == 1:
+                core = _mutate(rng, core, 0.08)
+            elif kind == 2:
+                core = motif * k                                # no flank: starts past |left|
+            elif kind == 3:
+                core = _rand_seq(rng, rng.randint(520, 1500))  # unrelated long read
+            cores.append(core[:3000])
+        specs.append((left, motif, T, cores))
+        refs.append(oracle.align_batch(cores, [tpl] * len(cores), n_threads=oracle.max_threads()))
+    with engine.Batch.begin(sc, "round2_flags") as b:
+        for left, motif, T, cores in specs:
+            b.add_round2(left, motif, T, cores)
+        b.commit()
+        score, tend, inside = b.run().fetch_round2()
+        score2, tend2, inside2 = b.run().fetch_round2()         # a second launch over the same scratch
+    assert np.array_equal(score, score2) and np.array_equal(tend, tend2) and np.array_equal(inside, inside2)
+    pos = 0
+    for (left, motif, T, cores), ref in zip(specs, refs):
+        n, n_left = len(cores), len(left)
+        sl = slice(pos, pos + n)
+        pos += n
+        assert np.array_equal(score[sl], ref["score"]), (rows, [len(c) for c in cores])
+        spans = ref["tend"] >= n_left
+        assert np.array_equal(tend[sl][spans], ref["tend"][spans])
+        assert (tend[sl][~spans] < max(n_left, 1)).all()
+        live = (ref["score"] > 0) & spans
+        assert np.array_equal(inside[sl][live], (ref["tstart"] <= n_left)[live])
