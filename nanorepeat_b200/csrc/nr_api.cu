@@ -310,7 +310,8 @@ struct nr_batch {
     bool r2flags = false;                     // round 2: records are (score, span predicate, tend); no tstart
     std::vector<nr::pr::Pair2> pairs2;        // single-stripe pairs first (n_pairs2_single), then the pairs of long reads
     std::vector<nr::pr::Pair3> pairs3;
-    int n_pairs2_single = 0;
+    int n_pairs2_single = 0, n_pairs3_single = 0;
+    bool long_redone = false;                 // the host-side rescoring of this run's undecidable long reads is merged
     int n_long_pairs = 0;                     // pairs of long reads: their stripes are entries of order[] (nr::pr::kPairEntry)
     void* d_pairs = nullptr;                  // inside the blob
     uint2* d_prung = nullptr;                 // round 3 pairs: (P, J) tokens per rung of a pair's ladder
@@ -502,6 +503,7 @@ int plan_batch(nr_batch* b) {
     Launch& L = b->launch;
     L = {};
     long long state_off = 0;
+    long long rung_off = 0;           // (P, J) token pairs of the paired ladders, single-stripe pairs first
     if (b->pair && fixed && !ladder && b->kind == KIND_ROUND2) {
         for (const RegionInfo& g : b->regions) {
             std::vector<int> ids;
@@ -525,7 +527,6 @@ int plan_batch(nr_batch* b) {
             });
         }
     } else if (b->pair && fixed && ladder && b->flag) {
-        long long rung_off = 0;
         if (b->qsrc && !b->qsrc->pairs2.empty() && (int)b->lt_src.size() == n) {
             // the reads were paired in round 2: same pairs, same halves, same rows per lane, so that the forward sweep
             // can take over the DP state round 2 kept after column |left| - 2 instead of sweeping the left anchor again
@@ -583,7 +584,6 @@ int plan_batch(nr_batch* b) {
             i0 = i1;
         }
         if (rung_off > 0x7fffffffLL) return fail(NR_ERR_TOO_LARGE, "more than 2^31 rungs in one batch");
-        b->prung_bytes = sizeof(uint2) * (size_t)std::max<long long>(rung_off, 1);
         L.redo_R = L.pair_R;
     }
     trace.mark("pairing");
@@ -611,6 +611,32 @@ int plan_batch(nr_batch* b) {
     struct LongPair { int a, b, n_left; long long cost; };
     std::vector<LongPair> long_pairs;
     long long long_pair_rows = 0;
+    b->n_pairs3_single = (int)b->pairs3.size();
+    if (b->pair && fixed && ladder && b->flag && !getenv("NR_NO_LONG_PAIRS")) {
+        // round 3: the same, over the reads that have a ladder; the pair sweeps the union of the two ladders
+        for (int i0 = 0; i0 < n;) {
+            int i1 = i0;
+            while (i1 < n && b->ltasks[i1].region == b->ltasks[i0].region) ++i1;
+            const nr::LadderRegion& g = b->lregs[b->ltasks[i0].region];
+            std::vector<int> ids;
+            if (g.n_left > 0 && g.n_right > 0)
+                for (int i = i0; i < i1; ++i)
+                    if (!paired[i] && b->ltasks[i].q_len > 32 * nr::pr::kMaxRPair3) ids.push_back(i);
+            std::sort(ids.begin(), ids.end(), [&](int x, int y) { return b->ltasks[x].q_len != b->ltasks[y].q_len ? b->ltasks[x].q_len > b->ltasks[y].q_len : x < y; });
+            for (size_t i = 0; i + 1 < ids.size();) {
+                const int x = ids[i], y = ids[i + 1];
+                if (2 * b->ltasks[y].q_len >= b->ltasks[x].q_len) {
+                    long_pairs.push_back({x, y, g.n_left, 0});
+                    paired[x] = paired[y] = 3;
+                    long_pair_rows += b->ltasks[x].q_len;
+                    i += 2;
+                } else {
+                    ++i;
+                }
+            }
+            i0 = i1;
+        }
+    }
     if (b->pair && fixed && !ladder && b->kind == KIND_ROUND2 && !getenv("NR_NO_LONG_PAIRS")) {
         for (const RegionInfo& g : b->regions) {
             std::vector<int> ids;
@@ -676,21 +702,29 @@ int plan_batch(nr_batch* b) {
     // long pairs at the common height; one that would need more than 62 stripes goes back to the 32-bit kernels
     {
         std::vector<LongPair> keep;
+        auto qlen_of = [&](int t) { return ladder ? b->ltasks[t].q_len : b->tasks[t].q_len; };
         for (LongPair& lp : long_pairs) {
-            const int q = b->tasks[lp.a].q_len, ns = (q + 32 * coop_height - 1) / (32 * coop_height);
-            if (ns > nr::kCodeFwd - 2 || b->pairs2.size() + keep.size() >= (1u << 22)) {
+            const int q = qlen_of(lp.a), ns = (q + 32 * coop_height - 1) / (32 * coop_height);
+            if (ns > nr::kCodeFwd - 2 || b->pairs2.size() + b->pairs3.size() + keep.size() >= (1u << 22)) {
                 for (int t : {lp.a, lp.b}) {
                     paired[t] = 0;
                     multis.push_back(t);
-                    int R = nr::coop_height_at_least(nr::coop_rows(b->tasks[t].q_len, nr::kCodeFwd - 2));
+                    int R = nr::coop_height_at_least(nr::coop_rows(qlen_of(t), nr::kCodeFwd - 2));
                     R = std::max(R, coop_height);
-                    const int ns1 = (b->tasks[t].q_len + 32 * R - 1) / (32 * R);
+                    const int ns1 = (qlen_of(t) + 32 * R - 1) / (32 * R);
                     cost[t] = cost[t] / ((long long)task_ns[t] * task_R[t]) * ((long long)ns1 * R);
                     task_ns[t] = ns1; task_R[t] = R;
                 }
                 continue;
             }
-            lp.cost = (long long)ns * 32 * coop_height * b->tasks[lp.a].t_len;
+            long long cols;
+            if (ladder) {
+                const nr::LadderRegion& g = b->lregs[b->ltasks[lp.a].region];
+                cols = (long long)g.n_right + g.n_left + (long long)g.m * std::max(b->ltasks[lp.a].kmax, b->ltasks[lp.b].kmax);
+            } else {
+                cols = b->tasks[lp.a].t_len;
+            }
+            lp.cost = (long long)ns * 32 * coop_height * cols;
             keep.push_back(lp);
         }
         long_pairs.swap(keep);
@@ -732,6 +766,33 @@ int plan_batch(nr_batch* b) {
     }
     std::vector<int> long_pair_ns;
     for (const LongPair& lp : long_pairs) {
+        if (ladder) {
+            const nr::LadderTask& ta = b->ltasks[lp.a];
+            const nr::LadderTask& tb = b->ltasks[lp.b];
+            const nr::LadderRegion& g = b->lregs[ta.region];
+            const int kmin = std::min(ta.kmin, tb.kmin), kmax = std::max(ta.kmax, tb.kmax), rungs = kmax - kmin + 1;
+            nr::CoopInfo ci = {};
+            ci.n_stripes = (ta.q_len + 32 * coop_height - 1) / (32 * coop_height);
+            ci.rows = coop_height;
+            ci.data_off = data_off;
+            ci.flag_off = (int)flag_off;
+            ci.bnd_stride = (std::max(g.n_left + g.m * kmax, g.n_right) + 63) / 32 * 32;
+            ci.b_stride = ci.n_stripes * 32 * coop_height;          // words per plane of the backward stripes' junction state
+            ci.tok_stride = (rungs + 1) / 2 * 2;
+            data_off += 4LL * ci.bnd_stride + (3LL * ci.b_stride + 3) / 4 + 2LL * ci.tok_stride;
+            flag_off += nr::kCoopFlagInts(ci.n_stripes);
+            if (flag_off > 0x7fffffffLL) return fail(NR_ERR_TOO_LARGE, "too many long tasks in one batch");
+            nr::pr::Pair3 p = {lp.a, lp.b, (int32_t)rung_off, -1, coop_height, {(int32_t)b->coop.size(), 0, 0}};
+            rung_off += rungs;
+            b->coop.push_back(ci);
+            b->pairs3.push_back(p);
+            long_pair_ns.push_back(ci.n_stripes);
+            L.pair_R = std::max(L.pair_R, coop_height);
+            b->paired_cells += 2 * lp.cost;
+            b->stats.executed_cells += 2 * lp.cost;
+            b->paired_useful += (long long)(ta.q_len + tb.q_len) * (lp.cost / ((long long)ci.n_stripes * 32 * coop_height));
+            continue;
+        }
         const nr::Task& ta = b->tasks[lp.a];
         nr::CoopInfo ci = {};
         ci.n_stripes = (ta.q_len + 32 * coop_height - 1) / (32 * coop_height);
@@ -752,6 +813,8 @@ int plan_batch(nr_batch* b) {
         b->paired_useful += (long long)(ta.q_len + b->tasks[lp.b].q_len) * ta.t_len;
     }
     b->n_long_pairs = (int)long_pairs.size();
+    if (rung_off > 0x7fffffffLL) return fail(NR_ERR_TOO_LARGE, "more than 2^31 rungs in one batch");
+    if (!b->pairs3.empty()) b->prung_bytes = sizeof(uint2) * (size_t)std::max<long long>(rung_off, 1);
     // Stripe-major: stripe 0 of every long task, then stripe 1 of every long task, ...  A stripe waits for the one above
     // it; listed task by task, all stripes of a task would be picked up at the same moment and stripe s would spin for
     // s x (lag of ~95 columns) before its first column -- with 20 stripes over the 1000 columns of the right anchor
@@ -764,16 +827,20 @@ int plan_batch(nr_batch* b) {
     for (int st = 0; st < max_ns; ++st) {                   // first sweep of every long task (ladder: backward)
         for (size_t k = 0; k < long_pair_ns.size(); ++k)    // (pairs of long reads: entries point into pairs[])
             if (st < long_pair_ns[k])
-                b->order.push_back(nr::pr::kPairEntry | ((b->n_pairs2_single + (int)k) << nr::kCodeBits) | (1 + st));
+                b->order.push_back(nr::pr::kPairEntry | (((ladder ? b->n_pairs3_single : b->n_pairs2_single) + (int)k) << nr::kCodeBits) | (1 + st));
         for (int i : multis) {
             if (st >= task_ns[i] || (ladder && b->lregs[b->ltasks[i].region].n_right == 0)) continue;
             b->order.push_back((i << nr::kCodeBits) | (1 + st));
         }
     }
     if (ladder)
-        for (int st = 0; st < max_ns; ++st)
+        for (int st = 0; st < max_ns; ++st) {
+            for (size_t k = 0; k < long_pair_ns.size(); ++k)
+                if (st < long_pair_ns[k])
+                    b->order.push_back(nr::pr::kPairEntry | ((b->n_pairs3_single + (int)k) << nr::kCodeBits) | (nr::kCodeFwd + st));
             for (int i : multis)
                 if (st < task_ns[i]) b->order.push_back((i << nr::kCodeBits) | (nr::kCodeFwd + st));
+        }
     for (int i : singles) b->order.push_back(i << nr::kCodeBits);
     const int n_rest = (int)b->order.size();
     L.ladder = ladder;
@@ -817,11 +884,11 @@ int plan_batch(nr_batch* b) {
         if ((rc = cached_alloc((void**)&b->h_sel, b->sel_bytes, BUF_PIN))) return rc;
     }
     if (!b->pairs3.empty()) {
-        b->redo_bytes = sizeof(int32_t) * (size_t)n;
+        b->redo_bytes = sizeof(int32_t) * (size_t)n * 2;       // [n] entries of the device-side redo launch | [n] long reads for the host
         if ((rc = cached_alloc((void**)&b->d_prung, b->prung_bytes, BUF_DEV))) return rc;
         if ((rc = cached_alloc((void**)&b->d_redo, b->redo_bytes, BUF_DEV))) return rc;
         if ((rc = cached_alloc((void**)&b->h_redo_count, 64, BUF_PIN))) return rc;
-        *b->h_redo_count = 0;
+        b->h_redo_count[0] = b->h_redo_count[1] = 0;
     }
     trace.mark("buffers (cached alloc)");
     char* h = static_cast<char*>(b->h_blob);
@@ -867,6 +934,8 @@ int rest_args(nr_batch* b, const int32_t* order, int count, cudaStream_t st, nr:
     ra.order = order; ra.n_order = count;
     ra.scratch = b->d_scratch; ra.coop = b->d_coop; ra.coop_idx = b->d_coop_idx; ra.flags = b->d_flags;
     ra.spin = b->d_counters + kSpinSlot;
+    ra.redo_long = b->d_redo ? b->d_redo + b->ltasks.size() : nullptr;
+    ra.redo_long_count = b->d_counters + 4;
     const long long no = g_launch_no.fetch_add(1);
     ra.epoch = (int)(no % kEpochs) + 1;
     if (b->d_scratch) {
@@ -938,6 +1007,7 @@ int run_batch(nr_batch* b, cudaStream_t st) {
     auto mark = [&](int i, cudaStream_t s) { return timing ? cudaEventRecord(b->ev_t[i], s) : cudaSuccess; };
     if (L.n_pairs || b->n_long_pairs) {
         // one persistent launch: the batch's 32-bit entries (long reads cut into stripes, ...) first, then its pairs
+        const bool ladder_batch = L.ladder;
         nr::RestArgs ra;
         if ((rc = rest_args(b, b->d_order, L.count, st, &ra))) return rc;
         int wpb = kWarpsPerBlock;
@@ -946,7 +1016,7 @@ int run_batch(nr_batch* b, cudaStream_t st) {
         nr::pr::Deal deal = nr::pr::make_deal(L.count, L.n_pairs, wpb, blocks);
         if (getenv("NR_PLAIN_DEAL")) deal.nb_long = -1;      // tuning / debugging
         CUDA_TRY(mark(2, st));
-        if (!b->pairs2.empty()) {
+        if (!ladder_batch) {
             const int stride = exact_smem_int4(std::max(L.pair_R, L.R));
             const size_t smem = (size_t)wpb * stride * sizeof(int4);
             if (smem > nrl::kMaxDynShared) return fail(NR_ERR_ARG, "launch needs %zu bytes of shared memory", smem);
@@ -968,11 +1038,12 @@ int run_batch(nr_batch* b, cudaStream_t st) {
         if (!b->pairs3.empty()) {
             // reads whose selection hinges on a tie the 16-bit words cannot order: 32-bit flag ladder, count on the device
             CUDA_TRY(mark(4, st));
-            if ((rc = launch_rest(b, st, k, b->d_redo, 0, std::min(g_ctx.sm_count, 2 * L.n_pairs), L.redo_R,
+            if ((rc = launch_rest(b, st, k, b->d_redo, 0, std::max(1, std::min(g_ctx.sm_count, 2 * L.n_pairs)), L.redo_R,
                                   b->d_counters + 2, b->d_counters + 3))) return rc;
             CUDA_TRY(mark(5, st));
             b->timed[2] = timing;
             CUDA_TRY(cudaMemcpyAsync(b->h_redo_count, b->d_counters + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(b->h_redo_count + 1, b->d_counters + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
             ++launches;
         }
     } else if (L.count) {
@@ -995,15 +1066,19 @@ int run_batch(nr_batch* b, cudaStream_t st) {
     }
     CUDA_TRY(cudaEventRecord(b->ev_done, st));
     b->stats.kernel_launches = launches;
+    b->long_redone = false;
     b->ran = true;
     return NR_OK;
 }
+
+int redo_long_reads(nr_batch* b);
 
 int fetch_raw(nr_batch* b) {
     if (!b->ran) return fail(NR_ERR_ARG, "batch was not run");
     CUDA_TRY(cudaEventSynchronize(b->ev_done));         // kernel + the copy nr_batch_run queued behind it
     if (b->h_spin && *b->h_spin)
         return fail(NR_ERR_CUDA, "a stripe of a long read gave up waiting for the stripe above it; the results of this batch are not valid");
+    if (b->n_long_pairs && b->h_redo_count && b->h_redo_count[1] > 0 && !b->long_redone) return redo_long_reads(b);
     return NR_OK;
 }
 
@@ -1266,6 +1341,50 @@ nr_batch* new_batch(const nr_scoring_t* sc, BatchKind kind) {
     b->flag = kind == KIND_ROUND3 && mode >= 2;
     b->pair = kind == KIND_ROUND3 && mode == 3;
     return b;
+}
+
+// Paired round 3, long reads: a read whose selection hinges on a tie between a marked and an unmarked candidate (the
+// 16-bit words carry no coordinates to order them) is rescored on 32-bit flag words.  For reads of one stripe the device
+// does that itself (redo launch); for the stripes of long reads the scratch would have to exist up front for every long
+// read, so the (rare: none in any of the five configs' data) cases come back as a list and are rescored here: a batch of
+// their own over the same packed reads and templates, the 32-bit ladder, results merged into this batch's records.
+int redo_long_reads(nr_batch* b) {
+    const int cnt = b->h_redo_count[1];
+    std::vector<int32_t> tids((size_t)cnt);
+    cudaStream_t st = b->run_stream ? b->run_stream : g_ctx.stream;
+    CUDA_TRY(cudaMemcpyAsync(tids.data(), b->d_redo + b->ltasks.size(), sizeof(int32_t) * (size_t)cnt, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    nr_batch* t = new_batch(&b->sc, KIND_ROUND3);
+    if (!t) return g_code;
+    t->ladder = true; t->flag = true; t->pair = false;          // mode 2 whatever the process-wide ladder mode says
+    t->qsrc = b->qsrc;
+    if (t->qsrc) ++t->qsrc->refs;
+    t->pool.words = b->pool.words;                              // the templates (and the reads, when the batch owns them)
+    t->lregs = b->lregs;
+    t->regions = b->regions;
+    t->rung_off.push_back(0);
+    for (int j = 0; j < cnt; ++j) {
+        if (tids[j] < 0 || tids[j] >= (int)b->ltasks.size()) { nr_batch_destroy(t); return fail(NR_ERR_CUDA, "corrupt redo list"); }
+        nr::LadderTask lt = b->ltasks[tids[j]];
+        lt.read = j;
+        lt.out_off = (int32_t)t->rung_off.back();
+        lt.pad = 0;
+        t->ltasks.push_back(lt);
+        t->lt_src.push_back(-1);
+        t->rung_off.push_back(t->rung_off.back() + (lt.kmax - lt.kmin + 1));
+        t->kmin.push_back(lt.kmin); t->kmax.push_back(lt.kmax);
+        t->read_region.push_back(0);
+    }
+    t->n_reads = cnt;
+    t->n_out = (size_t)t->rung_off.back();
+    int rc = plan_batch(t);
+    if (!rc) rc = run_batch(t, st);
+    if (!rc) rc = fetch_raw(t);
+    if (!rc)
+        for (int j = 0; j < cnt; ++j) b->h_sel[b->ltasks[tids[j]].read] = t->h_sel[j];
+    nr_batch_destroy(t);
+    if (!rc) b->long_redone = true;
+    return rc;
 }
 
 }  // namespace

@@ -751,6 +751,8 @@ struct RestArgs {
     int* flags;
     int* spin;                  // set to 1 by a warp that gave up waiting for another stripe (see wait_cols)
     int epoch;
+    int32_t* redo_long;         // paired round 3: long reads whose selection the 16-bit words cannot decide (task indices;
+    int* redo_long_count;       // the host rescoring them on 32-bit words, nr_api.cu)
 };
 
 template <int R, class SC>

@@ -135,6 +135,17 @@ struct Sweep {
     int* spin;
     int4 bcur;
     ulonglong2 bnxt;
+    // MULTI, forward sweep of a long pair: the junction vectors come from the backward stripes (global `bstage`,
+    // [state][reversed row] of two-half words) once all of them are done; tokens travel between the stripes as tagged
+    // 16-byte entries like those of nr_kernels.cuh
+    const ulonglong2* tok_in;
+    ulonglong2* tok_out;
+    const u32* bstage;
+    int b_stride, brow0;           // words per state plane; first forward row of this stripe's lane 0
+    const int* bdone;
+    int bdone_need;
+    bool late_pending;
+    u32* bsm_w;
     const uint4* prof;
     const uint32_t* twords;
     int t_len, lane;
@@ -192,6 +203,7 @@ struct Sweep {
         if (MULTI) {
             bcur = make_int4(0, 0, 0, 0); bnxt = make_ulonglong2(0ull, 0ull);
             if (top) bnxt = load_bnd(&bnd_in[lane < t_len ? lane : t_len - 1]);      // validated when it is taken over
+            late_pending = MODE == kPF;
         }
     }
 
@@ -256,6 +268,37 @@ struct Sweep {
             E2[r] = __viaddmax_u16x2(E2[r], pk(-1), __vminu2(E2[r], FLOOR));
         }
         hup_prev = __viaddmax_u16x2(hup_prev, pk(-1), FLOOR);
+    }
+
+    // MULTI forward sweep: fetch this stripe's junction vectors when the sweep reaches its first junction column, so that
+    // the forward stripes run beside the backward ones.  Forward row i of read A is reversed row q_a - 2 - i (B: q_b - 2 - i).
+    __device__ __forceinline__ void late_load() {
+        wait_cols(bdone, bdone_need, lane, spin);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int idx0 = brow0 + lane * R + r;
+            const int ia = q_a - 2 - idx0, ib = q_b - 2 - idx0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const u32 da = c == 0 ? (idx0 < q_a ? (u32)kBias : 0u) : 0u, db = c == 0 ? (idx0 < q_b ? (u32)kBias : 0u) : 0u;
+                const u32 a = ia >= 0 ? __ldcg(&bstage[c * b_stride + ia]) >> 16 : da;
+                const u32 b = ib >= 0 ? __ldcg(&bstage[c * b_stride + ib]) & 0xffffu : db;
+                bsm_w[(c * R + r) * 32 + lane] = (a << 16) | b;
+            }
+        }
+        __syncwarp();
+        late_pending = false;
+    }
+
+    // MULTI backward sweep, after the stripe: H of the last column and the gap states that entered it, by reversed row
+    __device__ __forceinline__ void store_stage(u32* stage, int stride, int row0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = row0 + lane * R + r;
+            __stcg(&stage[0 * stride + i], H[r]);
+            __stcg(&stage[1 * stride + i], E1[r] + pk(kRefund1));
+            __stcg(&stage[2 * stride + i], E2[r] + pk(kRefund2));
+        }
     }
 
     // kPB, after the sweep: the junction vectors.  Every lane still holds, for its R rows of the reversed reads, H of the
@@ -363,13 +406,27 @@ struct Sweep {
                 best = cm;
             }
             if (zone && jj + 1 == jnext) {
-                if (lane == 0) { tP = 0; tJ = 0; }
+                if (lane == 0) {
+                    tP = 0; tJ = 0;
+                    if (MULTI && top) {     // both 64-bit elements of the token carry the tag in their upper half
+                        ulonglong2 t = load_tok(&tok_in[kcnt]);
+                        for (int tries = 0; (int)(t.x >> 32) != tag_in || (int)(t.y >> 32) != tag_in; ++tries) {
+                            if (tries > kSpinLimit) { *spin = 1; break; }
+                            if (tries > 3) __nanosleep(32);
+                            t = load_tok(&tok_in[kcnt]);
+                        }
+                        tP = (u32)t.x; tJ = (u32)t.y;
+                    }
+                }
                 // rung 0's junction column is the last marked column: every forward part that scores started inside
                 // but is marked only after this step (candidates with an empty forward part are the R-only class again)
                 const u32 jv = jj == mark_col ? jhi - kOnes : jhi;
                 tokP = __vmaxu2(tP, best);
                 tokJ = __vmaxu2(tJ, jv);
-                if (lane == 31) rung_out[kcnt] = make_uint2(tokP, tokJ);
+                if (lane == 31) {
+                    if (MULTI && bot) __stcg(&tok_out[kcnt], make_ulonglong2(tokP | ((u64)(unsigned)tag_out << 32), tokJ | ((u64)(unsigned)tag_out << 32)));
+                    else rung_out[kcnt] = make_uint2(tokP, tokJ);
+                }
                 jnext += m;
                 ++kcnt;
             }
@@ -381,19 +438,23 @@ struct Sweep {
     __device__ __forceinline__ void slow_until(int& st, int end, u32 one, unsigned four) {
 #pragma unroll 1
         for (; st < end; ++st) {
+            if (MULTI && MODE == kPF && late_pending && st >= zone_start) late_load();
             if ((st & 15) == 0) refill();
             step<false, true>(st, one, four);
         }
     }
 
+    // steps per trip of the guard-free loop: the stripes of long pairs in round 3 (three loop variants per warp mix on
+    // an SM, bound by instruction fetch like their 32-bit counterparts, nr_kernels.cuh) run one, everything else four
+    static constexpr int kUnroll = (MULTI && MODE != kP2) ? 1 : 4;
     template <bool TRACK, bool SPECIAL = false>
     __device__ __forceinline__ void fast_until(int& st, int end, u32 one, unsigned four) {
         for (; st + 16 <= end; st += 16) {       // st is a multiple of 16 here
             refill();
 #pragma unroll 1
-            for (int b = 0; b < 16; b += 4) {
+            for (int b = 0; b < 16; b += kUnroll) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) step<true, TRACK, SPECIAL>(st + b + u, one, four);
+                for (int u = 0; u < kUnroll; ++u) step<true, TRACK, SPECIAL>(st + b + u, one, four);
             }
         }
     }
@@ -433,6 +494,7 @@ struct Sweep {
             // plain steps up to the first junction / marked column, then guard-free steps that look for both
             const int first = min(zone_start, mc >= 0 ? mc : zone_start);
             fast_until<true>(st, min(inside_end, (first >> 4) << 4), one, four);
+            if (MULTI && late_pending && st + 16 <= inside_end) late_load();      // the guard-free zone steps follow
             fast_until<true, true>(st, inside_end, one, four);
         }
         slow_until(st, nsteps, one, four);
@@ -668,6 +730,48 @@ __device__ __forceinline__ void rung_of(u32 P, u32 J, u32 rc, int& score, bool& 
     unmarked = np & 1u;
 }
 
+// The per-read selection over a pair's rung tokens (nanoRepeat_bam.py:423-431); reads whose result hinges on a tie the
+// 16-bit words cannot order are appended to redo[] (entries of ladder_kernel's order[]; long pairs: task indices for
+// the host, see nr_api.cu).
+__device__ __forceinline__ void pair3_select(const Pair3& pt, const LadderTask& ta, const LadderTask& tb, int kmin, u32 rcand,
+                                             const uint2* rungs, int lane, int min_score, int4* sel, int* redo_count, int32_t* redo,
+                                             int redo_shift) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int tid = half ? pt.b : pt.a;
+        if (tid < 0) continue;
+        const LadderTask& tk = half ? tb : ta;
+        const u32 rc = half ? (rcand & 0xffffu) : (rcand >> 16);
+        int top = 0;
+        for (int k = tk.kmin + lane; k <= tk.kmax; k += 32) {
+            const uint2 t = rungs[k - kmin];
+            int s; bool ir, um;
+            rung_of(half ? (t.x & 0xffffu) : (t.x >> 16), half ? (t.y & 0xffffu) : (t.y >> 16), rc, s, ir, um);
+            if (s >= min_score) top = max(top, s);
+        }
+        top = __reduce_max_sync(kFull, top);
+        int n = 0, sum = 0, unsure = 0;
+        if (top > 0) {
+            for (int k = tk.kmin + lane; k <= tk.kmax; k += 32) {
+                const uint2 t = rungs[k - kmin];
+                int s; bool ir, um;
+                rung_of(half ? (t.x & 0xffffu) : (t.x >> 16), half ? (t.y & 0xffffu) : (t.y >> 16), rc, s, ir, um);
+                if (s == top && ir) {
+                    if (um) unsure = 1;
+                    else { ++n; sum += k; }
+                }
+            }
+        }
+        n = __reduce_add_sync(kFull, n);
+        sum = __reduce_add_sync(kFull, sum);
+        unsure = __any_sync(kFull, unsure);
+        if (lane == 0) {
+            sel[tk.read] = make_int4(top, n, sum, 0);
+            if (unsure) redo[atomicAdd(redo_count, 1)] = tid << redo_shift;
+        }
+    }
+}
+
 template <int R>
 __device__ __forceinline__ void pair3_task(const Pair3& pt, const LadderTask* __restrict__ tasks,
                                            const uint32_t* __restrict__ qpool, const uint32_t* __restrict__ pool,
@@ -715,41 +819,109 @@ __device__ __forceinline__ void pair3_task(const Pair3& pt, const LadderTask* __
         sw.run(one, four, sw.jnext - 1 - sw.col0);
     }
     __syncwarp();
-    // selection per read (nanoRepeat_bam.py:423-431) over its own rungs
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int tid = half ? pt.b : pt.a;
-        if (tid < 0) continue;
-        const LadderTask& tk = half ? tb : ta;
-        const u32 rc = half ? (rcand & 0xffffu) : (rcand >> 16);
-        int top = 0;
-        for (int k = tk.kmin + lane; k <= tk.kmax; k += 32) {
-            const uint2 t = rungs[k - kmin];
-            int s; bool ir, um;
-            rung_of(half ? (t.x & 0xffffu) : (t.x >> 16), half ? (t.y & 0xffffu) : (t.y >> 16), rc, s, ir, um);
-            if (s >= min_score) top = max(top, s);
-        }
-        top = __reduce_max_sync(kFull, top);
-        int n = 0, sum = 0, unsure = 0;
-        if (top > 0) {
-            for (int k = tk.kmin + lane; k <= tk.kmax; k += 32) {
-                const uint2 t = rungs[k - kmin];
-                int s; bool ir, um;
-                rung_of(half ? (t.x & 0xffffu) : (t.x >> 16), half ? (t.y & 0xffffu) : (t.y >> 16), rc, s, ir, um);
-                if (s == top && ir) {
-                    if (um) unsure = 1;
-                    else { ++n; sum += k; }
-                }
-            }
-        }
-        n = __reduce_add_sync(kFull, n);
-        sum = __reduce_add_sync(kFull, sum);
-        unsure = __any_sync(kFull, unsure);
-        if (lane == 0) {
-            sel[tk.read] = make_int4(top, n, sum, 0);
-            if (unsure) redo[atomicAdd(redo_count, 1)] = tid << kCodeBits;     // an entry of ladder_kernel's order[]
-        }
+    pair3_select(pt, ta, tb, kmin, rcand, rungs, lane, min_score, sel, redo_count, redo, kCodeBits);
+}
+
+// Long pairs in round 3.  pt.pad[0] = the pair's CoopInfo; scratch (int4 units from ci.data_off): boundary rows a, b of the
+// backward sweep | a, b of the forward sweep | the backward stripes' junction state, 3 planes of ci.b_stride words |
+// token rows a, b.  Flag words: [2S] backward stripes done, [2S + 2] / [2S + 3] the R-only best of read A / read B.
+template <int R>
+__device__ __noinline__ void pair3_bwd_stripe(const Pair3& pt, int s, const LadderTask* __restrict__ tasks,
+                                              const uint32_t* __restrict__ qpool, const uint32_t* __restrict__ pool,
+                                              const LadderRegion* __restrict__ regs, const RestArgs& ra, uint4* prof, int lane,
+                                              u32 one, unsigned four) {
+    const CoopInfo ci = ra.coop[pt.pad[0]];
+    const int S = ci.n_stripes;
+    int* F = ra.flags + ci.flag_off;
+    ulonglong2* bnd_a = reinterpret_cast<ulonglong2*>(ra.scratch + ci.data_off);
+    ulonglong2* bnd_b = bnd_a + ci.bnd_stride;
+    u32* stage = reinterpret_cast<u32*>(ra.scratch + ci.data_off + 4 * ci.bnd_stride);
+    const LadderTask ta = tasks[pt.a], tb = tasks[pt.b];
+    const LadderRegion reg = regs[ta.region];
+    __syncwarp();
+    build_profile<R>(prof, qpool + ta.q_word, ta.q_len, qpool + tb.q_word, tb.q_len, s * 32 * R + lane * R, lane, true);
+    __syncwarp();
+    Sweep<R, kPB, true> sw;
+    sw.prof = prof; sw.twords = pool + reg.rev_word; sw.t_len = reg.n_right; sw.lane = lane;
+    sw.mark_col = -1; sw.q_a = ta.q_len; sw.q_b = tb.q_len;
+    sw.col0 = 0; sw.resume = nullptr; sw.save = nullptr; sw.save_col = -1;
+    sw.top = s > 0; sw.bot = s + 1 < S;
+    sw.bnd_in = (s & 1) ? bnd_a : bnd_b; sw.bnd_out = (s & 1) ? bnd_b : bnd_a;
+    sw.tag_in = stripe_tag(ra.epoch, s - 1); sw.tag_out = stripe_tag(ra.epoch, s); sw.spin = ra.spin;
+    sw.run(one, four, 0);
+    sw.store_stage(stage, ci.b_stride, s * 32 * R);
+    const u32 ba = __reduce_max_sync(kFull, sw.best >> 16), bb = __reduce_max_sync(kFull, sw.best & 0xffffu);
+    __syncwarp();                       // every lane's junction state is stored
+    if (lane == 0) {
+        unsigned* K = reinterpret_cast<unsigned*>(F + 2 * S + 2);
+        atomicMax(&K[0], ba);
+        atomicMax(&K[1], bb);
+        __threadfence();
+        atomicAdd(F + 2 * S, 1);
     }
+}
+
+template <int R>
+__device__ __noinline__ void pair3_fwd_stripe(const Pair3& pt, int s, const LadderTask* __restrict__ tasks,
+                                              const uint32_t* __restrict__ qpool, const uint32_t* __restrict__ pool,
+                                              const LadderRegion* __restrict__ regs, const RestArgs& ra, uint4* prof, int lane,
+                                              u32 one, unsigned four, int min_score, uint2* prung, int4* sel, int* redo_count,
+                                              int32_t* redo) {
+    const CoopInfo ci = ra.coop[pt.pad[0]];
+    const int S = ci.n_stripes;
+    int* F = ra.flags + ci.flag_off;
+    ulonglong2* bnd_a = reinterpret_cast<ulonglong2*>(ra.scratch + ci.data_off + 2 * ci.bnd_stride);
+    ulonglong2* bnd_b = bnd_a + ci.bnd_stride;
+    const u32* stage = reinterpret_cast<const u32*>(ra.scratch + ci.data_off + 4 * ci.bnd_stride);
+    ulonglong2* tok_a = reinterpret_cast<ulonglong2*>(ra.scratch + ci.data_off + 4 * ci.bnd_stride + (3 * ci.b_stride + 3) / 4);
+    ulonglong2* tok_b = tok_a + ci.tok_stride;
+    const LadderTask ta = tasks[pt.a], tb = tasks[pt.b];
+    const LadderRegion reg = regs[ta.region];
+    const int kmin = min(ta.kmin, tb.kmin), kmax = max(ta.kmax, tb.kmax);
+    u32* bsm = reinterpret_cast<u32*>(prof + StripeCfg<R>::PROF_INT4);
+    uint2* rungs = prung + pt.rung_off;
+    __syncwarp();
+    build_profile<R>(prof, qpool + ta.q_word, ta.q_len, qpool + tb.q_word, tb.q_len, s * 32 * R + lane * R, lane, false);
+    __syncwarp();
+    Sweep<R, kPF, true> sw;
+    sw.prof = prof; sw.twords = pool + reg.fwd_word; sw.t_len = reg.n_left + reg.m * kmax; sw.lane = lane;
+    sw.mark_col = reg.n_left - 1; sw.bsm = bsm; sw.bsm_w = bsm; sw.rung_out = rungs;
+    sw.m = reg.m; sw.jnext = reg.n_left + reg.m * kmin; sw.kcnt = 0;
+    sw.q_a = ta.q_len; sw.q_b = tb.q_len;
+    sw.save = nullptr; sw.save_col = -1; sw.col0 = 0; sw.resume = nullptr;
+    sw.top = s > 0; sw.bot = s + 1 < S;
+    sw.bnd_in = (s & 1) ? bnd_a : bnd_b; sw.bnd_out = (s & 1) ? bnd_b : bnd_a;
+    sw.tok_in = (s & 1) ? tok_a : tok_b; sw.tok_out = (s & 1) ? tok_b : tok_a;
+    sw.tag_in = stripe_tag(ra.epoch, s - 1); sw.tag_out = stripe_tag(ra.epoch, s); sw.spin = ra.spin;
+    sw.bstage = stage; sw.b_stride = ci.b_stride; sw.brow0 = s * 32 * R;
+    sw.bdone = F + 2 * S; sw.bdone_need = S;
+    sw.run(one, four, sw.jnext - 1);
+    if (s == S - 1) {
+        // the last rows finalised every rung: the selection of both reads (the R-only class from the backward stripes,
+        // which are all done: this stripe waited for them before its first junction column)
+        __syncwarp();
+        if (sw.late_pending) wait_cols(sw.bdone, sw.bdone_need, lane, ra.spin);
+        const unsigned* K = reinterpret_cast<const unsigned*>(F + 2 * S + 2);
+        const u32 rcand = pk2((int)__ldcg(&K[0]) + kBias + 1, (int)__ldcg(&K[1]) + kBias + 1);
+        pair3_select(pt, ta, tb, kmin, rcand, rungs, lane, min_score, sel, ra.redo_long_count, ra.redo_long, 0);
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void pair3_stripe_dispatch(int r, const Pair3& pt, int code, const LadderTask* __restrict__ tasks,
+                                                      const uint32_t* __restrict__ qpool, const uint32_t* __restrict__ pool,
+                                                      const LadderRegion* __restrict__ regs, const RestArgs& ra, uint4* prof,
+                                                      int lane, u32 one, unsigned four, int min_score, uint2* prung, int4* sel,
+                                                      int* redo_count, int32_t* redo) {
+    if constexpr (is_coop_height(R))
+        if (r == R) {
+            if (code < kCodeFwd) pair3_bwd_stripe<R>(pt, code - 1, tasks, qpool, pool, regs, ra, prof, lane, one, four);
+            else pair3_fwd_stripe<R>(pt, code - kCodeFwd, tasks, qpool, pool, regs, ra, prof, lane, one, four, min_score, prung, sel,
+                                     redo_count, redo);
+            return;
+        }
+    if constexpr (R < kMaxRLadder)
+        pair3_stripe_dispatch<R + 1>(r, pt, code, tasks, qpool, pool, regs, ra, prof, lane, one, four, min_score, prung, sel, redo_count, redo);
 }
 
 template <int R>
@@ -782,7 +954,14 @@ pair_ladder_kernel(const Pair3* __restrict__ pairs, Deal dl, const LadderTask* _
         const int i = next_item(dl, first, counter);
         if (i < 0) break;
         if (i < ra.n_order) {
-            ladder_entry<true, kMaxRLadder>(ra.order[i], tasks, qpool, pool, regs, sc, ra, reinterpret_cast<int4*>(prof), lane, out, sel);
+            const int e = ra.order[i];
+            if (e & kPairEntry) {           // a stripe of a pair of long reads: (pair index << 7) | (1 + s backward, 64 + s forward)
+                const Pair3 mp = pairs[(e & ~kPairEntry) >> kCodeBits];
+                pair3_stripe_dispatch<kMinR>(mp.R, mp, e & ((1 << kCodeBits) - 1), tasks, qpool, pool, regs, ra, prof, lane, (u32)sc.one,
+                                             sc.four, sc.min_score, prung, sel, redo_count, redo);
+            } else {
+                ladder_entry<true, kMaxRLadder>(e, tasks, qpool, pool, regs, sc, ra, reinterpret_cast<int4*>(prof), lane, out, sel);
+            }
             continue;
         }
         const Pair3 pt = pairs[i - ra.n_order];

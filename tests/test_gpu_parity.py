@@ -845,3 +845,34 @@ def test_round2_pairs_of_long_reads_equal_oracle(engine, oracle, rows, monkeypat
         assert (tend[sl][~spans] < max(n_left, 1)).all()
         live = (ref["score"] > 0) & spans
         assert np.array_equal(inside[sl][live], (ref["tstart"] <= n_left)[live])
+
+
+def test_long_pairs_undecidable_ties_are_rescored(engine, oracle):
+    """The same crafted ties as test_paired_ladder_undecidable_ties_are_rescored, on reads of 600 ... 1 000 bases: pairs
+    of long reads run stripe by stripe on u16x2 words; a read whose selection hinges on a tie between a marked and an
+    unmarked candidate comes back on the host's redo list and is rescored on 32-bit words.  Results == mode 2 == oracle."""
+    rng = random.Random(78)
+    left, right, motif = _rand_seq(rng, 50), _rand_seq(rng, 60), "CAG"
+    cores, kmin, kmax = [], [], []
+    for i in range(26):
+        k = rng.randint(190, 310)
+        lf = ["", left[-1:], left[-2:], _rand_seq(rng, 3), left[-30:]][i % 5]
+        rf = [right[:20], right[:1], "", right[:40]][i % 4]
+        cores.append(lf + motif * k + rf)
+        kmin.append(max(0, k - rng.randint(0, 4))); kmax.append(k + rng.randint(0, 4))
+    kmin, kmax = np.array(kmin, np.int32), np.array(kmax, np.int32)
+    sc = engine.get_preset("ont")
+    sc.min_dp_score = 1
+    ref, roff = oracle.align_ladders(cores, left, right, motif, kmin, kmax, n_threads=oracle.max_threads())
+    try:
+        for mode in (3, 2):
+            engine.set_ladder_mode(mode)
+            with engine.Batch.round3(sc, left, right, motif, cores, kmin, kmax) as b:
+                b.run()
+                _assert_flag_ladder(b, ref, roff, kmin, 50, 60, 3, 1, f"long tie cases, mode {mode}", rungs_too=mode == 2)
+                if mode == 3:
+                    assert b.launch_info()["n_pairs"] == 0 and b.stats()["executed_cells"] > 0      # all reads in long pairs
+                    b.run()                                                                        # and again over the same scratch
+                    _assert_flag_ladder(b, ref, roff, kmin, 50, 60, 3, 1, "long tie cases, second launch", rungs_too=False)
+    finally:
+        engine.set_ladder_mode(3)
