@@ -1850,8 +1850,19 @@ int estimate_regions(const nr_scoring_t* sc, int fast_mode, int n_regions, const
         if (T_out) T_out[g] = t;
     }
     // ---- groups of regions, software-pipelined: while the GPU scores one group the host packs the next ----
-    constexpr long long kMinReads = 4096;
-    const int n_groups = (int)std::max<long long>(1, std::min<long long>(8, total / kMinReads));
+    // Short reads: groups of >= 4096 reads, so that packing / planning / selection of one group hide behind the kernels
+    // of another.  Long reads (cores of a kilobase and more on average) are the opposite case: the host work is
+    // negligible beside the kernels, and every launch pays the serial chain of its longest read's stripes once, so the
+    // whole call is one group.
+    // (measured on the 60 000-read slice of config 3: groups of 16 384 reads 49 ms end to end, of 4 096 reads 63 ms --
+    // a launch of 2 500 pairs on 2 368 warp slots takes as long as one of 4 700; on config 2's 10 000 reads two groups of
+    // 5 000 beat one of 10 000 by 0.3 ms)
+    long long kMinReads = total >= 32768 ? 16384 : 4096;
+    if (const char* e = getenv("NR_GROUP_READS")) kMinReads = std::max(256, atoi(e));      // tuning
+    long long total_bases = 0;
+    for (int g = 0; g < n_regions; ++g) total_bases += regs[g].reads_len;
+    const bool long_reads = total > 0 && total_bases / total > 1000;
+    const int n_groups = long_reads ? 1 : (int)std::max<long long>(1, std::min<long long>(8, total / kMinReads));
     std::vector<Group> groups;
     {
         const double target = (double)total / n_groups;

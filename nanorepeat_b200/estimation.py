@@ -339,7 +339,16 @@ _POOL = None
 def _chunks(rrs):
     """Contiguous chunks of regions of at least CHUNK_MIN_READS reads each, at most 6."""
     total = sum(len(rr.read_dict) for rr in rrs)
-    n = max(1, min(6, total // CHUNK_MIN_READS))
+    # a mid-sized call (config 2: two regions of 5 000 reads) gains from two calls in flight; a big one is cut into groups
+    # of 16 384 reads inside the library, where more and smaller launches only cost (measured: 49 against 63-72 ms on
+    # config 3's 60 000-read slice)
+    n = max(1, min(6, total // CHUNK_MIN_READS)) if total < 4 * CHUNK_MIN_READS else 1
+    if n > 1:
+        # long reads (a kilobase and more on average, judged on a sample): the kernels dwarf the Python side and every
+        # launch pays the serial chain of its longest read's stripes, so one call with everything is the fastest
+        sample = [len(c) for rr in rrs[::max(1, len(rrs) // 16)] for c in list(rr.read_core_seq_dict.values())[:4]]
+        if sample and sum(sample) / len(sample) > 1000:
+            n = 1
     if n == 1:
         return [rrs]
     out, cur, acc = [], [], 0
