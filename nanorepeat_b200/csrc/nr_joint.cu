@@ -2,6 +2,7 @@
 // (read, template) task in one DP (nr_window_kernel.cuh).  C ABI: nr_window_tasks, nr_joint_grid.
 #include "nr_internal.h"
 #include "nr_window_kernel.cuh"
+#include "nr_window_ladder.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -107,6 +108,92 @@ int run_window_tasks(const nr_scoring_t* sc, std::vector<nrw::WinTask>& tasks, c
     return NR_OK;
 }
 
+// Device and pinned buffers of one call, given back to the caching allocator on scope exit.
+struct Bufs {
+    struct One { void* p; size_t bytes; bool pinned; };
+    std::vector<One> all;
+    int get(void** p, size_t bytes, bool pinned) {
+        *p = nullptr;
+        const int rc = nri::alloc(p, bytes, pinned);
+        if (rc == NR_OK) all.push_back({*p, bytes, pinned});
+        return rc;
+    }
+    ~Bufs() { for (const One& b : all) nri::release(b.p, b.bytes, b.pinned); }
+};
+
+nrw::WinScore window_score_words(const nr_scoring_t* sc) {
+    nrw::WinScore k;
+    k.match = sc->match << 16; k.mismatch = -(sc->mismatch << 16); k.ambiguous = -(sc->ambiguous << 16);
+    k.open1 = -((sc->gap_open1 + sc->gap_ext1) << 16); k.ext1 = -(sc->gap_ext1 << 16);
+    k.open2 = -((sc->gap_open2 + sc->gap_ext2) << 16); k.ext2 = -(sc->gap_ext2 << 16);
+    return k;
+}
+
+// The shared-sweep path (nr_window_ladder.cuh): backward tasks, then forward tasks; res[out_off + j] of every forward task.
+int run_ladder_tasks(const nr_scoring_t* sc, const std::vector<nrw::LadBwdTask>& btasks, std::vector<nrw::LadFwdTask>& ftasks,
+                     const SeqPool& pool, size_t bvec_words, size_t n_out, int max_t, std::vector<int2>& res) {
+    const int nb = (int)btasks.size(), nf = (int)ftasks.size();
+    res.assign(n_out, make_int2(0, 0));
+    if (nf == 0) return NR_OK;
+    // long tasks first
+    std::sort(ftasks.begin(), ftasks.end(), [](const nrw::LadFwdTask& x, const nrw::LadFwdTask& y) {
+        const long long cx = (long long)x.q_len * (x.n_pre + (long long)x.m2 * (x.k2_first + (long long)x.k2_step * (x.k2_count - 1)));
+        const long long cy = (long long)y.q_len * (y.n_pre + (long long)y.m2 * (y.k2_first + (long long)y.k2_step * (y.k2_count - 1)));
+        return cx != cy ? cx > cy : x.out_off < y.out_off;
+    });
+    const int blocks_b = std::max(1, std::min(2 * nri::sm_count(), (nb + nrw::kWarps - 1) / nrw::kWarps));
+    const int blocks_f = std::max(1, std::min(2 * nri::sm_count(), (nf + nrw::kWarps - 1) / nrw::kWarps));
+    const int stride = 2 * ((max_t + 31) / 32 * 32);
+    const size_t scratch_bytes = sizeof(int4) * (size_t)std::max(blocks_b, blocks_f) * nrw::kWarps * stride;
+    const size_t out_bytes = sizeof(int2) * n_out;
+    Bufs bufs;
+    void *d_b = nullptr, *d_f = nullptr, *d_pool = nullptr, *d_out = nullptr, *d_scratch = nullptr, *d_counter = nullptr,
+         *d_bvec = nullptr, *d_ronly = nullptr, *h_out = nullptr;
+    int rc;
+    if ((rc = bufs.get(&d_b, sizeof(nrw::LadBwdTask) * nb, false)) || (rc = bufs.get(&d_f, sizeof(nrw::LadFwdTask) * nf, false)) ||
+        (rc = bufs.get(&d_pool, sizeof(uint32_t) * (pool.words.size() + 4), false)) || (rc = bufs.get(&d_out, out_bytes, false)) ||
+        (rc = bufs.get(&d_scratch, scratch_bytes, false)) || (rc = bufs.get(&d_counter, 256, false)) ||
+        (rc = bufs.get(&d_bvec, sizeof(int) * std::max<size_t>(bvec_words, 1), false)) ||
+        (rc = bufs.get(&d_ronly, sizeof(int) * nb, false)) || (rc = bufs.get(&h_out, out_bytes, true)))
+        return rc;
+    cudaStream_t st = nri::stream();
+    const nrw::WinScore k = window_score_words(sc);
+    const size_t smem_b = (size_t)nrw::kWarps * 8 * nrw::kRows * sizeof(int);
+    const size_t smem_f = (size_t)nrw::kWarps * (11 * nrw::kRows + 2 * nrw::kMaxK2) * sizeof(int);
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&]() {
+        attr_err = cudaFuncSetAttribute(nrw::ladder_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(nrw::ladder_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
+    });
+    JTRY(attr_err);
+    JTRY(cudaMemcpyAsync(d_b, btasks.data(), sizeof(nrw::LadBwdTask) * nb, cudaMemcpyHostToDevice, st));
+    JTRY(cudaMemcpyAsync(d_f, ftasks.data(), sizeof(nrw::LadFwdTask) * nf, cudaMemcpyHostToDevice, st));
+    JTRY(cudaMemcpyAsync(d_pool, pool.words.data(), sizeof(uint32_t) * pool.words.size(), cudaMemcpyHostToDevice, st));
+    JTRY(cudaMemsetAsync(d_counter, 0, 256, st));
+    int* counter = static_cast<int*>(d_counter);
+    nrw::ladder_bwd_kernel<<<blocks_b, 32 * nrw::kWarps, smem_b, st>>>(static_cast<const nrw::LadBwdTask*>(d_b), nb,
+                                                                     static_cast<const uint32_t*>(d_pool), k, static_cast<int4*>(d_scratch),
+                                                                     stride, counter, static_cast<int*>(d_bvec), static_cast<int*>(d_ronly));
+    JTRY(cudaGetLastError());
+    nrw::ladder_fwd_kernel<<<blocks_f, 32 * nrw::kWarps, smem_f, st>>>(static_cast<const nrw::LadFwdTask*>(d_f), nf,
+                                                                     static_cast<const nrw::LadBwdTask*>(d_b), static_cast<const uint32_t*>(d_pool),
+                                                                     k, static_cast<int4*>(d_scratch), stride, counter + 32,
+                                                                     static_cast<const int*>(d_bvec), static_cast<const int*>(d_ronly),
+                                                                     static_cast<int2*>(d_out));
+    JTRY(cudaGetLastError());
+    JTRY(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    const auto t_launch = std::chrono::steady_clock::now();
+    const cudaError_t e = cudaStreamSynchronize(st);
+    if (getenv("NR_TRACE"))
+        fprintf(stderr, "[nr trace] joint ladder: %d backward + %d forward tasks, %zu grid points, kernels + download %.1f us\n", nb, nf,
+                n_out, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_launch).count());
+    if (e != cudaSuccess) { cudaGetLastError(); return nri::fail_msg(NR_ERR_CUDA, cudaGetErrorString(e)); }
+    std::copy(static_cast<const int2*>(h_out), static_cast<const int2*>(h_out) + n_out, res.begin());
+    return NR_OK;
+}
+
 }  // namespace
 
 extern "C" int nr_window_tasks(const nr_scoring_t* sc, int32_t n_tasks, const char* const* queries, const int32_t* qlen,
@@ -156,14 +243,118 @@ extern "C" int nr_joint_grid(const nr_scoring_t* sc, const char* left, int32_t n
         if (read_len[r] < 0) return nri::fail_msg(NR_ERR_ARG, "nr_joint_grid: negative read length");
         read_word[r] = pool.add(reads[r], read_len[r], true);
     }
-    // one template per distinct grid point: left + motif1 * k1 + mid + motif2 * k2 + right (nanoRepeat_joint.py:351-374)
+    for (int i = 0; i < n_points; ++i) {
+        if (point_read[i] < 0 || point_read[i] >= n_reads || point_k1[i] < 0 || point_k2[i] < 0)
+            return nri::fail_msg(NR_ERR_ARG, "nr_joint_grid: bad grid point");
+        out[i].score = out[i].window_score = 0;
+        if (strand) strand[i] = 0;
+    }
+    const int win_a = std::max(n_left - 10, 0);                                                   // nanoRepeat_joint.py:448-451
+
+    // ---- shared sweeps (nr_window_ladder.cuh) for every read whose points are a full K1 x K2 grid with K2 an arithmetic
+    // progression (what joint.py's round-2 and round-3 grids are); everything else is scored template by template below.
+    std::vector<char> by_ladder(n_points, 0);
+    std::vector<int> point_slot(n_points, -1);                      // record of strand '+'; strand '-' follows at +k2_count ... see below
+    std::vector<int> point_slot_rev(n_points, -1);
+    std::vector<nrw::LadBwdTask> btasks;
+    std::vector<nrw::LadFwdTask> ftasks;
+    size_t bvec_words = 0, n_lad_out = 0;
+    int lad_max_t = std::max(1, (int)n_right);
+    const bool ladder_on = !getenv("NR_JOINT_RECTANGLES") && n_right >= 10 && n_left >= 1;
+    if (ladder_on && n_points > 0) {
+        std::string rev(right, (size_t)n_right);
+        std::reverse(rev.begin(), rev.end());
+        const long long rev_word = pool.add(rev.data(), n_right, false);
+        std::vector<std::vector<int>> of_read(n_reads);
+        for (int i = 0; i < n_points; ++i) of_read[point_read[i]].push_back(i);
+        std::map<std::pair<int, int>, long long> fwd_tpl;                 // (k1, k2 of the longest) -> word
+        std::string s;
+        for (int r = 0; r < n_reads && rev_word >= 0; ++r) {
+            const std::vector<int>& pts = of_read[r];
+            if (pts.empty() || read_len[r] < 1) continue;
+            std::vector<int> K1, K2;
+            for (int i : pts) { K1.push_back(point_k1[i]); K2.push_back(point_k2[i]); }
+            std::sort(K1.begin(), K1.end()); K1.erase(std::unique(K1.begin(), K1.end()), K1.end());
+            std::sort(K2.begin(), K2.end()); K2.erase(std::unique(K2.begin(), K2.end()), K2.end());
+            if (K2.size() > (size_t)nrw::kMaxK2) continue;
+            std::map<std::pair<int, int>, int> seen;
+            for (int i : pts) ++seen[{point_k1[i], point_k2[i]}];
+            if (seen.size() != K1.size() * K2.size()) continue;                      // not a full grid
+            const int k2_step = K2.size() > 1 ? K2[1] - K2[0] : 1;
+            bool arithmetic = true;
+            for (size_t j = 1; j < K2.size(); ++j) arithmetic = arithmetic && K2[j] - K2[j - 1] == k2_step;
+            if (!arithmetic) continue;
+            const long long t_max = (long long)n_left + (long long)m1 * K1.back() + n_mid + (long long)m2 * K2.back();
+            if (t_max + n_right > kMaxTlen || t_max + 10 - win_a > kMaxWindow ||
+                (long long)sc->match * std::min<long long>(read_len[r], t_max + n_right) > kMaxScore)
+                continue;                                                            // the rectangle path decides (and skips) these
+            bool ok = true;
+            std::vector<long long> words(K1.size());
+            for (size_t a = 0; a < K1.size() && ok; ++a) {
+                auto key = std::make_pair(K1[a], K2.back());
+                auto it = fwd_tpl.find(key);
+                if (it == fwd_tpl.end()) {
+                    s.assign(left, (size_t)n_left);
+                    for (int u = 0; u < K1[a]; ++u) s.append(motif1, (size_t)m1);
+                    s.append(mid ? mid : "", (size_t)n_mid);
+                    for (int u = 0; u < K2.back(); ++u) s.append(motif2, (size_t)m2);
+                    it = fwd_tpl.emplace(key, pool.add(s.data(), (int)s.size(), false)).first;
+                }
+                words[a] = it->second;
+                ok = words[a] >= 0;
+            }
+            if (!ok) continue;
+            const int b0 = (int)btasks.size();
+            for (int sd = 0; sd < 2; ++sd) {
+                nrw::LadBwdTask bt = {};
+                bt.q_word = (uint32_t)read_word[r]; bt.q_len = read_len[r];
+                bt.rev_word = (uint32_t)rev_word; bt.n_right = n_right;
+                bt.reverse = sd; bt.bvec_off = (int)bvec_words;
+                bvec_words += 3 * (size_t)read_len[r];
+                btasks.push_back(bt);
+            }
+            std::map<std::pair<int, int>, int> slot;                                 // (k1, k2) -> record of strand '+'
+            for (size_t a = 0; a < K1.size(); ++a)
+                for (int sd = 0; sd < 2; ++sd) {
+                    nrw::LadFwdTask ft = {};
+                    ft.q_word = (uint32_t)read_word[r]; ft.q_len = read_len[r];
+                    ft.t_word = (uint32_t)words[a];
+                    ft.n_pre = n_left + m1 * K1[a] + n_mid;
+                    ft.m2 = m2; ft.k2_first = K2[0]; ft.k2_step = k2_step; ft.k2_count = (int)K2.size();
+                    ft.win_a = win_a; ft.reverse = sd; ft.bwd = b0 + sd; ft.out_off = (int)n_lad_out;
+                    if (sd == 0) for (size_t j = 0; j < K2.size(); ++j) slot[{K1[a], K2[j]}] = (int)(n_lad_out + j);
+                    n_lad_out += K2.size();
+                    lad_max_t = std::max(lad_max_t, ft.n_pre + m2 * K2.back());
+                    ftasks.push_back(ft);
+                }
+            for (int i : pts) {
+                by_ladder[i] = 1;
+                point_slot[i] = slot[{point_k1[i], point_k2[i]}];
+                point_slot_rev[i] = point_slot[i] + (int)K2.size();
+            }
+        }
+    }
+    if (!ftasks.empty()) {
+        std::vector<int2> res;
+        if ((rc = run_ladder_tasks(sc, btasks, ftasks, pool, bvec_words, n_lad_out, lad_max_t, res))) return rc;
+        for (int i = 0; i < n_points; ++i) {
+            if (!by_ladder[i]) continue;
+            const int2 f = res[point_slot[i]], v = res[point_slot_rev[i]];
+            const bool rev = v.x > f.x || (v.x == f.x && v.y > f.y);
+            out[i].score = rev ? v.x : f.x;
+            out[i].window_score = rev ? v.y : f.y;
+            if (strand) strand[i] = rev ? 1 : 0;
+        }
+    }
+
+    // ---- one template per distinct remaining grid point: left + motif1 * k1 + mid + motif2 * k2 + right (nanoRepeat_joint.py:351-374)
     std::map<std::pair<int, int>, std::pair<long long, int>> tpl;      // (k1, k2) -> (word, length)
     std::vector<nrw::WinTask> tasks;
-    tasks.reserve((size_t)n_points * 2);
+    std::vector<int> task_point;
     std::string s;
     for (int i = 0; i < n_points; ++i) {
+        if (by_ladder[i]) continue;
         const int r = point_read[i], k1 = point_k1[i], k2 = point_k2[i];
-        if (r < 0 || r >= n_reads || k1 < 0 || k2 < 0) return nri::fail_msg(NR_ERR_ARG, "nr_joint_grid: bad grid point");
         auto key = std::make_pair(k1, k2);
         auto it = tpl.find(key);
         if (it == tpl.end()) {
@@ -179,15 +370,17 @@ extern "C" int nr_joint_grid(const nr_scoring_t* sc, const char* left, int32_t n
         nrw::WinTask t = {};
         t.q_word = (uint32_t)read_word[r]; t.q_len = read_len[r];
         t.t_word = tw < 0 ? 0u : (uint32_t)tw; t.t_len = tw < 0 ? 0 : tl;
-        t.win_a = std::max(n_left - 10, 0);                                                   // nanoRepeat_joint.py:448-451
+        t.win_a = win_a;
         t.win_b = std::min(n_left + m1 * k1 + n_mid + m2 * k2 + 10, tl);
         t.reverse = 0; tasks.push_back(t);
         t.reverse = 1; tasks.push_back(t);
+        task_point.push_back(i);
     }
     std::vector<nr_window_t> res(tasks.size());
     if ((rc = run_window_tasks(sc, tasks, pool, res.data(), nullptr))) return rc;
-    for (int i = 0; i < n_points; ++i) {
-        const nr_window_t f = res[2 * (size_t)i], v = res[2 * (size_t)i + 1];
+    for (size_t j = 0; j < task_point.size(); ++j) {
+        const int i = task_point[j];
+        const nr_window_t f = res[2 * j], v = res[2 * j + 1];
         // the better strand by (score, window score); '+' on a full tie
         const bool rev = v.score > f.score || (v.score == f.score && v.window_score > f.window_score);
         out[i] = rev ? v : f;

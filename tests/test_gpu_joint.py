@@ -112,3 +112,61 @@ def test_quantify_two_repeats_equals_oracle_driven_run(engine, oracle):
     close = sum(abs(float(got["size1"][i]) - truth[i][0]) <= 2 and abs(float(got["size2"][i]) - truth[i][1]) <= 2
                 for i in range(len(reads)) if got["size1"][i] is not None)
     assert close >= 18
+
+
+def _grid_points(rng, n_reads, k1_lists, k2_lists):
+    pr, p1, p2 = [], [], []
+    for r in range(n_reads):
+        for k1 in k1_lists[r]:
+            for k2 in k2_lists[r]:
+                pr.append(r); p1.append(k1); p2.append(k2)
+    return pr, p1, p2
+
+
+@pytest.mark.parametrize("n_left,n_right", [(1000, 1000), (300, 10), (7, 40)])
+def test_joint_grid_shared_sweeps_equal_rectangles(engine, oracle, n_left, n_right):
+    """nr_joint_grid scores full K1 x K2 grids with shared sweeps (nr_window_ladder.cuh); every grid point must equal the
+    rectangle of its own template (nr_window_tasks, both strands, better strand), and the CPU oracle on a sample."""
+    rng = random.Random(1000 * n_left + n_right)
+    sc = engine.get_preset("ont")
+    left, right, mid = _rs(rng, n_left), _rs(rng, n_right), "CAACAGCCGCCA"
+    m1, m2 = "CAG", "CCG"
+    reads, K1s, K2s = [], [], []
+    for i in range(36):
+        k1, k2 = rng.choice([17, 55, 3]), rng.choice([7, 10, 0])
+        amp = left[-rng.randint(1, 400):] + m1 * k1 + mid + m2 * k2 + right[:rng.randint(1, 400)]
+        read = _mut(rng, amp, rng.choice([0.02, 0.08, 0.15]))
+        if i % 7 == 3:
+            read = read[:len(read) // 2] + "N" + read[len(read) // 2 + 1:]
+        if i % 11 == 5:
+            read = _rs(rng, rng.randint(1, 700))                                    # unrelated read
+        reads.append(_revcomp(read) if i % 2 else read)
+        lo1, step1 = max(0, k1 - rng.randint(0, 12)), rng.choice([1, 1, 2, 5])
+        lo2, step2 = max(0, k2 - rng.randint(0, 6)), rng.choice([1, 1, 2, 3])
+        K1s.append([lo1 + step1 * j for j in range(rng.randint(1, 6))] if i % 5 else [lo1, lo1 + 1, lo1 + 7])
+        K2s.append([lo2 + step2 * j for j in range(rng.randint(1, 9))])
+    K2s[4] = [2, 3, 7]                                                               # not arithmetic: template by template
+    pr, p1, p2 = _grid_points(rng, len(reads), K1s, K2s)
+    pr += [0, 0]; p1 += [91, 92]; p2 += [1, 5]                                       # read 0 is no longer a full grid
+    got, strand = engine.joint_grid(sc, left, mid, right, m1, m2, reads, pr, p1, p2)
+    qs, ts, aa, bb, rv = [], [], [], [], []
+    for r, k1, k2 in zip(pr, p1, p2):
+        tpl = left + m1 * k1 + mid + m2 * k2 + right
+        a, b = max(n_left - 10, 0), min(n_left + 3 * k1 + len(mid) + 3 * k2 + 10, len(tpl))
+        for rev in (0, 1):
+            qs.append(reads[r]); ts.append(tpl); aa.append(a); bb.append(b); rv.append(rev)
+    rect = engine.window_tasks(qs, ts, aa, bb, sc, reverse=rv)
+    bad = []
+    for i in range(len(pr)):
+        f = (int(rect["score"][2 * i]), int(rect["window_score"][2 * i]))
+        v = (int(rect["score"][2 * i + 1]), int(rect["window_score"][2 * i + 1]))
+        exp, exp_strand = (v, 1) if v > f else (f, 0)
+        if (int(got["score"][i]), int(got["window_score"][i])) != exp or int(strand[i]) != exp_strand:
+            bad.append((i, pr[i], p1[i], p2[i], tuple(int(x) for x in got[i]), int(strand[i]), exp, exp_strand))
+    assert not bad, (len(bad), len(pr), bad[:8])
+    for i in rng.sample(range(len(pr)), 25):
+        tpl = left + m1 * p1[i] + mid + m2 * p2[i] + right
+        a, b = max(n_left - 10, 0), min(n_left + 3 * p1[i] + len(mid) + 3 * p2[i] + 10, len(tpl))
+        f = oracle.align_window(reads[pr[i]], tpl, a, b, reverse=False)
+        v = oracle.align_window(reads[pr[i]], tpl, a, b, reverse=True)
+        assert (int(got["score"][i]), int(got["window_score"][i])) == max(f, v), (i, tuple(got[i]), f, v)
