@@ -31,62 +31,82 @@ def choose_best_step_size(repeat_unit_size, count_ranges):
     return count_list[0][0]
 
 
+def _ranges_array(ranges):
+    """per read (min, max) or None -> (lo, hi, present) arrays"""
+    n = len(ranges)
+    lo, hi, ok = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64), np.zeros(n, dtype=bool)
+    for r, a in enumerate(ranges):
+        if a is not None:
+            lo[r], hi[r], ok[r] = a[0], a[1], True
+    return lo, hi, ok
+
+
+def _points_of(mask1, mask2, K1, K2):
+    """mask1[k1 index, read], mask2[k2 index, read] -> the (read, k1, k2) of every set pair, k1 outermost, then k2, then the
+    read: the order of the reference's three nested loops."""
+    i1, i2, r = np.nonzero(mask1[:, None, :] & mask2[None, :, :])
+    return r.astype(np.int32), K1[i1].astype(np.int32), K2[i2].astype(np.int32)
+
+
 def round2_grid_points(range1, range2, min1, max1, min2, max2, step1, step2):
     """nanoRepeat_joint.py:397-410.  range1 / range2: per read (min, max) of repeat 1 / 2 from the initial estimate
     (None: the read has none); the grid runs k1 = min1..max1 step step1, k2 = min2..max2 step step2 and a read is aligned
     at a point when min <= k < max for both repeats.  -> (point_read, point_k1, point_k2) in the reference's loop order."""
-    pr, p1, p2 = [], [], []
-    for k1 in range(min1, max1 + 1, step1):
-        for k2 in range(min2, max2 + 1, step2):
-            for r, (a, b) in enumerate(zip(range1, range2)):
-                if a is None or b is None:
-                    continue
-                if a[0] <= k1 < a[1] and b[0] <= k2 < b[1]:
-                    pr.append(r); p1.append(k1); p2.append(k2)
-    return pr, p1, p2
+    K1, K2 = np.arange(min1, max1 + 1, step1, dtype=np.int64), np.arange(min2, max2 + 1, step2, dtype=np.int64)
+    lo1, hi1, ok1 = _ranges_array(range1)
+    lo2, hi2, ok2 = _ranges_array(range2)
+    ok = ok1 & ok2
+    mask1 = (lo1[None, :] <= K1[:, None]) & (K1[:, None] < hi1[None, :]) & ok[None, :]
+    mask2 = (lo2[None, :] <= K2[:, None]) & (K2[:, None] < hi2[None, :])
+    return _points_of(mask1, mask2, K1, K2)
 
 
 def round3_grid_points(range1, range2, size1, size2, buffer1, buffer2):
     """nanoRepeat_joint.py:296-333: the unit-step grid around every read's coarse estimate (size1 / size2: per read the
     round-2 sizes, None when round 2 gave none), clipped to the read's initial ranges."""
-    s1 = [v for v, w in zip(size1, size2) if v is not None and w is not None]
-    s2 = [w for v, w in zip(size1, size2) if v is not None and w is not None]
-    if not s1:
-        return [], [], []
-    min_size1 = max(int(min(s1) - buffer1), 0)
-    max_size1 = int(max(s1) + buffer1 + 2)
-    min_size2 = max(int(min(s2) - buffer2), 0)
-    max_size2 = int(max(s2) + buffer2 + 2)
-    pr, p1, p2 = [], [], []
-    for k1 in range(min_size1, max_size1):
-        for k2 in range(min_size2, max_size2):
-            for r, (v, w) in enumerate(zip(size1, size2)):
-                if v is None or w is None:
-                    continue
-                if k1 < v - buffer1 or k1 >= v + buffer1 or k2 < w - buffer2 or k2 >= w + buffer2:
-                    continue
-                a, b = range1[r], range2[r]
-                if k1 < a[0] or k1 >= a[1] or k2 < b[0] or k2 >= b[1]:
-                    continue
-                pr.append(r); p1.append(k1); p2.append(k2)
-    return pr, p1, p2
+    n = len(size1)
+    have = np.array([v is not None and w is not None for v, w in zip(size1, size2)], dtype=bool)
+    empty = np.zeros(0, dtype=np.int32)
+    if not have.any():
+        return empty, empty, empty
+    v = np.array([float(x) if h else 0.0 for x, h in zip(size1, have)])
+    w = np.array([float(x) if h else 0.0 for x, h in zip(size2, have)])
+    min_size1 = max(int(v[have].min() - buffer1), 0)
+    max_size1 = int(v[have].max() + buffer1 + 2)
+    min_size2 = max(int(w[have].min() - buffer2), 0)
+    max_size2 = int(w[have].max() + buffer2 + 2)
+    K1, K2 = np.arange(min_size1, max_size1, dtype=np.int64), np.arange(min_size2, max_size2, dtype=np.int64)
+    lo1, hi1, _ok1 = _ranges_array([a if h else None for a, h in zip(range1, have)])
+    lo2, hi2, _ok2 = _ranges_array([b if h else None for b, h in zip(range2, have)])
+    k1c, k2c = K1[:, None], K2[:, None]
+    mask1 = (k1c >= (v - buffer1)[None, :]) & (k1c < (v + buffer1)[None, :]) & (k1c >= lo1[None, :]) & (k1c < hi1[None, :]) & have[None, :]
+    mask2 = (k2c >= (w - buffer2)[None, :]) & (k2c < (w + buffer2)[None, :]) & (k2c >= lo2[None, :]) & (k2c < hi2[None, :])
+    return _points_of(mask1, mask2, K1, K2)
 
 
 def estimate_two_repeats(n_reads, point_read, point_k1, point_k2, records, min_dp_score=80):
     """nanoRepeat_joint.py:427-478 on binary records: per read the grid point(s) with the highest window score among the
     points that have an alignment at all (minimap2 prints no line below -s); the two sizes are the means of the tied
-    points' k1 and of their k2, separately (np.mean, as at :471-472).  -> (size1, size2): lists with None for reads
-    without any alignment."""
+    points' k1 and of their k2, separately (np.mean, as at :471-472: an exact integer sum over a count).  -> (size1, size2):
+    lists with None for reads without any alignment."""
     size1, size2 = [None] * n_reads, [None] * n_reads
-    per_read = {}
-    for r, k1, k2, rec in zip(point_read, point_k1, point_k2, records):
-        if rec["score"] <= 0 or rec["score"] < min_dp_score:
-            continue
-        per_read.setdefault(int(r), []).append((int(rec["window_score"]), int(k1), int(k2)))
-    for r, rows in per_read.items():
-        top = max(s for s, _a, _b in rows)
-        size1[r] = np.mean([k1 for s, k1, _k2 in rows if s == top])
-        size2[r] = np.mean([k2 for s, _k1, k2 in rows if s == top])
+    pr = np.asarray(point_read, dtype=np.int64)
+    if len(pr) == 0:
+        return size1, size2
+    score = np.asarray(records["score"], dtype=np.int64)
+    win = np.asarray(records["window_score"], dtype=np.int64)
+    keep = (score > 0) & (score >= min_dp_score)
+    pr, win = pr[keep], win[keep]
+    k1, k2 = np.asarray(point_k1, dtype=np.int64)[keep], np.asarray(point_k2, dtype=np.int64)[keep]
+    top = np.full(n_reads, np.iinfo(np.int64).min, dtype=np.int64)
+    np.maximum.at(top, pr, win)
+    tied = win == top[pr]
+    cnt = np.bincount(pr[tied], minlength=n_reads)
+    sum1 = np.bincount(pr[tied], weights=k1[tied], minlength=n_reads)
+    sum2 = np.bincount(pr[tied], weights=k2[tied], minlength=n_reads)
+    for r in np.nonzero(cnt)[0]:
+        size1[r] = sum1[r] / cnt[r]
+        size2[r] = sum2[r] / cnt[r]
     return size1, size2
 
 
