@@ -388,9 +388,10 @@ def measure_config(name, regs, torch, stream, flush, engine, peak16, peak32, ste
 
 def measure_joint(torch, engine, peak32, threads, n_reads=1000, n_check=48):
     """Config 2 read as what BASELINE.json literally names -- HTT CAG/CCG JOINT quantification: nanoRepeat-joint's grid
-    rounds 2 and 3 (nanoRepeat_joint.py:234-273) for one locus through nr_joint_grid; every (read, grid point, strand) is
-    its own rectangle here (no ladder sharing yet), the window score comes out of the DP.  A sample of grid points is
-    checked against the CPU oracle."""
+    rounds 2 and 3 (nanoRepeat_joint.py:234-273) for one locus through nr_joint_grid: one backward sweep per (read, strand)
+    and one forward sweep per k1 with a junction per k2 (nr_window_ladder.cuh); `cells` counts every grid point's full
+    rectangle (the algorithmic work the reference does), the window score comes out of the DP.  A sample of grid points
+    is checked against the CPU oracle."""
     from nanorepeat_b200 import joint, synth
     from oracle import nr_oracle
     loc = synth.joint_locus(seed=7, n_reads=n_reads)
@@ -399,7 +400,9 @@ def measure_joint(torch, engine, peak32, threads, n_reads=1000, n_check=48):
 
     def counting_grid(sc, left, mid, right, m1, m2, reads, pr, p1, p2):
         counted["points"] += len(pr)
-        counted["cells"] += sum(2 * len(reads[r]) * (len(left) + len(m1) * a + len(mid) + len(m2) * b + len(right)) for r, a, b in zip(pr, p1, p2))
+        lens = np.array([len(r) for r in reads], dtype=np.int64)
+        tlen = len(left) + len(mid) + len(right) + len(m1) * np.asarray(p1, dtype=np.int64) + len(m2) * np.asarray(p2, dtype=np.int64)
+        counted["cells"] += int((2 * lens[np.asarray(pr, dtype=np.int64)] * tlen).sum())
         counted["last"] = (pr, p1, p2)
         rec, strand = engine.joint_grid(sc, left, mid, right, m1, m2, reads, pr, p1, p2)
         counted["rec"], counted["strand"] = rec, strand
@@ -415,7 +418,7 @@ def measure_joint(torch, engine, peak32, threads, n_reads=1000, n_check=48):
     pr, p1, p2 = counted["last"]
     rng = np.random.default_rng(3)
     for i in rng.choice(len(pr), min(n_check, len(pr)), replace=False):
-        r, k1, k2 = pr[i], p1[i], p2[i]
+        r, k1, k2 = int(pr[i]), int(p1[i]), int(p2[i])
         tpl = loc["left"] + "CAG" * k1 + loc["mid"] + "CCG" * k2 + loc["right"]
         a, b = max(len(loc["left"]) - 10, 0), min(len(loc["left"]) + 3 * k1 + len(loc["mid"]) + 3 * k2 + 10, len(tpl))
         f = nr_oracle.align_window(loc["reads"][r], tpl, a, b, reverse=False)
@@ -426,11 +429,69 @@ def measure_joint(torch, engine, peak32, threads, n_reads=1000, n_check=48):
     good = sum(abs(float(a) - t[0]) <= 1 and abs(float(b) - t[1]) <= 1
                for a, b, t in zip(res["size1"], res["size2"], loc["truth"]) if a is not None)
     return {"workload": f"HTT-like locus, {n_reads} raw amplicon reads (either strand), grid rounds 2 and 3 of nanoRepeat-joint",
-            "reads": n_reads, "grid_points": counted["points"], "cells": counted["cells"], "s": dt, "reads_per_s": n_reads / dt,
-            "value": counted["cells"] / dt / 1e9, "unit": UNIT, "frac_of_32bit_peak_end_to_end": counted["cells"] / dt / 1e9 / peak32,
+            "reads": n_reads, "grid_points": int(counted["points"]), "cells": int(counted["cells"]), "s": dt, "reads_per_s": n_reads / dt,
+            "value": counted["cells"] / dt / 1e9, "unit": UNIT, "algorithmic_gcups_over_32bit_peak": counted["cells"] / dt / 1e9 / peak32,
             "oracle_checked_points": min(n_check, len(pr)), "reads_within_1_unit_of_both_simulated_counts": good,
             "path": "joint.quantify_two_repeats -> nr_joint_grid (host strings in, sizes out; both strands of every grid point; "
                     "time includes template building, packing, both launches and the selection)"}
+
+
+def measure_phasing(torch, engine, n_loci=2000, reads_per_locus=30, n_cpu=6):
+    """Step 4 for a config-3 slice: 1-D allele phasing of n_loci regions x reads_per_locus round-3 sizes in one
+    nr_phase_1d call (trim, 100x bootstrap, auto-GMM with 10 starts per fit, labels), beside the reference's recipe --
+    scikit-learn's GaussianMixture driven the way split_alleles.auto_GMM_1d drives it -- on n_cpu of the loci, one thread
+    (the reference pins MKL / OMP to one thread, split_alleles.py:30-32)."""
+    import math
+    import warnings
+    from oracle import gmm as ogmm
+    rng = np.random.default_rng(11)
+    loci, truth = [], []
+    for g in range(n_loci):
+        het = rng.random() < 0.6
+        a = int(rng.integers(5, 120))
+        b = a + int(rng.integers(6, 60)) if het else a
+        ks = np.where(rng.random(reads_per_locus) < 0.5, a, b)
+        loci.append(list(np.round(ks + rng.normal(0, 0.01 * (10 + ks)), 2)))
+        truth.append(2 if het else 1)
+    params = engine.GmmParams(error_rate=0.07, max_mutual_overlap=0.15, max_components=22, seed=5)
+    engine.phase_1d(params, loci[:64])                                              # warm-up
+    t0 = time.perf_counter()
+    fits = engine.phase_1d(params, loci)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    agree = int(sum(f["n"] == t for f, t in zip(fits, truth)))
+    # the reference recipe on a few loci
+    from sklearn.mixture import GaussianMixture
+    z = ogmm.std_isf(0.15)
+    t0 = time.perf_counter()
+    same = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for g in range(n_cpu):
+            xs = np.array(loci[g])
+            lo, hi = ogmm.outlier_cutoffs(xs)
+            kept = xs[(xs >= lo) & (xs <= hi)]
+            sim = np.tile(kept, 100)
+            sim = (sim + rng.normal(0, 1, len(sim)) * 0.07 * (10 + sim)).reshape(-1, 1)
+            best = 22
+            for n in range(2, 23):
+                gm = GaussianMixture(n_components=n, covariance_type="diag", n_init=10).fit(sim)
+                sd = np.maximum(1.0, np.sqrt(gm.covariances_[:, 0]))
+                m = gm.means_[:, 0]
+                if any(max(m[i] - z * sd[i], m[j] - z * sd[j]) - min(m[i] + z * sd[i], m[j] + z * sd[j]) <= 0
+                       for i in range(n) for j in range(i + 1, n)):
+                    best = n - 1
+                    break
+            GaussianMixture(n_components=best, covariance_type="diag", n_init=10).fit(sim)
+            same += int(best == fits[g]["n"])
+    cpu_dt = time.perf_counter() - t0
+    return {"workload": f"{n_loci} loci x {reads_per_locus} round-3 sizes (60 % heterozygous), error_rate 0.07, overlap 0.15, up to 22 components",
+            "s": dt, "loci_per_s": n_loci / dt, "samples_fitted": n_loci * reads_per_locus * 100,
+            "loci_with_the_simulated_number_of_alleles": agree,
+            "path": "engine.phase_1d -> nr_phase_1d (host sizes in, mixtures + labels out)",
+            "cpu_reference_recipe": {"loci": n_cpu, "s": cpu_dt, "loci_per_s": n_cpu / cpu_dt, "threads": 1,
+                                     "same_number_of_alleles": same,
+                                     "what": "scikit-learn GaussianMixture(n, 'diag', n_init=10) for n = 2.. until overlap + refit, as split_alleles.auto_GMM_1d"}}
 
 
 def main():
@@ -627,6 +688,7 @@ def main():
         line["configs"] = cfgs
     if not args.no_configs and world == 1:
         line["joint"] = measure_joint(torch, engine, peak32, threads)
+        line["phasing"] = measure_phasing(torch, engine)
     if not args.no_cpu_baseline:
         sample = synth.config2(seed=args.seed, n_reads=args.cpu_sample_reads)
         t0 = time.perf_counter()

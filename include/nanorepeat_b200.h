@@ -276,6 +276,47 @@ int nr_joint_grid(const nr_scoring_t* sc, const char* left, int32_t n_left, cons
                   const int32_t* point_read, const int32_t* point_k1, const int32_t* point_k2, nr_window_t* out,
                   uint8_t* strand);
 
+/* ---- Allele phasing in one dimension ------------------------------------------------------
+ * What the reference does per region after round 3 (nanoRepeat_bam.py:515-575 split_allele_using_gmm_1d): drop sizes
+ * outside mean +- 3 sd (split_alleles.py:98-154), bootstrap every kept size 100 times with Gaussian noise of
+ * sd = error_rate * (10 + size) (:82-88), fit sklearn GaussianMixture(n, 'diag', n_init = 10) for n = 2, 3, ... and stop
+ * at the first n where two components' [isf(1 - o), isf(o)] intervals (sd floored at 1.0) overlap, keeping n - 1
+ * (:171-200); label the kept sizes with that mixture (:258-279).  Here: all regions of a call at once, one thread
+ * block per (region, start) running scikit-learn's EM (same E / M steps, reg_covar, tolerance and choice among starts)
+ * in fp64.  The reference's random draws are unseeded (random.gauss, k-means inside sklearn), so it does not reproduce
+ * itself; this library draws from a counter-based generator keyed by (seed, region_id_base + region index), so a region's
+ * result is reproducible and does not depend on which other regions share the call.  Parity is therefore statistical
+ * (same number of alleles and labels, means within the bootstrap's standard error), bit-level only against the CPU
+ * checker that shares the generator.  Starts: k-means from evenly spread means (start 0) or hashed samples (others).
+ */
+#define NR_GMM_MAX_COMPONENTS 32
+typedef struct nr_gmm_params_t {
+    int32_t max_components;      /* --max_num_components (default ploidy + 20, nanoRepeat.py:159-160); <= NR_GMM_MAX_COMPONENTS */
+    int32_t n_init;              /* starts per fit: 10 (split_alleles.py:174) */
+    int32_t max_iter;            /* 100 (sklearn default) */
+    int32_t reserved;
+    double  error_rate;          /* 0.07 for every data type as the reference is written (nanoRepeat_bam.py:692-701) */
+    double  max_mutual_overlap;  /* --max_mutual_overlap, 0.15 (nanoRepeat.py:123) */
+    double  tol;                 /* 1e-3 (sklearn default) */
+    double  reg_covar;           /* 1e-6 (sklearn default) */
+    uint64_t seed;
+} nr_gmm_params_t;
+/* sizes[offsets[g] .. offsets[g + 1]) = the round-3 sizes of region g.  Per region: n_components[g] (0: fewer than two
+ * sizes, not phased, nanoRepeat_bam.py:533-539) and weights / means / variances [g * max_components + j]; per size:
+ * label (component index; -1: trimmed as an outlier or region not phased) and proba (the label's responsibility).
+ * Components come in ascending order of their means. */
+int nr_phase_1d(const nr_gmm_params_t* p, int32_t n_regions, const int64_t* offsets, const double* sizes,
+                int64_t region_id_base, int32_t* n_components, double* weights, double* means, double* variances,
+                int32_t* label, double* proba);
+/* The two device steps on their own (test seams): the bootstrap (out: 100 * offsets[n_regions] samples, region g's at
+ * 100 * offsets[g], sample rep * n + i from size i) and the best-of-n_init fit of n_components[i] components to explicit
+ * samples data[offsets[i] .. offsets[i + 1]) (region_id nullable: problem index). lower / iters nullable. */
+int nr_gmm_bootstrap(const nr_gmm_params_t* p, int32_t n_regions, const int64_t* offsets, const double* sizes,
+                     int64_t region_id_base, double* out);
+int nr_gmm1d_fit(const nr_gmm_params_t* p, int32_t n_problems, const int64_t* offsets, const double* data,
+                 const int32_t* n_components, const int64_t* region_id, double* lower, int32_t* iters,
+                 double* weights, double* means, double* variances);
+
 /* Counters of the last nr_score_tasks / nr_round2_region / nr_round3_region call on this thread. */
 int nr_last_stats(nr_stats_t* out);
 

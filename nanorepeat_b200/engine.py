@@ -53,6 +53,21 @@ ALN_DTYPE = np.dtype([("score", "<i4"), ("tstart", "<i4"), ("tend", "<i4")])
 RUNG_DTYPE = np.dtype([("score", "<i4"), ("starts_in_left", "u1"), ("ends_in_right", "u1"), ("pad", "u1", (2,))])
 
 
+class GmmParams(ctypes.Structure):
+    """nr_gmm_params_t (include/nanorepeat_b200.h); defaults = the reference's (split_alleles.py:174, nanoRepeat.py:123,
+    :159-160 with ploidy 2) and scikit-learn's."""
+    _fields_ = [("max_components", ctypes.c_int32), ("n_init", ctypes.c_int32), ("max_iter", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("error_rate", ctypes.c_double), ("max_mutual_overlap", ctypes.c_double),
+                ("tol", ctypes.c_double), ("reg_covar", ctypes.c_double), ("seed", ctypes.c_uint64)]
+
+    def __init__(self, error_rate=0.03, max_mutual_overlap=0.15, max_components=22, seed=0, n_init=10, max_iter=100, tol=1e-3,
+                 reg_covar=1e-6):
+        super().__init__(max_components, n_init, max_iter, 0, error_rate, max_mutual_overlap, tol, reg_covar, seed)
+
+
+GMM_MAX_COMPONENTS = 32
+
+
 class NanoRepeatB200Error(RuntimeError):
     def __init__(self, code, message):
         super().__init__(f"{ERROR_NAMES.get(code, code)}: {message}")
@@ -65,6 +80,8 @@ _cpp = ctypes.POINTER(ctypes.c_char_p)
 _i32p = ctypes.POINTER(ctypes.c_int32)
 _i64p = ctypes.POINTER(ctypes.c_int64)
 _scp = ctypes.POINTER(Scoring)
+_f64p = ctypes.POINTER(ctypes.c_double)
+_gmp = ctypes.POINTER(GmmParams)
 
 # name -> (restype, argtypes): every symbol include/nanorepeat_b200.h declares
 SYMBOLS = {
@@ -114,6 +131,9 @@ SYMBOLS = {
                                      ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32,
                                      ctypes.c_int32, _cpp, _i32p, ctypes.c_int32, _i32p, _i32p, _i32p, ctypes.c_void_p,
                                      ctypes.c_void_p]),
+    "nr_phase_1d": (ctypes.c_int, [_gmp, ctypes.c_int32, _i64p, _f64p, ctypes.c_int64, _i32p, _f64p, _f64p, _f64p, _i32p, _f64p]),
+    "nr_gmm_bootstrap": (ctypes.c_int, [_gmp, ctypes.c_int32, _i64p, _f64p, ctypes.c_int64, _f64p]),
+    "nr_gmm1d_fit": (ctypes.c_int, [_gmp, ctypes.c_int32, _i64p, _f64p, _i32p, _i64p, _f64p, _i32p, _f64p, _f64p, _f64p]),
     "nr_estimate_regions": (ctypes.c_int, [_scp, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(RegionIn),
                                            ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.c_void_p,
                                            ctypes.POINTER(ctypes.c_double), ctypes.c_void_p, _i32p, ctypes.POINTER(Stats)]),
@@ -542,3 +562,55 @@ def joint_grid(sc, left, mid, right, motif1, motif2, reads, point_read, point_k1
                                rl.ctypes.data_as(_i32p), n, pr.ctypes.data_as(_i32p), k1.ctypes.data_as(_i32p),
                                k2.ctypes.data_as(_i32p), out.ctypes.data, strand.ctypes.data))
     return out, strand
+
+
+def _ragged(lists):
+    """list of float sequences -> (offsets int64 [n + 1], values float64)"""
+    off = np.zeros(len(lists) + 1, dtype=np.int64)
+    if lists:
+        np.cumsum([len(v) for v in lists], out=off[1:])
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.float64) for v in lists]) if off[-1] else np.zeros(0))
+    return off, flat
+
+
+def gmm_bootstrap(params, size_lists, region_id_base=0):
+    """nr_gmm_bootstrap -> list of arrays (100 x len(sizes) samples per region)"""
+    off, flat = _ragged(size_lists)
+    out = np.zeros(100 * int(off[-1]), dtype=np.float64)
+    _check(lib().nr_gmm_bootstrap(ctypes.byref(params), len(size_lists), off.ctypes.data_as(_i64p), flat.ctypes.data_as(_f64p),
+                                  region_id_base, out.ctypes.data_as(_f64p)))
+    return [out[100 * off[g]:100 * off[g + 1]] for g in range(len(size_lists))]
+
+
+def gmm1d_fit(params, data_lists, n_components, region_ids=None):
+    """nr_gmm1d_fit: best of params.n_init starts per problem -> dict(lower, iters, weights, means, variances), the last
+    three as lists of arrays of n_components[i] entries."""
+    off, flat = _ragged(data_lists)
+    n = len(data_lists)
+    nc = np.ascontiguousarray(n_components, dtype=np.int32)
+    rid = None if region_ids is None else np.ascontiguousarray(region_ids, dtype=np.int64)
+    C = params.max_components
+    lower, iters = np.zeros(n), np.zeros(n, dtype=np.int32)
+    w, m, v = np.zeros((n, C)), np.zeros((n, C)), np.zeros((n, C))
+    _check(lib().nr_gmm1d_fit(ctypes.byref(params), n, off.ctypes.data_as(_i64p), flat.ctypes.data_as(_f64p), nc.ctypes.data_as(_i32p),
+                              None if rid is None else rid.ctypes.data_as(_i64p), lower.ctypes.data_as(_f64p),
+                              iters.ctypes.data_as(_i32p), w.ctypes.data_as(_f64p), m.ctypes.data_as(_f64p), v.ctypes.data_as(_f64p)))
+    return dict(lower=lower, iters=iters, weights=[w[i, :nc[i]] for i in range(n)], means=[m[i, :nc[i]] for i in range(n)],
+                variances=[v[i, :nc[i]] for i in range(n)])
+
+
+def phase_1d(params, size_lists, region_id_base=0):
+    """nr_phase_1d: every region's round-3 sizes -> per region dict(n, weights, means, variances, label, proba); label -1
+    marks a size trimmed as an outlier (or a region with fewer than two sizes)."""
+    off, flat = _ragged(size_lists)
+    n = len(size_lists)
+    C = params.max_components
+    ncomp = np.zeros(n, dtype=np.int32)
+    w, m, v = np.zeros((n, C)), np.zeros((n, C)), np.zeros((n, C))
+    label = np.full(int(off[-1]), -1, dtype=np.int32)
+    proba = np.zeros(int(off[-1]))
+    _check(lib().nr_phase_1d(ctypes.byref(params), n, off.ctypes.data_as(_i64p), flat.ctypes.data_as(_f64p), region_id_base,
+                             ncomp.ctypes.data_as(_i32p), w.ctypes.data_as(_f64p), m.ctypes.data_as(_f64p), v.ctypes.data_as(_f64p),
+                             label.ctypes.data_as(_i32p), proba.ctypes.data_as(_f64p)))
+    return [dict(n=int(ncomp[g]), weights=w[g, :ncomp[g]], means=m[g, :ncomp[g]], variances=v[g, :ncomp[g]],
+                 label=label[off[g]:off[g + 1]], proba=proba[off[g]:off[g + 1]]) for g in range(n)]
