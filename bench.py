@@ -357,6 +357,21 @@ def time_e2e(wl, torch, passes_total):
     return total
 
 
+def time_c_abi(wl, torch, passes_total):
+    """The same work through the C ABI's one call: lists of host strings in, numpy arrays out, no Read objects."""
+    lefts = [r.left_anchor_seq for r in wl.regs]
+    rights = [r.right_anchor_seq for r in wl.regs]
+    motifs = [r.repeat_unit_seq for r in wl.regs]
+    cores = [list(r.core_seqs) for r in wl.regs]
+    dists = np.array([d for r in wl.regs for d in r.dist_between_anchors], dtype=np.int32)
+    wl.engine.estimate_regions(wl.sc, wl.fast_mode, lefts, rights, motifs, cores, dists)
+    t0 = time.perf_counter()
+    for _ in range(passes_total):
+        wl.engine.estimate_regions(wl.sc, wl.fast_mode, lefts, rights, motifs, cores, dists)
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / passes_total * 1e3
+
+
 def measure_config(name, regs, torch, stream, flush, engine, peak16, peak32, steps, passes, e2e_passes, threads, check):
     t0 = time.perf_counter()
     wl = Workload(name, regs)
@@ -366,6 +381,7 @@ def measure_config(name, regs, torch, stream, flush, engine, peak16, peak32, ste
     dev_ms, kern_ms = time_resident(wl, torch, stream, flush, steps, passes, engine)
     linfo = [wl.b2.launch_info(), wl.b3.launch_info()]
     e2e_s = time_e2e(wl, torch, e2e_passes)
+    c_abi_ms = time_c_abi(wl, torch, e2e_passes)
     n_pass = steps * passes
     dev_s = sum(dev_ms) * 1e-3
     res = {
@@ -375,7 +391,8 @@ def measure_config(name, regs, torch, stream, flush, engine, peak16, peak32, ste
         "value": wl.cells * n_pass / dev_s / 1e9, "unit": UNIT, "reads_per_s": wl.units * n_pass / dev_s,
         "ms_per_pass": dev_s / n_pass * 1e3, "executed_gcups": wl.executed * n_pass / dev_s / 1e9,
         "e2e": {"value": wl.cells * e2e_passes / e2e_s / 1e9, "unit": UNIT, "reads_per_s": wl.units * e2e_passes / e2e_s,
-                "ms_per_pass": e2e_s / e2e_passes * 1e3, "h2d_bytes_per_pass": wl.h2d, "d2h_bytes_per_pass": wl.d2h},
+                "ms_per_pass": e2e_s / e2e_passes * 1e3, "c_abi_ms_per_pass": c_abi_ms,
+                "h2d_bytes_per_pass": wl.h2d, "d2h_bytes_per_pass": wl.d2h},
         "kernels": kernel_table(linfo, kern_ms, n_pass, peak16, peak32),
         "redo_reads_per_pass": linfo[1]["n_redo"], "unscored_reads": sum(s["n_skipped"] for s in wl.stats),
     }
@@ -563,6 +580,7 @@ def main():
         wl.e2e_pass(wl.fresh())
     barrier()
     e2e_s = time_e2e(wl, torch, e2e_passes)
+    c_abi_ms = time_c_abi(wl, torch, e2e_passes)
     barrier()
     clocks = sampler.stop()
     total_ms = float(sum(dev_ms))
@@ -648,6 +666,9 @@ def main():
                 "h2d_bytes_per_pass": wl.h2d, "d2h_bytes_per_pass": wl.d2h,
                 "reads_per_s": units_all * e2e_passes / e2e_s, "ms_per_pass": e2e_s / e2e_passes * 1e3,
                 "device_ms_per_pass": total_ms / n_pass, "passes_timed": e2e_passes,
+                "c_abi_ms_per_pass": c_abi_ms,
+                "c_abi_path": "engine.estimate_regions: lists of host strings in, numpy arrays out (the same nr_estimate_regions "
+                              "call without the per-Read attribute traffic of the operator API)",
                 "path": "nanorepeat_b200.estimate_regions on RepeatRegion / Read objects (host strings in, "
                         "Read.round{1,2,3}_repeat_size out) -> nr_estimate_regions (one C-ABI call, rounds 1-3)"},
         "gpu_launches": int(launches_pass * n_pass * world),

@@ -126,3 +126,23 @@ def test_phase_agrees_with_the_reference_recipe_on_sklearn(engine):
         differ = [k for k in ours if ours[k] != sk_lab[k]]
         assert len(differ) <= 1, (g, differ)
         assert all(c in ("HIGH", "LOW") for a in alleles for c in a.confidence_list)
+
+
+def test_steps_1_to_4_in_memory_find_the_simulated_alleles(engine):
+    """pipeline.quantify_regions(phase=True): raw reads of several regions -> anchors, cores, rounds 1-3, phased alleles,
+    all batched; the alleles' medians land on the simulated repeat counts."""
+    import nanorepeat_b200 as nrb
+    from nanorepeat_b200 import synth, pipeline
+    regions, reads, alleles = [], [], [(17, 55), (30, 30), (12, 40)]
+    for g, al in enumerate(alleles):
+        reg, names, seqs, truth = synth.region_reads(seed=20 + g, n_reads=50, motif="CAG", alleles=al)
+        rr = nrb.RepeatRegion()
+        rr.left_anchor_seq, rr.right_anchor_seq, rr.repeat_unit_seq = reg.left_anchor_seq, reg.right_anchor_seq, "CAG"
+        regions.append(rr); reads.append(dict(zip(names, seqs)))
+    pipeline.quantify_regions(regions, reads, "ont", phase=True, seed=4)
+    for rr, al in zip(regions, alleles):
+        assert rr.allele_list is not None
+        medians = sorted(a.repeat1_median_size for a in rr.allele_list if a.num_reads >= 5)
+        want = sorted(set(al))
+        assert len(medians) == len(want) and all(abs(m - w) <= 2 for m, w in zip(medians, want)), (al, medians)
+        assert sum(a.num_reads for a in rr.allele_list) <= len(rr.read_dict)
