@@ -130,27 +130,34 @@ nrw::WinScore window_score_words(const nr_scoring_t* sc) {
 }
 
 // The shared-sweep path (nr_window_ladder.cuh): backward tasks, then forward tasks; res[out_off + j] of every forward task.
-int run_ladder_tasks(const nr_scoring_t* sc, const std::vector<nrw::LadBwdTask>& btasks, std::vector<nrw::LadFwdTask>& ftasks,
-                     const SeqPool& pool, size_t bvec_words, size_t n_out, int max_t, std::vector<int2>& res) {
-    const int nb = (int)btasks.size(), nf = (int)ftasks.size();
+int run_ladder_tasks(const nr_scoring_t* sc, const std::vector<nrw::LadBwdTask>& btasks, std::vector<nrw::LadFwdTask>& ptasks,
+                     std::vector<nrw::LadFwdTask>& ftasks, const SeqPool& pool, size_t bvec_words, size_t cstate_words, size_t n_pbest1,
+                     size_t n_out, int max_t, std::vector<int2>& res) {
+    const int nb = (int)btasks.size(), nf = (int)ftasks.size(), np = (int)ptasks.size();
     res.assign(n_out, make_int2(0, 0));
     if (nf == 0) return NR_OK;
     // long tasks first
-    std::sort(ftasks.begin(), ftasks.end(), [](const nrw::LadFwdTask& x, const nrw::LadFwdTask& y) {
+    auto by_cost = [](const nrw::LadFwdTask& x, const nrw::LadFwdTask& y) {
         const long long cx = (long long)x.q_len * (x.n_pre + (long long)x.m2 * (x.k2_first + (long long)x.k2_step * (x.k2_count - 1)));
         const long long cy = (long long)y.q_len * (y.n_pre + (long long)y.m2 * (y.k2_first + (long long)y.k2_step * (y.k2_count - 1)));
         return cx != cy ? cx > cy : x.out_off < y.out_off;
-    });
+    };
+    std::sort(ftasks.begin(), ftasks.end(), by_cost);
+    std::sort(ptasks.begin(), ptasks.end(), by_cost);
     const int blocks_b = std::max(1, std::min(2 * nri::sm_count(), (nb + nrw::kWarps - 1) / nrw::kWarps));
     const int blocks_f = std::max(1, std::min(2 * nri::sm_count(), (nf + nrw::kWarps - 1) / nrw::kWarps));
+    const int blocks_p = std::max(1, std::min(2 * nri::sm_count(), (np + nrw::kWarps - 1) / nrw::kWarps));
     const int stride = 2 * ((max_t + 31) / 32 * 32);
-    const size_t scratch_bytes = sizeof(int4) * (size_t)std::max(blocks_b, blocks_f) * nrw::kWarps * stride;
+    const size_t scratch_bytes = sizeof(int4) * (size_t)std::max(std::max(blocks_b, blocks_f), blocks_p) * nrw::kWarps * stride;
     const size_t out_bytes = sizeof(int2) * n_out;
     Bufs bufs;
-    void *d_b = nullptr, *d_f = nullptr, *d_pool = nullptr, *d_out = nullptr, *d_scratch = nullptr, *d_counter = nullptr,
-         *d_bvec = nullptr, *d_ronly = nullptr, *h_out = nullptr;
+    void *d_b = nullptr, *d_f = nullptr, *d_p = nullptr, *d_pool = nullptr, *d_out = nullptr, *d_scratch = nullptr, *d_counter = nullptr,
+         *d_bvec = nullptr, *d_ronly = nullptr, *d_cstate = nullptr, *d_pbest1 = nullptr, *h_out = nullptr;
     int rc;
     if ((rc = bufs.get(&d_b, sizeof(nrw::LadBwdTask) * nb, false)) || (rc = bufs.get(&d_f, sizeof(nrw::LadFwdTask) * nf, false)) ||
+        (rc = bufs.get(&d_p, sizeof(nrw::LadFwdTask) * std::max(np, 1), false)) ||
+        (rc = bufs.get(&d_cstate, sizeof(int) * std::max<size_t>(cstate_words, 1), false)) ||
+        (rc = bufs.get(&d_pbest1, sizeof(int) * std::max<size_t>(n_pbest1, 1), false)) ||
         (rc = bufs.get(&d_pool, sizeof(uint32_t) * (pool.words.size() + 4), false)) || (rc = bufs.get(&d_out, out_bytes, false)) ||
         (rc = bufs.get(&d_scratch, scratch_bytes, false)) || (rc = bufs.get(&d_counter, 256, false)) ||
         (rc = bufs.get(&d_bvec, sizeof(int) * std::max<size_t>(bvec_words, 1), false)) ||
@@ -170,6 +177,7 @@ int run_ladder_tasks(const nr_scoring_t* sc, const std::vector<nrw::LadBwdTask>&
     JTRY(attr_err);
     JTRY(cudaMemcpyAsync(d_b, btasks.data(), sizeof(nrw::LadBwdTask) * nb, cudaMemcpyHostToDevice, st));
     JTRY(cudaMemcpyAsync(d_f, ftasks.data(), sizeof(nrw::LadFwdTask) * nf, cudaMemcpyHostToDevice, st));
+    if (np) JTRY(cudaMemcpyAsync(d_p, ptasks.data(), sizeof(nrw::LadFwdTask) * np, cudaMemcpyHostToDevice, st));
     JTRY(cudaMemcpyAsync(d_pool, pool.words.data(), sizeof(uint32_t) * pool.words.size(), cudaMemcpyHostToDevice, st));
     JTRY(cudaMemsetAsync(d_counter, 0, 256, st));
     int* counter = static_cast<int*>(d_counter);
@@ -177,18 +185,28 @@ int run_ladder_tasks(const nr_scoring_t* sc, const std::vector<nrw::LadBwdTask>&
                                                                      static_cast<const uint32_t*>(d_pool), k, static_cast<int4*>(d_scratch),
                                                                      stride, counter, static_cast<int*>(d_bvec), static_cast<int*>(d_ronly));
     JTRY(cudaGetLastError());
+    if (np) {       // prefix sweeps: the columns the continuation sweeps start from
+        nrw::ladder_fwd_kernel<<<blocks_p, 32 * nrw::kWarps, smem_f, st>>>(static_cast<const nrw::LadFwdTask*>(d_p), np,
+                                                                         static_cast<const nrw::LadBwdTask*>(d_b), static_cast<const uint32_t*>(d_pool),
+                                                                         k, static_cast<int4*>(d_scratch), stride, counter + 16,
+                                                                         static_cast<const int*>(d_bvec), static_cast<const int*>(d_ronly),
+                                                                         static_cast<int*>(d_cstate), static_cast<int*>(d_pbest1),
+                                                                         static_cast<int2*>(d_out));
+        JTRY(cudaGetLastError());
+    }
     nrw::ladder_fwd_kernel<<<blocks_f, 32 * nrw::kWarps, smem_f, st>>>(static_cast<const nrw::LadFwdTask*>(d_f), nf,
                                                                      static_cast<const nrw::LadBwdTask*>(d_b), static_cast<const uint32_t*>(d_pool),
                                                                      k, static_cast<int4*>(d_scratch), stride, counter + 32,
                                                                      static_cast<const int*>(d_bvec), static_cast<const int*>(d_ronly),
+                                                                     static_cast<int*>(d_cstate), static_cast<int*>(d_pbest1),
                                                                      static_cast<int2*>(d_out));
     JTRY(cudaGetLastError());
     JTRY(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
     const auto t_launch = std::chrono::steady_clock::now();
     const cudaError_t e = cudaStreamSynchronize(st);
     if (getenv("NR_TRACE"))
-        fprintf(stderr, "[nr trace] joint ladder: %d backward + %d forward tasks, %zu grid points, kernels + download %.1f us\n", nb, nf,
-                n_out, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_launch).count());
+        fprintf(stderr, "[nr trace] joint ladder: %d backward + %d prefix + %d forward tasks, %zu grid points, kernels + download %.1f us\n", nb, np,
+                nf, n_out, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_launch).count());
     if (e != cudaSuccess) { cudaGetLastError(); return nri::fail_msg(NR_ERR_CUDA, cudaGetErrorString(e)); }
     std::copy(static_cast<const int2*>(h_out), static_cast<const int2*>(h_out) + n_out, res.begin());
     return NR_OK;
@@ -257,8 +275,9 @@ extern "C" int nr_joint_grid(const nr_scoring_t* sc, const char* left, int32_t n
     std::vector<int> point_slot(n_points, -1);                      // record of strand '+'; strand '-' follows at +k2_count ... see below
     std::vector<int> point_slot_rev(n_points, -1);
     std::vector<nrw::LadBwdTask> btasks;
-    std::vector<nrw::LadFwdTask> ftasks;
-    size_t bvec_words = 0, n_lad_out = 0;
+    std::vector<nrw::LadFwdTask> ftasks, ptasks;
+    size_t bvec_words = 0, n_lad_out = 0, cstate_words = 0, n_pbest1 = 0;
+    const bool two_d = !getenv("NR_JOINT_NO_2D");
     int lad_max_t = std::max(1, (int)n_right);
     const bool ladder_on = !getenv("NR_JOINT_RECTANGLES") && n_right >= 10 && n_left >= 1;
     if (ladder_on && n_points > 0) {
@@ -268,6 +287,7 @@ extern "C" int nr_joint_grid(const nr_scoring_t* sc, const char* left, int32_t n
         std::vector<std::vector<int>> of_read(n_reads);
         for (int i = 0; i < n_points; ++i) of_read[point_read[i]].push_back(i);
         std::map<std::pair<int, int>, long long> fwd_tpl;                 // (k1, k2 of the longest) -> word
+        std::map<int, long long> pre_tpl, cont_tpl;                       // k1 of the longest -> left + m1*k1; k2 -> mid + m2*k2
         std::string s;
         for (int r = 0; r < n_reads && rev_word >= 0; ++r) {
             const std::vector<int>& pts = of_read[r];
@@ -288,9 +308,31 @@ extern "C" int nr_joint_grid(const nr_scoring_t* sc, const char* left, int32_t n
             if (t_max + n_right > kMaxTlen || t_max + 10 - win_a > kMaxWindow ||
                 (long long)sc->match * std::min<long long>(read_len[r], t_max + n_right) > kMaxScore)
                 continue;                                                            // the rectangle path decides (and skips) these
+            // 2-D: K1 arithmetic as well, a first junction with at least one column of its own, the saved columns within budget
+            const int k1_step = K1.size() > 1 ? K1[1] - K1[0] : 1;
+            bool share_k1 = two_d && K1.size() >= 2 && K1.size() <= (size_t)nrw::kMaxK2 && n_mid + m2 * K2[0] >= 1 &&
+                            cstate_words + 6 * K1.size() * (size_t)read_len[r] < ((size_t)1 << 29);
+            for (size_t j = 1; j < K1.size(); ++j) share_k1 = share_k1 && K1[j] - K1[j - 1] == k1_step;
+            long long pre_word = -1, cont_word = -1;
+            if (share_k1) {
+                auto ip = pre_tpl.find(K1.back());
+                if (ip == pre_tpl.end()) {
+                    s.assign(left, (size_t)n_left);
+                    for (int u = 0; u < K1.back(); ++u) s.append(motif1, (size_t)m1);
+                    ip = pre_tpl.emplace(K1.back(), pool.add(s.data(), (int)s.size(), false)).first;
+                }
+                auto ic = cont_tpl.find(K2.back());
+                if (ic == cont_tpl.end()) {
+                    s.assign(mid ? mid : "", (size_t)n_mid);
+                    for (int u = 0; u < K2.back(); ++u) s.append(motif2, (size_t)m2);
+                    ic = cont_tpl.emplace(K2.back(), pool.add(s.data(), (int)s.size(), false)).first;
+                }
+                pre_word = ip->second; cont_word = ic->second;
+                share_k1 = pre_word >= 0 && cont_word >= 0;
+            }
             bool ok = true;
             std::vector<long long> words(K1.size());
-            for (size_t a = 0; a < K1.size() && ok; ++a) {
+            for (size_t a = 0; a < K1.size() && ok && !share_k1; ++a) {
                 auto key = std::make_pair(K1[a], K2.back());
                 auto it = fwd_tpl.find(key);
                 if (it == fwd_tpl.end()) {
@@ -314,12 +356,37 @@ extern "C" int nr_joint_grid(const nr_scoring_t* sc, const char* left, int32_t n
                 btasks.push_back(bt);
             }
             std::map<std::pair<int, int>, int> slot;                                 // (k1, k2) -> record of strand '+'
+            int pre_pbest[2] = {0, 0};
+            long long pre_cstate[2] = {0, 0};
+            if (share_k1)
+                for (int sd = 0; sd < 2; ++sd) {
+                    nrw::LadFwdTask pt = {};
+                    pt.q_word = (uint32_t)read_word[r]; pt.q_len = read_len[r];
+                    pt.t_word = (uint32_t)pre_word;
+                    pt.n_pre = n_left; pt.m2 = m1; pt.k2_first = K1[0]; pt.k2_step = k1_step; pt.k2_count = (int)K1.size();
+                    pt.win_a = win_a; pt.reverse = sd; pt.bwd = b0 + sd; pt.mode = nrw::kPrefix;
+                    pt.out_off = pre_pbest[sd] = (int)n_pbest1;
+                    pt.cstate = pre_cstate[sd] = (long long)cstate_words;
+                    n_pbest1 += K1.size();
+                    cstate_words += 3 * K1.size() * (size_t)read_len[r];
+                    lad_max_t = std::max(lad_max_t, n_left + m1 * K1.back());
+                    ptasks.push_back(pt);
+                }
             for (size_t a = 0; a < K1.size(); ++a)
                 for (int sd = 0; sd < 2; ++sd) {
                     nrw::LadFwdTask ft = {};
                     ft.q_word = (uint32_t)read_word[r]; ft.q_len = read_len[r];
-                    ft.t_word = (uint32_t)words[a];
-                    ft.n_pre = n_left + m1 * K1[a] + n_mid;
+                    if (share_k1) {
+                        ft.t_word = (uint32_t)cont_word;
+                        ft.n_pre = n_mid;
+                        ft.mode = nrw::kCont;
+                        ft.pbest1 = pre_pbest[sd] + (int)a;
+                        ft.cstate = pre_cstate[sd] + (long long)(3 * a) * read_len[r];
+                    } else {
+                        ft.t_word = (uint32_t)words[a];
+                        ft.n_pre = n_left + m1 * K1[a] + n_mid;
+                        ft.mode = nrw::kWhole;
+                    }
                     ft.m2 = m2; ft.k2_first = K2[0]; ft.k2_step = k2_step; ft.k2_count = (int)K2.size();
                     ft.win_a = win_a; ft.reverse = sd; ft.bwd = b0 + sd; ft.out_off = (int)n_lad_out;
                     if (sd == 0) for (size_t j = 0; j < K2.size(); ++j) slot[{K1[a], K2[j]}] = (int)(n_lad_out + j);
@@ -336,7 +403,7 @@ extern "C" int nr_joint_grid(const nr_scoring_t* sc, const char* left, int32_t n
     }
     if (!ftasks.empty()) {
         std::vector<int2> res;
-        if ((rc = run_ladder_tasks(sc, btasks, ftasks, pool, bvec_words, n_lad_out, lad_max_t, res))) return rc;
+        if ((rc = run_ladder_tasks(sc, btasks, ptasks, ftasks, pool, bvec_words, cstate_words, n_pbest1, n_lad_out, lad_max_t, res))) return rc;
         for (int i = 0; i < n_points; ++i) {
             if (!by_ladder[i]) continue;
             const int2 f = res[point_slot[i]], v = res[point_slot_rev[i]];

@@ -16,6 +16,15 @@
 // Cells per read and strand:  |read| x (|right| + |K1| x (|left| + m1 k1 + |mid| + m2 k2max))  instead of
 // |K1| |K2| x |read| x |template|: a factor |K2| / (1 + 1/|K1|), 5-6 on the coarse grids of round 2, 3-4 on round 3's.
 //
+// Sharing over k1 as well (the 2-D ladder).  The forward sweeps of all k1 have  left + motif1*k1  in common up to the
+// column where motif1 stops, so when a read's K1 is an arithmetic progression too:
+//   * ONE prefix sweep per (read, strand) over left + motif1*k1max.  Whenever a lane finishes the column before
+//     c1(k1) = |left| + m1*k1 it saves its rows' states (H and the two gap states entering the next column) and the
+//     running maximum: the DP column every template of that k1 continues from;
+//   * per (read, strand, k1) ONE continuation sweep over  mid + motif2*k2max  that starts from the saved column instead
+//     of the empty one, with the junctions per k2 as above.
+// Cells per read and strand:  |read| x (|right| + |left| + m1 k1max + |K1| x (|mid| + m2 k2max)).
+//
 // The window and the payload across the junction.  The window of grid point (k1, k2) is [|left| - 10, J + 10) with J the
 // junction column: in the forward sweep every column from |left| - 10 on is inside it for every k2; in the backward sweep
 // the first ten bases of the right anchor are.  A deletion's window value depends only on how many of its bases lie in
@@ -44,8 +53,15 @@ struct LadFwdTask {        // one per (read, strand, k1)
     int32_t win_a;                         // |left| - 10 (>= 0)
     int32_t reverse;
     int32_t bwd;                           // index of the (read, strand)'s LadBwdTask
-    int32_t out_off;                       // first record of this task in out[]: k2_count records
+    int32_t out_off;                       // first record of this task in out[]: k2_count records (prefix: in pbest1[])
+    int32_t mode;                          // kWhole / kPrefix / kCont
+    int32_t pbest1;                        // kCont: index into pbest1[] of this k1's entry
+    long long cstate;                      // kPrefix: first word of its saved columns [k][3][q_len]; kCont: of its own column
 };
+// kWhole: the whole forward template from the empty column.  kPrefix: the fields n_pre / m2 / k2_* describe the k1
+// junctions (n_pre = |left|, m2 = m1, ...); nothing is joined, states are saved.  kCont: t_word = mid + motif2*k2max,
+// n_pre = |mid|, every column inside the window.
+constexpr int kWhole = 0, kPrefix = 1, kCont = 2;
 
 constexpr int kMaxK2 = 64;                 // grid points per forward task (shared-memory tables)
 
@@ -168,9 +184,10 @@ __device__ __forceinline__ void ladder_bwd_task(const LadBwdTask& tk, const uint
 }
 
 // ---- forward sweep of one (read, strand, k1) with a junction per k2 ----------------------------------------------------
+template <int MODE>
 __device__ __forceinline__ void ladder_fwd_task(const LadFwdTask& tk, const uint32_t* __restrict__ pool, const WinScore& sc,
                                                 int* prof, int* bsm, int* jbest, int* pbest, int4* bnd, const int* __restrict__ bvec,
-                                                int ronly, int2* out, int lane) {
+                                                int ronly, int* cstate, int* pbest1, int2* out, int lane) {
     const uint32_t* q = pool + tk.q_word;
     const uint32_t* tw = pool + tk.t_word;
     const int q_len = tk.q_len, a = tk.win_a;
@@ -178,24 +195,34 @@ __device__ __forceinline__ void ladder_fwd_task(const LadFwdTask& tk, const uint
     const int t_len = tk.n_pre + tk.m2 * (tk.k2_first + tk.k2_step * (tk.k2_count - 1));
     const int n_stripes = (q_len + kRows - 1) / kRows;
     for (int j = lane; j < tk.k2_count; j += 32) { jbest[j] = 0; pbest[j] = 0; }
+    int* cst = cstate + tk.cstate;                     // kPrefix: [k][3][q_len] to fill; kCont: [3][q_len] to start from
     for (int s = 0; s < n_stripes; ++s) {
         int best = 0;                                  // of this stripe's rows, columns up to the lane's current one
         __syncwarp();
         build_profile2(prof, q, q_len, tk.reverse != 0, false, s * kRows, lane, sc);
+        if (MODE != kPrefix) {
 #pragma unroll
-        for (int r = 0; r < kR; ++r) {
-            const int i = s * kRows + lane * kR + r;
+            for (int r = 0; r < kR; ++r) {
+                const int i = s * kRows + lane * kR + r;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) bsm[c * kRows + lane * kR + r] = i < q_len ? __ldcg(&bvec[c * q_len + i]) : kPad;
+                for (int c = 0; c < 3; ++c) bsm[c * kRows + lane * kR + r] = i < q_len ? __ldcg(&bvec[c * q_len + i]) : kPad;
+            }
         }
         __syncwarp();
         const int4* bin = bnd + (size_t)((s + 1) & 1) * t_len;
         int4* bout = bnd + (size_t)(s & 1) * t_len;
         const bool top = s > 0, bot = s + 1 < n_stripes;
         int H[kR], E1[kR], E2[kR];
+        int hup_prev = 0, h_out = 0, f1_out = 0, f2_out = 0;
 #pragma unroll
         for (int r = 0; r < kR; ++r) { H[r] = 0; E1[r] = sc.open1; E2[r] = sc.open2; }
-        int hup_prev = 0, h_out = 0, f1_out = 0, f2_out = 0;
+        if (MODE == kCont) {                           // the column this k1's templates continue from
+            const int row0 = s * kRows + lane * kR;
+#pragma unroll
+            for (int r = 0; r < kR; ++r)
+                if (row0 + r < q_len) { H[r] = __ldcg(&cst[row0 + r]); E1[r] = __ldcg(&cst[q_len + row0 + r]); E2[r] = __ldcg(&cst[2 * q_len + row0 + r]); }
+            if (row0 >= 1 && row0 - 1 < q_len) hup_prev = __ldcg(&cst[row0 - 1]);
+        }
         int4 bcur = make_int4(0, 0, 0, 0);
         int jidx = 0, jcol = c_first;                  // the next junction of this lane: grid point jidx after jcol columns (>= 1)
         const int nsteps = t_len + 31;
@@ -214,10 +241,10 @@ __device__ __forceinline__ void ladder_fwd_task(const LadFwdTask& tk, const uint
             const int p = st - lane;
             if (p >= 0 && p < t_len) {
                 const int code = (tw[p >> 4] >> (30 - 2 * (p & 15))) & 3;
-                const bool in_diag = p >= a;                          // (every grid point's window reaches past the junction)
-                const bool in_next = p + 1 >= a;
-                const bool in_ins = p + 1 > a;
-                const int h_open_pay = in_next ? -4 : 0, h_ext_pay = in_next ? (p + 1 == a ? -4 : -2) : 0;
+                const bool in_diag = MODE == kCont || p >= a;         // (every grid point's window reaches past the junction)
+                const bool in_next = MODE == kCont || p + 1 >= a;
+                const bool in_ins = MODE == kCont || p + 1 > a;
+                const int h_open_pay = in_next ? -4 : 0, h_ext_pay = in_next ? (MODE != kCont && p + 1 == a ? -4 : -2) : 0;
                 const int v_open_pay = in_ins ? -4 : 0, v_ext_pay = in_ins ? -2 : 0;
                 const int ho1 = sc.open1 + h_open_pay, ho2 = sc.open2 + h_open_pay, he1 = sc.ext1 + h_ext_pay, he2 = sc.ext2 + h_ext_pay;
                 const int vo1 = sc.open1 + v_open_pay, vo2 = sc.open2 + v_open_pay, ve1 = sc.ext1 + v_ext_pay, ve2 = sc.ext2 + v_ext_pay;
@@ -239,7 +266,7 @@ __device__ __forceinline__ void ladder_fwd_task(const LadFwdTask& tk, const uint
                     hd = hleft;
                     H[r] = h;
                     cm = max(cm, h);
-                    if (junc) {
+                    if (MODE != kPrefix && junc) {
                         const int x = lane * kR + r;
                         jmax = __vimax3_s32(jmax, h + bsm[x], e1pre + bsm[kRows + x]);
                         jmax = max(jmax, e2pre + bsm[2 * kRows + x]);
@@ -247,7 +274,15 @@ __device__ __forceinline__ void ladder_fwd_task(const LadFwdTask& tk, const uint
                 }
                 best = cm;
                 if (junc) {
-                    atomicMax(&jbest[jidx], jmax);
+                    if (MODE == kPrefix) {             // the states every template of this k1 continues from
+                        const int row0 = s * kRows + lane * kR;
+                        int* dst = cst + (size_t)jidx * 3 * q_len;
+#pragma unroll
+                        for (int r = 0; r < kR; ++r)
+                            if (row0 + r < q_len) { __stcg(&dst[row0 + r], H[r]); __stcg(&dst[q_len + row0 + r], E1[r]); __stcg(&dst[2 * q_len + row0 + r], E2[r]); }
+                    } else {
+                        atomicMax(&jbest[jidx], jmax);
+                    }
                     atomicMax(&pbest[jidx], best);
                     ++jidx;
                     jcol += c_step;
@@ -260,10 +295,16 @@ __device__ __forceinline__ void ladder_fwd_task(const LadFwdTask& tk, const uint
         __threadfence_block();
     }
     __syncwarp();
-    for (int j = lane; j < tk.k2_count; j += 32) {
-        const int w = max(max(pbest[j], jbest[j]), ronly);
-        const int score = (w + 0x8000) >> 16;
-        out[tk.out_off + j] = make_int2(score, w - (score << 16));
+    if (MODE == kPrefix) {
+        for (int j = lane; j < tk.k2_count; j += 32) pbest1[tk.out_off + j] = pbest[j];
+        __threadfence();
+    } else {
+        const int before = MODE == kCont ? max(ronly, __ldcg(&pbest1[tk.pbest1])) : ronly;
+        for (int j = lane; j < tk.k2_count; j += 32) {
+            const int w = max(max(pbest[j], jbest[j]), before);
+            const int score = (w + 0x8000) >> 16;
+            out[tk.out_off + j] = make_int2(score, w - (score << 16));
+        }
     }
     __syncwarp();
 }
@@ -288,7 +329,7 @@ ladder_bwd_kernel(const LadBwdTask* __restrict__ tasks, int n_tasks, const uint3
 __global__ void __launch_bounds__(32 * kWarps)
 ladder_fwd_kernel(const LadFwdTask* __restrict__ tasks, int n_tasks, const LadBwdTask* __restrict__ btasks,
                   const uint32_t* __restrict__ pool, WinScore sc, int4* scratch, int scratch_stride, int* counter,
-                  const int* __restrict__ bvec, const int* __restrict__ ronly, int2* out) {
+                  const int* __restrict__ bvec, const int* __restrict__ ronly, int* cstate, int* pbest1, int2* out) {
     extern __shared__ int wsmem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int* base = wsmem + warp * (8 * kRows + 3 * kRows + 2 * kMaxK2);
@@ -303,7 +344,12 @@ ladder_fwd_kernel(const LadFwdTask* __restrict__ tasks, int n_tasks, const LadBw
         i = __shfl_sync(kFull, i, 0);
         if (i >= n_tasks) break;
         const LadFwdTask tk = tasks[i];
-        ladder_fwd_task(tk, pool, sc, prof, bsm, jbest, pbest, bnd, bvec + btasks[tk.bwd].bvec_off, ronly[tk.bwd], out, lane);
+        if (tk.mode == kPrefix)
+            ladder_fwd_task<kPrefix>(tk, pool, sc, prof, bsm, jbest, pbest, bnd, bvec, 0, cstate, pbest1, out, lane);
+        else if (tk.mode == kCont)
+            ladder_fwd_task<kCont>(tk, pool, sc, prof, bsm, jbest, pbest, bnd, bvec + btasks[tk.bwd].bvec_off, ronly[tk.bwd], cstate, pbest1, out, lane);
+        else
+            ladder_fwd_task<kWhole>(tk, pool, sc, prof, bsm, jbest, pbest, bnd, bvec + btasks[tk.bwd].bvec_off, ronly[tk.bwd], cstate, pbest1, out, lane);
     }
 }
 

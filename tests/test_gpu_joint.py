@@ -123,13 +123,15 @@ def _grid_points(rng, n_reads, k1_lists, k2_lists):
     return pr, p1, p2
 
 
-@pytest.mark.parametrize("n_left,n_right", [(1000, 1000), (300, 10), (7, 40)])
-def test_joint_grid_shared_sweeps_equal_rectangles(engine, oracle, n_left, n_right):
-    """nr_joint_grid scores full K1 x K2 grids with shared sweeps (nr_window_ladder.cuh); every grid point must equal the
-    rectangle of its own template (nr_window_tasks, both strands, better strand), and the CPU oracle on a sample."""
+@pytest.mark.parametrize("n_left,n_right,mid", [(1000, 1000, "CAACAGCCGCCA"), (300, 10, "CAACAGCCGCCA"), (7, 40, "CAACAGCCGCCA"),
+                                                (200, 200, ""), (150, 120, "T")])
+def test_joint_grid_shared_sweeps_equal_rectangles(engine, oracle, n_left, n_right, mid):
+    """nr_joint_grid scores full K1 x K2 grids with shared sweeps (nr_window_ladder.cuh: arithmetic K1 -> one prefix sweep and
+    a continuation per k1, otherwise one forward sweep per k1; an empty mid with k2 from 0 takes the latter); every grid
+    point must equal the rectangle of its own template (nr_window_tasks, both strands, better strand), and the CPU oracle on a sample."""
     rng = random.Random(1000 * n_left + n_right)
     sc = engine.get_preset("ont")
-    left, right, mid = _rs(rng, n_left), _rs(rng, n_right), "CAACAGCCGCCA"
+    left, right = _rs(rng, n_left), _rs(rng, n_right)
     m1, m2 = "CAG", "CCG"
     reads, K1s, K2s = [], [], []
     for i in range(36):

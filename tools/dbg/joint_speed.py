@@ -10,7 +10,7 @@ sc = engine.get_preset("ont")
 ok1 = loc["range1"]; ok2 = loc["range2"]
 s1 = joint.choose_best_step_size(3, ok1); s2 = joint.choose_best_step_size(3, ok2)
 pr, p1, p2 = joint.round2_grid_points(ok1, ok2, min(a for a, _ in ok1), max(b for _, b in ok1), min(a for a, _ in ok2), max(b for _, b in ok2), s1, s2)
-cells = sum(len(loc["reads"][r]) * (2000 + 3 * k1 + 12 + 3 * k2) * 2 for r, k1, k2 in zip(pr, p1, p2))
+cells = sum(len(loc["reads"][int(r)]) * (2000 + 3 * int(k1) + 12 + 3 * int(k2)) * 2 for r, k1, k2 in zip(pr, p1, p2))
 for _ in range(2):
     t0 = time.perf_counter(); rec, strand = engine.joint_grid(sc, loc["left"], loc["mid"], loc["right"], "CAG", "CCG", loc["reads"], pr, p1, p2); dt = time.perf_counter() - t0
 print(f"{n} reads, steps {s1} {s2}, {len(pr)} grid points, {cells/1e9:.1f} Gcells, {dt*1e3:.1f} ms, {cells/dt/1e9:.0f} GCUPS (wall, incl. packing)")
