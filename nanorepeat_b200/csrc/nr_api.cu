@@ -424,7 +424,9 @@ struct PhaseTrace {
     void mark(const char* what) {
         if (!on) return;
         const auto t1 = std::chrono::steady_clock::now();
-        fprintf(stderr, "[nr trace] %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t1 - t0).count());
+        fprintf(stderr, "[nr trace] %-28s %8.1f us   (ends at %10.1f us, thread %04x)\n", what,
+                std::chrono::duration<double, std::micro>(t1 - t0).count(), std::fmod(std::chrono::duration<double, std::micro>(t1.time_since_epoch()).count(), 1e8),
+                (unsigned)(std::hash<std::thread::id>()(std::this_thread::get_id()) & 0xffff));
         t0 = t1;
     }
 };
@@ -1445,7 +1447,10 @@ void nr_batch_destroy(nr_batch_t* b) {
     if (!b) return;
     if (--b->refs > 0) return;           // a round-3 batch still reads this batch's packed reads: freed with it
     if (b->committed && b->ev_uploaded) cudaEventSynchronize(b->ev_uploaded);   // buffers return to the cache: the upload
-    if (b->ran && b->run_stream) cudaStreamSynchronize(b->run_stream);          // and the kernels must be done
+    // ... and the kernels and result copies must be done: this batch's own (its event), not whatever another thread's
+    // call has queued behind them on the same stream
+    if (b->ran && b->ev_done) cudaEventSynchronize(b->ev_done);
+    else if (b->ran && b->run_stream) cudaStreamSynchronize(b->run_stream);
     cached_free(b->d_blob, b->blob_bytes, BUF_DEV);
     cached_free(b->h_blob, b->blob_bytes, BUF_PIN);
     cached_free(b->d_out, b->out_bytes, BUF_DEV);

@@ -473,8 +473,10 @@ def _joined(strings):
     return big, ptr, off
 
 
-def estimate_regions(sc, fast_mode, lefts, rights, motifs, cores, dists, max_dists=None):
+def estimate_regions(sc, fast_mode, lefts, rights, motifs, cores, dists, max_dists=None, on_ready=None):
     """nr_estimate_regions: rounds 1-3 of many regions in one call into the library.
+    on_ready: called once the arguments are built, right before the library is entered (where ctypes drops the GIL) -- a
+    caller that runs this on a worker thread uses it to know when its own Python work can go on without competing.
     lefts / rights / motifs: one str per region; cores: one list of str per region (at least one read each); dists: all
     reads' dist_between_anchors, flat, in the same order; max_dists: per region None or the whole region's longest
     distance when the region is a piece of a split one.
@@ -518,6 +520,8 @@ def estimate_regions(sc, fast_mode, lefts, rights, motifs, cores, dists, max_dis
     T = np.zeros(max(n, 1), np.int32)
     st = Stats()
     dp = ctypes.POINTER(ctypes.c_double)
+    if on_ready is not None:
+        on_ready()
     _check(lib().nr_estimate_regions(ctypes.byref(sc), int(bool(fast_mode)), n, ctypes.cast(tab.ctypes.data, ctypes.POINTER(RegionIn)),
                                      r1.ctypes.data_as(dp), r2.ctypes.data_as(dp), r2_valid.ctypes.data, r3.ctypes.data_as(dp),
                                      r3_state.ctypes.data, T.ctypes.data_as(_i32p), ctypes.byref(st)))

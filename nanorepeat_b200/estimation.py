@@ -300,11 +300,17 @@ def _gather_chunk(rrs):
     return (lefts, rights, motifs, cores, dists, max_dists if any_max else None), todo
 
 
-def _run_chunk(sc, fast_mode, cols):
-    """One call into the library (ctypes releases the GIL for its duration)."""
+def _run_chunk(sc, fast_mode, cols, ready=None):
+    """One call into the library (ctypes releases the GIL for its duration).  ready: a threading.Event set when this
+    thread's Python work is over (the library entered, or the call failed before that)."""
     lefts, rights, motifs, cores, dists, max_dists = cols
     try:
-        return engine.estimate_regions(sc, fast_mode, lefts, rights, motifs, cores, dists, max_dists)
+        try:
+            return engine.estimate_regions(sc, fast_mode, lefts, rights, motifs, cores, dists, max_dists,
+                                           on_ready=ready.set if ready is not None else None)
+        finally:
+            if ready is not None:
+                ready.set()
     except engine.NanoRepeatB200Error as e:
         if e.code != -3:
             raise
@@ -381,11 +387,16 @@ def _estimate_regions_fused(dt, fast_mode, rrs):
     if _POOL is None:
         from concurrent.futures import ThreadPoolExecutor
         _POOL = ThreadPoolExecutor(max_workers=2, thread_name_prefix="nanorepeat_b200")
+    import threading
     pending = []
     for ch in chunks:
         cols, todo = _gather_chunk(ch)
         if todo:
-            pending.append((_POOL.submit(_run_chunk, sc, fast_mode, cols), todo))
+            # hand the chunk over and let the worker build its arguments NOW (it needs the interpreter for that; this
+            # thread would otherwise keep it through the next gather and the worker would start half a millisecond late)
+            ready = threading.Event()
+            pending.append((_POOL.submit(_run_chunk, sc, fast_mode, cols, ready), todo))
+            ready.wait()
         while pending and pending[0][0].done():
             fut, td = pending.pop(0)
             _assign_chunk(fut.result(), td)
