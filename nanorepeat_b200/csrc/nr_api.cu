@@ -24,6 +24,7 @@
 #include <new>
 #include <string>
 #include <thread>
+#include <memory>
 #include <unordered_map>
 #include <vector>
 
@@ -980,6 +981,22 @@ int launch_rest(nr_batch* b, cudaStream_t st, const nr::ScoreW& k, const int32_t
     return NR_OK;
 }
 
+// A stream of the calling thread's own for launches without cooperating stripes.  Two nr_estimate_regions calls on two
+// threads then overlap on the GPU block by block: as the persistent blocks of one call's kernel run out of work, the
+// other call's blocks take their SMs, instead of the whole second kernel waiting behind the first one's tail on the
+// library's one stream.  Launches WITH cooperating stripes (long reads) stay on the library's stream: their blocks wait
+// for one another, so two of them must never share the GPU half-resident each.
+thread_local cudaStream_t t_aux_stream = nullptr;
+cudaStream_t aux_stream_for(const nr_batch* b) {
+    static const bool off = getenv("NR_ONE_STREAM") != nullptr;
+    if (off || !b->coop.empty()) return nullptr;
+    if (!t_aux_stream && cudaStreamCreateWithFlags(&t_aux_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        t_aux_stream = nullptr;
+    }
+    return t_aux_stream;
+}
+
 int run_batch(nr_batch* b, cudaStream_t st) {
     if (!b->committed) return fail(NR_ERR_ARG, "batch was not committed");
     b->run_stream = st;
@@ -1862,7 +1879,7 @@ int estimate_regions(const nr_scoring_t* sc, int fast_mode, int n_regions, const
     // (measured on the 60 000-read slice of config 3: groups of 16 384 reads 49 ms end to end, of 4 096 reads 63 ms --
     // a launch of 2 500 pairs on 2 368 warp slots takes as long as one of 4 700; on config 2's 10 000 reads two groups of
     // 5 000 beat one of 10 000 by 0.3 ms)
-    long long kMinReads = total >= 32768 ? 16384 : 4096;
+    long long kMinReads = total >= 12288 ? 16384 : 4096;
     if (const char* e = getenv("NR_GROUP_READS")) kMinReads = std::max(256, atoi(e));      // tuning
     long long total_bases = 0;
     for (int g = 0; g < n_regions; ++g) total_bases += regs[g].reads_len;
@@ -1909,31 +1926,81 @@ int estimate_regions(const nr_scoring_t* sc, int fast_mode, int n_regions, const
         G.b2->pool.words.reserve((size_t)(bases / 16 + 2 * n_reads + 4 * (long long)G.regs.size() + 64));
         G.b2->tasks.reserve((size_t)n_reads);
     }
-    auto pack_group = [&](Group& G) {
-        if (!G.b2) return;
-        for (int g : G.regs) {
-            const nr_region_t& R = regs[g];
-            const int rc1 = nr_batch_add_round2_lines(G.b2, R.left, R.n_left, R.motif, R.motif_len, T[g], R.n_reads, R.reads, R.reads_len);
-            if (rc1) { G.rc = rc1; G.err = g_err; return; }      // (the message lives in this thread's g_err)
-        }
-    };
+    // Packing jobs: a group's regions in runs of about 4 096 reads, each run packed by one host thread into a batch of
+    // its own (no CUDA objects), the runs then appended to the group's batch in order (word indices shifted).
+    struct Job { Group* G; size_t i0, i1; std::unique_ptr<nr_batch> part; int rc = NR_OK; std::string err; };
+    std::vector<Job> jobs;
     {
-        const int nt = std::min<int>((int)groups.size(), host_threads());
+        const int nt_all = host_threads();
+        for (Group& G : groups) {
+            if (!G.b2) continue;
+            long long n_reads = 0;
+            for (int g : G.regs) n_reads += regs[g].n_reads;
+            const int parts = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(nt_all, 16), n_reads / 4096));
+            const double per = (double)n_reads / parts;
+            long long acc = 0;
+            size_t start = 0;
+            int made = 0;
+            for (size_t i = 0; i < G.regs.size(); ++i) {
+                acc += regs[G.regs[i]].n_reads;
+                if (made < parts - 1 && acc >= per * (made + 1)) { jobs.push_back({&G, start, i + 1, nullptr}); start = i + 1; ++made; }
+            }
+            if (start < G.regs.size()) jobs.push_back({&G, start, G.regs.size(), nullptr});
+        }
+        auto pack_job = [&](Job& J) {
+            J.part.reset(new (std::nothrow) nr_batch());
+            if (!J.part) { J.rc = NR_ERR_NOMEM; J.err = "out of host memory"; return; }
+            nr_batch* pb = J.part.get();
+            pb->kind = KIND_ROUND2;
+            pb->sc = *sc;
+            long long bases = 0, n_reads = 0;
+            for (size_t i = J.i0; i < J.i1; ++i) {
+                const nr_region_t& R = regs[J.G->regs[i]];
+                bases += R.reads_len + R.n_left + (long long)R.motif_len * T[J.G->regs[i]];
+                n_reads += R.n_reads;
+            }
+            pb->pool.words.reserve((size_t)(bases / 16 + 2 * n_reads + 4 * (long long)(J.i1 - J.i0) + 64));
+            pb->tasks.reserve((size_t)n_reads);
+            for (size_t i = J.i0; i < J.i1; ++i) {
+                const int g = J.G->regs[i];
+                const nr_region_t& R = regs[g];
+                const int rc1 = nr_batch_add_round2_lines(pb, R.left, R.n_left, R.motif, R.motif_len, T[g], R.n_reads, R.reads, R.reads_len);
+                if (rc1) { J.rc = rc1; J.err = g_err; return; }      // (the message lives in this thread's g_err)
+            }
+        };
+        const int nt = std::min<int>((int)jobs.size(), nt_all);
         if (nt <= 1) {
-            for (Group& G : groups) pack_group(G);
+            for (Job& J : jobs) pack_job(J);
         } else {
             std::atomic<int> next{0};
-            auto work = [&]() { for (int i; (i = next.fetch_add(1)) < (int)groups.size();) pack_group(groups[i]); };
+            auto work = [&]() { for (int i; (i = next.fetch_add(1)) < (int)jobs.size();) pack_job(jobs[i]); };
             std::vector<std::thread> th;
             for (int t = 1; t < nt; ++t) th.emplace_back(work);
             work();
             for (auto& x : th) x.join();
         }
+        for (Job& J : jobs) {
+            Group& G = *J.G;
+            if (G.rc) continue;
+            if (J.rc) { G.rc = J.rc; G.err = J.err; continue; }
+            nr_batch* pb = J.part.get();
+            nr_batch* b = G.b2;
+            const size_t base_w = b->pool.words.size();
+            if (base_w + pb->pool.words.size() > 0xfffffff0ULL) { G.rc = NR_ERR_TOO_LARGE; G.err = "sequence pool exceeds 2^32 words"; continue; }
+            b->pool.words.insert(b->pool.words.end(), pb->pool.words.begin(), pb->pool.words.end());
+            const size_t base_t = b->tasks.size();
+            b->tasks.insert(b->tasks.end(), pb->tasks.begin(), pb->tasks.end());
+            for (size_t t = base_t; t < b->tasks.size(); ++t) { b->tasks[t].q_word += (uint32_t)base_w; b->tasks[t].t_word += (uint32_t)base_w; }
+            for (RegionInfo& ri : pb->regions) { ri.first_read += b->n_reads; b->regions.push_back(std::move(ri)); }
+            b->n_reads += pb->n_reads;
+            b->n_ambiguous_reads += pb->n_ambiguous_reads;
+            J.part.reset();
+        }
     }
     trace.mark("estimate: round-2 add (pack, threads)");
     for (Group& G : groups) {
         if (G.rc) { const int rc1 = G.rc; const std::string msg = G.err; cleanup(); return fail(rc1, "%s", msg.c_str()); }
-        if (G.b2 && ((rc = nr_batch_commit(G.b2)) || (rc = nr_batch_run(G.b2, nullptr)))) { cleanup(); return rc; }
+        if (G.b2 && ((rc = nr_batch_commit(G.b2)) || (rc = nr_batch_run(G.b2, aux_stream_for(G.b2))))) { cleanup(); return rc; }
         trace.mark("estimate: round-2 commit + run");
     }
     // round-2 selection and the launch of round 3 (was pymm2.main per read at :497), group by group
@@ -1965,7 +2032,7 @@ int estimate_regions(const nr_scoring_t* sc, int fast_mode, int n_regions, const
             if ((rc = nr_batch_add_round3_reuse(G.b3, (int)i, R.right, R.n_right, kmin.data(), kmax.data()))) { cleanup(); return rc; }
         }
         trace.mark("estimate: select 2 + round-3 add");
-        if ((rc = nr_batch_commit(G.b3)) || (rc = nr_batch_run(G.b3, nullptr))) { cleanup(); return rc; }
+        if ((rc = nr_batch_commit(G.b3)) || (rc = nr_batch_run(G.b3, aux_stream_for(G.b3)))) { cleanup(); return rc; }
         trace.mark("estimate: round-3 commit + run");
     }
     // round-3 selection (:423-433)

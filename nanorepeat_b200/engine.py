@@ -4,6 +4,7 @@ The library is built in-tree by __graft_entry__.build() / `make -C nanorepeat_b2
 a missing GPU is an error -- there is no fallback path.
 """
 import ctypes
+import itertools
 import os
 
 import numpy as np
@@ -473,21 +474,29 @@ def _joined(strings):
     return big, ptr, off
 
 
-def estimate_regions(sc, fast_mode, lefts, rights, motifs, cores, dists, max_dists=None, on_ready=None):
+def estimate_regions(sc, fast_mode, lefts, rights, motifs, cores, dists, max_dists=None, on_ready=None, n_reads=None):
     """nr_estimate_regions: rounds 1-3 of many regions in one call into the library.
+    lefts / rights / motifs: one str per region; cores: one list of str per region (at least one read each) -- or, with
+    n_reads given (reads per region), ONE flat list of all regions' reads in order; dists: all reads'
+    dist_between_anchors, flat, in the same order; max_dists: per region None or the whole region's longest distance when
+    the region is a piece of a split one.
     on_ready: called once the arguments are built, right before the library is entered (where ctypes drops the GIL) -- a
     caller that runs this on a worker thread uses it to know when its own Python work can go on without competing.
-    lefts / rights / motifs: one str per region; cores: one list of str per region (at least one read each); dists: all
-    reads' dist_between_anchors, flat, in the same order; max_dists: per region None or the whole region's longest
-    distance when the region is a piece of a split one.
     -> dict of arrays over all reads in order: r1, r2, r2_valid, r3, r3_state (0 None / 1 mean of rungs / 2 = r2), plus T
-    per region and the summed stats.  The table of regions is built column by column (no per-region ctypes work)."""
+    per region and the summed stats.  The table of regions is built column by column (no per-region ctypes work) and the
+    reads travel as ONE buffer of lines (a single join)."""
     n = len(lefts)
     dists = np.ascontiguousarray(dists, dtype=np.int32)
-    n_reads = np.fromiter(map(len, cores), np.int64, n)
+    if n_reads is None:
+        n_reads = np.fromiter(map(len, cores), np.int64, n)
+        cores = list(itertools.chain.from_iterable(cores))
+    else:
+        n_reads = np.ascontiguousarray(n_reads, dtype=np.int64)
     total = int(n_reads.sum())
-    if total != len(dists):
+    if total != len(dists) or total != len(cores) or len(n_reads) != n:
         raise ValueError("cores and dist_between_anchors differ in length")
+    if n and int(n_reads.min()) < 1:
+        raise ValueError("every region needs at least one read")
     tab = np.zeros(max(n, 1), REGION_DTYPE)
     keep = []
     for name, seqs in (("left", lefts), ("right", rights), ("motif", motifs)):
@@ -495,18 +504,20 @@ def estimate_regions(sc, fast_mode, lefts, rights, motifs, cores, dists, max_dis
         keep.append(big)
         tab[name][:n] = ptr + off[:-1]
         tab["n_" + name if name != "motif" else "motif_len"][:n] = off[1:] - off[:-1]
-    lines = ["\n".join(c) for c in cores]                 # a region's reads as lines
-    big = "\n".join(lines)
+    big = "\n".join(cores)                               # every read a line; a region = n_reads consecutive lines
     size = ctypes.c_ssize_t()
     ptr = _utf8(big, ctypes.byref(size))
     keep.append(big)
-    llen = np.fromiter(map(len, lines), np.int64, n)
+    first = np.zeros(n + 1, np.int64)
+    np.cumsum(n_reads, out=first[1:])
+    clen = np.fromiter(map(len, cores), np.int64, total)
+    csum = np.zeros(total + 1, np.int64)
+    np.cumsum(clen, out=csum[1:])
+    llen = csum[first[1:]] - csum[first[:-1]] + (n_reads - 1)                 # a region's lines with the breaks between them
     start = np.zeros(n + 1, np.int64)
     np.cumsum(llen + 1, out=start[1:])
     if not ptr or (n and size.value != start[-1] - 1):
         raise ValueError("reads must be ASCII text")
-    first = np.zeros(n + 1, np.int64)
-    np.cumsum(n_reads, out=first[1:])
     tab["reads"][:n] = ptr + start[:-1]
     tab["reads_len"][:n] = llen
     tab["n_reads"][:n] = n_reads

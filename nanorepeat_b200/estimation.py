@@ -11,6 +11,8 @@ rungs) stays here in Python/numpy float64, written exactly as the reference writ
 """
 import weakref
 
+import os
+
 import numpy as np
 
 from . import engine
@@ -267,7 +269,7 @@ def round3_estimation(data_type, fast_mode, repeat_region, num_cpu=1):
 
 def _gather_chunk(rrs):
     """What nr_estimate_regions needs of a list of regions, column by column, plus the Read objects in result order."""
-    lefts, rights, motifs, cores, max_dists, todo = [], [], [], [], [], []
+    lefts, rights, motifs, cores, counts, max_dists, todo = [], [], [], [], [], [], []
     any_max = False
     for rr in rrs:
         reads = rr.read_dict
@@ -279,7 +281,7 @@ def _gather_chunk(rrs):
         max_dist = getattr(rr, "round1_max_dist", None)                         # a piece of a split region (sharding)
         if core_dict.keys() >= reads.keys():
             read_list = list(reads.values())
-            cores.append(list(map(core_dict.__getitem__, reads)))
+            cores.extend(map(core_dict.__getitem__, reads))
         else:
             m = len(rr.repeat_unit_seq)
             extra = [rd for n, rd in reads.items() if n not in core_dict]
@@ -291,23 +293,24 @@ def _gather_chunk(rrs):
             if not qnames:
                 continue
             read_list = list(map(reads.__getitem__, qnames))
-            cores.append(list(map(core_dict.__getitem__, qnames)))
+            cores.extend(map(core_dict.__getitem__, qnames))
         any_max = any_max or max_dist is not None
         lefts.append(rr.left_anchor_seq); rights.append(rr.right_anchor_seq); motifs.append(rr.repeat_unit_seq)
         max_dists.append(max_dist)
-        todo.append(read_list)
-    dists = [rd.dist_between_anchors for read_list in todo for rd in read_list]
-    return (lefts, rights, motifs, cores, dists, max_dists if any_max else None), todo
+        counts.append(len(read_list))
+        todo.extend(read_list)
+    dists = [rd.dist_between_anchors for rd in todo]
+    return (lefts, rights, motifs, cores, dists, max_dists if any_max else None, counts), todo
 
 
 def _run_chunk(sc, fast_mode, cols, ready=None):
     """One call into the library (ctypes releases the GIL for its duration).  ready: a threading.Event set when this
     thread's Python work is over (the library entered, or the call failed before that)."""
-    lefts, rights, motifs, cores, dists, max_dists = cols
+    lefts, rights, motifs, cores, dists, max_dists, counts = cols
     try:
         try:
             return engine.estimate_regions(sc, fast_mode, lefts, rights, motifs, cores, dists, max_dists,
-                                           on_ready=ready.set if ready is not None else None)
+                                           on_ready=ready.set if ready is not None else None, n_reads=counts)
         finally:
             if ready is not None:
                 ready.set()
@@ -316,39 +319,40 @@ def _run_chunk(sc, fast_mode, cols, ready=None):
             raise
         # a core with a line break inside or around it (the reads travel as lines): the reference's FASTQ round trip
         # drops white space around a read (:311-321), so do that here and go again
-        cores = [[c.strip() for c in cl] for cl in cores]
-        return engine.estimate_regions(sc, fast_mode, lefts, rights, motifs, cores, dists, max_dists)
+        cores = [c.strip() for c in cores]
+        return engine.estimate_regions(sc, fast_mode, lefts, rights, motifs, cores, dists, max_dists, n_reads=counts)
 
 
 def _assign_chunk(res, todo):
-    r1, r2, r3 = res["r1"].tolist(), res["r2"].tolist(), res["r3"]
-    ok2, st3 = res["r2_valid"].tolist(), res["r3_state"].tolist()
+    r3 = res["r3"]
     pos = 0
-    for read_list in todo:
-        for rd in read_list:
-            rd.round1_repeat_size = r1[pos]                                     # :341
-            if ok2[pos]:
-                v = r2[pos]
-                rd.round2_repeat_size = v                                       # :375-384
-                s = st3[pos]
-                if s == 1:
-                    rd.round3_repeat_size = r3[pos]                             # :431 (np.float64, like np.mean)
-                elif s == 2:
-                    rd.round3_repeat_size = v                                   # :433
-            pos += 1
+    for rd, a, ok, v, s in zip(todo, res["r1"].tolist(), res["r2_valid"].tolist(), res["r2"].tolist(), res["r3_state"].tolist()):
+        rd.round1_repeat_size = a                                               # :341
+        if ok:
+            rd.round2_repeat_size = v                                           # :375-384
+            if s == 1:
+                rd.round3_repeat_size = r3[pos]                                 # :431 (np.float64, like np.mean)
+            elif s == 2:
+                rd.round3_repeat_size = v                                       # :433
+        pos += 1
 
 
 CHUNK_MIN_READS = 4096      # reads per call into the library when a region list is cut into pipelined chunks
+BIG_CHUNK_READS = 16384     # ... for lists of 16 384 reads and more
 _POOL = None
 
 
 def _chunks(rrs):
     """Contiguous chunks of regions of at least CHUNK_MIN_READS reads each, at most 6."""
     total = sum(len(rr.read_dict) for rr in rrs)
-    # a mid-sized call (config 2: two regions of 5 000 reads) gains from two calls in flight; a big one is cut into groups
-    # of 16 384 reads inside the library, where more and smaller launches only cost (measured: 49 against 63-72 ms on
-    # config 3's 60 000-read slice)
-    n = max(1, min(6, total // CHUNK_MIN_READS)) if total < 4 * CHUNK_MIN_READS else 1
+    # A call's Python side (gathering strings before, assigning attributes after) is as long as its kernels; cut in chunks,
+    # one chunk's Python side runs while the library and the GPU work on its neighbours.  Chunks of CHUNK_MIN_READS for a
+    # mid-sized list (config 2: two regions of 5 000 reads -> two calls in flight), of BIG_CHUNK_READS for a long one
+    # (one launch per round and chunk inside the library; smaller launches only cost there).
+    per = CHUNK_MIN_READS if total < 4 * CHUNK_MIN_READS else BIG_CHUNK_READS
+    n = max(1, min(8, total // per))
+    if os.environ.get("NR_PY_CHUNKS"):
+        n = max(1, int(os.environ["NR_PY_CHUNKS"]))
     if n > 1:
         # long reads (a kilobase and more on average, judged on a sample): the kernels dwarf the Python side and every
         # launch pays the serial chain of its longest read's stripes, so one call with everything is the fastest
@@ -386,7 +390,7 @@ def _estimate_regions_fused(dt, fast_mode, rrs):
         return
     if _POOL is None:
         from concurrent.futures import ThreadPoolExecutor
-        _POOL = ThreadPoolExecutor(max_workers=2, thread_name_prefix="nanorepeat_b200")
+        _POOL = ThreadPoolExecutor(max_workers=3, thread_name_prefix="nanorepeat_b200")
     import threading
     pending = []
     for ch in chunks:
