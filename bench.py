@@ -119,6 +119,18 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def clock_snapshot(gpu_index):
+    """One reading of the SM clock and the throttle reasons (outside any timed section)."""
+    try:
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={ClockSampler.Q}", "--format=csv,noheader,nounits", "-i", str(gpu_index)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        return {"sm_mhz": float(out[1]), "sm_max_mhz": float(out[2]),
+                "reasons": [n for n, v in zip(names, out[5:9]) if v.strip().lower().startswith("active")]}
+    except (OSError, ValueError, IndexError, subprocess.TimeoutExpired):
+        return None
+
+
 def headline_config(args):
     """`config` of the JSON line: the same dictionary in both arms (the driver compares them)."""
     return {"workload": HEADLINE, "reads": args.reads, "regions": 2, "seed": args.seed, "passes_per_step": args.passes,
@@ -574,6 +586,11 @@ def main():
     ev_ms, kern_ms = time_resident(wl, torch, stream, flush, max(2, K // 4), P, engine)      # per-kernel event times
     linfo = [wl.b2.launch_info(), wl.b3.launch_info()]
     n_ev = max(2, K // 4) * P
+    # the 100 ms clock poll covers the device-timed region above and stops here: every NVML query stalls the CUDA calls
+    # of this process for a while, which a host-timed 6 ms pass feels (measured: +0.8 ms per pass under the poll); the e2e
+    # passes get one clock reading before and one after instead
+    clocks = sampler.stop()
+    clocks["e2e_before"] = clock_snapshot(local_rank)
     # e2e through the operator API
     e2e_passes = max(K, 10)
     for _ in range(2):
@@ -582,7 +599,7 @@ def main():
     e2e_s = time_e2e(wl, torch, e2e_passes)
     c_abi_ms = time_c_abi(wl, torch, e2e_passes)
     barrier()
-    clocks = sampler.stop()
+    clocks["e2e_after"] = clock_snapshot(local_rank)
     total_ms = float(sum(dev_ms))
 
     # resumed round 3 (from round 2's kept state) == a fresh round-3 batch (full forward sweeps): checked on every run
