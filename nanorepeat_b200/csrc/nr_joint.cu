@@ -255,12 +255,26 @@ extern "C" int nr_joint_grid(const nr_scoring_t* sc, const char* left, int32_t n
         return nri::fail_msg(NR_ERR_ARG, "nr_joint_grid: bad arguments");
     int rc = nri::ensure_init();
     if (rc) return rc;
+    const bool tracing = getenv("NR_TRACE") != nullptr;
+    auto t_mark = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!tracing) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[nr trace] joint grid: %-24s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t1 - t_mark).count());
+        t_mark = t1;
+    };
     SeqPool pool;
     std::vector<long long> read_word(n_reads);
+    {
+        size_t words = 0;
+        for (int r = 0; r < n_reads; ++r) words += (size_t)(std::max(read_len[r], 0) + 15) / 16 + 2;
+        pool.words.reserve(words + 4096);
+    }
     for (int r = 0; r < n_reads; ++r) {
         if (read_len[r] < 0) return nri::fail_msg(NR_ERR_ARG, "nr_joint_grid: negative read length");
         read_word[r] = pool.add(reads[r], read_len[r], true);
     }
+    mark("pack reads");
     for (int i = 0; i < n_points; ++i) {
         if (point_read[i] < 0 || point_read[i] >= n_reads || point_k1[i] < 0 || point_k2[i] < 0)
             return nri::fail_msg(NR_ERR_ARG, "nr_joint_grid: bad grid point");
@@ -297,9 +311,17 @@ extern "C" int nr_joint_grid(const nr_scoring_t* sc, const char* left, int32_t n
             std::sort(K1.begin(), K1.end()); K1.erase(std::unique(K1.begin(), K1.end()), K1.end());
             std::sort(K2.begin(), K2.end()); K2.erase(std::unique(K2.begin(), K2.end()), K2.end());
             if (K2.size() > (size_t)nrw::kMaxK2) continue;
-            std::map<std::pair<int, int>, int> seen;
-            for (int i : pts) ++seen[{point_k1[i], point_k2[i]}];
-            if (seen.size() != K1.size() * K2.size()) continue;                      // not a full grid
+            // a full grid: every (k1, k2) of K1 x K2 is among the points (duplicates allowed)
+            auto idx1 = [&](int k) { return (size_t)(std::lower_bound(K1.begin(), K1.end(), k) - K1.begin()); };
+            auto idx2 = [&](int k) { return (size_t)(std::lower_bound(K2.begin(), K2.end(), k) - K2.begin()); };
+            std::vector<uint8_t> seen(K1.size() * K2.size(), 0);
+            size_t distinct = 0;
+            for (int i : pts) {
+                uint8_t& c = seen[idx1(point_k1[i]) * K2.size() + idx2(point_k2[i])];
+                distinct += c == 0;
+                c = 1;
+            }
+            if (distinct != seen.size()) continue;                                   // not a full grid
             const int k2_step = K2.size() > 1 ? K2[1] - K2[0] : 1;
             bool arithmetic = true;
             for (size_t j = 1; j < K2.size(); ++j) arithmetic = arithmetic && K2[j] - K2[j - 1] == k2_step;
@@ -355,7 +377,7 @@ extern "C" int nr_joint_grid(const nr_scoring_t* sc, const char* left, int32_t n
                 bvec_words += 3 * (size_t)read_len[r];
                 btasks.push_back(bt);
             }
-            std::map<std::pair<int, int>, int> slot;                                 // (k1, k2) -> record of strand '+'
+            std::vector<int> slot(K1.size(), 0);                                     // k1 index -> first record of strand '+'
             int pre_pbest[2] = {0, 0};
             long long pre_cstate[2] = {0, 0};
             if (share_k1)
@@ -389,18 +411,19 @@ extern "C" int nr_joint_grid(const nr_scoring_t* sc, const char* left, int32_t n
                     }
                     ft.m2 = m2; ft.k2_first = K2[0]; ft.k2_step = k2_step; ft.k2_count = (int)K2.size();
                     ft.win_a = win_a; ft.reverse = sd; ft.bwd = b0 + sd; ft.out_off = (int)n_lad_out;
-                    if (sd == 0) for (size_t j = 0; j < K2.size(); ++j) slot[{K1[a], K2[j]}] = (int)(n_lad_out + j);
+                    if (sd == 0) slot[a] = (int)n_lad_out;
                     n_lad_out += K2.size();
                     lad_max_t = std::max(lad_max_t, ft.n_pre + m2 * K2.back());
                     ftasks.push_back(ft);
                 }
             for (int i : pts) {
                 by_ladder[i] = 1;
-                point_slot[i] = slot[{point_k1[i], point_k2[i]}];
+                point_slot[i] = slot[idx1(point_k1[i])] + (int)idx2(point_k2[i]);
                 point_slot_rev[i] = point_slot[i] + (int)K2.size();
             }
         }
     }
+    mark("tasks of the shared sweeps");
     if (!ftasks.empty()) {
         std::vector<int2> res;
         if ((rc = run_ladder_tasks(sc, btasks, ptasks, ftasks, pool, bvec_words, cstate_words, n_pbest1, n_lad_out, lad_max_t, res))) return rc;
@@ -414,6 +437,7 @@ extern "C" int nr_joint_grid(const nr_scoring_t* sc, const char* left, int32_t n
         }
     }
 
+    mark("shared sweeps + results");
     // ---- one template per distinct remaining grid point: left + motif1 * k1 + mid + motif2 * k2 + right (nanoRepeat_joint.py:351-374)
     std::map<std::pair<int, int>, std::pair<long long, int>> tpl;      // (k1, k2) -> (word, length)
     std::vector<nrw::WinTask> tasks;

@@ -121,7 +121,10 @@ __device__ __forceinline__ void ladder_bwd_task(const LadBwdTask& tk, const uint
         int hup_prev = 0, h_out = 0, f1_out = 0, f2_out = 0;
         int4 bcur = make_int4(0, 0, 0, 0);
         const int nsteps = t_len + 31;
-        for (int st = 0; st < nsteps; ++st) {
+        // One column step of this lane.  PLAIN: every lane's column lies outside the window and before the last column
+        // (off >= 11): no payload, nothing to capture -- the body the sweep runs for all but its last 42 steps.
+        auto step = [&](int st, auto plain_tag) {
+            constexpr bool PLAIN = decltype(plain_tag)::value;
             if (top && (st & 31) == 0) {
                 const int cj = st + lane;
                 bcur = cj < t_len ? __ldcg(&bin[cj]) : make_int4(0, 0, 0, 0);
@@ -137,25 +140,28 @@ __device__ __forceinline__ void ladder_bwd_task(const LadBwdTask& tk, const uint
             if (p >= 0 && p < t_len) {
                 const int off = t_len - 1 - p;
                 const int code = (tw[p >> 4] >> (30 - 2 * (p & 15))) & 3;
-                const bool in_diag = off < 10;
-                const bool in_next = off - 1 < 10 && off >= 1;                 // the next reversed column's base
-                const bool in_ins = off < 9;                                   // insertions at right-anchor position off (tk.py:477)
+                const bool in_diag = !PLAIN && off < 10;
+                const bool in_next = !PLAIN && off - 1 < 10 && off >= 1;       // the next reversed column's base
+                const bool in_ins = !PLAIN && off < 9;                         // insertions at right-anchor position off (tk.py:477)
                 const int h_open_pay = in_next ? -4 : 0, h_ext_pay = in_next ? (off - 1 == 9 ? -4 : -2) : 0;
                 const int v_open_pay = in_ins ? -4 : 0, v_ext_pay = in_ins ? -2 : 0;
                 const int ho1 = sc.open1 + h_open_pay, ho2 = sc.open2 + h_open_pay, he1 = sc.ext1 + h_ext_pay, he2 = sc.ext2 + h_ext_pay;
                 const int vo1 = sc.open1 + v_open_pay, vo2 = sc.open2 + v_open_pay, ve1 = sc.ext1 + v_ext_pay, ve2 = sc.ext2 + v_ext_pay;
                 const int* pr = prof + ((in_diag ? 4 : 0) + code) * kRows + lane * kR;
-                const bool last = p == t_len - 1;
+                const bool last = !PLAIN && p == t_len - 1;
                 int hd = hup_prev;
                 hup_prev = hup;
                 int cm = best;
+                if (last) {           // the gap states that ENTER the last column (they consume it): the spanning-gap joins
 #pragma unroll
-                for (int r = 0; r < kR; ++r) {
-                    const int hleft = H[r];
-                    if (last) {       // the gap states that ENTER the last column (they consume it): the spanning-gap joins
+                    for (int r = 0; r < kR; ++r) {
                         const int i = q_len - 2 - (s * kRows + lane * kR + r);
                         if (i >= 0) { bvec[q_len + i] = E1[r] + refund1; bvec[2 * q_len + i] = E2[r] + refund2; }
                     }
+                }
+#pragma unroll
+                for (int r = 0; r < kR; ++r) {
+                    const int hleft = H[r];
                     const int t = __vimax3_s32(hd + pr[r], E1[r], E2[r]);
                     const int h = __vimax3_s32_relu(t, f1, f2);
                     E1[r] = __viaddmax_s32(h, ho1, E1[r] + he1);
@@ -164,17 +170,23 @@ __device__ __forceinline__ void ladder_bwd_task(const LadBwdTask& tk, const uint
                     f2 = __viaddmax_s32(h, vo2, f2 + ve2);
                     hd = hleft;
                     H[r] = h;
-                    cm = max(cm, h);
-                    if (last) {
+                    if (r & 1) cm = __vimax3_s32(cm, h, H[r - 1]);
+                }
+                if (last) {
+#pragma unroll
+                    for (int r = 0; r < kR; ++r) {
                         const int i = q_len - 2 - (s * kRows + lane * kR + r);
-                        if (i >= 0) bvec[i] = h;
+                        if (i >= 0) bvec[i] = H[r];
                     }
                 }
                 best = cm;
                 h_out = H[kR - 1]; f1_out = f1; f2_out = f2;
                 if (bot && lane == 31) __stcg(&bout[p], make_int4(h_out, f1_out, f2_out, 0));
             }
-        }
+        };
+        int st = 0;
+        for (const int plain_end = min(nsteps, t_len - 11); st < plain_end; ++st) step(st, std::true_type{});   // lane 0's off >= 11
+        for (; st < nsteps; ++st) step(st, std::false_type{});
         __syncwarp();
         __threadfence_block();
     }
@@ -226,7 +238,10 @@ __device__ __forceinline__ void ladder_fwd_task(const LadFwdTask& tk, const uint
         int4 bcur = make_int4(0, 0, 0, 0);
         int jidx = 0, jcol = c_first;                  // the next junction of this lane: grid point jidx after jcol columns (>= 1)
         const int nsteps = t_len + 31;
-        for (int st = 0; st < nsteps; ++st) {
+        // One column step of this lane.  PLAIN: every lane's column lies before the window (p + 1 < a, so before every
+        // junction too): no payload, nothing to join or save -- the body of most of a sweep over a long left anchor.
+        auto step = [&](int st, auto plain_tag) {
+            constexpr bool PLAIN = decltype(plain_tag)::value;
             if (top && (st & 31) == 0) {
                 const int cj = st + lane;
                 bcur = cj < t_len ? __ldcg(&bin[cj]) : make_int4(0, 0, 0, 0);
@@ -241,15 +256,15 @@ __device__ __forceinline__ void ladder_fwd_task(const LadFwdTask& tk, const uint
             const int p = st - lane;
             if (p >= 0 && p < t_len) {
                 const int code = (tw[p >> 4] >> (30 - 2 * (p & 15))) & 3;
-                const bool in_diag = MODE == kCont || p >= a;         // (every grid point's window reaches past the junction)
-                const bool in_next = MODE == kCont || p + 1 >= a;
-                const bool in_ins = MODE == kCont || p + 1 > a;
+                const bool in_diag = !PLAIN && (MODE == kCont || p >= a);     // (every grid point's window reaches past the junction)
+                const bool in_next = !PLAIN && (MODE == kCont || p + 1 >= a);
+                const bool in_ins = !PLAIN && (MODE == kCont || p + 1 > a);
                 const int h_open_pay = in_next ? -4 : 0, h_ext_pay = in_next ? (MODE != kCont && p + 1 == a ? -4 : -2) : 0;
                 const int v_open_pay = in_ins ? -4 : 0, v_ext_pay = in_ins ? -2 : 0;
                 const int ho1 = sc.open1 + h_open_pay, ho2 = sc.open2 + h_open_pay, he1 = sc.ext1 + h_ext_pay, he2 = sc.ext2 + h_ext_pay;
                 const int vo1 = sc.open1 + v_open_pay, vo2 = sc.open2 + v_open_pay, ve1 = sc.ext1 + v_ext_pay, ve2 = sc.ext2 + v_ext_pay;
                 const int* pr = prof + ((in_diag ? 4 : 0) + code) * kRows + lane * kR;
-                const bool junc = jidx < tk.k2_count && p + 1 == jcol;
+                const bool junc = !PLAIN && jidx < tk.k2_count && p + 1 == jcol;
                 int hd = hup_prev;
                 hup_prev = hup;
                 int cm = best, jmax = 0;
@@ -265,8 +280,8 @@ __device__ __forceinline__ void ladder_fwd_task(const LadFwdTask& tk, const uint
                     f2 = __viaddmax_s32(h, vo2, f2 + ve2);
                     hd = hleft;
                     H[r] = h;
-                    cm = max(cm, h);
-                    if (MODE != kPrefix && junc) {
+                    if (r & 1) cm = __vimax3_s32(cm, h, H[r - 1]);
+                    if (!PLAIN && MODE != kPrefix && junc) {
                         const int x = lane * kR + r;
                         jmax = __vimax3_s32(jmax, h + bsm[x], e1pre + bsm[kRows + x]);
                         jmax = max(jmax, e2pre + bsm[2 * kRows + x]);
@@ -290,7 +305,11 @@ __device__ __forceinline__ void ladder_fwd_task(const LadFwdTask& tk, const uint
                 h_out = H[kR - 1]; f1_out = f1; f2_out = f2;
                 if (bot && lane == 31) __stcg(&bout[p], make_int4(h_out, f1_out, f2_out, 0));
             }
-        }
+        };
+        int st = 0;
+        if (MODE != kCont)
+            for (const int plain_end = min(nsteps, a - 1); st < plain_end; ++st) step(st, std::true_type{});   // lane 0: p + 1 < a
+        for (; st < nsteps; ++st) step(st, std::false_type{});
         __syncwarp();
         __threadfence_block();
     }
