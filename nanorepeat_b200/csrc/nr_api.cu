@@ -1154,8 +1154,9 @@ int add_reads(nr_batch* b, const ReadSrc& src, int n_reads, std::vector<uint32_t
     b->pool.words.resize(w, 0u);
     uint32_t* words = b->pool.words.data();
     std::vector<uint8_t> amb(n_reads, 0);
-    // ~0.1 us per read on one core: threads only pay for themselves from tens of thousands of reads on
-    parallel_for(n_reads, 8192, [&](int r) { amb[r] = !pack_seq(ptr[r], q_len[r], words + q_word[r]); });
+    // ~0.1 us per read on one core
+    static const int kPackGrain = [] { const char* e = getenv("NR_PACK_GRAIN"); return e && atoi(e) > 0 ? atoi(e) : 8192; }();
+    parallel_for(n_reads, kPackGrain, [&](int r) { amb[r] = !pack_seq(ptr[r], q_len[r], words + q_word[r]); });
     for (int r = 0; r < n_reads; ++r)
         if (amb[r]) {
             b->pool.link_plane(q_word[r], ptr[r], q_len[r]);
@@ -1926,6 +1927,7 @@ int estimate_regions(const nr_scoring_t* sc, int fast_mode, int n_regions, const
         G.b2->pool.words.reserve((size_t)(bases / 16 + 2 * n_reads + 4 * (long long)G.regs.size() + 64));
         G.b2->tasks.reserve((size_t)n_reads);
     }
+    static const long long kPackJobReads = [] { const char* e = getenv("NR_PACK_JOB_READS"); return e && atoi(e) > 0 ? (long long)atoi(e) : 4096LL; }();
     // Packing jobs: a group's regions in runs of about 4 096 reads, each run packed by one host thread into a batch of
     // its own (no CUDA objects), the runs then appended to the group's batch in order (word indices shifted).
     struct Job { Group* G; size_t i0, i1; std::unique_ptr<nr_batch> part; int rc = NR_OK; std::string err; };
@@ -1936,7 +1938,7 @@ int estimate_regions(const nr_scoring_t* sc, int fast_mode, int n_regions, const
             if (!G.b2) continue;
             long long n_reads = 0;
             for (int g : G.regs) n_reads += regs[g].n_reads;
-            const int parts = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(nt_all, 16), n_reads / 4096));
+            const int parts = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(nt_all, 16), n_reads / kPackJobReads));
             const double per = (double)n_reads / parts;
             long long acc = 0;
             size_t start = 0;
