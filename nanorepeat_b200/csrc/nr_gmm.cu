@@ -3,20 +3,25 @@
 // sd = error_rate * (10 + size), GaussianMixture(n, 'diag', n_init = 10) for n = 2, 3, ... until two components'
 // [isf(1 - o), isf(o)] intervals overlap -- for many regions at once.
 //
-// Mapping: one 128-thread block per (region, start) runs the whole EM of that start in fp64: every iteration is ONE pass
-// over the region's bootstrapped sizes that computes the responsibilities (E step) and accumulates the M step's three
-// sums per component, followed by a fixed-order block reduction (results do not depend on scheduling).  The stopping rule,
+// Mapping: one 128-thread block per (region, start) runs the whole EM of that start in fp64 -- for regions of many
+// samples (amplicon data: thousands of reads) a CLUSTER of 8 blocks whose partial sums meet through distributed shared
+// memory: every iteration is ONE pass over the region's bootstrapped sizes that computes the responsibilities (E step)
+// and accumulates the M step's three sums per component, followed by a fixed-order reduction (warps, block, cluster
+// ranks: results do not depend on scheduling).  The stopping rule,
 // the regularisation and the choice among the starts are scikit-learn's (BaseMixture.fit_predict); the random draws are
 // not: the reference uses unseeded generators (random.gauss, sklearn's k-means), this file a counter-based one
 // (splitmix64 of (seed, region, stream, index)) that the CPU checker shares -- a phased region is reproducible, and
 // independent of how regions are batched.  C ABI: nr_gmm_bootstrap, nr_gmm1d_fit, nr_phase_1d.
 #include "nr_internal.h"
 
+#include <cooperative_groups.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -34,6 +39,8 @@ constexpr int kMaxC = NR_GMM_MAX_COMPONENTS;      // components per mixture
 constexpr int kThreads = 128;
 constexpr int kBootstrap = 100;                   // split_alleles.py:83
 constexpr int kLloyd = 10;
+constexpr int kBigCluster = 8;                    // thread blocks per fit for regions of many samples (portable cluster size)
+constexpr int kBigSamples = 16384;                // ... from this many bootstrapped samples on
 constexpr double kLog2Pi = 1.8378770664093453;    // log(2 pi)
 constexpr double kEps10 = 10 * 2.220446049250313e-16;
 
@@ -75,47 +82,78 @@ __global__ void bootstrap_kernel(const double* __restrict__ sizes, const long lo
     }
 }
 
-// sum over the block of v[0..n) per thread -> every thread reads red[0..n); fixed order
-__device__ inline void block_sum(double* v, int n, double* red /* [4][kMaxVals] */, int stride) {
+constexpr int kVals = 3 * kMaxC + 2;
+
+// Sum of v[0..n) over every thread of the CLUSTER (the thread blocks that share one fit), in a fixed order: warps by
+// shuffle, the block's warps in shared memory, the cluster's blocks by rank through distributed shared memory.  Every
+// thread of every block may read tot[0..n) afterwards (all blocks hold the same totals, computed in the same order).
+__device__ inline void cluster_sum(cg::cluster_group& cluster, double* v, int n, double* red /* [4][kVals] */, double* tot /* [kVals] */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = 0; i < n; ++i) {
         double x = v[i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0) red[warp * stride + i] = x;
+        if (lane == 0) red[warp * kVals + i] = x;
     }
     __syncthreads();
     if (threadIdx.x < n) {
         double s = 0;
-        for (int w = 0; w < kThreads / 32; ++w) s += red[w * stride + threadIdx.x];
+        for (int w = 0; w < kThreads / 32; ++w) s += red[w * kVals + threadIdx.x];
         red[threadIdx.x] = s;                       // (row 0 of warp 0 is overwritten by its own column's total)
     }
-    __syncthreads();
+    const unsigned nb = cluster.num_blocks();
+    if (nb == 1) {
+        __syncthreads();
+        if (threadIdx.x < n) tot[threadIdx.x] = red[threadIdx.x];
+        __syncthreads();
+        return;
+    }
+    cluster.sync();                                 // every block's partial sums are in its red[0..n)
+    if (threadIdx.x < n) {
+        double s = 0;
+        for (unsigned r = 0; r < nb; ++r) s += cluster.map_shared_rank(red, r)[threadIdx.x];
+        tot[threadIdx.x] = s;
+    }
+    cluster.sync();                                 // nobody overwrites red while a neighbour still reads it
 }
 
-constexpr int kVals = 3 * kMaxC + 2;
-
+// One fit = one cluster of thread blocks (one block for small regions, kBigCluster for regions of many samples):
+// cluster `blockIdx.x / cluster size` is (problem, start).  Every block of the cluster walks its share of the samples,
+// the sums meet in cluster_sum, and every block then updates the same parameters redundantly (no broadcast).
 __global__ void __launch_bounds__(kThreads)
 fit_kernel(const Problem* __restrict__ problems, const double* __restrict__ data, int n_init, int max_iter, double tol, double reg_covar,
            unsigned long long seed, Fit* __restrict__ fits) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int nb = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int fit = (int)(blockIdx.x / nb);
     __shared__ double red[(kThreads / 32) * kVals];
+    __shared__ double tot[kVals];
     __shared__ double sw[kMaxC], sm[kMaxC], sv[kMaxC], spc[kMaxC], sc0[kMaxC];
-    const Problem pb = problems[blockIdx.x / n_init];
-    const int init = blockIdx.x % n_init, n = pb.n, N = pb.count;
+    const Problem pb = problems[fit / n_init];
+    const int init = fit % n_init, n = pb.n, N = pb.count;
     const double* x = data + pb.off;
+    const int first = rank * kThreads + (int)threadIdx.x, stride = nb * kThreads;      // this thread's samples
     double acc[kVals];
 
     // ---- start: means (init 0: evenly over [min, max]; else hashed sample positions), kLloyd rounds of 1-D k-means
     if (init == 0) {
         double lo = 1e300, hi = -1e300;
-        for (int i = threadIdx.x; i < N; i += kThreads) { lo = fmin(lo, x[i]); hi = fmax(hi, x[i]); }
+        for (int i = first; i < N; i += stride) { lo = fmin(lo, x[i]); hi = fmax(hi, x[i]); }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
         if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = lo; red[4 + (threadIdx.x >> 5)] = hi; }
         __syncthreads();
-        lo = fmin(fmin(red[0], red[1]), fmin(red[2], red[3]));
-        hi = fmax(fmax(red[4], red[5]), fmax(red[6], red[7]));
-        __syncthreads();
+        if (threadIdx.x == 0) {
+            red[8] = fmin(fmin(red[0], red[1]), fmin(red[2], red[3]));
+            red[9] = fmax(fmax(red[4], red[5]), fmax(red[6], red[7]));
+        }
+        if (nb > 1) cluster.sync(); else __syncthreads();
+        lo = 1e300; hi = -1e300;
+        for (int r = 0; r < nb; ++r) {
+            const double* rr = nb > 1 ? cluster.map_shared_rank(red, r) : red;
+            lo = fmin(lo, rr[8]); hi = fmax(hi, rr[9]);
+        }
+        if (nb > 1) cluster.sync(); else __syncthreads();
         if (threadIdx.x < n) sm[threadIdx.x] = lo + (threadIdx.x + 0.5) / n * (hi - lo);
     } else if (threadIdx.x < n) {
         sm[threadIdx.x] = x[key(seed, pb.region, 1000 + 32 * n + init, threadIdx.x) % (unsigned long long)N];
@@ -124,22 +162,22 @@ fit_kernel(const Problem* __restrict__ problems, const double* __restrict__ data
     for (int round = 0; round <= kLloyd; ++round) {
         // labels by the nearest mean (lowest index on ties); the last round turns them into the first M step
         for (int j = 0; j < 3 * n; ++j) acc[j] = 0;
-        for (int i = threadIdx.x; i < N; i += kThreads) {
+        for (int i = first; i < N; i += stride) {
             const double xi = x[i];
             int lab = 0;
             double bd = fabs(xi - sm[0]);
             for (int j = 1; j < n; ++j) { const double d = fabs(xi - sm[j]); if (d < bd) { bd = d; lab = j; } }
             acc[lab] += 1.0; acc[n + lab] += xi; acc[2 * n + lab] += xi * xi;
         }
-        block_sum(acc, 3 * n, red, kVals);
+        cluster_sum(cluster, acc, 3 * n, red, tot);
         if (threadIdx.x < n) {
             const int j = threadIdx.x;
             if (round < kLloyd) {
-                if (red[j] > 0) sm[j] = red[n + j] / red[j];
+                if (tot[j] > 0) sm[j] = tot[n + j] / tot[j];
             } else {          // sklearn _estimate_gaussian_parameters on one-hot responsibilities
-                const double nk = red[j] + kEps10;
-                const double mean = red[n + j] / nk;
-                sw[j] = nk / N; sm[j] = mean; sv[j] = red[2 * n + j] / nk - mean * mean + reg_covar;
+                const double nk = tot[j] + kEps10;
+                const double mean = tot[n + j] / nk;
+                sw[j] = nk / N; sm[j] = mean; sv[j] = tot[2 * n + j] / nk - mean * mean + reg_covar;
             }
         }
         __syncthreads();
@@ -157,7 +195,7 @@ fit_kernel(const Problem* __restrict__ problems, const double* __restrict__ data
         }
         __syncthreads();
         for (int j = 0; j < 3 * n + 1; ++j) acc[j] = 0;
-        for (int i = threadIdx.x; i < N; i += kThreads) {
+        for (int i = first; i < N; i += stride) {
             const double xi = x[i];
             double lp[kMaxC];
             double top = -INFINITY;
@@ -175,23 +213,25 @@ fit_kernel(const Problem* __restrict__ problems, const double* __restrict__ data
             }
             acc[3 * n] += norm;
         }
-        block_sum(acc, 3 * n + 1, red, kVals);
+        cluster_sum(cluster, acc, 3 * n + 1, red, tot);
         const double prev = lower;
-        lower = red[3 * n] / N;
+        lower = tot[3 * n] / N;
         __syncthreads();
         if (threadIdx.x < n) {
             const int j = threadIdx.x;
-            const double nk = red[j] + kEps10;
-            const double mean = red[n + j] / nk;
-            sw[j] = nk / N; sm[j] = mean; sv[j] = red[2 * n + j] / nk - mean * mean + reg_covar;
+            const double nk = tot[j] + kEps10;
+            const double mean = tot[n + j] / nk;
+            sw[j] = nk / N; sm[j] = mean; sv[j] = tot[2 * n + j] / nk - mean * mean + reg_covar;
         }
         __syncthreads();
         iters = it;
-        if (fabs(lower - prev) < tol) { converged = 1; break; }
+        if (fabs(lower - prev) < tol) { converged = 1; break; }        // (the same number in every block: all leave together)
     }
-    Fit& f = fits[blockIdx.x];
-    if (threadIdx.x == 0) { f.lower = lower; f.iters = iters; f.converged = converged; }
-    if (threadIdx.x < n) { f.w[threadIdx.x] = sw[threadIdx.x]; f.m[threadIdx.x] = sm[threadIdx.x]; f.v[threadIdx.x] = sv[threadIdx.x]; }
+    if (rank == 0) {
+        Fit& f = fits[fit];
+        if (threadIdx.x == 0) { f.lower = lower; f.iters = iters; f.converged = converged; }
+        if (threadIdx.x < n) { f.w[threadIdx.x] = sw[threadIdx.x]; f.m[threadIdx.x] = sm[threadIdx.x]; f.v[threadIdx.x] = sv[threadIdx.x]; }
+    }
 }
 
 struct Bufs {
@@ -244,23 +284,47 @@ int run_fits(const nr_gmm_params_t* p, const std::vector<Problem>& problems, con
         (rc = bufs.get(&h_fits, sizeof(Fit) * n_fits, true)))
         return rc;
     cudaStream_t st = nri::stream();
-    GTRY(cudaMemcpyAsync(d_prob, problems.data(), sizeof(Problem) * np, cudaMemcpyHostToDevice, st));
-    fit_kernel<<<(unsigned)n_fits, kThreads, 0, st>>>(static_cast<const Problem*>(d_prob), d_data, p->n_init, p->max_iter, p->tol, p->reg_covar,
-                                                     p->seed, static_cast<Fit*>(d_fits));
-    GTRY(cudaGetLastError());
+    // regions of few samples first (one thread block per fit), regions of many after them (a cluster of blocks per fit)
+    std::vector<int> perm(np);
+    for (int i = 0; i < np; ++i) perm[i] = i;
+    std::stable_partition(perm.begin(), perm.end(), [&](int i) { return problems[i].count < kBigSamples; });
+    int n_small = 0;
+    while (n_small < np && problems[perm[n_small]].count < kBigSamples) ++n_small;
+    std::vector<Problem> sorted(np);
+    for (int i = 0; i < np; ++i) sorted[i] = problems[perm[i]];
+    GTRY(cudaMemcpyAsync(d_prob, sorted.data(), sizeof(Problem) * np, cudaMemcpyHostToDevice, st));
+    auto launch = [&](int first, int count, int cluster) -> cudaError_t {
+        if (count == 0) return cudaSuccess;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((size_t)count * p->n_init * cluster));
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, fit_kernel, static_cast<const Problem*>(d_prob) + first, d_data, (int)p->n_init, (int)p->max_iter,
+                                  (double)p->tol, (double)p->reg_covar, (unsigned long long)p->seed,
+                                  static_cast<Fit*>(d_fits) + (size_t)first * p->n_init);
+    };
+    GTRY(launch(0, n_small, 1));
+    GTRY(launch(n_small, np - n_small, kBigCluster));
     GTRY(cudaMemcpyAsync(h_fits, d_fits, sizeof(Fit) * n_fits, cudaMemcpyDeviceToHost, st));
     GTRY(cudaStreamSynchronize(st));
     const Fit* f = static_cast<const Fit*>(h_fits);
-    for (int i = 0; i < np; ++i) {
+    for (int s = 0; s < np; ++s) {
+        const int i = perm[s];
         int b = 0;
         for (int k = 1; k < p->n_init; ++k)
-            if (f[(size_t)i * p->n_init + k].lower > f[(size_t)i * p->n_init + b].lower) b = k;
-        best[i] = f[(size_t)i * p->n_init + b];
+            if (f[(size_t)s * p->n_init + k].lower > f[(size_t)s * p->n_init + b].lower) b = k;
+        best[i] = f[(size_t)s * p->n_init + b];
         // components in ascending order of their means: which start won a near tie must not show in the result
         const int n = problems[i].n;
         int order[kMaxC];
         for (int j = 0; j < n; ++j) order[j] = j;
-        const Fit& src = f[(size_t)i * p->n_init + b];
+        const Fit& src = f[(size_t)s * p->n_init + b];
         std::stable_sort(order, order + n, [&](int a, int c) { return src.m[a] < src.m[c]; });
         for (int j = 0; j < n; ++j) { best[i].w[j] = src.w[order[j]]; best[i].m[j] = src.m[order[j]]; best[i].v[j] = src.v[order[j]]; }
     }

@@ -146,3 +146,28 @@ def test_steps_1_to_4_in_memory_find_the_simulated_alleles(engine):
         want = sorted(set(al))
         assert len(medians) == len(want) and all(abs(m - w) <= 2 for m, w in zip(medians, want)), (al, medians)
         assert sum(a.num_reads for a in rr.allele_list) <= len(rr.read_dict)
+
+
+def test_many_samples_take_the_cluster_path_and_equal_the_checker(engine):
+    """Regions of 16 384 bootstrapped samples and more are fitted by a cluster of thread blocks (partial sums through
+    distributed shared memory): same starts, same EM as the checker; the summation order is all that differs."""
+    from oracle import gmm
+    rng = random.Random(9)
+    p = engine.GmmParams(seed=77, max_components=4)
+    data = [_mixture(rng, (20, 60), (9000, 11000), err=0.05), _mixture(rng, (15, 40, 90), (7000, 6000, 8000), err=0.04),
+            _mixture(rng, (33,), (17000,), err=0.03), _mixture(rng, (20, 60), (300, 200), err=0.05)]
+    ncs = [2, 3, 2, 2]
+    got = engine.gmm1d_fit(p, data, ncs, region_ids=[5, 6, 7, 8])
+    for i, xs in enumerate(data):
+        w, m, v, lower, it, conv = gmm.best_fit(np.array(xs), ncs[i], 77, 5 + i)
+        assert abs(got["lower"][i] - lower) < 1e-8 and got["iters"][i] == it, (i, got["lower"][i], lower, got["iters"][i], it)
+        assert np.allclose(got["weights"][i], w, rtol=1e-6, atol=1e-10) and np.allclose(got["means"][i], m, rtol=1e-7), i
+        assert np.allclose(got["variances"][i], v, rtol=1e-5), i
+    # a region of 400 reads (40 000 samples) through the whole phasing, beside a small one
+    sizes = _mixture(rng, (17, 55), (210, 190), err=0.02)
+    pp = engine.GmmParams(error_rate=0.07, max_mutual_overlap=0.15, max_components=4, seed=2)
+    got = engine.phase_1d(pp, [sizes, sizes[:30]])
+    exp = gmm.phase_1d(sizes, 0.07, 4, 0.15, seed=2, region=0)
+    assert got[0]["n"] == exp["n"] == 2 and np.allclose(got[0]["means"], exp["means"], rtol=1e-6)
+    assert [int(l) for l in got[0]["label"] if l >= 0] == [int(l) for l in exp["label"]]
+    assert got[1]["n"] >= 1
