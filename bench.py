@@ -495,6 +495,13 @@ def measure_phasing(torch, engine, n_loci=2000, reads_per_locus=30, n_cpu=6):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     agree = int(sum(f["n"] == t for f, t in zip(fits, truth)))
+    # config 2's shape: two regions of 5 000 reads (500 000 bootstrapped samples each: a cluster of thread blocks per fit)
+    big = [list(np.round(np.where(rng.random(5000) < 0.5, a, b) + rng.normal(0, 0.4, 5000), 2)) for a, b in ((17, 55), (7, 10))]
+    engine.phase_1d(params, big)
+    t0 = time.perf_counter()
+    big_fits = engine.phase_1d(params, big)
+    torch.cuda.synchronize()
+    big_dt = time.perf_counter() - t0
     # the reference recipe on a few loci
     from sklearn.mixture import GaussianMixture
     z = ogmm.std_isf(0.15)
@@ -523,6 +530,8 @@ def measure_phasing(torch, engine, n_loci=2000, reads_per_locus=30, n_cpu=6):
     return {"workload": f"{n_loci} loci x {reads_per_locus} round-3 sizes (60 % heterozygous), error_rate 0.07, overlap 0.15, up to 22 components",
             "s": dt, "loci_per_s": n_loci / dt, "samples_fitted": n_loci * reads_per_locus * 100,
             "loci_with_the_simulated_number_of_alleles": agree,
+            "config2_shape": {"regions": 2, "reads_per_region": 5000, "s": big_dt, "alleles": [int(f["n"]) for f in big_fits],
+                              "means": [[round(float(m), 2) for m in f["means"]] for f in big_fits]},
             "path": "engine.phase_1d -> nr_phase_1d (host sizes in, mixtures + labels out)",
             "cpu_reference_recipe": {"loci": n_cpu, "s": cpu_dt, "loci_per_s": n_cpu / cpu_dt, "threads": 1,
                                      "same_number_of_alleles": same,

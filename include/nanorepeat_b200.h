@@ -236,6 +236,10 @@ void nr_batch_destroy(nr_batch_t* b);
  * '\n' (no trailing newline needed).  has_round1_max_dist: this "region" is one piece of a split region and
  * round1_max_dist is the whole region's longest dist_between_anchors (T is region-wide, :344).
  * Needs map-ont scoring (every preset of the reference) and nr_set_ladder_mode != 0.
+ * Threads: the call may be made from several host threads at once (the Python layer sends a long region list as a few
+ * chunks on a few threads).  Launches without cooperating stripes run on a stream of the calling thread's own, so two
+ * calls' kernels share the GPU block by block; launches with long reads' cooperating stripes stay on the library's one
+ * stream (two half-resident grids of waiting blocks must never meet).  A thread's stream lives as long as the process.
  */
 typedef struct nr_region_t {
     const char* left;  int32_t n_left;      /* RepeatRegion.left_anchor_seq  */
