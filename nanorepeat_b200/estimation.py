@@ -340,6 +340,7 @@ def _assign_chunk(res, todo):
 CHUNK_MIN_READS = 4096      # reads per call into the library when a region list is cut into pipelined chunks
 BIG_CHUNK_READS = 16384     # ... for lists of 16 384 reads and more
 _POOL = None
+_POOL_PID = None
 
 
 def _chunks(rrs):
@@ -380,7 +381,7 @@ def _estimate_regions_fused(dt, fast_mode, rrs):
     on one chunk, this thread gathers the next chunk's strings and assigns the previous chunk's results, so that the
     Python side of the boundary -- one attribute read and three attribute writes per Read object -- hides behind the
     kernels."""
-    global _POOL
+    global _POOL, _POOL_PID
     sc = _scoring_for(dt)
     chunks = _chunks(rrs)
     if len(chunks) == 1:
@@ -388,9 +389,10 @@ def _estimate_regions_fused(dt, fast_mode, rrs):
         if todo:
             _assign_chunk(_run_chunk(sc, fast_mode, cols), todo)
         return
-    if _POOL is None:
+    if _POOL is None or _POOL_PID != os.getpid():          # (a forked child inherits the object, not its threads)
         from concurrent.futures import ThreadPoolExecutor
         _POOL = ThreadPoolExecutor(max_workers=3, thread_name_prefix="nanorepeat_b200")
+        _POOL_PID = os.getpid()
     import threading
     pending = []
     for ch in chunks:
