@@ -16,7 +16,9 @@ torch.cuda.synchronize()
 ts = []
 for i in range(12):
     rrs = wl.fresh(); gc.collect(); gc.freeze()
+    if i == 0 and os.environ.get("TRACE_FIRST"): os.environ["NR_TRACE"] = "1"
     t0 = time.perf_counter(); wl.e2e_pass(rrs); torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
+    os.environ.pop("NR_TRACE", None)
     gc.unfreeze()
 print(which, "bench-flow e2e ms per pass:", [round(t * 1e3, 1) for t in ts])
 ts = []
