@@ -445,8 +445,16 @@ struct Sweep {
     }
 
     // steps per trip of the guard-free loop: the stripes of long pairs in round 3 (three loop variants per warp mix on
-    // an SM, bound by instruction fetch like their 32-bit counterparts, nr_kernels.cuh) run one, everything else four
-    static constexpr int kUnroll = (MULTI && MODE != kP2) ? 1 : 4;
+    // an SM, bound by instruction fetch like their 32-bit counterparts, nr_kernels.cuh) run one; round 3's single-stripe
+    // sweeps two (a trip of four is 11 KB of code per variant: the kernel then ran anywhere between 1.26 and 1.41 ms
+    // from run to run, same binary, and 1.24-1.25 ms on four GPUs in a row with two); round 2 (one loop variant) four
+#ifndef NR_PAIR3_UNROLL
+#define NR_PAIR3_UNROLL 2
+#endif
+#ifndef NR_PAIR2_UNROLL
+#define NR_PAIR2_UNROLL 4
+#endif
+    static constexpr int kUnroll = (MULTI && MODE != kP2) ? 1 : (MODE == kP2 ? NR_PAIR2_UNROLL : NR_PAIR3_UNROLL);
     template <bool TRACK, bool SPECIAL = false>
     __device__ __forceinline__ void fast_until(int& st, int end, u32 one, unsigned four) {
         for (; st + 16 <= end; st += 16) {       // st is a multiple of 16 here
