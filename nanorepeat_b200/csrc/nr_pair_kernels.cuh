@@ -444,17 +444,22 @@ struct Sweep {
         }
     }
 
-    // steps per trip of the guard-free loop: the stripes of long pairs in round 3 (three loop variants per warp mix on
-    // an SM, bound by instruction fetch like their 32-bit counterparts, nr_kernels.cuh) run one; round 3's single-stripe
-    // sweeps two (a trip of four is 11 KB of code per variant: the kernel then ran anywhere between 1.26 and 1.41 ms
-    // from run to run, same binary, and 1.24-1.25 ms on four GPUs in a row with two); round 2 (one loop variant) four
+    // steps per trip of the guard-free loop.  Round 3's warps are spread over several loop variants (backward sweep,
+    // forward sweep in and out of the junction zone; for long pairs three per stripe) and the kernel is sensitive to
+    // instruction fetch: with four steps per trip (11 KB of code per variant) config 2's launch took anywhere between
+    // 1.26 and 1.41 ms from build to build of the library (same kernel code, another place in memory), with two
+    // 1.24-1.25 ms on every build and box tried, with one 1.23-1.27 ms.  So: two for single-stripe pairs, one for the
+    // stripes of long pairs; round 2 has one loop variant per launch and is fastest with four (1.23 against 1.25 ms).
 #ifndef NR_PAIR3_UNROLL
 #define NR_PAIR3_UNROLL 2
 #endif
 #ifndef NR_PAIR2_UNROLL
 #define NR_PAIR2_UNROLL 4
 #endif
-    static constexpr int kUnroll = (MULTI && MODE != kP2) ? 1 : (MODE == kP2 ? NR_PAIR2_UNROLL : NR_PAIR3_UNROLL);
+#ifndef NR_PAIR2_MULTI_UNROLL
+#define NR_PAIR2_MULTI_UNROLL 4
+#endif
+    static constexpr int kUnroll = MODE == kP2 ? (MULTI ? NR_PAIR2_MULTI_UNROLL : NR_PAIR2_UNROLL) : (MULTI ? 1 : NR_PAIR3_UNROLL);
     template <bool TRACK, bool SPECIAL = false>
     __device__ __forceinline__ void fast_until(int& st, int end, u32 one, unsigned four) {
         for (; st + 16 <= end; st += 16) {       // st is a multiple of 16 here
