@@ -361,19 +361,21 @@ def time_e2e(wl, torch, passes_total):
     warm = 2
     total = 0.0
     wl.e2e_pass_ms = []
-    for i in range(warm + passes_total):
-        rrs = wl.fresh()
-        gc.collect()
-        gc.freeze()          # this process holds five workloads' worth of objects: keep the collector from walking them
-        t0 = time.perf_counter()          # inside the timed call (its cost there would be an artefact of the bench)
-        wl.e2e_pass(rrs)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+    gc.collect()
+    gc.freeze()              # this process holds five workloads' worth of objects: keep the collector from walking them
+    try:                     # inside the timed calls (its cost there would be an artefact of the bench); GC stays enabled
+        for i in range(warm + passes_total):
+            rrs = wl.fresh()
+            t0 = time.perf_counter()
+            wl.e2e_pass(rrs)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if i < warm:     # same flow as the timed passes: with three calls in flight the library may need a third set of
+                continue     # buffers that an earlier, differently interleaved pass never asked for (a one-off 100 ms)
+            total += dt
+            wl.e2e_pass_ms.append(round(dt * 1e3, 3))
+    finally:
         gc.unfreeze()
-        if i < warm:         # same flow as the timed passes: with three calls in flight the library may need a third set of
-            continue         # buffers that an earlier, differently interleaved pass never asked for (a one-off 100 ms)
-        total += dt
-        wl.e2e_pass_ms.append(round(dt * 1e3, 3))
     return total
 
 
