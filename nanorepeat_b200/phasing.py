@@ -91,7 +91,8 @@ def remove_noisy_reads_1d(allele_list, ploidy):
 def phase_regions_1d(read_size_dicts, ploidy=2, error_rate=0.07, max_mutual_overlap=0.15, max_num_components=-1,
                      remove_noisy_reads=False, seed=0, region_id_base=0):
     """read_size_dicts: per region {read name: round-3 size}.  -> per region (allele_list sorted by gmm_mean1,
-    num_removed_reads), or None where the reference phases nothing (fewer than two reads, :533-539)."""
+    num_removed_reads), or None where the reference phases nothing (fewer than two reads, :533-539).
+    max_num_components beyond the library's 32 (NR_GMM_MAX_COMPONENTS) is cut to 32: the default is ploidy + 20."""
     if ploidy < 1:
         raise ValueError("ploidy must be >= 1")
     if max_num_components == -1:
