@@ -510,10 +510,13 @@ def estimate_regions(sc, fast_mode, lefts, rights, motifs, cores, dists, max_dis
     keep.append(big)
     first = np.zeros(n + 1, np.int64)
     np.cumsum(n_reads, out=first[1:])
-    clen = np.fromiter(map(len, cores), np.int64, total)
-    csum = np.zeros(total + 1, np.int64)
-    np.cumsum(clen, out=csum[1:])
-    llen = csum[first[1:]] - csum[first[:-1]] + (n_reads - 1)                 # a region's lines with the breaks between them
+    if n == 1:
+        llen = np.array([len(big)], np.int64)                                 # one region: all the lines are its lines
+    else:
+        clen = np.fromiter(map(len, cores), np.int64, total)
+        csum = np.zeros(total + 1, np.int64)
+        np.cumsum(clen, out=csum[1:])
+        llen = csum[first[1:]] - csum[first[:-1]] + (n_reads - 1)             # a region's lines with the breaks between them
     start = np.zeros(n + 1, np.int64)
     np.cumsum(llen + 1, out=start[1:])
     if not ptr or (n and size.value != start[-1] - 1):
