@@ -324,17 +324,16 @@ def _run_chunk(sc, fast_mode, cols, ready=None):
 
 
 def _assign_chunk(res, todo):
-    r3 = res["r3"]
-    pos = 0
-    for rd, a, ok, v, s in zip(todo, res["r1"].tolist(), res["r2_valid"].tolist(), res["r2"].tolist(), res["r3_state"].tolist()):
+    # (round 3's mean stays an np.float64, like np.mean in the reference, :431; list(array) makes those in one sweep)
+    for rd, a, ok, v, s, w in zip(todo, res["r1"].tolist(), res["r2_valid"].tolist(), res["r2"].tolist(),
+                                  res["r3_state"].tolist(), list(res["r3"])):
         rd.round1_repeat_size = a                                               # :341
         if ok:
             rd.round2_repeat_size = v                                           # :375-384
             if s == 1:
-                rd.round3_repeat_size = r3[pos]                                 # :431 (np.float64, like np.mean)
+                rd.round3_repeat_size = w                                       # :431
             elif s == 2:
                 rd.round3_repeat_size = v                                       # :433
-        pos += 1
 
 
 CHUNK_MIN_READS = 4096      # reads per call into the library when a region list is cut into pipelined chunks
