@@ -63,3 +63,42 @@ def test_window_dp_equals_golden_and_the_reference_rescoring_of_its_own_cigar():
         assert nr_oracle.align_window(c["query"], c["target"], c["win_a"], c["win_b"], reverse=c["reverse"]) == (c["score"], c["window_score"])
         if c["score"] > 0:
             assert joint.window_stats(c["cigar"], c["tstart"], c["tend"], c["win_a"], c["win_b"])["score"] == c["window_score"]
+
+
+def test_grid_rounds_equal_the_reference_pipeline_end_to_end():
+    """nanorepeat_b200.joint.quantify_two_repeats (grid enumeration, step sizes, windows, tie selection), fed by the CPU
+    oracle's DP, returns per read exactly what the reference's own fine_tune_read_count returned when its pyminimap2
+    was replaced by a PAF printer over the same DP (tests/golden/make_golden_joint_pipeline.py): temp files, PAF text and
+    CIGAR re-scoring on one side, binary records with the window score carried through the DP on the other."""
+    import numpy as np
+    from nanorepeat_b200 import engine, joint as njoint
+    from oracle import nr_oracle
+    nr_oracle.build()
+    doc = _load("joint_pipeline_cases.json")
+    assert len(doc["cases"]) >= 6
+
+    def oracle_grid(sc, left, mid, right, motif1, motif2, reads_, pr, p1, p2):
+        rec = np.zeros(len(pr), dtype=engine.WINDOW_DTYPE)
+        strand = np.zeros(len(pr), dtype=np.uint8)
+        for i, (r, k1, k2) in enumerate(zip(pr, p1, p2)):
+            tpl = left + motif1 * int(k1) + mid + motif2 * int(k2) + right
+            a, b = max(len(left) - 10, 0), min(len(left) + len(motif1) * int(k1) + len(mid) + len(motif2) * int(k2) + 10, len(tpl))
+            f = nr_oracle.align_window(reads_[int(r)], tpl, a, b, reverse=False)
+            v = nr_oracle.align_window(reads_[int(r)], tpl, a, b, reverse=True)
+            best, strand[i] = (v, 1) if v > f else (f, 0)
+            rec[i] = best
+        return rec, strand
+
+    rounds3 = 0
+    for c in doc["cases"]:
+        r1 = [None if x is None else tuple(x) for x in c["range1"]]
+        r2 = [None if x is None else tuple(x) for x in c["range2"]]
+        got = njoint.quantify_two_repeats(c["reads"], c["left"], c["mid"], c["right"], c["motif1"], c["motif2"], r1, r2,
+                                          c["max_size1"], c["max_size2"], align=oracle_grid)
+        assert (got["step1"], got["step2"]) == (c["step1"], c["step2"])
+        assert [None if v is None else float(v) for v in got["size1"]] == c["size1"]
+        assert [None if v is None else float(v) for v in got["size2"]] == c["size2"]
+        rounds3 += c["alignment_calls"] > 100
+        close = sum(v is not None and abs(v - t[0]) <= 2 for v, t in zip(c["size1"], c["truth"]))
+        assert close >= 7, (close, c["size1"], c["truth"])
+    assert rounds3 >= 4
