@@ -171,3 +171,27 @@ def test_many_samples_take_the_cluster_path_and_equal_the_checker(engine):
     assert got[0]["n"] == exp["n"] == 2 and np.allclose(got[0]["means"], exp["means"], rtol=1e-6)
     assert [int(l) for l in got[0]["label"] if l >= 0] == [int(l) for l in exp["label"]]
     assert got[1]["n"] >= 1
+
+
+def test_phase_equals_the_reference_step4_on_separated_alleles(engine):
+    """The reference's own, unmodified split_allele_using_gmm_1d (scikit-learn, its own random draws, seeded when the
+    fixture was made: tests/golden/make_golden_phasing_pipeline.py) against phasing.phase_regions_1d on the same sizes:
+    same number of alleles, same median size and read count per allele, every read in the same allele."""
+    import json
+    import os
+    from nanorepeat_b200 import phasing
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "phasing_pipeline_cases.json")) as f:
+        doc = json.load(f)
+    assert len(doc["cases"]) >= 6
+    dicts = [c["sizes"] for c in doc["cases"]]
+    for g, c in enumerate(doc["cases"]):
+        alleles, removed = phasing.phase_regions_1d([dicts[g]], ploidy=c["ploidy"], error_rate=c["error_rate"],
+                                                    max_mutual_overlap=c["max_mutual_overlap"], max_num_components=c["ploidy"] + 20,
+                                                    remove_noisy_reads=c["remove_noisy_reads"], seed=g, region_id_base=g)[0]
+        assert len(alleles) == c["num_alleles"], (g, len(alleles), c["num_alleles"])
+        assert [(a.repeat1_median_size, a.num_reads) for a in alleles] == [(e["median"], e["num_reads"]) for e in c["alleles"]], g
+        ours = {name: i + 1 for i, a in enumerate(alleles) for name in a.readname_list}
+        assert ours == {n: r["allele_id"] for n, r in c["reads"].items()}, g
+        conf = {name: cf for a in alleles for name, cf in zip(a.readname_list, a.confidence_list)}
+        differ = [n for n, r in c["reads"].items() if conf[n] != r["confidence"]]
+        assert len(differ) <= max(1, len(conf) // 20), (g, differ)          # HIGH / LOW sits on a fitted 2-sd bound: a boundary read may flip
